@@ -1,0 +1,88 @@
+/**
+ * \file customer.h
+ * \brief Per-(app, customer) inbox and request tracker.
+ *
+ * A Customer owns one inbox (filled by the van receive thread through Accept)
+ * and a tracker that counts responses per request timestamp so that Wait(ts)
+ * can block until every addressed server has answered.
+ *
+ * Re-designed relative to the reference (include/ps/internal/customer.h:28-115,
+ * src/customer.cc:18-74):
+ *  - the tracker is a power-of-two ring recycled by `ts & mask` (the reference's
+ *    vector grows by one entry per request forever);
+ *  - PS_DIRECT_DISPATCH=1 runs the receive handle inline on the van thread
+ *    (one hop instead of two) for handlers that never block, e.g. the GPU server
+ *    engine which only enqueues kernels.
+ */
+#ifndef PS_INTERNAL_CUSTOMER_H_
+#define PS_INTERNAL_CUSTOMER_H_
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
+#include <utility>
+#include <vector>
+#include "ps/internal/message.h"
+#include "ps/internal/threadsafe_queue.h"
+
+namespace ps {
+
+class Postoffice;
+
+class Customer {
+ public:
+  /*! \brief invoked for every message addressed to this customer */
+  using RecvHandle = std::function<void(const Message& recved)>;
+
+  Customer(int app_id, int customer_id, const RecvHandle& recv_handle, Postoffice* postoffice);
+  ~Customer();
+
+  int app_id() const { return app_id_; }
+  int customer_id() const { return customer_id_; }
+
+  /*!
+   * \brief open a request addressed to node group `recver`; returns its timestamp.
+   *  The expected response count is the number of *groups* in `recver` (a worker
+   *  instance talks to exactly one instance of each server group), 1 for a single
+   *  node id, or `num_expected` if given.
+   */
+  int NewRequest(int recver, int num_expected = -1);
+  /*! \brief block until every expected response of `timestamp` has arrived */
+  void WaitRequest(int timestamp);
+  /*! \brief responses received so far */
+  int NumResponse(int timestamp);
+  /*! \brief count `num` responses without a message (e.g. skipped empty slices) */
+  void AddResponse(int timestamp, int num = 1);
+  /*! \brief called by the van receive thread */
+  void Accept(const Message& recved);
+
+ private:
+  struct Slot {
+    int ts = -1;
+    int expected = 0;
+    int received = 0;
+  };
+  void Receiving();
+  void Deliver(const Message& m);
+  Slot* Find(int ts);  // requires tracker_mu_
+
+  int app_id_;
+  int customer_id_;
+  RecvHandle recv_handle_;
+  Postoffice* postoffice_;
+  bool direct_dispatch_ = false;
+  ThreadsafeQueue<Message> inbox_;
+  std::unique_ptr<std::thread> recv_thread_;
+
+  std::mutex tracker_mu_;
+  std::condition_variable tracker_cv_;
+  std::vector<Slot> ring_;
+  int next_ts_ = 0;
+  Customer(const Customer&) = delete;
+  Customer& operator=(const Customer&) = delete;
+};
+
+}  // namespace ps
+#endif  // PS_INTERNAL_CUSTOMER_H_

@@ -1,0 +1,126 @@
+/**
+ * \file customer.cc
+ * \brief Customer inbox + ring-recycled request tracker (see customer.h).
+ */
+#include "ps/internal/customer.h"
+#include <limits>
+#include "ps/internal/postoffice.h"
+
+namespace ps {
+
+const int Node::kEmpty = std::numeric_limits<short>::max();
+const int Meta::kEmpty = std::numeric_limits<short>::max();
+
+namespace {
+const size_t kInitialRing = 1024;
+}
+
+Customer::Customer(int app_id, int customer_id, const RecvHandle& recv_handle,
+                   Postoffice* postoffice)
+    : app_id_(app_id), customer_id_(customer_id), recv_handle_(recv_handle),
+      postoffice_(postoffice) {
+  ring_.resize(kInitialRing);
+  direct_dispatch_ = GetEnv("PS_DIRECT_DISPATCH", 0) != 0;
+  postoffice_->AddCustomer(this);
+  if (!direct_dispatch_) {
+    recv_thread_.reset(new std::thread(&Customer::Receiving, this));
+  }
+}
+
+Customer::~Customer() {
+  postoffice_->RemoveCustomer(this);
+  if (recv_thread_) {
+    Message bye;
+    bye.meta.control.cmd = Control::TERMINATE;
+    inbox_.Push(bye);
+    recv_thread_->join();
+  }
+}
+
+Customer::Slot* Customer::Find(int ts) {
+  Slot& s = ring_[static_cast<size_t>(ts) & (ring_.size() - 1)];
+  return s.ts == ts ? &s : nullptr;
+}
+
+int Customer::NewRequest(int recver, int num_expected) {
+  // requests fan out to one instance of every group in `recver`
+  int groups = num_expected;
+  if (groups < 0) {
+    const int members = static_cast<int>(postoffice_->GetNodeIDs(recver).size());
+    const bool is_group = recver < 8;
+    groups = is_group ? std::max(1, members / postoffice_->group_size()) : members;
+  }
+  std::lock_guard<std::mutex> lk(tracker_mu_);
+  const int ts = next_ts_++;
+  for (;;) {
+    Slot& s = ring_[static_cast<size_t>(ts) & (ring_.size() - 1)];
+    if (s.ts < 0 || s.received >= s.expected) {
+      s.ts = ts;
+      s.expected = groups;
+      s.received = 0;
+      break;
+    }
+    // the slot we would recycle is still in flight: double the ring and re-home
+    std::vector<Slot> bigger(ring_.size() * 2);
+    for (const Slot& old : ring_) {
+      if (old.ts >= 0) bigger[static_cast<size_t>(old.ts) & (bigger.size() - 1)] = old;
+    }
+    ring_.swap(bigger);
+  }
+  return ts;
+}
+
+void Customer::WaitRequest(int timestamp) {
+  std::unique_lock<std::mutex> lk(tracker_mu_);
+  tracker_cv_.wait(lk, [this, timestamp] {
+    Slot* s = Find(timestamp);
+    // a recycled slot means the request completed long ago
+    return s == nullptr || s->received >= s->expected;
+  });
+}
+
+int Customer::NumResponse(int timestamp) {
+  std::lock_guard<std::mutex> lk(tracker_mu_);
+  Slot* s = Find(timestamp);
+  return s ? s->received : 0;
+}
+
+void Customer::AddResponse(int timestamp, int num) {
+  {
+    std::lock_guard<std::mutex> lk(tracker_mu_);
+    Slot* s = Find(timestamp);
+    if (s) s->received += num;
+  }
+  tracker_cv_.notify_all();
+}
+
+void Customer::Deliver(const Message& m) {
+  recv_handle_(m);
+  if (!m.meta.request) {
+    {
+      std::lock_guard<std::mutex> lk(tracker_mu_);
+      Slot* s = Find(m.meta.timestamp);
+      if (s) ++s->received;
+    }
+    tracker_cv_.notify_all();
+  }
+}
+
+void Customer::Accept(const Message& recved) {
+  if (direct_dispatch_) {
+    Deliver(recved);
+  } else {
+    inbox_.Push(recved);
+  }
+}
+
+void Customer::Receiving() {
+  for (;;) {
+    Message m;
+    inbox_.WaitAndPop(&m);
+    if (!m.meta.control.empty() && m.meta.control.cmd == Control::TERMINATE) break;
+    Deliver(m);
+  }
+}
+
+}  // namespace ps

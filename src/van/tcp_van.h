@@ -1,0 +1,505 @@
+/**
+ * \file tcp_van.h
+ * \brief TcpVan: the CPU / control-plane transport (answers to "zmq", "0", "tcp").
+ *
+ * Fills the role of the reference's ZMQVan (src/zmq_van.h:43-480) without
+ * libzmq: plain stream sockets, one outbound connection per peer, one epoll
+ * loop for everything inbound, and a loopback queue for self-addressed
+ * messages. Design points:
+ *   - frame = [FrameHeader][u64 seg_len x n][meta][seg0][seg1]... sent with a
+ *     single gathered sendmsg(); payload SArrays are never copied on send.
+ *   - RecvMsg runs the epoll loop *in the van receive thread itself* — there is
+ *     no transport-side thread or intermediate queue (the reference has one
+ *     recv thread per socket pushing into a queue while holding the send mutex).
+ *   - payload bytes are read straight into their final buffer: a registered
+ *     receive buffer if one matches (sender, key), else a fresh page-aligned one.
+ *   - DMLC_LOCAL=1 switches to abstract-namespace unix sockets ("ipc" mode).
+ */
+#ifndef PS_VAN_TCP_VAN_H_
+#define PS_VAN_TCP_VAN_H_
+#include <arpa/inet.h>
+#include <errno.h>
+#include <fcntl.h>
+#include <netdb.h>
+#include <netinet/in.h>
+#include <netinet/tcp.h>
+#include <sys/epoll.h>
+#include <sys/eventfd.h>
+#include <sys/socket.h>
+#include <sys/uio.h>
+#include <sys/un.h>
+#include <unistd.h>
+
+#include <chrono>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "ps/internal/postoffice.h"
+#include "ps/internal/van.h"
+
+namespace ps {
+
+class TcpVan : public Van {
+ public:
+  explicit TcpVan(Postoffice* postoffice) : Van(postoffice) {}
+  ~TcpVan() override { CloseAll(); }
+
+  std::string GetType() const override { return "zmq"; }
+
+  void Start(int customer_id, bool standalone) override {
+    {
+      std::lock_guard<std::mutex> lk(init_mu_);
+      if (epfd_ < 0) {
+        local_ipc_ = GetEnv("DMLC_LOCAL", 0) != 0;
+        connect_timeout_s_ = GetEnv("PS_CONNECT_TIMEOUT", 120);
+        epfd_ = epoll_create1(EPOLL_CLOEXEC);
+        CHECK_GE(epfd_, 0) << strerror(errno);
+        wake_fd_ = eventfd(0, EFD_NONBLOCK | EFD_CLOEXEC);
+        CHECK_GE(wake_fd_, 0) << strerror(errno);
+        AddToEpoll(wake_fd_);
+      }
+    }
+    Van::Start(customer_id, standalone);
+  }
+
+  void Stop() override {
+    Van::Stop();
+    CloseAll();
+  }
+
+  /*! \brief later pushes of (msg.meta.sender, msg.meta.key) land in msg.data[1] */
+  void RegisterRecvBuffer(Message& msg) override {
+    CHECK_GE(msg.data.size(), (size_t)2);
+    std::lock_guard<std::mutex> lk(reg_mu_);
+    registered_[std::make_pair(msg.meta.sender, msg.meta.key)] = msg.data[1];
+  }
+
+ protected:
+  // the wire prefix of every frame
+  struct FrameHeader {
+    uint32_t magic;
+    int32_t sender;
+    int32_t recver;
+    uint32_t meta_len;
+    uint32_t num_segments;
+    uint32_t reserved;
+  };
+  static constexpr uint32_t kFrameMagic = 0x4d524650u;  // "PFRM"
+  static constexpr uint32_t kMaxSegments = 16;
+
+  struct Peer {
+    int fd = -1;
+    std::mutex mu;  // serialises whole frames on this socket
+  };
+
+  int Bind(Node& node, int max_retry) override {
+    int port = node.port;
+    unsigned seed = static_cast<unsigned>(time(nullptr)) + static_cast<unsigned>(getpid()) +
+                    static_cast<unsigned>(port);
+    for (int attempt = 0; attempt <= max_retry; ++attempt) {
+      int fd = -1;
+      bool ok = false;
+      if (local_ipc_) {
+        fd = socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
+        CHECK_GE(fd, 0) << strerror(errno);
+        struct sockaddr_un sa;
+        socklen_t len = UnixAddr(port, &sa);
+        ok = bind(fd, reinterpret_cast<struct sockaddr*>(&sa), len) == 0;
+      } else {
+        fd = socket(AF_INET, SOCK_STREAM | SOCK_CLOEXEC, 0);
+        CHECK_GE(fd, 0) << strerror(errno);
+        int one = 1;
+        setsockopt(fd, SOL_SOCKET, SO_REUSEADDR, &one, sizeof(one));
+        struct sockaddr_in sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.sin_family = AF_INET;
+        sa.sin_addr.s_addr = htonl(INADDR_ANY);
+        sa.sin_port = htons(static_cast<uint16_t>(port));
+        ok = bind(fd, reinterpret_cast<struct sockaddr*>(&sa), sizeof(sa)) == 0;
+      }
+      if (ok && listen(fd, 1024) == 0) {
+        listen_fd_ = fd;
+        AddToEpoll(fd);
+        return port;
+      }
+      close(fd);
+      if (attempt == max_retry) break;
+      port = 10000 + static_cast<int>(rand_r(&seed) % 40000);
+    }
+    return -1;
+  }
+
+  void Connect(const Node& node) override {
+    CHECK_NE(node.id, Node::kEmpty);
+    CHECK_NE(node.port, Node::kEmpty);
+    CHECK(!node.hostname.empty());
+    // same-role peers never exchange messages (except a node with itself,
+    // which is served by the loopback queue and needs no socket)
+    if (node.id == my_node_.id) return;
+    if (node.role == my_node_.role && node.role != Node::SCHEDULER) return;
+
+    int fd = -1;
+    const auto deadline =
+        std::chrono::steady_clock::now() + std::chrono::seconds(connect_timeout_s_);
+    for (;;) {
+      fd = local_ipc_ ? ConnectUnix(node.port) : ConnectTcp(node.hostname, node.port);
+      if (fd >= 0) break;
+      CHECK(std::chrono::steady_clock::now() < deadline)
+          << "cannot connect to " << node.DebugString() << ": " << strerror(errno);
+      std::this_thread::sleep_for(std::chrono::milliseconds(20));
+    }
+    std::shared_ptr<Peer> peer(new Peer());
+    peer->fd = fd;
+    std::shared_ptr<Peer> old;
+    {
+      std::lock_guard<std::mutex> lk(peers_mu_);
+      auto it = peers_.find(node.id);
+      if (it != peers_.end()) old = it->second;
+      peers_[node.id] = peer;
+    }
+    if (old) {  // reconnect after recovery: retire the stale socket
+      std::lock_guard<std::mutex> lk(old->mu);
+      if (old->fd >= 0) close(old->fd);
+      old->fd = -1;
+    }
+  }
+
+  int SendMsg(Message& msg) override {
+    const int recver = msg.meta.recver;
+    CHECK_NE(recver, Meta::kEmpty);
+    if (recver == my_node_.id) return Loopback(msg);
+
+    std::shared_ptr<Peer> peer;
+    {
+      std::lock_guard<std::mutex> lk(peers_mu_);
+      auto it = peers_.find(recver);
+      if (it == peers_.end()) {
+        LOG(WARNING) << "there is no socket to node " << recver;
+        return -1;
+      }
+      peer = it->second;
+    }
+    std::vector<char> meta_buf;
+    PackMeta(msg.meta, &meta_buf);
+    const uint32_t nseg = static_cast<uint32_t>(msg.data.size());
+    CHECK_LE(nseg, kMaxSegments);
+    FrameHeader hdr;
+    hdr.magic = kFrameMagic;
+    hdr.sender = my_node_.id;
+    hdr.recver = recver;
+    hdr.meta_len = static_cast<uint32_t>(meta_buf.size());
+    hdr.num_segments = nseg;
+    hdr.reserved = 0;
+    uint64_t seg_len[kMaxSegments];
+    struct iovec iov[3 + kMaxSegments];
+    int niov = 0;
+    size_t total = 0;
+    iov[niov++] = {&hdr, sizeof(hdr)};
+    if (nseg) iov[niov++] = {seg_len, sizeof(uint64_t) * nseg};
+    iov[niov++] = {meta_buf.data(), meta_buf.size()};
+    for (uint32_t i = 0; i < nseg; ++i) {
+      CHECK(!msg.data[i].on_gpu()) << "TcpVan cannot send device memory: " << msg.DebugString();
+      seg_len[i] = msg.data[i].size();
+      if (seg_len[i]) iov[niov++] = {msg.data[i].data(), msg.data[i].size()};
+    }
+    for (int i = 0; i < niov; ++i) total += iov[i].iov_len;
+
+    std::lock_guard<std::mutex> lk(peer->mu);
+    if (peer->fd < 0) return -1;
+    if (!SendAll(peer->fd, iov, niov)) {
+      LOG(WARNING) << "failed to send to node " << recver << ": " << strerror(errno);
+      return -1;
+    }
+    return static_cast<int>(std::min<size_t>(total, 0x7fffffff));
+  }
+
+  int RecvMsg(Message* msg) override {
+    msg->data.clear();
+    for (;;) {
+      if (PopLoopback(msg)) return 1 + static_cast<int>(msg->meta.data_size & 0x3fffffff);
+      // sockets epoll reported readable and that we have not looked at yet; only
+      // this thread reads them, so each still holds at least one byte
+      while (!ready_fds_.empty()) {
+        const int fd = ready_fds_.front();
+        ready_fds_.pop_front();
+        int bytes = ReadFrame(fd, msg);
+        if (bytes > 0) return bytes;  // 0: the peer closed
+      }
+      struct epoll_event evs[16];
+      int n = epoll_wait(epfd_, evs, 16, -1);
+      if (n < 0) {
+        if (errno == EINTR) continue;
+        LOG(WARNING) << "epoll_wait: " << strerror(errno);
+        return -1;
+      }
+      for (int i = 0; i < n; ++i) {
+        const int fd = evs[i].data.fd;
+        if (fd == wake_fd_) {
+          uint64_t junk;
+          ssize_t r = read(wake_fd_, &junk, sizeof(junk));
+          (void)r;
+        } else if (fd == listen_fd_) {
+          AcceptOne();
+        } else {
+          ready_fds_.push_back(fd);  // level-triggered: drained one frame at a time
+        }
+      }
+    }
+  }
+
+ private:
+  socklen_t UnixAddr(int port, struct sockaddr_un* sa) {
+    memset(sa, 0, sizeof(*sa));
+    sa->sun_family = AF_UNIX;
+    // abstract namespace: no filesystem entry to clean up
+    std::string name = "pslite_b200_" + std::to_string(port);
+    sa->sun_path[0] = '\0';
+    memcpy(sa->sun_path + 1, name.data(), name.size());
+    return static_cast<socklen_t>(offsetof(struct sockaddr_un, sun_path) + 1 + name.size());
+  }
+  int ConnectUnix(int port) {
+    int fd = socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
+    if (fd < 0) return -1;
+    struct sockaddr_un sa;
+    socklen_t len = UnixAddr(port, &sa);
+    if (connect(fd, reinterpret_cast<struct sockaddr*>(&sa), len) != 0) {
+      close(fd);
+      return -1;
+    }
+    return fd;
+  }
+  int ConnectTcp(const std::string& host, int port) {
+    struct addrinfo hints, *res = nullptr;
+    memset(&hints, 0, sizeof(hints));
+    hints.ai_family = AF_INET;
+    hints.ai_socktype = SOCK_STREAM;
+    if (getaddrinfo(host.c_str(), std::to_string(port).c_str(), &hints, &res) != 0 || !res) {
+      return -1;
+    }
+    int fd = socket(res->ai_family, res->ai_socktype | SOCK_CLOEXEC, res->ai_protocol);
+    if (fd < 0) {
+      freeaddrinfo(res);
+      return -1;
+    }
+    if (connect(fd, res->ai_addr, res->ai_addrlen) != 0) {
+      close(fd);
+      freeaddrinfo(res);
+      return -1;
+    }
+    freeaddrinfo(res);
+    int one = 1;
+    setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+    int buf = 8 << 20;
+    setsockopt(fd, SOL_SOCKET, SO_SNDBUF, &buf, sizeof(buf));
+    return fd;
+  }
+
+  void AddToEpoll(int fd) {
+    struct epoll_event ev;
+    memset(&ev, 0, sizeof(ev));
+    ev.events = EPOLLIN;
+    ev.data.fd = fd;
+    CHECK_EQ(epoll_ctl(epfd_, EPOLL_CTL_ADD, fd, &ev), 0) << strerror(errno);
+  }
+
+  void AcceptOne() {
+    // the listen socket is blocking; accept exactly the one pending connection
+    int fd = accept4(listen_fd_, nullptr, nullptr, SOCK_CLOEXEC);
+    if (fd < 0) return;
+    if (!local_ipc_) {
+      int one = 1;
+      setsockopt(fd, IPPROTO_TCP, TCP_NODELAY, &one, sizeof(one));
+      int buf = 8 << 20;
+      setsockopt(fd, SOL_SOCKET, SO_RCVBUF, &buf, sizeof(buf));
+    }
+    inbound_.push_back(fd);
+    AddToEpoll(fd);
+  }
+
+  static bool SendAll(int fd, struct iovec* iov, int niov) {
+    while (niov > 0) {
+      struct msghdr mh;
+      memset(&mh, 0, sizeof(mh));
+      mh.msg_iov = iov;
+      mh.msg_iovlen = static_cast<size_t>(niov);
+      ssize_t n = sendmsg(fd, &mh, MSG_NOSIGNAL);
+      if (n < 0) {
+        if (errno == EINTR) continue;
+        return false;
+      }
+      size_t left = static_cast<size_t>(n);
+      while (niov > 0 && left >= iov->iov_len) {
+        left -= iov->iov_len;
+        ++iov;
+        --niov;
+      }
+      if (niov > 0 && left) {
+        iov->iov_base = static_cast<char*>(iov->iov_base) + left;
+        iov->iov_len -= left;
+      }
+    }
+    return true;
+  }
+
+  /*! \brief 1 = got n bytes, 0 = orderly close before the first byte, -1 = error */
+  static int ReadAll(int fd, void* dst, size_t n) {
+    char* p = static_cast<char*>(dst);
+    size_t got = 0;
+    while (got < n) {
+      ssize_t r = recv(fd, p + got, n - got, 0);
+      if (r == 0) return got == 0 ? 0 : -1;
+      if (r < 0) {
+        if (errno == EINTR) continue;
+        return -1;
+      }
+      got += static_cast<size_t>(r);
+    }
+    return 1;
+  }
+
+  void DropInbound(int fd) {
+    epoll_ctl(epfd_, EPOLL_CTL_DEL, fd, nullptr);
+    close(fd);
+    for (auto it = inbound_.begin(); it != inbound_.end(); ++it) {
+      if (*it == fd) {
+        inbound_.erase(it);
+        break;
+      }
+    }
+  }
+
+  static SArray<char> AllocSegment(size_t len) {
+    SArray<char> seg;
+    if (len == 0) return seg;
+    char* p = nullptr;
+    if (len >= 4096) {
+      void* vp = nullptr;
+      CHECK_EQ(posix_memalign(&vp, 4096, (len + 4095) & ~size_t(4095)), 0);
+      p = static_cast<char*>(vp);
+      seg.reset(p, len, [](char* q) { free(q); });
+    } else {
+      p = new char[len];
+      seg.reset(p, len, [](char* q) { delete[] q; });
+    }
+    return seg;
+  }
+
+  /*! \brief read one whole frame from fd; >0 bytes, 0 if the socket went away */
+  int ReadFrame(int fd, Message* msg) {
+    FrameHeader hdr;
+    int rc = ReadAll(fd, &hdr, sizeof(hdr));
+    if (rc <= 0) {
+      DropInbound(fd);
+      return 0;
+    }
+    CHECK_EQ(hdr.magic, kFrameMagic) << "corrupt frame";
+    CHECK_LE(hdr.num_segments, kMaxSegments);
+    uint64_t seg_len[kMaxSegments];
+    if (hdr.num_segments) {
+      CHECK_EQ(ReadAll(fd, seg_len, sizeof(uint64_t) * hdr.num_segments), 1);
+    }
+    std::vector<char> meta_buf(hdr.meta_len);
+    CHECK_EQ(ReadAll(fd, meta_buf.data(), meta_buf.size()), 1);
+    CHECK(UnpackMeta(meta_buf.data(), meta_buf.size(), &msg->meta)) << "corrupt meta";
+    msg->meta.sender = hdr.sender;
+    msg->meta.recver = my_node_.id;
+    size_t total = sizeof(hdr) + meta_buf.size();
+    msg->data.clear();
+    for (uint32_t i = 0; i < hdr.num_segments; ++i) {
+      SArray<char> seg;
+      if (i == 1 && msg->meta.push && msg->meta.request) {
+        std::lock_guard<std::mutex> lk(reg_mu_);
+        auto it = registered_.find(std::make_pair(msg->meta.sender, msg->meta.key));
+        if (it != registered_.end()) {
+          CHECK_GE(it->second.size(), seg_len[i]) << "registered buffer too small";
+          seg = it->second.segment(0, seg_len[i]);
+        }
+      }
+      if (seg.size() != seg_len[i]) seg = AllocSegment(seg_len[i]);
+      if (seg_len[i]) CHECK_EQ(ReadAll(fd, seg.data(), seg_len[i]), 1);
+      // the bytes now live in host memory of this node
+      seg.src_device_type_ = CPU;
+      seg.src_device_id_ = 0;
+      seg.dst_device_type_ = msg->meta.dst_dev_type == UNK ? CPU : msg->meta.dst_dev_type;
+      seg.dst_device_id_ = msg->meta.dst_dev_id < 0 ? 0 : msg->meta.dst_dev_id;
+      if (i != 1) {
+        seg.dst_device_type_ = CPU;
+        seg.dst_device_id_ = 0;
+      }
+      msg->data.push_back(seg);
+      total += seg_len[i];
+    }
+    return static_cast<int>(std::min<size_t>(total, 0x7fffffff));
+  }
+
+  int Loopback(const Message& msg) {
+    {
+      std::lock_guard<std::mutex> lk(loop_mu_);
+      loop_q_.push_back(msg);
+      loop_q_.back().meta.sender = my_node_.id;
+    }
+    uint64_t one = 1;
+    ssize_t r = write(wake_fd_, &one, sizeof(one));
+    (void)r;
+    return 1 + static_cast<int>(msg.meta.data_size & 0x3fffffff);
+  }
+  bool PopLoopback(Message* msg) {
+    std::lock_guard<std::mutex> lk(loop_mu_);
+    if (loop_q_.empty()) return false;
+    *msg = std::move(loop_q_.front());
+    loop_q_.pop_front();
+    return true;
+  }
+
+  void CloseAll() {
+    std::lock_guard<std::mutex> ilk(init_mu_);
+    {
+      std::lock_guard<std::mutex> lk(peers_mu_);
+      for (auto& kv : peers_) {
+        std::lock_guard<std::mutex> plk(kv.second->mu);
+        if (kv.second->fd >= 0) close(kv.second->fd);
+        kv.second->fd = -1;
+      }
+      peers_.clear();
+    }
+    for (int fd : inbound_) close(fd);
+    inbound_.clear();
+    ready_fds_.clear();
+    if (listen_fd_ >= 0) close(listen_fd_);
+    listen_fd_ = -1;
+    if (wake_fd_ >= 0) close(wake_fd_);
+    wake_fd_ = -1;
+    if (epfd_ >= 0) close(epfd_);
+    epfd_ = -1;
+    {
+      std::lock_guard<std::mutex> lk(loop_mu_);
+      loop_q_.clear();
+    }
+  }
+
+  std::mutex init_mu_;
+  bool local_ipc_ = false;
+  int connect_timeout_s_ = 120;
+  int epfd_ = -1;
+  int wake_fd_ = -1;
+  int listen_fd_ = -1;
+  std::vector<int> inbound_;       // touched by the receive thread only
+  std::deque<int> ready_fds_;      // touched by the receive thread only
+  std::mutex peers_mu_;
+  std::unordered_map<int, std::shared_ptr<Peer>> peers_;
+  std::mutex loop_mu_;
+  std::deque<Message> loop_q_;
+  std::mutex reg_mu_;
+  std::map<std::pair<int, uint64_t>, SArray<char>> registered_;
+};
+
+}  // namespace ps
+
+#endif  // PS_VAN_TCP_VAN_H_
