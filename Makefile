@@ -1,0 +1,70 @@
+# b200-ps native build. Targets:
+#   make            -> build/libpslite.a, benchmark apps, C++ unit tests
+#   make check      -> run the C++ unit tests (CPU only)
+# CUDA sources are cross-compiled for sm_100a (no GPU needed to build).
+# Feature flags mirror the reference Makefile (USE_CUDA/USE_KEY32/ASAN, Makefile:24-84).
+USE_CUDA ?= 1
+USE_KEY32 ?= 0
+ASAN ?= 0
+CUDA_HOME ?= /usr/local/cuda
+BUILD ?= build
+
+CXX ?= g++
+NVCC ?= $(CUDA_HOME)/bin/nvcc
+CXXFLAGS := -std=c++17 -O2 -g -Wall -Wno-unused-function -fPIC -Iinclude -Isrc -pthread
+NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Isrc -Iinclude
+LDFLAGS := -pthread -lrt
+ifeq ($(USE_KEY32),1)
+CXXFLAGS += -DUSE_KEY32=1
+endif
+ifeq ($(ASAN),1)
+CXXFLAGS += -fsanitize=address -fno-omit-frame-pointer
+LDFLAGS += -fsanitize=address
+endif
+
+CORE_SRCS := src/core/wire.cc src/core/customer.cc src/core/postoffice.cc src/core/van.cc src/van/van_factory.cc
+CU_SRCS :=
+ifeq ($(USE_CUDA),1)
+CXXFLAGS += -DPS_USE_CUDA=1 -I$(CUDA_HOME)/include
+CORE_SRCS += src/van/cuda_domain.cc src/server/gpu_server.cc
+CU_SRCS += src/kernels/copy_kernels.cu src/kernels/update_kernels.cu
+LDFLAGS += -L$(CUDA_HOME)/lib64 -lcudart -ldl
+endif
+
+CORE_OBJS := $(patsubst %.cc,$(BUILD)/%.o,$(CORE_SRCS))
+CU_OBJS := $(patsubst %.cu,$(BUILD)/%.o,$(CU_SRCS))
+LIB := $(BUILD)/libpslite.a
+
+APPS := $(BUILD)/test_benchmark $(BUILD)/kernel_bench
+TESTS := $(patsubst cpp_tests/%.cc,$(BUILD)/cpp_tests/%,$(wildcard cpp_tests/*.cc))
+
+all: $(LIB) $(APPS) $(TESTS)
+
+$(BUILD)/%.o: %.cc
+	@mkdir -p $(dir $@)
+	$(CXX) $(CXXFLAGS) -MMD -MP -c $< -o $@
+
+$(BUILD)/%.o: %.cu
+	@mkdir -p $(dir $@)
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(CORE_OBJS) $(CU_OBJS)
+	@rm -f $@
+	ar rcs $@ $^
+
+$(BUILD)/%: apps/%.cc $(LIB)
+	@mkdir -p $(dir $@)
+	$(CXX) $(CXXFLAGS) $< $(LIB) $(LDFLAGS) -o $@
+
+$(BUILD)/cpp_tests/%: cpp_tests/%.cc $(LIB)
+	@mkdir -p $(dir $@)
+	$(CXX) $(CXXFLAGS) $< $(LIB) $(LDFLAGS) -o $@
+
+check: $(TESTS)
+	@set -e; for t in $(TESTS); do echo "== $$t"; timeout 120 $$t; done; echo ALL CPP TESTS PASSED
+
+clean:
+	rm -rf $(BUILD)
+
+-include $(CORE_OBJS:.o=.d)
+.PHONY: all check clean

@@ -169,6 +169,8 @@ struct MemRef {
   int32_t region = -1;
   /*! \brief byte offset of the span inside the region */
   uint64_t offset = 0;
+  /*! \brief bytes of payload placed at the span (wire form) */
+  uint64_t bytes = 0;
   /*! \brief value the producer will store to the span's ready-flag; 0 = no flag */
   uint64_t flag_seq = 0;
   bool valid() const { return region >= 0; }
@@ -200,7 +202,8 @@ struct Meta {
       for (auto d : data_type) os << " " << DataTypeName[static_cast<int>(d)];
       os << " }";
     }
-    if (mem.valid()) os << ", mem={r" << mem.region << "+" << mem.offset << " seq=" << mem.flag_seq << "}";
+    if (mem.valid()) os << ", mem={r" << mem.region << "+" << mem.offset << " bytes=" << mem.bytes << "}";
+    if (codec) os << ", codec=" << codec << ", scale=" << scale;
     if (!control.empty() || simple_app) os << ". NOT DATA MSG!";
     return os.str();
   }
@@ -235,12 +238,27 @@ struct Meta {
   int sid = 0;
   /*! \brief peer-mappable location of the value buffer, if any */
   MemRef mem;
+  /*! \brief transform the sender's copy engine applied to the values (WireCodec) */
+  int codec = 0;
+  /*! \brief scale folded into the transform (e.g. 1/num_workers on gradient push) */
+  float scale = 1.0f;
+};
+
+/*! \brief per-send options that never travel on the wire */
+struct SendOpts {
+  /*! \brief WireCodec applied while copying the values into peer memory */
+  int codec = 0;
+  float scale = 1.0f;
+  /*! \brief cudaEvent_t the copy must wait for (producer of the values), or null */
+  void* wait_event = nullptr;
 };
 
 /*! \brief meta + zero-copy payload segments */
 struct Message {
   Meta meta;
   std::vector<SArray<char>> data;
+  /*! \brief local-only: event gating the one-sided copy of data[1] */
+  void* wait_event = nullptr;
 
   /*! \brief append a segment; the second one (the values) sets the placement fields */
   template <typename V>

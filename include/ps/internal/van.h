@@ -68,6 +68,13 @@ class Van {
   virtual void RegisterRecvBuffer(Message& /*msg*/) {}
   /*! \brief make [addr, addr+length) reachable by peers (export / map) ahead of use */
   virtual void PinMemory(void* /*addr*/, size_t /*length*/, bool /*gpu*/, int /*dev_index*/ = 0) {}
+  /*! \brief memory peers can map (HBM on the NVLink van, shm on the shm van, else heap) */
+  virtual void* AllocExportable(size_t bytes) { return malloc(bytes); }
+  virtual void FreeExportable(void* p) { free(p); }
+  /*! \brief this process's mapping of a span a peer announced (one-sided vans), else null */
+  virtual void* ResolvePeerMem(int /*node_id*/, const MemRef& /*mem*/) { return nullptr; }
+  /*! \brief stream the van's copy kernels run on (cudaStream_t), null for CPU vans */
+  virtual void* DataStream() { return nullptr; }
   /*! \brief install the node identity (after the scheduler assigned the id) */
   virtual void SetNode(const Node& node) {
     my_node_ = node;

@@ -54,6 +54,9 @@ struct KVMeta {
   int option = 0;
   /*! \brief peer-mappable location of the worker's value buffer (one-sided vans) */
   MemRef mem;
+  /*! \brief WireCodec the sender applied to the values, and its scale */
+  int codec = 0;
+  float scale = 1.0f;
 };
 
 namespace kv_detail {
@@ -129,13 +132,22 @@ class KVWorker : public SimpleApp {
    */
   int ZPush(const SArray<Key>& keys, const SArray<Val>& vals, const SArray<int>& lens = {},
             int cmd = 0, const Callback& cb = nullptr) {
+    return ZPush(keys, vals, lens, cmd, cb, SendOpts());
+  }
+  /*!
+   * \brief ZPush whose transport copy is fused with a transform (`opts.codec`:
+   *        scale / cast to bf16 / block-scaled fp8) and gated on `opts.wait_event`.
+   *        One-sided vans only; the server sees the wire form.
+   */
+  int ZPush(const SArray<Key>& keys, const SArray<Val>& vals, const SArray<int>& lens, int cmd,
+            const Callback& cb, const SendOpts& opts) {
     const int ts = obj_->NewRequest(kServerGroup);
     AddCallback(ts, cb);
     KVPairs<Val> kvs;
     kvs.keys = keys;
     kvs.vals = vals;
     kvs.lens = lens;
-    Send(ts, true, cmd, kvs);
+    Send(ts, true, cmd, kvs, opts);
     return ts;
   }
 
@@ -164,7 +176,7 @@ class KVWorker : public SimpleApp {
     callbacks_[timestamp] = cb;
   }
   void RunCallback(int timestamp);
-  void Send(int timestamp, bool push, int cmd, KVPairs<Val>& kvs);
+  void Send(int timestamp, bool push, int cmd, KVPairs<Val>& kvs, const SendOpts& opts = SendOpts());
   void Process(const Message& msg);
   void DefaultSlicer(const KVPairs<Val>& send, const std::vector<Range>& ranges,
                      SlicedKVs* sliced);
@@ -202,7 +214,11 @@ class KVServer : public SimpleApp {
   }
 
   /*! \brief reply to `req`; `res` is empty for a push ack */
-  void Response(const KVMeta& req, const KVPairs<Val>& res = KVPairs<Val>());
+  void Response(const KVMeta& req, const KVPairs<Val>& res = KVPairs<Val>()) {
+    Response(req, res, SendOpts());
+  }
+  /*! \brief reply whose value copy is fused with `opts.codec` and gated on `opts.wait_event` */
+  void Response(const KVMeta& req, const KVPairs<Val>& res, const SendOpts& opts);
 
   /*! \brief deprecated: takes an instance-level worker *id* */
   void RegisterRecvBuffer(int worker_id, SArray<Key>& keys, const SArray<Val>& vals,
@@ -288,6 +304,8 @@ void KVServer<Val>::Process(const Message& msg) {
   meta.val_len = msg.meta.val_len;
   meta.option = msg.meta.option;
   meta.mem = msg.meta.mem;
+  meta.codec = msg.meta.codec;
+  meta.scale = msg.meta.scale;
   KVPairs<Val> data;
   const size_t n = msg.data.size();
   if (n) {
@@ -305,7 +323,7 @@ void KVServer<Val>::Process(const Message& msg) {
 }
 
 template <typename Val>
-void KVServer<Val>::Response(const KVMeta& req, const KVPairs<Val>& res) {
+void KVServer<Val>::Response(const KVMeta& req, const KVPairs<Val>& res, const SendOpts& opts) {
   // answer the instance of the worker group that pairs with this server instance
   const int worker_rank = Postoffice::IDtoRank(req.sender);
   Message msg;
@@ -321,6 +339,9 @@ void KVServer<Val>::Response(const KVMeta& req, const KVPairs<Val>& res) {
   msg.meta.val_len = req.val_len;
   msg.meta.option = req.option;
   msg.meta.mem = req.mem;
+  msg.meta.codec = opts.codec;
+  msg.meta.scale = opts.scale;
+  msg.wait_event = opts.wait_event;
   if (res.keys.size()) {
     msg.AddData(res.keys);
     msg.AddData(res.vals);
@@ -384,7 +405,8 @@ void KVWorker<Val>::DefaultSlicer(const KVPairs<Val>& send, const std::vector<Ra
 }
 
 template <typename Val>
-void KVWorker<Val>::Send(int timestamp, bool push, int cmd, KVPairs<Val>& kvs) {
+void KVWorker<Val>::Send(int timestamp, bool push, int cmd, KVPairs<Val>& kvs,
+                         const SendOpts& opts) {
   SlicedKVs sliced;
   slicer_(kvs, postoffice_->GetServerKeyRanges(), &sliced);
 
@@ -410,6 +432,9 @@ void KVWorker<Val>::Send(int timestamp, bool push, int cmd, KVPairs<Val>& kvs) {
     msg.meta.addr = reinterpret_cast<uint64_t>(part.vals.data());
     msg.meta.val_len = static_cast<int64_t>(part.vals.size());
     if (part.keys.size()) msg.meta.key = part.keys[0];
+    msg.meta.codec = opts.codec;
+    msg.meta.scale = opts.scale;
+    msg.wait_event = opts.wait_event;
     const SArray<Val> dest = part.vals;  // placement of the pull destination
     if (!push) part.vals.clear();
     if (part.keys.size()) {

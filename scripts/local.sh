@@ -1,0 +1,29 @@
+#!/bin/bash
+# Run a ps-lite style job on this host: 1 scheduler + S servers + W workers.
+# usage: scripts/local.sh <num_servers> <num_workers> <binary> [args...]
+# (parity: reference tests/local.sh:8-37). Extra env is inherited.
+set -u
+if [ $# -lt 3 ]; then
+  echo "usage: $0 num_servers num_workers bin [args..]"; exit 1
+fi
+export DMLC_NUM_SERVER=$1; shift
+export DMLC_NUM_WORKER=$1; shift
+bin=$1; shift
+args="$@"
+export DMLC_PS_ROOT_URI=${DMLC_PS_ROOT_URI:-127.0.0.1}
+export DMLC_PS_ROOT_PORT=${DMLC_PS_ROOT_PORT:-$((20000 + RANDOM % 20000))}
+export DMLC_NODE_HOST=${DMLC_NODE_HOST:-127.0.0.1}
+pids=()
+DMLC_ROLE=scheduler ${bin} ${args} &
+pids+=($!)
+for ((i=0; i<${DMLC_NUM_SERVER}; ++i)); do
+  DMLC_ROLE=server PS_CUDA_DEVICE=${SERVER_GPU_BASE:+$((SERVER_GPU_BASE + i))} ${bin} ${args} &
+  pids+=($!)
+done
+for ((i=0; i<${DMLC_NUM_WORKER}; ++i)); do
+  DMLC_ROLE=worker PS_CUDA_DEVICE=${WORKER_GPU_BASE:+$((WORKER_GPU_BASE + i))} ${bin} ${args} &
+  pids+=($!)
+done
+rc=0
+for p in "${pids[@]}"; do wait $p || rc=$?; done
+exit $rc

@@ -94,8 +94,11 @@ void PackMeta(const Meta& m, std::vector<char>* out) {
   if (flags & kFlagHasMem) {
     w.Put<int32_t>(m.mem.region);
     w.Put<uint64_t>(m.mem.offset);
+    w.Put<uint64_t>(m.mem.bytes);
     w.Put<uint64_t>(m.mem.flag_seq);
   }
+  w.Put<int32_t>(m.codec);
+  w.Put<float>(m.scale);
   w.PutString(m.body);
   w.Put<uint8_t>(static_cast<uint8_t>(m.data_type.size()));
   for (DataType d : m.data_type) w.Put<uint8_t>(static_cast<uint8_t>(d));
@@ -140,8 +143,11 @@ bool UnpackMeta(const char* buf, size_t len, Meta* m) {
   if (flags & kFlagHasMem) {
     m->mem.region = r.Get<int32_t>();
     m->mem.offset = r.Get<uint64_t>();
+    m->mem.bytes = r.Get<uint64_t>();
     m->mem.flag_seq = r.Get<uint64_t>();
   }
+  m->codec = r.Get<int32_t>();
+  m->scale = r.Get<float>();
   m->body = r.GetString();
   int ndt = r.Get<uint8_t>();
   m->data_type.resize(ndt);

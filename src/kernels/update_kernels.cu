@@ -1,0 +1,329 @@
+/**
+ * \file update_kernels.cu
+ * \brief K_update: the GPU-resident server's push handler, fused (sm_100a).
+ *
+ * The reference aggregates on the CPU with `store[key] += val`
+ * (include/ps/kv_app.h:441-447) and leaves the optimizer to the consumer. Here
+ * one memory-bound pass per parameter shard does everything the server owes its
+ * workers for a round:
+ *     g      = grad_scale * sum_w dequant(slot_w)      (bf16 | fp8-block | f32 slots)
+ *     m,v,p  = AdamW / SGD-momentum on fp32 state
+ *     out_k  = bf16(p)  for every destination k       (<= 9: local + W workers)
+ * The destinations may be peer-mapped worker parameter buffers, so the update
+ * is also the pull reply: parameters leave the SM once and fan out over NVLink
+ * as plain 16-byte stores — there is no intermediate shard copy to re-read.
+ *
+ * Roofline: per element it must read W*g + 12 B (master, m, v) and write 12 B +
+ * 2 B per destination; no reuse, so the target is HBM / NVLink bandwidth.
+ * Each thread-iteration handles 8 elements: 16-byte loads for bf16 grads, 8-byte
+ * for fp8, 2 x 16-byte for each fp32 state array, 16-byte bf16 stores.
+ */
+#include <cuda_bf16.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "kernels/ps_kernels.h"
+
+namespace ps_kernels_internal {
+void CountLaunch(int n);
+}
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kNumSMs = 148;
+
+struct UpdateDev {
+  size_t n;
+  int num_grads;
+  int num_outs;
+  const void* grads[PS_MAX_FANIN];
+  float* master;
+  float* m;
+  float* v;
+  void* outs[PS_MAX_FANOUT];
+};
+
+__device__ __forceinline__ int4 ldg16(const void* p) {
+  int4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ uint2 ldg8(const void* p) {
+  uint2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];"
+               : "=r"(r.x), "=r"(r.y)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ float4 ldf4(const float* p) {
+  float4 r;
+  asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void stf4(float* p, const float4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x),
+               "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ void st16(void* p, const int4& v) {
+  asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float2 bf2(uint32_t u) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(t);
+}
+__device__ __forceinline__ uint32_t pk(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ float e8m0(uint32_t biased) {
+  const int be = max(1, min(254, static_cast<int>(biased)));
+  return __uint_as_float(static_cast<uint32_t>(be) << 23);
+}
+__device__ __forceinline__ void fp8x4_to_f32(uint32_t q, float s, float* out) {
+  const __half2_raw lo = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>(q & 0xffffu),
+                                                    __NV_E4M3);
+  const __half2_raw hi = __nv_cvt_fp8x2_to_halfraw2(static_cast<__nv_fp8x2_storage_t>(q >> 16),
+                                                    __NV_E4M3);
+  const float2 a = __half22float2(__half2(lo)), b = __half22float2(__half2(hi));
+  out[0] = a.x * s; out[1] = a.y * s; out[2] = b.x * s; out[3] = b.y * s;
+}
+
+/*! \brief sum of 8 consecutive gradient elements starting at 8*i over all W slots */
+template <int FMT>
+__device__ __forceinline__ void gather_grads(const UpdateDev& a, size_t i, float* g) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  const size_t npad = (a.n + 31) / 32 * 32;
+#pragma unroll 1
+  for (int w = 0; w < a.num_grads; ++w) {
+    const unsigned char* base = static_cast<const unsigned char*>(a.grads[w]);
+    if (FMT == PS_GRAD_BF16) {
+      const int4 q = ldg16(base + i * 16);
+      float2 f;
+      f = bf2(q.x); g[0] += f.x; g[1] += f.y;
+      f = bf2(q.y); g[2] += f.x; g[3] += f.y;
+      f = bf2(q.z); g[4] += f.x; g[5] += f.y;
+      f = bf2(q.w); g[6] += f.x; g[7] += f.y;
+    } else if (FMT == PS_GRAD_FP8BLOCK) {
+      const uint2 q = ldg8(base + i * 8);
+      const float s = e8m0(base[npad + (i >> 2)]);
+      float t[8];
+      fp8x4_to_f32(q.x, s, t);
+      fp8x4_to_f32(q.y, s, t + 4);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g[j] += t[j];
+    } else {
+      const int4 q0 = ldg16(base + i * 32), q1 = ldg16(base + i * 32 + 16);
+      g[0] += __int_as_float(q0.x); g[1] += __int_as_float(q0.y);
+      g[2] += __int_as_float(q0.z); g[3] += __int_as_float(q0.w);
+      g[4] += __int_as_float(q1.x); g[5] += __int_as_float(q1.y);
+      g[6] += __int_as_float(q1.z); g[7] += __int_as_float(q1.w);
+    }
+  }
+}
+
+template <int FMT>
+__device__ __forceinline__ float gather_one(const UpdateDev& a, size_t e) {
+  float g = 0.f;
+  const size_t npad = (a.n + 31) / 32 * 32;
+  for (int w = 0; w < a.num_grads; ++w) {
+    const unsigned char* base = static_cast<const unsigned char*>(a.grads[w]);
+    if (FMT == PS_GRAD_BF16) {
+      g += __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[e]);
+    } else if (FMT == PS_GRAD_FP8BLOCK) {
+      const __half_raw h = __nv_cvt_fp8_to_halfraw(base[e], __NV_E4M3);
+      g += __half2float(__half(h)) * e8m0(base[npad + (e >> 5)]);
+    } else {
+      g += reinterpret_cast<const float*>(base)[e];
+    }
+  }
+  return g;
+}
+
+template <int OPT>
+__device__ __forceinline__ void step(float& p, float& m, float& v, float g,
+                                     const ps_opt_params& o) {
+  if (OPT == PS_OPT_ADAMW) {
+    m = o.beta1 * m + (1.f - o.beta1) * g;
+    v = o.beta2 * v + (1.f - o.beta2) * g * g;
+    const float mhat = m / o.bias_corr1;
+    const float vhat = v / o.bias_corr2;
+    p = p - o.lr * (mhat / (sqrtf(vhat) + o.eps) + o.weight_decay * p);
+  } else {
+    g += o.weight_decay * p;
+    m = o.beta1 * m + g;
+    p = p - o.lr * m;
+  }
+}
+
+template <int FMT, int OPT, bool OUT_F32>
+__global__ void __launch_bounds__(kThreads)
+k_update(const UpdateDev a, const ps_opt_params o) {
+  const size_t n8 = a.n / 8;
+  const size_t stride = static_cast<size_t>(gridDim.x) * kThreads;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x; i < n8; i += stride) {
+    // issue the state loads first so they overlap the W gradient loads
+    float4 p0 = ldf4(a.master + i * 8), p1 = ldf4(a.master + i * 8 + 4);
+    float4 m0 = ldf4(a.m + i * 8), m1 = ldf4(a.m + i * 8 + 4);
+    float4 v0 = make_float4(0, 0, 0, 0), v1 = v0;
+    if (OPT == PS_OPT_ADAMW) {
+      v0 = ldf4(a.v + i * 8);
+      v1 = ldf4(a.v + i * 8 + 4);
+    }
+    float g[8];
+    gather_grads<FMT>(a, i, g);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] *= o.grad_scale;
+    step<OPT>(p0.x, m0.x, v0.x, g[0], o); step<OPT>(p0.y, m0.y, v0.y, g[1], o);
+    step<OPT>(p0.z, m0.z, v0.z, g[2], o); step<OPT>(p0.w, m0.w, v0.w, g[3], o);
+    step<OPT>(p1.x, m1.x, v1.x, g[4], o); step<OPT>(p1.y, m1.y, v1.y, g[5], o);
+    step<OPT>(p1.z, m1.z, v1.z, g[6], o); step<OPT>(p1.w, m1.w, v1.w, g[7], o);
+    stf4(a.master + i * 8, p0); stf4(a.master + i * 8 + 4, p1);
+    stf4(a.m + i * 8, m0); stf4(a.m + i * 8 + 4, m1);
+    if (OPT == PS_OPT_ADAMW) {
+      stf4(a.v + i * 8, v0);
+      stf4(a.v + i * 8 + 4, v1);
+    }
+    if (OUT_F32) {
+#pragma unroll 1
+      for (int k = 0; k < a.num_outs; ++k) {
+        stf4(static_cast<float*>(a.outs[k]) + i * 8, p0);
+        stf4(static_cast<float*>(a.outs[k]) + i * 8 + 4, p1);
+      }
+    } else {
+      int4 out;
+      out.x = pk(p0.x, p0.y); out.y = pk(p0.z, p0.w);
+      out.z = pk(p1.x, p1.y); out.w = pk(p1.z, p1.w);
+#pragma unroll 1
+      for (int k = 0; k < a.num_outs; ++k) st16(static_cast<char*>(a.outs[k]) + i * 16, out);
+    }
+  }
+  // ragged tail (< 8 elements) handled by the first threads of block 0
+  if (blockIdx.x == 0) {
+    const size_t e = n8 * 8 + threadIdx.x;
+    if (e < a.n) {
+      float p = a.master[e], m = a.m[e], v = OPT == PS_OPT_ADAMW ? a.v[e] : 0.f;
+      const float g = gather_one<FMT>(a, e) * o.grad_scale;
+      step<OPT>(p, m, v, g, o);
+      a.master[e] = p;
+      a.m[e] = m;
+      if (OPT == PS_OPT_ADAMW) a.v[e] = v;
+      for (int k = 0; k < a.num_outs; ++k) {
+        if (OUT_F32) static_cast<float*>(a.outs[k])[e] = p;
+        else static_cast<__nv_bfloat16*>(a.outs[k])[e] = __float2bfloat16_rn(p);
+      }
+    }
+  }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kThreads)
+k_sum(float* __restrict__ out, const UpdateDev a, float scale, int accumulate) {
+  const size_t n8 = a.n / 8;
+  const size_t stride = static_cast<size_t>(gridDim.x) * kThreads;
+  for (size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x; i < n8; i += stride) {
+    float g[8];
+    gather_grads<FMT>(a, i, g);
+    float4 o0 = make_float4(0, 0, 0, 0), o1 = o0;
+    if (accumulate) {
+      o0 = ldf4(out + i * 8);
+      o1 = ldf4(out + i * 8 + 4);
+    }
+    o0.x += g[0] * scale; o0.y += g[1] * scale; o0.z += g[2] * scale; o0.w += g[3] * scale;
+    o1.x += g[4] * scale; o1.y += g[5] * scale; o1.z += g[6] * scale; o1.w += g[7] * scale;
+    stf4(out + i * 8, o0);
+    stf4(out + i * 8 + 4, o1);
+  }
+  if (blockIdx.x == 0) {
+    const size_t e = n8 * 8 + threadIdx.x;
+    if (e < a.n) out[e] = (accumulate ? out[e] : 0.f) + gather_one<FMT>(a, e) * scale;
+  }
+}
+
+int GridFor(size_t items, int max_ctas, int per_sm) {
+  size_t want = (items + kThreads - 1) / kThreads;
+  size_t cap = max_ctas > 0 ? static_cast<size_t>(max_ctas) : static_cast<size_t>(kNumSMs) * per_sm;
+  if (want > cap) want = cap;
+  return want < 1 ? 1 : static_cast<int>(want);
+}
+
+template <int FMT, int OPT>
+void LaunchUpdate(const UpdateDev& d, const ps_opt_params& o, bool out_f32, int grid,
+                  cudaStream_t st) {
+  if (out_f32) k_update<FMT, OPT, true><<<grid, kThreads, 0, st>>>(d, o);
+  else k_update<FMT, OPT, false><<<grid, kThreads, 0, st>>>(d, o);
+}
+
+}  // namespace
+
+extern "C" int ps_launch_update(const ps_update_args* args, const ps_opt_params* opt, int max_ctas,
+                                ps_stream_t stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  if (args->n == 0) return 0;
+  if (args->num_grads < 1 || args->num_grads > PS_MAX_FANIN) return cudaErrorInvalidValue;
+  if (args->num_outs < 0 || args->num_outs > PS_MAX_FANOUT) return cudaErrorInvalidValue;
+  UpdateDev d;
+  d.n = args->n;
+  d.num_grads = args->num_grads;
+  d.num_outs = args->num_outs;
+  for (int i = 0; i < PS_MAX_FANIN; ++i) d.grads[i] = i < args->num_grads ? args->grads[i] : nullptr;
+  for (int i = 0; i < PS_MAX_FANOUT; ++i) d.outs[i] = i < args->num_outs ? args->outs[i] : nullptr;
+  d.master = args->master;
+  d.m = args->m;
+  d.v = args->v;
+  // 2 resident CTAs/SM x 148 keeps ~100 KB of loads in flight per SM
+  const int grid = GridFor(args->n / 8 + 1, max_ctas, 4);
+  const bool f32 = args->out_f32 != 0;
+  const bool adam = opt->optimizer == PS_OPT_ADAMW;
+  switch (args->grad_format) {
+    case PS_GRAD_BF16:
+      adam ? LaunchUpdate<PS_GRAD_BF16, PS_OPT_ADAMW>(d, *opt, f32, grid, st)
+           : LaunchUpdate<PS_GRAD_BF16, PS_OPT_SGD>(d, *opt, f32, grid, st);
+      break;
+    case PS_GRAD_FP8BLOCK:
+      adam ? LaunchUpdate<PS_GRAD_FP8BLOCK, PS_OPT_ADAMW>(d, *opt, f32, grid, st)
+           : LaunchUpdate<PS_GRAD_FP8BLOCK, PS_OPT_SGD>(d, *opt, f32, grid, st);
+      break;
+    case PS_GRAD_F32:
+      adam ? LaunchUpdate<PS_GRAD_F32, PS_OPT_ADAMW>(d, *opt, f32, grid, st)
+           : LaunchUpdate<PS_GRAD_F32, PS_OPT_SGD>(d, *opt, f32, grid, st);
+      break;
+    default:
+      return cudaErrorInvalidValue;
+  }
+  ps_kernels_internal::CountLaunch(1);
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ps_launch_sum(float* out, const void* const* grads, int num_grads, int fmt, size_t n,
+                             float scale, int accumulate, ps_stream_t stream_) {
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream_);
+  if (n == 0) return 0;
+  if (num_grads < 1 || num_grads > PS_MAX_FANIN) return cudaErrorInvalidValue;
+  UpdateDev d;
+  d.n = n;
+  d.num_grads = num_grads;
+  d.num_outs = 0;
+  for (int i = 0; i < PS_MAX_FANIN; ++i) d.grads[i] = i < num_grads ? grads[i] : nullptr;
+  for (int i = 0; i < PS_MAX_FANOUT; ++i) d.outs[i] = nullptr;
+  d.master = d.m = d.v = nullptr;
+  const int grid = GridFor(n / 8 + 1, 0, 4);
+  if (fmt == PS_GRAD_BF16) k_sum<PS_GRAD_BF16><<<grid, kThreads, 0, st>>>(out, d, scale, accumulate);
+  else if (fmt == PS_GRAD_FP8BLOCK)
+    k_sum<PS_GRAD_FP8BLOCK><<<grid, kThreads, 0, st>>>(out, d, scale, accumulate);
+  else if (fmt == PS_GRAD_F32)
+    k_sum<PS_GRAD_F32><<<grid, kThreads, 0, st>>>(out, d, scale, accumulate);
+  else return cudaErrorInvalidValue;
+  ps_kernels_internal::CountLaunch(1);
+  return static_cast<int>(cudaGetLastError());
+}

@@ -1,0 +1,216 @@
+/**
+ * \file cuda_domain.cc
+ * \brief CudaDomain implementation (see cuda_domain.h).
+ */
+#include "van/cuda_domain.h"
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <unordered_map>
+
+#include "kernels/ps_kernels.h"
+
+namespace ps {
+
+#define PS_CUDA_CHECK(expr)                                                       \
+  do {                                                                            \
+    cudaError_t e_ = (expr);                                                      \
+    CHECK(e_ == cudaSuccess) << "CUDA: " #expr " -> " << cudaGetErrorString(e_);  \
+  } while (0)
+
+int CudaDeviceCount() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+namespace {
+
+class CudaDomain : public MemDomain {
+ public:
+  explicit CudaDomain(int dev) : dev_(dev) {
+    PS_CUDA_CHECK(cudaSetDevice(dev_));
+    int lo = 0, hi = 0;
+    PS_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    PS_CUDA_CHECK(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, hi));
+    max_ctas_ = GetEnv("PS_COPY_CTAS", 0);
+  }
+  ~CudaDomain() override {
+    cudaSetDevice(dev_);
+    cudaStreamSynchronize(stream_);
+    for (cudaEvent_t e : free_events_) cudaEventDestroy(e);
+    for (auto& kv : imported_) cudaIpcCloseMemHandle(kv.second);
+    cudaStreamDestroy(stream_);
+  }
+  const char* name() const override { return "nvl"; }
+  int device() const override { return dev_; }
+  void* Stream() override { return stream_; }
+
+  bool Handles(int device_type, const void* /*ptr*/) override { return device_type == GPU; }
+
+  void* Alloc(size_t bytes) override {
+    PS_CUDA_CHECK(cudaSetDevice(dev_));
+    void* p = nullptr;
+    PS_CUDA_CHECK(cudaMalloc(&p, bytes));
+    return p;
+  }
+  void Free(void* p) override {
+    cudaSetDevice(dev_);
+    cudaFree(p);
+  }
+
+  bool Export(const void* p, RegionDesc* out) override {
+    PS_CUDA_CHECK(cudaSetDevice(dev_));
+    CUdeviceptr base = 0;
+    size_t size = 0;
+    // resolved through the runtime so that the library has no link-time dependency on
+    // libcuda.so (absent on GPU-less build / CI hosts)
+    typedef CUresult (*GetRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
+    static GetRangeFn get_range = [] {
+      void* fn = nullptr;
+      cudaDriverEntryPointQueryResult q;
+      if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) !=
+              cudaSuccess || q != cudaDriverEntryPointSuccess) {
+        cudaGetLastError();
+        fn = nullptr;
+      }
+      return reinterpret_cast<GetRangeFn>(fn);
+    }();
+    if (!get_range || get_range(&base, &size, reinterpret_cast<CUdeviceptr>(p)) != CUDA_SUCCESS) {
+      return false;
+    }
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = exported_.find(base);
+    if (it == exported_.end()) {
+      cudaIpcMemHandle_t h;
+      cudaError_t e = cudaIpcGetMemHandle(&h, reinterpret_cast<void*>(base));
+      if (e != cudaSuccess) {
+        LOG(WARNING) << "cudaIpcGetMemHandle failed (" << cudaGetErrorString(e)
+                     << "): memory from a VMM / expandable-segments allocator cannot be exported";
+        cudaGetLastError();
+        return false;
+      }
+      it = exported_.emplace(base, h).first;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle must fit RegionDesc::handle");
+    memcpy(out->handle, &it->second, 64);
+    out->pid = static_cast<int32_t>(getpid());
+    out->dev = dev_;
+    out->base = static_cast<uint64_t>(base);
+    out->size = size;
+    return true;
+  }
+
+  void* Import(const RegionDesc& d) override {
+    PS_CUDA_CHECK(cudaSetDevice(dev_));
+    if (d.pid == static_cast<int32_t>(getpid())) {
+      // same address space: no IPC; only make sure the two devices can see each other
+      if (d.dev >= 0 && d.dev != dev_) {
+        cudaError_t e = cudaDeviceEnablePeerAccess(d.dev, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+          LOG(FATAL) << "cudaDeviceEnablePeerAccess(" << d.dev << "): " << cudaGetErrorString(e);
+        }
+        cudaGetLastError();
+      }
+      return reinterpret_cast<void*>(d.base);
+    }
+    std::string key(d.handle, 64);
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = imported_.find(key);
+    if (it != imported_.end()) return it->second;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, d.handle, 64);
+    void* base = nullptr;
+    PS_CUDA_CHECK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    imported_[key] = base;
+    return base;
+  }
+
+  Ticket CopyAsync(void* dst, const void* src, size_t n, int codec, float scale,
+                   void* wait_event) override {
+    PS_CUDA_CHECK(cudaSetDevice(dev_));
+    if (wait_event) {
+      PS_CUDA_CHECK(cudaStreamWaitEvent(stream_, static_cast<cudaEvent_t>(wait_event), 0));
+    }
+    if (n) {
+      cudaPointerAttributes attr;
+      bool src_on_device = true;
+      if (cudaPointerGetAttributes(&attr, src) != cudaSuccess ||
+          (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)) {
+        cudaGetLastError();
+        src_on_device = false;
+      }
+      if (!src_on_device) {
+        CHECK_EQ(codec, (int)kCodecRaw) << "host-resident values can only be sent raw";
+        PS_CUDA_CHECK(cudaMemcpyAsync(dst, src, n, cudaMemcpyDefault, stream_));
+      } else {
+        int rc = ps_launch_copy(dst, src, n, codec, scale, max_ctas_,
+                                reinterpret_cast<ps_stream_t>(stream_));
+        CHECK_EQ(rc, 0) << "copy kernel launch failed: "
+                        << cudaGetErrorString(static_cast<cudaError_t>(rc));
+      }
+    }
+    cudaEvent_t ev = AcquireEvent();
+    PS_CUDA_CHECK(cudaEventRecord(ev, stream_));
+    Ticket t;
+    t.event = ev;
+    return t;
+  }
+
+  void Wait(Ticket t) override {
+    if (!t.event) return;
+    cudaEvent_t ev = static_cast<cudaEvent_t>(t.event);
+    PS_CUDA_CHECK(cudaEventSynchronize(ev));
+    std::lock_guard<std::mutex> lk(mu_);
+    free_events_.push_back(ev);
+  }
+
+ private:
+  cudaEvent_t AcquireEvent() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (!free_events_.empty()) {
+        cudaEvent_t e = free_events_.back();
+        free_events_.pop_back();
+        return e;
+      }
+    }
+    cudaEvent_t e;
+    PS_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return e;
+  }
+
+  int dev_;
+  int max_ctas_ = 0;
+  cudaStream_t stream_ = nullptr;
+  std::mutex mu_;
+  std::vector<cudaEvent_t> free_events_;
+  std::unordered_map<CUdeviceptr, cudaIpcMemHandle_t> exported_;
+  std::unordered_map<std::string, void*> imported_;
+};
+
+}  // namespace
+
+MemDomain* CreateCudaDomain() {
+  const int n = CudaDeviceCount();
+  if (n <= 0) {
+    LOG(ERROR) << "the nvl van needs a CUDA device and none is visible";
+    return nullptr;
+  }
+  int dev = -1;
+  if (const char* v = Environment::Get()->find("PS_CUDA_DEVICE")) {
+    dev = atoi(v);
+  } else if (const char* lr = Environment::Get()->find("LOCAL_RANK")) {
+    dev = atoi(lr) % n;
+  } else {
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+  }
+  CHECK(dev >= 0 && dev < n) << "CUDA device " << dev << " out of range (" << n << " visible)";
+  return new CudaDomain(dev);
+}
+
+}  // namespace ps

@@ -1,0 +1,340 @@
+/**
+ * \file mem_domain.h
+ * \brief Peer-mappable memory: the abstraction the one-sided van is written against.
+ *
+ * A MemDomain is "a kind of memory that another endpoint can map and write":
+ *   - CudaDomain (cuda_domain.h): B200 HBM, exported with CUDA IPC handles and
+ *     written by sm_100a copy kernels over NVLink peer mappings;
+ *   - ShmDomain (here): POSIX shared memory written by memcpy — the GPU-less
+ *     twin used by CPU-only CI and by same-host CPU workers (the role the
+ *     reference's IPCTransport plays, src/rdma_transport.h:469-633).
+ * It replaces the reference's ibverbs machinery: RegionDesc stands in for
+ * (ibv_mr, rkey), Import for the rendezvous address exchange, CopyAsync for
+ * RDMA WRITE, and the Ticket for the completion-queue entry
+ * (src/rdma_utils.h:75-140, src/rdma_transport.h:211-231).
+ *
+ * Also here: ArenaAllocator (offset first-fit with coalescing; the reference's
+ * MemoryAllocator, src/rdma_utils.h:75-140) and IndexPool (dense index <->
+ * pointer table; the reference's AddressPool, src/van_common.h:72-122).
+ */
+#ifndef PS_VAN_MEM_DOMAIN_H_
+#define PS_VAN_MEM_DOMAIN_H_
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "ps/internal/utils.h"
+#include "ps/sarray.h"
+
+namespace ps {
+
+/*! \brief round `v` up / down to a multiple of `a` (a power of two) */
+inline uint64_t AlignUp(uint64_t v, uint64_t a) { return (v + a - 1) & ~(a - 1); }
+inline uint64_t AlignDown(uint64_t v, uint64_t a) { return v & ~(a - 1); }
+
+/*! \brief everything a peer needs to map one exported allocation */
+struct RegionDesc {
+  int32_t region = -1;     // id, unique within the exporting node
+  int32_t owner = -1;      // exporting node id
+  int32_t pid = 0;         // exporting process
+  int32_t dev = -1;        // CUDA ordinal, -1 for host memory
+  uint64_t base = 0;       // virtual address in the exporter
+  uint64_t size = 0;
+  char handle[64] = {0};   // cudaIpcMemHandle_t, or a shm object name
+  char host[64] = {0};     // exporter hostname (same-process detection)
+
+  std::string Serialize() const { return std::string(reinterpret_cast<const char*>(this), sizeof(*this)); }
+  static bool Parse(const std::string& s, size_t at, RegionDesc* out) {
+    if (s.size() < at + sizeof(RegionDesc)) return false;
+    memcpy(out, s.data() + at, sizeof(RegionDesc));
+    return true;
+  }
+};
+
+/*! \brief completion token of an asynchronous copy */
+struct Ticket {
+  void* event = nullptr;  // domain-specific; nullptr = already complete
+};
+
+/*! \brief optional transform applied by the copy engine while it moves the bytes */
+enum WireCodec : int {
+  kCodecRaw = 0,           // byte copy
+  kCodecF32ToBf16 = 1,     // dst_bf16[i] = src_f32[i] * scale
+  kCodecBf16Scale = 2,     // dst_bf16[i] = src_bf16[i] * scale
+  kCodecF32ToFp8Block = 3, // block-scaled e4m3: 32 elements share one e8m0 exponent
+  kCodecBf16ToFp8Block = 4,
+  kCodecPlaced = 5,        // payload already written by the application; send descriptor only
+  kCodecNumCodecs
+};
+
+/*! \brief bytes the wire form of `n_src_bytes` of source occupies */
+inline uint64_t WireBytes(int codec, uint64_t n_src_bytes) {
+  switch (codec) {
+    case kCodecF32ToBf16: return n_src_bytes / 2;
+    case kCodecBf16Scale: return n_src_bytes;
+    case kCodecF32ToFp8Block: {  // n elements -> n bytes of e4m3 + n/32 scale bytes
+      const uint64_t n = n_src_bytes / 4;
+      return AlignUp(n, 32) + AlignUp(n, 32) / 32;
+    }
+    case kCodecBf16ToFp8Block: {
+      const uint64_t n = n_src_bytes / 2;
+      return AlignUp(n, 32) + AlignUp(n, 32) / 32;
+    }
+    default: return n_src_bytes;
+  }
+}
+
+class MemDomain {
+ public:
+  virtual ~MemDomain() {}
+  virtual const char* name() const = 0;
+  /*! \brief true if values tagged (type, ptr) should travel one-sided through this domain */
+  virtual bool Handles(int device_type, const void* ptr) = 0;
+  /*! \brief CUDA ordinal this domain is bound to, -1 for host domains */
+  virtual int device() const { return -1; }
+  /*! \brief allocate exportable memory (landing slots) */
+  virtual void* Alloc(size_t bytes) = 0;
+  virtual void Free(void* p) = 0;
+  /*! \brief describe the exportable allocation that contains `p` (region id left unset) */
+  virtual bool Export(const void* p, RegionDesc* out) = 0;
+  /*! \brief map a peer's region; returns the local address of its base */
+  virtual void* Import(const RegionDesc& d) = 0;
+  /*!
+   * \brief enqueue dst <- codec(src, n_src_bytes). `dst` may be a peer mapping.
+   *        `wait_event` (domain specific, may be null) gates the copy on the
+   *        producer of `src`.
+   */
+  virtual Ticket CopyAsync(void* dst, const void* src, size_t n_src_bytes, int codec, float scale,
+                           void* wait_event) = 0;
+  /*! \brief block until the copy behind `t` is globally visible; recycles the ticket */
+  virtual void Wait(Ticket t) = 0;
+  /*! \brief stream-like handle applications may enqueue their own work on (may be null) */
+  virtual void* Stream() { return nullptr; }
+};
+
+/*! \brief first-fit offset allocator with coalescing; thread-safe */
+class ArenaAllocator {
+ public:
+  ArenaAllocator() {}
+  ArenaAllocator(uint64_t size, uint64_t align) { Reset(size, align); }
+  void Reset(uint64_t size, uint64_t align) {
+    std::lock_guard<std::mutex> lk(mu_);
+    size_ = size;
+    align_ = align;
+    free_.clear();
+    used_.clear();
+    free_[0] = size;
+  }
+  /*! \brief offset of a block of >= bytes, or UINT64_MAX */
+  uint64_t Alloc(uint64_t bytes) {
+    bytes = AlignUp(bytes ? bytes : 1, align_);
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto it = free_.begin(); it != free_.end(); ++it) {
+      if (it->second < bytes) continue;
+      const uint64_t off = it->first, len = it->second;
+      free_.erase(it);
+      if (len > bytes) free_[off + bytes] = len - bytes;
+      used_[off] = bytes;
+      return off;
+    }
+    return UINT64_MAX;
+  }
+  bool Free(uint64_t off) {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto u = used_.find(off);
+    if (u == used_.end()) return false;
+    uint64_t len = u->second;
+    used_.erase(u);
+    auto next = free_.lower_bound(off);
+    if (next != free_.end() && off + len == next->first) {
+      len += next->second;
+      next = free_.erase(next);
+    }
+    if (next != free_.begin()) {
+      auto prev = std::prev(next);
+      if (prev->first + prev->second == off) {
+        prev->second += len;
+        return true;
+      }
+    }
+    free_[off] = len;
+    return true;
+  }
+  uint64_t BytesInUse() {
+    std::lock_guard<std::mutex> lk(mu_);
+    uint64_t n = 0;
+    for (auto& kv : used_) n += kv.second;
+    return n;
+  }
+  uint64_t size() const { return size_; }
+
+ private:
+  std::mutex mu_;
+  uint64_t size_ = 0, align_ = 256;
+  std::map<uint64_t, uint64_t> free_;  // offset -> length
+  std::map<uint64_t, uint64_t> used_;
+};
+
+/*! \brief dense index <-> pointer table (32-bit immediates for descriptors) */
+template <typename T>
+class IndexPool {
+ public:
+  explicit IndexPool(size_t capacity = 0) {
+    if (capacity == 0) capacity = static_cast<size_t>(GetEnv("BYTEPS_ADDRESS_POOL_SIZE", 10240));
+    table_.assign(capacity, nullptr);
+  }
+  /*! \brief store `p`, return its index (grows when full) */
+  uint32_t Store(T* p) {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (size_t probe = 0; probe < table_.size(); ++probe) {
+      size_t i = (cursor_ + probe) % table_.size();
+      if (table_[i] == nullptr) {
+        table_[i] = p;
+        cursor_ = i + 1;
+        return static_cast<uint32_t>(i);
+      }
+    }
+    table_.push_back(p);
+    cursor_ = table_.size();
+    return static_cast<uint32_t>(table_.size() - 1);
+  }
+  T* Get(uint32_t i) {
+    std::lock_guard<std::mutex> lk(mu_);
+    return i < table_.size() ? table_[i] : nullptr;
+  }
+  T* Release(uint32_t i) {
+    std::lock_guard<std::mutex> lk(mu_);
+    if (i >= table_.size()) return nullptr;
+    T* p = table_[i];
+    table_[i] = nullptr;
+    return p;
+  }
+
+ private:
+  std::mutex mu_;
+  size_t cursor_ = 0;
+  std::vector<T*> table_;
+};
+
+/*!
+ * \brief host shared memory domain. Memory comes from named POSIX shm arenas
+ *        (PS_SHM_ARENA_MB each, default 256) so a peer process can map it.
+ */
+class ShmDomain : public MemDomain {
+ public:
+  ShmDomain() { arena_bytes_ = static_cast<uint64_t>(GetEnv("PS_SHM_ARENA_MB", 256)) << 20; }
+  ~ShmDomain() override {
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto& a : arenas_) {
+      munmap(a->base, a->size);
+      shm_unlink(a->name.c_str());
+    }
+    for (auto& m : imported_) munmap(m.second.first, m.second.second);
+  }
+  const char* name() const override { return "shm"; }
+
+  bool Handles(int /*device_type*/, const void* ptr) override { return FindArena(ptr) != nullptr; }
+
+  void* Alloc(size_t bytes) override {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      for (auto& a : arenas_) {
+        uint64_t off = a->alloc.Alloc(bytes);
+        if (off != UINT64_MAX) return a->base + off;
+      }
+    }
+    Arena* a = NewArena(std::max<uint64_t>(arena_bytes_, AlignUp(bytes, 4096)));
+    uint64_t off = a->alloc.Alloc(bytes);
+    CHECK_NE(off, UINT64_MAX);
+    return a->base + off;
+  }
+  void Free(void* p) override {
+    Arena* a = FindArena(p);
+    if (a) a->alloc.Free(static_cast<uint64_t>(static_cast<char*>(p) - a->base));
+  }
+  bool Export(const void* p, RegionDesc* out) override {
+    Arena* a = FindArena(p);
+    if (!a) return false;
+    out->pid = static_cast<int32_t>(getpid());
+    out->dev = -1;
+    out->base = reinterpret_cast<uint64_t>(a->base);
+    out->size = a->size;
+    memset(out->handle, 0, sizeof(out->handle));
+    strncpy(out->handle, a->name.c_str(), sizeof(out->handle) - 1);
+    return true;
+  }
+  void* Import(const RegionDesc& d) override {
+    if (d.pid == static_cast<int32_t>(getpid())) return reinterpret_cast<void*>(d.base);
+    std::lock_guard<std::mutex> lk(mu_);
+    std::string key(d.handle);
+    auto it = imported_.find(key);
+    if (it != imported_.end()) return it->second.first;
+    int fd = shm_open(d.handle, O_RDWR, 0600);
+    CHECK_GE(fd, 0) << "shm_open(" << d.handle << "): " << strerror(errno);
+    void* base = mmap(nullptr, d.size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    CHECK(base != MAP_FAILED) << strerror(errno);
+    imported_[key] = std::make_pair(base, static_cast<size_t>(d.size));
+    return base;
+  }
+  Ticket CopyAsync(void* dst, const void* src, size_t n, int codec, float /*scale*/,
+                   void* /*wait_event*/) override {
+    CHECK_EQ(codec, (int)kCodecRaw) << "the shm domain moves raw bytes only";
+    if (n && dst != src) memcpy(dst, src, n);
+    // make the payload visible before the descriptor that announces it
+    std::atomic_thread_fence(std::memory_order_release);
+    return Ticket();
+  }
+  void Wait(Ticket) override {}
+
+ private:
+  struct Arena {
+    std::string name;
+    char* base = nullptr;
+    uint64_t size = 0;
+    ArenaAllocator alloc;
+  };
+  Arena* NewArena(uint64_t bytes) {
+    static std::atomic<int> counter{0};
+    std::unique_ptr<Arena> a(new Arena());
+    a->name = "/pslite_b200_" + std::to_string(getpid()) + "_" + std::to_string(counter++);
+    a->size = AlignUp(bytes, 4096);
+    shm_unlink(a->name.c_str());
+    int fd = shm_open(a->name.c_str(), O_CREAT | O_RDWR | O_EXCL, 0600);
+    CHECK_GE(fd, 0) << "shm_open(" << a->name << "): " << strerror(errno);
+    CHECK_EQ(ftruncate(fd, static_cast<off_t>(a->size)), 0) << strerror(errno);
+    void* base = mmap(nullptr, a->size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    CHECK(base != MAP_FAILED) << strerror(errno);
+    a->base = static_cast<char*>(base);
+    a->alloc.Reset(a->size, 256);
+    std::lock_guard<std::mutex> lk(mu_);
+    arenas_.push_back(std::move(a));
+    return arenas_.back().get();
+  }
+  Arena* FindArena(const void* p) {
+    std::lock_guard<std::mutex> lk(mu_);
+    const char* c = static_cast<const char*>(p);
+    for (auto& a : arenas_) {
+      if (c >= a->base && c < a->base + a->size) return a.get();
+    }
+    return nullptr;
+  }
+  std::mutex mu_;
+  uint64_t arena_bytes_;
+  std::vector<std::unique_ptr<Arena>> arenas_;
+  std::map<std::string, std::pair<void*, size_t>> imported_;
+};
+
+}  // namespace ps
+#endif  // PS_VAN_MEM_DOMAIN_H_

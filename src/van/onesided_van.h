@@ -1,0 +1,500 @@
+/**
+ * \file onesided_van.h
+ * \brief OneSidedVan: push / pull payloads are *written into the receiver's
+ *        memory by the sender*; only a small descriptor travels over TCP.
+ *
+ * This is the B200 counterpart of the reference's RDMA-class vans (RDMAVan
+ * src/rdma_van.h:26-950 + RDMATransport src/rdma_transport.h:198-467, and the
+ * CUDA-aware UCXVan src/ucx_van.h:874-1339): same protocol shape, different
+ * fabric. Mapping:
+ *   ibv_reg_mr / rkey            -> MemDomain::Export -> RegionDesc (CUDA IPC / shm)
+ *   rendezvous start / reply     -> ADDR_REQUEST / ADDR_RESOLVED control messages,
+ *                                   result cached per (peer, key)   [push landing slot]
+ *   RDMA WRITE of the payload    -> MemDomain::CopyAsync: an sm_100a kernel storing
+ *                                   straight into peer HBM over NVLink, optionally
+ *                                   fused with scale / bf16 cast / fp8 block quant
+ *   WRITE_WITH_IMM of the meta   -> the descriptor (Meta with MemRef) sent on the
+ *                                   TCP control channel *after* the copy's ticket
+ *                                   completes, by the completion thread
+ *   zero-copy pull               -> the pull request carries the MemRef of the
+ *                                   worker's destination tensor; the server's copy
+ *                                   kernel writes the values there
+ *   registered recv buffers      -> RegisterRecvBuffer'd SArrays become the landing
+ *                                   slots (pointer identity preserved)
+ *   IPCTransport (same host)     -> same-process peers skip IPC and use raw pointers
+ * The TCP side (connection setup, control plane, CPU payloads) is inherited
+ * from TcpVan. The memory backend is a MemDomain: CudaDomain ("nvl") or
+ * ShmDomain ("shm", the GPU-less twin that keeps this protocol testable on CPU).
+ */
+#ifndef PS_VAN_ONESIDED_VAN_H_
+#define PS_VAN_ONESIDED_VAN_H_
+#include <condition_variable>
+#include <deque>
+#include <atomic>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <set>
+#include <string>
+#include <thread>
+#include <utility>
+#include <vector>
+
+#include "van/mem_domain.h"
+#include "van/tcp_van.h"
+
+namespace ps {
+
+class OneSidedVan : public TcpVan {
+ public:
+  OneSidedVan(Postoffice* postoffice, MemDomain* domain, const std::string& type_name)
+      : TcpVan(postoffice), domain_(domain), type_(type_name) {}
+  ~OneSidedVan() override { StopCompleter(); }
+
+  std::string GetType() const override { return type_; }
+
+  void Start(int customer_id, bool standalone) override {
+    {
+      std::lock_guard<std::mutex> lk(cq_mu_);
+      if (!completer_) {
+        cq_stop_ = false;
+        completer_.reset(new std::thread(&OneSidedVan::CompletionLoop, this));
+      }
+    }
+    TcpVan::Start(customer_id, standalone);
+  }
+
+  void Stop() override {
+    StopCompleter();
+    TcpVan::Stop();
+    std::lock_guard<std::mutex> lk(rv_mu_);
+    push_slots_.clear();
+    landing_.clear();
+    peer_regions_.clear();
+    announced_.clear();
+  }
+
+  void SetNode(const Node& node) override {
+    Node n = node;
+    n.dev_id = domain_->device();
+    Van::SetNode(n);
+  }
+
+  void RegisterRecvBuffer(Message& msg) override {
+    CHECK_GE(msg.data.size(), (size_t)2);
+    if (!domain_->Handles(msg.data[1].src_device_type_, msg.data[1].data())) {
+      TcpVan::RegisterRecvBuffer(msg);  // plain host buffer: two-sided path
+      return;
+    }
+    std::lock_guard<std::mutex> lk(rv_mu_);
+    registered_slots_[std::make_pair(msg.meta.sender, msg.meta.key)] = msg.data[1];
+  }
+
+  void PinMemory(void* addr, size_t /*length*/, bool /*gpu*/, int /*dev*/ = 0) override {
+    RegionDesc d;
+    if (domain_->Export(addr, &d)) RegionIdFor(&d);
+  }
+
+  void* AllocExportable(size_t bytes) override { return domain_->Alloc(bytes); }
+  void FreeExportable(void* p) override { domain_->Free(p); }
+  void* DataStream() override { return domain_->Stream(); }
+  MemDomain* domain() { return domain_.get(); }
+
+  /*! \brief local address of `mem` inside a region node `peer` announced, or null */
+  void* ResolvePeerMem(int peer, const MemRef& mem) override {
+    std::lock_guard<std::mutex> lk(rv_mu_);
+    auto it = peer_regions_.find(std::make_pair(peer, mem.region));
+    return it == peer_regions_.end() ? nullptr : it->second + mem.offset;
+  }
+
+  /*! \brief one-sided transfers issued / bytes moved (for tests and benchmarks) */
+  uint64_t num_onesided_copies() const { return copies_.load(); }
+  uint64_t onesided_bytes() const { return copy_bytes_.load(); }
+
+ protected:
+  int SendMsg(Message& msg) override {
+    if (!msg.meta.control.empty() || msg.meta.simple_app) return TcpVan::SendMsg(msg);
+    const bool has_vals = msg.data.size() >= 2 && msg.data[1].size() > 0;
+    if (msg.meta.request && msg.meta.push && has_vals &&
+        domain_->Handles(msg.data[1].src_device_type_, msg.data[1].data())) {
+      return SendPush(msg);
+    }
+    if (msg.meta.request && !msg.meta.push && msg.meta.addr != 0 &&
+        domain_->Handles(msg.meta.src_dev_type, reinterpret_cast<void*>(msg.meta.addr))) {
+      AttachPullDestination(&msg);
+      return Ordered(msg, Ticket());
+    }
+    if (!msg.meta.request && !msg.meta.push && msg.meta.mem.valid() && has_vals) {
+      if (msg.meta.codec == kCodecPlaced) return SendPlacedResponse(msg);
+      return SendPullResponse(msg);
+    }
+    // nothing was placed one-sidedly: do not let the receiver rebuild a payload
+    if (!msg.meta.request) msg.meta.mem = MemRef();
+    return Ordered(msg, Ticket());
+  }
+
+  int RecvMsg(Message* msg) override {
+    for (;;) {
+      const int n = TcpVan::RecvMsg(msg);
+      if (n < 0) return n;
+      const auto cmd = msg->meta.control.cmd;
+      if (cmd == Control::ADDR_REQUEST) {
+        OnSlotRequest(*msg);
+        continue;
+      }
+      if (cmd == Control::ADDR_RESOLVED) {
+        OnRegionMessage(*msg);
+        continue;
+      }
+      if (msg->meta.control.empty() && !msg->meta.simple_app && msg->meta.mem.valid()) {
+        RebuildPayload(msg);
+      }
+      return n;
+    }
+  }
+
+ private:
+  struct Slot {
+    char* ptr = nullptr;      // address usable by this process (local or peer-mapped)
+    uint64_t capacity = 0;
+    int32_t region = -1;      // id in the owner's table
+    uint64_t offset = 0;
+  };
+  using PeerKey = std::pair<int, uint64_t>;
+
+  static size_t DataTypeSize(DataType t) {
+    switch (t) {
+      case INT16: case UINT16: return 2;
+      case INT32: case UINT32: case FLOAT: return 4;
+      case INT64: case UINT64: case DOUBLE: return 8;
+      default: return 1;
+    }
+  }
+
+  // -- region bookkeeping -----------------------------------------------------
+
+  /*! \brief id of the exported region with d->base (assigned on first sight); fills d */
+  int32_t RegionIdFor(RegionDesc* d) {
+    std::lock_guard<std::mutex> lk(rv_mu_);
+    auto it = region_of_base_.find(d->base);
+    if (it == region_of_base_.end()) {
+      const int32_t id = static_cast<int32_t>(my_regions_.size());
+      d->region = id;
+      d->owner = my_node_.id;
+      strncpy(d->host, my_node_.hostname.c_str(), sizeof(d->host) - 1);
+      my_regions_.push_back(*d);
+      region_of_base_[d->base] = id;
+      return id;
+    }
+    *d = my_regions_[it->second];
+    d->owner = my_node_.id;
+    return it->second;
+  }
+
+  char* ImportPeerRegion(int peer, const RegionDesc& d) {
+    {
+      std::lock_guard<std::mutex> lk(rv_mu_);
+      auto it = peer_regions_.find(std::make_pair(peer, d.region));
+      if (it != peer_regions_.end()) return it->second;
+    }
+    char* base = static_cast<char*>(domain_->Import(d));
+    std::lock_guard<std::mutex> lk(rv_mu_);
+    peer_regions_[std::make_pair(peer, d.region)] = base;
+    return base;
+  }
+
+  // -- push: sender side -------------------------------------------------------
+
+  int SendPush(Message& msg) {
+    const int recver = msg.meta.recver;
+    const SArray<char>& vals = msg.data[1];
+    const uint64_t wire = WireBytes(msg.meta.codec, vals.size());
+    Slot slot = AcquirePushSlot(recver, msg.meta.key, wire);
+    Ticket t = domain_->CopyAsync(slot.ptr, vals.data(), vals.size(), msg.meta.codec,
+                                  msg.meta.scale, msg.wait_event);
+    ++copies_;
+    copy_bytes_ += wire;
+    Message desc;
+    desc.meta = msg.meta;
+    desc.meta.mem.region = slot.region;
+    desc.meta.mem.offset = slot.offset;
+    desc.meta.mem.bytes = wire;
+    desc.data = msg.data;
+    desc.data[1] = vals.segment(0, 0);  // payload already placed; keep the segment slot
+    desc.meta.data_size = msg.meta.data_size - static_cast<int64_t>(vals.size());
+    // keep the source alive until the copy has completed
+    return Ordered(desc, t, vals) + static_cast<int>(std::min<uint64_t>(wire, 0x3fffffff));
+  }
+
+  /*! \brief landing slot at `recver` for `key`; rendezvous on first use or growth */
+  Slot AcquirePushSlot(int recver, uint64_t key, uint64_t bytes) {
+    std::unique_lock<std::mutex> lk(rv_mu_);
+    const PeerKey pk(recver, key);
+    auto it = push_slots_.find(pk);
+    if (it != push_slots_.end() && it->second.capacity >= bytes) return it->second;
+    push_slots_.erase(pk);
+    lk.unlock();
+    Message req;
+    req.meta.recver = recver;
+    req.meta.request = true;
+    req.meta.control.cmd = Control::ADDR_REQUEST;
+    req.meta.key = key;
+    req.meta.val_len = static_cast<int64_t>(bytes);
+    req.meta.timestamp = GetTimestamp();
+    CHECK_GT(TcpVan::SendMsg(req), 0);
+    lk.lock();
+    rv_cv_.wait(lk, [&] { return push_slots_.count(pk) > 0; });
+    return push_slots_[pk];
+  }
+
+  // -- push: receiver side -----------------------------------------------------
+
+  void OnSlotRequest(const Message& req) {
+    const int sender = req.meta.sender;
+    const uint64_t key = req.meta.key;
+    const uint64_t bytes = static_cast<uint64_t>(req.meta.val_len);
+    const PeerKey pk(sender, key);
+    char* ptr = nullptr;
+    uint64_t cap = 0;
+    {
+      std::lock_guard<std::mutex> lk(rv_mu_);
+      auto reg = registered_slots_.find(pk);
+      auto have = landing_.find(pk);
+      if (reg != registered_slots_.end()) {
+        CHECK_GE(reg->second.size(), bytes) << "registered buffer smaller than the push";
+        ptr = reg->second.data();
+        cap = reg->second.size();
+      } else if (have != landing_.end() && have->second.second >= bytes) {
+        ptr = have->second.first;
+        cap = have->second.second;
+      }
+    }
+    if (!ptr) {
+      cap = AlignUp(bytes, 256);
+      ptr = static_cast<char*>(domain_->Alloc(cap));
+      CHECK(ptr) << "out of " << domain_->name() << " memory for a " << cap << " B landing slot";
+    }
+    RegionDesc d;
+    CHECK(domain_->Export(ptr, &d)) << "landing slot is not exportable";
+    RegionIdFor(&d);
+    {
+      std::lock_guard<std::mutex> lk(rv_mu_);
+      landing_[pk] = std::make_pair(ptr, cap);
+    }
+    Message rep;
+    rep.meta.recver = sender;
+    rep.meta.request = false;
+    rep.meta.control.cmd = Control::ADDR_RESOLVED;
+    rep.meta.head = kReplySlot;
+    rep.meta.key = key;
+    rep.meta.val_len = static_cast<int64_t>(cap);
+    rep.meta.addr = reinterpret_cast<uint64_t>(ptr) - d.base;  // offset inside the region
+    rep.meta.body = d.Serialize();
+    rep.meta.timestamp = GetTimestamp();
+    CHECK_GT(TcpVan::SendMsg(rep), 0);
+  }
+
+  /*! \brief ADDR_RESOLVED: either a slot reply or a region announcement */
+  void OnRegionMessage(const Message& m) {
+    RegionDesc d;
+    CHECK(RegionDesc::Parse(m.meta.body, 0, &d)) << "malformed region descriptor";
+    char* base = ImportPeerRegion(m.meta.sender, d);
+    if (m.meta.head == kReplySlot) {
+      Slot s;
+      s.ptr = base + m.meta.addr;
+      s.capacity = static_cast<uint64_t>(m.meta.val_len);
+      s.region = d.region;
+      s.offset = m.meta.addr;
+      {
+        std::lock_guard<std::mutex> lk(rv_mu_);
+        push_slots_[PeerKey(m.meta.sender, m.meta.key)] = s;
+      }
+      rv_cv_.notify_all();
+    }
+  }
+
+  // -- pull ----------------------------------------------------------------------
+
+  /*! \brief name the pull destination so the server can write into it */
+  void AttachPullDestination(Message* msg) {
+    RegionDesc d;
+    if (!domain_->Export(reinterpret_cast<void*>(msg->meta.addr), &d)) return;  // two-sided
+    const int32_t id = RegionIdFor(&d);
+    bool need_announce = false;
+    {
+      std::lock_guard<std::mutex> lk(rv_mu_);
+      need_announce = announced_.insert(std::make_pair(msg->meta.recver, id)).second;
+    }
+    if (need_announce) {
+      Message ann;
+      ann.meta.recver = msg->meta.recver;
+      ann.meta.request = true;
+      ann.meta.control.cmd = Control::ADDR_RESOLVED;
+      ann.meta.head = kAnnounceRegion;
+      ann.meta.body = d.Serialize();
+      ann.meta.timestamp = GetTimestamp();
+      CHECK_GT(TcpVan::SendMsg(ann), 0);
+    }
+    const size_t esz = msg->meta.data_type.size() > 1 ? DataTypeSize(msg->meta.data_type[1]) : 1;
+    msg->meta.mem.region = id;
+    msg->meta.mem.offset = msg->meta.addr - d.base;
+    msg->meta.mem.bytes = static_cast<uint64_t>(msg->meta.val_len) * esz;
+  }
+
+  int SendPullResponse(Message& msg) {
+    const int recver = msg.meta.recver;
+    char* base = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(rv_mu_);
+      auto it = peer_regions_.find(std::make_pair(recver, msg.meta.mem.region));
+      CHECK(it != peer_regions_.end()) << "pull destination region " << msg.meta.mem.region
+                                       << " of node " << recver << " was never announced";
+      base = it->second;
+    }
+    const SArray<char>& vals = msg.data[1];
+    const uint64_t wire = WireBytes(msg.meta.codec, vals.size());
+    if (msg.meta.mem.bytes) {
+      CHECK_LE(wire, msg.meta.mem.bytes) << "pull response larger than the destination";
+    }
+    Ticket t = domain_->CopyAsync(base + msg.meta.mem.offset, vals.data(), vals.size(),
+                                  msg.meta.codec, msg.meta.scale, msg.wait_event);
+    ++copies_;
+    copy_bytes_ += wire;
+    Message desc;
+    desc.meta = msg.meta;
+    desc.meta.mem.bytes = wire;
+    desc.data = msg.data;
+    desc.data[1] = vals.segment(0, 0);
+    desc.meta.data_size = msg.meta.data_size - static_cast<int64_t>(vals.size());
+    return Ordered(desc, t, vals) + static_cast<int>(std::min<uint64_t>(wire, 0x3fffffff));
+  }
+
+  /*!
+   * \brief the application already wrote the values into the destination (e.g. the
+   *        fused update kernel stores the new parameters straight into every
+   *        worker's buffer); only gate the descriptor on `wait_event`.
+   */
+  int SendPlacedResponse(Message& msg) {
+    Ticket t = domain_->CopyAsync(nullptr, nullptr, 0, kCodecRaw, 1.f, msg.wait_event);
+    Message desc;
+    desc.meta = msg.meta;
+    desc.meta.codec = kCodecRaw;
+    desc.meta.mem.bytes = msg.data[1].size();
+    desc.data = msg.data;
+    desc.data[1] = msg.data[1].segment(0, 0);
+    desc.meta.data_size = msg.meta.data_size - static_cast<int64_t>(msg.data[1].size());
+    return Ordered(desc, t);
+  }
+
+  // -- receive-side payload reconstruction -----------------------------------------
+
+  void RebuildPayload(Message* msg) {
+    const MemRef& mem = msg->meta.mem;
+    char* ptr = nullptr;
+    if (msg->meta.request && msg->meta.push) {
+      std::lock_guard<std::mutex> lk(rv_mu_);
+      CHECK_LT(static_cast<size_t>(mem.region), my_regions_.size());
+      ptr = reinterpret_cast<char*>(my_regions_[mem.region].base + mem.offset);
+    } else if (!msg->meta.request && !msg->meta.push) {
+      ptr = reinterpret_cast<char*>(msg->meta.addr);
+    } else {
+      return;  // pull request: the MemRef is for the handler, there is no payload
+    }
+    if (msg->data.size() < 2) return;  // e.g. an empty ack that merely echoes the MemRef
+    const int dev = domain_->device();
+    SArray<char> vals;
+    vals.reset(ptr, mem.bytes, [](char*) {}, dev >= 0 ? GPU : CPU, dev >= 0 ? dev : 0,
+               dev >= 0 ? GPU : CPU, dev >= 0 ? dev : 0);
+    msg->data[1] = vals;
+    msg->meta.data_size += static_cast<int64_t>(mem.bytes);
+  }
+
+  // -- ordered, completion-gated descriptor sends -----------------------------------
+
+  struct Pending {
+    Message msg;
+    Ticket ticket;
+    SArray<char> keep_alive;
+  };
+
+  /*!
+   * \brief send `msg` after `t` completes, preserving the order of SendMsg calls.
+   *        With nothing in flight and no ticket the send happens inline.
+   */
+  int Ordered(Message& msg, Ticket t, const SArray<char>& keep_alive = SArray<char>()) {
+    {
+      std::lock_guard<std::mutex> lk(cq_mu_);
+      if (t.event != nullptr || !cq_.empty() || cq_busy_) {
+        Pending p;
+        p.msg = msg;
+        p.ticket = t;
+        p.keep_alive = keep_alive;
+        cq_.push_back(std::move(p));
+        cq_cv_.notify_one();
+        return 1 + static_cast<int>(msg.meta.data_size & 0x3fffffff);
+      }
+    }
+    return TcpVan::SendMsg(msg);
+  }
+
+  void CompletionLoop() {
+    std::unique_lock<std::mutex> lk(cq_mu_);
+    for (;;) {
+      cq_cv_.wait(lk, [this] { return cq_stop_ || !cq_.empty(); });
+      if (cq_.empty()) {
+        if (cq_stop_) return;
+        continue;
+      }
+      Pending p = std::move(cq_.front());
+      cq_.pop_front();
+      cq_busy_ = true;
+      lk.unlock();
+      domain_->Wait(p.ticket);  // payload is globally visible after this
+      if (TcpVan::SendMsg(p.msg) < 0) {
+        LOG(WARNING) << "failed to send descriptor: " << p.msg.DebugString();
+      }
+      p.keep_alive.clear();
+      lk.lock();
+      cq_busy_ = false;
+    }
+  }
+
+  void StopCompleter() {
+    std::unique_ptr<std::thread> t;
+    {
+      std::lock_guard<std::mutex> lk(cq_mu_);
+      cq_stop_ = true;
+      t.swap(completer_);
+    }
+    cq_cv_.notify_all();
+    if (t) t->join();
+  }
+
+  enum { kReplySlot = 1, kAnnounceRegion = 2 };
+
+  std::unique_ptr<MemDomain> domain_;
+  std::string type_;
+
+  std::mutex rv_mu_;
+  std::condition_variable rv_cv_;
+  std::map<PeerKey, Slot> push_slots_;                          // sender: where my pushes land
+  std::map<PeerKey, std::pair<char*, uint64_t>> landing_;       // receiver: slots I handed out
+  std::map<PeerKey, SArray<char>> registered_slots_;            // receiver: user-registered
+  std::vector<RegionDesc> my_regions_;                          // regions I exported, by id
+  std::map<uint64_t, int32_t> region_of_base_;
+  std::map<std::pair<int, int32_t>, char*> peer_regions_;       // (peer, region) -> mapping
+  std::set<std::pair<int, int32_t>> announced_;                 // (peer, my region) announced
+
+  std::mutex cq_mu_;
+  std::condition_variable cq_cv_;
+  std::deque<Pending> cq_;
+  bool cq_stop_ = false;
+  bool cq_busy_ = false;
+  std::unique_ptr<std::thread> completer_;
+
+  std::atomic<uint64_t> copies_{0};
+  std::atomic<uint64_t> copy_bytes_{0};
+};
+
+}  // namespace ps
+#endif  // PS_VAN_ONESIDED_VAN_H_

@@ -7,7 +7,11 @@
  */
 #include "van/van_factory.h"
 #include "ps/internal/postoffice.h"
+#include "van/onesided_van.h"
 #include "van/tcp_van.h"
+#ifdef PS_USE_CUDA
+#include "van/cuda_domain.h"
+#endif
 
 namespace ps {
 
@@ -15,6 +19,16 @@ Van* CreateVanByType(const std::string& type, Postoffice* postoffice) {
   LOG_IF(INFO, GetEnv("PS_VERBOSE", 0) >= 1) << "Creating Van: " << type;
   if (type == "zmq" || type == "0" || type == "tcp" || type.empty()) {
     return new TcpVan(postoffice);
+  }
+  if (type == "shm") return new OneSidedVan(postoffice, new ShmDomain(), "shm");
+  if (type == "nvl" || type == "1" || type == "ibverbs" || type == "ucx" || type == "fabric") {
+#ifdef PS_USE_CUDA
+    MemDomain* dom = CreateCudaDomain();
+    CHECK(dom) << "van type '" << type << "' maps to the NVLink van, which needs a GPU";
+    return new OneSidedVan(postoffice, dom, "nvl");
+#else
+    LOG(FATAL) << "van type '" << type << "' needs a build with PS_USE_CUDA";
+#endif
   }
   LOG(FATAL) << "unsupported van type: " << type;
   return nullptr;
