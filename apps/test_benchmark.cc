@@ -57,6 +57,7 @@ struct Options {
   bool skip_dev_check = false;
   bool debug = false;
   bool json = false;
+  bool exportable = false;
   int group_size = 1;
 };
 Options opt;
@@ -88,6 +89,12 @@ SArray<T> AllocArray(size_t count, bool on_gpu, int dst_dev, bool dst_gpu) {
 #else
     LOG(FATAL) << "GPU buffers need a build with USE_CUDA=1";
 #endif
+  } else if (opt.exportable && sizeof(T) == 1) {
+    // value buffers from the van's peer-mappable memory (shm arena on the shm van)
+    void* p = Postoffice::Get()->van()->AllocExportable(bytes);
+    CHECK(p);
+    memset(p, 1, bytes);
+    out.reset(static_cast<T*>(p), count, [](T*) {}, CPU, 0, dst_gpu ? GPU : CPU, dst_dev);
   } else {
     void* p = nullptr;
     const size_t page = static_cast<size_t>(sysconf(_SC_PAGESIZE));
@@ -309,6 +316,8 @@ int main(int argc, char* argv[]) {
   opt.skip_dev_check = EnvInt("SKIP_DEV_ID_CHECK", 0) != 0;
   opt.debug = Environment::Get()->find("DEBUG_MODE") != nullptr;
   opt.json = EnvInt("BENCH_JSON", 0) != 0;
+  opt.exportable = EnvInt("TEST_EXPORTABLE_VALS", 0) != 0 ||
+                   std::string(GetEnv("PS_VAN_TYPE", "")) == "shm";
   opt.group_size = std::max(1, EnvInt("DMLC_GROUP_SIZE", 1));
   LOG(INFO) << opt.num_ports << " ports per node; recv buffer registration is "
             << (opt.recv_buffer ? "enabled" : "NOT enabled") << "; gpu worker/server = "

@@ -1,0 +1,375 @@
+/**
+ * \file bindings.cc
+ * \brief Python / PyTorch binding of the native parameter-server runtime.
+ *
+ * The reference has no Python API (BytePS, its consumer, owns the torch plugin);
+ * this is new scope. The binding is deliberately thin: tensors are
+ * wrapped as zero-copy SArrays (placement taken from tensor.device, lifetime
+ * pinned by capturing the tensor in the SArray deleter), and every call maps 1:1
+ * onto the C++ API — KVWorker::ZPush/ZPull/Wait, KVServer handlers, GpuServer,
+ * Postoffice barriers. CUDA work is never synchronised here: a push takes an
+ * event recorded on the caller's current stream and hands it to the van's copy
+ * kernel (SendOpts::wait_event).
+ */
+#include <torch/extension.h>
+#include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAStream.h>
+
+#include <cuda_runtime.h>
+
+#include <mutex>
+#include <unordered_map>
+
+#include "kernels/ps_kernels.h"
+#include "ps/ps.h"
+#include "server/gpu_server.h"
+#include "van/mem_domain.h"
+
+namespace py = pybind11;
+using namespace ps;
+
+namespace {
+
+bool CudaUsable() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return n > 0;
+}
+
+/*! \brief zero-copy byte view of a contiguous tensor; the tensor lives as long as the view */
+SArray<char> ViewOf(const torch::Tensor& t) {
+  TORCH_CHECK(t.is_contiguous(), "pslite: tensors must be contiguous");
+  SArray<char> a;
+  torch::Tensor keep = t;
+  const bool gpu = t.is_cuda();
+  const int dev = gpu ? t.get_device() : 0;
+  a.reset(static_cast<char*>(t.data_ptr()), static_cast<size_t>(t.nbytes()),
+          [keep](char*) mutable { keep.reset(); }, gpu ? GPU : CPU, dev, gpu ? GPU : CPU, dev);
+  return a;
+}
+
+SArray<Key> OneKey(uint64_t k) {
+  SArray<Key> a(1);
+  a[0] = static_cast<Key>(k);
+  return a;
+}
+SArray<int> OneLen(size_t n) {
+  SArray<int> a(1);
+  a[0] = static_cast<int>(std::min<size_t>(n, 0x7fffffff));
+  return a;
+}
+
+/*! \brief cudaEvent recorded on the calling thread's current stream of `dev` */
+cudaEvent_t RecordOnCurrentStream(int dev) {
+  cudaEvent_t ev;
+  TORCH_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) == cudaSuccess);
+  cudaStream_t cur = at::cuda::getCurrentCUDAStream(dev).stream();
+  TORCH_CHECK(cudaEventRecord(ev, cur) == cudaSuccess);
+  return ev;
+}
+
+class PyKVWorker {
+ public:
+  PyKVWorker(int app_id, int customer_id, int instance_idx)
+      : kv_(new KVWorker<char>(app_id, customer_id, instance_idx)) {}
+
+  /*! \brief encode "the idx-th key owned by server `server`" like the benchmarks do */
+  uint64_t server_key(int server, uint64_t idx) {
+    const auto& ranges = Postoffice::GetWorker()->GetServerKeyRanges();
+    TORCH_CHECK(server >= 0 && server < static_cast<int>(ranges.size()), "bad server rank");
+    return ranges[server].begin() + idx;
+  }
+
+  int push(uint64_t key, const torch::Tensor& t, int cmd, int codec, float scale,
+           bool order_after_current_stream) {
+    SArray<char> vals = ViewOf(t);
+    SendOpts opts;
+    opts.codec = codec;
+    opts.scale = scale;
+    cudaEvent_t ev = nullptr;
+    if (t.is_cuda() && order_after_current_stream) {
+      ev = RecordOnCurrentStream(t.get_device());
+      opts.wait_event = ev;
+    }
+    py::gil_scoped_release nogil;
+    // the event must outlive the copy that waits on it: destroy it on completion
+    auto cb = ev ? KVWorker<char>::Callback([ev]() { cudaEventDestroy(ev); })
+                 : KVWorker<char>::Callback();
+    return kv_->ZPush(OneKey(key), vals, OneLen(vals.size()), cmd, cb, opts);
+  }
+
+  int pull(uint64_t key, torch::Tensor t, int cmd) {
+    // the destination view must stay alive until the response lands: own it here
+    auto* dst = new SArray<char>(ViewOf(t));
+    auto* len = new SArray<int>(OneLen(dst->size()));
+    py::gil_scoped_release nogil;
+    return kv_->ZPull(OneKey(key), dst, len, cmd, [dst, len]() {
+      delete dst;
+      delete len;
+    });
+  }
+
+  void wait(int ts) {
+    py::gil_scoped_release nogil;
+    kv_->Wait(ts);
+  }
+
+ private:
+  std::unique_ptr<KVWorker<char>> kv_;
+};
+
+/*! \brief a KVServer whose handler is a Python callable (tests, small CPU models) */
+class PyKVServer {
+ public:
+  explicit PyKVServer(int app_id) : kv_(new KVServer<char>(app_id)) {}
+  ~PyKVServer() {
+    py::gil_scoped_release nogil;
+    kv_.reset();
+  }
+
+  /*! \brief handler(meta: dict, key: int, vals: uint8 tensor view) -> None; must call response() */
+  void set_request_handle(py::function fn) {
+    handler_ = fn;
+    kv_->set_request_handle([this](const KVMeta& m, const KVPairs<char>& d, KVServer<char>*) {
+      py::gil_scoped_acquire gil;
+      const int id = next_id_++;
+      pending_[id] = m;
+      py::dict meta;
+      meta["id"] = id;
+      meta["push"] = m.push;
+      meta["cmd"] = m.cmd;
+      meta["sender"] = m.sender;
+      meta["sender_rank"] = Postoffice::IDtoRank(m.sender);
+      meta["timestamp"] = m.timestamp;
+      meta["key"] = static_cast<uint64_t>(d.keys.size() ? d.keys[0] : m.key);
+      meta["val_len"] = m.val_len;
+      meta["codec"] = m.codec;
+      meta["scale"] = m.scale;
+      py::object vals = py::none();
+      if (d.vals.size()) {
+        SArray<char> keep = d.vals;
+        auto opts = torch::TensorOptions().dtype(torch::kUInt8);
+        if (keep.on_gpu()) opts = opts.device(torch::kCUDA, keep.src_device_id_);
+        vals = py::cast(torch::from_blob(keep.data(), {static_cast<int64_t>(keep.size())},
+                                         [keep](void*) mutable { keep.clear(); }, opts));
+      }
+      handler_(meta, meta["key"], vals);
+    });
+  }
+
+  void response(int id, py::object vals) {
+    KVMeta m;
+    {
+      auto it = pending_.find(id);
+      TORCH_CHECK(it != pending_.end(), "unknown / already answered request id");
+      m = it->second;
+      pending_.erase(it);
+    }
+    KVPairs<char> res;
+    if (!vals.is_none()) {
+      torch::Tensor t = vals.cast<torch::Tensor>();
+      res.keys = OneKey(m.key);
+      res.vals = ViewOf(t);
+      res.lens = OneLen(res.vals.size());
+    }
+    py::gil_scoped_release nogil;
+    kv_->Response(m, res);
+  }
+
+ private:
+  std::unique_ptr<KVServer<char>> kv_;
+  py::function handler_;
+  std::unordered_map<int, KVMeta> pending_;  // guarded by the GIL
+  int next_id_ = 0;
+};
+
+class PyGpuServer {
+ public:
+  PyGpuServer(int app_id, int num_workers, const std::string& optimizer, float lr, float beta1,
+              float beta2, float eps, float weight_decay, float grad_scale, bool fuse_pull,
+              const std::string& raw_grad, int max_ctas) {
+    GpuServerConfig c;
+    c.num_workers = num_workers;
+    c.opt.optimizer = optimizer == "sgd" ? PS_OPT_SGD : PS_OPT_ADAMW;
+    c.opt.lr = lr;
+    c.opt.beta1 = beta1;
+    c.opt.beta2 = beta2;
+    c.opt.eps = eps;
+    c.opt.weight_decay = weight_decay;
+    c.opt.grad_scale = grad_scale;
+    c.fuse_pull = fuse_pull;
+    c.raw_grad_format = raw_grad == "f32" ? PS_GRAD_F32 : PS_GRAD_BF16;
+    c.max_ctas = max_ctas;
+    impl_.reset(new GpuServer(app_id, c));
+  }
+  ~PyGpuServer() {
+    py::gil_scoped_release nogil;
+    impl_.reset();
+  }
+  void set_lr(float lr) { impl_->SetLearningRate(lr); }
+  uint64_t num_updates() { return impl_->num_updates(); }
+  uint64_t num_fused_fanouts() { return impl_->num_fused_fanouts(); }
+  size_t num_keys() { return impl_->num_keys(); }
+  size_t state_bytes() { return impl_->state_bytes(); }
+  bool save(const std::string& path) {
+    py::gil_scoped_release nogil;
+    return impl_->SaveCheckpoint(path);
+  }
+  bool load(const std::string& path) {
+    py::gil_scoped_release nogil;
+    return impl_->LoadCheckpoint(path);
+  }
+  torch::Tensor read_master(uint64_t key) {
+    std::vector<float> host;
+    TORCH_CHECK(impl_->ReadMaster(static_cast<Key>(key), &host), "unknown key");
+    return torch::from_blob(host.data(), {static_cast<int64_t>(host.size())}, torch::kFloat32).clone();
+  }
+
+ private:
+  std::unique_ptr<GpuServer> impl_;
+};
+
+ps_stream_t CurrentStream(const torch::Tensor& t) {
+  return reinterpret_cast<ps_stream_t>(at::cuda::getCurrentCUDAStream(t.get_device()).stream());
+}
+
+void CheckRc(int rc, const char* what) {
+  TORCH_CHECK(rc == 0, what, " failed: ", cudaGetErrorString(static_cast<cudaError_t>(rc)));
+}
+
+}  // namespace
+
+PYBIND11_MODULE(_C, m) {
+  m.doc() = "pslite_b200 native runtime";
+  m.def("set_env", [](const std::string& k, const std::string& v) { Environment::Get()->set(k, v); });
+  m.def("cuda_usable", &CudaUsable);
+  m.def("start_ps", [](int customer_id, const std::string& role, int rank, bool do_barrier) {
+    py::gil_scoped_release nogil;
+    StartPS(customer_id, GetRole(role), rank, do_barrier);
+  }, py::arg("customer_id") = 0, py::arg("role"), py::arg("rank") = -1, py::arg("do_barrier") = true);
+  m.def("finalize", [](int customer_id, const std::string& role, bool do_barrier) {
+    py::gil_scoped_release nogil;
+    Finalize(customer_id, GetRole(role), do_barrier);
+  }, py::arg("customer_id") = 0, py::arg("role"), py::arg("do_barrier") = true);
+  m.def("reset", []() { Postoffice::Reset(); });
+  m.def("num_workers", []() { return NumWorkers(); });
+  m.def("num_servers", []() { return NumServers(); });
+  m.def("worker_rank", []() { return Postoffice::GetWorker()->my_rank(); });
+  m.def("server_rank", []() { return Postoffice::GetServer()->my_rank(); });
+  m.def("barrier", [](int customer_id, int group, const std::string& as_role) {
+    py::gil_scoped_release nogil;
+    Postoffice* po = as_role == "server" ? Postoffice::GetServer()
+                     : as_role == "scheduler" ? Postoffice::GetScheduler() : Postoffice::GetWorker();
+    po->Barrier(customer_id, group);
+  }, py::arg("customer_id") = 0, py::arg("group") = kWorkerGroup + kServerGroup,
+     py::arg("as_role") = "worker");
+  m.attr("SCHEDULER_GROUP") = kScheduler;
+  m.attr("SERVER_GROUP") = kServerGroup;
+  m.attr("WORKER_GROUP") = kWorkerGroup;
+  m.attr("CODEC_RAW") = static_cast<int>(kCodecRaw);
+  m.attr("CODEC_F32_TO_BF16") = static_cast<int>(kCodecF32ToBf16);
+  m.attr("CODEC_BF16_SCALE") = static_cast<int>(kCodecBf16Scale);
+  m.attr("CODEC_F32_TO_FP8BLOCK") = static_cast<int>(kCodecF32ToFp8Block);
+  m.attr("CODEC_BF16_TO_FP8BLOCK") = static_cast<int>(kCodecBf16ToFp8Block);
+  m.attr("CMD_GRAD") = static_cast<int>(kCmdGrad);
+  m.attr("CMD_INIT_BF16") = static_cast<int>(kCmdInitBf16);
+  m.attr("CMD_INIT_F32") = static_cast<int>(kCmdInitF32);
+  m.attr("GRAD_F32") = static_cast<int>(PS_GRAD_F32);
+  m.attr("GRAD_BF16") = static_cast<int>(PS_GRAD_BF16);
+  m.attr("GRAD_FP8BLOCK") = static_cast<int>(PS_GRAD_FP8BLOCK);
+
+  m.def("wire_bytes", [](int codec, uint64_t src_bytes) { return WireBytes(codec, src_bytes); });
+  m.def("kernel_launch_count", []() { return ps_kernel_launch_count(); });
+  m.def("van_bytes", []() {
+    Van* v = Postoffice::Get()->van();
+    return std::make_pair(v->send_bytes(), v->recv_bytes());
+  });
+
+  /*! \brief exportable memory of the worker van as a uint8 tensor (HBM on nvl, shm on shm) */
+  m.def("alloc_exportable", [](int64_t nbytes, const std::string& as_role) {
+    Postoffice* po = as_role == "server" ? Postoffice::GetServer() : Postoffice::GetWorker();
+    Van* van = po->van();
+    void* p = van->AllocExportable(static_cast<size_t>(nbytes));
+    TORCH_CHECK(p, "allocation failed");
+    auto opts = torch::TensorOptions().dtype(torch::kUInt8);
+    const int dev = van->my_node().dev_id;
+    if (van->GetType() == "nvl") opts = opts.device(torch::kCUDA, dev);
+    return torch::from_blob(p, {nbytes}, [van](void* q) { van->FreeExportable(q); }, opts);
+  }, py::arg("nbytes"), py::arg("as_role") = "worker");
+
+  py::class_<PyKVWorker>(m, "KVWorker")
+      .def(py::init<int, int, int>(), py::arg("app_id") = 0, py::arg("customer_id") = 0,
+           py::arg("instance_idx") = 0)
+      .def("server_key", &PyKVWorker::server_key)
+      .def("push", &PyKVWorker::push, py::arg("key"), py::arg("tensor"), py::arg("cmd") = 0,
+           py::arg("codec") = 0, py::arg("scale") = 1.0f,
+           py::arg("order_after_current_stream") = true)
+      .def("pull", &PyKVWorker::pull, py::arg("key"), py::arg("tensor"), py::arg("cmd") = 0)
+      .def("wait", &PyKVWorker::wait);
+
+  py::class_<PyKVServer>(m, "KVServer")
+      .def(py::init<int>(), py::arg("app_id") = 0)
+      .def("set_request_handle", &PyKVServer::set_request_handle)
+      .def("response", &PyKVServer::response, py::arg("id"), py::arg("vals") = py::none());
+
+  py::class_<PyGpuServer>(m, "GpuServer")
+      .def(py::init<int, int, const std::string&, float, float, float, float, float, float, bool,
+                    const std::string&, int>(),
+           py::arg("app_id") = 0, py::arg("num_workers") = 1, py::arg("optimizer") = "adamw",
+           py::arg("lr") = 1e-3f, py::arg("beta1") = 0.9f, py::arg("beta2") = 0.95f,
+           py::arg("eps") = 1e-8f, py::arg("weight_decay") = 0.0f, py::arg("grad_scale") = 1.0f,
+           py::arg("fuse_pull") = true, py::arg("raw_grad") = "bf16", py::arg("max_ctas") = 0)
+      .def("set_lr", &PyGpuServer::set_lr)
+      .def("num_updates", &PyGpuServer::num_updates)
+      .def("num_fused_fanouts", &PyGpuServer::num_fused_fanouts)
+      .def("num_keys", &PyGpuServer::num_keys)
+      .def("state_bytes", &PyGpuServer::state_bytes)
+      .def("save", &PyGpuServer::save)
+      .def("load", &PyGpuServer::load)
+      .def("read_master", &PyGpuServer::read_master);
+
+  // ---- raw kernel entry points (numerics tests, standalone use) ----
+  m.def("copy_codec", [](torch::Tensor dst, const torch::Tensor& src, int codec, float scale,
+                         int max_ctas) {
+    TORCH_CHECK(dst.is_cuda() && src.is_cuda(), "copy_codec needs CUDA tensors");
+    CheckRc(ps_launch_copy(dst.data_ptr(), src.data_ptr(), static_cast<size_t>(src.nbytes()), codec,
+                           scale, max_ctas, CurrentStream(src)), "ps_launch_copy");
+  }, py::arg("dst"), py::arg("src"), py::arg("codec") = 0, py::arg("scale") = 1.0f,
+     py::arg("max_ctas") = 0);
+  m.def("decode", [](torch::Tensor dst_f32, const torch::Tensor& wire, int64_t n, int fmt) {
+    CheckRc(ps_launch_decode(dst_f32.data_ptr(), wire.data_ptr(), static_cast<size_t>(n), fmt,
+                             CurrentStream(wire)), "ps_launch_decode");
+  });
+  m.def("fused_update", [](std::vector<torch::Tensor> grads, int grad_format, torch::Tensor master,
+                           torch::Tensor mom, torch::Tensor var, std::vector<torch::Tensor> outs,
+                           const std::string& optimizer, float lr, float beta1, float beta2,
+                           float eps, float wd, int step, float grad_scale, int max_ctas) {
+    ps_update_args a;
+    memset(&a, 0, sizeof(a));
+    a.n = static_cast<size_t>(master.numel());
+    a.num_grads = static_cast<int>(grads.size());
+    a.grad_format = grad_format;
+    TORCH_CHECK(a.num_grads <= PS_MAX_FANIN && outs.size() <= PS_MAX_FANOUT);
+    for (size_t i = 0; i < grads.size(); ++i) a.grads[i] = grads[i].data_ptr();
+    a.master = master.data_ptr<float>();
+    a.m = mom.data_ptr<float>();
+    a.v = var.data_ptr<float>();
+    a.num_outs = static_cast<int>(outs.size());
+    for (size_t i = 0; i < outs.size(); ++i) a.outs[i] = outs[i].data_ptr();
+    a.out_f32 = !outs.empty() && outs[0].scalar_type() == torch::kFloat32;
+    ps_opt_params o;
+    o.optimizer = optimizer == "sgd" ? PS_OPT_SGD : PS_OPT_ADAMW;
+    o.lr = lr; o.beta1 = beta1; o.beta2 = beta2; o.eps = eps; o.weight_decay = wd;
+    o.bias_corr1 = o.optimizer == PS_OPT_ADAMW ? 1.f - std::pow(beta1, (float)step) : 1.f;
+    o.bias_corr2 = o.optimizer == PS_OPT_ADAMW ? 1.f - std::pow(beta2, (float)step) : 1.f;
+    o.grad_scale = grad_scale;
+    CheckRc(ps_launch_update(&a, &o, max_ctas, CurrentStream(master)), "ps_launch_update");
+  }, py::arg("grads"), py::arg("grad_format"), py::arg("master"), py::arg("m"), py::arg("v"),
+     py::arg("outs"), py::arg("optimizer") = "adamw", py::arg("lr") = 1e-3f,
+     py::arg("beta1") = 0.9f, py::arg("beta2") = 0.95f, py::arg("eps") = 1e-8f,
+     py::arg("weight_decay") = 0.0f, py::arg("step") = 1, py::arg("grad_scale") = 1.0f,
+     py::arg("max_ctas") = 0);
+}

@@ -1,0 +1,109 @@
+"""Turn a torchrun job (one process per GPU) into a parameter-server cluster.
+
+torchrun gives RANK / LOCAL_RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT; ps-lite wants a
+scheduler plus DMLC_* roles (reference docs/env.md:5-15, tracker/dmlc_local.py:59-70).
+Rank 0 spawns the scheduler as a child process; every rank then starts its role(s):
+
+    topology "joint": every rank is worker r AND server r (co-located, the IPC-benchmark
+                      shape of the reference, tests/test_ipc_benchmark.cc) — all N GPUs compute.
+    topology "split": ranks [0, N/2) are workers, ranks [N/2, N) are servers
+                      (the 4w+4s shape named in BASELINE.json).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+from dataclasses import dataclass
+
+from ..utils.env import free_port
+
+
+@dataclass
+class PSContext:
+    rank: int
+    world: int
+    local_rank: int
+    topology: str
+    num_workers: int
+    num_servers: int
+    is_worker: bool
+    is_server: bool
+    worker_rank: int
+    server_rank: int
+    role: str
+    van: str
+    scheduler: subprocess.Popen | None = None
+
+    def shutdown(self):
+        from .. import native
+
+        native().finalize(0, self.role, True)
+        if self.scheduler is not None:
+            self.scheduler.wait(timeout=60)
+
+
+def _share_port(rank: int, world: int) -> int:
+    """Pick the scheduler port on rank 0 and tell everyone (torch.distributed if present)."""
+    if world == 1:
+        return free_port()
+    import torch.distributed as dist
+
+    assert dist.is_initialized(), "init torch.distributed before init_ps() when WORLD_SIZE > 1"
+    box = [free_port() if rank == 0 else None]
+    dist.broadcast_object_list(box, src=0)
+    return int(box[0])
+
+
+def init_ps(topology: str = "joint", van: str | None = None, extra_env: dict | None = None) -> PSContext:
+    """Start the PS runtime for this torchrun rank and return its context."""
+    from .. import native
+
+    C = native()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", str(rank)))
+    host = os.environ.get("MASTER_ADDR", "127.0.0.1")
+    if van is None:
+        van = "nvl" if C.cuda_usable() else "shm"
+    if topology == "split" and world < 2:
+        topology = "joint"
+    if topology == "joint":
+        nw = ns = world
+        is_worker = is_server = True
+        wrank = srank = rank
+        role = "joint"
+    elif topology == "split":
+        assert world % 2 == 0, "split topology needs an even number of ranks"
+        nw = ns = world // 2
+        is_worker = rank < nw
+        is_server = not is_worker
+        wrank = rank if is_worker else -1
+        srank = rank - nw if is_server else -1
+        role = "worker" if is_worker else "server"
+    else:
+        raise ValueError(f"unknown topology {topology}")
+
+    port = _share_port(rank, world)
+    env = {
+        "DMLC_NUM_WORKER": nw, "DMLC_NUM_SERVER": ns,
+        "DMLC_PS_ROOT_URI": host if host not in ("localhost",) else "127.0.0.1",
+        "DMLC_PS_ROOT_PORT": port, "DMLC_NODE_HOST": "127.0.0.1",
+        "PS_VAN_TYPE": van, "PS_CUDA_DEVICE": local_rank, "DMLC_ROLE": role,
+    }
+    if extra_env:
+        env.update(extra_env)
+    sched = None
+    if rank == 0:
+        child_env = dict(os.environ)
+        child_env.update({k: str(v) for k, v in env.items()})
+        child_env["DMLC_ROLE"] = "scheduler"
+        child_env["PS_VAN_TYPE"] = "zmq"  # the scheduler moves no payload
+        sched = subprocess.Popen([sys.executable, "-m", "pslite_b200.parallel.scheduler"],
+                                 env=child_env)
+    for k, v in env.items():
+        C.set_env(k, str(v))
+    preferred = wrank if is_worker else srank
+    C.start_ps(0, role, preferred, True)
+    return PSContext(rank, world, local_rank, topology, nw, ns, is_worker, is_server, wrank, srank,
+                     role, van, sched)

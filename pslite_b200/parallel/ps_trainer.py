@@ -1,0 +1,158 @@
+"""Synchronous data-parallel training through the parameter server.
+
+Worker side of the BytePS-style loop the reference is built for (docs/overview.md:60-69:
+"workers push gradients, pull weights") written for B200:
+
+* every parameter tensor is cut into chunks (`chunk_elems`, default 32 Mi elements) and
+  each chunk is a key; chunk j lives on server j % S (the test_benchmark key encoding);
+* gradients are pushed from `post_accumulate_grad` hooks *during backward*: the push is a
+  one-sided write into the server's HBM slot issued by an sm_100a kernel on the van's
+  stream, fused with the wire transform (block-scaled fp8 by default, or bf16), gated on
+  an event recorded on the autograd stream — backward never waits for communication;
+* the pull of the same key is issued right behind the push; the server answers it from
+  its fused update kernel, which stores the new bf16 parameters straight into
+  `param.data` of every worker over NVLink. `step()` only waits for those descriptors;
+* gradient tensors are handed to the transport and dropped (`p.grad = None`), so there is
+  no flat gradient buffer to zero and backward's peak memory shrinks as it proceeds.
+
+The optimizer state (fp32 master, Adam moments) lives only on the servers, sharded by key.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from .. import native
+
+
+@dataclass
+class _Chunk:
+    key: int
+    param_index: int
+    start: int
+    stop: int
+    server: int
+
+
+@dataclass
+class PSTrainerStats:
+    pushes: int = 0
+    pulls: int = 0
+    push_bytes_wire: int = 0
+    pull_bytes: int = 0
+    keys: int = 0
+
+
+class PSWorkerOptimizer:
+    """Drop-in "optimizer" for a worker: hooks gradients, exposes step()/zero_grad()."""
+
+    def __init__(self, params, kv, num_servers: int, num_workers: int, worker_rank: int,
+                 grad_wire: str = "fp8", chunk_elems: int = 32 << 20, app_barrier=None):
+        C = native()
+        self._C = C
+        self.kv = kv
+        self.S = num_servers
+        self.W = num_workers
+        self.rank = worker_rank
+        self.params = [p for p in params if p.requires_grad]
+        assert chunk_elems % 1024 == 0
+        self.chunk_elems = chunk_elems
+        self.grad_wire = grad_wire
+        self.stats = PSTrainerStats()
+        self._pending: list[int] = []
+        self._hooks = []
+        self._barrier = app_barrier
+        self.accumulate = False  # True on non-final micro-batches: keep grads local
+        # chunk table
+        self.chunks: list[list[_Chunk]] = []
+        j = 0
+        for i, p in enumerate(self.params):
+            assert p.is_contiguous(), "PS parameters must be contiguous"
+            per = []
+            n = p.numel()
+            for a in range(0, n, chunk_elems):
+                b = min(n, a + chunk_elems)
+                server = j % self.S
+                per.append(_Chunk(kv.server_key(server, j), i, a, b, server))
+                j += 1
+            self.chunks.append(per)
+        self.stats.keys = j
+
+    # -- wire format -------------------------------------------------------------
+    def _codec(self, t: torch.Tensor) -> int:
+        C = self._C
+        if self.grad_wire == "fp8":
+            return C.CODEC_F32_TO_FP8BLOCK if t.dtype == torch.float32 else C.CODEC_BF16_TO_FP8BLOCK
+        if t.dtype == torch.float32:
+            return C.CODEC_F32_TO_BF16
+        return C.CODEC_RAW  # bf16 gradients travel as they are
+
+    # -- one-time parameter initialisation ----------------------------------------
+    def init_parameters(self, barrier=None):
+        """Worker 0 seeds the servers with the initial values; everyone then pulls them."""
+        C = self._C
+        if self.rank == 0:
+            ts = []
+            for p, per in zip(self.params, self.chunks):
+                flat = p.data.view(-1)
+                cmd = C.CMD_INIT_F32 if p.dtype == torch.float32 else C.CMD_INIT_BF16
+                for c in per:
+                    ts.append(self.kv.push(c.key, flat[c.start:c.stop], cmd=cmd))
+            for t in ts:
+                self.kv.wait(t)
+        (barrier or self._barrier or (lambda: None))()
+        ts = []
+        for p, per in zip(self.params, self.chunks):
+            assert p.dtype == torch.bfloat16, "servers emit bf16 parameters"
+            flat = p.data.view(-1)
+            for c in per:
+                ts.append(self.kv.pull(c.key, flat[c.start:c.stop]))
+        for t in ts:
+            self.kv.wait(t)
+
+    # -- gradient hooks ---------------------------------------------------------------
+    def attach(self):
+        for i, p in enumerate(self.params):
+            self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(i)))
+        return self
+
+    def detach(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks.clear()
+
+    def _make_hook(self, i: int):
+        def hook(p: torch.Tensor):
+            if self.accumulate:
+                return
+            g = p.grad
+            p.grad = None  # the transport keeps the tensor alive until the push completes
+            self._push_pull(i, g)
+        return hook
+
+    def _push_pull(self, i: int, g: torch.Tensor):
+        if not g.is_contiguous():
+            g = g.contiguous()
+        gflat = g.view(-1)
+        pflat = self.params[i].data.view(-1)
+        codec = self._codec(g)
+        for c in self.chunks[i]:
+            gs = gflat[c.start:c.stop]
+            self._pending.append(self.kv.push(c.key, gs, cmd=self._C.CMD_GRAD, codec=codec, scale=1.0))
+            self._pending.append(self.kv.pull(c.key, pflat[c.start:c.stop]))
+            self.stats.pushes += 1
+            self.stats.pulls += 1
+            self.stats.push_bytes_wire += self._C.wire_bytes(codec, gs.numel() * gs.element_size())
+            self.stats.pull_bytes += (c.stop - c.start) * 2
+
+    # -- optimizer-like surface ---------------------------------------------------------
+    def step(self):
+        """Block until every parameter chunk of this round has been rewritten by its server."""
+        pend, self._pending = self._pending, []
+        for ts in pend:
+            self.kv.wait(ts)
+
+    def zero_grad(self, set_to_none: bool = True):
+        for p in self.params:
+            p.grad = None

@@ -1,7 +1,8 @@
 #!/bin/bash
 # Run a ps-lite style job on this host: 1 scheduler + S servers + W workers.
 # usage: scripts/local.sh <num_servers> <num_workers> <binary> [args...]
-# (parity: reference tests/local.sh:8-37). Extra env is inherited.
+# (parity: reference tests/local.sh:8-37). Extra env is inherited. If any process
+# fails, the rest are killed so a crash never turns into a hang.
 set -u
 if [ $# -lt 3 ]; then
   echo "usage: $0 num_servers num_workers bin [args..]"; exit 1
@@ -17,13 +18,25 @@ pids=()
 DMLC_ROLE=scheduler ${bin} ${args} &
 pids+=($!)
 for ((i=0; i<${DMLC_NUM_SERVER}; ++i)); do
-  DMLC_ROLE=server PS_CUDA_DEVICE=${SERVER_GPU_BASE:+$((SERVER_GPU_BASE + i))} ${bin} ${args} &
+  if [ -n "${SERVER_GPU_BASE:-}" ]; then export PS_CUDA_DEVICE=$((SERVER_GPU_BASE + i)); fi
+  DMLC_ROLE=server ${bin} ${args} &
   pids+=($!)
 done
 for ((i=0; i<${DMLC_NUM_WORKER}; ++i)); do
-  DMLC_ROLE=worker PS_CUDA_DEVICE=${WORKER_GPU_BASE:+$((WORKER_GPU_BASE + i))} ${bin} ${args} &
+  if [ -n "${WORKER_GPU_BASE:-}" ]; then export PS_CUDA_DEVICE=$((WORKER_GPU_BASE + i)); fi
+  DMLC_ROLE=worker ${bin} ${args} &
   pids+=($!)
 done
 rc=0
-for p in "${pids[@]}"; do wait $p || rc=$?; done
+remaining=${#pids[@]}
+while [ $remaining -gt 0 ]; do
+  wait -n; st=$?
+  remaining=$((remaining - 1))
+  if [ $st -ne 0 ]; then
+    rc=$st
+    for p in "${pids[@]}"; do kill $p 2>/dev/null; done
+    break
+  fi
+done
+wait 2>/dev/null
 exit $rc

@@ -46,6 +46,58 @@
 
 namespace ps {
 
+/*!
+ * \brief recycles page-aligned receive buffers by size so steady-state traffic never
+ *        page-faults fresh memory (the dominant cost of a 1 MB receive on loopback)
+ */
+class RecvBufferPool : public std::enable_shared_from_this<RecvBufferPool> {
+ public:
+  explicit RecvBufferPool(size_t cap_bytes) : cap_(cap_bytes) {}
+  ~RecvBufferPool() {
+    for (auto& kv : free_)
+      for (char* p : kv.second) free(p);
+  }
+  SArray<char> Get(size_t len) {
+    const size_t rounded = (len + 4095) & ~size_t(4095);
+    char* p = nullptr;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      auto it = free_.find(rounded);
+      if (it != free_.end() && !it->second.empty()) {
+        p = it->second.back();
+        it->second.pop_back();
+        cached_ -= rounded;
+      }
+    }
+    if (!p) {
+      void* vp = nullptr;
+      CHECK_EQ(posix_memalign(&vp, 4096, rounded), 0);
+      p = static_cast<char*>(vp);
+    }
+    std::shared_ptr<RecvBufferPool> self = shared_from_this();
+    SArray<char> seg;
+    seg.reset(p, len, [self, rounded](char* q) { self->Put(q, rounded); });
+    return seg;
+  }
+
+ private:
+  void Put(char* p, size_t rounded) {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (cached_ + rounded <= cap_) {
+        free_[rounded].push_back(p);
+        cached_ += rounded;
+        return;
+      }
+    }
+    free(p);
+  }
+  std::mutex mu_;
+  size_t cap_;
+  size_t cached_ = 0;
+  std::map<size_t, std::vector<char*>> free_;
+};
+
 class TcpVan : public Van {
  public:
   explicit TcpVan(Postoffice* postoffice) : Van(postoffice) {}
@@ -59,6 +111,11 @@ class TcpVan : public Van {
       if (epfd_ < 0) {
         local_ipc_ = GetEnv("DMLC_LOCAL", 0) != 0;
         connect_timeout_s_ = GetEnv("PS_CONNECT_TIMEOUT", 120);
+        direct_pull_ = GetEnv("PS_TCP_DIRECT_PULL", 1) != 0;
+        if (!pool_) {
+          pool_ = std::make_shared<RecvBufferPool>(
+              static_cast<size_t>(GetEnv("PS_TCP_POOL_MB", 1024)) << 20);
+        }
         epfd_ = epoll_create1(EPOLL_CLOEXEC);
         CHECK_GE(epfd_, 0) << strerror(errno);
         wake_fd_ = eventfd(0, EFD_NONBLOCK | EFD_CLOEXEC);
@@ -205,8 +262,9 @@ class TcpVan : public Van {
     if (nseg) iov[niov++] = {seg_len, sizeof(uint64_t) * nseg};
     iov[niov++] = {meta_buf.data(), meta_buf.size()};
     for (uint32_t i = 0; i < nseg; ++i) {
-      CHECK(!msg.data[i].on_gpu()) << "TcpVan cannot send device memory: " << msg.DebugString();
       seg_len[i] = msg.data[i].size();
+      CHECK(seg_len[i] == 0 || !msg.data[i].on_gpu())
+          << "TcpVan cannot send device memory: " << msg.DebugString();
       if (seg_len[i]) iov[niov++] = {msg.data[i].data(), msg.data[i].size()};
     }
     for (int i = 0; i < niov; ++i) total += iov[i].iov_len;
@@ -323,6 +381,15 @@ class TcpVan : public Van {
     AddToEpoll(fd);
   }
 
+  static size_t ElemSize(DataType t) {
+    switch (t) {
+      case INT16: case UINT16: return 2;
+      case INT32: case UINT32: case FLOAT: return 4;
+      case INT64: case UINT64: case DOUBLE: return 8;
+      default: return 1;
+    }
+  }
+
   static bool SendAll(int fd, struct iovec* iov, int niov) {
     while (niov > 0) {
       struct msghdr mh;
@@ -375,19 +442,12 @@ class TcpVan : public Van {
     }
   }
 
-  static SArray<char> AllocSegment(size_t len) {
+  SArray<char> AllocSegment(size_t len) {
     SArray<char> seg;
     if (len == 0) return seg;
-    char* p = nullptr;
-    if (len >= 4096) {
-      void* vp = nullptr;
-      CHECK_EQ(posix_memalign(&vp, 4096, (len + 4095) & ~size_t(4095)), 0);
-      p = static_cast<char*>(vp);
-      seg.reset(p, len, [](char* q) { free(q); });
-    } else {
-      p = new char[len];
-      seg.reset(p, len, [](char* q) { delete[] q; });
-    }
+    if (len >= 4096) return pool_->Get(len);
+    char* p = new char[len];
+    seg.reset(p, len, [](char* q) { delete[] q; });
     return seg;
   }
 
@@ -420,6 +480,15 @@ class TcpVan : public Van {
         if (it != registered_.end()) {
           CHECK_GE(it->second.size(), seg_len[i]) << "registered buffer too small";
           seg = it->second.segment(0, seg_len[i]);
+        }
+      }
+      // a pull response can land straight in the buffer the request named (meta.addr
+      // is this process's own pointer, echoed back by the server): zero-copy pull
+      if (i == 1 && direct_pull_ && !msg->meta.request && !msg->meta.push && msg->meta.addr != 0 &&
+          seg_len[i] > 0 && msg->meta.src_dev_type != GPU) {
+        const size_t esz = msg->meta.data_type.size() > 1 ? ElemSize(msg->meta.data_type[1]) : 1;
+        if (seg_len[i] <= static_cast<uint64_t>(msg->meta.val_len) * esz) {
+          seg.reset(reinterpret_cast<char*>(msg->meta.addr), seg_len[i], [](char*) {});
         }
       }
       if (seg.size() != seg_len[i]) seg = AllocSegment(seg_len[i]);
@@ -485,6 +554,8 @@ class TcpVan : public Van {
   }
 
   std::mutex init_mu_;
+  std::shared_ptr<RecvBufferPool> pool_;
+  bool direct_pull_ = true;
   bool local_ipc_ = false;
   int connect_timeout_s_ = 120;
   int epfd_ = -1;
