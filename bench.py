@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""Headline benchmark of pslite_b200 (driver contract: see the task statement).
+
+    python bench.py --gpus N --steps K --warmup W [--impl ours|reference] [--metric pushpull|llama]
+
+Default metric — the reference's own headline benchmark (tests/test_benchmark.cc,
+BASELINE.json "push+pull GB/s ... (test_benchmark)"): every worker ZPush-es and ZPull-s
+`keys_per_server x num_servers` values of `len` bytes per step (= one round of the
+reference's timing loop) and the job reports payload goodput with the reference's
+formula (payload counted once per push+pull pair), in GB/s, summed over workers.
+    N = 1        : 1 worker + 1 server co-located on the GPU (test_ipc_benchmark shape)
+    N = 2, 4, 8  : N/2 worker GPUs + N/2 server GPUs over the NVLink van (4w+4s at N=8)
+Values live in HBM and move as one-sided sm_100a copy kernels into peer memory; only
+descriptors use TCP. `--metric llama` instead times Llama-3-8B synchronous PS training
+(fp8 gradient push, fused server-side AdamW, bf16 pull) in tokens/s.
+
+`--impl reference` runs the UNMODIFIED reference build (baseline/_ref, ZMQ van — the
+only reference transport buildable without ibverbs/UCX) through its own test_benchmark
+binary with the same len / keys / mode and prints the same JSON line.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC_NAME = {
+    "pushpull": "test_benchmark push+pull goodput",
+    "llama": "Llama-3-8B PS training throughput",
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--metric", default="pushpull", choices=["pushpull", "llama"])
+    ap.add_argument("--len", type=int, default=4096000, help="bytes per value (reference test.sh preset)")
+    ap.add_argument("--keys-per-server", type=int, default=40)
+    ap.add_argument("--topology", default=None, choices=[None, "joint", "split"])
+    ap.add_argument("--van", default=None)
+    ap.add_argument("--no-e2e", action="store_true")
+    # llama
+    ap.add_argument("--seq-len", type=int, default=8192)
+    ap.add_argument("--micro-batch", type=int, default=1)
+    ap.add_argument("--grad-wire", default="fp8", choices=["fp8", "bf16"])
+    ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "llama-1b", "tiny"])
+    ap.add_argument("--ckpt-layers", type=int, default=-1)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------
+# distributed plumbing
+# ----------------------------------------------------------------------------------------
+class Dist:
+    """torch.distributed when WORLD_SIZE > 1 (gloo for host-side barriers / reductions so the
+    measured GPUs run nothing but the benchmark), no-ops otherwise."""
+
+    def __init__(self):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.gloo = None
+        if self.world > 1:
+            import torch
+            import torch.distributed as dist
+
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            backend = "cpu:gloo,cuda:nccl" if torch.cuda.is_available() else "gloo"
+            dist.init_process_group(backend=backend, rank=self.rank, world_size=self.world)
+            self.gloo = dist.new_group(backend="gloo")
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.barrier(group=self.gloo)
+
+    def reduce(self, value: float, op: str) -> float:
+        if self.world == 1:
+            return value
+        import torch
+        import torch.distributed as dist
+
+        t = torch.tensor([value], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if op == "max" else dist.ReduceOp.SUM, group=self.gloo)
+        return float(t.item())
+
+    def shutdown(self):
+        if self.world > 1:
+            import torch.distributed as dist
+
+            dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------
+# ours: push/pull
+# ----------------------------------------------------------------------------------------
+def run_pushpull(args, dist: Dist) -> dict:
+    import torch
+
+    from pslite_b200 import native
+    from pslite_b200.parallel.launch import init_ps
+    from pslite_b200.utils.timing import ClockSampler
+
+    C = native()
+    torch.cuda.set_device(dist.local_rank)
+    topo = args.topology or ("joint" if dist.world == 1 else "split")
+    ctx = init_ps(topo, van=args.van)
+    server = C.BenchServer(0) if ctx.is_server else None
+    S, W = ctx.num_servers, ctx.num_workers
+    total_keys = S * args.keys_per_server
+    dev = torch.device("cuda", dist.local_rank)
+    kv = keys = vals = None
+    if ctx.is_worker:
+        kv = C.KVWorker(0, 0)
+        keys = [kv.server_key(k % S, k) for k in range(total_keys)]
+        vals = [torch.full((args.len,), 1, dtype=torch.uint8, device=dev) for _ in range(total_keys)]
+        for k in range(total_keys):  # rendezvous + store creation, untimed (as the reference does)
+            kv.wait(kv.push(keys[k], vals[k], order_after_current_stream=False))
+    dist.barrier()
+
+    def one_round():
+        ts = []
+        for k in range(total_keys):
+            ts.append(kv.push(keys[k], vals[k], order_after_current_stream=False))
+            ts.append(kv.pull(keys[k], vals[k]))
+        for t in ts:
+            kv.wait(t)
+
+    def timed(fn, steps: int):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = C.kernel_launch_count()
+        e0.record()
+        if ctx.is_worker:
+            for _ in range(steps):
+                fn()
+        torch.cuda.synchronize()
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        dist.barrier()  # servers keep serving until every worker is done
+        launches = C.kernel_launch_count() - launches0
+        return dist.reduce(ms, "max"), dist.reduce(float(launches), "sum")
+
+    if ctx.is_worker:
+        for _ in range(args.warmup):
+            one_round()
+    sampler = ClockSampler(dist.local_rank).start() if dist.rank == 0 else None
+    ms, launches = timed(one_round, args.steps)
+    clocks = sampler.stop() if sampler else None
+    payload = float(args.len) * total_keys * W  # per step, counted once per push+pull pair
+    value = payload * args.steps / (ms * 1e-3) / 1e9
+
+    e2e = None
+    if not args.no_e2e:
+        host_in = host_out = None
+        if ctx.is_worker:
+            host_in = [torch.full((args.len,), 2, dtype=torch.uint8).pin_memory() for _ in range(total_keys)]
+            host_out = [torch.empty(args.len, dtype=torch.uint8).pin_memory() for _ in range(total_keys)]
+
+        def e2e_round():
+            ts = []
+            for k in range(total_keys):
+                vals[k].copy_(host_in[k], non_blocking=True)          # H2D of this step's input
+                ts.append(kv.push(keys[k], vals[k], order_after_current_stream=True))
+                ts.append(kv.pull(keys[k], vals[k]))
+            for t in ts:
+                kv.wait(t)
+            for k in range(total_keys):
+                host_out[k].copy_(vals[k], non_blocking=True)         # D2H of the pulled result
+            torch.cuda.synchronize()
+
+        if ctx.is_worker:
+            e2e_round()
+        e2e_steps = max(3, args.steps // 4)
+        ms2, _ = timed(e2e_round, e2e_steps)
+        e2e = {"value": payload * e2e_steps / (ms2 * 1e-3) / 1e9, "unit": "GB/s",
+               "h2d_bytes_per_step": int(args.len) * total_keys * W,
+               "d2h_bytes_per_step": int(args.len) * total_keys * W, "steps": e2e_steps}
+
+    ctx.shutdown()
+    return {
+        "metric": METRIC_NAME["pushpull"], "value": value, "unit": "GB/s",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "uint8 payload (bit-exact copy)", "data": "synthetic",
+        "config": {"model": "test_benchmark PUSH_PULL", "msg_bytes": args.len,
+                   "keys_per_server": args.keys_per_server, "num_workers": W, "num_servers": S,
+                   "global_batch": total_keys * W, "seq_len": args.len,
+                   "parallelism": f"{W}w+{S}s {'co-located' if topo == 'joint' else 'split'} on {dist.world} GPU(s), nvl van",
+                   "l2": f"working set {args.len * total_keys / 1e6:.0f} MB per worker > 126 MB L2"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+    }
+
+
+# ----------------------------------------------------------------------------------------
+# ours: Llama-3-8B PS training
+# ----------------------------------------------------------------------------------------
+def run_llama(args, dist: Dist) -> dict:
+    import torch
+
+    from pslite_b200 import native
+    from pslite_b200.models.llama import Llama, LlamaConfig
+    from pslite_b200.parallel.launch import init_ps
+    from pslite_b200.parallel.ps_trainer import PSWorkerOptimizer
+    from pslite_b200.utils.timing import ClockSampler
+
+    C = native()
+    torch.cuda.set_device(dist.local_rank)
+    dev = torch.device("cuda", dist.local_rank)
+    topo = args.topology or "joint"
+    ctx = init_ps(topo, van=args.van)
+    W, S = ctx.num_workers, ctx.num_servers
+    server = None
+    if ctx.is_server:
+        server = C.GpuServer(0, num_workers=W, optimizer="adamw", lr=3e-4, beta1=0.9, beta2=0.95,
+                             eps=1e-8, weight_decay=0.1, grad_scale=1.0 / W, fuse_pull=True)
+    if args.model == "llama3-8b":
+        cfg = LlamaConfig.llama3_8b(max_seq_len=args.seq_len)
+    elif args.model == "llama-1b":
+        cfg = LlamaConfig(dim=2048, n_layers=16, n_heads=32, n_kv_heads=8, ffn_dim=8192,
+                          max_seq_len=args.seq_len)
+    else:
+        cfg = LlamaConfig.tiny(max_seq_len=args.seq_len)
+    if args.ckpt_layers >= 0:
+        cfg.ckpt_layers = args.ckpt_layers
+    B, T = args.micro_batch, args.seq_len
+    model = opt = kv = None
+    if ctx.is_worker:
+        with torch.device(dev):
+            model = Llama(cfg).to(torch.bfloat16)
+        model.init_weights(seed=0)
+        model.train()
+        kv = C.KVWorker(0, 0)
+        opt = PSWorkerOptimizer(model.parameters(), kv, S, W, ctx.worker_rank,
+                                grad_wire=args.grad_wire).attach()
+        opt.init_parameters(barrier=lambda: C.barrier(0, C.WORKER_GROUP, "worker"))
+    dist.barrier()
+    g = torch.Generator().manual_seed(1234 + dist.rank)
+    host_tok = torch.randint(0, cfg.vocab_size, (B, T + 1), generator=g).pin_memory()
+
+    def step(e2e: bool):
+        if e2e:
+            tok = host_tok.to(dev, non_blocking=True)
+        else:
+            tok = step.dev_tok
+        loss = model(tok[:, :-1], tok[:, 1:])
+        loss.backward()
+        opt.step()
+        return loss.item() if e2e else loss
+
+    step.dev_tok = host_tok.to(dev) if ctx.is_worker else None
+
+    def timed(fn, steps):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = C.kernel_launch_count()
+        e0.record()
+        if ctx.is_worker:
+            for _ in range(steps):
+                fn()
+        torch.cuda.synchronize()
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        dist.barrier()
+        return dist.reduce(ms, "max"), dist.reduce(float(C.kernel_launch_count() - l0), "sum")
+
+    if ctx.is_worker:
+        for _ in range(args.warmup):
+            step(False)
+    sampler = ClockSampler(dist.local_rank).start() if dist.rank == 0 else None
+    ms, launches = timed(lambda: step(False), args.steps)
+    clocks = sampler.stop() if sampler else None
+    tokens = B * T * W
+    value = tokens * args.steps / (ms * 1e-3)
+    e2e = None
+    if not args.no_e2e:
+        k = max(2, args.steps // 2)
+        ms2, _ = timed(lambda: step(True), k)
+        e2e = {"value": tokens * k / (ms2 * 1e-3), "unit": "tokens/s",
+               "h2d_bytes_per_step": int(host_tok.numel() * host_tok.element_size()) * W,
+               "d2h_bytes_per_step": 4 * W, "steps": k}
+    mfu = None
+    if ctx.is_worker:
+        peak = 1386e12
+        mfu = cfg.flops_per_token(T) * B * T / (ms / args.steps * 1e-3) / peak
+    stats = {"server_updates": server.num_updates() if server else 0,
+             "server_fused_fanouts": server.num_fused_fanouts() if server else 0}
+    ctx.shutdown()
+    return {
+        "metric": METRIC_NAME["llama"], "value": value, "unit": "tokens/s",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic tokens, random-init weights",
+        "config": {"model": args.model, "params": cfg.num_params(), "global_batch": B * W,
+                   "seq_len": T, "parallelism": f"ps-dp{W} ({W}w+{S}s {topo}), grad wire {args.grad_wire}, server AdamW",
+                   "ckpt_layers": cfg.ckpt_layers, "l2": "per-step working set >> 126 MB L2"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "mfu_vs_sustained_bf16": mfu,
+        "server": stats,
+    }
+
+
+# ----------------------------------------------------------------------------------------
+# reference arm
+# ----------------------------------------------------------------------------------------
+def run_reference(args, dist: Dist) -> dict:
+    if args.metric != "pushpull":
+        return {"impl": "reference", "unavailable":
+                "the reference is a communication library with no trainer or model code; only its test_benchmark can be run"}
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import build_reference
+
+    res = build_reference.build()
+    if not res["ok"]:
+        return {"impl": "reference", "unavailable": res["why"]}
+    out = None
+    if dist.rank == 0:
+        W = S = 1 if dist.world == 1 else dist.world // 2
+        port = 20000 + (os.getpid() % 20000)
+        env = dict(os.environ)
+        env.update({"DMLC_NUM_WORKER": str(W), "DMLC_NUM_SERVER": str(S),
+                    "DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": str(port),
+                    "DMLC_NODE_HOST": "127.0.0.1", "DMLC_GROUP_SIZE": "1", "DMLC_LOCAL": "1",
+                    "NUM_KEY_PER_SERVER": str(args.keys_per_server),
+                    "LOG_DURATION": str(args.steps),
+                    "TOTAL_DURATION": str(args.steps * (1 + max(1, -(-args.warmup // args.steps))))})
+        for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "MASTER_ADDR", "MASTER_PORT"):
+            env.pop(k, None)
+        cmd = [res["bin"], str(args.len), "10", "1"]
+        procs, logs = [], []
+        t0 = time.time()
+        for role, n in (("scheduler", 1), ("server", S), ("worker", W)):
+            for _ in range(n):
+                e = dict(env)
+                e["DMLC_ROLE"] = role
+                p = subprocess.Popen(cmd, env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                procs.append((role, p))
+        gbps = []
+        ok = True
+        for role, p in procs:
+            try:
+                o, _ = p.communicate(timeout=1800)
+            except subprocess.TimeoutExpired:
+                p.kill()
+                o, _ = p.communicate()
+                ok = False
+            if role == "worker":
+                found = re.findall(r"Application goodput: ([0-9.eE+-]+) Gbps", o)
+                if found:
+                    gbps.append(float(found[-1]))  # last window = after warm-up
+                else:
+                    ok = False
+        wall = time.time() - t0
+        if ok and len(gbps) == W:
+            value = sum(gbps) / 8.0  # Gbps -> GB/s, summed over workers
+            payload = float(args.len) * args.keys_per_server * S * W
+            out = {"impl": "reference", "metric": METRIC_NAME["pushpull"], "value": value,
+                   "unit": "GB/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                   "ms_per_step": payload / (value * 1e9) * 1e3, "higher_is_better": True,
+                   "scaling": "weak", "vs_baseline": None, "dtype": "uint8 payload", "data": "synthetic",
+                   "config": {"model": "test_benchmark PUSH_PULL", "msg_bytes": args.len,
+                              "keys_per_server": args.keys_per_server, "num_workers": W,
+                              "num_servers": S, "global_batch": args.keys_per_server * S * W,
+                              "seq_len": args.len,
+                              "parallelism": f"{W}w+{S}s processes, reference ZMQ van over ipc:// with CPU buffers "
+                                             "(its RDMA/UCX vans need ibverbs/UCX, absent in this image; ZMQ cannot carry device pointers)"},
+                   "timing": "host clock inside the reference binary (its own goodput print), last LOG_DURATION window",
+                   "wall_s": wall, "gpu_launches": 0}
+        else:
+            out = {"impl": "reference", "unavailable": "reference test_benchmark did not report goodput"}
+    dist.barrier()
+    return out
+
+
+def main():
+    args = parse_args()
+    dist = Dist()
+    if args.gpus != dist.world and dist.world > 1:
+        args.gpus = dist.world
+    if args.impl == "reference":
+        out = run_reference(args, dist)
+    elif args.metric == "llama":
+        out = run_llama(args, dist)
+    else:
+        out = run_pushpull(args, dist)
+    if dist.rank == 0 and out is not None:
+        out.setdefault("impl", "ours")
+        out.setdefault("n_gpus", args.gpus)
+        out.setdefault("steps", args.steps)
+        out.setdefault("warmup", args.warmup)
+        print(json.dumps(out), flush=True)
+    dist.shutdown()
+
+
+if __name__ == "__main__":
+    main()

@@ -17,6 +17,7 @@
 
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 
@@ -186,6 +187,55 @@ class PyKVServer {
   int next_id_ = 0;
 };
 
+/*!
+ * \brief native twin of test_benchmark's server: the first push of a key becomes its
+ *        store (the landing slot itself), pulls are answered from the store.
+ */
+class PyBenchServer {
+ public:
+  explicit PyBenchServer(int app_id) : kv_(new KVServer<char>(app_id)) {
+    kv_->set_request_handle([this](const KVMeta& m, const KVPairs<char>& d, KVServer<char>* s) {
+      const uint64_t key = d.keys.size() ? d.keys[0] : m.key;
+      if (m.push) {
+        {
+          std::lock_guard<std::mutex> lk(mu_);
+          auto it = store_.find(key);
+          if (it == store_.end()) {
+            KVPairs<char>& slot = store_[key];
+            slot.keys.CopyFrom(d.keys);
+            slot.lens.CopyFrom(d.lens);
+            slot.vals = d.vals;
+          }
+        }
+        ++pushes_;
+        s->Response(m);
+      } else {
+        KVPairs<char> res;
+        {
+          std::lock_guard<std::mutex> lk(mu_);
+          auto it = store_.find(key);
+          CHECK(it != store_.end()) << "pull of a key that was never pushed: " << key;
+          res = it->second;
+        }
+        ++pulls_;
+        s->Response(m, res);
+      }
+    });
+  }
+  ~PyBenchServer() {
+    py::gil_scoped_release nogil;
+    kv_.reset();
+  }
+  uint64_t pushes() const { return pushes_.load(); }
+  uint64_t pulls() const { return pulls_.load(); }
+
+ private:
+  std::unique_ptr<KVServer<char>> kv_;
+  std::mutex mu_;
+  std::unordered_map<uint64_t, KVPairs<char>> store_;
+  std::atomic<uint64_t> pushes_{0}, pulls_{0};
+};
+
 class PyGpuServer {
  public:
   PyGpuServer(int app_id, int num_workers, const std::string& optimizer, float lr, float beta1,
@@ -314,6 +364,11 @@ PYBIND11_MODULE(_C, m) {
       .def(py::init<int>(), py::arg("app_id") = 0)
       .def("set_request_handle", &PyKVServer::set_request_handle)
       .def("response", &PyKVServer::response, py::arg("id"), py::arg("vals") = py::none());
+
+  py::class_<PyBenchServer>(m, "BenchServer")
+      .def(py::init<int>(), py::arg("app_id") = 0)
+      .def("pushes", &PyBenchServer::pushes)
+      .def("pulls", &PyBenchServer::pulls);
 
   py::class_<PyGpuServer>(m, "GpuServer")
       .def(py::init<int, int, const std::string&, float, float, float, float, float, float, bool,

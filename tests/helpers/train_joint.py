@@ -1,0 +1,70 @@
+"""Joint (worker + GPU server in one process) PS training of a tiny model, compared with
+a local fp32-master AdamW run. usage: train_joint.py <grad_wire> <steps>"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import pslite_b200  # noqa: E402
+from pslite_b200.models.llama import Llama, LlamaConfig  # noqa: E402
+from pslite_b200.parallel.launch import init_ps  # noqa: E402
+from pslite_b200.parallel.ps_trainer import PSWorkerOptimizer  # noqa: E402
+
+
+def main():
+    wire, steps = sys.argv[1], int(sys.argv[2])
+    C = pslite_b200.native()
+    torch.cuda.set_device(0)
+    ctx = init_ps("joint", van="nvl")
+    lr, wd = 3e-3, 0.1
+    server = C.GpuServer(0, num_workers=1, optimizer="adamw", lr=lr, beta1=0.9, beta2=0.95, eps=1e-8,
+                         weight_decay=wd, grad_scale=1.0, fuse_pull=True)
+    cfg = LlamaConfig.tiny()
+    torch.manual_seed(0)
+    with torch.device("cuda:0"):
+        model = Llama(cfg).to(torch.bfloat16)
+        ref = Llama(cfg).to(torch.bfloat16)
+    model.init_weights(seed=1)
+    ref.load_state_dict(model.state_dict())
+    # local reference: fp32 master copy + torch AdamW, bf16 compute weights
+    masters = [p.detach().float().clone().requires_grad_(True) for p in ref.parameters()]
+    ropt = torch.optim.AdamW(masters, lr=lr, betas=(0.9, 0.95), eps=1e-8, weight_decay=wd)
+    kv = C.KVWorker(0, 0)
+    opt = PSWorkerOptimizer(model.parameters(), kv, 1, 1, 0, grad_wire=wire, chunk_elems=1 << 14).attach()
+    opt.init_parameters(barrier=lambda: None)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    ps_losses, ref_losses = [], []
+    for _ in range(steps):
+        tok = torch.randint(0, cfg.vocab_size, (2, 65), device="cuda", generator=g)
+        loss = model(tok[:, :-1], tok[:, 1:])
+        loss.backward()
+        opt.step()
+        ps_losses.append(loss.item())
+        rl = ref(tok[:, :-1], tok[:, 1:])
+        rl.backward()
+        for mp, p in zip(masters, ref.parameters()):
+            mp.grad = p.grad.float()
+            p.grad = None
+        ropt.step()
+        with torch.no_grad():
+            for mp, p in zip(masters, ref.parameters()):
+                p.copy_(mp.to(torch.bfloat16))
+        ref_losses.append(rl.item())
+    torch.cuda.synchronize()
+    worst = max(float((p.float() - q.float()).abs().max()) for p, q in zip(model.parameters(), ref.parameters()))
+    print("PS  ", ["%.4f" % x for x in ps_losses])
+    print("REF ", ["%.4f" % x for x in ref_losses])
+    print(f"max_param_diff={worst:.5f} updates={server.num_updates()} fused={server.num_fused_fanouts()} "
+          f"keys={server.num_keys()} launches={C.kernel_launch_count()}")
+    ok = ps_losses[-1] < ps_losses[0] and abs(ps_losses[-1] - ref_losses[-1]) < (0.02 if wire == "bf16" else 0.08)
+    ok = ok and server.num_fused_fanouts() > 0
+    ctx.shutdown()
+    print("PASS" if ok else "FAIL")
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

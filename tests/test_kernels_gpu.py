@@ -1,0 +1,120 @@
+"""Numerics of the sm_100a kernels against plain PyTorch fp32 references (B200 only)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+
+
+def ref_fp8_block(x: torch.Tensor):
+    """fp32 reference of the block-scaled e4m3 wire format: per-32 power-of-two scale."""
+    n = x.numel()
+    pad = (32 - n % 32) % 32
+    xp = torch.cat([x.float(), x.new_zeros(pad, dtype=torch.float32)]).view(-1, 32)
+    amax = xp.abs().amax(dim=1)
+    e = torch.ceil(torch.log2(amax.clamp_min(1e-38) / 448.0)).clamp(-127, 127)
+    e = torch.where(amax > 0, e, torch.full_like(e, -127.0))
+    scale = torch.exp2(e)
+    q = (xp / scale[:, None]).to(torch.float8_e4m3fn).float() * scale[:, None]
+    return q.view(-1)[:n]
+
+
+@pytest.mark.parametrize("n", [1, 31, 4096, 100003, 1 << 20])
+def test_raw_copy(native, n):
+    _require_cuda()
+    src = torch.randint(0, 255, (n,), dtype=torch.uint8, device="cuda")
+    dst = torch.zeros_like(src)
+    native.copy_codec(dst, src, native.CODEC_RAW, 1.0)
+    torch.cuda.synchronize()
+    assert torch.equal(dst, src)
+
+
+@pytest.mark.parametrize("n", [8, 1000, 100003])
+def test_f32_to_bf16_scaled(native, n):
+    _require_cuda()
+    x = torch.randn(n, device="cuda")
+    out = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    native.copy_codec(out.view(torch.uint8), x.view(torch.uint8), native.CODEC_F32_TO_BF16, 0.25)
+    torch.cuda.synchronize()
+    ref = (x * 0.25).to(torch.bfloat16)
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("src_dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n", [32, 4096, 100003])
+def test_fp8_block_quant_roundtrip(native, src_dtype, n):
+    _require_cuda()
+    x = (torch.randn(n, device="cuda") * torch.logspace(-3, 2, n, device="cuda")).to(src_dtype)
+    codec = native.CODEC_F32_TO_FP8BLOCK if src_dtype == torch.float32 else native.CODEC_BF16_TO_FP8BLOCK
+    wire = torch.zeros(native.wire_bytes(codec, x.numel() * x.element_size()), dtype=torch.uint8, device="cuda")
+    native.copy_codec(wire, x.view(torch.uint8), codec, 1.0)
+    dec = torch.empty(n, dtype=torch.float32, device="cuda")
+    native.decode(dec, wire, n, native.GRAD_FP8BLOCK)
+    torch.cuda.synchronize()
+    ref = ref_fp8_block(x.float())
+    # identical scale choice and RN rounding -> bit-identical to the fp32 reference
+    assert torch.allclose(dec, ref, rtol=0, atol=0), (dec - ref).abs().max()
+
+
+@pytest.mark.parametrize("fmt", ["bf16", "fp8", "f32"])
+@pytest.mark.parametrize("W,fan", [(1, 1), (2, 3), (4, 5)])
+def test_fused_adamw_update(native, fmt, W, fan):
+    _require_cuda()
+    n = 50003
+    torch.manual_seed(0)
+    p = torch.randn(n, device="cuda")
+    m = torch.randn(n, device="cuda") * 0.1
+    v = torch.rand(n, device="cuda") * 0.01
+    grads_f32 = [torch.randn(n, device="cuda") * 0.05 for _ in range(W)]
+    if fmt == "bf16":
+        wires = [g.to(torch.bfloat16) for g in grads_f32]
+        dec = [w.float() for w in wires]
+        gfmt = native.GRAD_BF16
+    elif fmt == "f32":
+        wires = grads_f32
+        dec = grads_f32
+        gfmt = native.GRAD_F32
+    else:
+        wires, dec = [], []
+        for g in grads_f32:
+            w = torch.zeros(native.wire_bytes(native.CODEC_F32_TO_FP8BLOCK, n * 4), dtype=torch.uint8, device="cuda")
+            native.copy_codec(w, g.view(torch.uint8), native.CODEC_F32_TO_FP8BLOCK, 1.0)
+            wires.append(w)
+            dec.append(ref_fp8_block(g))
+        gfmt = native.GRAD_FP8BLOCK
+    lr, b1, b2, eps, wd, step, gs = 1e-2, 0.9, 0.95, 1e-8, 0.1, 3, 1.0 / W
+    # fp32 PyTorch reference
+    g = sum(dec) * gs
+    m_ref = b1 * m + (1 - b1) * g
+    v_ref = b2 * v + (1 - b2) * g * g
+    mhat = m_ref / (1 - b1 ** step)
+    vhat = v_ref / (1 - b2 ** step)
+    p_ref = p - lr * (mhat / (vhat.sqrt() + eps) + wd * p)
+    pk, mk, vk = p.clone(), m.clone(), v.clone()
+    outs = [torch.empty(n, dtype=torch.bfloat16, device="cuda") for _ in range(fan)]
+    native.fused_update(wires, gfmt, pk, mk, vk, outs, "adamw", lr, b1, b2, eps, wd, step, gs, 0)
+    torch.cuda.synchronize()
+    assert torch.allclose(mk, m_ref, rtol=1e-5, atol=1e-7)
+    assert torch.allclose(vk, v_ref, rtol=1e-5, atol=1e-9)
+    assert torch.allclose(pk, p_ref, rtol=1e-5, atol=1e-6)
+    for o in outs:
+        assert torch.equal(o, pk.to(torch.bfloat16))
+
+
+def test_fused_sgd_update(native):
+    _require_cuda()
+    n = 4099
+    p = torch.randn(n, device="cuda")
+    m = torch.zeros(n, device="cuda")
+    v = torch.zeros(n, device="cuda")
+    g = torch.randn(n, device="cuda").to(torch.bfloat16)
+    out = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    pk = p.clone()
+    native.fused_update([g], native.GRAD_BF16, pk, m, v, [out], "sgd", 0.1, 0.9, 0.0, 0.0, 0.0, 1, 1.0, 0)
+    torch.cuda.synchronize()
+    ref = p - 0.1 * g.float()
+    assert torch.allclose(pk, ref, rtol=1e-6, atol=1e-6)

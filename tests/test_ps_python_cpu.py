@@ -1,0 +1,49 @@
+"""Python-level push/pull through the native runtime on CPU (tcp and shm vans)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from pslite_b200.utils.env import free_port
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+NODE = os.path.join(HERE, "helpers", "ps_node.py")
+
+
+def run_cluster(van, nw, ns, n_elems=1000, timeout=120):
+    port = str(free_port())
+    procs = []
+    env = dict(os.environ)
+    env["PSLITE_NO_AUTOBUILD"] = "1"
+    for role, count in (("scheduler", 1), ("server", ns), ("worker", nw)):
+        for _ in range(count):
+            procs.append((role, subprocess.Popen(
+                [sys.executable, NODE, role, van, str(nw), str(ns), port, str(n_elems)],
+                env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    outs = []
+    rc = 0
+    for role, p in procs:
+        try:
+            o, _ = p.communicate(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            for _, q in procs:
+                q.kill()
+            o, _ = p.communicate()
+            rc = rc or 124
+        outs.append((role, p.returncode, o))
+        rc = rc or p.returncode
+    return rc, outs
+
+
+@pytest.mark.parametrize("van,nw,ns", [("zmq", 1, 1), ("zmq", 2, 2), ("shm", 1, 1), ("shm", 2, 2)])
+def test_python_push_pull(native, van, nw, ns):
+    rc, outs = run_cluster(van, nw, ns)
+    assert rc == 0, "\n".join(f"[{r} rc={c}]\n{o[-1500:]}" for r, c, o in outs)
+    passes = sum(o.count("PASS") for r, c, o in outs if r == "worker")
+    assert passes == nw
+
+
+def test_python_large_message_shm(native):
+    rc, outs = run_cluster("shm", 1, 1, n_elems=2_000_000)
+    assert rc == 0, "\n".join(f"[{r} rc={c}]\n{o[-1500:]}" for r, c, o in outs)
