@@ -1,0 +1,241 @@
+// Unit tests: SArray, Range, Environment, queues, wire codec, allocators.
+#include <thread>
+#include "core/wire.h"
+#include "ps/internal/parallel_sort.h"
+#include "ps/internal/parallel_kv_match.h"
+#include "test_util.h"
+#include "van/mem_domain.h"
+
+using namespace ps;
+
+TEST(sarray_basic) {
+  SArray<int> a(4, 7);
+  CHECK_EQ(a.size(), (size_t)4);
+  CHECK_EQ(a[3], 7);
+  a.push_back(9);
+  CHECK_EQ(a.back(), 9);
+  SArray<int> seg = a.segment(1, 3);
+  CHECK_EQ(seg.size(), (size_t)2);
+  seg[0] = 42;
+  CHECK_EQ(a[1], 42);  // zero-copy view
+  a.resize(2);
+  CHECK_EQ(a.size(), (size_t)2);
+  SArray<int> il{1, 2, 3};
+  CHECK_EQ(il[2], 3);
+}
+
+TEST(sarray_cast_and_placement) {
+  SArray<float> f(8, 1.0f);
+  f.src_device_type_ = GPU;
+  f.src_device_id_ = 3;
+  f.dst_device_type_ = GPU;
+  f.dst_device_id_ = 5;
+  SArray<char> bytes(f);
+  CHECK_EQ(bytes.size(), (size_t)32);
+  CHECK_EQ((int)bytes.src_device_type_, (int)GPU);
+  CHECK_EQ(bytes.dst_device_id_, 5);
+  SArray<float> back(bytes);
+  CHECK_EQ(back.size(), (size_t)8);
+  CHECK(back.data() == f.data());
+  SArray<char> odd(7);
+  EXPECT_THROW(SArray<float> bad(odd));
+}
+
+TEST(sarray_keepalive) {
+  int released = 0;
+  {
+    SArray<char> outer;
+    {
+      SArray<char> a;
+      char* p = new char[16];
+      a.reset(p, 16, [&released](char* q) { delete[] q; ++released; });
+      outer = a.segment(4, 8);
+    }
+    CHECK_EQ(released, 0);  // the segment keeps the buffer alive
+  }
+  CHECK_EQ(released, 1);
+}
+
+TEST(sarray_append_self) {
+  SArray<int> a{1, 2, 3};
+  a.append(a);
+  CHECK_EQ(a.size(), (size_t)6);
+  CHECK_EQ(a[5], 3);
+}
+
+TEST(find_range) {
+  SArray<Key> a{1, 3, 5, 7, 9};
+  Range r = FindRange(a, (Key)2, (Key)7);
+  CHECK_EQ(r.begin(), (uint64_t)1);
+  CHECK_EQ(r.end(), (uint64_t)3);
+}
+
+TEST(environment_override) {
+  Environment::Get()->set("PS_TEST_KNOB", "17");
+  CHECK_EQ(GetEnv("PS_TEST_KNOB", 0), 17);
+  CHECK_EQ(GetEnv("PS_TEST_MISSING", 5), 5);
+  setenv("PS_TEST_FROM_OS", "abc", 1);
+  CHECK_EQ(GetEnvStr("PS_TEST_FROM_OS"), std::string("abc"));
+}
+
+TEST(spsc_queue) {
+  SPSCQueue<int> q(8);
+  std::thread prod([&] {
+    for (int i = 0; i < 100000; ++i) {
+      while (!q.try_push(i)) {
+      }
+    }
+  });
+  long long sum = 0;
+  for (int got = 0; got < 100000;) {
+    int v;
+    if (q.try_pop(&v)) {
+      CHECK_EQ(v, got);
+      sum += v;
+      ++got;
+    }
+  }
+  prod.join();
+  CHECK_EQ(sum, 100000LL * 99999 / 2);
+}
+
+TEST(threadsafe_queue_both_modes) {
+  for (const char* mode : {"0", "1"}) {
+    Environment::Get()->set("DMLC_LOCKLESS_QUEUE", mode);
+    ThreadsafeQueue<int> q;
+    std::vector<std::thread> prods;
+    for (int t = 0; t < 4; ++t) {
+      prods.emplace_back([&q, t] {
+        for (int i = 0; i < 5000; ++i) q.Push(t * 5000 + i);
+      });
+    }
+    long long sum = 0;
+    for (int i = 0; i < 20000; ++i) {
+      int v;
+      q.WaitAndPop(&v);
+      sum += v;
+    }
+    for (auto& t : prods) t.join();
+    CHECK_EQ(sum, 20000LL * 19999 / 2);
+  }
+  Environment::Get()->set("DMLC_LOCKLESS_QUEUE", "0");
+}
+
+TEST(wire_roundtrip_data_meta) {
+  Meta m;
+  m.head = 3; m.app_id = 1; m.customer_id = 2; m.timestamp = 77; m.request = true; m.push = true;
+  m.body = "hello";
+  m.data_type = {UINT64, CHAR, INT32};
+  m.src_dev_type = GPU; m.src_dev_id = 1; m.dst_dev_type = GPU; m.dst_dev_id = 6;
+  m.data_size = (int64_t)5 << 32;  // > 2 GiB must survive
+  m.key = 0xfeedfacecafebeefULL; m.addr = 0x7f0000001000ULL; m.val_len = (int64_t)3 << 31;
+  m.option = -2; m.sid = 9;
+  m.mem.region = 4; m.mem.offset = 4096; m.mem.bytes = 1234567; m.mem.flag_seq = 11;
+  m.codec = 3; m.scale = 0.125f;
+  std::vector<char> buf;
+  wire::PackMeta(m, &buf);
+  CHECK_EQ(buf.size(), wire::PackedMetaSize(m));
+  Meta r;
+  CHECK(wire::UnpackMeta(buf.data(), buf.size(), &r));
+  CHECK_EQ(r.head, 3); CHECK_EQ(r.timestamp, 77); CHECK(r.request); CHECK(r.push); CHECK(!r.simple_app);
+  CHECK_EQ(r.body, std::string("hello"));
+  CHECK_EQ(r.data_type.size(), (size_t)3); CHECK_EQ((int)r.data_type[2], (int)INT32);
+  CHECK_EQ(r.data_size, (int64_t)5 << 32); CHECK_EQ(r.key, 0xfeedfacecafebeefULL);
+  CHECK_EQ(r.val_len, (int64_t)3 << 31); CHECK_EQ(r.option, -2);
+  CHECK_EQ(r.mem.region, 4); CHECK_EQ(r.mem.bytes, (uint64_t)1234567);
+  CHECK_EQ(r.codec, 3); CHECK_EQ(r.scale, 0.125f);
+  CHECK_EQ((int)r.dst_dev_type, (int)GPU); CHECK_EQ(r.dst_dev_id, 6);
+  // truncated buffers are rejected, never mis-parsed
+  for (size_t cut : {(size_t)0, (size_t)3, buf.size() / 2, buf.size() - 1}) {
+    Meta bad;
+    CHECK(!wire::UnpackMeta(buf.data(), cut, &bad));
+  }
+}
+
+TEST(wire_roundtrip_control_nodes) {
+  Meta m;
+  m.control.cmd = Control::ADD_NODE;
+  m.control.barrier_group = 7;
+  m.control.msg_sig = 99;
+  for (int i = 0; i < 3; ++i) {
+    Node n;
+    n.role = i ? Node::WORKER : Node::SERVER;
+    n.id = 8 + i; n.hostname = "10.0.0." + std::to_string(i); n.port = 9000 + i;
+    n.num_ports = 2; n.ports[0] = 9000 + i; n.ports[1] = 9100 + i;
+    n.dev_types[1] = GPU; n.dev_ids[1] = i;
+    n.is_recovery = i == 2; n.aux_id = i; n.pid = 1000 + i; n.dev_id = i;
+    memcpy(n.endpoint_name, "0123456789abcdef", 16);
+    n.endpoint_name_len = 16;
+    m.control.node.push_back(n);
+  }
+  std::vector<char> buf;
+  wire::PackMeta(m, &buf);
+  Meta r;
+  CHECK(wire::UnpackMeta(buf.data(), buf.size(), &r));
+  CHECK_EQ((int)r.control.cmd, (int)Control::ADD_NODE);
+  CHECK_EQ(r.control.node.size(), (size_t)3);
+  CHECK_EQ(r.control.node[2].hostname, std::string("10.0.0.2"));
+  CHECK(r.control.node[2].is_recovery);
+  CHECK_EQ(r.control.node[1].ports[1], 9101);
+  CHECK_EQ(r.control.node[1].dev_types[1], (int)GPU);
+  CHECK_EQ(r.control.node[1].pid, 1001);
+  CHECK_EQ(r.control.node[0].endpoint_name_len, (size_t)16);
+  CHECK_EQ(memcmp(r.control.node[0].endpoint_name, "0123456789abcdef", 16), 0);
+  // a node costs tens of bytes, not the reference's 552-byte RawNode
+  CHECK_LT(buf.size(), (size_t)400);
+}
+
+TEST(arena_allocator) {
+  ArenaAllocator a(1 << 20, 256);
+  uint64_t x = a.Alloc(1000), y = a.Alloc(5000), z = a.Alloc(100);
+  CHECK_EQ(x % 256, (uint64_t)0);
+  CHECK(x != y && y != z);
+  CHECK(a.Free(y));
+  CHECK(!a.Free(y));
+  uint64_t y2 = a.Alloc(4000);  // fits in the hole
+  CHECK_EQ(y2, y);
+  CHECK(a.Free(x)); CHECK(a.Free(y2)); CHECK(a.Free(z));
+  CHECK_EQ(a.BytesInUse(), (uint64_t)0);
+  CHECK_EQ(a.Alloc(1 << 20), (uint64_t)0);  // fully coalesced again
+  CHECK_EQ(a.Alloc(1), UINT64_MAX);
+}
+
+TEST(index_pool) {
+  IndexPool<int> pool(4);
+  int v[6];
+  uint32_t idx[6];
+  for (int i = 0; i < 6; ++i) idx[i] = pool.Store(&v[i]);  // grows past the initial 4
+  for (int i = 0; i < 6; ++i) CHECK(pool.Get(idx[i]) == &v[i]);
+  CHECK(pool.Release(idx[2]) == &v[2]);
+  CHECK(pool.Get(idx[2]) == nullptr);
+}
+
+TEST(wire_bytes_table) {
+  CHECK_EQ(WireBytes(kCodecRaw, 1000), (uint64_t)1000);
+  CHECK_EQ(WireBytes(kCodecF32ToBf16, 4000), (uint64_t)2000);
+  CHECK_EQ(WireBytes(kCodecF32ToFp8Block, 4 * 64), (uint64_t)(64 + 2));
+  CHECK_EQ(WireBytes(kCodecBf16ToFp8Block, 2 * 33), (uint64_t)(64 + 2));  // padded to 2 blocks
+}
+
+TEST(parallel_sort_and_match) {
+  SArray<int> a(100000);
+  for (size_t i = 0; i < a.size(); ++i) a[i] = (int)((i * 7919) % 100003);
+  ParallelSort(&a, 4, std::less<int>());
+  for (size_t i = 1; i < a.size(); ++i) CHECK_LE(a[i - 1], a[i]);
+  SArray<Key> src_k{1, 3, 5, 7};
+  SArray<float> src_v{1.f, 3.f, 5.f, 7.f};
+  SArray<Key> dst_k{3, 4, 7, 9};
+  SArray<float> dst_v(4, 10.f);
+  size_t matched = ParallelOrderedMatch(src_k, src_v, dst_k, &dst_v, 1, PLUS, 2);
+  CHECK_EQ(matched, (size_t)2);
+  CHECK_EQ(dst_v[0], 13.f); CHECK_EQ(dst_v[1], 10.f); CHECK_EQ(dst_v[2], 17.f);
+}
+
+TEST(logging_check_throws) {
+  EXPECT_THROW(CHECK_EQ(1, 2) << "boom");
+  EXPECT_THROW(LOG(FATAL) << "fatal");
+  int x = 3;
+  CHECK_NOTNULL(&x);
+}
+
+int main() { return RunAllTests(); }

@@ -37,8 +37,8 @@ def main():
     opt.init_parameters(barrier=lambda: None)
     g = torch.Generator(device="cuda").manual_seed(7)
     ps_losses, ref_losses = [], []
+    tok = torch.randint(0, cfg.vocab_size, (2, 65), device="cuda", generator=g)  # one fixed batch
     for _ in range(steps):
-        tok = torch.randint(0, cfg.vocab_size, (2, 65), device="cuda", generator=g)
         loss = model(tok[:, :-1], tok[:, 1:])
         loss.backward()
         opt.step()
@@ -54,7 +54,8 @@ def main():
                 p.copy_(mp.to(torch.bfloat16))
         ref_losses.append(rl.item())
     torch.cuda.synchronize()
-    worst = max(float((p.float() - q.float()).abs().max()) for p, q in zip(model.parameters(), ref.parameters()))
+    with torch.no_grad():
+        worst = max(float((p.float() - q.float()).abs().max()) for p, q in zip(model.parameters(), ref.parameters()))
     print("PS  ", ["%.4f" % x for x in ps_losses])
     print("REF ", ["%.4f" % x for x in ref_losses])
     print(f"max_param_diff={worst:.5f} updates={server.num_updates()} fused={server.num_fused_fanouts()} "

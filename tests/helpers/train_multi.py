@@ -1,0 +1,79 @@
+"""Multi-GPU PS training under torchrun (one process per GPU). Every rank trains the same
+tiny Llama on its own data shard through the PS; at the end all workers must hold
+bit-identical parameters (they all pulled the same server state) and the loss must drop.
+usage: torchrun ... train_multi.py <topology> <grad_wire> <steps>"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import pslite_b200  # noqa: E402
+from pslite_b200.models.llama import Llama, LlamaConfig  # noqa: E402
+from pslite_b200.parallel.launch import init_ps  # noqa: E402
+from pslite_b200.parallel.ps_trainer import PSWorkerOptimizer  # noqa: E402
+
+
+def main():
+    topo, wire, steps = sys.argv[1], sys.argv[2], int(sys.argv[3])
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    use_cuda = torch.cuda.is_available()
+    dist.init_process_group("cpu:gloo,cuda:nccl" if use_cuda else "gloo")
+    gloo = dist.new_group(backend="gloo")
+    C = pslite_b200.native()
+    if use_cuda:
+        torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    ctx = init_ps(topo, van="nvl")
+    W, S = ctx.num_workers, ctx.num_servers
+    server = None
+    if ctx.is_server:
+        server = C.GpuServer(0, num_workers=W, optimizer="adamw", lr=3e-3, beta1=0.9, beta2=0.95,
+                             eps=1e-8, weight_decay=0.0, grad_scale=1.0 / W, fuse_pull=True)
+    ok = True
+    checksum = torch.zeros(1, dtype=torch.float64)
+    losses = []
+    if ctx.is_worker:
+        cfg = LlamaConfig.tiny()
+        with torch.device(dev):
+            model = Llama(cfg).to(torch.bfloat16)
+        model.init_weights(seed=3)
+        kv = C.KVWorker(0, 0)
+        opt = PSWorkerOptimizer(model.parameters(), kv, S, W, ctx.worker_rank, grad_wire=wire,
+                                chunk_elems=1 << 14).attach()
+        opt.init_parameters(barrier=lambda: C.barrier(0, C.WORKER_GROUP, "worker"))
+        g = torch.Generator(device=dev).manual_seed(100 + ctx.worker_rank)
+        tok = torch.randint(0, cfg.vocab_size, (2, 65), device=dev, generator=g)
+        for _ in range(steps):
+            loss = model(tok[:, :-1], tok[:, 1:])
+            loss.backward()
+            opt.step()
+            losses.append(loss.item())
+        torch.cuda.synchronize()
+        with torch.no_grad():
+            checksum[0] = sum(float(p.double().sum()) for p in model.parameters())
+        ok = losses[-1] < losses[0]
+    # all workers pulled the same parameters
+    sums = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
+    dist.all_gather(sums, checksum, group=gloo)
+    wsums = [float(s) for i, s in enumerate(sums) if (topo == "joint" or i < W)]
+    same = all(abs(x - wsums[0]) < 1e-9 for x in wsums)
+    print(f"rank {rank}: losses {['%.3f' % l for l in losses[:2]]}..{['%.3f' % l for l in losses[-2:]]} "
+          f"checksums_equal={same} updates={server.num_updates() if server else 0} "
+          f"fused={server.num_fused_fanouts() if server else 0}", flush=True)
+    ok = ok and same
+    flag = torch.tensor([1.0 if ok else 0.0])
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=gloo)
+    ctx.shutdown()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("PASS" if flag.item() > 0 else "FAIL", flush=True)
+    sys.exit(0 if flag.item() > 0 else 1)
+
+
+if __name__ == "__main__":
+    main()
