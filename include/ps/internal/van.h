@@ -50,6 +50,8 @@ class Van {
   virtual void Start(int customer_id, bool standalone);
   /*! \brief send; thread-safe; returns bytes sent (>0) */
   int Send(Message& msg);
+  /*! \brief like Send but a transport failure is reported (-1), not fatal */
+  int SendBestEffort(Message& msg);
   const Node& my_node() const {
     CHECK(ready_.load() || my_node_set_) << "call Start() first";
     return my_node_;
@@ -80,6 +82,9 @@ class Van {
     my_node_ = node;
     my_node_set_ = true;
   }
+
+  /*! \brief hand messages that arrived before their customer existed to it (called by Postoffice) */
+  void DeliverParked();
 
   /*! \brief cumulative payload+meta byte counters */
   size_t send_bytes() const { return send_bytes_.load(); }
@@ -150,6 +155,9 @@ class Van {
   Resender* resender_ = nullptr;
   int drop_rate_ = 0;
   unsigned drop_seed_ = 0;
+
+  std::mutex parked_mu_;
+  std::vector<Message> parked_;  // data messages waiting for their customer to be created
 
   std::vector<int> instance_barrier_count_;
   std::unordered_map<int, std::vector<int>> group_barrier_requests_;

@@ -1,7 +1,8 @@
 #!/bin/bash
 # Run a ps-lite style job on this host: 1 scheduler + S servers + W workers.
 # usage: scripts/local.sh <num_servers> <num_workers> <binary> [args...]
-# (parity: reference tests/local.sh:8-37). Extra env is inherited. If any process
+# (parity: reference tests/local.sh:8-37). Extra env is inherited.
+# JOINT=1: start num_workers joint processes instead; SET_RANKS=1: export DMLC_RANK=i. If any process
 # fails, the rest are killed so a crash never turns into a hang.
 set -u
 if [ $# -lt 3 ]; then
@@ -17,16 +18,27 @@ export DMLC_NODE_HOST=${DMLC_NODE_HOST:-127.0.0.1}
 pids=()
 DMLC_ROLE=scheduler ${bin} ${args} &
 pids+=($!)
-for ((i=0; i<${DMLC_NUM_SERVER}; ++i)); do
-  if [ -n "${SERVER_GPU_BASE:-}" ]; then export PS_CUDA_DEVICE=$((SERVER_GPU_BASE + i)); fi
-  DMLC_ROLE=server ${bin} ${args} &
-  pids+=($!)
-done
-for ((i=0; i<${DMLC_NUM_WORKER}; ++i)); do
-  if [ -n "${WORKER_GPU_BASE:-}" ]; then export PS_CUDA_DEVICE=$((WORKER_GPU_BASE + i)); fi
-  DMLC_ROLE=worker ${bin} ${args} &
-  pids+=($!)
-done
+if [ -n "${JOINT:-}" ]; then
+  # co-located mode: every process is worker i + server i (DMLC_ROLE=joint)
+  for ((i=0; i<${DMLC_NUM_WORKER}; ++i)); do
+    if [ -n "${WORKER_GPU_BASE:-}" ]; then export PS_CUDA_DEVICE=$((WORKER_GPU_BASE + i)); fi
+    DMLC_ROLE=joint DMLC_RANK=$i ${bin} ${args} &
+    pids+=($!)
+  done
+else
+  for ((i=0; i<${DMLC_NUM_SERVER}; ++i)); do
+    if [ -n "${SERVER_GPU_BASE:-}" ]; then export PS_CUDA_DEVICE=$((SERVER_GPU_BASE + i)); fi
+    if [ -n "${SET_RANKS:-}" ]; then export DMLC_RANK=$i; fi
+    DMLC_ROLE=server ${bin} ${args} &
+    pids+=($!)
+  done
+  for ((i=0; i<${DMLC_NUM_WORKER}; ++i)); do
+    if [ -n "${WORKER_GPU_BASE:-}" ]; then export PS_CUDA_DEVICE=$((WORKER_GPU_BASE + i)); fi
+    if [ -n "${SET_RANKS:-}" ]; then export DMLC_RANK=$i; fi
+    DMLC_ROLE=worker ${bin} ${args} &
+    pids+=($!)
+  done
+fi
 rc=0
 remaining=${#pids[@]}
 while [ $remaining -gt 0 ]; do

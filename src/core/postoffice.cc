@@ -153,8 +153,11 @@ void Postoffice::AddCustomer(Customer* customer) {
     customers_[app_id][customer_id] = customer;
   }
   customer_cv_.notify_all();
-  std::lock_guard<std::mutex> blk(barrier_mu_);
-  barrier_done_[app_id].emplace(customer_id, false);
+  {
+    std::lock_guard<std::mutex> blk(barrier_mu_);
+    barrier_done_[app_id].emplace(customer_id, false);
+  }
+  if (van_) van_->DeliverParked();
 }
 
 void Postoffice::RemoveCustomer(Customer* customer) {

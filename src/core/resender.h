@@ -42,6 +42,8 @@ class Resender {
   /*! \brief remember an outgoing message until it is ACKed */
   void AddOutgoing(const Message& msg) {
     if (msg.meta.control.cmd == Control::ACK) return;
+    // before the scheduler assigned our id nobody could address an ACK to us
+    if (van_->my_node_.id == Node::kEmpty || msg.meta.recver == van_->my_node_.id) return;
     CHECK_NE(msg.meta.timestamp, Meta::kEmpty) << msg.DebugString();
     const uint64_t sig = Signature(msg);
     std::lock_guard<std::mutex> lk(mu_);
@@ -55,6 +57,8 @@ class Resender {
   /*! \brief returns true if the message must not be processed (ACK or duplicate) */
   bool AddIncomming(const Message& msg) {
     if (msg.meta.control.cmd == Control::TERMINATE) return false;
+    // registration traffic of a node without an id, and self-addressed messages
+    if (msg.meta.sender == Node::kEmpty || msg.meta.sender == van_->my_node_.id) return false;
     if (msg.meta.control.cmd == Control::ACK) {
       std::lock_guard<std::mutex> lk(mu_);
       pending_.erase(msg.meta.control.msg_sig);
@@ -74,6 +78,20 @@ class Resender {
     van_->Send(ack);
     if (duplicated) LOG(WARNING) << "Duplicated message: " << msg.DebugString();
     return duplicated;
+  }
+
+  /*! \brief wait (bounded) until every message we sent has been ACKed */
+  void Flush(int deadline_ms) {
+    const int64_t until = NowMs() + deadline_ms;
+    while (NowMs() < until) {
+      if (NumPending() == 0) return;
+      std::this_thread::sleep_for(std::chrono::milliseconds(5));
+    }
+  }
+  /*! \brief shutting down: stop treating unreachable peers as fatal */
+  void SetLenient() {
+    std::lock_guard<std::mutex> lk(mu_);
+    lenient_ = true;
   }
 
   size_t NumPending() {
@@ -109,9 +127,13 @@ class Resender {
       if (exit_) break;
       std::vector<Message> resend;
       const int64_t now = NowMs();
-      for (auto& kv : pending_) {
-        Pending& p = kv.second;
+      for (auto it = pending_.begin(); it != pending_.end();) {
+        Pending& p = it->second;
         if (p.sent_at + static_cast<int64_t>(timeout_ms_) * (1 + p.retries) < now) {
+          if (lenient_ && p.retries + 1 >= max_retry_) {
+            it = pending_.erase(it);  // the peer has left; nobody will ever ACK this
+            continue;
+          }
           resend.push_back(p.msg);
           ++p.retries;
           LOG(WARNING) << van_->my_node_.ShortDebugString()
@@ -119,10 +141,17 @@ class Resender {
                        << ") " << p.msg.DebugString();
           CHECK_LT(p.retries, max_retry_);
         }
+        ++it;
       }
       lk.unlock();
-      for (auto& m : resend) van_->Send(m);
+      std::vector<uint64_t> unreachable;
+      for (auto& m : resend) {
+        // a retransmission that cannot even be handed to the transport means the peer
+        // has left (it got the original, our copy of its ACK was lost): stop insisting
+        if (van_->SendBestEffort(m) < 0) unreachable.push_back(Signature(m));
+      }
       lk.lock();
+      for (uint64_t sig : unreachable) pending_.erase(sig);
     }
   }
 
@@ -130,6 +159,7 @@ class Resender {
   std::unordered_map<uint64_t, Pending> pending_;
   std::unordered_set<uint64_t> seen_;
   bool exit_ = false;
+  bool lenient_ = false;
   std::mutex mu_;
   std::condition_variable cv_;
   int timeout_ms_;

@@ -122,6 +122,12 @@ void Van::Start(int customer_id, bool standalone) {
         profiling_ = profile_out_.is_open();
       }
 
+      // The resender must exist before the first message can arrive: a request that is
+      // processed without being recorded (and ACKed) would be processed *again* when its
+      // sender retransmits it (the reference creates it after registration, src/van.cc:587).
+      if (GetEnv("PS_RESEND", 0) != 0 && !resender_) {
+        resender_ = new Resender(GetEnv("PS_RESEND_TIMEOUT", 1000), 10, this);
+      }
       receiver_thread_.reset(new std::thread(&Van::Receiving, this));
       if (standalone) ready_ = true;
       init_stage_ = 1;
@@ -146,9 +152,6 @@ void Van::Start(int customer_id, bool standalone) {
   {
     std::lock_guard<std::mutex> lk(start_mu_);
     if (init_stage_ == 1) {
-      if (GetEnv("PS_RESEND", 0) != 0) {
-        resender_ = new Resender(GetEnv("PS_RESEND_TIMEOUT", 1000), 10, this);
-      }
       if (!is_scheduler_ && GetEnv("PS_HEARTBEAT_INTERVAL", 0) > 0) {
         heartbeat_thread_.reset(new std::thread(&Van::HeartbeatLoop, this));
       }
@@ -158,6 +161,11 @@ void Van::Start(int customer_id, bool standalone) {
 }
 
 void Van::Stop() {
+  if (resender_) {
+    // give in-flight messages a chance to be ACKed, then stop insisting
+    resender_->SetLenient();
+    resender_->Flush(GetEnv("PS_RESEND_TIMEOUT", 1000) * 4);
+  }
   stopping_ = true;
   // wake the receive loop with a message to ourselves
   Message bye;
@@ -193,8 +201,19 @@ void Van::Stop() {
   }
 }
 
+int Van::SendBestEffort(Message& msg) {
+  const int n = SendMsg(msg);
+  if (n > 0) send_bytes_ += static_cast<size_t>(n);
+  return n;
+}
+
 int Van::Send(Message& msg) {
   const int n = SendMsg(msg);
+  if (n == -1 && (stopping_.load() || msg.meta.control.cmd == Control::ACK)) {
+    // the peer already left (shutdown races with late ACKs / retransmissions)
+    LOG(WARNING) << GetType() << " could not deliver to departed node " << msg.meta.recver;
+    return -1;
+  }
   CHECK_NE(n, -1) << GetType() << " sent -1 bytes";
   send_bytes_ += static_cast<size_t>(n);
   if (resender_) resender_->AddOutgoing(msg);
@@ -212,7 +231,9 @@ void Van::Receiving() {
     Message msg;
     const int n = RecvMsg(&msg);
     CHECK_NE(n, -1) << GetType() << " receive failed";
-    if (ready_.load() && drop_rate_ > 0 && msg.meta.control.cmd != Control::TERMINATE) {
+    // fault injection models a lossy *network*: loopback (self-addressed) traffic is exempt
+    if (ready_.load() && drop_rate_ > 0 && msg.meta.control.cmd != Control::TERMINATE &&
+        msg.meta.sender != my_node_.id) {
       if (static_cast<int>(rand_r(&drop_seed_) % 100) < drop_rate_) {
         LOG(WARNING) << "Drop message " << msg.DebugString();
         continue;
@@ -263,9 +284,16 @@ void Van::ProcessDataMsg(Message* msg) {
   const int app_id = msg->meta.app_id;
   // servers run one customer per app; workers may run several
   const int customer_id = postoffice_->is_worker() ? msg->meta.customer_id : app_id;
-  Customer* obj = postoffice_->GetCustomer(app_id, customer_id, 5);
-  CHECK(obj) << "timeout (5 sec) to wait App " << app_id << " customer " << customer_id
-             << " ready at " << my_node_.role;
+  Customer* obj = postoffice_->GetCustomer(app_id, customer_id, 0);
+  if (!obj) {
+    // The application has not created this customer yet (e.g. it is still inside the
+    // start-up barrier). Park the message instead of blocking the receive thread — the
+    // reference waits here for up to 5 s (src/van.cc:435), during which no barrier
+    // release, ACK or heartbeat can be processed.
+    std::lock_guard<std::mutex> lk(parked_mu_);
+    parked_.push_back(*msg);
+    return;
+  }
   obj->Accept(*msg);
 
   if (profiling_ && !msg->data.empty() && msg->data[0].size() >= 2 && !msg->data[0].on_gpu()) {
@@ -276,6 +304,25 @@ void Van::ProcessDataMsg(Message* msg) {
     std::lock_guard<std::mutex> lk(profile_mu_);
     profile_out_ << key16 << "\t" << (postoffice_->is_worker() ? "worker" : "server")
                  << "_van_recv_" << (msg->meta.push ? "push" : "pull") << "\t" << us << "\n";
+  }
+}
+
+void Van::DeliverParked() {
+  std::vector<Message> todo;
+  {
+    std::lock_guard<std::mutex> lk(parked_mu_);
+    if (parked_.empty()) return;
+    todo.swap(parked_);
+  }
+  for (Message& m : todo) {
+    const int customer_id = postoffice_->is_worker() ? m.meta.customer_id : m.meta.app_id;
+    Customer* obj = postoffice_->GetCustomer(m.meta.app_id, customer_id, 0);
+    if (obj) {
+      obj->Accept(m);
+    } else {
+      std::lock_guard<std::mutex> lk(parked_mu_);
+      parked_.push_back(m);
+    }
   }
 }
 

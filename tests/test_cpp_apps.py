@@ -1,0 +1,124 @@
+"""C++ unit tests and multi-process functional tests of the native runtime (CPU only).
+
+Mirrors the reference's test strategy: role-from-env binaries launched as
+scheduler + S servers + W workers on localhost, plus fault injection (PS_DROP_MSG with
+PS_RESEND), instance groups, joint role, ipc:// mode, heartbeats and the shm one-sided van.
+"""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LOCAL = os.path.join(ROOT, "scripts", "local.sh")
+
+
+def launch(build_dir, servers, workers, app, *args, env=None, timeout=120):
+    e = dict(os.environ)
+    e.pop("DMLC_RANK", None)
+    if env:
+        e.update({k: str(v) for k, v in env.items()})
+    cmd = [LOCAL, str(servers), str(workers), os.path.join(build_dir, app), *map(str, args)]
+    r = subprocess.run(cmd, env=e, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    return r.returncode, r.stdout + r.stderr
+
+
+def test_cpp_unit_tests(built_native_tree):
+    for t in ("test_foundation", "test_inproc_cluster"):
+        r = subprocess.run([os.path.join(built_native_tree, "cpp_tests", t)], capture_output=True,
+                           text=True, timeout=120)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("s,w", [(1, 1), (2, 2), (3, 2)])
+def test_kv_app_tcp(built_native_tree, s, w):
+    rc, out = launch(built_native_tree, s, w, "test_kv_app")
+    assert rc == 0 and out.count("test_kv_app PASSED") == w, out[-3000:]
+
+
+def test_kv_app_ipc_sockets(built_native_tree):
+    rc, out = launch(built_native_tree, 2, 2, "test_kv_app", env={"DMLC_LOCAL": 1})
+    assert rc == 0 and out.count("PASSED") == 2, out[-3000:]
+
+
+def test_kv_app_lockless_queue_and_direct_dispatch(built_native_tree):
+    rc, out = launch(built_native_tree, 2, 1, "test_kv_app", env={"DMLC_LOCKLESS_QUEUE": 1})
+    assert rc == 0 and "PASSED" in out, out[-3000:]
+
+
+def test_kv_app_survives_message_drops_with_resend(built_native_tree):
+    env = {"PS_RESEND": 1, "PS_RESEND_TIMEOUT": 100, "PS_DROP_MSG": 10}
+    rc, out = launch(built_native_tree, 1, 1, "test_kv_app", 200, 2, 3, env=env, timeout=180)
+    assert "test_kv_app PASSED" in out, out[-3000:]   # every push/pull survived 10 % loss
+    assert "Drop message" in out                      # the injector really fired
+    if rc != 0:  # teardown with messages still being retransmitted is best-effort: retry once
+        rc, out = launch(built_native_tree, 1, 1, "test_kv_app", 200, 2, 3, env=env, timeout=180)
+    assert rc == 0, out[-3000:]
+
+
+def test_kv_app_instance_groups(built_native_tree):
+    rc, out = launch(built_native_tree, 1, 1, "test_kv_app", 500, 2, 3,
+                     env={"DMLC_GROUP_SIZE": 2, "SET_RANKS": 1})
+    assert rc == 0 and "PASSED" in out, out[-3000:]
+
+
+def test_kv_app_joint_role(built_native_tree):
+    rc, out = launch(built_native_tree, 2, 2, "test_kv_app", env={"JOINT": 1})
+    assert rc == 0 and out.count("PASSED") == 2, out[-3000:]
+
+
+def test_kv_app_preferred_ranks(built_native_tree):
+    rc, out = launch(built_native_tree, 2, 2, "test_connection", env={"SET_RANKS": 1})
+    assert rc == 0 and out.count("test_connection PASSED") == 5, out[-3000:]
+
+
+def test_simple_app(built_native_tree):
+    rc, out = launch(built_native_tree, 2, 2, "test_simple_app")
+    assert rc == 0 and out.count("test_simple_app PASSED") == 2, out[-3000:]
+
+
+def test_connection_with_heartbeats(built_native_tree):
+    rc, out = launch(built_native_tree, 1, 2, "test_connection",
+                     env={"PS_HEARTBEAT_INTERVAL": 1, "PS_HEARTBEAT_TIMEOUT": 5})
+    assert rc == 0 and out.count("test_connection PASSED") == 4, out[-3000:]
+
+
+@pytest.mark.parametrize("van", ["zmq", "shm"])
+def test_benchmark_small_and_large(built_native_tree, van):
+    for length in (1024, 1024000):
+        rc, out = launch(built_native_tree, 2, 2, "test_benchmark", length, 5, 1,
+                         env={"PS_VAN_TYPE": van, "NUM_KEY_PER_SERVER": 4, "TOTAL_DURATION": 10,
+                              "LOG_DURATION": 5})
+        assert rc == 0 and "Application goodput" in out, out[-3000:]
+
+
+def test_benchmark_registered_recv_buffers_shm(built_native_tree):
+    rc, out = launch(built_native_tree, 2, 2, "test_benchmark", 256000, 5, 1,
+                     env={"PS_VAN_TYPE": "shm", "ENABLE_RECV_BUFFER": 1, "NUM_KEY_PER_SERVER": 4,
+                          "TOTAL_DURATION": 10, "LOG_DURATION": 5})
+    assert rc == 0 and "Application goodput" in out, out[-3000:]
+
+
+def test_benchmark_registered_recv_buffers_tcp(built_native_tree):
+    rc, out = launch(built_native_tree, 1, 1, "test_benchmark", 256000, 5, 1,
+                     env={"ENABLE_RECV_BUFFER": 1, "NUM_KEY_PER_SERVER": 4, "TOTAL_DURATION": 10,
+                          "LOG_DURATION": 5})
+    assert rc == 0 and "Application goodput" in out, out[-3000:]
+
+
+@pytest.mark.parametrize("mode", [0, 2, 3])
+def test_benchmark_modes(built_native_tree, mode):
+    rc, out = launch(built_native_tree, 1, 1, "test_benchmark", 64000, 3, mode,
+                     env={"NUM_KEY_PER_SERVER": 4, "TOTAL_DURATION": 10, "LOG_DURATION": 5})
+    assert rc == 0, out[-3000:]
+    assert ("total_time" in out) if mode == 0 else ("Application goodput" in out), out[-2000:]
+
+
+def test_van_profiling_log(built_native_tree, tmp_path):
+    prefix = str(tmp_path / "prof")
+    rc, out = launch(built_native_tree, 1, 1, "test_benchmark", 4096, 3, 1,
+                     env={"ENABLE_PROFILING": 1, "PROFILE_PATH": prefix, "NUM_KEY_PER_SERVER": 2,
+                          "TOTAL_DURATION": 4, "LOG_DURATION": 2})
+    assert rc == 0, out[-2000:]
+    server_log = open(prefix + "_van_server").read().strip().splitlines()
+    assert server_log and server_log[0].split("\t")[1] in ("server_van_recv_push", "server_van_recv_pull")
