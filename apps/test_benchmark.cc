@@ -77,7 +77,7 @@ int MyDevice() {
 
 /*! \brief page-aligned host buffer or device buffer, wrapped with the right placement */
 template <typename T>
-SArray<T> AllocArray(size_t count, bool on_gpu, int dst_dev, bool dst_gpu) {
+SArray<T> AllocArray(size_t count, bool on_gpu, int dst_dev, bool dst_gpu, int src_dev = 0) {
   SArray<T> out;
   const size_t bytes = count * sizeof(T);
   if (on_gpu) {
@@ -100,7 +100,7 @@ SArray<T> AllocArray(size_t count, bool on_gpu, int dst_dev, bool dst_gpu) {
     const size_t page = static_cast<size_t>(sysconf(_SC_PAGESIZE));
     CHECK_EQ(posix_memalign(&p, page, (bytes + page - 1) / page * page), 0);
     memset(p, 1, bytes);
-    out.reset(static_cast<T*>(p), count, [](T*) {}, CPU, 0, dst_gpu ? GPU : CPU, dst_dev);
+    out.reset(static_cast<T*>(p), count, [](T*) {}, CPU, src_dev, dst_gpu ? GPU : CPU, dst_dev);
   }
   return out;
 }
@@ -112,7 +112,7 @@ struct KeySet {
 };
 
 /*! \brief key k lives on server k % S and is encoded as range[server].begin() + k */
-KeySet MakeKeySet(int total_keys, bool vals_on_gpu, bool dst_gpu) {
+KeySet MakeKeySet(int total_keys, bool vals_on_gpu, bool dst_gpu, int rank = 0) {
   KeySet ks;
   const auto& ranges = Postoffice::Get()->GetServerKeyRanges();
   const int S = static_cast<int>(ranges.size());
@@ -124,7 +124,9 @@ KeySet MakeKeySet(int total_keys, bool vals_on_gpu, bool dst_gpu) {
     const int dst_dev = dst_gpu ? 0 : (k % opt.num_ports);
     ks.keys.push_back(key);
     ks.lens.push_back(len);
-    ks.vals.push_back(AllocArray<char>(opt.len, vals_on_gpu, dst_dev, dst_gpu));
+    // multi-port vans pick the sending rail from the source context (reference src_key2ctx)
+    ks.vals.push_back(AllocArray<char>(opt.len, vals_on_gpu, dst_dev, dst_gpu,
+                                       (k + rank) % opt.num_ports));
   }
   return ks;
 }
@@ -269,7 +271,7 @@ void RunWorker(KVWorker<char>* kv, int tid) {
   const int S = static_cast<int>(Postoffice::Get()->GetServerKeyRanges().size());
   CHECK_GT(S, 0);
   const int total_keys = S * opt.keys_per_server;
-  KeySet ks = MakeKeySet(total_keys, opt.gpu_worker, opt.gpu_server);
+  KeySet ks = MakeKeySet(total_keys, opt.gpu_worker, opt.gpu_server, Postoffice::Get()->my_rank());
   if (opt.recv_buffer) {
     Postoffice::Get()->Barrier(0, kWorkerGroup + kServerGroup);
     LOG(INFO) << "Server recv buff registration is DONE.";

@@ -49,6 +49,7 @@ def parse_args():
     ap.add_argument("--topology", default=None, choices=[None, "joint", "split"])
     ap.add_argument("--van", default=None)
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--sweep", default="", help="comma-separated extra message sizes (bytes) to report")
     # llama
     ap.add_argument("--seq-len", type=int, default=8192)
     ap.add_argument("--micro-batch", type=int, default=1)
@@ -154,10 +155,15 @@ def run_pushpull(args, dist: Dist) -> dict:
         launches = C.kernel_launch_count() - launches0
         return dist.reduce(ms, "max"), dist.reduce(float(launches), "sum")
 
+    # clocks are sampled from the warm-up on (same load as the timed steps): K steps of this
+    # benchmark can be shorter than one nvidia-smi sampling period
+    sampler = ClockSampler(dist.local_rank, period_ms=100).start() if dist.rank == 0 else None
     if ctx.is_worker:
-        for _ in range(args.warmup):
+        t_end = time.time() + 1.0
+        n_warm = 0
+        while n_warm < args.warmup or time.time() < t_end:
             one_round()
-    sampler = ClockSampler(dist.local_rank).start() if dist.rank == 0 else None
+            n_warm += 1
     ms, launches = timed(one_round, args.steps)
     clocks = sampler.stop() if sampler else None
     payload = float(args.len) * total_keys * W  # per step, counted once per push+pull pair
@@ -190,8 +196,36 @@ def run_pushpull(args, dist: Dist) -> dict:
                "h2d_bytes_per_step": int(args.len) * total_keys * W,
                "d2h_bytes_per_step": int(args.len) * total_keys * W, "steps": e2e_steps}
 
+    sweep = []
+    for sz in [int(x) for x in args.sweep.split(",") if x]:
+        nk = max(1, min(args.keys_per_server, (512 << 20) // max(sz, 1))) * S
+        if ctx.is_worker:
+            skeys = [kv.server_key(k % S, 100000 + k) for k in range(nk)]
+            svals = [torch.full((sz,), 1, dtype=torch.uint8, device=dev) for _ in range(nk)]
+            for k in range(nk):
+                kv.wait(kv.push(skeys[k], svals[k], order_after_current_stream=False))
+
+            def sround():
+                ts = []
+                for k in range(nk):
+                    ts.append(kv.push(skeys[k], svals[k], order_after_current_stream=False))
+                    ts.append(kv.pull(skeys[k], svals[k]))
+                for t in ts:
+                    kv.wait(t)
+            for _ in range(3):
+                sround()
+        else:
+            sround = None
+        reps = max(3, min(50, int(2e9 // max(sz * nk, 1)) + 3))
+        ms_s, _ = timed(sround, reps)
+        sweep.append({"msg_bytes": sz, "keys": nk, "GBps": float(sz) * nk * W * reps / (ms_s * 1e-3) / 1e9,
+                      "us_per_key": ms_s * 1e3 / reps / nk})
+        if ctx.is_worker:
+            del svals
+
     ctx.shutdown()
     return {
+        "sweep": sweep,
         "metric": METRIC_NAME["pushpull"], "value": value, "unit": "GB/s",
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "uint8 payload (bit-exact copy)", "data": "synthetic",

@@ -106,23 +106,7 @@ class TcpVan : public Van {
   std::string GetType() const override { return "zmq"; }
 
   void Start(int customer_id, bool standalone) override {
-    {
-      std::lock_guard<std::mutex> lk(init_mu_);
-      if (epfd_ < 0) {
-        local_ipc_ = GetEnv("DMLC_LOCAL", 0) != 0;
-        connect_timeout_s_ = GetEnv("PS_CONNECT_TIMEOUT", 120);
-        direct_pull_ = GetEnv("PS_TCP_DIRECT_PULL", 1) != 0;
-        if (!pool_) {
-          pool_ = std::make_shared<RecvBufferPool>(
-              static_cast<size_t>(GetEnv("PS_TCP_POOL_MB", 1024)) << 20);
-        }
-        epfd_ = epoll_create1(EPOLL_CLOEXEC);
-        CHECK_GE(epfd_, 0) << strerror(errno);
-        wake_fd_ = eventfd(0, EFD_NONBLOCK | EFD_CLOEXEC);
-        CHECK_GE(wake_fd_, 0) << strerror(errno);
-        AddToEpoll(wake_fd_);
-      }
-    }
+    InitTransport();
     Van::Start(customer_id, standalone);
   }
 
@@ -139,6 +123,24 @@ class TcpVan : public Van {
   }
 
  protected:
+  /*! \brief create the epoll set / wake fd / buffer pool (idempotent) */
+  void InitTransport() {
+    std::lock_guard<std::mutex> lk(init_mu_);
+    if (epfd_ >= 0) return;
+    local_ipc_ = GetEnv("DMLC_LOCAL", 0) != 0;
+    connect_timeout_s_ = GetEnv("PS_CONNECT_TIMEOUT", 120);
+    direct_pull_ = GetEnv("PS_TCP_DIRECT_PULL", 1) != 0;
+    if (!pool_) {
+      pool_ = std::make_shared<RecvBufferPool>(static_cast<size_t>(GetEnv("PS_TCP_POOL_MB", 1024))
+                                               << 20);
+    }
+    epfd_ = epoll_create1(EPOLL_CLOEXEC);
+    CHECK_GE(epfd_, 0) << strerror(errno);
+    wake_fd_ = eventfd(0, EFD_NONBLOCK | EFD_CLOEXEC);
+    CHECK_GE(wake_fd_, 0) << strerror(errno);
+    AddToEpoll(wake_fd_);
+  }
+
   // the wire prefix of every frame
   struct FrameHeader {
     uint32_t magic;
@@ -508,6 +510,8 @@ class TcpVan : public Van {
     return static_cast<int>(std::min<size_t>(total, 0x7fffffff));
   }
 
+ protected:
+  /*! \brief enqueue a message for this van's own RecvMsg and wake it */
   int Loopback(const Message& msg) {
     {
       std::lock_guard<std::mutex> lk(loop_mu_);
@@ -519,6 +523,7 @@ class TcpVan : public Van {
     (void)r;
     return 1 + static_cast<int>(msg.meta.data_size & 0x3fffffff);
   }
+ private:
   bool PopLoopback(Message* msg) {
     std::lock_guard<std::mutex> lk(loop_mu_);
     if (loop_q_.empty()) return false;

@@ -7,6 +7,7 @@
  */
 #include "van/van_factory.h"
 #include "ps/internal/postoffice.h"
+#include "van/multi_van.h"
 #include "van/onesided_van.h"
 #include "van/tcp_van.h"
 #ifdef PS_USE_CUDA
@@ -20,6 +21,7 @@ Van* CreateVanByType(const std::string& type, Postoffice* postoffice) {
   if (type == "zmq" || type == "0" || type == "tcp" || type.empty()) {
     return new TcpVan(postoffice);
   }
+  if (type == "multivan") return new MultiVan(postoffice);
   if (type == "shm") return new OneSidedVan(postoffice, new ShmDomain(), "shm");
   if (type == "nvl" || type == "1" || type == "ibverbs" || type == "ucx" || type == "fabric") {
 #ifdef PS_USE_CUDA
