@@ -131,12 +131,8 @@ def run_pushpull(args, dist: Dist) -> dict:
     dist.barrier()
 
     def one_round():
-        ts = []
-        for k in range(total_keys):
-            ts.append(kv.push(keys[k], vals[k], order_after_current_stream=False))
-            ts.append(kv.pull(keys[k], vals[k]))
-        for t in ts:
-            kv.wait(t)
+        # one call issues ZPush + ZPull for every key (test_benchmark's inner loop), then Wait all
+        kv.wait_all(kv.push_pull_batch(keys, vals, order_after_current_stream=False))
 
     def timed(fn, steps: int):
         dist.barrier()
@@ -177,13 +173,9 @@ def run_pushpull(args, dist: Dist) -> dict:
             host_out = [torch.empty(args.len, dtype=torch.uint8).pin_memory() for _ in range(total_keys)]
 
         def e2e_round():
-            ts = []
             for k in range(total_keys):
                 vals[k].copy_(host_in[k], non_blocking=True)          # H2D of this step's input
-                ts.append(kv.push(keys[k], vals[k], order_after_current_stream=True))
-                ts.append(kv.pull(keys[k], vals[k]))
-            for t in ts:
-                kv.wait(t)
+            kv.wait_all(kv.push_pull_batch(keys, vals, order_after_current_stream=True))
             for k in range(total_keys):
                 host_out[k].copy_(vals[k], non_blocking=True)         # D2H of the pulled result
             torch.cuda.synchronize()

@@ -118,6 +118,51 @@ class PyKVWorker {
     kv_->Wait(ts);
   }
 
+  /*! \brief one push + one pull per (key, tensor) with a single Python call; returns all timestamps */
+  std::vector<int> push_pull_batch(const std::vector<uint64_t>& keys,
+                                   const std::vector<torch::Tensor>& tensors, int cmd, int codec,
+                                   float scale, bool order_after_current_stream, bool do_push,
+                                   bool do_pull) {
+    TORCH_CHECK(keys.size() == tensors.size(), "keys / tensors length mismatch");
+    std::vector<SArray<char>> views;
+    views.reserve(keys.size());
+    for (const auto& t : tensors) views.push_back(ViewOf(t));
+    cudaEvent_t ev = nullptr;
+    if (do_push && order_after_current_stream && !tensors.empty() && tensors[0].is_cuda()) {
+      ev = RecordOnCurrentStream(tensors[0].get_device());
+    }
+    py::gil_scoped_release nogil;
+    std::vector<int> ts;
+    ts.reserve(keys.size() * 2);
+    auto remaining = std::make_shared<std::atomic<int>>(do_push ? static_cast<int>(keys.size()) : 0);
+    for (size_t i = 0; i < keys.size(); ++i) {
+      if (do_push) {
+        SendOpts opts;
+        opts.codec = codec;
+        opts.scale = scale;
+        opts.wait_event = ev;
+        auto cb = ev ? KVWorker<char>::Callback([ev, remaining]() {
+          if (remaining->fetch_sub(1) == 1) cudaEventDestroy(ev);
+        }) : KVWorker<char>::Callback();
+        ts.push_back(kv_->ZPush(OneKey(keys[i]), views[i], OneLen(views[i].size()), cmd, cb, opts));
+      }
+      if (do_pull) {
+        auto* dst = new SArray<char>(views[i]);
+        auto* len = new SArray<int>(OneLen(dst->size()));
+        ts.push_back(kv_->ZPull(OneKey(keys[i]), dst, len, cmd, [dst, len]() {
+          delete dst;
+          delete len;
+        }));
+      }
+    }
+    return ts;
+  }
+
+  void wait_all(const std::vector<int>& ts) {
+    py::gil_scoped_release nogil;
+    for (int t : ts) kv_->Wait(t);
+  }
+
  private:
   std::unique_ptr<KVWorker<char>> kv_;
 };
@@ -358,7 +403,12 @@ PYBIND11_MODULE(_C, m) {
            py::arg("codec") = 0, py::arg("scale") = 1.0f,
            py::arg("order_after_current_stream") = true)
       .def("pull", &PyKVWorker::pull, py::arg("key"), py::arg("tensor"), py::arg("cmd") = 0)
-      .def("wait", &PyKVWorker::wait);
+      .def("wait", &PyKVWorker::wait)
+      .def("wait_all", &PyKVWorker::wait_all)
+      .def("push_pull_batch", &PyKVWorker::push_pull_batch, py::arg("keys"), py::arg("tensors"),
+           py::arg("cmd") = 0, py::arg("codec") = 0, py::arg("scale") = 1.0f,
+           py::arg("order_after_current_stream") = true, py::arg("push") = true,
+           py::arg("pull") = true);
 
   py::class_<PyKVServer>(m, "KVServer")
       .def(py::init<int>(), py::arg("app_id") = 0)

@@ -131,18 +131,18 @@ class CudaDomain : public MemDomain {
   }
 
   Ticket CopyAsync(void* dst, const void* src, size_t n, int codec, float scale,
-                   void* wait_event) override {
+                   void* wait_event, int src_device_type = UNK) override {
     PS_CUDA_CHECK(cudaSetDevice(dev_));
     if (wait_event) {
       PS_CUDA_CHECK(cudaStreamWaitEvent(stream_, static_cast<cudaEvent_t>(wait_event), 0));
     }
     if (n) {
-      cudaPointerAttributes attr;
-      bool src_on_device = true;
-      if (cudaPointerGetAttributes(&attr, src) != cudaSuccess ||
-          (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)) {
-        cudaGetLastError();
-        src_on_device = false;
+      bool src_on_device = src_device_type == GPU;
+      if (src_device_type == UNK) {  // untagged source: ask the driver (about 1 us)
+        cudaPointerAttributes attr;
+        src_on_device = cudaPointerGetAttributes(&attr, src) == cudaSuccess &&
+                        (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+        if (!src_on_device) cudaGetLastError();
       }
       if (!src_on_device) {
         CHECK_EQ(codec, (int)kCodecRaw) << "host-resident values can only be sent raw";

@@ -115,7 +115,7 @@ class MemDomain {
    *        producer of `src`.
    */
   virtual Ticket CopyAsync(void* dst, const void* src, size_t n_src_bytes, int codec, float scale,
-                           void* wait_event) = 0;
+                           void* wait_event, int src_device_type = UNK) = 0;
   /*! \brief block until the copy behind `t` is globally visible; recycles the ticket */
   virtual void Wait(Ticket t) = 0;
   /*! \brief stream-like handle applications may enqueue their own work on (may be null) */
@@ -288,7 +288,7 @@ class ShmDomain : public MemDomain {
     return base;
   }
   Ticket CopyAsync(void* dst, const void* src, size_t n, int codec, float /*scale*/,
-                   void* /*wait_event*/) override {
+                   void* /*wait_event*/, int /*src_device_type*/ = UNK) override {
     CHECK_EQ(codec, (int)kCodecRaw) << "the shm domain moves raw bytes only";
     if (n && dst != src) memcpy(dst, src, n);
     // make the payload visible before the descriptor that announces it

@@ -211,7 +211,7 @@ class OneSidedVan : public TcpVan {
     const uint64_t wire = WireBytes(msg.meta.codec, vals.size());
     Slot slot = AcquirePushSlot(recver, msg.meta.key, wire);
     Ticket t = domain_->CopyAsync(slot.ptr, vals.data(), vals.size(), msg.meta.codec,
-                                  msg.meta.scale, msg.wait_event);
+                                  msg.meta.scale, msg.wait_event, vals.src_device_type_);
     ++copies_;
     copy_bytes_ += wire;
     Message desc;
@@ -357,7 +357,8 @@ class OneSidedVan : public TcpVan {
       CHECK_LE(wire, msg.meta.mem.bytes) << "pull response larger than the destination";
     }
     Ticket t = domain_->CopyAsync(base + msg.meta.mem.offset, vals.data(), vals.size(),
-                                  msg.meta.codec, msg.meta.scale, msg.wait_event);
+                                  msg.meta.codec, msg.meta.scale, msg.wait_event,
+                                  vals.src_device_type_);
     ++copies_;
     copy_bytes_ += wire;
     Message desc;

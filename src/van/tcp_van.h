@@ -30,6 +30,7 @@
 #include <sys/un.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
 #include <deque>
 #include <map>
@@ -307,7 +308,7 @@ class TcpVan : public Van {
           (void)r;
         } else if (fd == listen_fd_) {
           AcceptOne();
-        } else {
+        } else if (std::find(ready_fds_.begin(), ready_fds_.end(), fd) == ready_fds_.end()) {
           ready_fds_.push_back(fd);  // level-triggered: drained one frame at a time
         }
       }
@@ -379,7 +380,7 @@ class TcpVan : public Van {
       int buf = 8 << 20;
       setsockopt(fd, SOL_SOCKET, SO_RCVBUF, &buf, sizeof(buf));
     }
-    inbound_.push_back(fd);
+    inbound_[fd].reset(new Inbound());
     AddToEpoll(fd);
   }
 
@@ -436,12 +437,7 @@ class TcpVan : public Van {
   void DropInbound(int fd) {
     epoll_ctl(epfd_, EPOLL_CTL_DEL, fd, nullptr);
     close(fd);
-    for (auto it = inbound_.begin(); it != inbound_.end(); ++it) {
-      if (*it == fd) {
-        inbound_.erase(it);
-        break;
-      }
-    }
+    inbound_.erase(fd);
   }
 
   SArray<char> AllocSegment(size_t len) {
@@ -453,22 +449,80 @@ class TcpVan : public Van {
     return seg;
   }
 
+  /*!
+   * \brief per-connection read buffer: a descriptor-sized frame (header + segment table
+   *        + meta + key + len) is consumed with ONE recv() instead of five
+   */
+  struct Inbound {
+    static constexpr size_t kCap = 64 * 1024;
+    std::unique_ptr<char[]> buf{new char[kCap]};
+    size_t head = 0, tail = 0;
+    size_t avail() const { return tail - head; }
+  };
+
+  /*! \brief make >= n bytes available in the buffer (n <= kCap). 1 ok, 0 closed, -1 error */
+  int Fill(int fd, Inbound* in, size_t n) {
+    if (in->avail() >= n) return 1;
+    if (in->head && in->head + n > Inbound::kCap) {
+      memmove(in->buf.get(), in->buf.get() + in->head, in->avail());
+      in->tail -= in->head;
+      in->head = 0;
+    } else if (in->avail() == 0) {
+      in->head = in->tail = 0;
+    }
+    const bool first_byte = in->avail() == 0;
+    while (in->avail() < n) {
+      ssize_t r = recv(fd, in->buf.get() + in->tail, Inbound::kCap - in->tail, 0);
+      if (r == 0) return (first_byte && in->avail() == 0) ? 0 : -1;
+      if (r < 0) {
+        if (errno == EINTR) continue;
+        return -1;
+      }
+      in->tail += static_cast<size_t>(r);
+    }
+    return 1;
+  }
+
+  /*! \brief copy n bytes of the stream to dst: buffered bytes first, then straight from the socket */
+  int Take(int fd, Inbound* in, void* dst, size_t n) {
+    char* out = static_cast<char*>(dst);
+    const size_t from_buf = std::min(n, in->avail());
+    if (from_buf) {
+      memcpy(out, in->buf.get() + in->head, from_buf);
+      in->head += from_buf;
+    }
+    if (n == from_buf) return 1;
+    if (n - from_buf <= 4096) {  // small tail: go through the buffer to batch with what follows
+      int rc = Fill(fd, in, n - from_buf);
+      if (rc <= 0) return -1;
+      memcpy(out + from_buf, in->buf.get() + in->head, n - from_buf);
+      in->head += n - from_buf;
+      return 1;
+    }
+    return ReadAll(fd, out + from_buf, n - from_buf) == 1 ? 1 : -1;
+  }
+
   /*! \brief read one whole frame from fd; >0 bytes, 0 if the socket went away */
   int ReadFrame(int fd, Message* msg) {
+    auto iit = inbound_.find(fd);
+    if (iit == inbound_.end()) return 0;
+    Inbound* in = iit->second.get();
     FrameHeader hdr;
-    int rc = ReadAll(fd, &hdr, sizeof(hdr));
+    int rc = Fill(fd, in, sizeof(hdr));
     if (rc <= 0) {
       DropInbound(fd);
       return 0;
     }
+    memcpy(&hdr, in->buf.get() + in->head, sizeof(hdr));
+    in->head += sizeof(hdr);
     CHECK_EQ(hdr.magic, kFrameMagic) << "corrupt frame";
     CHECK_LE(hdr.num_segments, kMaxSegments);
     uint64_t seg_len[kMaxSegments];
     if (hdr.num_segments) {
-      CHECK_EQ(ReadAll(fd, seg_len, sizeof(uint64_t) * hdr.num_segments), 1);
+      CHECK_EQ(Take(fd, in, seg_len, sizeof(uint64_t) * hdr.num_segments), 1);
     }
     std::vector<char> meta_buf(hdr.meta_len);
-    CHECK_EQ(ReadAll(fd, meta_buf.data(), meta_buf.size()), 1);
+    CHECK_EQ(Take(fd, in, meta_buf.data(), meta_buf.size()), 1);
     CHECK(UnpackMeta(meta_buf.data(), meta_buf.size(), &msg->meta)) << "corrupt meta";
     msg->meta.sender = hdr.sender;
     msg->meta.recver = my_node_.id;
@@ -494,7 +548,7 @@ class TcpVan : public Van {
         }
       }
       if (seg.size() != seg_len[i]) seg = AllocSegment(seg_len[i]);
-      if (seg_len[i]) CHECK_EQ(ReadAll(fd, seg.data(), seg_len[i]), 1);
+      if (seg_len[i]) CHECK_EQ(Take(fd, in, seg.data(), seg_len[i]), 1);
       // the bytes now live in host memory of this node
       seg.src_device_type_ = CPU;
       seg.src_device_id_ = 0;
@@ -507,6 +561,8 @@ class TcpVan : public Van {
       msg->data.push_back(seg);
       total += seg_len[i];
     }
+    // frames already sitting in the buffer will not wake epoll: keep this fd runnable
+    if (in->avail() > 0) ready_fds_.push_back(fd);
     return static_cast<int>(std::min<size_t>(total, 0x7fffffff));
   }
 
@@ -543,7 +599,7 @@ class TcpVan : public Van {
       }
       peers_.clear();
     }
-    for (int fd : inbound_) close(fd);
+    for (auto& kv : inbound_) close(kv.first);
     inbound_.clear();
     ready_fds_.clear();
     if (listen_fd_ >= 0) close(listen_fd_);
@@ -566,7 +622,7 @@ class TcpVan : public Van {
   int epfd_ = -1;
   int wake_fd_ = -1;
   int listen_fd_ = -1;
-  std::vector<int> inbound_;       // touched by the receive thread only
+  std::unordered_map<int, std::unique_ptr<Inbound>> inbound_;  // receive thread only
   std::deque<int> ready_fds_;      // touched by the receive thread only
   std::mutex peers_mu_;
   std::unordered_map<int, std::shared_ptr<Peer>> peers_;
