@@ -148,7 +148,7 @@ int SelfCheck(cudaStream_t st) {
     memset(&a, 0, sizeof(a));
     a.n = m; a.num_grads = 2; a.grad_format = PS_GRAD_BF16;
     a.grads[0] = w0; a.grads[1] = w1;
-    a.master = dp; a.m = dm; a.v = dv; a.num_outs = 1; a.outs[0] = outb;
+    a.master = dp; a.m = dm; a.v = dv; a.num_outs = 1; a.outs[0] = outb; a.body_outs = 1;
     ps_opt_params o;
     o.optimizer = PS_OPT_ADAMW; o.lr = 1e-2f; o.beta1 = 0.9f; o.beta2 = 0.95f; o.eps = 1e-8f;
     o.weight_decay = 0.1f; o.bias_corr1 = 1.f - 0.9f; o.bias_corr2 = 1.f - 0.95f; o.grad_scale = 0.5f;
@@ -265,6 +265,7 @@ int main(int argc, char** argv) {
           for (int w = 0; w < W; ++w) a.grads[w] = slots[w];
           a.master = master; a.m = m; a.v = v;
           a.num_outs = fan;
+          a.body_outs = fan;
           for (int k = 0; k < fan; ++k) a.outs[k] = outs[k];
           ps_opt_params o;
           o.optimizer = PS_OPT_ADAMW; o.lr = 1e-3f; o.beta1 = 0.9f; o.beta2 = 0.95f; o.eps = 1e-8f;

@@ -56,6 +56,8 @@ def parse_args():
     ap.add_argument("--grad-wire", default="fp8", choices=["fp8", "bf16"])
     ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "llama-1b", "tiny"])
     ap.add_argument("--ckpt-layers", type=int, default=-1)
+    ap.add_argument("--symmetric", action="store_true",
+                    help="parameters in symmetric memory; NVLS multicast pull fan-out (N > 1)")
     return ap.parse_args()
 
 
@@ -268,9 +270,25 @@ def run_llama(args, dist: Dist) -> dict:
             model = Llama(cfg).to(torch.bfloat16)
         model.init_weights(seed=0)
         model.train()
+    use_symm = args.symmetric and dist.world > 1
+    mc = 0
+    if use_symm:
+        import torch.distributed as tdist
+
+        from pslite_b200.parallel.ps_trainer import setup_symmetric_params, symmetric_layout
+
+        with torch.device("meta"):
+            shapes = list(Llama(cfg).parameters())
+        _, total = symmetric_layout(shapes)
+        plist = list(model.parameters()) if model is not None else None
+        flat, hdl, mc, peers, nbytes = setup_symmetric_params(plist, total, tdist.group.WORLD, dev,
+                                                              list(range(W)))
+        if server is not None:
+            server.set_symmetric(mc, peers, nbytes)
+    if ctx.is_worker:
         kv = C.KVWorker(0, 0)
         opt = PSWorkerOptimizer(model.parameters(), kv, S, W, ctx.worker_rank,
-                                grad_wire=args.grad_wire).attach()
+                                grad_wire=args.grad_wire, symmetric=use_symm).attach()
         opt.init_parameters(barrier=lambda: C.barrier(0, C.WORKER_GROUP, "worker"))
     dist.barrier()
     g = torch.Generator().manual_seed(1234 + dist.rank)
@@ -324,7 +342,9 @@ def run_llama(args, dist: Dist) -> dict:
         peak = 1386e12
         mfu = cfg.flops_per_token(T) * B * T / (ms / args.steps * 1e-3) / peak
     stats = {"server_updates": server.num_updates() if server else 0,
-             "server_fused_fanouts": server.num_fused_fanouts() if server else 0}
+             "server_fused_fanouts": server.num_fused_fanouts() if server else 0,
+             "server_multicast_fanouts": server.num_multicast_fanouts() if server else 0,
+             "multicast_available": bool(mc)}
     ctx.shutdown()
     return {
         "metric": METRIC_NAME["llama"], "value": value, "unit": "tokens/s",

@@ -251,7 +251,16 @@ struct SendOpts {
   float scale = 1.0f;
   /*! \brief cudaEvent_t the copy must wait for (producer of the values), or null */
   void* wait_event = nullptr;
+  /*!
+   * \brief pulls only: the destination is already known to the server under this name
+   *        (e.g. an offset inside a symmetric / multicast-bound parameter buffer), so the
+   *        van must not try to export it.
+   */
+  MemRef dest_mem;
 };
+
+/*! \brief MemRef::region value meaning "offset inside the job-wide symmetric buffer" */
+static const int32_t kSymmetricRegion = 0x40000000;
 
 /*! \brief meta + zero-copy payload segments */
 struct Message {

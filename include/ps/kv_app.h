@@ -156,6 +156,11 @@ class KVWorker : public SimpleApp {
             const Callback& cb = nullptr) {
     return Pull_(keys, vals, lens, cmd, cb);
   }
+  /*! \brief ZPull whose destination the server already knows as `opts.dest_mem` */
+  int ZPull(const SArray<Key>& keys, SArray<Val>* vals, SArray<int>* lens, int cmd,
+            const Callback& cb, const SendOpts& opts) {
+    return Pull_(keys, vals, lens, cmd, cb, opts);
+  }
 
   using SlicedKVs = std::vector<std::pair<bool, KVPairs<Val>>>;
   /*! \brief cuts `send` by `ranges`; sliced[i].first==false means "nothing for server i" */
@@ -168,7 +173,8 @@ class KVWorker : public SimpleApp {
 
  private:
   template <typename C, typename D>
-  int Pull_(const SArray<Key>& keys, C* vals, D* lens, int cmd, const Callback& cb);
+  int Pull_(const SArray<Key>& keys, C* vals, D* lens, int cmd, const Callback& cb,
+            const SendOpts& opts = SendOpts());
 
   void AddCallback(int timestamp, const Callback& cb) {
     if (!cb) return;
@@ -435,6 +441,7 @@ void KVWorker<Val>::Send(int timestamp, bool push, int cmd, KVPairs<Val>& kvs,
     msg.meta.codec = opts.codec;
     msg.meta.scale = opts.scale;
     msg.wait_event = opts.wait_event;
+    if (!push && opts.dest_mem.valid()) msg.meta.mem = opts.dest_mem;
     const SArray<Val> dest = part.vals;  // placement of the pull destination
     if (!push) part.vals.clear();
     if (part.keys.size()) {
@@ -487,7 +494,8 @@ void KVWorker<Val>::RunCallback(int timestamp) {
 
 template <typename Val>
 template <typename C, typename D>
-int KVWorker<Val>::Pull_(const SArray<Key>& keys, C* vals, D* lens, int cmd, const Callback& cb) {
+int KVWorker<Val>::Pull_(const SArray<Key>& keys, C* vals, D* lens, int cmd, const Callback& cb,
+                         const SendOpts& opts) {
   CHECK_NOTNULL(vals);
   const int ts = obj_->NewRequest(kServerGroup);
   AddCallback(ts, [this, ts, keys, vals, lens, cb]() mutable {
@@ -546,7 +554,7 @@ int KVWorker<Val>::Pull_(const SArray<Key>& keys, C* vals, D* lens, int cmd, con
   kvs.keys = keys;
   kvs.vals = kv_detail::ViewOf(vals);
   if (lens && !lens->empty()) kvs.lens = kv_detail::ViewOf(lens);
-  Send(ts, false, cmd, kvs);
+  Send(ts, false, cmd, kvs, opts);
   return ts;
 }
 

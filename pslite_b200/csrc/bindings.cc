@@ -102,15 +102,21 @@ class PyKVWorker {
     return kv_->ZPush(OneKey(key), vals, OneLen(vals.size()), cmd, cb, opts);
   }
 
-  int pull(uint64_t key, torch::Tensor t, int cmd) {
+  int pull(uint64_t key, torch::Tensor t, int cmd, int64_t symm_offset) {
     // the destination view must stay alive until the response lands: own it here
     auto* dst = new SArray<char>(ViewOf(t));
     auto* len = new SArray<int>(OneLen(dst->size()));
+    SendOpts opts;
+    if (symm_offset >= 0) {  // destination = offset inside the job-wide symmetric buffer
+      opts.dest_mem.region = kSymmetricRegion;
+      opts.dest_mem.offset = static_cast<uint64_t>(symm_offset);
+      opts.dest_mem.bytes = dst->size();
+    }
     py::gil_scoped_release nogil;
     return kv_->ZPull(OneKey(key), dst, len, cmd, [dst, len]() {
       delete dst;
       delete len;
-    });
+    }, opts);
   }
 
   void wait(int ts) {
@@ -305,6 +311,12 @@ class PyGpuServer {
     impl_.reset();
   }
   void set_lr(float lr) { impl_->SetLearningRate(lr); }
+  void set_symmetric(uint64_t mc_ptr, const std::vector<uint64_t>& peer_ptrs, uint64_t bytes) {
+    std::vector<void*> peers;
+    for (uint64_t p : peer_ptrs) peers.push_back(reinterpret_cast<void*>(p));
+    impl_->SetSymmetricParams(reinterpret_cast<void*>(mc_ptr), peers, bytes);
+  }
+  uint64_t num_multicast_fanouts() { return impl_->num_multicast_fanouts(); }
   uint64_t num_updates() { return impl_->num_updates(); }
   uint64_t num_fused_fanouts() { return impl_->num_fused_fanouts(); }
   size_t num_keys() { return impl_->num_keys(); }
@@ -402,7 +414,8 @@ PYBIND11_MODULE(_C, m) {
       .def("push", &PyKVWorker::push, py::arg("key"), py::arg("tensor"), py::arg("cmd") = 0,
            py::arg("codec") = 0, py::arg("scale") = 1.0f,
            py::arg("order_after_current_stream") = true)
-      .def("pull", &PyKVWorker::pull, py::arg("key"), py::arg("tensor"), py::arg("cmd") = 0)
+      .def("pull", &PyKVWorker::pull, py::arg("key"), py::arg("tensor"), py::arg("cmd") = 0,
+           py::arg("symm_offset") = -1)
       .def("wait", &PyKVWorker::wait)
       .def("wait_all", &PyKVWorker::wait_all)
       .def("push_pull_batch", &PyKVWorker::push_pull_batch, py::arg("keys"), py::arg("tensors"),
@@ -428,6 +441,9 @@ PYBIND11_MODULE(_C, m) {
            py::arg("eps") = 1e-8f, py::arg("weight_decay") = 0.0f, py::arg("grad_scale") = 1.0f,
            py::arg("fuse_pull") = true, py::arg("raw_grad") = "bf16", py::arg("max_ctas") = 0)
       .def("set_lr", &PyGpuServer::set_lr)
+      .def("set_symmetric", &PyGpuServer::set_symmetric, py::arg("mc_ptr"), py::arg("peer_ptrs"),
+           py::arg("bytes"))
+      .def("num_multicast_fanouts", &PyGpuServer::num_multicast_fanouts)
       .def("num_updates", &PyGpuServer::num_updates)
       .def("num_fused_fanouts", &PyGpuServer::num_fused_fanouts)
       .def("num_keys", &PyGpuServer::num_keys)
@@ -451,7 +467,8 @@ PYBIND11_MODULE(_C, m) {
   m.def("fused_update", [](std::vector<torch::Tensor> grads, int grad_format, torch::Tensor master,
                            torch::Tensor mom, torch::Tensor var, std::vector<torch::Tensor> outs,
                            const std::string& optimizer, float lr, float beta1, float beta2,
-                           float eps, float wd, int step, float grad_scale, int max_ctas) {
+                           float eps, float wd, int step, float grad_scale, int max_ctas,
+                           uint64_t mc_ptr) {
     ps_update_args a;
     memset(&a, 0, sizeof(a));
     a.n = static_cast<size_t>(master.numel());
@@ -465,6 +482,8 @@ PYBIND11_MODULE(_C, m) {
     a.num_outs = static_cast<int>(outs.size());
     for (size_t i = 0; i < outs.size(); ++i) a.outs[i] = outs[i].data_ptr();
     a.out_f32 = !outs.empty() && outs[0].scalar_type() == torch::kFloat32;
+    a.mc_out = reinterpret_cast<void*>(mc_ptr);
+    a.body_outs = mc_ptr ? std::min<int>(1, a.num_outs) : a.num_outs;
     ps_opt_params o;
     o.optimizer = optimizer == "sgd" ? PS_OPT_SGD : PS_OPT_ADAMW;
     o.lr = lr; o.beta1 = beta1; o.beta2 = beta2; o.eps = eps; o.weight_decay = wd;
@@ -476,5 +495,5 @@ PYBIND11_MODULE(_C, m) {
      py::arg("outs"), py::arg("optimizer") = "adamw", py::arg("lr") = 1e-3f,
      py::arg("beta1") = 0.9f, py::arg("beta2") = 0.95f, py::arg("eps") = 1e-8f,
      py::arg("weight_decay") = 0.0f, py::arg("step") = 1, py::arg("grad_scale") = 1.0f,
-     py::arg("max_ctas") = 0);
+     py::arg("max_ctas") = 0, py::arg("mc_ptr") = 0);
 }

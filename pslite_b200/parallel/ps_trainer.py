@@ -44,11 +44,48 @@ class PSTrainerStats:
     keys: int = 0
 
 
+def _round_up(n: int, m: int) -> int:
+    return (n + m - 1) // m * m
+
+
+def symmetric_layout(params) -> tuple[list[int], int]:
+    """Element offsets of every parameter inside the job-wide symmetric bf16 buffer
+    (each parameter starts on a 128-byte boundary) and the total element count."""
+    offs, cur = [], 0
+    for p in params:
+        offs.append(cur)
+        cur += _round_up(p.numel(), 64)
+    return offs, max(cur, 64)
+
+
+def setup_symmetric_params(params, total_elems: int, group, device, worker_ranks: list[int]):
+    """Move `params` (may be None on server-only ranks) into a symmetric-memory buffer that
+    every rank of `group` allocates identically, rendezvous, and return
+    (flat, multicast_ptr, peer_ptrs_of_workers, nbytes). With NVSwitch multicast support the
+    server's update kernel can then publish new parameters to ALL workers with one
+    multimem.st stream (NVLS) instead of one unicast stream per worker."""
+    import torch.distributed._symmetric_memory as symm_mem
+
+    flat = symm_mem.empty(total_elems, dtype=torch.bfloat16, device=device)
+    hdl = symm_mem.rendezvous(flat, group)
+    if params is not None:
+        offs, _ = symmetric_layout(params)
+        with torch.no_grad():
+            for p, off in zip(params, offs):
+                view = flat[off:off + p.numel()].view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+    mc = int(hdl.multicast_ptr) if getattr(hdl, "multicast_ptr", 0) else 0
+    peers = [int(hdl.buffer_ptrs[r]) for r in worker_ranks]
+    return flat, hdl, mc, peers, total_elems * 2
+
+
 class PSWorkerOptimizer:
     """Drop-in "optimizer" for a worker: hooks gradients, exposes step()/zero_grad()."""
 
     def __init__(self, params, kv, num_servers: int, num_workers: int, worker_rank: int,
-                 grad_wire: str = "fp8", chunk_elems: int = 32 << 20, app_barrier=None):
+                 grad_wire: str = "fp8", chunk_elems: int = 32 << 20, app_barrier=None,
+                 symmetric: bool = False):
         C = native()
         self._C = C
         self.kv = kv
@@ -64,6 +101,8 @@ class PSWorkerOptimizer:
         self._hooks = []
         self._barrier = app_barrier
         self.accumulate = False  # True on non-final micro-batches: keep grads local
+        # byte offset of every parameter in the symmetric buffer (see setup_symmetric_params)
+        self.symm_off = [o * 2 for o in symmetric_layout(self.params)[0]] if symmetric else None
         # chunk table
         self.chunks: list[list[_Chunk]] = []
         j = 0
@@ -107,9 +146,12 @@ class PSWorkerOptimizer:
             assert p.dtype == torch.bfloat16, "servers emit bf16 parameters"
             flat = p.data.view(-1)
             for c in per:
-                ts.append(self.kv.pull(c.key, flat[c.start:c.stop]))
+                ts.append(self.kv.pull(c.key, flat[c.start:c.stop], symm_offset=self._symm(c)))
         for t in ts:
             self.kv.wait(t)
+
+    def _symm(self, c: _Chunk) -> int:
+        return -1 if self.symm_off is None else self.symm_off[c.param_index] + c.start * 2
 
     # -- gradient hooks ---------------------------------------------------------------
     def attach(self):
@@ -140,7 +182,7 @@ class PSWorkerOptimizer:
         for c in self.chunks[i]:
             gs = gflat[c.start:c.stop]
             self._pending.append(self.kv.push(c.key, gs, cmd=self._C.CMD_GRAD, codec=codec, scale=1.0))
-            self._pending.append(self.kv.pull(c.key, pflat[c.start:c.stop]))
+            self._pending.append(self.kv.pull(c.key, pflat[c.start:c.stop], symm_offset=self._symm(c)))
             self.stats.pushes += 1
             self.stats.pulls += 1
             self.stats.push_bytes_wire += self._C.wire_bytes(codec, gs.numel() * gs.element_size())

@@ -83,6 +83,13 @@ typedef struct {
   int num_outs;                        // bf16 destinations
   void* outs[PS_MAX_FANOUT];           // local copy and/or peer-mapped worker buffers
   int out_f32;                         // outs[] receive fp32 instead of bf16
+  /* NVLS: a multicast address (cuMulticast / symmetric memory) bound to the SAME offset of
+   * every worker's parameter buffer. When set, the 16-byte body stores go out as ONE
+   * multimem.st per vector (the switch replicates it to all workers) and only
+   * outs[0..body_outs) are written unicast in the body; the ragged tail (< 8 elements)
+   * still uses all of outs[]. */
+  void* mc_out;
+  int body_outs;
 } ps_update_args;
 
 /*! \brief fused dequant + W-way sum + optimizer + bf16 fan-out for one shard */

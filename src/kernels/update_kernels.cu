@@ -44,6 +44,8 @@ struct UpdateDev {
   float* m;
   float* v;
   void* outs[PS_MAX_FANOUT];
+  void* mc_out;     // NVLS multicast destination (bf16), or null
+  int body_outs;    // unicast outputs written in the vector body
 };
 
 __device__ __forceinline__ int4 ldg16(const void* p) {
@@ -75,6 +77,13 @@ __device__ __forceinline__ void stf4(float* p, const float4& v) {
 __device__ __forceinline__ void st16(void* p, const int4& v) {
   asm volatile("st.global.L1::no_allocate.v4.s32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x),
                "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
+}
+/*! one store, replicated by the NVSwitch to every GPU bound to the multicast object */
+__device__ __forceinline__ void multimem_st16(void* p, const int4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p),
+               "f"(__int_as_float(v.x)), "f"(__int_as_float(v.y)), "f"(__int_as_float(v.z)),
+               "f"(__int_as_float(v.w))
                : "memory");
 }
 __device__ __forceinline__ float2 bf2(uint32_t u) {
@@ -209,7 +218,7 @@ k_update(const UpdateDev a, const ps_opt_params o) {
     }
     if (OUT_F32) {
 #pragma unroll 1
-      for (int k = 0; k < a.num_outs; ++k) {
+      for (int k = 0; k < a.body_outs; ++k) {
         stf4(static_cast<float*>(a.outs[k]) + i * 8, p0);
         stf4(static_cast<float*>(a.outs[k]) + i * 8 + 4, p1);
       }
@@ -218,7 +227,8 @@ k_update(const UpdateDev a, const ps_opt_params o) {
       out.x = pk(p0.x, p0.y); out.y = pk(p0.z, p0.w);
       out.z = pk(p1.x, p1.y); out.w = pk(p1.z, p1.w);
 #pragma unroll 1
-      for (int k = 0; k < a.num_outs; ++k) st16(static_cast<char*>(a.outs[k]) + i * 16, out);
+      for (int k = 0; k < a.body_outs; ++k) st16(static_cast<char*>(a.outs[k]) + i * 16, out);
+      if (a.mc_out) multimem_st16(static_cast<char*>(a.mc_out) + i * 16, out);
     }
   }
   // ragged tail (< 8 elements) handled by the first threads of block 0
@@ -294,6 +304,9 @@ extern "C" int ps_launch_update(const ps_update_args* args, const ps_opt_params*
   d.master = args->master;
   d.m = args->m;
   d.v = args->v;
+  d.mc_out = args->out_f32 ? nullptr : args->mc_out;
+  d.body_outs = d.mc_out ? args->body_outs : args->num_outs;
+  if (d.body_outs < 0 || d.body_outs > args->num_outs) return cudaErrorInvalidValue;
   // 2 resident CTAs/SM x 148 keeps ~100 KB of loads in flight per SM
   const int grid = GridFor(args->n / 8 + 1, max_ctas, 4);
   const bool f32 = args->out_f32 != 0;
@@ -335,6 +348,8 @@ extern "C" int ps_launch_sum(float* out, const void* const* grads, int num_grads
   for (int i = 0; i < PS_MAX_FANIN; ++i) d.grads[i] = i < num_grads ? grads[i] : nullptr;
   for (int i = 0; i < PS_MAX_FANOUT; ++i) d.outs[i] = nullptr;
   d.master = d.m = d.v = nullptr;
+  d.mc_out = nullptr;
+  d.body_outs = 0;
   const int grid = GridFor(n / 8 + 1, 0, 4);
   if (fmt == PS_GRAD_BF16) k_sum<PS_GRAD_BF16><<<grid, kThreads, 0, st>>>(out, d, scale, accumulate);
   else if (fmt == PS_GRAD_FP8BLOCK)

@@ -68,6 +68,15 @@ void GpuServer::SetLearningRate(float lr) {
   cfg_.opt.lr = lr;
 }
 
+void GpuServer::SetSymmetricParams(void* mc_base, const std::vector<void*>& peer_bases,
+                                   size_t bytes) {
+  std::lock_guard<std::mutex> lk(mu_);
+  CHECK_EQ(peer_bases.size(), static_cast<size_t>(cfg_.num_workers));
+  mc_base_ = mc_base;
+  peer_bases_ = peer_bases;
+  symm_bytes_ = bytes;
+}
+
 size_t GpuServer::num_keys() {
   std::lock_guard<std::mutex> lk(mu_);
   return shards_.size();
@@ -201,6 +210,10 @@ void GpuServer::HandlePull(Shard* s, const KVMeta& req, const KVPairs<char>& /*d
 void* GpuServer::WorkerDest(const KVMeta& pull) {
   if (!pull.mem.valid()) return nullptr;
   const int rank = Postoffice::IDtoRank(pull.sender);
+  if (pull.mem.region == kSymmetricRegion) {
+    if (peer_bases_.empty() || pull.mem.offset + pull.mem.bytes > symm_bytes_) return nullptr;
+    return static_cast<char*>(peer_bases_[rank]) + pull.mem.offset;
+  }
   const int instance_id = po_->GroupWorkerRankToInstanceID(rank, instance_idx_);
   return po_->van()->ResolvePeerMem(instance_id, pull.mem);
 }
@@ -222,13 +235,25 @@ void GpuServer::MaybeRunRound(Key key, Shard* s) {
   a.outs[0] = s->param_bf16;
   a.num_outs = 1;
   std::vector<char> placed(s->waiting_pulls.size(), 0);
+  bool all_symmetric = mc_base_ != nullptr && static_cast<int>(s->waiting_pulls.size()) == W;
   for (size_t i = 0; i < s->waiting_pulls.size(); ++i) {
-    void* dst = WorkerDest(s->waiting_pulls[i]);
-    if (dst && a.num_outs < PS_MAX_FANOUT &&
-        s->waiting_pulls[i].mem.bytes >= s->n * 2 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    const KVMeta& pull = s->waiting_pulls[i];
+    void* dst = WorkerDest(pull);
+    if (dst && a.num_outs < PS_MAX_FANOUT && pull.mem.bytes >= s->n * 2 &&
+        (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
       a.outs[a.num_outs++] = dst;
       placed[i] = 1;
     }
+    all_symmetric = all_symmetric && placed[i] && pull.mem.region == kSymmetricRegion &&
+                    pull.mem.offset == s->waiting_pulls[0].mem.offset;
+  }
+  a.body_outs = a.num_outs;
+  if (all_symmetric) {
+    // every worker wants this shard at the same symmetric offset: one multicast store
+    // stream replaces the W unicast streams (outs[1..] only serve the ragged tail)
+    a.mc_out = static_cast<char*>(mc_base_) + s->waiting_pulls[0].mem.offset;
+    a.body_outs = 1;
+    ++mcast_;
   }
   ps_opt_params o = cfg_.opt;
   ++s->step;
@@ -263,7 +288,18 @@ void GpuServer::ServePullFromLocal(Key key, Shard* s, const KVMeta& req) {
   KVPairs<char> res;
   res.keys = OneKey(key);
   res.lens = OneLen(s->n * 2);
-  if (req.mem.valid()) {
+  if (req.mem.valid() && req.mem.region == kSymmetricRegion) {
+    // symmetric destination: the van knows no region for it, so place the values here
+    void* dst = WorkerDest(req);
+    CHECK(dst) << "symmetric pull without SetSymmetricParams";
+    CHECK_EQ(ps_launch_copy(dst, s->param_bf16, s->n * 2, PS_CODEC_RAW, 1.f, cfg_.max_ctas,
+                            reinterpret_cast<ps_stream_t>(stream_)), 0);
+    res.vals = SArray<char>(static_cast<char*>(s->param_bf16), s->n * 2, GPU, dev_, GPU, dev_);
+    SendOpts placed;
+    placed.codec = kCodecPlaced;
+    server_->Response(req, res, placed);
+    return;
+  } else if (req.mem.valid()) {
     // the van's copy kernel (same stream, so ordered after any update) writes it over
     res.vals = SArray<char>(static_cast<char*>(s->param_bf16), s->n * 2, GPU, dev_, GPU, dev_);
   } else {

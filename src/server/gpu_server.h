@@ -69,6 +69,17 @@ class GpuServer {
   ~GpuServer();
 
   void SetLearningRate(float lr);
+  /*!
+   * \brief NVLS pull fan-out. Every worker keeps its parameters in a buffer that is
+   *        symmetric across the job (same layout at the same offset) and bound to one
+   *        multicast object. `mc_base` is this process's mapping of the multicast address,
+   *        `peer_bases[w]` its unicast mapping of worker w's buffer. Pull requests that
+   *        name their destination as MemRef{kSymmetricRegion, offset} are then answered by
+   *        ONE multimem.st stream from the update kernel instead of W unicast streams.
+   */
+  void SetSymmetricParams(void* mc_base, const std::vector<void*>& peer_bases, size_t bytes);
+  /*! \brief update kernels whose fan-out went through the multicast address */
+  uint64_t num_multicast_fanouts() const { return mcast_.load(); }
   /*! \brief optimizer steps applied, summed over keys */
   uint64_t num_updates() const { return updates_.load(); }
   /*! \brief update kernels whose destinations included worker buffers (fused pull replies) */
@@ -123,6 +134,10 @@ class GpuServer {
   std::unordered_map<Key, Shard> shards_;
   std::atomic<uint64_t> updates_{0};
   std::atomic<uint64_t> fused_{0};
+  std::atomic<uint64_t> mcast_{0};
+  void* mc_base_ = nullptr;
+  std::vector<void*> peer_bases_;
+  size_t symm_bytes_ = 0;
 };
 
 }  // namespace ps

@@ -121,7 +121,8 @@ class OneSidedVan : public TcpVan {
     }
     if (msg.meta.request && !msg.meta.push && msg.meta.addr != 0 &&
         domain_->Handles(msg.meta.src_dev_type, reinterpret_cast<void*>(msg.meta.addr))) {
-      AttachPullDestination(&msg);
+      // a caller-named destination (symmetric buffer) needs no export / announcement
+      if (!msg.meta.mem.valid()) AttachPullDestination(&msg);
       return Ordered(msg, Ticket());
     }
     if (!msg.meta.request && !msg.meta.push && msg.meta.mem.valid() && has_vals) {

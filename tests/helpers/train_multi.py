@@ -14,11 +14,13 @@ import torch.distributed as dist  # noqa: E402
 import pslite_b200  # noqa: E402
 from pslite_b200.models.llama import Llama, LlamaConfig  # noqa: E402
 from pslite_b200.parallel.launch import init_ps  # noqa: E402
-from pslite_b200.parallel.ps_trainer import PSWorkerOptimizer  # noqa: E402
+from pslite_b200.parallel.ps_trainer import (PSWorkerOptimizer, setup_symmetric_params,  # noqa: E402
+                                              symmetric_layout)
 
 
 def main():
     topo, wire, steps = sys.argv[1], sys.argv[2], int(sys.argv[3])
+    symmetric = len(sys.argv) > 4 and sys.argv[4] == "symm"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     use_cuda = torch.cuda.is_available()
@@ -37,14 +39,29 @@ def main():
     ok = True
     checksum = torch.zeros(1, dtype=torch.float64)
     losses = []
+    cfg = LlamaConfig.tiny()
+    model = None
     if ctx.is_worker:
-        cfg = LlamaConfig.tiny()
         with torch.device(dev):
             model = Llama(cfg).to(torch.bfloat16)
         model.init_weights(seed=3)
+    mcast_info = ""
+    if symmetric:
+        # every rank (servers too) allocates the same symmetric buffer; workers move their
+        # parameters into it; servers learn the multicast + peer addresses
+        with torch.device("meta"):
+            shapes = [p for p in Llama(cfg).parameters()]
+        _, total = symmetric_layout(shapes)
+        plist = list(model.parameters()) if model is not None else None
+        flat, hdl, mc, peers, nbytes = setup_symmetric_params(plist, total, dist.group.WORLD, dev,
+                                                              list(range(W)))
+        mcast_info = f" multicast_ptr={'yes' if mc else 'NO'}"
+        if server is not None:
+            server.set_symmetric(mc, peers, nbytes)
+    if ctx.is_worker:
         kv = C.KVWorker(0, 0)
         opt = PSWorkerOptimizer(model.parameters(), kv, S, W, ctx.worker_rank, grad_wire=wire,
-                                chunk_elems=1 << 14).attach()
+                                chunk_elems=1 << 14, symmetric=symmetric).attach()
         opt.init_parameters(barrier=lambda: C.barrier(0, C.WORKER_GROUP, "worker"))
         g = torch.Generator(device=dev).manual_seed(100 + ctx.worker_rank)
         tok = torch.randint(0, cfg.vocab_size, (2, 65), device=dev, generator=g)
@@ -64,7 +81,8 @@ def main():
     same = all(abs(x - wsums[0]) < 1e-9 for x in wsums)
     print(f"rank {rank}: losses {['%.3f' % l for l in losses[:2]]}..{['%.3f' % l for l in losses[-2:]]} "
           f"checksums_equal={same} updates={server.num_updates() if server else 0} "
-          f"fused={server.num_fused_fanouts() if server else 0}", flush=True)
+          f"fused={server.num_fused_fanouts() if server else 0} "
+          f"mcast={server.num_multicast_fanouts() if server else 0}{mcast_info}", flush=True)
     ok = ok and same
     flag = torch.tensor([1.0 if ok else 0.0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=gloo)
