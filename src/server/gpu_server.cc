@@ -59,7 +59,6 @@ GpuServer::~GpuServer() {
     cudaFree(kv.second.master);
     cudaFree(kv.second.m);
     cudaFree(kv.second.v);
-    cudaFree(kv.second.param_bf16);
   }
 }
 
@@ -85,7 +84,7 @@ size_t GpuServer::num_keys() {
 size_t GpuServer::state_bytes() {
   std::lock_guard<std::mutex> lk(mu_);
   size_t b = 0;
-  for (auto& kv : shards_) b += kv.second.n * 14;
+  for (auto& kv : shards_) b += kv.second.n * 12;
   return b;
 }
 
@@ -127,12 +126,10 @@ GpuServer::Shard* GpuServer::GetShard(Key key, size_t n) {
   GS_CUDA(cudaMalloc(&s.master, n * 4));
   GS_CUDA(cudaMalloc(&s.m, n * 4));
   GS_CUDA(cudaMalloc(&s.v, n * 4));
-  GS_CUDA(cudaMalloc(&s.param_bf16, n * 2 + 16));
   cudaStream_t st = static_cast<cudaStream_t>(stream_);
   GS_CUDA(cudaMemsetAsync(s.master, 0, n * 4, st));
   GS_CUDA(cudaMemsetAsync(s.m, 0, n * 4, st));
   GS_CUDA(cudaMemsetAsync(s.v, 0, n * 4, st));
-  GS_CUDA(cudaMemsetAsync(s.param_bf16, 0, n * 2, st));
   s.slots.assign(cfg_.num_workers, nullptr);
   s.pushed.assign(cfg_.num_workers, 0);
   return &s;
@@ -170,8 +167,6 @@ void GpuServer::HandleInit(Shard* s, const KVMeta& req, const KVPairs<char>& dat
     }
     CHECK_EQ(ps_launch_decode(s->master, src, s->n, f32 ? PS_GRAD_F32 : PS_GRAD_BF16,
                               reinterpret_cast<ps_stream_t>(stream_)), 0);
-    CHECK_EQ(ps_launch_copy(s->param_bf16, s->master, s->n * 4, PS_CODEC_F32_TO_BF16, 1.f,
-                            cfg_.max_ctas, reinterpret_cast<ps_stream_t>(stream_)), 0);
     if (staged) {
       GS_CUDA(cudaStreamSynchronize(st));
       cudaFree(staged);
@@ -232,8 +227,7 @@ void GpuServer::MaybeRunRound(Key key, Shard* s) {
   a.master = s->master;
   a.m = s->m;
   a.v = s->v;
-  a.outs[0] = s->param_bf16;
-  a.num_outs = 1;
+  a.num_outs = 0;  // no server-side bf16 copy: late pulls are cast from the fp32 master on demand
   std::vector<char> placed(s->waiting_pulls.size(), 0);
   bool all_symmetric = mc_base_ != nullptr && static_cast<int>(s->waiting_pulls.size()) == W;
   for (size_t i = 0; i < s->waiting_pulls.size(); ++i) {
@@ -252,7 +246,7 @@ void GpuServer::MaybeRunRound(Key key, Shard* s) {
     // every worker wants this shard at the same symmetric offset: one multicast store
     // stream replaces the W unicast streams (outs[1..] only serve the ragged tail)
     a.mc_out = static_cast<char*>(mc_base_) + s->waiting_pulls[0].mem.offset;
-    a.body_outs = 1;
+    a.body_outs = 0;
     ++mcast_;
   }
   ps_opt_params o = cfg_.opt;
@@ -263,7 +257,7 @@ void GpuServer::MaybeRunRound(Key key, Shard* s) {
   }
   CHECK_EQ(ps_launch_update(&a, &o, cfg_.max_ctas, reinterpret_cast<ps_stream_t>(stream_)), 0);
   ++updates_;
-  if (a.num_outs > 1) ++fused_;
+  if (a.num_outs > 0) ++fused_;
 
   SendOpts placed_opts;
   placed_opts.codec = kCodecPlaced;
@@ -272,7 +266,8 @@ void GpuServer::MaybeRunRound(Key key, Shard* s) {
     if (placed[i]) {
       KVPairs<char> res;
       res.keys = OneKey(key);
-      res.vals = SArray<char>(static_cast<char*>(s->param_bf16), s->n * 2, GPU, dev_, GPU, dev_);
+      // the values are already in the worker's buffer; `vals` only conveys their size
+      res.vals = SArray<char>(reinterpret_cast<char*>(s->master), s->n * 2, GPU, dev_, GPU, dev_);
       res.lens = OneLen(s->n * 2);
       server_->Response(pull, res, placed_opts);
     } else {
@@ -288,28 +283,31 @@ void GpuServer::ServePullFromLocal(Key key, Shard* s, const KVMeta& req) {
   KVPairs<char> res;
   res.keys = OneKey(key);
   res.lens = OneLen(s->n * 2);
-  if (req.mem.valid() && req.mem.region == kSymmetricRegion) {
-    // symmetric destination: the van knows no region for it, so place the values here
-    void* dst = WorkerDest(req);
-    CHECK(dst) << "symmetric pull without SetSymmetricParams";
-    CHECK_EQ(ps_launch_copy(dst, s->param_bf16, s->n * 2, PS_CODEC_RAW, 1.f, cfg_.max_ctas,
-                            reinterpret_cast<ps_stream_t>(stream_)), 0);
-    res.vals = SArray<char>(static_cast<char*>(s->param_bf16), s->n * 2, GPU, dev_, GPU, dev_);
+  ps_stream_t st = reinterpret_cast<ps_stream_t>(stream_);
+  if (void* dst = WorkerDest(req)) {
+    // cast fp32 master -> bf16 straight into the worker's buffer (peer HBM); the kernel runs
+    // on the update stream, so it is ordered after any update of this shard
+    CHECK_GE(req.mem.bytes, s->n * 2) << "pull destination smaller than the shard";
+    CHECK_EQ(ps_launch_copy(dst, s->master, s->n * 4, PS_CODEC_F32_TO_BF16, 1.f, cfg_.max_ctas, st),
+             0);
+    res.vals = SArray<char>(reinterpret_cast<char*>(s->master), s->n * 2, GPU, dev_, GPU, dev_);
     SendOpts placed;
     placed.codec = kCodecPlaced;
     server_->Response(req, res, placed);
     return;
-  } else if (req.mem.valid()) {
-    // the van's copy kernel (same stream, so ordered after any update) writes it over
-    res.vals = SArray<char>(static_cast<char*>(s->param_bf16), s->n * 2, GPU, dev_, GPU, dev_);
-  } else {
-    // two-sided requester: stage through host memory
-    SArray<char> host(s->n * 2);
-    cudaStream_t st = static_cast<cudaStream_t>(stream_);
-    GS_CUDA(cudaMemcpyAsync(host.data(), s->param_bf16, s->n * 2, cudaMemcpyDeviceToHost, st));
-    GS_CUDA(cudaStreamSynchronize(st));
-    res.vals = host;
   }
+  CHECK(!req.mem.valid()) << "pull destination region unknown to this server";
+  // two-sided requester (TCP): cast into a scratch buffer and stage through host memory
+  void* scratch = nullptr;
+  GS_CUDA(cudaMalloc(&scratch, s->n * 2 + 16));
+  CHECK_EQ(ps_launch_copy(scratch, s->master, s->n * 4, PS_CODEC_F32_TO_BF16, 1.f, cfg_.max_ctas, st),
+           0);
+  SArray<char> host(s->n * 2);
+  cudaStream_t cst = static_cast<cudaStream_t>(stream_);
+  GS_CUDA(cudaMemcpyAsync(host.data(), scratch, s->n * 2, cudaMemcpyDeviceToHost, cst));
+  GS_CUDA(cudaStreamSynchronize(cst));
+  cudaFree(scratch);
+  res.vals = host;
   server_->Response(req, res);
 }
 
@@ -385,8 +383,6 @@ bool GpuServer::LoadCheckpoint(const std::string& path) {
       ok = ok && fread(buf.data(), 4, e.n, f) == e.n;
       GS_CUDA(cudaMemcpy(dst, buf.data(), e.n * 4, cudaMemcpyHostToDevice));
     }
-    CHECK_EQ(ps_launch_copy(s->param_bf16, s->master, s->n * 4, PS_CODEC_F32_TO_BF16, 1.f, 0,
-                            reinterpret_cast<ps_stream_t>(stream_)), 0);
   }
   GS_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream_)));
   fclose(f);

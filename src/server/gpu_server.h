@@ -15,8 +15,9 @@
  *     slots, runs AdamW / SGD on the fp32 state and stores bf16 parameters
  *     directly into every worker's parameter buffer through the peer mapping:
  *     push handler + optimizer + pull reply in a single memory-bound pass;
- *   - pulls that cannot be fused (late, or initial fetch) are served from the
- *     server's bf16 shard copy through the van's copy kernel.
+ *   - pulls that cannot be fused (late, or initial fetch) are cast from the fp32 master
+ *     straight into the worker's buffer by the copy kernel; the server keeps no bf16
+ *     copy of its shards (12 B of state per parameter).
  * The handler only enqueues work on the van's data stream and never blocks, so
  * it can run inline on the van thread (PS_DIRECT_DISPATCH=1).
  */
@@ -103,7 +104,6 @@ class GpuServer {
     float* master = nullptr;
     float* m = nullptr;
     float* v = nullptr;
-    void* param_bf16 = nullptr;   // local bf16 copy served to non-fused pulls
     bool initialized = false;
     int step = 0;
     int grad_format = PS_GRAD_BF16;

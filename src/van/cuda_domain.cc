@@ -44,6 +44,7 @@ class CudaDomain : public MemDomain {
     cudaStreamSynchronize(stream_);
     for (cudaEvent_t e : free_events_) cudaEventDestroy(e);
     for (auto& kv : imported_) cudaIpcCloseMemHandle(kv.second);
+    for (auto& a : arenas_) cudaFree(a->base);
     cudaStreamDestroy(stream_);
   }
   const char* name() const override { return "nvl"; }
@@ -52,15 +53,54 @@ class CudaDomain : public MemDomain {
 
   bool Handles(int device_type, const void* /*ptr*/) override { return device_type == GPU; }
 
+  /*!
+   * Landing slots come from large device arenas (PS_NVL_ARENA_MB each, default 1024) carved
+   * by an offset allocator: one CUDA IPC handle / peer mapping per arena instead of one per
+   * slot, and a slot can be returned and re-cut without invalidating any peer's mapping
+   * (cudaFree of memory a peer still has open is undefined). The reference's counterpart is
+   * the registered-memory MemoryAllocator, src/rdma_utils.h:75-140.
+   */
   void* Alloc(size_t bytes) override {
     PS_CUDA_CHECK(cudaSetDevice(dev_));
-    void* p = nullptr;
-    PS_CUDA_CHECK(cudaMalloc(&p, bytes));
-    return p;
+    const uint64_t want = AlignUp(bytes ? bytes : 1, 512);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      for (auto& a : arenas_) {
+        const uint64_t off = a->alloc.Alloc(want);
+        if (off != UINT64_MAX) return a->base + off;
+      }
+    }
+    const uint64_t chunk = static_cast<uint64_t>(GetEnv("PS_NVL_ARENA_MB", 1024)) << 20;
+    std::unique_ptr<DevArena> a(new DevArena());
+    a->size = std::max<uint64_t>(chunk, AlignUp(want, 2u << 20));
+    void* base = nullptr;
+    cudaError_t e = cudaMalloc(&base, a->size);
+    if (e != cudaSuccess && a->size > want) {  // little memory left: fall back to an exact fit
+      cudaGetLastError();
+      a->size = AlignUp(want, 2u << 20);
+      e = cudaMalloc(&base, a->size);
+    }
+    PS_CUDA_CHECK(e);
+    a->base = static_cast<char*>(base);
+    a->alloc.Reset(a->size, 512);
+    const uint64_t off = a->alloc.Alloc(want);
+    std::lock_guard<std::mutex> lk(mu_);
+    arenas_.push_back(std::move(a));
+    return arenas_.back()->base + off;
   }
   void Free(void* p) override {
     cudaSetDevice(dev_);
-    cudaFree(p);
+    // a kernel may still be reading the slot: drain the device before the bytes are re-cut
+    cudaDeviceSynchronize();
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto& a : arenas_) {
+      char* c = static_cast<char*>(p);
+      if (c >= a->base && c < a->base + a->size) {
+        a->alloc.Free(static_cast<uint64_t>(c - a->base));
+        return;
+      }
+    }
+    cudaFree(p);  // not ours (never happens for slots handed out by Alloc)
   }
 
   bool Export(const void* p, RegionDesc* out) override {
@@ -184,6 +224,12 @@ class CudaDomain : public MemDomain {
     return e;
   }
 
+  struct DevArena {
+    char* base = nullptr;
+    uint64_t size = 0;
+    ArenaAllocator alloc;
+  };
+  std::vector<std::unique_ptr<DevArena>> arenas_;
   int dev_;
   int max_ctas_ = 0;
   cudaStream_t stream_ = nullptr;

@@ -163,6 +163,11 @@ class OneSidedVan : public TcpVan {
   };
   using PeerKey = std::pair<int, uint64_t>;
 
+  /*! \brief a slot more than 1.5x (+4 KB) larger than what is pushed now is re-made to size */
+  static bool Oversized(uint64_t capacity, uint64_t bytes) {
+    return capacity > bytes + bytes / 2 + 4096;
+  }
+
   static size_t DataTypeSize(DataType t) {
     switch (t) {
       case INT16: case UINT16: return 2;
@@ -232,8 +237,11 @@ class OneSidedVan : public TcpVan {
     std::unique_lock<std::mutex> lk(rv_mu_);
     const PeerKey pk(recver, key);
     auto it = push_slots_.find(pk);
-    if (it != push_slots_.end() && it->second.capacity >= bytes) return it->second;
-    push_slots_.erase(pk);
+    if (it != push_slots_.end() && it->second.capacity >= bytes &&
+        !Oversized(it->second.capacity, bytes)) {
+      return it->second;
+    }
+    push_slots_.erase(pk);  // too small, or far too large (e.g. bf16 init, then fp8 gradients)
     lk.unlock();
     Message req;
     req.meta.recver = recver;
@@ -265,9 +273,14 @@ class OneSidedVan : public TcpVan {
         CHECK_GE(reg->second.size(), bytes) << "registered buffer smaller than the push";
         ptr = reg->second.data();
         cap = reg->second.size();
-      } else if (have != landing_.end() && have->second.second >= bytes) {
+      } else if (have != landing_.end() && have->second.second >= bytes &&
+                 !Oversized(have->second.second, bytes)) {
         ptr = have->second.first;
         cap = have->second.second;
+      } else if (have != landing_.end()) {
+        // wrong size: give the old slot back (Free synchronises with kernels still reading it)
+        domain_->Free(have->second.first);
+        landing_.erase(have);
       }
     }
     if (!ptr) {

@@ -47,3 +47,37 @@ def test_python_push_pull(native, van, nw, ns):
 def test_python_large_message_shm(native):
     rc, outs = run_cluster("shm", 1, 1, n_elems=2_000_000)
     assert rc == 0, "\n".join(f"[{r} rc={c}]\n{o[-1500:]}" for r, c, o in outs)
+
+
+def test_trainer_logic_on_cpu(native):
+    """PSWorkerOptimizer (hooks, chunked keys, init, sync rounds) against a Python SGD server."""
+    node = os.path.join(HERE, "helpers", "train_cpu_node.py")
+    port = str(free_port())
+    env = dict(os.environ)
+    env["PSLITE_NO_AUTOBUILD"] = "1"
+    nw, steps = 2, 5
+    procs = []
+    for role, count in (("scheduler", 1), ("server", 1), ("worker", nw)):
+        for _ in range(count):
+            procs.append((role, subprocess.Popen([sys.executable, node, role, str(nw), port, str(steps)],
+                                                 env=env, stdout=subprocess.PIPE,
+                                                 stderr=subprocess.STDOUT, text=True)))
+    outs = []
+    for role, p in procs:
+        try:
+            o, _ = p.communicate(timeout=180)
+        except subprocess.TimeoutExpired:
+            for _, q in procs:
+                q.kill()
+            o, _ = p.communicate()
+        outs.append((role, p.returncode, o))
+    assert all(c == 0 for _, c, _ in outs), "\n".join(f"[{r} rc={c}]\n{o[-2000:]}" for r, c, o in outs)
+    sums = []
+    for role, _, o in outs:
+        for line in o.splitlines():
+            if line.startswith("CHECKSUM"):
+                f = line.split()
+                sums.append((float(f[2]), float(f[4])))
+    assert len(sums) == nw
+    assert abs(sums[0][0] - sums[1][0]) < 1e-9          # all workers hold the same parameters
+    assert abs(sums[0][0] - sums[0][1]) < 5e-2          # and they match the local simulation
