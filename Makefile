@@ -35,7 +35,7 @@ CORE_OBJS := $(patsubst %.cc,$(BUILD)/%.o,$(CORE_SRCS))
 CU_OBJS := $(patsubst %.cu,$(BUILD)/%.o,$(CU_SRCS))
 LIB := $(BUILD)/libpslite.a
 
-APPS := $(BUILD)/test_benchmark $(BUILD)/kernel_bench $(BUILD)/test_kv_app $(BUILD)/test_simple_app $(BUILD)/test_connection $(BUILD)/test_ipc_benchmark $(BUILD)/test_benchmark_stress
+APPS := $(BUILD)/test_benchmark $(BUILD)/kernel_bench $(BUILD)/test_kv_app $(BUILD)/test_simple_app $(BUILD)/test_connection $(BUILD)/test_ipc_benchmark $(BUILD)/test_benchmark_stress $(BUILD)/test_recovery
 TESTS := $(patsubst cpp_tests/%.cc,$(BUILD)/cpp_tests/%,$(wildcard cpp_tests/*.cc))
 
 all: $(LIB) $(APPS) $(TESTS)

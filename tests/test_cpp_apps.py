@@ -122,3 +122,37 @@ def test_van_profiling_log(built_native_tree, tmp_path):
     assert rc == 0, out[-2000:]
     server_log = open(prefix + "_van_server").read().strip().splitlines()
     assert server_log and server_log[0].split("\t")[1] in ("server_van_recv_push", "server_van_recv_pull")
+
+
+def test_dead_node_is_replaced_by_late_registration(built_native_tree):
+    """heartbeats -> dead-node detection -> a late worker inherits the dead worker's id."""
+    import random
+    import time
+
+    app = os.path.join(built_native_tree, "test_recovery")
+    env = dict(os.environ)
+    env.update({"DMLC_NUM_SERVER": "1", "DMLC_NUM_WORKER": "2", "DMLC_PS_ROOT_URI": "127.0.0.1",
+                "DMLC_PS_ROOT_PORT": str(21000 + random.randrange(10000)), "DMLC_NODE_HOST": "127.0.0.1",
+                "PS_HEARTBEAT_INTERVAL": "1", "PS_HEARTBEAT_TIMEOUT": "2"})
+    env.pop("DMLC_RANK", None)
+
+    def spawn(role, **extra):
+        e = dict(env, DMLC_ROLE=role, **extra)
+        return subprocess.Popen([app], env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+
+    procs = [spawn("scheduler"), spawn("server"), spawn("worker"), spawn("worker", RECOVERY_CRASH="1")]
+    time.sleep(5)  # > heartbeat timeout: the crashed worker is now considered dead
+    procs.append(spawn("worker", RECOVERY_LATE="1"))
+    outs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=60)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            o, _ = p.communicate()
+        outs.append(o)
+    joined = "\n".join(outs)
+    assert "test_recovery PASSED" in joined, joined[-4000:]
+    assert "recovery worker adopted rank" in joined  # whichever rank the dead worker had
+    assert all(p.returncode == 0 for p in procs), [p.returncode for p in procs]
