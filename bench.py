@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--grad-wire", default="fp8", choices=["fp8", "bf16"])
     ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "llama-1b", "tiny"])
     ap.add_argument("--ckpt-layers", type=int, default=-1)
+    ap.add_argument("--attn-backend", default="auto", choices=["auto", "cudnn", "flash", "efficient", "math"])
     ap.add_argument("--symmetric", action="store_true",
                     help="parameters in symmetric memory; NVLS multicast pull fan-out (N > 1)")
     return ap.parse_args()
@@ -263,6 +264,7 @@ def run_llama(args, dist: Dist) -> dict:
         cfg = LlamaConfig.tiny(max_seq_len=args.seq_len)
     if args.ckpt_layers >= 0:
         cfg.ckpt_layers = args.ckpt_layers
+    cfg.attn_backend = args.attn_backend
     B, T = args.micro_batch, args.seq_len
     model = opt = kv = None
     if ctx.is_worker:

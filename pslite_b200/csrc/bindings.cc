@@ -21,6 +21,7 @@
 #include <mutex>
 #include <unordered_map>
 
+#include "kernels/model_kernels.h"
 #include "kernels/ps_kernels.h"
 #include "ps/ps.h"
 #include "server/gpu_server.h"
@@ -451,6 +452,54 @@ PYBIND11_MODULE(_C, m) {
       .def("save", &PyGpuServer::save)
       .def("load", &PyGpuServer::load)
       .def("read_master", &PyGpuServer::read_master);
+
+  // ---- fused Llama-block kernels (see pslite_b200/ops/fused.py for the autograd wrappers) ----
+  m.def("rope_split", [](const torch::Tensor& qkv, const torch::Tensor& cos, const torch::Tensor& sin,
+                         int n_heads, int n_kv, int hd) {
+    TORCH_CHECK(qkv.is_cuda() && qkv.is_contiguous() && qkv.scalar_type() == torch::kBFloat16);
+    TORCH_CHECK(cos.scalar_type() == torch::kFloat32 && cos.is_contiguous() && sin.is_contiguous());
+    const int64_t B = qkv.size(0), S = qkv.size(1);
+    TORCH_CHECK(qkv.size(2) == static_cast<int64_t>(n_heads + 2 * n_kv) * hd && cos.size(0) >= S);
+    auto q = torch::empty({B, S, n_heads, hd}, qkv.options());
+    auto k = torch::empty({B, S, n_kv, hd}, qkv.options());
+    auto v = torch::empty({B, S, n_kv, hd}, qkv.options());
+    CheckRc(ps_launch_rope_split(qkv.data_ptr(), q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                 cos.data_ptr<float>(), sin.data_ptr<float>(),
+                                 static_cast<size_t>(B * S), static_cast<int>(S), n_heads, n_kv, hd,
+                                 CurrentStream(qkv)), "rope_split");
+    return std::make_tuple(q, k, v);
+  });
+  m.def("rope_merge_bwd", [](const torch::Tensor& dq, const torch::Tensor& dk, const torch::Tensor& dv,
+                             const torch::Tensor& cos, const torch::Tensor& sin, int n_heads, int n_kv,
+                             int hd) {
+    TORCH_CHECK(dq.is_contiguous() && dk.is_contiguous() && dv.is_contiguous());
+    const int64_t B = dq.size(0), S = dq.size(1);
+    auto dqkv = torch::empty({B, S, static_cast<int64_t>(n_heads + 2 * n_kv) * hd}, dq.options());
+    CheckRc(ps_launch_rope_merge_bwd(dq.data_ptr(), dk.data_ptr(), dv.data_ptr(), dqkv.data_ptr(),
+                                     cos.data_ptr<float>(), sin.data_ptr<float>(),
+                                     static_cast<size_t>(B * S), static_cast<int>(S), n_heads, n_kv,
+                                     hd, CurrentStream(dq)), "rope_merge_bwd");
+    return dqkv;
+  });
+  m.def("swiglu_fwd", [](const torch::Tensor& gu) {
+    TORCH_CHECK(gu.is_cuda() && gu.is_contiguous() && gu.scalar_type() == torch::kBFloat16);
+    const int64_t f = gu.size(-1) / 2;
+    auto sizes = gu.sizes().vec();
+    sizes.back() = f;
+    auto out = torch::empty(sizes, gu.options());
+    CheckRc(ps_launch_swiglu_fwd(gu.data_ptr(), out.data_ptr(), static_cast<size_t>(gu.numel() / (2 * f)),
+                                 static_cast<int>(f), CurrentStream(gu)), "swiglu_fwd");
+    return out;
+  });
+  m.def("swiglu_bwd", [](const torch::Tensor& gu, const torch::Tensor& dout) {
+    TORCH_CHECK(gu.is_contiguous() && dout.is_contiguous());
+    const int64_t f = gu.size(-1) / 2;
+    auto dgu = torch::empty_like(gu);
+    CheckRc(ps_launch_swiglu_bwd(gu.data_ptr(), dout.data_ptr(), dgu.data_ptr(),
+                                 static_cast<size_t>(gu.numel() / (2 * f)), static_cast<int>(f),
+                                 CurrentStream(gu)), "swiglu_bwd");
+    return dgu;
+  });
 
   // ---- raw kernel entry points (numerics tests, standalone use) ----
   m.def("copy_codec", [](torch::Tensor dst, const torch::Tensor& src, int codec, float scale,

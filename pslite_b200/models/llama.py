@@ -33,6 +33,8 @@ class LlamaConfig:
     max_seq_len: int = 8192
     ckpt_layers: int = 32          # how many (leading) layers recompute in backward
     loss_chunk: int = 2048         # tokens per LM-head / cross-entropy chunk
+    attn_backend: str = "auto"     # auto | cudnn | flash | efficient | math (PyTorch SDPA backends)
+    fused_ops: bool = True         # own RoPE-split / SwiGLU kernels on CUDA (pslite_b200.ops.fused)
 
     @staticmethod
     def llama3_8b(**kw) -> "LlamaConfig":
@@ -86,9 +88,25 @@ class RMSNorm(nn.Module):
         return F.rms_norm(x, (x.shape[-1],), self.weight, self.eps)
 
 
+def _sdpa_context(backend: str):
+    """Restrict PyTorch SDPA to one backend (cuDNN's fused attention is the tcgen05 path on
+    Blackwell; the bundled flash kernels are the sm_80-era mma.sync ones)."""
+    import contextlib
+
+    if backend == "auto":
+        return contextlib.nullcontext()
+    from torch.nn.attention import SDPBackend, sdpa_kernel
+
+    table = {"cudnn": SDPBackend.CUDNN_ATTENTION, "flash": SDPBackend.FLASH_ATTENTION,
+             "efficient": SDPBackend.EFFICIENT_ATTENTION, "math": SDPBackend.MATH}
+    return sdpa_kernel([table[backend]])
+
+
 class Attention(nn.Module):
     def __init__(self, cfg: LlamaConfig):
         super().__init__()
+        self.backend = cfg.attn_backend
+        self.fused = cfg.fused_ops
         self.n_heads, self.n_kv = cfg.n_heads, cfg.n_kv_heads
         self.hd = cfg.dim // cfg.n_heads
         self.wqkv = nn.Linear(cfg.dim, (cfg.n_heads + 2 * cfg.n_kv_heads) * self.hd, bias=False)
@@ -97,11 +115,19 @@ class Attention(nn.Module):
     def forward(self, x, cos, sin):
         B, S, _ = x.shape
         qkv = self.wqkv(x)
-        q, k, v = qkv.split([self.n_heads * self.hd, self.n_kv * self.hd, self.n_kv * self.hd], dim=-1)
-        q = apply_rope(q.view(B, S, self.n_heads, self.hd), cos, sin).transpose(1, 2)
-        k = apply_rope(k.view(B, S, self.n_kv, self.hd), cos, sin).transpose(1, 2)
-        v = v.view(B, S, self.n_kv, self.hd).transpose(1, 2)
-        o = F.scaled_dot_product_attention(q, k, v, is_causal=True, enable_gqa=self.n_kv != self.n_heads)
+        if self.fused and qkv.is_cuda:
+            from ..ops.fused import rope_split
+
+            q, k, v = rope_split(qkv, cos, sin, self.n_heads, self.n_kv, self.hd)
+            q, k, v = q.transpose(1, 2), k.transpose(1, 2), v.transpose(1, 2)
+        else:
+            q, k, v = qkv.split([self.n_heads * self.hd, self.n_kv * self.hd, self.n_kv * self.hd], dim=-1)
+            q = apply_rope(q.view(B, S, self.n_heads, self.hd), cos, sin).transpose(1, 2)
+            k = apply_rope(k.view(B, S, self.n_kv, self.hd), cos, sin).transpose(1, 2)
+            v = v.view(B, S, self.n_kv, self.hd).transpose(1, 2)
+        with _sdpa_context(self.backend):
+            o = F.scaled_dot_product_attention(q, k, v, is_causal=True,
+                                               enable_gqa=self.n_kv != self.n_heads)
         return self.wo(o.transpose(1, 2).reshape(B, S, -1))
 
 
@@ -110,9 +136,15 @@ class MLP(nn.Module):
         super().__init__()
         self.w13 = nn.Linear(cfg.dim, 2 * cfg.ffn_dim, bias=False)  # gate and up fused
         self.w2 = nn.Linear(cfg.ffn_dim, cfg.dim, bias=False)
+        self.fused = cfg.fused_ops
 
     def forward(self, x):
-        g, u = self.w13(x).chunk(2, dim=-1)
+        gu = self.w13(x)
+        if self.fused and gu.is_cuda:
+            from ..ops.fused import swiglu
+
+            return self.w2(swiglu(gu))
+        g, u = gu.chunk(2, dim=-1)
         return self.w2(F.silu(g) * u)
 
 

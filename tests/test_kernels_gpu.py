@@ -118,3 +118,40 @@ def test_fused_sgd_update(native):
     torch.cuda.synchronize()
     ref = p - 0.1 * g.float()
     assert torch.allclose(pk, ref, rtol=1e-6, atol=1e-6)
+
+
+def test_fused_rope_split_matches_reference(native):
+    _require_cuda()
+    from pslite_b200.models.llama import precompute_rope
+    from pslite_b200.ops.fused import rope_split, rope_split_reference
+
+    B, S, H, KV, D = 2, 48, 8, 2, 64
+    cos, sin = precompute_rope(D, 64, 500000.0, "cuda")
+    qkv = torch.randn(B, S, (H + 2 * KV) * D, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    qkv_ref = qkv.detach().clone().requires_grad_(True)
+    q, k, v = rope_split(qkv, cos, sin, H, KV, D)
+    qr, kr, vr = rope_split_reference(qkv_ref, cos, sin, H, KV, D)
+    assert torch.allclose(q.float(), qr.float(), atol=2e-2, rtol=2e-2)
+    assert torch.allclose(k.float(), kr.float(), atol=2e-2, rtol=2e-2)
+    assert torch.equal(v, vr)
+    gq, gk, gv = torch.randn_like(q), torch.randn_like(k), torch.randn_like(v)
+    (q * gq).sum().add((k * gk).sum()).add((v * gv).sum()).backward()
+    (qr * gq).sum().add((kr * gk).sum()).add((vr * gv).sum()).backward()
+    assert torch.allclose(qkv.grad.float(), qkv_ref.grad.float(), atol=3e-2, rtol=3e-2)
+
+
+def test_fused_swiglu_matches_reference(native):
+    _require_cuda()
+    from pslite_b200.ops.fused import swiglu, swiglu_reference
+
+    gu = (torch.randn(3, 40, 2 * 256, device="cuda") * 2).to(torch.bfloat16).requires_grad_(True)
+    gu_ref = gu.detach().clone().float().requires_grad_(True)
+    out = swiglu(gu)
+    g, u = gu_ref.chunk(2, dim=-1)
+    ref = torch.nn.functional.silu(g) * u
+    assert torch.allclose(out.float(), ref, atol=2e-2, rtol=2e-2)
+    assert torch.allclose(out.float(), swiglu_reference(gu.detach()).float(), atol=2e-2, rtol=2e-2)
+    d = torch.randn_like(out)
+    out.backward(d)
+    ref.backward(d.float())
+    assert torch.allclose(gu.grad.float(), gu_ref.grad, atol=3e-2, rtol=3e-2)
