@@ -343,6 +343,7 @@ def run_llama(args, dist: Dist) -> dict:
     if ctx.is_worker:
         peak = 1386e12
         mfu = cfg.flops_per_token(T) * B * T / (ms / args.steps * 1e-3) / peak
+    peak_mem = round(torch.cuda.max_memory_allocated() / 2**30, 1)
     stats = {"server_updates": server.num_updates() if server else 0,
              "server_fused_fanouts": server.num_fused_fanouts() if server else 0,
              "server_multicast_fanouts": server.num_multicast_fanouts() if server else 0,
@@ -356,6 +357,7 @@ def run_llama(args, dist: Dist) -> dict:
                    "seq_len": T, "parallelism": f"ps-dp{W} ({W}w+{S}s {topo}), grad wire {args.grad_wire}, server AdamW",
                    "ckpt_layers": cfg.ckpt_layers, "l2": "per-step working set >> 126 MB L2"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "mfu_vs_sustained_bf16": mfu,
+        "peak_torch_mem_gb": peak_mem,
         "server": stats,
     }
 

@@ -36,11 +36,23 @@ class PSContext:
     scheduler: subprocess.Popen | None = None
 
     def shutdown(self):
+        """Normal end of the job: barrier with every node, stop the vans, reap the scheduler."""
         from .. import native
 
         native().finalize(0, self.role, True)
         if self.scheduler is not None:
-            self.scheduler.wait(timeout=60)
+            try:
+                self.scheduler.wait(timeout=60)
+            except subprocess.TimeoutExpired:
+                self.scheduler.kill()
+            self.scheduler = None
+
+    def abort(self):
+        """Error path: do not wait for peers; make sure no scheduler child outlives us (an
+        orphan would also keep inherited stdout/stderr pipes open for whoever waits on them)."""
+        if self.scheduler is not None:
+            self.scheduler.kill()
+            self.scheduler = None
 
 
 def _share_port(rank: int, world: int) -> int:
@@ -101,6 +113,9 @@ def init_ps(topology: str = "joint", van: str | None = None, extra_env: dict | N
         child_env["PS_VAN_TYPE"] = "zmq"  # the scheduler moves no payload
         sched = subprocess.Popen([sys.executable, "-m", "pslite_b200.parallel.scheduler"],
                                  env=child_env)
+        import atexit
+
+        atexit.register(lambda p=sched: p.poll() is None and p.kill())
     for k, v in env.items():
         C.set_env(k, str(v))
     preferred = wrank if is_worker else srank

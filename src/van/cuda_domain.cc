@@ -7,6 +7,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <map>
 #include <unordered_map>
 
 #include "kernels/ps_kernels.h"
@@ -104,6 +105,23 @@ class CudaDomain : public MemDomain {
   }
 
   bool Export(const void* p, RegionDesc* out) override {
+    {
+      // fast path: the pointer lies in an allocation that was exported before (one map
+      // lookup instead of two driver calls on every pull request)
+      std::lock_guard<std::mutex> lk(mu_);
+      auto it = ranges_.upper_bound(reinterpret_cast<uint64_t>(p));
+      if (it != ranges_.begin()) {
+        --it;
+        if (reinterpret_cast<uint64_t>(p) < it->first + it->second.first) {
+          memcpy(out->handle, &it->second.second, 64);
+          out->pid = static_cast<int32_t>(getpid());
+          out->dev = dev_;
+          out->base = it->first;
+          out->size = it->second.first;
+          return true;
+        }
+      }
+    }
     PS_CUDA_CHECK(cudaSetDevice(dev_));
     CUdeviceptr base = 0;
     size_t size = 0;
@@ -135,6 +153,7 @@ class CudaDomain : public MemDomain {
         return false;
       }
       it = exported_.emplace(base, h).first;
+      ranges_[static_cast<uint64_t>(base)] = std::make_pair(size, h);
     }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle must fit RegionDesc::handle");
     memcpy(out->handle, &it->second, 64);
@@ -201,6 +220,16 @@ class CudaDomain : public MemDomain {
     return t;
   }
 
+  bool Ready(Ticket t) override {
+    if (!t.event) return true;
+    cudaError_t e = cudaEventQuery(static_cast<cudaEvent_t>(t.event));
+    if (e == cudaErrorNotReady) {
+      cudaGetLastError();
+      return false;
+    }
+    return e == cudaSuccess;
+  }
+
   void Wait(Ticket t) override {
     if (!t.event) return;
     cudaEvent_t ev = static_cast<cudaEvent_t>(t.event);
@@ -236,6 +265,7 @@ class CudaDomain : public MemDomain {
   std::mutex mu_;
   std::vector<cudaEvent_t> free_events_;
   std::unordered_map<CUdeviceptr, cudaIpcMemHandle_t> exported_;
+  std::map<uint64_t, std::pair<size_t, cudaIpcMemHandle_t>> ranges_;  // base -> (size, handle)
   std::unordered_map<std::string, void*> imported_;
 };
 

@@ -118,6 +118,8 @@ class MemDomain {
                            void* wait_event, int src_device_type = UNK) = 0;
   /*! \brief block until the copy behind `t` is globally visible; recycles the ticket */
   virtual void Wait(Ticket t) = 0;
+  /*! \brief non-blocking: has the copy behind `t` completed? (does not recycle the ticket) */
+  virtual bool Ready(Ticket t) { return t.event == nullptr; }
   /*! \brief stream-like handle applications may enqueue their own work on (may be null) */
   virtual void* Stream() { return nullptr; }
 };

@@ -454,21 +454,44 @@ class OneSidedVan : public TcpVan {
 
   void CompletionLoop() {
     std::unique_lock<std::mutex> lk(cq_mu_);
+    std::vector<Pending> batch;
     for (;;) {
       cq_cv_.wait(lk, [this] { return cq_stop_ || !cq_.empty(); });
       if (cq_.empty()) {
         if (cq_stop_) return;
         continue;
       }
-      Pending p = std::move(cq_.front());
+      batch.clear();
+      batch.push_back(std::move(cq_.front()));
       cq_.pop_front();
       cq_busy_ = true;
       lk.unlock();
-      domain_->Wait(p.ticket);  // payload is globally visible after this
-      if (TcpVan::SendMsg(p.msg) < 0) {
-        LOG(WARNING) << "failed to send descriptor: " << p.msg.DebugString();
+      domain_->Wait(batch[0].ticket);  // payload is globally visible after this
+      // everything queued behind it whose copy has also finished leaves in the same flush:
+      // one sendmsg per peer instead of one per descriptor
+      lk.lock();
+      while (!cq_.empty() && batch.size() < 48 && domain_->Ready(cq_.front().ticket)) {
+        batch.push_back(std::move(cq_.front()));
+        cq_.pop_front();
       }
-      p.keep_alive.clear();
+      lk.unlock();
+      for (size_t i = 1; i < batch.size(); ++i) domain_->Wait(batch[i].ticket);  // recycle tickets
+      if (batch.size() == 1) {
+        if (TcpVan::SendMsg(batch[0].msg) < 0) {
+          LOG(WARNING) << "failed to send descriptor: " << batch[0].msg.DebugString();
+        }
+      } else {
+        // group by peer, preserving the per-peer order
+        std::map<int, std::vector<Message*>> per_peer;
+        for (Pending& p : batch) per_peer[p.msg.meta.recver].push_back(&p.msg);
+        for (auto& kv : per_peer) {
+          if (TcpVan::SendMsgBatch(kv.first, kv.second) < 0) {
+            LOG(WARNING) << "failed to send " << kv.second.size() << " descriptors to node "
+                         << kv.first;
+          }
+        }
+      }
+      batch.clear();  // drops the keep-alive references
       lk.lock();
       cq_busy_ = false;
     }

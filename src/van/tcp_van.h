@@ -31,6 +31,7 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <deque>
 #include <map>
@@ -277,6 +278,63 @@ class TcpVan : public Van {
     if (!SendAll(peer->fd, iov, niov)) {
       LOG(WARNING) << "failed to send to node " << recver << ": " << strerror(errno);
       return -1;
+    }
+    return static_cast<int>(std::min<size_t>(total, 0x7fffffff));
+  }
+
+  /*!
+   * \brief several messages for ONE peer in a single gathered sendmsg (frames back to back).
+   *        Used by the one-sided van to flush a backlog of descriptors with one system call.
+   */
+  int SendMsgBatch(int recver, const std::vector<Message*>& msgs) {
+    if (msgs.empty()) return 0;
+    if (msgs.size() == 1 || recver == my_node_.id) {
+      int total = 0;
+      for (Message* m : msgs) {
+        int n = SendMsg(*m);
+        if (n < 0) return -1;
+        total += n;
+      }
+      return total;
+    }
+    std::shared_ptr<Peer> peer;
+    {
+      std::lock_guard<std::mutex> lk(peers_mu_);
+      auto it = peers_.find(recver);
+      if (it == peers_.end()) return -1;
+      peer = it->second;
+    }
+    const size_t n = msgs.size();
+    std::vector<FrameHeader> hdrs(n);
+    std::vector<std::array<uint64_t, kMaxSegments>> lens(n);
+    std::vector<std::vector<char>> metas(n);
+    std::vector<struct iovec> iov;
+    iov.reserve(n * 6);
+    size_t total = 0;
+    for (size_t i = 0; i < n; ++i) {
+      Message& m = *msgs[i];
+      PackMeta(m.meta, &metas[i]);
+      const uint32_t nseg = static_cast<uint32_t>(m.data.size());
+      CHECK_LE(nseg, kMaxSegments);
+      hdrs[i] = {kFrameMagic, my_node_.id, recver, static_cast<uint32_t>(metas[i].size()), nseg, 0};
+      iov.push_back({&hdrs[i], sizeof(FrameHeader)});
+      if (nseg) iov.push_back({lens[i].data(), sizeof(uint64_t) * nseg});
+      iov.push_back({metas[i].data(), metas[i].size()});
+      for (uint32_t sgi = 0; sgi < nseg; ++sgi) {
+        lens[i][sgi] = m.data[sgi].size();
+        CHECK(lens[i][sgi] == 0 || !m.data[sgi].on_gpu()) << "TcpVan cannot send device memory";
+        if (lens[i][sgi]) iov.push_back({m.data[sgi].data(), m.data[sgi].size()});
+      }
+    }
+    for (auto& v : iov) total += v.iov_len;
+    std::lock_guard<std::mutex> lk(peer->mu);
+    if (peer->fd < 0) return -1;
+    // IOV_MAX is 1024 on Linux: flush in slices
+    size_t at = 0;
+    while (at < iov.size()) {
+      const int cnt = static_cast<int>(std::min<size_t>(512, iov.size() - at));
+      if (!SendAll(peer->fd, iov.data() + at, cnt)) return -1;
+      at += static_cast<size_t>(cnt);
     }
     return static_cast<int>(std::min<size_t>(total, 0x7fffffff));
   }

@@ -28,6 +28,6 @@ def test_smoke_entry():
         pytest.skip("no CUDA device")
     root = os.path.dirname(HERE)
     r = subprocess.run([sys.executable, "-c", "import __graft_entry__ as g; g.smoke()"], cwd=root,
-                       capture_output=True, text=True, timeout=600)
+                       capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "smoke ok" in r.stdout
