@@ -1,7 +1,7 @@
 /**
  * \file base.h
  * \brief Key type and the bit-OR-able node-group ids.
- * Parity: reference include/ps/base.h:11-25.
+ * Parity: reference include/ps/base.h:11-25 (same public names and values).
  */
 #ifndef PS_BASE_H_
 #define PS_BASE_H_
@@ -11,18 +11,25 @@
 
 namespace ps {
 
+/*! \brief keys are 64-bit unless the build asks for 32 (make USE_KEY32=1) */
 #if USE_KEY32
-using Key = uint32_t;
+typedef uint32_t Key;
 #else
-using Key = uint64_t;
+typedef uint64_t Key;
 #endif
-/*! \brief largest representable key; server key ranges partition [0, kMaxKey) */
-static const Key kMaxKey = std::numeric_limits<Key>::max();
 
-/*! \brief group ids are single bits so that groups compose with + or | */
-static const int kScheduler = 1;
-static const int kServerGroup = 2;
-static const int kWorkerGroup = 4;
+/*! \brief one past the largest key a server range can end at: ranges tile [0, kMaxKey) */
+constexpr Key kMaxKey = std::numeric_limits<Key>::max();
+
+/*!
+ * \brief node-group ids. Each is a single bit, so any union of groups is the sum (or OR)
+ *        of its members: kWorkerGroup + kServerGroup addresses every worker and server.
+ */
+enum NodeGroup : int {
+  kScheduler = 1 << 0,
+  kServerGroup = 1 << 1,
+  kWorkerGroup = 1 << 2,
+};
 
 }  // namespace ps
 #endif  // PS_BASE_H_

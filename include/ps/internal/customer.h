@@ -33,15 +33,23 @@ class Postoffice;
 
 class Customer {
  public:
-  /*! \brief invoked for every message addressed to this customer */
-  using RecvHandle = std::function<void(const Message& recved)>;
+  /*! \brief invoked (on the customer thread, or inline) for every message addressed here */
+  typedef std::function<void(const Message& recved)> RecvHandle;
 
   Customer(int app_id, int customer_id, const RecvHandle& recv_handle, Postoffice* postoffice);
   ~Customer();
+  Customer(const Customer&) = delete;
+  Customer& operator=(const Customer&) = delete;
 
+  // ---- identity -------------------------------------------------------------
   int app_id() const { return app_id_; }
   int customer_id() const { return customer_id_; }
 
+  // ---- inbox (van receive thread -> application) ------------------------------
+  /*! \brief hand a received message to this customer */
+  void Accept(const Message& recved);
+
+  // ---- request tracker -----------------------------------------------------------
   /*!
    * \brief open a request addressed to node group `recver`; returns its timestamp.
    *  The expected response count is the number of *groups* in `recver` (a worker
@@ -49,30 +57,30 @@ class Customer {
    *  node id, or `num_expected` if given.
    */
   int NewRequest(int recver, int num_expected = -1);
-  /*! \brief block until every expected response of `timestamp` has arrived */
-  void WaitRequest(int timestamp);
-  /*! \brief responses received so far */
-  int NumResponse(int timestamp);
-  /*! \brief count `num` responses without a message (e.g. skipped empty slices) */
+  /*! \brief count `num` responses that will never arrive as messages (e.g. empty slices) */
   void AddResponse(int timestamp, int num = 1);
-  /*! \brief called by the van receive thread */
-  void Accept(const Message& recved);
+  /*! \brief responses counted so far for `timestamp` */
+  int NumResponse(int timestamp);
+  /*! \brief block until `timestamp` has all its responses */
+  void WaitRequest(int timestamp);
 
  private:
+  /*! \brief one in-flight request; lives in ring_[ts & mask] until a later ts recycles it */
   struct Slot {
     int ts = -1;
     int expected = 0;
     int received = 0;
   };
-  void Receiving();
+  Slot* Find(int ts);  // caller holds tracker_mu_
   void Deliver(const Message& m);
-  Slot* Find(int ts);  // requires tracker_mu_
+  void Receiving();
 
-  int app_id_;
-  int customer_id_;
+  const int app_id_;
+  const int customer_id_;
   RecvHandle recv_handle_;
   Postoffice* postoffice_;
   bool direct_dispatch_ = false;
+
   ThreadsafeQueue<Message> inbox_;
   std::unique_ptr<std::thread> recv_thread_;
 
@@ -80,8 +88,6 @@ class Customer {
   std::condition_variable tracker_cv_;
   std::vector<Slot> ring_;
   int next_ts_ = 0;
-  Customer(const Customer&) = delete;
-  Customer& operator=(const Customer&) = delete;
 };
 
 }  // namespace ps
