@@ -374,9 +374,9 @@ PYBIND11_MODULE(_C, m) {
     po->Barrier(customer_id, group);
   }, py::arg("customer_id") = 0, py::arg("group") = kWorkerGroup + kServerGroup,
      py::arg("as_role") = "worker");
-  m.attr("SCHEDULER_GROUP") = kScheduler;
-  m.attr("SERVER_GROUP") = kServerGroup;
-  m.attr("WORKER_GROUP") = kWorkerGroup;
+  m.attr("SCHEDULER_GROUP") = static_cast<int>(kScheduler);
+  m.attr("SERVER_GROUP") = static_cast<int>(kServerGroup);
+  m.attr("WORKER_GROUP") = static_cast<int>(kWorkerGroup);
   m.attr("CODEC_RAW") = static_cast<int>(kCodecRaw);
   m.attr("CODEC_F32_TO_BF16") = static_cast<int>(kCodecF32ToBf16);
   m.attr("CODEC_BF16_SCALE") = static_cast<int>(kCodecBf16Scale);
