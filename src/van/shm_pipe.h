@@ -1,0 +1,212 @@
+/**
+ * \file shm_pipe.h
+ * \brief ShmPipe: a unidirectional byte stream through a POSIX shared-memory ring.
+ *
+ * On one box every peer is "same host", so message descriptors do not need the
+ * kernel's socket path (2 system calls and 2 copies per message). The sending
+ * van writes its frames into this ring; the receiving van's thread polls it and
+ * only falls back to sleeping in epoll — woken by a 1-byte doorbell on the TCP
+ * connection — when it has been idle for a while. This is the host-side mailbox
+ * of the SURVEY design (§5.8 "descriptor in a per-pair SPSC mailbox ring").
+ *
+ * Layout: [Ctl | data[capacity]]; head/tail are free-running byte counters on
+ * separate cache-line pairs; capacity is a power of two. A frame larger than the
+ * ring streams through it (the writer publishes as it goes).
+ */
+#ifndef PS_VAN_SHM_PIPE_H_
+#define PS_VAN_SHM_PIPE_H_
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <string>
+#include <thread>
+
+namespace ps {
+
+class ShmPipe {
+ public:
+  ~ShmPipe() {
+    if (base_) munmap(base_, map_bytes_);
+    if (owner_ && !name_.empty()) shm_unlink(name_.c_str());
+  }
+
+  /*! \brief producer side: create and map a fresh ring */
+  static std::unique_ptr<ShmPipe> Create(const std::string& name, size_t capacity) {
+    size_t cap = 4096;
+    while (cap < capacity) cap <<= 1;
+    shm_unlink(name.c_str());
+    int fd = shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+    if (fd < 0) return nullptr;
+    const size_t bytes = sizeof(Ctl) + cap;
+    if (ftruncate(fd, static_cast<off_t>(bytes)) != 0) {
+      close(fd);
+      shm_unlink(name.c_str());
+      return nullptr;
+    }
+    void* p = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) {
+      shm_unlink(name.c_str());
+      return nullptr;
+    }
+    std::unique_ptr<ShmPipe> pipe(new ShmPipe());
+    pipe->Adopt(p, bytes, name, true);
+    Ctl* c = pipe->ctl_;
+    new (&c->tail) std::atomic<uint64_t>(0);
+    new (&c->head) std::atomic<uint64_t>(0);
+    new (&c->sleeping) std::atomic<uint32_t>(1);  // the first message rings the doorbell
+    c->capacity = static_cast<uint32_t>(cap);
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    return pipe;
+  }
+
+  /*! \brief consumer side: map an existing ring (the name can be unlinked afterwards) */
+  static std::unique_ptr<ShmPipe> Attach(const std::string& name) {
+    int fd = shm_open(name.c_str(), O_RDWR, 0600);
+    if (fd < 0) return nullptr;
+    struct stat st;
+    if (fstat(fd, &st) != 0 || static_cast<size_t>(st.st_size) <= sizeof(Ctl)) {
+      close(fd);
+      return nullptr;
+    }
+    void* p = mmap(nullptr, static_cast<size_t>(st.st_size), PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) return nullptr;
+    std::unique_ptr<ShmPipe> pipe(new ShmPipe());
+    pipe->Adopt(p, static_cast<size_t>(st.st_size), name, false);
+    return pipe;
+  }
+
+  // ---- producer ---------------------------------------------------------------
+  /*! \brief append n bytes (streams when n exceeds the free space); false if the reader is gone */
+  bool Write(const void* src, size_t n) {
+    const char* p = static_cast<const char*>(src);
+    const uint64_t cap = ctl_->capacity, mask = cap - 1;
+    uint64_t tail = ctl_->tail.load(std::memory_order_relaxed);
+    auto idle_since = std::chrono::steady_clock::time_point();
+    while (n) {
+      const uint64_t head = ctl_->head.load(std::memory_order_acquire);
+      const uint64_t space = cap - (tail - head);
+      if (space == 0) {
+        // ring full: the reader may be asleep — it must be woken by the caller's doorbell,
+        // so report "needs doorbell" through the flag and keep waiting politely
+        if (idle_since == std::chrono::steady_clock::time_point()) {
+          idle_since = std::chrono::steady_clock::now();
+        } else if (std::chrono::steady_clock::now() - idle_since > std::chrono::seconds(60)) {
+          return false;
+        }
+        if (full_hook_) full_hook_();
+        std::this_thread::yield();
+        continue;
+      }
+      idle_since = std::chrono::steady_clock::time_point();
+      const size_t chunk = static_cast<size_t>(std::min<uint64_t>(space, n));
+      const size_t at = static_cast<size_t>(tail & mask);
+      const size_t first = std::min(chunk, static_cast<size_t>(cap - at));
+      memcpy(data_ + at, p, first);
+      if (chunk > first) memcpy(data_, p + first, chunk - first);
+      tail += chunk;
+      p += chunk;
+      n -= chunk;
+      ctl_->tail.store(tail, std::memory_order_release);
+    }
+    return true;
+  }
+  /*! \brief after a frame: true if the reader declared itself asleep (ring its doorbell) */
+  bool ReaderNeedsDoorbell() {
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    if (ctl_->sleeping.load(std::memory_order_seq_cst) == 0) return false;
+    return ctl_->sleeping.exchange(0, std::memory_order_seq_cst) != 0;
+  }
+  /*! \brief called while the ring is full (lets the owner ring the doorbell) */
+  void set_full_hook(std::function<void()> f) { full_hook_ = std::move(f); }
+
+  // ---- consumer ---------------------------------------------------------------
+  size_t Readable() const {
+    return static_cast<size_t>(ctl_->tail.load(std::memory_order_acquire) -
+                               ctl_->head.load(std::memory_order_relaxed));
+  }
+  /*! \brief consume exactly n bytes, waiting for the writer if needed; false on a dead writer */
+  bool Read(void* dst, size_t n) {
+    char* p = static_cast<char*>(dst);
+    const uint64_t cap = ctl_->capacity, mask = cap - 1;
+    uint64_t head = ctl_->head.load(std::memory_order_relaxed);
+    auto idle_since = std::chrono::steady_clock::time_point();
+    while (n) {
+      const uint64_t avail = ctl_->tail.load(std::memory_order_acquire) - head;
+      if (avail == 0) {
+        if (idle_since == std::chrono::steady_clock::time_point()) {
+          idle_since = std::chrono::steady_clock::now();
+        } else if (std::chrono::steady_clock::now() - idle_since > std::chrono::seconds(60)) {
+          return false;
+        }
+        std::this_thread::yield();
+        continue;
+      }
+      idle_since = std::chrono::steady_clock::time_point();
+      const size_t chunk = static_cast<size_t>(std::min<uint64_t>(avail, n));
+      const size_t at = static_cast<size_t>(head & mask);
+      const size_t first = std::min(chunk, static_cast<size_t>(cap - at));
+      memcpy(p, data_ + at, first);
+      if (chunk > first) memcpy(p + first, data_, chunk - first);
+      head += chunk;
+      p += chunk;
+      n -= chunk;
+      ctl_->head.store(head, std::memory_order_release);
+    }
+    return true;
+  }
+  /*! \brief announce "about to sleep"; returns false (and cancels) if data is already there */
+  bool PrepareSleep() {
+    ctl_->sleeping.store(1, std::memory_order_seq_cst);
+    std::atomic_thread_fence(std::memory_order_seq_cst);
+    if (Readable() > 0) {
+      ctl_->sleeping.store(0, std::memory_order_seq_cst);
+      return false;
+    }
+    return true;
+  }
+  void CancelSleep() { ctl_->sleeping.store(0, std::memory_order_seq_cst); }
+
+  const std::string& name() const { return name_; }
+  void Unlink() {
+    if (!name_.empty()) shm_unlink(name_.c_str());
+  }
+
+ private:
+  struct Ctl {
+    alignas(128) std::atomic<uint64_t> tail;
+    alignas(128) std::atomic<uint64_t> head;
+    alignas(128) std::atomic<uint32_t> sleeping;
+    uint32_t capacity;
+    char pad[128 - sizeof(std::atomic<uint32_t>) - sizeof(uint32_t)];
+  };
+  ShmPipe() {}
+  void Adopt(void* p, size_t bytes, const std::string& name, bool owner) {
+    base_ = p;
+    map_bytes_ = bytes;
+    ctl_ = static_cast<Ctl*>(p);
+    data_ = static_cast<char*>(p) + sizeof(Ctl);
+    name_ = name;
+    owner_ = owner;
+  }
+  void* base_ = nullptr;
+  size_t map_bytes_ = 0;
+  Ctl* ctl_ = nullptr;
+  char* data_ = nullptr;
+  std::string name_;
+  bool owner_ = false;
+  std::function<void()> full_hook_;
+};
+
+}  // namespace ps
+#endif  // PS_VAN_SHM_PIPE_H_

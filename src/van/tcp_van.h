@@ -45,6 +45,7 @@
 
 #include "ps/internal/postoffice.h"
 #include "ps/internal/van.h"
+#include "van/shm_pipe.h"
 
 namespace ps {
 
@@ -132,6 +133,9 @@ class TcpVan : public Van {
     local_ipc_ = GetEnv("DMLC_LOCAL", 0) != 0;
     connect_timeout_s_ = GetEnv("PS_CONNECT_TIMEOUT", 120);
     direct_pull_ = GetEnv("PS_TCP_DIRECT_PULL", 1) != 0;
+    use_pipes_ = GetEnv("PS_SHM_PIPE", 1) != 0;
+    pipe_bytes_ = static_cast<size_t>(GetEnv("PS_SHM_PIPE_KB", 4096)) << 10;
+    pipe_spin_us_ = GetEnv("PS_SHM_PIPE_SPIN_US", 50);
     if (!pool_) {
       pool_ = std::make_shared<RecvBufferPool>(static_cast<size_t>(GetEnv("PS_TCP_POOL_MB", 1024))
                                                << 20);
@@ -158,7 +162,10 @@ class TcpVan : public Van {
   struct Peer {
     int fd = -1;
     std::mutex mu;  // serialises whole frames on this socket
+    /*! \brief same-host fast path: frames go through this ring, the socket carries doorbells */
+    std::unique_ptr<ShmPipe> pipe;
   };
+  static constexpr uint32_t kPipeMagic = 0x45504950u;  // "PIPE": "frames follow in shm ring <name>"
 
   int Bind(Node& node, int max_retry) override {
     int port = node.port;
@@ -218,6 +225,9 @@ class TcpVan : public Van {
     }
     std::shared_ptr<Peer> peer(new Peer());
     peer->fd = fd;
+    if (use_pipes_ && !my_node_.hostname.empty() && node.hostname == my_node_.hostname) {
+      OfferPipe(peer.get(), node.id);
+    }
     std::shared_ptr<Peer> old;
     {
       std::lock_guard<std::mutex> lk(peers_mu_);
@@ -275,7 +285,7 @@ class TcpVan : public Van {
 
     std::lock_guard<std::mutex> lk(peer->mu);
     if (peer->fd < 0) return -1;
-    if (!SendAll(peer->fd, iov, niov)) {
+    if (!(peer->pipe ? SendThroughPipe(peer.get(), iov, niov) : SendAll(peer->fd, iov, niov))) {
       LOG(WARNING) << "failed to send to node " << recver << ": " << strerror(errno);
       return -1;
     }
@@ -329,6 +339,10 @@ class TcpVan : public Van {
     for (auto& v : iov) total += v.iov_len;
     std::lock_guard<std::mutex> lk(peer->mu);
     if (peer->fd < 0) return -1;
+    if (peer->pipe) {
+      if (!SendThroughPipe(peer.get(), iov.data(), static_cast<int>(iov.size()))) return -1;
+      return static_cast<int>(std::min<size_t>(total, 0x7fffffff));
+    }
     // IOV_MAX is 1024 on Linux: flush in slices
     size_t at = 0;
     while (at < iov.size()) {
@@ -341,18 +355,38 @@ class TcpVan : public Van {
 
   int RecvMsg(Message* msg) override {
     msg->data.clear();
+    auto last_activity = std::chrono::steady_clock::now();
     for (;;) {
       if (PopLoopback(msg)) return 1 + static_cast<int>(msg->meta.data_size & 0x3fffffff);
+      // same-host peers: frames arrive in shared-memory rings (round-robin for fairness)
+      if (int bytes = PollPipes(msg)) return bytes;
       // sockets epoll reported readable and that we have not looked at yet; only
       // this thread reads them, so each still holds at least one byte
       while (!ready_fds_.empty()) {
         const int fd = ready_fds_.front();
         ready_fds_.pop_front();
         int bytes = ReadFrame(fd, msg);
-        if (bytes > 0) return bytes;  // 0: the peer closed
+        if (bytes > 0) return bytes;  // 0: the peer closed, rang a doorbell or offered a ring
+      }
+      if (int bytes = PollPipes(msg)) return bytes;
+      int timeout_ms = -1;
+      if (!pipe_fds_.empty()) {
+        // stay hot for a short while after the last message, then declare ourselves asleep
+        // on every ring so that the next writer rings the doorbell
+        const auto idle = std::chrono::steady_clock::now() - last_activity;
+        if (idle < std::chrono::microseconds(pipe_spin_us_)) {
+          timeout_ms = 0;
+        } else if (!SleepOnPipes()) {
+          last_activity = std::chrono::steady_clock::now();
+          continue;  // something arrived while we were getting ready to sleep
+        }
       }
       struct epoll_event evs[16];
-      int n = epoll_wait(epfd_, evs, 16, -1);
+      int n = epoll_wait(epfd_, evs, 16, timeout_ms);
+      if (timeout_ms != 0) {
+        WakeFromPipes();
+        last_activity = std::chrono::steady_clock::now();
+      }
       if (n < 0) {
         if (errno == EINTR) continue;
         LOG(WARNING) << "epoll_wait: " << strerror(errno);
@@ -370,6 +404,7 @@ class TcpVan : public Van {
           ready_fds_.push_back(fd);  // level-triggered: drained one frame at a time
         }
       }
+      if (n > 0) last_activity = std::chrono::steady_clock::now();
     }
   }
 
@@ -442,6 +477,40 @@ class TcpVan : public Van {
     AddToEpoll(fd);
   }
 
+  /*! \brief create a ring for this connection and tell the peer its name over the socket */
+  void OfferPipe(Peer* peer, int peer_id) {
+    static std::atomic<int> seq{0};
+    const std::string name = "/pslb200_" + std::to_string(getpid()) + "_" + std::to_string(peer_id) +
+                             "_" + std::to_string(seq++);
+    std::unique_ptr<ShmPipe> pipe = ShmPipe::Create(name, pipe_bytes_);
+    if (!pipe) return;  // no /dev/shm: stay on the socket
+    FrameHeader hello = {kPipeMagic, my_node_.id, peer_id, static_cast<uint32_t>(name.size()), 0, 0};
+    struct iovec iov[2] = {{&hello, sizeof(hello)}, {const_cast<char*>(name.data()), name.size()}};
+    if (!SendAll(peer->fd, iov, 2)) return;
+    const int fd = peer->fd;
+    ShmPipe* raw = pipe.get();
+    // a sleeping reader never drains a full ring: wake it from inside the blocked write
+    pipe->set_full_hook([fd, raw] {
+      if (raw->ReaderNeedsDoorbell()) RingDoorbell(fd);
+    });
+    peer->pipe = std::move(pipe);
+  }
+
+  static void RingDoorbell(int fd) {
+    const char b = 1;
+    ssize_t r = send(fd, &b, 1, MSG_NOSIGNAL);
+    (void)r;
+  }
+
+  /*! \brief write whole frames into the peer's ring; doorbell only if the reader sleeps */
+  bool SendThroughPipe(Peer* peer, const struct iovec* iov, int niov) {
+    for (int i = 0; i < niov; ++i) {
+      if (!peer->pipe->Write(iov[i].iov_base, iov[i].iov_len)) return false;
+    }
+    if (peer->pipe->ReaderNeedsDoorbell()) RingDoorbell(peer->fd);
+    return true;
+  }
+
   static size_t ElemSize(DataType t) {
     switch (t) {
       case INT16: case UINT16: return 2;
@@ -492,7 +561,40 @@ class TcpVan : public Van {
     return 1;
   }
 
+  /*! \brief deliver the next frame of any ring that has bytes; 0 if all are empty */
+  int PollPipes(Message* msg) {
+    const size_t n = pipe_fds_.size();
+    for (size_t k = 0; k < n; ++k) {
+      const size_t idx = (pipe_cursor_ + k) % n;
+      auto it = inbound_.find(pipe_fds_[idx]);
+      if (it == inbound_.end() || !it->second->pipe) continue;
+      if (it->second->pipe->Readable() == 0) continue;
+      pipe_cursor_ = (idx + 1) % n;
+      return ReadFramePipe(it->second->pipe.get(), msg);
+    }
+    return 0;
+  }
+  /*! \brief flag every ring "reader asleep"; false (flags cleared) if one has data after all */
+  bool SleepOnPipes() {
+    for (int fd : pipe_fds_) {
+      auto it = inbound_.find(fd);
+      if (it == inbound_.end() || !it->second->pipe) continue;
+      if (!it->second->pipe->PrepareSleep()) {
+        WakeFromPipes();
+        return false;
+      }
+    }
+    return true;
+  }
+  void WakeFromPipes() {
+    for (int fd : pipe_fds_) {
+      auto it = inbound_.find(fd);
+      if (it != inbound_.end() && it->second->pipe) it->second->pipe->CancelSleep();
+    }
+  }
+
   void DropInbound(int fd) {
+    pipe_fds_.erase(std::remove(pipe_fds_.begin(), pipe_fds_.end(), fd), pipe_fds_.end());
     epoll_ctl(epfd_, EPOLL_CTL_DEL, fd, nullptr);
     close(fd);
     inbound_.erase(fd);
@@ -516,6 +618,8 @@ class TcpVan : public Van {
     std::unique_ptr<char[]> buf{new char[kCap]};
     size_t head = 0, tail = 0;
     size_t avail() const { return tail - head; }
+    /*! \brief once the peer offered a ring, its frames arrive here and the socket only rings */
+    std::unique_ptr<ShmPipe> pipe;
   };
 
   /*! \brief make >= n bytes available in the buffer (n <= kCap). 1 ok, 0 closed, -1 error */
@@ -560,11 +664,18 @@ class TcpVan : public Van {
     return ReadAll(fd, out + from_buf, n - from_buf) == 1 ? 1 : -1;
   }
 
-  /*! \brief read one whole frame from fd; >0 bytes, 0 if the socket went away */
+  /*! \brief read one whole frame from fd; >0 bytes, 0 if nothing to deliver (closed / doorbell) */
   int ReadFrame(int fd, Message* msg) {
     auto iit = inbound_.find(fd);
     if (iit == inbound_.end()) return 0;
     Inbound* in = iit->second.get();
+    if (in->pipe) {
+      // the socket of a pipe-backed connection only carries 1-byte doorbells (or EOF)
+      char junk[256];
+      ssize_t r = recv(fd, junk, sizeof(junk), MSG_DONTWAIT);
+      if (r == 0) DropInbound(fd);
+      return 0;  // RecvMsg polls the ring next
+    }
     FrameHeader hdr;
     int rc = Fill(fd, in, sizeof(hdr));
     if (rc <= 0) {
@@ -573,14 +684,37 @@ class TcpVan : public Van {
     }
     memcpy(&hdr, in->buf.get() + in->head, sizeof(hdr));
     in->head += sizeof(hdr);
+    if (hdr.magic == kPipeMagic) {
+      std::string name(hdr.meta_len, '\0');
+      CHECK_EQ(Take(fd, in, &name[0], name.size()), 1);
+      in->pipe = ShmPipe::Attach(name);
+      CHECK(in->pipe) << "cannot attach shared-memory ring " << name << ": " << strerror(errno);
+      in->pipe->Unlink();  // both ends have it mapped: the name is no longer needed
+      pipe_fds_.push_back(fd);
+      return 0;
+    }
+    const int bytes = ParseFrame(hdr, msg, [&](void* dst, size_t n) { return Take(fd, in, dst, n) == 1; });
+    // frames already sitting in the buffer will not wake epoll: keep this fd runnable
+    if (in->avail() > 0) ready_fds_.push_back(fd);
+    return bytes;
+  }
+
+  /*! \brief next frame from a ring, if one has started to arrive */
+  int ReadFramePipe(ShmPipe* pipe, Message* msg) {
+    FrameHeader hdr;
+    CHECK(pipe->Read(&hdr, sizeof(hdr))) << "shared-memory ring writer vanished";
+    return ParseFrame(hdr, msg, [&](void* dst, size_t n) { return pipe->Read(dst, n); });
+  }
+
+  /*! \brief everything after the FrameHeader; `take(dst, n)` pulls the next n stream bytes */
+  template <typename TakeFn>
+  int ParseFrame(const FrameHeader& hdr, Message* msg, TakeFn take) {
     CHECK_EQ(hdr.magic, kFrameMagic) << "corrupt frame";
     CHECK_LE(hdr.num_segments, kMaxSegments);
     uint64_t seg_len[kMaxSegments];
-    if (hdr.num_segments) {
-      CHECK_EQ(Take(fd, in, seg_len, sizeof(uint64_t) * hdr.num_segments), 1);
-    }
+    if (hdr.num_segments) CHECK(take(seg_len, sizeof(uint64_t) * hdr.num_segments));
     std::vector<char> meta_buf(hdr.meta_len);
-    CHECK_EQ(Take(fd, in, meta_buf.data(), meta_buf.size()), 1);
+    CHECK(take(meta_buf.data(), meta_buf.size()));
     CHECK(UnpackMeta(meta_buf.data(), meta_buf.size(), &msg->meta)) << "corrupt meta";
     msg->meta.sender = hdr.sender;
     msg->meta.recver = my_node_.id;
@@ -606,7 +740,7 @@ class TcpVan : public Van {
         }
       }
       if (seg.size() != seg_len[i]) seg = AllocSegment(seg_len[i]);
-      if (seg_len[i]) CHECK_EQ(Take(fd, in, seg.data(), seg_len[i]), 1);
+      if (seg_len[i]) CHECK(take(seg.data(), seg_len[i]));
       // the bytes now live in host memory of this node
       seg.src_device_type_ = CPU;
       seg.src_device_id_ = 0;
@@ -619,8 +753,6 @@ class TcpVan : public Van {
       msg->data.push_back(seg);
       total += seg_len[i];
     }
-    // frames already sitting in the buffer will not wake epoll: keep this fd runnable
-    if (in->avail() > 0) ready_fds_.push_back(fd);
     return static_cast<int>(std::min<size_t>(total, 0x7fffffff));
   }
 
@@ -659,6 +791,7 @@ class TcpVan : public Van {
     }
     for (auto& kv : inbound_) close(kv.first);
     inbound_.clear();
+    pipe_fds_.clear();
     ready_fds_.clear();
     if (listen_fd_ >= 0) close(listen_fd_);
     listen_fd_ = -1;
@@ -681,6 +814,11 @@ class TcpVan : public Van {
   int wake_fd_ = -1;
   int listen_fd_ = -1;
   std::unordered_map<int, std::unique_ptr<Inbound>> inbound_;  // receive thread only
+  std::vector<int> pipe_fds_;                                  // inbound connections with a ring
+  size_t pipe_cursor_ = 0;
+  bool use_pipes_ = true;
+  size_t pipe_bytes_ = 4u << 20;
+  int pipe_spin_us_ = 50;
   std::deque<int> ready_fds_;      // touched by the receive thread only
   std::mutex peers_mu_;
   std::unordered_map<int, std::shared_ptr<Peer>> peers_;
