@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "llama-1b", "tiny"])
     ap.add_argument("--ckpt-layers", type=int, default=-1)
     ap.add_argument("--attn-backend", default="auto", choices=["auto", "cudnn", "flash", "efficient", "math"])
+    ap.add_argument("--nvls-reduce", action="store_true",
+                    help="with --symmetric: bf16 gradients staged in symmetric memory and summed inside "
+                         "the NVSwitch by the update kernel (multimem.ld_reduce)")
     ap.add_argument("--symmetric", action="store_true",
                     help="parameters in symmetric memory; NVLS multicast pull fan-out (N > 1)")
     return ap.parse_args()
@@ -299,10 +302,19 @@ def run_llama(args, dist: Dist) -> dict:
                                                               list(range(W)))
         if server is not None:
             server.set_symmetric(mc, peers, nbytes)
+    gbuf = None
+    if use_symm and args.nvls_reduce and mc:
+        from pslite_b200.parallel.ps_trainer import setup_symmetric_grads
+
+        gbuf, ghdl, gmc, gbytes = setup_symmetric_grads(total, tdist.group.WORLD, dev)
+        if server is not None:
+            server.set_symmetric_grads(gmc, gbytes)
+        dist.barrier()
     if ctx.is_worker:
         kv = C.KVWorker(0, 0)
         opt = PSWorkerOptimizer(model.parameters(), kv, S, W, ctx.worker_rank,
-                                grad_wire=args.grad_wire, symmetric=use_symm).attach()
+                                grad_wire=args.grad_wire, symmetric=use_symm,
+                                grad_buffer=gbuf).attach()
         opt.init_parameters(barrier=lambda: C.barrier(0, C.WORKER_GROUP, "worker"))
     dist.barrier()
     g = torch.Generator().manual_seed(1234 + dist.rank)
@@ -359,6 +371,7 @@ def run_llama(args, dist: Dist) -> dict:
     stats = {"server_updates": server.num_updates() if server else 0,
              "server_fused_fanouts": server.num_fused_fanouts() if server else 0,
              "server_multicast_fanouts": server.num_multicast_fanouts() if server else 0,
+             "server_switch_reductions": server.num_switch_reductions() if server else 0,
              "multicast_available": bool(mc)}
     ctx.shutdown()
     return {
@@ -366,7 +379,9 @@ def run_llama(args, dist: Dist) -> dict:
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16", "data": "synthetic tokens, random-init weights",
         "config": {"model": args.model, "params": cfg.num_params(), "global_batch": B * W,
-                   "seq_len": T, "parallelism": f"ps-dp{W} ({W}w+{S}s {topo}), grad wire {args.grad_wire}, server AdamW",
+                   "seq_len": T,
+                   "parallelism": f"ps-dp{W} ({W}w+{S}s {topo}), grad wire "
+                                  f"{'bf16 in-switch reduce' if gbuf is not None else args.grad_wire}, server AdamW",
                    "ckpt_layers": cfg.ckpt_layers, "l2": "per-step working set >> 126 MB L2"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "mfu_vs_sustained_bf16": mfu,
         "peak_torch_mem_gb": peak_mem,

@@ -252,11 +252,15 @@ struct SendOpts {
   /*! \brief cudaEvent_t the copy must wait for (producer of the values), or null */
   void* wait_event = nullptr;
   /*!
-   * \brief pulls only: the destination is already known to the server under this name
-   *        (e.g. an offset inside a symmetric / multicast-bound parameter buffer), so the
-   *        van must not try to export it.
+   * \brief the remote side already knows this buffer under a name (e.g. an offset inside a
+   *        symmetric / multicast-bound buffer), so the van must not export or rendezvous.
+   *        Pull: where the reply lands. Push: where the (encoded) values are staged — in the
+   *        SENDER's own symmetric buffer, at `stage`; the server then reads all workers'
+   *        copies at that offset through the multicast address (in-switch reduction).
    */
   MemRef dest_mem;
+  /*! \brief push with a symmetric `dest_mem`: local address the values are encoded into */
+  void* stage = nullptr;
 };
 
 /*! \brief MemRef::region value meaning "offset inside the job-wide symmetric buffer" */
@@ -268,6 +272,8 @@ struct Message {
   std::vector<SArray<char>> data;
   /*! \brief local-only: event gating the one-sided copy of data[1] */
   void* wait_event = nullptr;
+  /*! \brief local-only: staging address of a symmetric push (see SendOpts::stage) */
+  void* stage = nullptr;
 
   /*! \brief append a segment; the second one (the values) sets the placement fields */
   template <typename V>

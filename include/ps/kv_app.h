@@ -441,7 +441,10 @@ void KVWorker<Val>::Send(int timestamp, bool push, int cmd, KVPairs<Val>& kvs,
     msg.meta.codec = opts.codec;
     msg.meta.scale = opts.scale;
     msg.wait_event = opts.wait_event;
-    if (!push && opts.dest_mem.valid()) msg.meta.mem = opts.dest_mem;
+    if (opts.dest_mem.valid()) {
+      msg.meta.mem = opts.dest_mem;
+      if (push) msg.stage = opts.stage;
+    }
     const SArray<Val> dest = part.vals;  // placement of the pull destination
     if (!push) part.vals.clear();
     if (part.keys.size()) {

@@ -86,11 +86,20 @@ class PyKVWorker {
   }
 
   int push(uint64_t key, const torch::Tensor& t, int cmd, int codec, float scale,
-           bool order_after_current_stream) {
+           bool order_after_current_stream, int64_t symm_offset, uint64_t symm_base) {
     SArray<char> vals = ViewOf(t);
     SendOpts opts;
     opts.codec = codec;
     opts.scale = scale;
+    if (symm_offset >= 0) {
+      // stage the encoded gradient in this worker's symmetric buffer; the server reads the
+      // sum of all workers' copies through the multicast address (multimem.ld_reduce)
+      TORCH_CHECK(symm_base != 0, "symmetric push needs the local base address of the buffer");
+      opts.dest_mem.region = kSymmetricRegion;
+      opts.dest_mem.offset = static_cast<uint64_t>(symm_offset);
+      opts.dest_mem.bytes = WireBytes(codec, vals.size());
+      opts.stage = reinterpret_cast<void*>(symm_base + static_cast<uint64_t>(symm_offset));
+    }
     cudaEvent_t ev = nullptr;
     if (t.is_cuda() && order_after_current_stream) {
       ev = RecordOnCurrentStream(t.get_device());
@@ -317,6 +326,10 @@ class PyGpuServer {
     for (uint64_t p : peer_ptrs) peers.push_back(reinterpret_cast<void*>(p));
     impl_->SetSymmetricParams(reinterpret_cast<void*>(mc_ptr), peers, bytes);
   }
+  void set_symmetric_grads(uint64_t mc_ptr, uint64_t bytes) {
+    impl_->SetSymmetricGrads(reinterpret_cast<void*>(mc_ptr), bytes);
+  }
+  uint64_t num_switch_reductions() { return impl_->num_switch_reductions(); }
   uint64_t num_multicast_fanouts() { return impl_->num_multicast_fanouts(); }
   uint64_t num_updates() { return impl_->num_updates(); }
   uint64_t num_fused_fanouts() { return impl_->num_fused_fanouts(); }
@@ -388,6 +401,7 @@ PYBIND11_MODULE(_C, m) {
   m.attr("GRAD_F32") = static_cast<int>(PS_GRAD_F32);
   m.attr("GRAD_BF16") = static_cast<int>(PS_GRAD_BF16);
   m.attr("GRAD_FP8BLOCK") = static_cast<int>(PS_GRAD_FP8BLOCK);
+  m.attr("GRAD_MC_BF16") = static_cast<int>(PS_GRAD_MC_BF16);
 
   m.def("wire_bytes", [](int codec, uint64_t src_bytes) { return WireBytes(codec, src_bytes); });
   m.def("kernel_launch_count", []() { return ps_kernel_launch_count(); });
@@ -414,7 +428,8 @@ PYBIND11_MODULE(_C, m) {
       .def("server_key", &PyKVWorker::server_key)
       .def("push", &PyKVWorker::push, py::arg("key"), py::arg("tensor"), py::arg("cmd") = 0,
            py::arg("codec") = 0, py::arg("scale") = 1.0f,
-           py::arg("order_after_current_stream") = true)
+           py::arg("order_after_current_stream") = true, py::arg("symm_offset") = -1,
+           py::arg("symm_base") = 0)
       .def("pull", &PyKVWorker::pull, py::arg("key"), py::arg("tensor"), py::arg("cmd") = 0,
            py::arg("symm_offset") = -1)
       .def("wait", &PyKVWorker::wait)
@@ -445,6 +460,8 @@ PYBIND11_MODULE(_C, m) {
       .def("set_symmetric", &PyGpuServer::set_symmetric, py::arg("mc_ptr"), py::arg("peer_ptrs"),
            py::arg("bytes"))
       .def("num_multicast_fanouts", &PyGpuServer::num_multicast_fanouts)
+      .def("set_symmetric_grads", &PyGpuServer::set_symmetric_grads, py::arg("mc_ptr"), py::arg("bytes"))
+      .def("num_switch_reductions", &PyGpuServer::num_switch_reductions)
       .def("num_updates", &PyGpuServer::num_updates)
       .def("num_fused_fanouts", &PyGpuServer::num_fused_fanouts)
       .def("num_keys", &PyGpuServer::num_keys)
@@ -517,7 +534,7 @@ PYBIND11_MODULE(_C, m) {
                            torch::Tensor mom, torch::Tensor var, std::vector<torch::Tensor> outs,
                            const std::string& optimizer, float lr, float beta1, float beta2,
                            float eps, float wd, int step, float grad_scale, int max_ctas,
-                           uint64_t mc_ptr) {
+                           uint64_t mc_ptr, uint64_t grad_mc_ptr) {
     ps_update_args a;
     memset(&a, 0, sizeof(a));
     a.n = static_cast<size_t>(master.numel());
@@ -525,6 +542,10 @@ PYBIND11_MODULE(_C, m) {
     a.grad_format = grad_format;
     TORCH_CHECK(a.num_grads <= PS_MAX_FANIN && outs.size() <= PS_MAX_FANOUT);
     for (size_t i = 0; i < grads.size(); ++i) a.grads[i] = grads[i].data_ptr();
+    if (grad_mc_ptr) {  // PS_GRAD_MC_BF16: the gradients are read through a multicast address
+      a.num_grads = 1;
+      a.grads[0] = reinterpret_cast<const void*>(grad_mc_ptr);
+    }
     a.master = master.data_ptr<float>();
     a.m = mom.data_ptr<float>();
     a.v = var.data_ptr<float>();
@@ -544,5 +565,5 @@ PYBIND11_MODULE(_C, m) {
      py::arg("outs"), py::arg("optimizer") = "adamw", py::arg("lr") = 1e-3f,
      py::arg("beta1") = 0.9f, py::arg("beta2") = 0.95f, py::arg("eps") = 1e-8f,
      py::arg("weight_decay") = 0.0f, py::arg("step") = 1, py::arg("grad_scale") = 1.0f,
-     py::arg("max_ctas") = 0, py::arg("mc_ptr") = 0);
+     py::arg("max_ctas") = 0, py::arg("mc_ptr") = 0, py::arg("grad_mc_ptr") = 0);
 }

@@ -16,6 +16,12 @@ Worker side of the BytePS-style loop the reference is built for (docs/overview.m
   no flat gradient buffer to zero and backward's peak memory shrinks as it proceeds.
 
 The optimizer state (fp32 master, Adam moments) lives only on the servers, sharded by key.
+
+With NVSwitch multicast (`symmetric=True`, `grad_buffer=...`) a whole round is ONE kernel per
+shard that never touches NCCL: `multimem.ld_reduce` (the switch sums the W workers' gradient
+buffers in fp32) -> AdamW on the fp32 state -> `multimem.st` (the switch replicates the new
+bf16 parameters into every worker's `param.data`): reduce-scatter + optimizer + all-gather
+fused, tile by tile, over NVLink.
 """
 from __future__ import annotations
 
@@ -80,12 +86,26 @@ def setup_symmetric_params(params, total_elems: int, group, device, worker_ranks
     return flat, hdl, mc, peers, total_elems * 2
 
 
+def setup_symmetric_grads(total_elems: int, group, device):
+    """Second job-wide symmetric bf16 buffer, for gradients (same layout as the parameters).
+    Every rank of `group` allocates it zero-filled — server-only ranks never write theirs, so
+    they add nothing to the in-switch sum. Returns (flat, handle, multicast_ptr, nbytes)."""
+    import torch.distributed._symmetric_memory as symm_mem
+
+    flat = symm_mem.empty(total_elems, dtype=torch.bfloat16, device=device)
+    flat.zero_()
+    hdl = symm_mem.rendezvous(flat, group)
+    torch.cuda.synchronize(device)
+    mc = int(hdl.multicast_ptr) if getattr(hdl, "multicast_ptr", 0) else 0
+    return flat, hdl, mc, total_elems * 2
+
+
 class PSWorkerOptimizer:
     """Drop-in "optimizer" for a worker: hooks gradients, exposes step()/zero_grad()."""
 
     def __init__(self, params, kv, num_servers: int, num_workers: int, worker_rank: int,
                  grad_wire: str = "fp8", chunk_elems: int = 32 << 20, app_barrier=None,
-                 symmetric: bool = False):
+                 symmetric: bool = False, grad_buffer: torch.Tensor | None = None):
         C = native()
         self._C = C
         self.kv = kv
@@ -103,6 +123,12 @@ class PSWorkerOptimizer:
         self.accumulate = False  # True on non-final micro-batches: keep grads local
         # byte offset of every parameter in the symmetric buffer (see setup_symmetric_params)
         self.symm_off = [o * 2 for o in symmetric_layout(self.params)[0]] if symmetric else None
+        # NVLS aggregation: gradients are staged (bf16) in this symmetric buffer and the server
+        # reads the sum over all workers with multimem.ld_reduce (see setup_symmetric_grads)
+        self.grad_buffer = grad_buffer
+        if grad_buffer is not None:
+            assert symmetric, "in-switch reduction uses the symmetric parameter layout"
+            assert grad_buffer.dtype == torch.bfloat16 and grad_buffer.is_contiguous()
         # chunk table
         self.chunks: list[list[_Chunk]] = []
         j = 0
@@ -121,6 +147,8 @@ class PSWorkerOptimizer:
     # -- wire format -------------------------------------------------------------
     def _codec(self, t: torch.Tensor) -> int:
         C = self._C
+        if self.grad_buffer is not None:  # the switch adds bf16 values
+            return C.CODEC_F32_TO_BF16 if t.dtype == torch.float32 else C.CODEC_RAW
         if self.grad_wire == "fp8":
             return C.CODEC_F32_TO_FP8BLOCK if t.dtype == torch.float32 else C.CODEC_BF16_TO_FP8BLOCK
         if t.dtype == torch.float32:
@@ -181,7 +209,12 @@ class PSWorkerOptimizer:
         codec = self._codec(g)
         for c in self.chunks[i]:
             gs = gflat[c.start:c.stop]
-            self._pending.append(self.kv.push(c.key, gs, cmd=self._C.CMD_GRAD, codec=codec, scale=1.0))
+            if self.grad_buffer is not None:
+                self._pending.append(self.kv.push(c.key, gs, cmd=self._C.CMD_GRAD, codec=codec, scale=1.0,
+                                                  symm_offset=self._symm(c),
+                                                  symm_base=self.grad_buffer.data_ptr()))
+            else:
+                self._pending.append(self.kv.push(c.key, gs, cmd=self._C.CMD_GRAD, codec=codec, scale=1.0))
             self._pending.append(self.kv.pull(c.key, pflat[c.start:c.stop], symm_offset=self._symm(c)))
             self.stats.pushes += 1
             self.stats.pulls += 1

@@ -41,6 +41,12 @@ enum {
   PS_GRAD_F32 = 0,
   PS_GRAD_BF16 = 1,
   PS_GRAD_FP8BLOCK = 2,  // [n_pad e4m3 bytes][n_pad/32 e8m0 bytes], n_pad = roundup(n,32)
+  /* NVLS in-switch aggregation: grads[0] is a MULTICAST address bound to the same offset of
+   * every worker's (symmetric) bf16 gradient buffer; num_grads must be 1. The kernel reads it
+   * with multimem.ld_reduce.add (fp32 accumulation inside the NVSwitch), so the W-way sum
+   * costs one 2 B/element stream on the server's link instead of W slot reads. The buffers
+   * must be padded to an even element count (the ragged tail loads bf16 pairs). */
+  PS_GRAD_MC_BF16 = 3,
 };
 
 enum { PS_OPT_SGD = 0, PS_OPT_ADAMW = 1 };

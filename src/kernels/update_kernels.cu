@@ -6,7 +6,8 @@
  * (include/ps/kv_app.h:441-447) and leaves the optimizer to the consumer. Here
  * one memory-bound pass per parameter shard does everything the server owes its
  * workers for a round:
- *     g      = grad_scale * sum_w dequant(slot_w)      (bf16 | fp8-block | f32 slots)
+ *     g      = grad_scale * sum_w dequant(slot_w)      (bf16 | fp8-block | f32 slots, or ONE
+ *              multimem.ld_reduce stream: the NVSwitch sums the W workers' symmetric buffers)
  *     m,v,p  = AdamW / SGD-momentum on fp32 state
  *     out_k  = bf16(p)  for every destination k       (<= 9: local + W workers)
  * The destinations may be peer-mapped worker parameter buffers, so the update
@@ -86,6 +87,23 @@ __device__ __forceinline__ void multimem_st16(void* p, const int4& v) {
                "f"(__int_as_float(v.w))
                : "memory");
 }
+/*! sum over every GPU bound to the multicast object, reduced by the NVSwitch in fp32 */
+__device__ __forceinline__ int4 multimem_ld_reduce16(const void* p) {
+  int4 r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+               : "l"(p)
+               : "memory");
+  return r;
+}
+__device__ __forceinline__ uint32_t multimem_ld_reduce4(const void* p) {
+  uint32_t r;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.bf16x2 %0, [%1];"
+               : "=r"(r)
+               : "l"(p)
+               : "memory");
+  return r;
+}
 __device__ __forceinline__ float2 bf2(uint32_t u) {
   __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(t);
@@ -112,6 +130,15 @@ template <int FMT>
 __device__ __forceinline__ void gather_grads(const UpdateDev& a, size_t i, float* g) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) g[j] = 0.f;
+  if (FMT == PS_GRAD_MC_BF16) {
+    const int4 q = multimem_ld_reduce16(static_cast<const unsigned char*>(a.grads[0]) + i * 16);
+    float2 f;
+    f = bf2(q.x); g[0] = f.x; g[1] = f.y;
+    f = bf2(q.y); g[2] = f.x; g[3] = f.y;
+    f = bf2(q.z); g[4] = f.x; g[5] = f.y;
+    f = bf2(q.w); g[6] = f.x; g[7] = f.y;
+    return;
+  }
   const size_t npad = (a.n + 31) / 32 * 32;
 #pragma unroll 1
   for (int w = 0; w < a.num_grads; ++w) {
@@ -144,6 +171,10 @@ __device__ __forceinline__ void gather_grads(const UpdateDev& a, size_t i, float
 template <int FMT>
 __device__ __forceinline__ float gather_one(const UpdateDev& a, size_t e) {
   float g = 0.f;
+  if (FMT == PS_GRAD_MC_BF16) {
+    const float2 f = bf2(multimem_ld_reduce4(static_cast<const unsigned char*>(a.grads[0]) + (e & ~size_t(1)) * 2));
+    return (e & 1) ? f.y : f.x;
+  }
   const size_t npad = (a.n + 31) / 32 * 32;
   for (int w = 0; w < a.num_grads; ++w) {
     const unsigned char* base = static_cast<const unsigned char*>(a.grads[w]);
@@ -329,6 +360,11 @@ extern "C" int ps_launch_update(const ps_update_args* args, const ps_opt_params*
       adam ? LaunchUpdate<PS_GRAD_F32, PS_OPT_ADAMW>(d, o, f32, grid, st)
            : LaunchUpdate<PS_GRAD_F32, PS_OPT_SGD>(d, o, f32, grid, st);
       break;
+    case PS_GRAD_MC_BF16:
+      if (args->num_grads != 1) return cudaErrorInvalidValue;
+      adam ? LaunchUpdate<PS_GRAD_MC_BF16, PS_OPT_ADAMW>(d, o, f32, grid, st)
+           : LaunchUpdate<PS_GRAD_MC_BF16, PS_OPT_SGD>(d, o, f32, grid, st);
+      break;
     default:
       return cudaErrorInvalidValue;
   }
@@ -356,6 +392,8 @@ extern "C" int ps_launch_sum(float* out, const void* const* grads, int num_grads
     k_sum<PS_GRAD_FP8BLOCK><<<grid, kThreads, 0, st>>>(out, d, scale, accumulate);
   else if (fmt == PS_GRAD_F32)
     k_sum<PS_GRAD_F32><<<grid, kThreads, 0, st>>>(out, d, scale, accumulate);
+  else if (fmt == PS_GRAD_MC_BF16 && num_grads == 1)
+    k_sum<PS_GRAD_MC_BF16><<<grid, kThreads, 0, st>>>(out, d, scale, accumulate);
   else return cudaErrorInvalidValue;
   ps_kernels_internal::CountLaunch(1);
   return static_cast<int>(cudaGetLastError());

@@ -76,6 +76,12 @@ void GpuServer::SetSymmetricParams(void* mc_base, const std::vector<void*>& peer
   symm_bytes_ = bytes;
 }
 
+void GpuServer::SetSymmetricGrads(void* mc_base, size_t bytes) {
+  std::lock_guard<std::mutex> lk(mu_);
+  mc_grad_base_ = mc_base;
+  symm_grad_bytes_ = bytes;
+}
+
 size_t GpuServer::num_keys() {
   std::lock_guard<std::mutex> lk(mu_);
   return shards_.size();
@@ -181,11 +187,29 @@ void GpuServer::HandleGrad(Shard* s, const KVMeta& req, const KVPairs<char>& dat
   CHECK_LT(rank, cfg_.num_workers);
   CHECK(!s->pushed[rank]) << "worker " << rank << " pushed key " << req.key
                           << " twice in one round";
-  CHECK(data.vals.on_gpu()) << "gradient pushes must arrive through the one-sided van";
-  const int fmt = FormatOf(req, cfg_.raw_grad_format);
+  int fmt;
+  const void* slot;
+  if (req.mem.region == kSymmetricRegion) {
+    // staged in the worker's symmetric gradient buffer: read later through the multicast address
+    CHECK(mc_grad_base_ != nullptr) << "symmetric push but SetSymmetricGrads was never called";
+    CHECK_EQ(FormatOf(req, PS_GRAD_BF16), (int)PS_GRAD_BF16) << "in-switch reduction adds bf16 values";
+    CHECK_LE(req.mem.offset + s->n * 2, symm_grad_bytes_);
+    CHECK_EQ(req.mem.offset % 16, (uint64_t)0);
+    fmt = PS_GRAD_MC_BF16;
+    slot = static_cast<const char*>(mc_grad_base_) + req.mem.offset;
+  } else {
+    CHECK(data.vals.on_gpu()) << "gradient pushes must arrive through the one-sided van";
+    fmt = FormatOf(req, cfg_.raw_grad_format);
+    slot = data.vals.data();
+  }
   if (s->num_pushed == 0) s->grad_format = fmt;
   CHECK_EQ(s->grad_format, fmt) << "workers disagree on the gradient wire format";
-  s->slots[rank] = data.vals.data();
+  if (fmt == PS_GRAD_MC_BF16 && s->num_pushed > 0) {
+    for (int w = 0; w < cfg_.num_workers; ++w) {
+      if (s->pushed[w]) CHECK(s->slots[w] == slot) << "workers disagree on the symmetric offset";
+    }
+  }
+  s->slots[rank] = slot;
   s->pushed[rank] = 1;
   ++s->num_pushed;
   // the payload already sits in its slot: the push is complete for the worker
@@ -224,6 +248,10 @@ void GpuServer::MaybeRunRound(Key key, Shard* s) {
   a.num_grads = W;
   a.grad_format = s->grad_format;
   for (int w = 0; w < W; ++w) a.grads[w] = s->slots[w];
+  if (s->grad_format == PS_GRAD_MC_BF16) {
+    a.num_grads = 1;  // one stream: the switch returns the sum over all bound GPUs
+    ++mc_reduce_;
+  }
   a.master = s->master;
   a.m = s->m;
   a.v = s->v;

@@ -79,6 +79,16 @@ class GpuServer {
    *        ONE multimem.st stream from the update kernel instead of W unicast streams.
    */
   void SetSymmetricParams(void* mc_base, const std::vector<void*>& peer_bases, size_t bytes);
+  /*!
+   * \brief NVLS aggregation. Workers stage bf16 gradients in a second symmetric buffer and
+   *        push only a descriptor {kSymmetricRegion, offset}; `mc_base` is this process's
+   *        multicast mapping of that buffer. The update kernel then reads the W-way SUM with
+   *        multimem.ld_reduce (the switch adds in fp32): no landing slots, one 2 B/element
+   *        stream into the server instead of W. Server-only ranks keep their copy zeroed.
+   */
+  void SetSymmetricGrads(void* mc_base, size_t bytes);
+  /*! \brief update kernels whose gradients were reduced inside the switch */
+  uint64_t num_switch_reductions() const { return mc_reduce_.load(); }
   /*! \brief update kernels whose fan-out went through the multicast address */
   uint64_t num_multicast_fanouts() const { return mcast_.load(); }
   /*! \brief optimizer steps applied, summed over keys */
@@ -135,6 +145,9 @@ class GpuServer {
   std::atomic<uint64_t> updates_{0};
   std::atomic<uint64_t> fused_{0};
   std::atomic<uint64_t> mcast_{0};
+  std::atomic<uint64_t> mc_reduce_{0};
+  void* mc_grad_base_ = nullptr;
+  size_t symm_grad_bytes_ = 0;
   void* mc_base_ = nullptr;
   std::vector<void*> peer_bases_;
   size_t symm_bytes_ = 0;

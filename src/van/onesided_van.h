@@ -215,7 +215,17 @@ class OneSidedVan : public TcpVan {
     const int recver = msg.meta.recver;
     const SArray<char>& vals = msg.data[1];
     const uint64_t wire = WireBytes(msg.meta.codec, vals.size());
-    Slot slot = AcquirePushSlot(recver, msg.meta.key, wire);
+    Slot slot;
+    if (msg.meta.mem.region == kSymmetricRegion) {
+      // symmetric push: encode into the sender's OWN copy of the job-wide buffer; the
+      // receiver reads every worker's copy at this offset through the multicast mapping
+      CHECK(msg.stage != nullptr) << "symmetric push without a staging address";
+      slot.ptr = static_cast<char*>(msg.stage);
+      slot.region = kSymmetricRegion;
+      slot.offset = msg.meta.mem.offset;
+    } else {
+      slot = AcquirePushSlot(recver, msg.meta.key, wire);
+    }
     Ticket t = domain_->CopyAsync(slot.ptr, vals.data(), vals.size(), msg.meta.codec,
                                   msg.meta.scale, msg.wait_event, vals.src_device_type_);
     ++copies_;
@@ -407,6 +417,7 @@ class OneSidedVan : public TcpVan {
     const MemRef& mem = msg->meta.mem;
     char* ptr = nullptr;
     if (msg->meta.request && msg->meta.push) {
+      if (mem.region == kSymmetricRegion) return;  // the handler resolves the offset itself
       std::lock_guard<std::mutex> lk(rv_mu_);
       CHECK_LT(static_cast<size_t>(mem.region), my_regions_.size());
       ptr = reinterpret_cast<char*>(my_regions_[mem.region].base + mem.offset);

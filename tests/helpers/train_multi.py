@@ -1,7 +1,7 @@
 """Multi-GPU PS training under torchrun (one process per GPU). Every rank trains the same
 tiny Llama on its own data shard through the PS; at the end all workers must hold
 bit-identical parameters (they all pulled the same server state) and the loss must drop.
-usage: torchrun ... train_multi.py <topology> <grad_wire> <steps>"""
+usage: torchrun ... train_multi.py <topology> <grad_wire> <steps> [symm|nvls]"""
 import os
 import sys
 
@@ -14,13 +14,14 @@ import torch.distributed as dist  # noqa: E402
 import pslite_b200  # noqa: E402
 from pslite_b200.models.llama import Llama, LlamaConfig  # noqa: E402
 from pslite_b200.parallel.launch import init_ps  # noqa: E402
-from pslite_b200.parallel.ps_trainer import (PSWorkerOptimizer, setup_symmetric_params,  # noqa: E402
-                                              symmetric_layout)
+from pslite_b200.parallel.ps_trainer import (PSWorkerOptimizer, setup_symmetric_grads,  # noqa: E402
+                                              setup_symmetric_params, symmetric_layout)
 
 
 def main():
     topo, wire, steps = sys.argv[1], sys.argv[2], int(sys.argv[3])
-    symmetric = len(sys.argv) > 4 and sys.argv[4] == "symm"
+    symmetric = len(sys.argv) > 4 and sys.argv[4] in ("symm", "nvls")
+    nvls_reduce = len(sys.argv) > 4 and sys.argv[4] == "nvls"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     use_cuda = torch.cuda.is_available()
@@ -58,10 +59,20 @@ def main():
         mcast_info = f" multicast_ptr={'yes' if mc else 'NO'}"
         if server is not None:
             server.set_symmetric(mc, peers, nbytes)
+    gbuf = None
+    if nvls_reduce:
+        gbuf, ghdl, gmc, gbytes = setup_symmetric_grads(total, dist.group.WORLD, dev)
+        if not gmc:  # no NVSwitch multicast here: fall back to landing slots
+            nvls_reduce = False
+            mcast_info += " nvls=unavailable"
+        elif server is not None:
+            server.set_symmetric_grads(gmc, gbytes)
+        dist.barrier(group=gloo)
     if ctx.is_worker:
         kv = C.KVWorker(0, 0)
         opt = PSWorkerOptimizer(model.parameters(), kv, S, W, ctx.worker_rank, grad_wire=wire,
-                                chunk_elems=1 << 14, symmetric=symmetric).attach()
+                                chunk_elems=1 << 14, symmetric=symmetric,
+                                grad_buffer=gbuf if nvls_reduce else None).attach()
         opt.init_parameters(barrier=lambda: C.barrier(0, C.WORKER_GROUP, "worker"))
         g = torch.Generator(device=dev).manual_seed(100 + ctx.worker_rank)
         tok = torch.randint(0, cfg.vocab_size, (2, 65), device=dev, generator=g)
@@ -82,7 +93,10 @@ def main():
     print(f"rank {rank}: losses {['%.3f' % l for l in losses[:2]]}..{['%.3f' % l for l in losses[-2:]]} "
           f"checksums_equal={same} updates={server.num_updates() if server else 0} "
           f"fused={server.num_fused_fanouts() if server else 0} "
-          f"mcast={server.num_multicast_fanouts() if server else 0}{mcast_info}", flush=True)
+          f"mcast={server.num_multicast_fanouts() if server else 0} "
+          f"switch_reduce={server.num_switch_reductions() if server else 0}{mcast_info}", flush=True)
+    if nvls_reduce and server is not None:
+        ok = ok and server.num_switch_reductions() == server.num_updates() > 0
     ok = ok and same
     flag = torch.tensor([1.0 if ok else 0.0])
     dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=gloo)
