@@ -25,12 +25,14 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <condition_variable>
 #include <cstdint>
 #include <cstring>
 #include <map>
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "ps/internal/utils.h"
@@ -234,8 +236,21 @@ class IndexPool {
  */
 class ShmDomain : public MemDomain {
  public:
-  ShmDomain() { arena_bytes_ = static_cast<uint64_t>(GetEnv("PS_SHM_ARENA_MB", 256)) << 20; }
+  ShmDomain() {
+    arena_bytes_ = static_cast<uint64_t>(GetEnv("PS_SHM_ARENA_MB", 256)) << 20;
+    // PS_SHM_ASYNC=1: copies run on a background "stream" thread and complete later, like
+    // kernels on a CUDA stream: the van's completion / batching logic gets exercised on CPU
+    if (GetEnv("PS_SHM_ASYNC", 0) != 0) copier_.reset(new std::thread(&ShmDomain::CopierLoop, this));
+  }
   ~ShmDomain() override {
+    if (copier_) {
+      {
+        std::lock_guard<std::mutex> lk(q_mu_);
+        q_stop_ = true;
+      }
+      q_cv_.notify_all();
+      copier_->join();
+    }
     std::lock_guard<std::mutex> lk(mu_);
     for (auto& a : arenas_) {
       munmap(a->base, a->size);
@@ -292,20 +307,66 @@ class ShmDomain : public MemDomain {
   Ticket CopyAsync(void* dst, const void* src, size_t n, int codec, float /*scale*/,
                    void* /*wait_event*/, int /*src_device_type*/ = UNK) override {
     CHECK_EQ(codec, (int)kCodecRaw) << "the shm domain moves raw bytes only";
+    if (copier_) {
+      AsyncOp* op = new AsyncOp();
+      op->dst = dst;
+      op->src = src;
+      op->n = dst != src ? n : 0;
+      {
+        std::lock_guard<std::mutex> lk(q_mu_);
+        q_.push_back(op);
+      }
+      q_cv_.notify_one();
+      Ticket t;
+      t.event = op;
+      return t;
+    }
     if (n && dst != src) memcpy(dst, src, n);
     // make the payload visible before the descriptor that announces it
     std::atomic_thread_fence(std::memory_order_release);
     return Ticket();
   }
-  void Wait(Ticket) override {}
+  bool Ready(Ticket t) override {
+    return !t.event || static_cast<AsyncOp*>(t.event)->done.load(std::memory_order_acquire);
+  }
+  void Wait(Ticket t) override {
+    if (!t.event) return;
+    AsyncOp* op = static_cast<AsyncOp*>(t.event);
+    while (!op->done.load(std::memory_order_acquire)) std::this_thread::yield();
+    delete op;
+  }
 
  private:
+  struct AsyncOp {
+    void* dst = nullptr;
+    const void* src = nullptr;
+    size_t n = 0;
+    std::atomic<bool> done{false};
+  };
+  void CopierLoop() {
+    std::unique_lock<std::mutex> lk(q_mu_);
+    for (;;) {
+      q_cv_.wait(lk, [this] { return q_stop_ || !q_.empty(); });
+      if (q_.empty()) return;
+      AsyncOp* op = q_.front();
+      q_.erase(q_.begin());
+      lk.unlock();
+      if (op->n) memcpy(op->dst, op->src, op->n);
+      op->done.store(true, std::memory_order_release);
+      lk.lock();
+    }
+  }
   struct Arena {
     std::string name;
     char* base = nullptr;
     uint64_t size = 0;
     ArenaAllocator alloc;
   };
+  std::unique_ptr<std::thread> copier_;
+  std::mutex q_mu_;
+  std::condition_variable q_cv_;
+  std::vector<AsyncOp*> q_;
+  bool q_stop_ = false;
   Arena* NewArena(uint64_t bytes) {
     static std::atomic<int> counter{0};
     std::unique_ptr<Arena> a(new Arena());

@@ -301,7 +301,9 @@ class TcpVan : public Van {
     if (msgs.size() == 1 || recver == my_node_.id) {
       int total = 0;
       for (Message* m : msgs) {
-        int n = SendMsg(*m);
+        // qualified on purpose: a derived van's SendMsg would treat the descriptor as a
+        // fresh message (and strip the MemRef it carries)
+        int n = TcpVan::SendMsg(*m);
         if (n < 0) return -1;
         total += n;
       }
@@ -357,6 +359,7 @@ class TcpVan : public Van {
     msg->data.clear();
     auto last_activity = std::chrono::steady_clock::now();
     for (;;) {
+      if (PollDeferred(msg)) return 1 + static_cast<int>(msg->meta.data_size & 0x3fffffff);
       if (PopLoopback(msg)) return 1 + static_cast<int>(msg->meta.data_size & 0x3fffffff);
       // same-host peers: frames arrive in shared-memory rings (round-robin for fairness)
       if (int bytes = PollPipes(msg)) return bytes;
@@ -369,8 +372,9 @@ class TcpVan : public Van {
         if (bytes > 0) return bytes;  // 0: the peer closed, rang a doorbell or offered a ring
       }
       if (int bytes = PollPipes(msg)) return bytes;
-      int timeout_ms = -1;
-      if (!pipe_fds_.empty()) {
+      // a derived van with asynchronous receives in flight keeps this thread polling
+      int timeout_ms = HasDeferred() ? 0 : -1;
+      if (timeout_ms != 0 && !pipe_fds_.empty()) {
         // stay hot for a short while after the last message, then declare ourselves asleep
         // on every ring so that the next writer rings the doorbell
         const auto idle = std::chrono::steady_clock::now() - last_activity;
@@ -757,6 +761,13 @@ class TcpVan : public Van {
   }
 
  protected:
+  /*!
+   * \brief hooks for transports whose payload arrives asynchronously (NcclVan): called on the
+   *        receive thread at the top of every RecvMsg iteration; return true with a message
+   *        whose payload has completed. HasDeferred() == true turns the idle wait into a poll.
+   */
+  virtual bool PollDeferred(Message* /*msg*/) { return false; }
+  virtual bool HasDeferred() { return false; }
   /*! \brief enqueue a message for this van's own RecvMsg and wake it */
   int Loopback(const Message& msg) {
     {
