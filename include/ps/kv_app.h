@@ -529,8 +529,11 @@ int KVWorker<Val>::Pull_(const SArray<Key>& keys, C* vals, D* lens, int cmd, con
     } else {
       CHECK_GE(vals->size(), total_val);
     }
-    if (!is_worker_zpull_) {
-      // two-sided van: stitch the per-server slices into the caller's buffers
+    {
+      // stitch the per-server slices into the caller's buffers. A slice that landed in place
+      // (zero-copy pull of a one-sided van, or TcpVan's direct landing) is skipped by the
+      // pointer test, so this is also right when a one-sided van had to fall back to a
+      // two-sided transfer for a buffer it could not export.
       Val* out = vals->data();
       int* out_len = nullptr;
       if (lens) {
@@ -542,7 +545,11 @@ int KVWorker<Val>::Pull_(const SArray<Key>& keys, C* vals, D* lens, int cmd, con
         out_len = lens->data();
       }
       for (const auto& s : parts) {
-        if (s.vals.data() != out) memcpy(out, s.vals.data(), s.vals.size() * sizeof(Val));
+        if (s.vals.data() != out && s.vals.size()) {
+          CHECK(!s.vals.on_gpu()) << "pulled values are in device memory but did not land in the "
+                                     "destination; pull into an exportable device buffer";
+          memcpy(out, s.vals.data(), s.vals.size() * sizeof(Val));
+        }
         out += s.vals.size();
         if (out_len) {
           memcpy(out_len, s.lens.data(), s.lens.size() * sizeof(int));

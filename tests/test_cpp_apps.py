@@ -36,6 +36,23 @@ def test_kv_app_tcp(built_native_tree, s, w):
     assert rc == 0 and out.count("test_kv_app PASSED") == w, out[-3000:]
 
 
+@pytest.mark.parametrize("async_copies", [0, 1])
+def test_kv_app_one_sided_van_with_plain_buffers(built_native_tree, async_copies):
+    """std::vector buffers cannot be exported: the shm van falls back to two-sided transfers for
+    them and Pull() must still stitch the slices into the caller's vector."""
+    rc, out = launch(built_native_tree, 2, 2, "test_kv_app",
+                     env={"PS_VAN_TYPE": "shm", "PS_SHM_ASYNC": async_copies})
+    assert rc == 0 and out.count("test_kv_app PASSED") == 2, out[-3000:]
+
+
+def test_benchmark_one_sided_async_copies_many_peers(built_native_tree):
+    """3 workers x 3 servers, exportable buffers, copies completing asynchronously."""
+    env = {"PS_VAN_TYPE": "shm", "PS_SHM_ASYNC": 1, "TEST_EXPORTABLE_VALS": 1, "NUM_KEY_PER_SERVER": 10,
+           "TOTAL_DURATION": 4, "LOG_DURATION": 2}
+    rc, out = launch(built_native_tree, 3, 3, "test_benchmark", 262144, 100, 1, env=env)
+    assert rc == 0 and "goodput" in out, out[-3000:]
+
+
 def test_kv_app_ipc_sockets(built_native_tree):
     rc, out = launch(built_native_tree, 2, 2, "test_kv_app", env={"DMLC_LOCAL": 1})
     assert rc == 0 and out.count("PASSED") == 2, out[-3000:]
