@@ -1,4 +1,5 @@
 // Unit tests: SArray, Range, Environment, queues, wire codec, allocators.
+#include <sys/wait.h>
 #include <thread>
 #include "core/wire.h"
 #include "ps/internal/parallel_sort.h"
@@ -240,6 +241,27 @@ TEST(shm_pipe_stream_and_doorbell) {
   CHECK(tx->ReaderNeedsDoorbell());
   CHECK(!rx->PrepareSleep());
   CHECK(rx->Read(&got, sizeof(got)));
+}
+
+TEST(stale_shm_sweep) {
+  // an object named after a process that no longer exists is removed; a live creator's is kept
+  pid_t child = fork();
+  if (child == 0) _exit(0);
+  int status = 0;
+  waitpid(child, &status, 0);
+  const std::string dead = "/pslite_sweeptest_" + std::to_string(child) + "_0";
+  const std::string live = "/pslite_sweeptest_" + std::to_string(getpid()) + "_0";
+  for (const std::string& n : {dead, live}) {
+    int fd = shm_open(n.c_str(), O_CREAT | O_RDWR, 0600);
+    CHECK_GE(fd, 0);
+    close(fd);
+  }
+  CHECK_GE(SweepStaleShm("pslite_sweeptest_"), 1);
+  CHECK_LT(shm_open(dead.c_str(), O_RDWR, 0600), 0);
+  int fd = shm_open(live.c_str(), O_RDWR, 0600);
+  CHECK_GE(fd, 0);
+  close(fd);
+  shm_unlink(live.c_str());
 }
 
 TEST(index_pool) {

@@ -37,6 +37,7 @@
 
 #include "ps/internal/utils.h"
 #include "ps/sarray.h"
+#include "van/shm_util.h"
 
 namespace ps {
 
@@ -124,6 +125,8 @@ class MemDomain {
   virtual bool Ready(Ticket t) { return t.event == nullptr; }
   /*! \brief stream-like handle applications may enqueue their own work on (may be null) */
   virtual void* Stream() { return nullptr; }
+  /*! \brief the van stopped: drop global names (mappings stay valid until the process ends) */
+  virtual void ReleaseNames() {}
 };
 
 /*! \brief first-fit offset allocator with coalescing; thread-safe */
@@ -238,6 +241,8 @@ class ShmDomain : public MemDomain {
  public:
   ShmDomain() {
     arena_bytes_ = static_cast<uint64_t>(GetEnv("PS_SHM_ARENA_MB", 256)) << 20;
+    static const int swept = SweepStaleShm("pslite_b200_");  // arenas of processes that were killed
+    (void)swept;
     // PS_SHM_ASYNC=1: copies run on a background "stream" thread and complete later, like
     // kernels on a CUDA stream: the van's completion / batching logic gets exercised on CPU
     if (GetEnv("PS_SHM_ASYNC", 0) != 0) copier_.reset(new std::thread(&ShmDomain::CopierLoop, this));
@@ -254,11 +259,19 @@ class ShmDomain : public MemDomain {
     std::lock_guard<std::mutex> lk(mu_);
     for (auto& a : arenas_) {
       munmap(a->base, a->size);
-      shm_unlink(a->name.c_str());
+      if (!a->retired) shm_unlink(a->name.c_str());
     }
     for (auto& m : imported_) munmap(m.second.first, m.second.second);
   }
   const char* name() const override { return "shm"; }
+  void ReleaseNames() override {
+    // the process-wide Postoffice (and with it this domain) is never destroyed: unlink here
+    std::lock_guard<std::mutex> lk(mu_);
+    for (auto& a : arenas_) {
+      if (!a->retired) shm_unlink(a->name.c_str());
+      a->retired = true;  // still mapped (old pointers stay valid) but never handed out again
+    }
+  }
 
   bool Handles(int /*device_type*/, const void* ptr) override { return FindArena(ptr) != nullptr; }
 
@@ -266,6 +279,7 @@ class ShmDomain : public MemDomain {
     {
       std::lock_guard<std::mutex> lk(mu_);
       for (auto& a : arenas_) {
+        if (a->retired) continue;
         uint64_t off = a->alloc.Alloc(bytes);
         if (off != UINT64_MAX) return a->base + off;
       }
@@ -281,7 +295,7 @@ class ShmDomain : public MemDomain {
   }
   bool Export(const void* p, RegionDesc* out) override {
     Arena* a = FindArena(p);
-    if (!a) return false;
+    if (!a || a->retired) return false;
     out->pid = static_cast<int32_t>(getpid());
     out->dev = -1;
     out->base = reinterpret_cast<uint64_t>(a->base);
@@ -358,6 +372,7 @@ class ShmDomain : public MemDomain {
   }
   struct Arena {
     std::string name;
+    bool retired = false;
     char* base = nullptr;
     uint64_t size = 0;
     ArenaAllocator alloc;

@@ -67,6 +67,7 @@ class OneSidedVan : public TcpVan {
   void Stop() override {
     StopCompleter();
     TcpVan::Stop();
+    domain_->ReleaseNames();
     std::lock_guard<std::mutex> lk(rv_mu_);
     push_slots_.clear();
     landing_.clear();

@@ -47,7 +47,10 @@ class ShmPipe {
     int fd = shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
     if (fd < 0) return nullptr;
     const size_t bytes = sizeof(Ctl) + cap;
-    if (ftruncate(fd, static_cast<off_t>(bytes)) != 0) {
+    // reserve the pages now: on a small /dev/shm (containers default to 64 MB) a ring that
+    // only ftruncate()d would SIGBUS on first touch instead of failing here
+    if (ftruncate(fd, static_cast<off_t>(bytes)) != 0 ||
+        posix_fallocate(fd, 0, static_cast<off_t>(bytes)) != 0) {
       close(fd);
       shm_unlink(name.c_str());
       return nullptr;

@@ -46,6 +46,7 @@
 #include "ps/internal/postoffice.h"
 #include "ps/internal/van.h"
 #include "van/shm_pipe.h"
+#include "van/shm_util.h"
 
 namespace ps {
 
@@ -134,8 +135,12 @@ class TcpVan : public Van {
     connect_timeout_s_ = GetEnv("PS_CONNECT_TIMEOUT", 120);
     direct_pull_ = GetEnv("PS_TCP_DIRECT_PULL", 1) != 0;
     use_pipes_ = GetEnv("PS_SHM_PIPE", 1) != 0;
-    pipe_bytes_ = static_cast<size_t>(GetEnv("PS_SHM_PIPE_KB", 4096)) << 10;
+    pipe_bytes_ = static_cast<size_t>(GetEnv("PS_SHM_PIPE_KB", 256)) << 10;
     pipe_spin_us_ = GetEnv("PS_SHM_PIPE_SPIN_US", 50);
+    if (use_pipes_) {
+      static const int swept = SweepStaleShm("pslb200_");  // rings of processes that were killed
+      (void)swept;
+    }
     if (!pool_) {
       pool_ = std::make_shared<RecvBufferPool>(static_cast<size_t>(GetEnv("PS_TCP_POOL_MB", 1024))
                                                << 20);
@@ -828,7 +833,7 @@ class TcpVan : public Van {
   std::vector<int> pipe_fds_;                                  // inbound connections with a ring
   size_t pipe_cursor_ = 0;
   bool use_pipes_ = true;
-  size_t pipe_bytes_ = 4u << 20;
+  size_t pipe_bytes_ = 256u << 10;
   int pipe_spin_us_ = 50;
   std::deque<int> ready_fds_;      // touched by the receive thread only
   std::mutex peers_mu_;
