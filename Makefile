@@ -26,7 +26,7 @@ CORE_SRCS := src/core/wire.cc src/core/customer.cc src/core/postoffice.cc src/co
 CU_SRCS :=
 ifeq ($(USE_CUDA),1)
 CXXFLAGS += -DPS_USE_CUDA=1 -I$(CUDA_HOME)/include
-CORE_SRCS += src/van/cuda_domain.cc src/server/gpu_server.cc
+CORE_SRCS += src/van/cuda_domain.cc src/van/nccl_van.cc src/server/gpu_server.cc
 CU_SRCS += src/kernels/copy_kernels.cu src/kernels/update_kernels.cu src/kernels/model_kernels.cu
 LDFLAGS += -L$(CUDA_HOME)/lib64 -lcudart -ldl
 endif

@@ -325,11 +325,26 @@ void GpuServer::ServePullFromLocal(Key key, Shard* s, const KVMeta& req) {
     return;
   }
   CHECK(!req.mem.valid()) << "pull destination region unknown to this server";
-  // two-sided requester (TCP): cast into a scratch buffer and stage through host memory
+  // two-sided requester: cast into a scratch buffer ...
   void* scratch = nullptr;
   GS_CUDA(cudaMalloc(&scratch, s->n * 2 + 16));
   CHECK_EQ(ps_launch_copy(scratch, s->master, s->n * 4, PS_CODEC_F32_TO_BF16, 1.f, cfg_.max_ctas, st),
            0);
+  if (po_->van()->GetType() == "nccl") {
+    // ... which the nccl van sends from device memory (it orders the send behind this stream)
+    const int dev = dev_;
+    SArray<char> dvals;
+    dvals.reset(static_cast<char*>(scratch), s->n * 2,
+                [dev](char* p) {
+                  cudaSetDevice(dev);
+                  cudaFree(p);
+                },
+                GPU, dev_, GPU, dev_);
+    res.vals = dvals;
+    server_->Response(req, res);
+    return;
+  }
+  // ... or, for a host-only transport (TCP), stage it through host memory
   SArray<char> host(s->n * 2);
   cudaStream_t cst = static_cast<cudaStream_t>(stream_);
   GS_CUDA(cudaMemcpyAsync(host.data(), scratch, s->n * 2, cudaMemcpyDeviceToHost, cst));

@@ -3,7 +3,8 @@
  * \brief Transport selection. The RDMA-class names of the reference ("1",
  * "ibverbs", "ucx", "fabric"; src/van.cc:79-103, src/postoffice.cc:52-58) all
  * resolve to the one-sided NVLink van: on a B200 NVSwitch box peer HBM over
- * NVLink *is* the RDMA fabric.
+ * NVLink *is* the RDMA fabric. "nccl" selects the two-sided NcclVan (the FabricVan
+ * counterpart) for peers that cannot map each other's memory.
  */
 #include "van/van_factory.h"
 #include "ps/internal/postoffice.h"
@@ -12,6 +13,7 @@
 #include "van/tcp_van.h"
 #ifdef PS_USE_CUDA
 #include "van/cuda_domain.h"
+#include "van/nccl_van.h"
 #endif
 
 namespace ps {
@@ -30,6 +32,15 @@ Van* CreateVanByType(const std::string& type, Postoffice* postoffice) {
     return new OneSidedVan(postoffice, dom, "nvl");
 #else
     LOG(FATAL) << "van type '" << type << "' needs a build with PS_USE_CUDA";
+#endif
+  }
+  if (type == "nccl") {
+#ifdef PS_USE_CUDA
+    Van* van = CreateNcclVan(postoffice);
+    CHECK(van) << "van type 'nccl' needs a GPU and libnccl.so.2";
+    return van;
+#else
+    LOG(FATAL) << "van type 'nccl' needs a build with PS_USE_CUDA";
 #endif
   }
   LOG(FATAL) << "unsupported van type: " << type;
