@@ -405,7 +405,7 @@ def run_reference(args, dist: Dist) -> dict:
     out = None
     if dist.rank == 0:
         W = S = 1 if dist.world == 1 else dist.world // 2
-        port = 20000 + (os.getpid() % 20000)
+        port = 12000 + (os.getpid() % 20000)
         env = dict(os.environ)
         env.update({"DMLC_NUM_WORKER": str(W), "DMLC_NUM_SERVER": str(S),
                     "DMLC_PS_ROOT_URI": "127.0.0.1", "DMLC_PS_ROOT_PORT": str(port),

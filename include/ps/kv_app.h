@@ -18,6 +18,9 @@
 #ifndef PS_KV_APP_H_
 #define PS_KV_APP_H_
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <functional>
 #include <mutex>
 #include <string>
@@ -216,7 +219,12 @@ class KVServer : public SimpleApp {
                                        KVServer* server)>;
   void set_request_handle(const ReqHandle& h) {
     CHECK(h) << "invalid request handle";
-    request_handle_ = h;
+    {
+      std::lock_guard<std::mutex> lk(handle_mu_);
+      request_handle_ = h;
+      handle_ready_.store(true, std::memory_order_release);
+    }
+    handle_cv_.notify_all();
   }
 
   /*! \brief reply to `req`; `res` is empty for a push ack */
@@ -250,6 +258,11 @@ class KVServer : public SimpleApp {
   void RegisterRecvBuffer_(int worker_id, SArray<Key>& keys, const SArray<Val>& vals,
                            const SArray<int>& lens, int cmd);
   ReqHandle request_handle_;
+  // a request can arrive between the constructor (which starts receiving) and
+  // set_request_handle(): Process waits for the handle instead of failing
+  std::mutex handle_mu_;
+  std::condition_variable handle_cv_;
+  std::atomic<bool> handle_ready_{false};
 };
 
 /*! \brief example handler: store[key] += val on push, lookup on pull (scalar per key) */
@@ -324,7 +337,12 @@ void KVServer<Val>::Process(const Message& msg) {
       CHECK_EQ(data.lens.size(), data.keys.size());
     }
   }
-  CHECK(request_handle_);
+  if (!handle_ready_.load(std::memory_order_acquire)) {
+    std::unique_lock<std::mutex> lk(handle_mu_);
+    handle_cv_.wait_for(lk, std::chrono::seconds(30),
+                        [this] { return handle_ready_.load(std::memory_order_acquire); });
+  }
+  CHECK(handle_ready_.load(std::memory_order_acquire)) << "KVServer got a request but no request handle was set";
   request_handle_(meta, data, this);
 }
 

@@ -13,7 +13,7 @@ run_ours() {  # van len extra-env...
     timeout 300 scripts/local.sh 1 1 build/test_benchmark $len 100000 1 2>&1 | grep -oE "goodput: [0-9.e+-]+" | tail -n 1 | cut -d' ' -f2
 }
 run_ref() {
-  local len=$1 port=$((20000 + RANDOM % 20000))
+  local len=$1 port=$((12000 + RANDOM % 20000))
   local common="DMLC_NUM_WORKER=1 DMLC_NUM_SERVER=1 DMLC_PS_ROOT_URI=127.0.0.1 DMLC_PS_ROOT_PORT=$port DMLC_NODE_HOST=127.0.0.1 DMLC_GROUP_SIZE=1 DMLC_LOCAL=1 NUM_KEY_PER_SERVER=40 TOTAL_DURATION=12 LOG_DURATION=4"
   export LD_LIBRARY_PATH=baseline/_ref/lib:$LD_LIBRARY_PATH
   env $common DMLC_ROLE=scheduler timeout 300 $REF $len 10 1 >/dev/null 2>&1 &

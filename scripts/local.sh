@@ -13,7 +13,7 @@ export DMLC_NUM_WORKER=$1; shift
 bin=$1; shift
 args="$@"
 export DMLC_PS_ROOT_URI=${DMLC_PS_ROOT_URI:-127.0.0.1}
-export DMLC_PS_ROOT_PORT=${DMLC_PS_ROOT_PORT:-$((20000 + RANDOM % 20000))}
+export DMLC_PS_ROOT_PORT=${DMLC_PS_ROOT_PORT:-$((12000 + RANDOM % 20000))}
 export DMLC_NODE_HOST=${DMLC_NODE_HOST:-127.0.0.1}
 pids=()
 DMLC_ROLE=scheduler ${bin} ${args} &

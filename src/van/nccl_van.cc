@@ -385,6 +385,17 @@ class NcclVan : public TcpVan {
     slot = std::move(link);
   }
 
+  /*! \brief bytes per element of the value segment (Meta::val_len counts elements) */
+  static uint64_t ValueSize(const Message& msg) {
+    if (msg.meta.data_type.size() < 2) return 1;
+    switch (msg.meta.data_type[1]) {
+      case INT16: case UINT16: return 2;
+      case INT32: case UINT32: case FLOAT: return 4;
+      case INT64: case UINT64: case DOUBLE: return 8;
+      default: return 1;
+    }
+  }
+
   static bool IsDevicePointer(const void* p) {
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
@@ -407,7 +418,7 @@ class NcclVan : public TcpVan {
       auto it = gpu_registered_.find(pk);
       if (it != gpu_registered_.end() && it->second.size() >= wire) return it->second.data();
     } else if (!msg.meta.request && !msg.meta.push && msg.meta.addr != 0 &&
-               static_cast<uint64_t>(msg.meta.val_len) >= wire) {
+               static_cast<uint64_t>(msg.meta.val_len) * ValueSize(msg) >= wire) {
       char* dst = reinterpret_cast<char*>(msg.meta.addr);
       if (IsDevicePointer(dst)) return dst;
       *host_dst = dst;

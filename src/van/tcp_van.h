@@ -176,6 +176,7 @@ class TcpVan : public Van {
     int port = node.port;
     unsigned seed = static_cast<unsigned>(time(nullptr)) + static_cast<unsigned>(getpid()) +
                     static_cast<unsigned>(port);
+    int fixed_port_waits = 0;
     for (int attempt = 0; attempt <= max_retry; ++attempt) {
       int fd = -1;
       bool ok = false;
@@ -202,7 +203,16 @@ class TcpVan : public Van {
         AddToEpoll(fd);
         return port;
       }
+      const int why = errno;
       close(fd);
+      if (max_retry == 0 && why == EADDRINUSE && fixed_port_waits < 30) {
+        // a fixed port (the scheduler's) that something — typically a short-lived outgoing
+        // connection that was handed this number — still occupies: wait for it, do not give up
+        ++fixed_port_waits;
+        --attempt;
+        std::this_thread::sleep_for(std::chrono::milliseconds(100));
+        continue;
+      }
       if (attempt == max_retry) break;
       port = 10000 + static_cast<int>(rand_r(&seed) % 40000);
     }
