@@ -2,10 +2,12 @@
 #   make            -> build/libpslite.a, benchmark apps, C++ unit tests
 #   make check      -> run the C++ unit tests (CPU only)
 # CUDA sources are cross-compiled for sm_100a (no GPU needed to build).
-# Feature flags mirror the reference Makefile (USE_CUDA/USE_KEY32/ASAN, Makefile:24-84).
+# Feature flags mirror the reference Makefile (USE_CUDA/USE_KEY32/ASAN, Makefile:24-84); TSAN is new.
+# Sanitizer builds: make CXX=/usr/bin/g++ ASAN=1 USE_CUDA=0 BUILD=build-asan (or TSAN=1, build-tsan).
 USE_CUDA ?= 1
 USE_KEY32 ?= 0
 ASAN ?= 0
+TSAN ?= 0
 CUDA_HOME ?= /usr/local/cuda
 BUILD ?= build
 
@@ -21,6 +23,10 @@ ifeq ($(ASAN),1)
 CXXFLAGS += -fsanitize=address -fno-omit-frame-pointer
 LDFLAGS += -fsanitize=address
 endif
+ifeq ($(TSAN),1)
+CXXFLAGS += -fsanitize=thread -fno-omit-frame-pointer
+LDFLAGS += -fsanitize=thread
+endif
 
 CORE_SRCS := src/core/wire.cc src/core/customer.cc src/core/postoffice.cc src/core/van.cc src/van/van_factory.cc
 CU_SRCS :=
@@ -35,7 +41,10 @@ CORE_OBJS := $(patsubst %.cc,$(BUILD)/%.o,$(CORE_SRCS))
 CU_OBJS := $(patsubst %.cu,$(BUILD)/%.o,$(CU_SRCS))
 LIB := $(BUILD)/libpslite.a
 
-APPS := $(BUILD)/test_benchmark $(BUILD)/kernel_bench $(BUILD)/test_kv_app $(BUILD)/test_simple_app $(BUILD)/test_connection $(BUILD)/test_ipc_benchmark $(BUILD)/test_benchmark_stress $(BUILD)/test_recovery
+APPS := $(BUILD)/test_benchmark $(BUILD)/test_kv_app $(BUILD)/test_simple_app $(BUILD)/test_connection $(BUILD)/test_ipc_benchmark $(BUILD)/test_benchmark_stress $(BUILD)/test_recovery
+ifeq ($(USE_CUDA),1)
+APPS += $(BUILD)/kernel_bench
+endif
 TESTS := $(patsubst cpp_tests/%.cc,$(BUILD)/cpp_tests/%,$(wildcard cpp_tests/*.cc))
 
 all: $(LIB) $(APPS) $(TESTS)

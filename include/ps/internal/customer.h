@@ -36,7 +36,16 @@ class Customer {
   /*! \brief invoked (on the customer thread, or inline) for every message addressed here */
   typedef std::function<void(const Message& recved)> RecvHandle;
 
-  Customer(int app_id, int customer_id, const RecvHandle& recv_handle, Postoffice* postoffice);
+  /*!
+   * \param start_now register with the postoffice and start receiving inside the constructor.
+   *        Owners that store the pointer in a member their handler uses (KVWorker / KVServer /
+   *        SimpleApp keep it in `obj_`) pass false and call Start() after the assignment: a
+   *        message parked for this customer would otherwise reach the handler before `obj_` is set.
+   */
+  Customer(int app_id, int customer_id, const RecvHandle& recv_handle, Postoffice* postoffice,
+           bool start_now = true);
+  /*! \brief register + start the receive thread (idempotent) */
+  void Start();
   ~Customer();
   Customer(const Customer&) = delete;
   Customer& operator=(const Customer&) = delete;
@@ -80,6 +89,7 @@ class Customer {
   RecvHandle recv_handle_;
   Postoffice* postoffice_;
   bool direct_dispatch_ = false;
+  bool started_ = false;
 
   ThreadsafeQueue<Message> inbox_;
   std::unique_ptr<std::thread> recv_thread_;

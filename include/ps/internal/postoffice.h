@@ -17,6 +17,7 @@
 #include <functional>
 #include <memory>
 #include <mutex>
+#include <shared_mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -50,6 +51,12 @@ class Postoffice {
   void RemoveCustomer(Customer* customer);
   /*! \brief lookup; waits up to `timeout` seconds for the customer to be created */
   Customer* GetCustomer(int app_id, int customer_id, int timeout = 0) const;
+  /*!
+   * \brief hand `msg` to the customer if it exists (false otherwise). Unlike
+   *        GetCustomer()->Accept() this cannot race with the customer's destruction:
+   *        RemoveCustomer waits for deliveries in flight.
+   */
+  bool Deliver(int app_id, int customer_id, const Message& msg);
 
   /*! \brief instance ids of a group id, or {id} for a single node id */
   const std::vector<int>& GetNodeIDs(int node_id) const {
@@ -117,6 +124,7 @@ class Postoffice {
 
   Van* van_ = nullptr;
   mutable std::mutex mu_;
+  std::shared_mutex deliver_mu_;  // shared: a delivery in flight; exclusive: a customer leaving
   mutable std::condition_variable customer_cv_;
   std::unordered_map<int, std::unordered_map<int, Customer*>> customers_;
   std::unordered_map<int, std::vector<int>> node_ids_;

@@ -102,9 +102,10 @@ class KVWorker : public SimpleApp {
     instance_idx_ = instance_idx;
     CHECK_GT(postoffice_->group_size(), instance_idx);
     slicer_ = std::bind(&KVWorker<Val>::DefaultSlicer, this, _1, _2, _3);
-    obj_ = new Customer(app_id, customer_id, std::bind(&KVWorker<Val>::Process, this, _1),
-                        postoffice_);
     is_worker_zpull_ = kv_detail::OneSidedVanSelected();
+    obj_ = new Customer(app_id, customer_id, std::bind(&KVWorker<Val>::Process, this, _1),
+                        postoffice_, false);
+    obj_->Start();  // only now: Process() dereferences obj_
   }
   virtual ~KVWorker() {
     delete obj_;
@@ -207,7 +208,8 @@ class KVServer : public SimpleApp {
     CHECK(postoffice_) << is_scheduler << " " << instance_idx;
     instance_idx_ = instance_idx;
     // servers run exactly one customer per app: customer_id == app_id
-    obj_ = new Customer(app_id, app_id, std::bind(&KVServer::Process, this, _1), postoffice_);
+    obj_ = new Customer(app_id, app_id, std::bind(&KVServer::Process, this, _1), postoffice_, false);
+    obj_->Start();  // only now: Process() / Response() dereference obj_
   }
   virtual ~KVServer() {
     delete obj_;

@@ -43,7 +43,8 @@ class SimpleApp {
   explicit SimpleApp(int app_id, int customer_id, Postoffice* postoffice = nullptr) : SimpleApp() {
     postoffice_ = postoffice != nullptr ? postoffice : Postoffice::Get();
     obj_ = new Customer(app_id, customer_id,
-                        [this](const Message& m) { this->Process(m); }, postoffice_);
+                        [this](const Message& m) { this->Process(m); }, postoffice_, false);
+    obj_->Start();  // after the assignment: handlers reach the customer through obj_
   }
   virtual ~SimpleApp() {
     delete obj_;

@@ -16,11 +16,17 @@ const size_t kInitialRing = 1024;
 }
 
 Customer::Customer(int app_id, int customer_id, const RecvHandle& recv_handle,
-                   Postoffice* postoffice)
+                   Postoffice* postoffice, bool start_now)
     : app_id_(app_id), customer_id_(customer_id), recv_handle_(recv_handle),
       postoffice_(postoffice) {
   ring_.resize(kInitialRing);
   direct_dispatch_ = GetEnv("PS_DIRECT_DISPATCH", 0) != 0;
+  if (start_now) Start();
+}
+
+void Customer::Start() {
+  if (started_) return;
+  started_ = true;
   postoffice_->AddCustomer(this);
   if (!direct_dispatch_) {
     recv_thread_.reset(new std::thread(&Customer::Receiving, this));
@@ -28,7 +34,7 @@ Customer::Customer(int app_id, int customer_id, const RecvHandle& recv_handle,
 }
 
 Customer::~Customer() {
-  postoffice_->RemoveCustomer(this);
+  if (started_) postoffice_->RemoveCustomer(this);
   if (recv_thread_) {
     Message bye;
     bye.meta.control.cmd = Control::TERMINATE;

@@ -161,12 +161,25 @@ void Postoffice::AddCustomer(Customer* customer) {
 }
 
 void Postoffice::RemoveCustomer(Customer* customer) {
-  std::lock_guard<std::mutex> lk(mu_);
-  const int app_id = CHECK_NOTNULL(customer)->app_id();
-  auto it = customers_.find(app_id);
-  if (it == customers_.end()) return;
-  it->second.erase(customer->customer_id());
-  if (it->second.empty()) customers_.erase(it);
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    const int app_id = CHECK_NOTNULL(customer)->app_id();
+    auto it = customers_.find(app_id);
+    if (it != customers_.end()) {
+      it->second.erase(customer->customer_id());
+      if (it->second.empty()) customers_.erase(it);
+    }
+  }
+  // nobody can look the customer up any more; let deliveries that already did finish
+  std::unique_lock<std::shared_mutex> drain(deliver_mu_);
+}
+
+bool Postoffice::Deliver(int app_id, int customer_id, const Message& msg) {
+  std::shared_lock<std::shared_mutex> in_flight(deliver_mu_);
+  Customer* obj = GetCustomer(app_id, customer_id, 0);
+  if (!obj) return false;
+  obj->Accept(msg);
+  return true;
 }
 
 Customer* Postoffice::GetCustomer(int app_id, int customer_id, int timeout) const {

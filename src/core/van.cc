@@ -284,8 +284,7 @@ void Van::ProcessDataMsg(Message* msg) {
   const int app_id = msg->meta.app_id;
   // servers run one customer per app; workers may run several
   const int customer_id = postoffice_->is_worker() ? msg->meta.customer_id : app_id;
-  Customer* obj = postoffice_->GetCustomer(app_id, customer_id, 0);
-  if (!obj) {
+  if (!postoffice_->Deliver(app_id, customer_id, *msg)) {
     // The application has not created this customer yet (e.g. it is still inside the
     // start-up barrier). Park the message instead of blocking the receive thread — the
     // reference waits here for up to 5 s (src/van.cc:435), during which no barrier
@@ -294,7 +293,6 @@ void Van::ProcessDataMsg(Message* msg) {
     parked_.push_back(*msg);
     return;
   }
-  obj->Accept(*msg);
 
   if (profiling_ && !msg->data.empty() && msg->data[0].size() >= 2 && !msg->data[0].on_gpu()) {
     auto us = std::chrono::duration_cast<std::chrono::microseconds>(
@@ -316,10 +314,7 @@ void Van::DeliverParked() {
   }
   for (Message& m : todo) {
     const int customer_id = postoffice_->is_worker() ? m.meta.customer_id : m.meta.app_id;
-    Customer* obj = postoffice_->GetCustomer(m.meta.app_id, customer_id, 0);
-    if (obj) {
-      obj->Accept(m);
-    } else {
+    if (!postoffice_->Deliver(m.meta.app_id, customer_id, m)) {
       std::lock_guard<std::mutex> lk(parked_mu_);
       parked_.push_back(m);
     }

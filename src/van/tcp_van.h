@@ -133,7 +133,10 @@ class TcpVan : public Van {
     if (epfd_ >= 0) return;
     local_ipc_ = GetEnv("DMLC_LOCAL", 0) != 0;
     connect_timeout_s_ = GetEnv("PS_CONNECT_TIMEOUT", 120);
-    direct_pull_ = GetEnv("PS_TCP_DIRECT_PULL", 1) != 0;
+    // landing a pull reply straight in the caller's buffer is only safe if every reply is
+    // wanted: with PS_RESEND a retransmitted duplicate can arrive after the caller has
+    // already consumed the first copy and released the buffer
+    direct_pull_ = GetEnv("PS_TCP_DIRECT_PULL", 1) != 0 && GetEnv("PS_RESEND", 0) == 0;
     use_pipes_ = GetEnv("PS_SHM_PIPE", 1) != 0;
     pipe_bytes_ = static_cast<size_t>(GetEnv("PS_SHM_PIPE_KB", 256)) << 10;
     pipe_spin_us_ = GetEnv("PS_SHM_PIPE_SPIN_US", 50);
