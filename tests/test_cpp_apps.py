@@ -24,7 +24,7 @@ def launch(build_dir, servers, workers, app, *args, env=None, timeout=120):
 
 
 def test_cpp_unit_tests(built_native_tree):
-    for t in ("test_foundation", "test_inproc_cluster"):
+    for t in ("test_foundation", "test_inproc_cluster", "test_api_surface"):
         r = subprocess.run([os.path.join(built_native_tree, "cpp_tests", t)], capture_output=True,
                            text=True, timeout=120)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
