@@ -13,7 +13,7 @@ BUILD ?= build
 
 CXX ?= g++
 NVCC ?= $(CUDA_HOME)/bin/nvcc
-CXXFLAGS := -std=c++17 -O2 -g -Wall -Wno-unused-function -fPIC -Iinclude -Isrc -pthread
+CXXFLAGS := -std=c++17 -O2 -g -Wall -Wno-unused-function -Wno-overloaded-virtual -fPIC -Iinclude -Isrc -pthread
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Isrc -Iinclude
 LDFLAGS := -pthread -lrt
 ifeq ($(USE_KEY32),1)
@@ -28,11 +28,11 @@ CXXFLAGS += -fsanitize=thread -fno-omit-frame-pointer
 LDFLAGS += -fsanitize=thread
 endif
 
-CORE_SRCS := src/core/wire.cc src/core/customer.cc src/core/postoffice.cc src/core/van.cc src/van/van_factory.cc
+CORE_SRCS := src/core/wire.cc src/core/customer.cc src/core/postoffice.cc src/core/van.cc src/van/van_factory.cc src/kernels/host_kernels.cc src/server/gpu_server.cc
 CU_SRCS :=
 ifeq ($(USE_CUDA),1)
 CXXFLAGS += -DPS_USE_CUDA=1 -I$(CUDA_HOME)/include
-CORE_SRCS += src/van/cuda_domain.cc src/van/nccl_van.cc src/server/gpu_server.cc
+CORE_SRCS += src/van/cuda_domain.cc src/van/nccl_van.cc
 CU_SRCS += src/kernels/copy_kernels.cu src/kernels/update_kernels.cu src/kernels/model_kernels.cu
 LDFLAGS += -L$(CUDA_HOME)/lib64 -lcudart -ldl
 endif

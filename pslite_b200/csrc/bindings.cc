@@ -22,6 +22,7 @@
 #include <unordered_map>
 
 #include "kernels/model_kernels.h"
+#include "kernels/host_kernels.h"
 #include "kernels/ps_kernels.h"
 #include "ps/ps.h"
 #include "server/gpu_server.h"
@@ -332,6 +333,7 @@ class PyGpuServer {
   uint64_t num_switch_reductions() { return impl_->num_switch_reductions(); }
   uint64_t num_multicast_fanouts() { return impl_->num_multicast_fanouts(); }
   uint64_t num_updates() { return impl_->num_updates(); }
+  bool on_device() { return impl_->on_device(); }
   uint64_t num_fused_fanouts() { return impl_->num_fused_fanouts(); }
   size_t num_keys() { return impl_->num_keys(); }
   size_t state_bytes() { return impl_->state_bytes(); }
@@ -460,6 +462,7 @@ PYBIND11_MODULE(_C, m) {
       .def("set_symmetric", &PyGpuServer::set_symmetric, py::arg("mc_ptr"), py::arg("peer_ptrs"),
            py::arg("bytes"))
       .def("num_multicast_fanouts", &PyGpuServer::num_multicast_fanouts)
+      .def("on_device", &PyGpuServer::on_device)
       .def("set_symmetric_grads", &PyGpuServer::set_symmetric_grads, py::arg("mc_ptr"), py::arg("bytes"))
       .def("num_switch_reductions", &PyGpuServer::num_switch_reductions)
       .def("num_updates", &PyGpuServer::num_updates)
@@ -521,12 +524,22 @@ PYBIND11_MODULE(_C, m) {
   // ---- raw kernel entry points (numerics tests, standalone use) ----
   m.def("copy_codec", [](torch::Tensor dst, const torch::Tensor& src, int codec, float scale,
                          int max_ctas) {
-    TORCH_CHECK(dst.is_cuda() && src.is_cuda(), "copy_codec needs CUDA tensors");
+    if (!dst.is_cuda() && !src.is_cuda()) {  // CPU twin (src/kernels/host_kernels.cc)
+      TORCH_CHECK(ps_host_copy(dst.data_ptr(), src.data_ptr(), static_cast<size_t>(src.nbytes()), codec,
+                               scale) == 0, "ps_host_copy: unknown codec");
+      return;
+    }
+    TORCH_CHECK(dst.is_cuda() && src.is_cuda(), "copy_codec needs both tensors on the same kind of device");
     CheckRc(ps_launch_copy(dst.data_ptr(), src.data_ptr(), static_cast<size_t>(src.nbytes()), codec,
                            scale, max_ctas, CurrentStream(src)), "ps_launch_copy");
   }, py::arg("dst"), py::arg("src"), py::arg("codec") = 0, py::arg("scale") = 1.0f,
      py::arg("max_ctas") = 0);
   m.def("decode", [](torch::Tensor dst_f32, const torch::Tensor& wire, int64_t n, int fmt) {
+    if (!wire.is_cuda()) {
+      TORCH_CHECK(ps_host_decode(dst_f32.data_ptr<float>(), wire.data_ptr(), static_cast<size_t>(n), fmt) == 0,
+                  "ps_host_decode: unknown format");
+      return;
+    }
     CheckRc(ps_launch_decode(dst_f32.data_ptr(), wire.data_ptr(), static_cast<size_t>(n), fmt,
                              CurrentStream(wire)), "ps_launch_decode");
   });
@@ -560,6 +573,10 @@ PYBIND11_MODULE(_C, m) {
     o.bias_corr1 = o.optimizer == PS_OPT_ADAMW ? 1.f - std::pow(beta1, (float)step) : 1.f;
     o.bias_corr2 = o.optimizer == PS_OPT_ADAMW ? 1.f - std::pow(beta2, (float)step) : 1.f;
     o.grad_scale = grad_scale;
+    if (!master.is_cuda()) {
+      TORCH_CHECK(ps_host_update(&a, &o) == 0, "ps_host_update: bad arguments");
+      return;
+    }
     CheckRc(ps_launch_update(&a, &o, max_ctas, CurrentStream(master)), "ps_launch_update");
   }, py::arg("grads"), py::arg("grad_format"), py::arg("master"), py::arg("m"), py::arg("v"),
      py::arg("outs"), py::arg("optimizer") = "adamw", py::arg("lr") = 1e-3f,

@@ -4,20 +4,129 @@
  */
 #include "server/gpu_server.h"
 
+#ifdef PS_USE_CUDA
 #include <cuda_runtime.h>
+#endif
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
+#include "kernels/host_kernels.h"
 #include "van/mem_domain.h"
 
 namespace ps {
 
+/*!
+ * \brief where the shards live and who does the math. The round logic above it (sync
+ *        rounds, fused pull fan-out, late pulls, checkpoints) is the same for both:
+ *        CudaBackend — HBM + the sm_100a kernels on the van's stream (asynchronous);
+ *        HostBackend — host memory + the CPU twins (synchronous): the engine for CPU
+ *        servers (the reference's deployment model) and for GPU-less tests.
+ */
+class GpuServer::Backend {
+ public:
+  virtual ~Backend() {}
+  virtual bool on_device() const = 0;
+  virtual void Bind() {}
+  /*! \brief zero-filled memory for fp32 state */
+  virtual void* Alloc(size_t bytes) = 0;
+  virtual void Free(void* p) = 0;
+  virtual void Decode(float* dst, const void* wire, size_t n, int fmt) = 0;
+  virtual void Update(const ps_update_args& a, const ps_opt_params& o, int max_ctas) = 0;
+  virtual void Copy(void* dst, const void* src, size_t n_src_bytes, int codec, float scale,
+                    int max_ctas) = 0;
+  /*! \brief synchronous transfers between backend memory and host memory */
+  virtual void Upload(void* dst, const void* host, size_t bytes) = 0;
+  virtual void Download(void* host, const void* src, size_t bytes) = 0;
+  /*! \brief all queued work has completed */
+  virtual void Sync() = 0;
+};
+
+namespace {
+
+class HostBackend : public GpuServer::Backend {
+ public:
+  bool on_device() const override { return false; }
+  void* Alloc(size_t bytes) override {
+    void* p = calloc(1, bytes ? bytes : 1);
+    CHECK(p) << "out of host memory for " << bytes << " B of server state";
+    return p;
+  }
+  void Free(void* p) override { free(p); }
+  void Decode(float* dst, const void* wire, size_t n, int fmt) override {
+    CHECK_EQ(ps_host_decode(dst, wire, n, fmt), 0);
+  }
+  void Update(const ps_update_args& a, const ps_opt_params& o, int /*max_ctas*/) override {
+    CHECK_EQ(ps_host_update(&a, &o), 0) << "unsupported gradient format " << a.grad_format;
+  }
+  void Copy(void* dst, const void* src, size_t n, int codec, float scale, int /*max_ctas*/) override {
+    CHECK_EQ(ps_host_copy(dst, src, n, codec, scale), 0);
+  }
+  void Upload(void* dst, const void* host, size_t bytes) override { memcpy(dst, host, bytes); }
+  void Download(void* host, const void* src, size_t bytes) override { memcpy(host, src, bytes); }
+  void Sync() override {}
+};
+
+#ifdef PS_USE_CUDA
 #define GS_CUDA(expr)                                                             \
   do {                                                                            \
     cudaError_t e_ = (expr);                                                      \
     CHECK(e_ == cudaSuccess) << "CUDA: " #expr " -> " << cudaGetErrorString(e_);  \
   } while (0)
+
+class CudaBackend : public GpuServer::Backend {
+ public:
+  CudaBackend(int dev, void* stream) : dev_(dev), stream_(static_cast<cudaStream_t>(stream)) {
+    GS_CUDA(cudaSetDevice(dev_));
+    if (!stream_) {
+      GS_CUDA(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+      own_stream_ = true;
+    }
+  }
+  ~CudaBackend() override {
+    cudaSetDevice(dev_);
+    cudaStreamSynchronize(stream_);
+    if (own_stream_) cudaStreamDestroy(stream_);
+  }
+  bool on_device() const override { return true; }
+  void Bind() override { GS_CUDA(cudaSetDevice(dev_)); }
+  void* Alloc(size_t bytes) override {
+    void* p = nullptr;
+    GS_CUDA(cudaMalloc(&p, bytes ? bytes : 1));
+    GS_CUDA(cudaMemsetAsync(p, 0, bytes, stream_));
+    return p;
+  }
+  void Free(void* p) override { cudaFree(p); }
+  void Decode(float* dst, const void* wire, size_t n, int fmt) override {
+    CHECK_EQ(ps_launch_decode(dst, wire, n, fmt, ps_stream()), 0);
+  }
+  void Update(const ps_update_args& a, const ps_opt_params& o, int max_ctas) override {
+    CHECK_EQ(ps_launch_update(&a, &o, max_ctas, ps_stream()), 0);
+  }
+  void Copy(void* dst, const void* src, size_t n, int codec, float scale, int max_ctas) override {
+    CHECK_EQ(ps_launch_copy(dst, src, n, codec, scale, max_ctas, ps_stream()), 0);
+  }
+  void Upload(void* dst, const void* host, size_t bytes) override {
+    GS_CUDA(cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, stream_));
+    GS_CUDA(cudaStreamSynchronize(stream_));
+  }
+  void Download(void* host, const void* src, size_t bytes) override {
+    GS_CUDA(cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, stream_));
+    GS_CUDA(cudaStreamSynchronize(stream_));
+  }
+  void Sync() override { GS_CUDA(cudaStreamSynchronize(stream_)); }
+
+ private:
+  ps_stream_t ps_stream() const { return reinterpret_cast<ps_stream_t>(stream_); }
+  int dev_;
+  cudaStream_t stream_;
+  bool own_stream_ = false;
+};
+#endif  // PS_USE_CUDA
+
+}  // namespace
 
 namespace {
 SArray<Key> OneKey(Key k) {
@@ -38,14 +147,23 @@ GpuServer::GpuServer(int app_id, const GpuServerConfig& cfg, int instance_idx)
   CHECK_LE(cfg_.num_workers, PS_MAX_FANIN);
   po_ = Postoffice::GetServer(instance_idx);
   dev_ = po_->van()->my_node().dev_id;
-  if (dev_ < 0) GS_CUDA(cudaGetDevice(&dev_));
-  GS_CUDA(cudaSetDevice(dev_));
   stream_ = po_->van()->DataStream();
-  if (!stream_) {
-    cudaStream_t s;
-    GS_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    stream_ = s;
+  const std::string van_type = po_->van()->GetType();
+  // a GPU van (nvl, nccl) means GPU-resident shards; host vans (tcp, shm, multivan) get the
+  // CPU engine unless PS_SERVER_DEVICE=cuda asks for the GPU anyway
+  bool want_device = dev_ >= 0 || van_type == "nvl" || van_type == "nccl";
+  const std::string forced = GetEnvStr("PS_SERVER_DEVICE", "");
+  if (forced == "cuda") want_device = true;
+  if (forced == "cpu") want_device = false;
+#ifdef PS_USE_CUDA
+  if (want_device) {
+    if (dev_ < 0) GS_CUDA(cudaGetDevice(&dev_));
+    be_.reset(new CudaBackend(dev_, stream_));
   }
+#else
+  CHECK(!want_device) << "this build has no CUDA support (PS_USE_CUDA)";
+#endif
+  if (!be_) be_.reset(new HostBackend());
   server_.reset(new KVServer<char>(app_id, false, instance_idx));
   using namespace std::placeholders;
   server_->set_request_handle(std::bind(&GpuServer::Handle, this, _1, _2, _3));
@@ -53,14 +171,16 @@ GpuServer::GpuServer(int app_id, const GpuServerConfig& cfg, int instance_idx)
 
 GpuServer::~GpuServer() {
   server_.reset();
-  cudaSetDevice(dev_);
-  cudaStreamSynchronize(static_cast<cudaStream_t>(stream_));
+  be_->Bind();
+  be_->Sync();
   for (auto& kv : shards_) {
-    cudaFree(kv.second.master);
-    cudaFree(kv.second.m);
-    cudaFree(kv.second.v);
+    be_->Free(kv.second.master);
+    be_->Free(kv.second.m);
+    be_->Free(kv.second.v);
   }
 }
+
+bool GpuServer::on_device() const { return be_->on_device(); }
 
 void GpuServer::SetLearningRate(float lr) {
   std::lock_guard<std::mutex> lk(mu_);
@@ -129,20 +249,17 @@ GpuServer::Shard* GpuServer::GetShard(Key key, size_t n) {
   CHECK_GT(n, (size_t)0) << "pull of unknown key " << key;
   Shard& s = shards_[key];
   s.n = n;
-  GS_CUDA(cudaMalloc(&s.master, n * 4));
-  GS_CUDA(cudaMalloc(&s.m, n * 4));
-  GS_CUDA(cudaMalloc(&s.v, n * 4));
-  cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  GS_CUDA(cudaMemsetAsync(s.master, 0, n * 4, st));
-  GS_CUDA(cudaMemsetAsync(s.m, 0, n * 4, st));
-  GS_CUDA(cudaMemsetAsync(s.v, 0, n * 4, st));
+  s.master = static_cast<float*>(be_->Alloc(n * 4));
+  s.m = static_cast<float*>(be_->Alloc(n * 4));
+  s.v = static_cast<float*>(be_->Alloc(n * 4));
   s.slots.assign(cfg_.num_workers, nullptr);
+  s.slot_refs.assign(cfg_.num_workers, SArray<char>());
   s.pushed.assign(cfg_.num_workers, 0);
   return &s;
 }
 
 void GpuServer::Handle(const KVMeta& req, const KVPairs<char>& data, KVServer<char>* /*server*/) {
-  GS_CUDA(cudaSetDevice(dev_));
+  be_->Bind();
   std::lock_guard<std::mutex> lk(mu_);
   const Key key = data.keys.size() ? data.keys[0] : req.key;
   if (req.push) {
@@ -161,21 +278,19 @@ void GpuServer::Handle(const KVMeta& req, const KVPairs<char>& data, KVServer<ch
 }
 
 void GpuServer::HandleInit(Shard* s, const KVMeta& req, const KVPairs<char>& data) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream_);
   if (!s->initialized) {
     const bool f32 = req.cmd == kCmdInitF32;
     const void* src = data.vals.data();
     void* staged = nullptr;
-    if (!data.vals.on_gpu()) {
-      GS_CUDA(cudaMalloc(&staged, data.vals.size()));
-      GS_CUDA(cudaMemcpyAsync(staged, src, data.vals.size(), cudaMemcpyHostToDevice, st));
+    if (be_->on_device() && !data.vals.on_gpu()) {  // values came over a host path
+      staged = be_->Alloc(data.vals.size());
+      be_->Upload(staged, src, data.vals.size());
       src = staged;
     }
-    CHECK_EQ(ps_launch_decode(s->master, src, s->n, f32 ? PS_GRAD_F32 : PS_GRAD_BF16,
-                              reinterpret_cast<ps_stream_t>(stream_)), 0);
+    be_->Decode(s->master, src, s->n, f32 ? PS_GRAD_F32 : PS_GRAD_BF16);
     if (staged) {
-      GS_CUDA(cudaStreamSynchronize(st));
-      cudaFree(staged);
+      be_->Sync();
+      be_->Free(staged);
     }
     s->initialized = true;
   }
@@ -198,7 +313,12 @@ void GpuServer::HandleGrad(Shard* s, const KVMeta& req, const KVPairs<char>& dat
     fmt = PS_GRAD_MC_BF16;
     slot = static_cast<const char*>(mc_grad_base_) + req.mem.offset;
   } else {
-    CHECK(data.vals.on_gpu()) << "gradient pushes must arrive through the one-sided van";
+    if (be_->on_device()) {
+      CHECK(data.vals.on_gpu()) << "gradient pushes must arrive through a GPU van (nvl / nccl)";
+    } else {
+      CHECK(!data.vals.on_gpu()) << "this server keeps its shards in host memory";
+      s->slot_refs[rank] = data.vals;  // a two-sided payload lives in a pooled receive buffer
+    }
     fmt = FormatOf(req, cfg_.raw_grad_format);
     slot = data.vals.data();
   }
@@ -283,7 +403,7 @@ void GpuServer::MaybeRunRound(Key key, Shard* s) {
     o.bias_corr1 = 1.f - std::pow(o.beta1, static_cast<float>(s->step));
     o.bias_corr2 = 1.f - std::pow(o.beta2, static_cast<float>(s->step));
   }
-  CHECK_EQ(ps_launch_update(&a, &o, cfg_.max_ctas, reinterpret_cast<ps_stream_t>(stream_)), 0);
+  be_->Update(a, o, cfg_.max_ctas);
   ++updates_;
   if (a.num_outs > 0) ++fused_;
 
@@ -304,6 +424,7 @@ void GpuServer::MaybeRunRound(Key key, Shard* s) {
   }
   s->waiting_pulls.clear();
   std::fill(s->pushed.begin(), s->pushed.end(), 0);
+  for (auto& ref : s->slot_refs) ref = SArray<char>();
   s->num_pushed = 0;
 }
 
@@ -311,33 +432,38 @@ void GpuServer::ServePullFromLocal(Key key, Shard* s, const KVMeta& req) {
   KVPairs<char> res;
   res.keys = OneKey(key);
   res.lens = OneLen(s->n * 2);
-  ps_stream_t st = reinterpret_cast<ps_stream_t>(stream_);
+  const DeviceType where = be_->on_device() ? GPU : CPU;
+  const int where_id = be_->on_device() ? dev_ : 0;
   if (void* dst = WorkerDest(req)) {
-    // cast fp32 master -> bf16 straight into the worker's buffer (peer HBM); the kernel runs
-    // on the update stream, so it is ordered after any update of this shard
+    // cast fp32 master -> bf16 straight into the worker's buffer (peer HBM / shared memory);
+    // on the device this runs on the update stream, so it is ordered after any update
     CHECK_GE(req.mem.bytes, s->n * 2) << "pull destination smaller than the shard";
-    CHECK_EQ(ps_launch_copy(dst, s->master, s->n * 4, PS_CODEC_F32_TO_BF16, 1.f, cfg_.max_ctas, st),
-             0);
-    res.vals = SArray<char>(reinterpret_cast<char*>(s->master), s->n * 2, GPU, dev_, GPU, dev_);
+    be_->Copy(dst, s->master, s->n * 4, PS_CODEC_F32_TO_BF16, 1.f, cfg_.max_ctas);
+    res.vals = SArray<char>(reinterpret_cast<char*>(s->master), s->n * 2, where, where_id, where, where_id);
     SendOpts placed;
     placed.codec = kCodecPlaced;
     server_->Response(req, res, placed);
     return;
   }
   CHECK(!req.mem.valid()) << "pull destination region unknown to this server";
-  // two-sided requester: cast into a scratch buffer ...
-  void* scratch = nullptr;
-  GS_CUDA(cudaMalloc(&scratch, s->n * 2 + 16));
-  CHECK_EQ(ps_launch_copy(scratch, s->master, s->n * 4, PS_CODEC_F32_TO_BF16, 1.f, cfg_.max_ctas, st),
-           0);
+  if (!be_->on_device()) {  // host shards, two-sided requester: cast into the reply buffer
+    SArray<char> host(s->n * 2);
+    be_->Copy(host.data(), s->master, s->n * 4, PS_CODEC_F32_TO_BF16, 1.f, cfg_.max_ctas);
+    res.vals = host;
+    server_->Response(req, res);
+    return;
+  }
+  // device shards, two-sided requester: cast into a scratch buffer ...
+  void* scratch = be_->Alloc(s->n * 2 + 16);
+  be_->Copy(scratch, s->master, s->n * 4, PS_CODEC_F32_TO_BF16, 1.f, cfg_.max_ctas);
   if (po_->van()->GetType() == "nccl") {
     // ... which the nccl van sends from device memory (it orders the send behind this stream)
-    const int dev = dev_;
+    Backend* be = be_.get();
     SArray<char> dvals;
     dvals.reset(static_cast<char*>(scratch), s->n * 2,
-                [dev](char* p) {
-                  cudaSetDevice(dev);
-                  cudaFree(p);
+                [be](char* p) {
+                  be->Bind();
+                  be->Free(p);
                 },
                 GPU, dev_, GPU, dev_);
     res.vals = dvals;
@@ -346,10 +472,8 @@ void GpuServer::ServePullFromLocal(Key key, Shard* s, const KVMeta& req) {
   }
   // ... or, for a host-only transport (TCP), stage it through host memory
   SArray<char> host(s->n * 2);
-  cudaStream_t cst = static_cast<cudaStream_t>(stream_);
-  GS_CUDA(cudaMemcpyAsync(host.data(), scratch, s->n * 2, cudaMemcpyDeviceToHost, cst));
-  GS_CUDA(cudaStreamSynchronize(cst));
-  cudaFree(scratch);
+  be_->Download(host.data(), scratch, s->n * 2);
+  be_->Free(scratch);
   res.vals = host;
   server_->Response(req, res);
 }
@@ -358,12 +482,9 @@ bool GpuServer::ReadMaster(Key key, std::vector<float>* out) {
   std::lock_guard<std::mutex> lk(mu_);
   auto it = shards_.find(key);
   if (it == shards_.end()) return false;
-  GS_CUDA(cudaSetDevice(dev_));
+  be_->Bind();
   out->resize(it->second.n);
-  cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  GS_CUDA(cudaMemcpyAsync(out->data(), it->second.master, it->second.n * 4, cudaMemcpyDeviceToHost,
-                          st));
-  GS_CUDA(cudaStreamSynchronize(st));
+  be_->Download(out->data(), it->second.master, it->second.n * 4);
   return true;
 }
 
@@ -382,9 +503,8 @@ struct CkptEntry {
 
 bool GpuServer::SaveCheckpoint(const std::string& path) {
   std::lock_guard<std::mutex> lk(mu_);
-  GS_CUDA(cudaSetDevice(dev_));
-  cudaStream_t st = static_cast<cudaStream_t>(stream_);
-  GS_CUDA(cudaStreamSynchronize(st));
+  be_->Bind();
+  be_->Sync();
   FILE* f = fopen(path.c_str(), "wb");
   if (!f) return false;
   CkptHeader h;
@@ -398,7 +518,7 @@ bool GpuServer::SaveCheckpoint(const std::string& path) {
     ok = ok && fwrite(&e, sizeof(e), 1, f) == 1;
     buf.resize(s.n);
     for (float* src : {s.master, s.m, s.v}) {
-      GS_CUDA(cudaMemcpy(buf.data(), src, s.n * 4, cudaMemcpyDeviceToHost));
+      be_->Download(buf.data(), src, s.n * 4);
       ok = ok && fwrite(buf.data(), 4, s.n, f) == s.n;
     }
   }
@@ -408,7 +528,7 @@ bool GpuServer::SaveCheckpoint(const std::string& path) {
 
 bool GpuServer::LoadCheckpoint(const std::string& path) {
   std::lock_guard<std::mutex> lk(mu_);
-  GS_CUDA(cudaSetDevice(dev_));
+  be_->Bind();
   FILE* f = fopen(path.c_str(), "rb");
   if (!f) return false;
   CkptHeader h;
@@ -424,10 +544,10 @@ bool GpuServer::LoadCheckpoint(const std::string& path) {
     buf.resize(e.n);
     for (float* dst : {s->master, s->m, s->v}) {
       ok = ok && fread(buf.data(), 4, e.n, f) == e.n;
-      GS_CUDA(cudaMemcpy(dst, buf.data(), e.n * 4, cudaMemcpyHostToDevice));
+      if (ok) be_->Upload(dst, buf.data(), e.n * 4);
     }
   }
-  GS_CUDA(cudaStreamSynchronize(static_cast<cudaStream_t>(stream_)));
+  be_->Sync();
   fclose(f);
   return ok;
 }

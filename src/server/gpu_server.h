@@ -20,6 +20,11 @@
  *     copy of its shards (12 B of state per parameter).
  * The handler only enqueues work on the van's data stream and never blocks, so
  * it can run inline on the van thread (PS_DIRECT_DISPATCH=1).
+ *
+ * The same engine runs on CPU servers — the reference's deployment model — when the
+ * process uses a host van (tcp / shm / multivan) or PS_SERVER_DEVICE=cpu: shards in host
+ * memory, the CPU twins of the kernels (src/kernels/host_kernels.cc), pull replies written
+ * into the worker's shared-memory buffer by the shm van or sent two-sided over TCP.
  */
 #ifndef PS_SERVER_GPU_SERVER_H_
 #define PS_SERVER_GPU_SERVER_H_
@@ -107,6 +112,10 @@ class GpuServer {
   bool ReadMaster(Key key, std::vector<float>* out);
 
   KVServer<char>* kv() { return server_.get(); }
+  /*! \brief true: shards in HBM, sm_100a kernels; false: shards in host memory, CPU twins */
+  bool on_device() const;
+
+  class Backend;  // memory + math provider (gpu_server.cc)
 
  private:
   struct Shard {
@@ -118,6 +127,7 @@ class GpuServer {
     int step = 0;
     int grad_format = PS_GRAD_BF16;
     std::vector<const void*> slots;      // per worker rank: landing slot of this round
+    std::vector<SArray<char>> slot_refs; // host shards: keeps a two-sided payload alive until the round runs
     std::vector<char> pushed;            // per worker rank: pushed in the open round
     int num_pushed = 0;
     std::vector<KVMeta> waiting_pulls;   // pulls of workers that already pushed this round
@@ -138,6 +148,7 @@ class GpuServer {
   int instance_idx_;
   int dev_ = 0;
   void* stream_ = nullptr;
+  std::unique_ptr<Backend> be_;
   std::unique_ptr<KVServer<char>> server_;
   Postoffice* po_ = nullptr;
   std::mutex mu_;

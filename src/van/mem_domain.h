@@ -36,6 +36,7 @@
 #include <vector>
 
 #include "ps/internal/utils.h"
+#include "kernels/host_kernels.h"
 #include "ps/sarray.h"
 #include "van/shm_util.h"
 
@@ -318,14 +319,15 @@ class ShmDomain : public MemDomain {
     imported_[key] = std::make_pair(base, static_cast<size_t>(d.size));
     return base;
   }
-  Ticket CopyAsync(void* dst, const void* src, size_t n, int codec, float /*scale*/,
+  Ticket CopyAsync(void* dst, const void* src, size_t n, int codec, float scale,
                    void* /*wait_event*/, int /*src_device_type*/ = UNK) override {
-    CHECK_EQ(codec, (int)kCodecRaw) << "the shm domain moves raw bytes only";
     if (copier_) {
       AsyncOp* op = new AsyncOp();
       op->dst = dst;
       op->src = src;
-      op->n = dst != src ? n : 0;
+      op->n = (dst != src || codec != kCodecRaw) ? n : 0;
+      op->codec = codec;
+      op->scale = scale;
       {
         std::lock_guard<std::mutex> lk(q_mu_);
         q_.push_back(op);
@@ -335,7 +337,7 @@ class ShmDomain : public MemDomain {
       t.event = op;
       return t;
     }
-    if (n && dst != src) memcpy(dst, src, n);
+    if (n) CHECK_EQ(ps_host_copy(dst, src, n, codec, scale), 0) << "unknown wire codec " << codec;
     // make the payload visible before the descriptor that announces it
     std::atomic_thread_fence(std::memory_order_release);
     return Ticket();
@@ -355,6 +357,8 @@ class ShmDomain : public MemDomain {
     void* dst = nullptr;
     const void* src = nullptr;
     size_t n = 0;
+    int codec = 0;
+    float scale = 1.f;
     std::atomic<bool> done{false};
   };
   void CopierLoop() {
@@ -365,7 +369,7 @@ class ShmDomain : public MemDomain {
       AsyncOp* op = q_.front();
       q_.erase(q_.begin());
       lk.unlock();
-      if (op->n) memcpy(op->dst, op->src, op->n);
+      if (op->n) ps_host_copy(op->dst, op->src, op->n, op->codec, op->scale);
       op->done.store(true, std::memory_order_release);
       lk.lock();
     }

@@ -45,6 +45,7 @@
 
 #include "ps/internal/postoffice.h"
 #include "ps/internal/van.h"
+#include "van/mem_domain.h"
 #include "van/shm_pipe.h"
 #include "van/shm_util.h"
 
@@ -173,6 +174,8 @@ class TcpVan : public Van {
     /*! \brief same-host fast path: frames go through this ring, the socket carries doorbells */
     std::unique_ptr<ShmPipe> pipe;
   };
+  /*! \brief transient MemRef::region marker, never on the wire (see SendMsg) */
+  static constexpr int32_t kEncodedOnHost = 0x4000007f;
   static constexpr uint32_t kPipeMagic = 0x45504950u;  // "PIPE": "frames follow in shm ring <name>"
 
   int Bind(Node& node, int max_retry) override {
@@ -261,8 +264,27 @@ class TcpVan : public Van {
   }
 
   int SendMsg(Message& msg) override {
+    CHECK_NE(msg.meta.recver, Meta::kEmpty);
+    // a push that asks for a wire codec but travels two-sided (host values a one-sided van
+    // could not export, or the plain TCP van): encode here, the receiver sees wire bytes
+    if (msg.meta.request && msg.meta.push && msg.meta.codec > kCodecRaw && msg.meta.codec < kCodecPlaced &&
+        msg.data.size() >= 2 && msg.data[1].size() > 0 && !msg.data[1].on_gpu() && !msg.meta.mem.valid()) {
+      const size_t raw = msg.data[1].size();
+      SArray<char> encoded(WireBytes(msg.meta.codec, raw));
+      CHECK_EQ(ps_host_copy(encoded.data(), msg.data[1].data(), raw, msg.meta.codec, msg.meta.scale), 0);
+      Message wire_msg = msg;
+      wire_msg.data[1] = encoded;
+      wire_msg.meta.data_size += static_cast<int64_t>(encoded.size()) - static_cast<int64_t>(raw);
+      wire_msg.meta.mem.region = kEncodedOnHost;  // "do not encode again", cleared by SendFrame
+      return SendFrame(wire_msg);
+    }
+    return SendFrame(msg);
+  }
+
+  /*! \brief serialise one message to its peer (socket, ring or own loopback queue) */
+  int SendFrame(Message& msg) {
+    if (msg.meta.mem.region == kEncodedOnHost) msg.meta.mem = MemRef();
     const int recver = msg.meta.recver;
-    CHECK_NE(recver, Meta::kEmpty);
     if (recver == my_node_.id) return Loopback(msg);
 
     std::shared_ptr<Peer> peer;

@@ -30,8 +30,10 @@ def main():
     C = pslite_b200.native()
     if use_cuda:
         torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    ctx = init_ps(topo, van="nvl")
+    dev = torch.device("cuda", local) if use_cuda else torch.device("cpu")
+    # without a GPU the same job runs on the CPU engine: shm one-sided van + host-resident shards
+    ctx = init_ps(topo, van="nvl" if use_cuda else "shm")
+    exportable = os.environ.get("PSLITE_TEST_EXPORTABLE_PARAMS", "0") == "1"
     W, S = ctx.num_workers, ctx.num_servers
     server = None
     if ctx.is_server:
@@ -46,6 +48,15 @@ def main():
         with torch.device(dev):
             model = Llama(cfg).to(torch.bfloat16)
         model.init_weights(seed=3)
+        if exportable and not use_cuda:
+            # parameters in shared memory: pulls land in place (zero-copy), as they do in HBM
+            keep = []
+            for p in model.parameters():
+                buf = C.alloc_exportable(p.numel() * p.element_size(), "worker")
+                view = buf.view(p.dtype).view(p.shape)
+                view.copy_(p.data)
+                p.data = view
+                keep.append(buf)
     mcast_info = ""
     if symmetric:
         # every rank (servers too) allocates the same symmetric buffer; workers move their
@@ -81,7 +92,8 @@ def main():
             loss.backward()
             opt.step()
             losses.append(loss.item())
-        torch.cuda.synchronize()
+        if use_cuda:
+            torch.cuda.synchronize()
         with torch.no_grad():
             checksum[0] = sum(float(p.double().sum()) for p in model.parameters())
         ok = losses[-1] < losses[0]
@@ -90,7 +102,8 @@ def main():
     dist.all_gather(sums, checksum, group=gloo)
     wsums = [float(s) for i, s in enumerate(sums) if (topo == "joint" or i < W)]
     same = all(abs(x - wsums[0]) < 1e-9 for x in wsums)
-    print(f"rank {rank}: losses {['%.3f' % l for l in losses[:2]]}..{['%.3f' % l for l in losses[-2:]]} "
+    engine = ("device" if server.on_device() else "host") if server else "-"
+    print(f"rank {rank}: engine={engine} losses {['%.3f' % l for l in losses[:2]]}..{['%.3f' % l for l in losses[-2:]]} "
           f"checksums_equal={same} updates={server.num_updates() if server else 0} "
           f"fused={server.num_fused_fanouts() if server else 0} "
           f"mcast={server.num_multicast_fanouts() if server else 0} "

@@ -1,0 +1,62 @@
+"""The full PS training stack without a GPU: tiny Llama workers + the server engine on its host
+backend (shards in host memory, CPU twins of the kernels), shm one-sided van, under torchrun.
+Same helper and same checks as the multi-GPU tests (tests/test_multigpu.py): the loss must drop
+and every worker must end with identical parameters. What differs from a GPU run is only the
+MemDomain (shared memory instead of HBM) and the kernel implementations."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+from pslite_b200.utils.env import free_port
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HELPER = os.path.join(ROOT, "tests", "helpers", "train_multi.py")
+
+
+def _run(nproc, topo, wire, steps, **env_extra):
+    env = dict(os.environ)
+    env.update({"PSLITE_NO_AUTOBUILD": "1", "OMP_NUM_THREADS": "1", "CUDA_VISIBLE_DEVICES": ""})
+    env.update({k: str(v) for k, v in env_extra.items()})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), HELPER, topo, wire, str(steps)]
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=280, cwd=ROOT)
+    out = p.stdout + p.stderr
+    assert p.returncode == 0 and "PASS" in out, out[-3000:]
+    return out
+
+
+@pytest.mark.timeout(300)
+def test_two_sided_fallback_with_fp8_wire(native):
+    """plain torch tensors cannot be exported: gradients are fp8-encoded on the host and travel
+    in the frames, pull replies come back two-sided; 2 workers + 2 servers, co-located"""
+    out = _run(2, "joint", "fp8", 6)
+    assert "engine=host" in out and "fused=0 " in out
+
+
+@pytest.mark.timeout(300)
+def test_zero_copy_fused_fanout_many_peers_async(native):
+    """parameters in shared memory, copies completing asynchronously (as on a CUDA stream):
+    every update writes the new bf16 parameters straight into all 4 workers' buffers"""
+    out = _run(4, "joint", "fp8", 5, PSLITE_TEST_EXPORTABLE_PARAMS=1, PS_SHM_ASYNC=1)
+    assert "engine=host" in out and "fused=0 " not in out
+
+
+@pytest.mark.timeout(300)
+def test_split_topology_bf16_wire(native):
+    """dedicated server processes (2 workers + 2 servers), bf16 gradient wire"""
+    _run(4, "split", "bf16", 5, PSLITE_TEST_EXPORTABLE_PARAMS=1)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("wire", ["bf16", "fp8"])
+def test_host_engine_matches_local_adamw_and_checkpoints(native, wire):
+    """one worker + the host engine in one process: the loss curve tracks a local fp32-master AdamW
+    run, and a save / train on / load cycle restores the saved fp32 master bit for bit"""
+    env = dict(os.environ)
+    env.update({"PSLITE_NO_AUTOBUILD": "1", "CUDA_VISIBLE_DEVICES": ""})
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "helpers", "train_joint.py"), wire, "8"],
+                       env=env, capture_output=True, text=True, timeout=280, cwd=ROOT)
+    out = p.stdout + p.stderr
+    assert p.returncode == 0 and "PASS" in out and "restored_equal=True" in out, out[-3000:]
