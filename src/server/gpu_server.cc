@@ -171,8 +171,12 @@ GpuServer::GpuServer(int app_id, const GpuServerConfig& cfg, int instance_idx)
 
 GpuServer::~GpuServer() {
   server_.reset();
-  be_->Bind();
-  be_->Sync();
+  try {
+    be_->Bind();
+    be_->Sync();
+  } catch (const std::exception& e) {  // e.g. the CUDA context is already gone at exit
+    LOG(WARNING) << "server engine teardown: " << e.what();
+  }
   for (auto& kv : shards_) {
     be_->Free(kv.second.master);
     be_->Free(kv.second.m);
