@@ -302,7 +302,7 @@ class PyGpuServer {
  public:
   PyGpuServer(int app_id, int num_workers, const std::string& optimizer, float lr, float beta1,
               float beta2, float eps, float weight_decay, float grad_scale, bool fuse_pull,
-              const std::string& raw_grad, int max_ctas) {
+              const std::string& raw_grad, int max_ctas, bool async_updates) {
     GpuServerConfig c;
     c.num_workers = num_workers;
     c.opt.optimizer = optimizer == "sgd" ? PS_OPT_SGD : PS_OPT_ADAMW;
@@ -313,6 +313,7 @@ class PyGpuServer {
     c.opt.weight_decay = weight_decay;
     c.opt.grad_scale = grad_scale;
     c.fuse_pull = fuse_pull;
+    c.async_updates = async_updates;
     c.raw_grad_format = raw_grad == "f32" ? PS_GRAD_F32 : PS_GRAD_BF16;
     c.max_ctas = max_ctas;
     impl_.reset(new GpuServer(app_id, c));
@@ -453,11 +454,12 @@ PYBIND11_MODULE(_C, m) {
 
   py::class_<PyGpuServer>(m, "GpuServer")
       .def(py::init<int, int, const std::string&, float, float, float, float, float, float, bool,
-                    const std::string&, int>(),
+                    const std::string&, int, bool>(),
            py::arg("app_id") = 0, py::arg("num_workers") = 1, py::arg("optimizer") = "adamw",
            py::arg("lr") = 1e-3f, py::arg("beta1") = 0.9f, py::arg("beta2") = 0.95f,
            py::arg("eps") = 1e-8f, py::arg("weight_decay") = 0.0f, py::arg("grad_scale") = 1.0f,
-           py::arg("fuse_pull") = true, py::arg("raw_grad") = "bf16", py::arg("max_ctas") = 0)
+           py::arg("fuse_pull") = true, py::arg("raw_grad") = "bf16", py::arg("max_ctas") = 0,
+           py::arg("async_updates") = false)
       .def("set_lr", &PyGpuServer::set_lr)
       .def("set_symmetric", &PyGpuServer::set_symmetric, py::arg("mc_ptr"), py::arg("peer_ptrs"),
            py::arg("bytes"))

@@ -336,6 +336,19 @@ void GpuServer::HandleGrad(Shard* s, const KVMeta& req, const KVPairs<char>& dat
   s->slots[rank] = slot;
   s->pushed[rank] = 1;
   ++s->num_pushed;
+  if (cfg_.async_updates) {
+    CHECK_NE(fmt, (int)PS_GRAD_MC_BF16) << "in-switch reduction is a synchronous-round feature";
+    s->grad_format = fmt;
+    ApplyOnArrival(s, rank);
+    if (be_->on_device()) {
+      // ack only after the update has consumed the slot (descriptor gated on this stream)
+      SendOpts after_update;
+      after_update.codec = kCodecPlaced;
+      KVPairs<char> none;
+      server_->Response(req, none, after_update);
+      return;
+    }
+  }
   // the payload already sits in its slot: the push is complete for the worker
   server_->Response(req);
 }
@@ -343,7 +356,7 @@ void GpuServer::HandleGrad(Shard* s, const KVMeta& req, const KVPairs<char>& dat
 void GpuServer::HandlePull(Shard* s, const KVMeta& req, const KVPairs<char>& /*data*/) {
   const int rank = Postoffice::IDtoRank(req.sender);
   CHECK_LT(rank, cfg_.num_workers);
-  if (s->pushed[rank]) {
+  if (!cfg_.async_updates && s->pushed[rank]) {
     s->waiting_pulls.push_back(req);  // wants the parameters *after* this round's update
   } else {
     ServePullFromLocal(req.key, s, req);
@@ -361,7 +374,33 @@ void* GpuServer::WorkerDest(const KVMeta& pull) {
   return po_->van()->ResolvePeerMem(instance_id, pull.mem);
 }
 
+void GpuServer::ApplyOnArrival(Shard* s, int rank) {
+  ps_update_args a;
+  memset(&a, 0, sizeof(a));
+  a.n = s->n;
+  a.num_grads = 1;
+  a.grad_format = s->grad_format;
+  a.grads[0] = s->slots[rank];
+  a.master = s->master;
+  a.m = s->m;
+  a.v = s->v;
+  ps_opt_params o = cfg_.opt;
+  ++s->step;
+  if (o.optimizer == PS_OPT_ADAMW) {
+    o.bias_corr1 = 1.f - std::pow(o.beta1, static_cast<float>(s->step));
+    o.bias_corr2 = 1.f - std::pow(o.beta2, static_cast<float>(s->step));
+  }
+  be_->Update(a, o, cfg_.max_ctas);
+  ++updates_;
+  // the slot may be overwritten by this worker's next push as soon as it is acked: on the
+  // device the ack is sent behind the update on the same stream, on the host Update is synchronous
+  s->pushed[rank] = 0;
+  s->slot_refs[rank] = SArray<char>();
+  s->num_pushed = 0;
+}
+
 void GpuServer::MaybeRunRound(Key key, Shard* s) {
+  if (cfg_.async_updates) return;
   const int W = cfg_.num_workers;
   if (s->num_pushed < W) return;
   if (cfg_.fuse_pull && static_cast<int>(s->waiting_pulls.size()) < W) return;

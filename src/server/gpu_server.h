@@ -54,6 +54,13 @@ struct GpuServerConfig {
   ps_opt_params opt;
   /*! \brief wait for all W pulls of a round and fan the new parameters out from the update kernel */
   bool fuse_pull = true;
+  /*!
+   * \brief asynchronous SGD (docs/overview.md of the reference: "asynchronous: the server
+   *        updates as soon as a gradient arrives"): every push is applied on arrival as its own
+   *        optimizer step, pulls are answered at once with the current parameters; there are no
+   *        rounds and no barrier between workers. `opt.grad_scale` is applied per push.
+   */
+  bool async_updates = false;
   /*! \brief cap on CTAs per kernel, 0 = fill the GPU */
   int max_ctas = 0;
   GpuServerConfig() {
@@ -138,6 +145,7 @@ class GpuServer {
   void HandleGrad(Shard* s, const KVMeta& req, const KVPairs<char>& data);
   void HandlePull(Shard* s, const KVMeta& req, const KVPairs<char>& data);
   void MaybeRunRound(Key key, Shard* s);
+  void ApplyOnArrival(Shard* s, int rank);
   void ServePullFromLocal(Key key, Shard* s, const KVMeta& req);
   Shard* GetShard(Key key, size_t n);
   void* WorkerDest(const KVMeta& pull);

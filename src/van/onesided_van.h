@@ -132,6 +132,12 @@ class OneSidedVan : public TcpVan {
     }
     // nothing was placed one-sidedly: do not let the receiver rebuild a payload
     if (!msg.meta.request) msg.meta.mem = MemRef();
+    if (!msg.meta.request && msg.meta.codec == kCodecPlaced) {
+      // a value-less reply marked "placed" (e.g. the ack of a push whose slot a queued kernel
+      // still reads): gate it on the work already enqueued on the data stream
+      msg.meta.codec = kCodecRaw;
+      return Ordered(msg, domain_->CopyAsync(nullptr, nullptr, 0, kCodecRaw, 1.f, msg.wait_event));
+    }
     return Ordered(msg, Ticket());
   }
 

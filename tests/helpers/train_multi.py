@@ -1,7 +1,7 @@
 """Multi-GPU PS training under torchrun (one process per GPU). Every rank trains the same
 tiny Llama on its own data shard through the PS; at the end all workers must hold
 bit-identical parameters (they all pulled the same server state) and the loss must drop.
-usage: torchrun ... train_multi.py <topology> <grad_wire> <steps> [symm|nvls]"""
+usage: torchrun ... train_multi.py <topology> <grad_wire> <steps> [symm|nvls|async]"""
 import os
 import sys
 
@@ -22,6 +22,8 @@ def main():
     topo, wire, steps = sys.argv[1], sys.argv[2], int(sys.argv[3])
     symmetric = len(sys.argv) > 4 and sys.argv[4] in ("symm", "nvls")
     nvls_reduce = len(sys.argv) > 4 and sys.argv[4] == "nvls"
+    # asynchronous SGD: every push is its own optimizer step, workers never wait for each other
+    async_sgd = len(sys.argv) > 4 and sys.argv[4] == "async"
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     use_cuda = torch.cuda.is_available()
@@ -37,8 +39,9 @@ def main():
     W, S = ctx.num_workers, ctx.num_servers
     server = None
     if ctx.is_server:
-        server = C.GpuServer(0, num_workers=W, optimizer="adamw", lr=3e-3, beta1=0.9, beta2=0.95,
-                             eps=1e-8, weight_decay=0.0, grad_scale=1.0 / W, fuse_pull=True)
+        server = C.GpuServer(0, num_workers=W, optimizer="adamw", lr=3e-3 / (W if async_sgd else 1), beta1=0.9,
+                             beta2=0.95, eps=1e-8, weight_decay=0.0, grad_scale=1.0 if async_sgd else 1.0 / W,
+                             fuse_pull=True, async_updates=async_sgd)
     ok = True
     checksum = torch.zeros(1, dtype=torch.float64)
     losses = []
@@ -101,7 +104,8 @@ def main():
     sums = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
     dist.all_gather(sums, checksum, group=gloo)
     wsums = [float(s) for i, s in enumerate(sums) if (topo == "joint" or i < W)]
-    same = all(abs(x - wsums[0]) < 1e-9 for x in wsums)
+    # (asynchronous workers pull at different moments: their copies legitimately differ)
+    same = async_sgd or all(abs(x - wsums[0]) < 1e-9 for x in wsums)
     engine = ("device" if server.on_device() else "host") if server else "-"
     print(f"rank {rank}: engine={engine} losses {['%.3f' % l for l in losses[:2]]}..{['%.3f' % l for l in losses[-2:]]} "
           f"checksums_equal={same} updates={server.num_updates() if server else 0} "

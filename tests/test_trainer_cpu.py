@@ -60,3 +60,17 @@ def test_host_engine_matches_local_adamw_and_checkpoints(native, wire):
                        env=env, capture_output=True, text=True, timeout=280, cwd=ROOT)
     out = p.stdout + p.stderr
     assert p.returncode == 0 and "PASS" in out and "restored_equal=True" in out, out[-3000:]
+
+
+@pytest.mark.timeout(300)
+def test_asynchronous_sgd(native):
+    """async_updates: each push is applied on arrival as its own AdamW step and pulls never wait
+    for other workers (the reference's asynchronous mode, docs/overview.md)"""
+    env = dict(os.environ)
+    env.update({"PSLITE_NO_AUTOBUILD": "1", "OMP_NUM_THREADS": "1", "CUDA_VISIBLE_DEVICES": "",
+                "PSLITE_TEST_EXPORTABLE_PARAMS": "1"})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()), HELPER, "joint", "bf16", "8", "async"]
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=280, cwd=ROOT)
+    out = p.stdout + p.stderr
+    assert p.returncode == 0 and "PASS" in out, out[-3000:]
