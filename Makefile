@@ -41,7 +41,7 @@ CORE_OBJS := $(patsubst %.cc,$(BUILD)/%.o,$(CORE_SRCS))
 CU_OBJS := $(patsubst %.cu,$(BUILD)/%.o,$(CU_SRCS))
 LIB := $(BUILD)/libpslite.a
 
-APPS := $(BUILD)/test_benchmark $(BUILD)/test_kv_app $(BUILD)/test_simple_app $(BUILD)/test_connection $(BUILD)/test_ipc_benchmark $(BUILD)/test_benchmark_stress $(BUILD)/test_recovery
+APPS := $(BUILD)/kv_hello $(BUILD)/test_benchmark $(BUILD)/test_kv_app $(BUILD)/test_simple_app $(BUILD)/test_connection $(BUILD)/test_ipc_benchmark $(BUILD)/test_benchmark_stress $(BUILD)/test_recovery
 ifeq ($(USE_CUDA),1)
 APPS += $(BUILD)/kernel_bench
 endif
@@ -62,6 +62,10 @@ $(LIB): $(CORE_OBJS) $(CU_OBJS)
 	ar rcs $@ $^
 
 $(BUILD)/%: apps/%.cc $(LIB)
+	@mkdir -p $(dir $@)
+	$(CXX) $(CXXFLAGS) $< $(LIB) $(LDFLAGS) -o $@
+
+$(BUILD)/%: examples/%.cc $(LIB)
 	@mkdir -p $(dir $@)
 	$(CXX) $(CXXFLAGS) $< $(LIB) $(LDFLAGS) -o $@
 

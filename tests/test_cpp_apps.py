@@ -53,6 +53,12 @@ def test_benchmark_one_sided_async_copies_many_peers(built_native_tree):
     assert rc == 0 and "goodput" in out, out[-3000:]
 
 
+def test_tutorial_example_runs(built_native_tree):
+    """examples/kv_hello.cc is the program printed in docs/tutorials.md"""
+    rc, out = launch(built_native_tree, 2, 2, "kv_hello")
+    assert rc == 0 and out.count("kv_hello PASSED") == 2, out[-3000:]
+
+
 def test_kv_app_ipc_sockets(built_native_tree):
     rc, out = launch(built_native_tree, 2, 2, "test_kv_app", env={"DMLC_LOCAL": 1})
     assert rc == 0 and out.count("PASSED") == 2, out[-3000:]
