@@ -1,0 +1,35 @@
+#!/bin/bash
+# First GPU call of the next session: everything that was written after the GPU budget of round 1
+# ran out, cheapest first, each step under its own timeout. Run with `gpurun --gpus 2`.
+#   1. the regular GPU test-suite + smoke (1 GPU)
+#   2. bit-exactness of the push kernels against their CPU twins
+#   3. 2-GPU training tests incl. NVLS multicast fan-out, then the gated ones:
+#      in-switch reduction (multimem.ld_reduce) and the nccl van
+#   4. bench.py at N=1 and N=2 (the multi-peer descriptor-batch fix)
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+export PSLITE_NO_AUTOBUILD=1
+echo "== 1. pytest -m gpu (without the multi-GPU module)"
+timeout 900 python -m pytest tests -m gpu -x -q --ignore=tests/test_multigpu.py 2>&1 | tail -n 8
+echo "== 3a. multi-GPU module, verified flows"
+timeout 900 python -m pytest tests/test_multigpu.py -m gpu -q 2>&1 | tail -n 8
+echo "== 3b. in-switch gradient reduction"
+PSLITE_TEST_NVLS_REDUCE=1 timeout 400 python -m pytest tests/test_multigpu.py -m gpu -q -k in_switch 2>&1 | tail -n 15
+echo "== 3c. nccl van"
+PSLITE_TEST_NCCL_VAN=1 timeout 400 python -m pytest tests/test_multigpu.py -m gpu -q -k nccl 2>&1 | tail -n 15
+echo "== 4. bench N=1"
+timeout 400 python bench.py --steps 20 --warmup 3 2>gpurun_out/v_b1.err | tee gpurun_out/v_bench1.json | tail -c 900
+echo "== 4. bench N=2"
+timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29931 \
+  bench.py --gpus 2 --steps 20 --warmup 3 2>gpurun_out/v_b2.err | tee gpurun_out/v_bench2.json | tail -c 900
+echo "== 4. llama-1b N=2 joint, unicast / multicast / in-switch reduce"
+for extra in "" "--symmetric" "--symmetric --nvls-reduce --grad-wire bf16"; do
+  timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29932 \
+    bench.py --metric llama --model llama-1b --seq-len 4096 --gpus 2 --steps 4 --warmup 2 --no-e2e $extra 2>>gpurun_out/v_l2.err \
+    | python -c "
+import sys, json
+for l in sys.stdin:
+    try:
+        d = json.loads(l); print('$extra', round(d['value']), 'tok/s', d.get('server'))
+    except Exception: pass"
+done

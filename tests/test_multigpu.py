@@ -58,3 +58,19 @@ def test_in_switch_gradient_reduction_two_gpus():
     if "nvls=unavailable" in out:
         pytest.skip("no NVSwitch multicast on this box")
     assert "switch_reduce=" in out and "switch_reduce=0 " not in out
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.skipif(os.environ.get("PSLITE_TEST_NCCL_VAN", "0") != "1",
+                    reason="nccl van not yet validated on hardware; set PSLITE_TEST_NCCL_VAN=1")
+def test_nccl_van_benchmark_two_gpus():
+    """worker on GPU 0, server on GPU 1, values in HBM, payloads over ncclSend / ncclRecv"""
+    env = dict(os.environ)
+    env.update({"PS_VAN_TYPE": "nccl", "TEST_NUM_GPU_WORKER": "1", "TEST_NUM_GPU_SERVER": "1",
+                "WORKER_GPU_BASE": "0", "SERVER_GPU_BASE": "1", "NUM_KEY_PER_SERVER": "8",
+                "TOTAL_DURATION": "20", "LOG_DURATION": "10"})
+    p = subprocess.run([os.path.join(ROOT, "scripts", "local.sh"), "1", "1",
+                        os.path.join(ROOT, "build", "test_benchmark"), "4194304", "10", "1"],
+                       env=env, cwd=ROOT, capture_output=True, text=True, timeout=280)
+    out = p.stdout + p.stderr
+    assert p.returncode == 0 and "Application goodput" in out, out[-3000:]
