@@ -238,12 +238,18 @@ void SteadyState(KVWorker<char>* kv, KeySet& ks, int total_keys, int tid) {
   auto t0 = std::chrono::steady_clock::now();
   int rounds_in_window = 0;
   double best_gbps = 0;
+  Van* van = Postoffice::GetWorker(tid)->van();
   for (int round = 0; round < opt.total_rounds; ++round) {
-    for (int k = 0; k < total_keys; ++k) {
-      if (opt.mode != PULL_ONLY) in_flight.push_back(kv->ZPush(ks.keys[k], ks.vals[k], ks.lens[k]));
-      // the destination arrays must outlive the asynchronous pull (the reference
-      // test passes pointers to loop locals, which only works by stack-slot luck)
-      if (opt.mode != PUSH_ONLY) in_flight.push_back(kv->ZPull(ks.keys[k], &ks.vals[k], &ks.lens[k]));
+    // all messages of a round are issued back to back: with PS_COALESCE_LAUNCHES their one-sided
+    // copies share kernel launches and one completion event (a no-op otherwise)
+    {
+      Van::CorkScope cork(van);  // released before the first Wait: the messages leave here
+      for (int k = 0; k < total_keys; ++k) {
+        if (opt.mode != PULL_ONLY) in_flight.push_back(kv->ZPush(ks.keys[k], ks.vals[k], ks.lens[k]));
+        // the destination arrays must outlive the asynchronous pull (the reference
+        // test passes pointers to loop locals, which only works by stack-slot luck)
+        if (opt.mode != PUSH_ONLY) in_flight.push_back(kv->ZPull(ks.keys[k], &ks.vals[k], &ks.lens[k]));
+      }
     }
     for (int ts : in_flight) kv->Wait(ts);
     in_flight.clear();

@@ -77,6 +77,30 @@ class Van {
   virtual void* ResolvePeerMem(int /*node_id*/, const MemRef& /*mem*/) { return nullptr; }
   /*! \brief stream the van's copy kernels run on (cudaStream_t), null for CPU vans */
   virtual void* DataStream() { return nullptr; }
+  /*!
+   * \brief launch coalescing. Between Cork() and the matching Uncork() the calling thread's
+   *        data messages are held back; Uncork() issues all their one-sided copies as one batch
+   *        (few kernel launches, one completion event) and then sends the messages in the
+   *        order they were submitted. Nests; other threads are unaffected. No-ops for vans
+   *        that have nothing to merge.
+   */
+  virtual void Cork() {}
+  virtual void Uncork() {}
+  /*! \brief RAII helper for Cork / Uncork */
+  class CorkScope {
+   public:
+    explicit CorkScope(Van* van) : van_(van) {
+      if (van_) van_->Cork();
+    }
+    ~CorkScope() {
+      if (van_) van_->Uncork();
+    }
+    CorkScope(const CorkScope&) = delete;
+    CorkScope& operator=(const CorkScope&) = delete;
+
+   private:
+    Van* van_;
+  };
   /*! \brief install the node identity (after the scheduler assigned the id) */
   virtual void SetNode(const Node& node) {
     my_node_ = node;

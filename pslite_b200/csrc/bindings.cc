@@ -77,7 +77,7 @@ cudaEvent_t RecordOnCurrentStream(int dev) {
 class PyKVWorker {
  public:
   PyKVWorker(int app_id, int customer_id, int instance_idx)
-      : kv_(new KVWorker<char>(app_id, customer_id, instance_idx)) {}
+      : kv_(new KVWorker<char>(app_id, customer_id, instance_idx)), instance_(instance_idx) {}
 
   /*! \brief encode "the idx-th key owned by server `server`" like the benchmarks do */
   uint64_t server_key(int server, uint64_t idx) {
@@ -149,6 +149,8 @@ class PyKVWorker {
       ev = RecordOnCurrentStream(tensors[0].get_device());
     }
     py::gil_scoped_release nogil;
+    // with PS_COALESCE_LAUNCHES all pushes of this call share kernel launches and one event
+    Van::CorkScope cork(Postoffice::GetWorker(instance_)->van());
     std::vector<int> ts;
     ts.reserve(keys.size() * 2);
     auto remaining = std::make_shared<std::atomic<int>>(do_push ? static_cast<int>(keys.size()) : 0);
@@ -182,6 +184,7 @@ class PyKVWorker {
 
  private:
   std::unique_ptr<KVWorker<char>> kv_;
+  int instance_ = 0;
 };
 
 /*! \brief a KVServer whose handler is a Python callable (tests, small CPU models) */
@@ -536,6 +539,23 @@ PYBIND11_MODULE(_C, m) {
                            scale, max_ctas, CurrentStream(src)), "ps_launch_copy");
   }, py::arg("dst"), py::arg("src"), py::arg("codec") = 0, py::arg("scale") = 1.0f,
      py::arg("max_ctas") = 0);
+  m.def("copy_multi", [](std::vector<torch::Tensor> dsts, const std::vector<torch::Tensor>& srcs, int max_ctas) {
+    TORCH_CHECK(dsts.size() == srcs.size(), "dsts / srcs length mismatch");
+    if (dsts.empty()) return;
+    std::vector<ps_copy_seg> segs;
+    for (size_t i = 0; i < dsts.size(); ++i) {
+      TORCH_CHECK(dsts[i].nbytes() >= srcs[i].nbytes(), "destination ", i, " too small");
+      TORCH_CHECK(dsts[i].is_cuda() == srcs[0].is_cuda() && srcs[i].is_cuda() == srcs[0].is_cuda(),
+                  "all tensors must live on the same kind of device");
+      segs.push_back(ps_copy_seg{dsts[i].data_ptr(), srcs[i].data_ptr(), static_cast<size_t>(srcs[i].nbytes())});
+    }
+    if (!srcs[0].is_cuda()) {
+      for (const ps_copy_seg& g : segs) ps_host_copy(g.dst, g.src, g.bytes, PS_CODEC_RAW, 1.f);
+      return;
+    }
+    CheckRc(ps_launch_copy_multi(segs.data(), static_cast<int>(segs.size()), max_ctas, CurrentStream(srcs[0])),
+            "ps_launch_copy_multi");
+  }, py::arg("dsts"), py::arg("srcs"), py::arg("max_ctas") = 0);
   m.def("decode", [](torch::Tensor dst_f32, const torch::Tensor& wire, int64_t n, int fmt) {
     if (!wire.is_cuda()) {
       TORCH_CHECK(ps_host_decode(dst_f32.data_ptr<float>(), wire.data_ptr(), static_cast<size_t>(n), fmt) == 0,

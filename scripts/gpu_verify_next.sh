@@ -11,6 +11,8 @@ mkdir -p gpurun_out
 export PSLITE_NO_AUTOBUILD=1
 echo "== 1. pytest -m gpu (without the multi-GPU module)"
 timeout 900 python -m pytest tests -m gpu -x -q --ignore=tests/test_multigpu.py 2>&1 | tail -n 8
+echo "== 2. kernels written after the GPU budget ran out (multi-segment copy, host/GPU bit-exactness)"
+PSLITE_TEST_UNVERIFIED=1 timeout 400 python -m pytest tests/test_kernels_gpu.py tests/test_kernels_host.py -m gpu -q -k "multi_segment or wire_bytes" 2>&1 | tail -n 8
 echo "== 3a. multi-GPU module, verified flows"
 timeout 900 python -m pytest tests/test_multigpu.py -m gpu -q 2>&1 | tail -n 8
 echo "== 3b. in-switch gradient reduction"
@@ -19,6 +21,8 @@ echo "== 3c. nccl van"
 PSLITE_TEST_NCCL_VAN=1 timeout 400 python -m pytest tests/test_multigpu.py -m gpu -q -k nccl 2>&1 | tail -n 15
 echo "== 4. bench N=1"
 timeout 400 python bench.py --steps 20 --warmup 3 2>gpurun_out/v_b1.err | tee gpurun_out/v_bench1.json | tail -c 900
+echo "== 4. bench N=1 with launch coalescing"
+PS_COALESCE_LAUNCHES=1 timeout 400 python bench.py --steps 20 --warmup 3 --no-e2e 2>gpurun_out/v_b1c.err | tee gpurun_out/v_bench1_coalesce.json | tail -c 600
 echo "== 4. bench N=2"
 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29931 \
   bench.py --gpus 2 --steps 20 --warmup 3 2>gpurun_out/v_b2.err | tee gpurun_out/v_bench2.json | tail -c 900

@@ -121,11 +121,30 @@ void Customer::Accept(const Message& recved) {
 }
 
 void Customer::Receiving() {
+  // PS_COALESCE_LAUNCHES: handle everything that is already queued under one cork, so that
+  // the copies the handlers issue (pull replies, acks gated on kernels) share launches / events
+  const bool coalesce = GetEnv("PS_COALESCE_LAUNCHES", 0) != 0;
   for (;;) {
     Message m;
     inbox_.WaitAndPop(&m);
     if (!m.meta.control.empty() && m.meta.control.cmd == Control::TERMINATE) break;
-    Deliver(m);
+    if (!coalesce) {
+      Deliver(m);
+      continue;
+    }
+    bool stop = false;
+    {
+      Van::CorkScope cork(postoffice_->van());
+      Deliver(m);
+      for (int n = 1; n < 32 && inbox_.TryPop(&m); ++n) {
+        if (!m.meta.control.empty() && m.meta.control.cmd == Control::TERMINATE) {
+          stop = true;
+          break;
+        }
+        Deliver(m);
+      }
+    }
+    if (stop) break;
   }
 }
 

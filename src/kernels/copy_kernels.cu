@@ -77,6 +77,44 @@ __global__ void k_copy_bytes(unsigned char* __restrict__ dst, const unsigned cha
 }
 
 // ---------------------------------------------------------------------------
+// raw copy of MANY buffers in one launch (launch coalescing): blockIdx.y picks the segment,
+// the x-blocks grid-stride over it. A 4 MB message costs ~3 us of copy time but ~3 us of CPU
+// per launch + event; a round of 40 pushes becomes 2 launches and ONE event.
+// ---------------------------------------------------------------------------
+struct MultiSegs {
+  unsigned char* dst[PS_MAX_COPY_SEGS];
+  const unsigned char* src[PS_MAX_COPY_SEGS];
+  size_t bytes[PS_MAX_COPY_SEGS];
+};
+
+__global__ void __launch_bounds__(kThreads) k_copy_multi(const MultiSegs segs) {
+  const int sgi = blockIdx.y;
+  unsigned char* __restrict__ dst = segs.dst[sgi];
+  const unsigned char* __restrict__ src = segs.src[sgi];
+  const size_t n = segs.bytes[sgi];
+  const size_t stride = static_cast<size_t>(gridDim.x) * kThreads;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0;
+  size_t done = 0;
+  if (aligned) {
+    const size_t n16 = n / 16;
+    int4* d4 = reinterpret_cast<int4*>(dst);
+    const int4* s4 = reinterpret_cast<const int4*>(src);
+    size_t i = tid;
+    for (; i + 3 * stride < n16; i += 4 * stride) {
+      int4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = ld_stream(s4 + i + u * stride);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) st_stream(d4 + i + u * stride, v[u]);
+    }
+    for (; i < n16; i += stride) st_stream(d4 + i, ld_stream(s4 + i));
+    done = n16 * 16;
+  }
+  for (size_t i = done + tid; i < n; i += stride) dst[i] = src[i];  // tail / unaligned segment
+}
+
+// ---------------------------------------------------------------------------
 // raw copy, TMA bulk flavour: global -> smem -> global, driven by one thread
 // ---------------------------------------------------------------------------
 constexpr int kTmaStages = 4;
@@ -468,6 +506,42 @@ extern "C" int ps_launch_copy(void* dst, const void* src, size_t n, int codec, f
     }
     default:
       return static_cast<int>(cudaErrorInvalidValue);
+  }
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ps_launch_copy_multi(const ps_copy_seg* segs, int nseg, int max_ctas,
+                                    ps_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  int at = 0;
+  while (at < nseg) {
+    MultiSegs m;
+    int cnt = 0;
+    size_t longest = 0;
+    for (; at < nseg && cnt < PS_MAX_COPY_SEGS; ++at) {
+      if (segs[at].bytes == 0) continue;
+      m.dst[cnt] = static_cast<unsigned char*>(segs[at].dst);
+      m.src[cnt] = static_cast<const unsigned char*>(segs[at].src);
+      m.bytes[cnt] = segs[at].bytes;
+      longest = longest > segs[at].bytes ? longest : segs[at].bytes;
+      ++cnt;
+    }
+    if (cnt == 0) break;
+    for (int i = cnt; i < PS_MAX_COPY_SEGS; ++i) {
+      m.dst[i] = nullptr;
+      m.src[i] = nullptr;
+      m.bytes[i] = 0;
+    }
+    // enough x-blocks that the longest segment gets 4 x 16 B per thread per pass, but not more
+    // than 8 resident CTAs per SM over all segments
+    size_t want = (longest / 64 + kThreads - 1) / kThreads;
+    size_t cap = static_cast<size_t>(max_ctas > 0 ? max_ctas : kNumSMs * 8) / static_cast<size_t>(cnt);
+    if (cap < 1) cap = 1;
+    if (want > cap) want = cap;
+    if (want < 1) want = 1;
+    dim3 grid(static_cast<unsigned>(want), static_cast<unsigned>(cnt));
+    k_copy_multi<<<grid, kThreads, 0, stream>>>(m);
+    ++g_launches;
   }
   return static_cast<int>(cudaGetLastError());
 }

@@ -62,6 +62,15 @@ enum { PS_OPT_SGD = 0, PS_OPT_ADAMW = 1 };
 int ps_launch_copy(void* dst, const void* src, size_t n_src_bytes, int codec, float scale,
                    int max_ctas, ps_stream_t stream);
 
+/*! \brief byte copies of up to PS_MAX_COPY_SEGS unrelated buffers per kernel launch */
+#define PS_MAX_COPY_SEGS 32
+typedef struct {
+  void* dst;
+  const void* src;
+  size_t bytes;
+} ps_copy_seg;
+int ps_launch_copy_multi(const ps_copy_seg* segs, int nseg, int max_ctas, ps_stream_t stream);
+
 /*! \brief inverse transforms, for tests and for unpacking a pulled wire buffer */
 int ps_launch_decode(void* dst_f32, const void* wire, size_t n_elems, int grad_format,
                      ps_stream_t stream);

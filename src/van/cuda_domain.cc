@@ -220,6 +220,39 @@ class CudaDomain : public MemDomain {
     return t;
   }
 
+  /*! \brief raw device-to-device items share launches (ps_launch_copy_multi), one event in all */
+  Ticket CopyBatchAsync(const std::vector<CopyItem>& items) override {
+    PS_CUDA_CHECK(cudaSetDevice(dev_));
+    for (const CopyItem& it : items) {
+      if (it.wait_event) {
+        PS_CUDA_CHECK(cudaStreamWaitEvent(stream_, static_cast<cudaEvent_t>(it.wait_event), 0));
+      }
+    }
+    std::vector<ps_copy_seg> raw;
+    raw.reserve(items.size());
+    for (const CopyItem& it : items) {
+      if (it.n_src_bytes == 0) continue;
+      if (it.codec == kCodecRaw && it.src_device_type == GPU) {
+        raw.push_back(ps_copy_seg{it.dst, it.src, it.n_src_bytes});
+        continue;
+      }
+      // transforms and host-resident sources keep their own launch (still no event of their own)
+      Ticket t = CopyAsync(it.dst, it.src, it.n_src_bytes, it.codec, it.scale, nullptr, it.src_device_type);
+      std::lock_guard<std::mutex> lk(mu_);
+      free_events_.push_back(static_cast<cudaEvent_t>(t.event));  // recorded, never waited on
+    }
+    if (!raw.empty()) {
+      const int rc = ps_launch_copy_multi(raw.data(), static_cast<int>(raw.size()), max_ctas_,
+                                          reinterpret_cast<ps_stream_t>(stream_));
+      CHECK_EQ(rc, 0) << "multi-copy launch failed: " << cudaGetErrorString(static_cast<cudaError_t>(rc));
+    }
+    cudaEvent_t ev = AcquireEvent();
+    PS_CUDA_CHECK(cudaEventRecord(ev, stream_));
+    Ticket t;
+    t.event = ev;
+    return t;
+  }
+
   bool Ready(Ticket t) override {
     if (!t.event) return true;
     cudaError_t e = cudaEventQuery(static_cast<cudaEvent_t>(t.event));

@@ -120,6 +120,30 @@ class MemDomain {
    */
   virtual Ticket CopyAsync(void* dst, const void* src, size_t n_src_bytes, int codec, float scale,
                            void* wait_event, int src_device_type = UNK) = 0;
+  /*! \brief one element of a coalesced batch (see CopyBatchAsync) */
+  struct CopyItem {
+    void* dst = nullptr;
+    const void* src = nullptr;
+    size_t n_src_bytes = 0;
+    int codec = 0;
+    float scale = 1.f;
+    void* wait_event = nullptr;
+    int src_device_type = UNK;
+  };
+  /*!
+   * \brief enqueue all items and return ONE ticket that completes after the last of them
+   *        (and after everything enqueued on the domain's stream before this call). Domains
+   *        with a launch cost override this to merge the items into few launches.
+   */
+  virtual Ticket CopyBatchAsync(const std::vector<CopyItem>& items) {
+    Ticket last;
+    for (const CopyItem& it : items) {
+      if (last.event) Wait(last);  // stream order makes the newest ticket cover the older ones
+      last = CopyAsync(it.dst, it.src, it.n_src_bytes, it.codec, it.scale, it.wait_event, it.src_device_type);
+    }
+    if (items.empty()) last = CopyAsync(nullptr, nullptr, 0, 0, 1.f, nullptr);
+    return last;
+  }
   /*! \brief block until the copy behind `t` is globally visible; recycles the ticket */
   virtual void Wait(Ticket t) = 0;
   /*! \brief non-blocking: has the copy behind `t` completed? (does not recycle the ticket) */

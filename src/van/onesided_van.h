@@ -68,6 +68,10 @@ class OneSidedVan : public TcpVan {
     StopCompleter();
     TcpVan::Stop();
     domain_->ReleaseNames();
+    if (coalesce_) {
+      PS_VLOG(1) << type_ << " van " << my_node_.id << ": " << coalesced_copies_.load() << " copies in "
+                 << coalesced_batches_.load() << " coalesced batches";
+    }
     std::lock_guard<std::mutex> lk(rv_mu_);
     push_slots_.clear();
     landing_.clear();
@@ -124,7 +128,7 @@ class OneSidedVan : public TcpVan {
         domain_->Handles(msg.meta.src_dev_type, reinterpret_cast<void*>(msg.meta.addr))) {
       // a caller-named destination (symmetric buffer) needs no export / announcement
       if (!msg.meta.mem.valid()) AttachPullDestination(&msg);
-      return Ordered(msg, Ticket());
+      return Submit(msg, nullptr, false);
     }
     if (!msg.meta.request && !msg.meta.push && msg.meta.mem.valid() && has_vals) {
       if (msg.meta.codec == kCodecPlaced) return SendPlacedResponse(msg);
@@ -136,9 +140,11 @@ class OneSidedVan : public TcpVan {
       // a value-less reply marked "placed" (e.g. the ack of a push whose slot a queued kernel
       // still reads): gate it on the work already enqueued on the data stream
       msg.meta.codec = kCodecRaw;
-      return Ordered(msg, domain_->CopyAsync(nullptr, nullptr, 0, kCodecRaw, 1.f, msg.wait_event));
+      MemDomain::CopyItem gate;
+      gate.wait_event = msg.wait_event;
+      return Submit(msg, &gate, true);
     }
-    return Ordered(msg, Ticket());
+    return Submit(msg, nullptr, false);
   }
 
   int RecvMsg(Message* msg) override {
@@ -233,8 +239,14 @@ class OneSidedVan : public TcpVan {
     } else {
       slot = AcquirePushSlot(recver, msg.meta.key, wire);
     }
-    Ticket t = domain_->CopyAsync(slot.ptr, vals.data(), vals.size(), msg.meta.codec,
-                                  msg.meta.scale, msg.wait_event, vals.src_device_type_);
+    MemDomain::CopyItem item;
+    item.dst = slot.ptr;
+    item.src = vals.data();
+    item.n_src_bytes = vals.size();
+    item.codec = msg.meta.codec;
+    item.scale = msg.meta.scale;
+    item.wait_event = msg.wait_event;
+    item.src_device_type = vals.src_device_type_;
     ++copies_;
     copy_bytes_ += wire;
     Message desc;
@@ -246,7 +258,7 @@ class OneSidedVan : public TcpVan {
     desc.data[1] = vals.segment(0, 0);  // payload already placed; keep the segment slot
     desc.meta.data_size = msg.meta.data_size - static_cast<int64_t>(vals.size());
     // keep the source alive until the copy has completed
-    return Ordered(desc, t, vals) + static_cast<int>(std::min<uint64_t>(wire, 0x3fffffff));
+    return Submit(desc, &item, false, vals) + static_cast<int>(std::min<uint64_t>(wire, 0x3fffffff));
   }
 
   /*! \brief landing slot at `recver` for `key`; rendezvous on first use or growth */
@@ -387,9 +399,14 @@ class OneSidedVan : public TcpVan {
     if (msg.meta.mem.bytes) {
       CHECK_LE(wire, msg.meta.mem.bytes) << "pull response larger than the destination";
     }
-    Ticket t = domain_->CopyAsync(base + msg.meta.mem.offset, vals.data(), vals.size(),
-                                  msg.meta.codec, msg.meta.scale, msg.wait_event,
-                                  vals.src_device_type_);
+    MemDomain::CopyItem item;
+    item.dst = base + msg.meta.mem.offset;
+    item.src = vals.data();
+    item.n_src_bytes = vals.size();
+    item.codec = msg.meta.codec;
+    item.scale = msg.meta.scale;
+    item.wait_event = msg.wait_event;
+    item.src_device_type = vals.src_device_type_;
     ++copies_;
     copy_bytes_ += wire;
     Message desc;
@@ -398,7 +415,7 @@ class OneSidedVan : public TcpVan {
     desc.data = msg.data;
     desc.data[1] = vals.segment(0, 0);
     desc.meta.data_size = msg.meta.data_size - static_cast<int64_t>(vals.size());
-    return Ordered(desc, t, vals) + static_cast<int>(std::min<uint64_t>(wire, 0x3fffffff));
+    return Submit(desc, &item, false, vals) + static_cast<int>(std::min<uint64_t>(wire, 0x3fffffff));
   }
 
   /*!
@@ -407,7 +424,8 @@ class OneSidedVan : public TcpVan {
    *        worker's buffer); only gate the descriptor on `wait_event`.
    */
   int SendPlacedResponse(Message& msg) {
-    Ticket t = domain_->CopyAsync(nullptr, nullptr, 0, kCodecRaw, 1.f, msg.wait_event);
+    MemDomain::CopyItem gate;  // no bytes to move: only wait for the stream (and the event)
+    gate.wait_event = msg.wait_event;
     Message desc;
     desc.meta = msg.meta;
     desc.meta.codec = kCodecRaw;
@@ -415,7 +433,7 @@ class OneSidedVan : public TcpVan {
     desc.data = msg.data;
     desc.data[1] = msg.data[1].segment(0, 0);
     desc.meta.data_size = msg.meta.data_size - static_cast<int64_t>(msg.data[1].size());
-    return Ordered(desc, t);
+    return Submit(desc, &gate, true);
   }
 
   // -- receive-side payload reconstruction -----------------------------------------
@@ -450,6 +468,83 @@ class OneSidedVan : public TcpVan {
     SArray<char> keep_alive;
   };
 
+  // -- launch coalescing ------------------------------------------------------------------
+
+  struct Held {
+    Message msg;
+    SArray<char> keep_alive;
+  };
+  struct CorkState {
+    int depth = 0;
+    bool gate = false;  // some message must wait for the data stream even without a copy
+    std::vector<MemDomain::CopyItem> items;
+    std::vector<Held> held;
+  };
+  /*! \brief this thread's cork on this van */
+  CorkState& MyCork() {
+    thread_local std::map<const OneSidedVan*, CorkState> per_van;
+    return per_van[this];
+  }
+
+  /*!
+   * \brief the one way out for data messages: `item` (may be null) is the copy that must
+   *        complete before `msg` may leave; `gate_only` marks an item that moves no bytes.
+   *        Corked: remember both; otherwise issue the copy now and queue the message behind it.
+   */
+  int Submit(Message& msg, const MemDomain::CopyItem* item, bool gate_only,
+             const SArray<char>& keep_alive = SArray<char>()) {
+    if (coalesce_) {
+      CorkState& c = MyCork();
+      if (c.depth > 0) {
+        if (item && !gate_only) c.items.push_back(*item);
+        if (item && gate_only) {
+          c.gate = true;
+          if (item->wait_event) c.items.push_back(*item);  // zero bytes: only its event matters
+        }
+        Held h;
+        h.msg = msg;
+        h.keep_alive = keep_alive;
+        c.held.push_back(std::move(h));
+        return 1 + static_cast<int>(msg.meta.data_size & 0x3fffffff);
+      }
+    }
+    Ticket t;
+    if (item) {
+      t = domain_->CopyAsync(item->dst, item->src, gate_only ? 0 : item->n_src_bytes, item->codec,
+                             item->scale, item->wait_event, item->src_device_type);
+    }
+    return Ordered(msg, t, keep_alive);
+  }
+
+ public:
+  void Cork() override {
+    if (coalesce_) ++MyCork().depth;
+  }
+  void Uncork() override {
+    if (!coalesce_) return;
+    CorkState& c = MyCork();
+    if (c.depth == 0 || --c.depth > 0) return;
+    if (c.held.empty()) return;
+    Ticket t;
+    if (!c.items.empty() || c.gate) {
+      t = domain_->CopyBatchAsync(c.items);
+      ++coalesced_batches_;
+      coalesced_copies_ += c.items.size();
+    }
+    // the first message carries the ticket; the queue is FIFO, so the others (and their
+    // keep-alive references) follow it out only after the whole batch has completed
+    for (size_t i = 0; i < c.held.size(); ++i) {
+      Ordered(c.held[i].msg, i == 0 ? t : Ticket(), c.held[i].keep_alive);
+    }
+    c.items.clear();
+    c.held.clear();
+    c.gate = false;
+  }
+  /*! \brief batches flushed by Uncork / copies that shared a batch (tests, benchmarks) */
+  uint64_t num_coalesced_batches() const { return coalesced_batches_.load(); }
+  uint64_t num_coalesced_copies() const { return coalesced_copies_.load(); }
+
+ private:
   /*!
    * \brief send `msg` after `t` completes, preserving the order of SendMsg calls.
    *        With nothing in flight and no ticket the send happens inline.
@@ -550,6 +645,10 @@ class OneSidedVan : public TcpVan {
 
   std::atomic<uint64_t> copies_{0};
   std::atomic<uint64_t> copy_bytes_{0};
+  /*! \brief PS_COALESCE_LAUNCHES: honour Cork / Uncork (off: every copy is its own launch) */
+  bool coalesce_ = GetEnv("PS_COALESCE_LAUNCHES", 0) != 0;
+  std::atomic<uint64_t> coalesced_batches_{0};
+  std::atomic<uint64_t> coalesced_copies_{0};
 };
 
 }  // namespace ps

@@ -33,6 +33,21 @@ def test_raw_copy(native, n):
     assert torch.equal(dst, src)
 
 
+@pytest.mark.skipif(__import__("os").environ.get("PSLITE_TEST_UNVERIFIED", "0") != "1",
+                    reason="k_copy_multi not yet validated on hardware; set PSLITE_TEST_UNVERIFIED=1")
+def test_multi_segment_copy(native):
+    """one launch, many unrelated buffers (launch coalescing), incl. unaligned and tiny ones"""
+    _require_cuda()
+    sizes = [1, 15, 16, 4097, 65536, 1 << 20, 3 * (1 << 20) + 5] * 7  # 49 segments: two launches
+    srcs = [torch.randint(0, 255, (n,), dtype=torch.uint8, device="cuda") for n in sizes]
+    srcs[3] = torch.randint(0, 255, (4098,), dtype=torch.uint8, device="cuda")[1:]  # misaligned source
+    dsts = [torch.zeros(s.numel(), dtype=torch.uint8, device="cuda") for s in srcs]
+    native.copy_multi(dsts, srcs)
+    torch.cuda.synchronize()
+    for d, s in zip(dsts, srcs):
+        assert torch.equal(d, s)
+
+
 @pytest.mark.parametrize("n", [8, 1000, 100003])
 def test_f32_to_bf16_scaled(native, n):
     _require_cuda()

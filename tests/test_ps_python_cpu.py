@@ -85,17 +85,23 @@ def test_trainer_logic_on_cpu(native):
 
 @pytest.mark.parametrize("nproc,topo,length,async_copies", [
     (8, "split", 4096, "1"), (8, "split", 1 << 20, "1"), (4, "joint", 65536, "1"), (4, "split", 4096, "0")])
-def test_bench_loop_many_peers(native, nproc, topo, length, async_copies):
+def test_bench_loop_many_peers(native, nproc, topo, length, async_copies, coalesce="0"):
     """bench.py's push_pull_batch loop under torchrun with several workers AND servers, over the
     one-sided van with *asynchronous* copies (PS_SHM_ASYNC: copies complete later, as kernels
     on a CUDA stream do). Descriptors for different peers then share completion batches — the
     case a per-peer batch of one once mishandled (pull replies arrived without their MemRef)."""
     helper = os.path.join(HERE, "helpers", "pushpull_multi.py")
     env = dict(os.environ)
-    env.update({"PSLITE_NO_AUTOBUILD": "1", "PS_SHM_ASYNC": async_copies, "OMP_NUM_THREADS": "1"})
+    env.update({"PSLITE_NO_AUTOBUILD": "1", "PS_SHM_ASYNC": async_copies, "OMP_NUM_THREADS": "1",
+                "PS_COALESCE_LAUNCHES": coalesce})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()), helper, "shm", str(length), "10",
            "10", topo]
     for attempt in range(2):  # the hang this guards against was probabilistic: run it a few times
         p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=150)
         assert p.returncode == 0 and "PASS" in p.stdout, (p.stdout + p.stderr)[-3000:]
+
+
+def test_bench_loop_with_launch_coalescing(native):
+    """the same loop with every push_pull_batch call and every handler batch corked"""
+    test_bench_loop_many_peers(native, 8, "split", 65536, "1", coalesce="1")

@@ -74,3 +74,11 @@ def test_asynchronous_sgd(native):
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=280, cwd=ROOT)
     out = p.stdout + p.stderr
     assert p.returncode == 0 and "PASS" in out, out[-3000:]
+
+
+@pytest.mark.timeout(300)
+def test_launch_coalescing_keeps_results(native):
+    """PS_COALESCE_LAUNCHES=1: handlers and batch calls run corked — their copies are issued as
+    one batch and the held messages leave in order afterwards; training must be unaffected"""
+    out = _run(4, "joint", "fp8", 5, PSLITE_TEST_EXPORTABLE_PARAMS=1, PS_SHM_ASYNC=1, PS_COALESCE_LAUNCHES=1)
+    assert "engine=host" in out
