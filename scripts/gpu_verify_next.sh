@@ -9,7 +9,8 @@
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 export PSLITE_NO_AUTOBUILD=1
-echo "== 1. pytest -m gpu (without the multi-GPU module)"
+echo "== 1. pytest -m gpu (without the multi-GPU module); PSLITE_TEST_UNVERIFIED=1 adds the checkpoint round trip"
+export PSLITE_TEST_UNVERIFIED=1
 timeout 900 python -m pytest tests -m gpu -x -q --ignore=tests/test_multigpu.py 2>&1 | tail -n 8
 echo "== 2. kernels written after the GPU budget ran out (multi-segment copy, host/GPU bit-exactness)"
 PSLITE_TEST_UNVERIFIED=1 timeout 400 python -m pytest tests/test_kernels_gpu.py tests/test_kernels_host.py -m gpu -q -k "multi_segment or wire_bytes" 2>&1 | tail -n 8
