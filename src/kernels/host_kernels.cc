@@ -63,28 +63,21 @@ const float* E4m3Table() {
 
 /*! \brief fp32 -> e4m3, round to nearest even, saturating at +-448 (cvt.rn.satfinite) */
 inline uint8_t F32ToE4m3(float f) {
-  const uint32_t u = F2U(f);
+  uint32_t u = F2U(f);
   const uint8_t sign = static_cast<uint8_t>((u >> 24) & 0x80);
-  const float a = std::fabs(f);
-  if (a != a) return static_cast<uint8_t>(sign | 0x7f);
-  if (a >= 448.f) return static_cast<uint8_t>(sign | 0x7e);
-  if (a < std::ldexp(1.f, -10)) return sign;  // below half of the smallest subnormal (2^-9)
-  int e;
-  std::frexp(a, &e);  // a = m * 2^e, m in [0.5, 1)
-  int exp = e - 1;    // a = 1.xxx * 2^exp
-  if (exp < -6) exp = -6;  // subnormal range shares the exponent of 2^-6
-  // quantum of the 3-bit mantissa at this exponent
-  const float q = std::ldexp(1.f, exp - 3);
-  float r = std::nearbyint(a / q);  // current rounding mode is nearest-even
-  float v = r * q;
-  if (v >= 448.f) return static_cast<uint8_t>(sign | 0x7e);
-  if (v < std::ldexp(1.f, -6)) {  // subnormal result: mantissa = v / 2^-9
-    return static_cast<uint8_t>(sign | static_cast<uint8_t>(std::lrint(std::ldexp(v, 9))));
+  u &= 0x7fffffffu;
+  if (u > 0x7f800000u) return static_cast<uint8_t>(sign | 0x7f);  // NaN
+  const float a = U2F(u);
+  if (a < 0.015625f) {
+    // below 2^-6 the grid is uniform (step 2^-9): subnormals, and 8 * 2^-9 is the first normal
+    return static_cast<uint8_t>(sign | static_cast<uint8_t>(std::lrintf(a * 512.f)));
   }
-  std::frexp(v, &e);
-  exp = e - 1;
-  const int man = static_cast<int>(std::lrint((std::ldexp(v, -exp) - 1.f) * 8.f));
-  return static_cast<uint8_t>(sign | ((exp + 7) << 3) | man);
+  // keep 3 mantissa bits: add half of the dropped 20 bits (ties to even), truncate
+  u += 0x7ffffu + ((u >> 20) & 1u);
+  u &= 0xfff00000u;
+  if (u > 0x43e00000u) return static_cast<uint8_t>(sign | 0x7e);  // > 448 (or inf): saturate
+  const uint32_t exp = (u >> 23) - 120u;  // biased by 7: 2^-6 -> 1
+  return static_cast<uint8_t>(sign | (exp << 3) | ((u >> 20) & 7u));
 }
 
 inline uint32_t E8m0ForAmax(float amax) {
@@ -234,42 +227,86 @@ extern "C" int ps_host_sum(float* out, const void* const* grads, int num_grads, 
   return 0;
 }
 
+namespace {
+/*! \brief g[0..cnt) = sum over the W slots of elements [i0, i0+cnt), format fixed at compile time */
+template <int FMT>
+inline void GatherBlock(const ps_update_args& a, size_t i0, int cnt, size_t npad, const float* e4m3,
+                        float* g) {
+  for (int j = 0; j < cnt; ++j) g[j] = 0.f;
+  for (int w = 0; w < a.num_grads; ++w) {
+    const unsigned char* base = static_cast<const unsigned char*>(a.grads[w]);
+    if (FMT == PS_GRAD_BF16) {
+      const uint16_t* s = reinterpret_cast<const uint16_t*>(base) + i0;
+      for (int j = 0; j < cnt; ++j) g[j] += Bf16ToF32(s[j]);
+    } else if (FMT == PS_GRAD_FP8BLOCK) {
+      const unsigned char* q = base + i0;
+      const unsigned char* sc = base + npad;
+      for (int j = 0; j < cnt; ++j) g[j] += e4m3[q[j]] * Exp2FromE8m0(sc[(i0 + j) >> 5]);
+    } else {
+      const float* s = reinterpret_cast<const float*>(base) + i0;
+      for (int j = 0; j < cnt; ++j) g[j] += s[j];
+    }
+  }
+}
+
+template <int FMT>
+void UpdateRange(const ps_update_args& args, const ps_opt_params& opt, size_t b0, size_t b1) {
+  constexpr int kBlock = 256;
+  const size_t npad = (args.n + 31) / 32 * 32;
+  const float* e4m3 = E4m3Table();
+  const bool adam = opt.optimizer == PS_OPT_ADAMW;
+  const float inv_bc1 = adam ? 1.f / opt.bias_corr1 : 1.f, inv_bc2 = adam ? 1.f / opt.bias_corr2 : 1.f;
+  float g[kBlock], pnew[kBlock];
+  for (size_t i0 = b0; i0 < b1; i0 += kBlock) {
+    const int cnt = static_cast<int>(std::min<size_t>(kBlock, b1 - i0));
+    GatherBlock<FMT>(args, i0, cnt, npad, e4m3, g);
+    float* p = args.master + i0;
+    float* m = args.m + i0;
+    if (adam) {
+      float* v = args.v + i0;
+      for (int j = 0; j < cnt; ++j) {
+        const float gj = g[j] * opt.grad_scale;
+        const float mj = opt.beta1 * m[j] + (1.f - opt.beta1) * gj;
+        const float vj = opt.beta2 * v[j] + (1.f - opt.beta2) * gj * gj;
+        const float denom = std::sqrt(vj * inv_bc2) + opt.eps;
+        pnew[j] = p[j] - opt.lr * ((mj * inv_bc1) / denom + opt.weight_decay * p[j]);
+        m[j] = mj;
+        v[j] = vj;
+      }
+    } else {
+      for (int j = 0; j < cnt; ++j) {
+        const float gj = g[j] * opt.grad_scale + opt.weight_decay * p[j];
+        const float mj = opt.beta1 * m[j] + gj;
+        pnew[j] = p[j] - opt.lr * mj;
+        m[j] = mj;
+      }
+    }
+    for (int j = 0; j < cnt; ++j) p[j] = pnew[j];
+    for (int k = 0; k < args.num_outs; ++k) {
+      if (args.out_f32) {
+        float* out = static_cast<float*>(args.outs[k]) + i0;
+        for (int j = 0; j < cnt; ++j) out[j] = pnew[j];
+      } else {
+        uint16_t* out = static_cast<uint16_t*>(args.outs[k]) + i0;
+        for (int j = 0; j < cnt; ++j) out[j] = F32ToBf16(pnew[j]);
+      }
+    }
+  }
+}
+}  // namespace
+
 extern "C" int ps_host_update(const ps_update_args* a, const ps_opt_params* o) {
   if (a->n == 0) return 0;
   if (a->num_grads < 1 || a->num_grads > PS_MAX_FANIN) return 1;
   if (a->num_outs < 0 || a->num_outs > PS_MAX_FANOUT) return 1;
   const int fmt = a->grad_format;
   if (fmt != PS_GRAD_BF16 && fmt != PS_GRAD_FP8BLOCK && fmt != PS_GRAD_F32) return 1;
-  const size_t n = a->n, npad = (n + 31) / 32 * 32;
-  const float* e4m3 = E4m3Table();
   const ps_update_args args = *a;
   const ps_opt_params opt = *o;
-  const bool adam = opt.optimizer == PS_OPT_ADAMW;
-  ParallelFor(n, 32, [=](size_t b0, size_t b1) {
-    for (size_t i = b0; i < b1; ++i) {
-      float g = 0.f;
-      for (int w = 0; w < args.num_grads; ++w) g += LoadGrad(args.grads[w], fmt, i, npad, e4m3);
-      g *= opt.grad_scale;
-      float p = args.master[i], m = args.m[i];
-      if (adam) {
-        float v = args.v[i];
-        m = opt.beta1 * m + (1.f - opt.beta1) * g;
-        v = opt.beta2 * v + (1.f - opt.beta2) * g * g;
-        const float denom = std::sqrt(v / opt.bias_corr2) + opt.eps;
-        p = p - opt.lr * ((m / opt.bias_corr1) / denom + opt.weight_decay * p);
-        args.v[i] = v;
-      } else {
-        g += opt.weight_decay * p;
-        m = opt.beta1 * m + g;
-        p = p - opt.lr * m;
-      }
-      args.master[i] = p;
-      args.m[i] = m;
-      for (int k = 0; k < args.num_outs; ++k) {
-        if (args.out_f32) static_cast<float*>(args.outs[k])[i] = p;
-        else static_cast<uint16_t*>(args.outs[k])[i] = F32ToBf16(p);
-      }
-    }
+  ParallelFor(args.n, 256, [=](size_t b0, size_t b1) {
+    if (fmt == PS_GRAD_BF16) UpdateRange<PS_GRAD_BF16>(args, opt, b0, b1);
+    else if (fmt == PS_GRAD_FP8BLOCK) UpdateRange<PS_GRAD_FP8BLOCK>(args, opt, b0, b1);
+    else UpdateRange<PS_GRAD_F32>(args, opt, b0, b1);
   });
   return 0;
 }
