@@ -13,6 +13,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "core/nvtx.h"
 #include "kernels/host_kernels.h"
 #include "van/mem_domain.h"
 
@@ -404,6 +405,7 @@ void GpuServer::MaybeRunRound(Key key, Shard* s) {
   const int W = cfg_.num_workers;
   if (s->num_pushed < W) return;
   if (cfg_.fuse_pull && static_cast<int>(s->waiting_pulls.size()) < W) return;
+  NvtxRange nvtx("ps.server_round");
 
   ps_update_args a;
   memset(&a, 0, sizeof(a));

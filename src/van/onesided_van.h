@@ -40,6 +40,7 @@
 #include <utility>
 #include <vector>
 
+#include "core/nvtx.h"
 #include "van/mem_domain.h"
 #include "van/tcp_van.h"
 
@@ -225,6 +226,7 @@ class OneSidedVan : public TcpVan {
   // -- push: sender side -------------------------------------------------------
 
   int SendPush(Message& msg) {
+    NvtxRange nvtx("ps.push");
     const int recver = msg.meta.recver;
     const SArray<char>& vals = msg.data[1];
     const uint64_t wire = WireBytes(msg.meta.codec, vals.size());
@@ -385,6 +387,7 @@ class OneSidedVan : public TcpVan {
   }
 
   int SendPullResponse(Message& msg) {
+    NvtxRange nvtx("ps.pull_reply");
     const int recver = msg.meta.recver;
     char* base = nullptr;
     {
@@ -525,6 +528,7 @@ class OneSidedVan : public TcpVan {
     CorkState& c = MyCork();
     if (c.depth == 0 || --c.depth > 0) return;
     if (c.held.empty()) return;
+    NvtxRange nvtx("ps.uncork");
     Ticket t;
     if (!c.items.empty() || c.gate) {
       t = domain_->CopyBatchAsync(c.items);
