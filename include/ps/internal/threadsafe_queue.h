@@ -19,6 +19,7 @@
 #include <thread>
 #include <utility>
 #include "ps/internal/env.h"
+#include "ps/internal/utils.h"
 #include "ps/internal/spsc_queue.h"
 
 namespace ps {
@@ -48,6 +49,7 @@ class ThreadsafeQueue {
     {
       std::lock_guard<std::mutex> lk(mu_);
       items_.push_back(std::move(v));
+      count_.fetch_add(1, std::memory_order_release);
     }
     cv_.notify_one();
   }
@@ -69,19 +71,32 @@ class ThreadsafeQueue {
       }
       return;
     }
+    // stay hot for a moment before sleeping: a producer that finds no sleeper skips the futex
+    // wake (a system call per message otherwise), and the consumer skips the context switch
+    if (spin_us_ > 0 && count_.load(std::memory_order_acquire) == 0) {
+      const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us_);
+      int polls = 0;
+      while (count_.load(std::memory_order_acquire) == 0) {
+        if ((++polls & 63) == 0 && std::chrono::steady_clock::now() >= deadline) break;
+        CpuRelax();
+      }
+    }
     std::unique_lock<std::mutex> lk(mu_);
     cv_.wait(lk, [this] { return !items_.empty(); });
     *out = std::move(items_.front());
     items_.pop_front();
+    count_.fetch_sub(1, std::memory_order_release);
   }
 
   /*! \brief non-blocking pop */
   bool TryPop(T* out) {
     if (lockless_) return ring_->try_pop(out);
+    if (count_.load(std::memory_order_acquire) == 0) return false;
     std::lock_guard<std::mutex> lk(mu_);
     if (items_.empty()) return false;
     *out = std::move(items_.front());
     items_.pop_front();
+    count_.fetch_sub(1, std::memory_order_release);
     return true;
   }
 
@@ -95,9 +110,18 @@ class ThreadsafeQueue {
   static constexpr size_t kRingCapacity = 32768;
   bool lockless_ = false;
   long long spin_ns_ = 1000;
+  static void CpuRelax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#else
+    std::this_thread::yield();
+#endif
+  }
   std::mutex mu_;
   std::condition_variable cv_;
   std::deque<T> items_;
+  std::atomic<size_t> count_{0};  // == items_.size(), readable without the lock
+  int spin_us_ = GetEnv("PS_QUEUE_SPIN_US", 20);
   std::unique_ptr<SPSCQueue<T>> ring_;
   std::atomic_flag push_lock_ = ATOMIC_FLAG_INIT;
 };

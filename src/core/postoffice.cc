@@ -5,6 +5,7 @@
  * GetCustomer waits on a condition variable instead of polling every 1 ms.
  */
 #include "ps/internal/postoffice.h"
+#include "core/sampler.h"
 #include <chrono>
 #include <thread>
 #include "ps/base.h"
@@ -91,6 +92,7 @@ void Postoffice::BuildGroupTable() {
 
 void Postoffice::Start(int customer_id, const Node::Role role, int rank, const bool do_barrier,
                        const char* argv0) {
+  SampleProfiler::StartIfRequested();  // PS_SAMPLE_PROFILE=<file>: CPU sampling of this process
   CHECK_GE(rank, -1);
   preferred_rank_ = rank;
   {

@@ -425,6 +425,13 @@ class TcpVan : public Van {
           continue;  // something arrived while we were getting ready to sleep
         }
       }
+      if (timeout_ms == 0 && (++spin_polls_ & 15) != 0) {
+        // busy phase: the rings and the loopback queue are checked every pass, the sockets
+        // (control traffic, doorbells, new connections) only every 16th: epoll_wait is a
+        // system call even when it returns at once
+        CpuRelax();
+        continue;
+      }
       struct epoll_event evs[16];
       int n = epoll_wait(epfd_, evs, 16, timeout_ms);
       if (timeout_ms != 0) {
@@ -865,6 +872,12 @@ class TcpVan : public Van {
   int wake_fd_ = -1;
   int listen_fd_ = -1;
   std::unordered_map<int, std::unique_ptr<Inbound>> inbound_;  // receive thread only
+  static void CpuRelax() {
+#if defined(__x86_64__) || defined(__i386__)
+    __builtin_ia32_pause();
+#endif
+  }
+  uint32_t spin_polls_ = 0;
   std::vector<int> pipe_fds_;                                  // inbound connections with a ring
   size_t pipe_cursor_ = 0;
   bool use_pipes_ = true;
