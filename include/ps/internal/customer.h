@@ -57,6 +57,8 @@ class Customer {
   // ---- inbox (van receive thread -> application) ------------------------------
   /*! \brief hand a received message to this customer */
   void Accept(const Message& recved);
+  /*! \brief same, taking ownership: saves the deep copy of the Meta on the receive thread */
+  void Accept(Message&& recved);
 
   // ---- request tracker -----------------------------------------------------------
   /*!

@@ -57,6 +57,8 @@ class Postoffice {
    *        RemoveCustomer waits for deliveries in flight.
    */
   bool Deliver(int app_id, int customer_id, const Message& msg);
+  /*! \brief same; `*msg` is moved from only when true is returned */
+  bool DeliverOwned(int app_id, int customer_id, Message* msg);
 
   /*! \brief instance ids of a group id, or {id} for a single node id */
   const std::vector<int>& GetNodeIDs(int node_id) const {

@@ -120,6 +120,14 @@ void Customer::Accept(const Message& recved) {
   }
 }
 
+void Customer::Accept(Message&& recved) {
+  if (direct_dispatch_) {
+    Deliver(recved);
+  } else {
+    inbox_.Push(std::move(recved));
+  }
+}
+
 void Customer::Receiving() {
   // PS_COALESCE_LAUNCHES: handle everything that is already queued under one cork, so that
   // the copies the handlers issue (pull replies, acks gated on kernels) share launches / events

@@ -176,6 +176,14 @@ void Postoffice::RemoveCustomer(Customer* customer) {
   std::unique_lock<std::shared_mutex> drain(deliver_mu_);
 }
 
+bool Postoffice::DeliverOwned(int app_id, int customer_id, Message* msg) {
+  std::shared_lock<std::shared_mutex> in_flight(deliver_mu_);
+  Customer* obj = GetCustomer(app_id, customer_id, 0);
+  if (!obj) return false;
+  obj->Accept(std::move(*msg));
+  return true;
+}
+
 bool Postoffice::Deliver(int app_id, int customer_id, const Message& msg) {
   std::shared_lock<std::shared_mutex> in_flight(deliver_mu_);
   Customer* obj = GetCustomer(app_id, customer_id, 0);

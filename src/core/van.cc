@@ -284,7 +284,15 @@ void Van::ProcessDataMsg(Message* msg) {
   const int app_id = msg->meta.app_id;
   // servers run one customer per app; workers may run several
   const int customer_id = postoffice_->is_worker() ? msg->meta.customer_id : app_id;
-  if (!postoffice_->Deliver(app_id, customer_id, *msg)) {
+  // what the profiling line needs, read before the message is handed over
+  const bool log_it = profiling_ && !msg->data.empty() && msg->data[0].size() >= 2 && !msg->data[0].on_gpu();
+  int key16 = 0;
+  const bool is_push = msg->meta.push;
+  if (log_it) {
+    const unsigned char* k = reinterpret_cast<const unsigned char*>(msg->data[0].data());
+    key16 = k[0] + 256 * k[1];
+  }
+  if (!postoffice_->DeliverOwned(app_id, customer_id, msg)) {
     // The application has not created this customer yet (e.g. it is still inside the
     // start-up barrier). Park the message instead of blocking the receive thread — the
     // reference waits here for up to 5 s (src/van.cc:435), during which no barrier
@@ -293,15 +301,12 @@ void Van::ProcessDataMsg(Message* msg) {
     parked_.push_back(*msg);
     return;
   }
-
-  if (profiling_ && !msg->data.empty() && msg->data[0].size() >= 2 && !msg->data[0].on_gpu()) {
+  if (log_it) {
     auto us = std::chrono::duration_cast<std::chrono::microseconds>(
                   std::chrono::system_clock::now().time_since_epoch()).count();
-    const unsigned char* k = reinterpret_cast<const unsigned char*>(msg->data[0].data());
-    const int key16 = k[0] + 256 * k[1];
     std::lock_guard<std::mutex> lk(profile_mu_);
     profile_out_ << key16 << "\t" << (postoffice_->is_worker() ? "worker" : "server")
-                 << "_van_recv_" << (msg->meta.push ? "push" : "pull") << "\t" << us << "\n";
+                 << "_van_recv_" << (is_push ? "push" : "pull") << "\t" << us << "\n";
   }
 }
 
