@@ -65,6 +65,21 @@ TEST(sarray_append_self) {
   CHECK_EQ(a[5], 3);
 }
 
+TEST(sarray_compact) {
+  for (size_t n : {size_t(1), size_t(8), size_t(16), size_t(17), size_t(1000)}) {
+    SArray<uint32_t> a = SArray<uint32_t>::Compact(n);
+    CHECK_EQ(a.size(), n);
+    CHECK_EQ(reinterpret_cast<uintptr_t>(a.data()) % alignof(uint32_t), (uintptr_t)0);
+    for (size_t i = 0; i < n; ++i) a[i] = static_cast<uint32_t>(i * 3 + 1);
+    SArray<uint32_t> b = a;  // shares the block
+    SArray<char> bytes(a);   // converting view keeps it alive too
+    a.clear();
+    for (size_t i = 0; i < n; ++i) CHECK_EQ(b[i], static_cast<uint32_t>(i * 3 + 1));
+    CHECK_EQ(bytes.size(), n * 4);
+  }
+  CHECK(SArray<char>::Compact(0).empty());
+}
+
 TEST(find_range) {
   SArray<Key> a{1, 3, 5, 7, 9};
   Range r = FindRange(a, (Key)2, (Key)7);

@@ -655,9 +655,7 @@ class TcpVan : public Van {
     SArray<char> seg;
     if (len == 0) return seg;
     if (len >= 4096) return pool_->Get(len);
-    char* p = new char[len];
-    seg.reset(p, len, [](char* q) { delete[] q; });
-    return seg;
+    return SArray<char>::Compact(len);  // keys / lens: one allocation, not two
   }
 
   /*!
