@@ -12,6 +12,7 @@
 #define PS_CORE_SAMPLER_H_
 #include <execinfo.h>
 #include <signal.h>
+#include <sys/syscall.h>
 #include <sys/time.h>
 #include <unistd.h>
 
@@ -54,6 +55,7 @@ class SampleProfiler {
     std::atomic<int> next{0};
     void* frames[kMaxSamples][kDepth];
     int depth[kMaxSamples];
+    int tid[kMaxSamples];
   };
   static Store& State() {
     static Store* s = new Store();
@@ -64,6 +66,7 @@ class SampleProfiler {
     const int i = s.next.fetch_add(1);
     if (i >= kMaxSamples) return;
     s.depth[i] = backtrace(s.frames[i], kDepth);
+    s.tid[i] = static_cast<int>(syscall(SYS_gettid));
   }
   static void Dump() {
     struct itimerval off = {};
@@ -80,6 +83,7 @@ class SampleProfiler {
     }
     const int n = s.next.load() < kMaxSamples ? s.next.load() : kMaxSamples;
     for (int i = 0; i < n; ++i) {
+      fprintf(f, "t%d ", s.tid[i]);
       for (int d = 2; d < s.depth[i]; ++d) fprintf(f, "%p ", s.frames[i][d]);  // skip handler frames
       fputc('\n', f);
     }
