@@ -84,6 +84,14 @@ class Van {
    *        order they were submitted. Nests; other threads are unaffected. No-ops for vans
    *        that have nothing to merge.
    */
+  /*!
+   * \brief in-process hand-off: take a data message another van of THIS process built for us,
+   *        exactly as if the receive loop had read it (byte count, verbose log, customer
+   *        lookup). False — and `*msg` untouched — when per-message receive processing is
+   *        active (resend bookkeeping, drop injection, profiling log), the van is not running,
+   *        or the customer does not exist yet: the caller then uses the normal transport.
+   */
+  bool AcceptHandoff(Message* msg);
   virtual void Cork() {}
   virtual void Uncork() {}
   /*! \brief RAII helper for Cork / Uncork */

@@ -310,6 +310,21 @@ void Van::ProcessDataMsg(Message* msg) {
   }
 }
 
+bool Van::AcceptHandoff(Message* msg) {
+  if (!ready_.load() || stopping_.load() || resender_ != nullptr || drop_rate_ > 0 || profiling_) {
+    return false;
+  }
+  if (msg->meta.app_id == Meta::kEmpty) return false;
+  const int customer_id = postoffice_->is_worker() ? msg->meta.customer_id : msg->meta.app_id;
+  const size_t bytes = static_cast<size_t>(msg->meta.data_size > 0 ? msg->meta.data_size : 0) + 64;
+  if (postoffice_->verbose() >= 2) {
+    LOG(INFO) << GetType() << " " << my_node_.id << "\treceived (in-process): " << msg->DebugString();
+  }
+  if (!postoffice_->DeliverOwned(msg->meta.app_id, customer_id, msg)) return false;
+  recv_bytes_ += bytes;
+  return true;
+}
+
 void Van::DeliverParked() {
   std::vector<Message> todo;
   {

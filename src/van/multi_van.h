@@ -56,6 +56,8 @@ class MultiVan : public Van {
   class Rail : public TcpVan {
    public:
     explicit Rail(Postoffice* po) : TcpVan(po) {}
+    // a rail is driven by the MultiVan's own receive logic, never by Van::Receiving
+    bool AllowLocalHandoff() const override { return false; }
     void Open() { InitTransport(); }
     void Identify(const Node& n) { Van::SetNode(n); }
     int BindPort(Node& n, int retry) { return Bind(n, retry); }

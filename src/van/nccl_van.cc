@@ -318,6 +318,9 @@ class NcclVan : public TcpVan {
     }
   }
 
+  // payload messages complete asynchronously on this van's receive thread: no in-process shortcut
+  bool AllowLocalHandoff() const override { return false; }
+
   bool HasDeferred() override { return !deferred_.empty(); }
 
   bool PollDeferred(Message* msg) override {

@@ -148,6 +148,24 @@ class OneSidedVan : public TcpVan {
     return Submit(msg, nullptr, false);
   }
 
+  /*! \brief a descriptor handed over in-process still has to be turned into its payload view */
+  void OnLocalDeliver(Message* msg) override {
+    if (msg->meta.control.empty() && !msg->meta.simple_app && msg->meta.mem.valid()) RebuildPayload(msg);
+  }
+
+  /*! \brief rendezvous messages of an in-process peer are served on the caller's thread */
+  bool OnLocalControl(Message* msg) override {
+    if (msg->meta.control.cmd == Control::ADDR_REQUEST) {
+      OnSlotRequest(*msg);
+      return true;
+    }
+    if (msg->meta.control.cmd == Control::ADDR_RESOLVED) {
+      OnRegionMessage(*msg);
+      return true;
+    }
+    return false;
+  }
+
   int RecvMsg(Message* msg) override {
     for (;;) {
       const int n = TcpVan::RecvMsg(msg);

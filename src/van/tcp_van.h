@@ -32,6 +32,7 @@
 
 #include <algorithm>
 #include <array>
+#include <shared_mutex>
 #include <chrono>
 #include <deque>
 #include <map>
@@ -113,9 +114,18 @@ class TcpVan : public Van {
   void Start(int customer_id, bool standalone) override {
     InitTransport();
     Van::Start(customer_id, standalone);
+    if (handoff_ && AllowLocalHandoff() && !standalone) {
+      std::unique_lock<std::shared_mutex> lk(LocalVans().mu);
+      LocalVans().by_port[my_node_.port] = this;
+    }
   }
 
   void Stop() override {
+    {
+      std::unique_lock<std::shared_mutex> lk(LocalVans().mu);  // waits for hand-offs in flight
+      auto& m = LocalVans().by_port;
+      for (auto it = m.begin(); it != m.end();) it = it->second == this ? m.erase(it) : std::next(it);
+    }
     Van::Stop();
     CloseAll();
   }
@@ -173,6 +183,13 @@ class TcpVan : public Van {
     std::mutex mu;  // serialises whole frames on this socket
     /*! \brief same-host fast path: frames go through this ring, the socket carries doorbells */
     std::unique_ptr<ShmPipe> pipe;
+    /*! \brief the peer lives in this very process (joint roles, in-process clusters) */
+    bool same_process = false;
+    int port = 0;
+    /*! \brief hand-off decision for data messages: 0 untried, 1 direct, 2 wire only. A peer that
+     *  ever needed the wire keeps using it, so a handed-off message can never overtake one
+     *  that is still in the ring (or parked at the receiver). */
+    std::atomic<int> handoff_state{0};
   };
   /*! \brief transient MemRef::region marker, never on the wire (see SendMsg) */
   static constexpr int32_t kEncodedOnHost = 0x4000007f;
@@ -246,6 +263,9 @@ class TcpVan : public Van {
     }
     std::shared_ptr<Peer> peer(new Peer());
     peer->fd = fd;
+    peer->port = node.port;
+    peer->same_process = node.pid != 0 && node.pid == static_cast<int>(getpid()) &&
+                         node.hostname == my_node_.hostname;
     if (use_pipes_ && !my_node_.hostname.empty() && node.hostname == my_node_.hostname) {
       OfferPipe(peer.get(), node.id);
     }
@@ -296,6 +316,16 @@ class TcpVan : public Van {
         return -1;
       }
       peer = it->second;
+    }
+    const bool transport_ctrl = msg.meta.control.cmd == Control::ADDR_REQUEST ||
+                                msg.meta.control.cmd == Control::ADDR_RESOLVED;
+    if (peer->same_process && handoff_ && (msg.meta.control.empty() || transport_ctrl) &&
+        peer->handoff_state.load(std::memory_order_acquire) != 2) {
+      if (HandOff(peer.get(), msg)) {
+        peer->handoff_state.store(1, std::memory_order_release);
+        return 1 + static_cast<int>(msg.meta.data_size & 0x3fffffff);
+      }
+      peer->handoff_state.store(2, std::memory_order_release);
     }
     std::vector<char> meta_buf;
     PackMeta(msg.meta, &meta_buf);
@@ -755,6 +785,74 @@ class TcpVan : public Van {
     return ParseFrame(hdr, msg, [&](void* dst, size_t n) { return pipe->Read(dst, n); });
   }
 
+  /*!
+   * \brief where segment `i` (len bytes) of an arriving message goes: the buffer registered for
+   *        (sender, key), the pull's own destination (zero-copy pull), else fresh memory
+   */
+  SArray<char> SegmentDestination(const Meta& meta, uint32_t i, uint64_t len) {
+    SArray<char> seg;
+    if (i == 1 && meta.push && meta.request) {
+      std::lock_guard<std::mutex> lk(reg_mu_);
+      auto it = registered_.find(std::make_pair(meta.sender, meta.key));
+      if (it != registered_.end()) {
+        CHECK_GE(it->second.size(), len) << "registered buffer too small";
+        seg = it->second.segment(0, len);
+      }
+    }
+    // a pull response can land straight in the buffer the request named (meta.addr
+    // is this process's own pointer, echoed back by the server): zero-copy pull
+    if (i == 1 && direct_pull_ && !meta.request && !meta.push && meta.addr != 0 && len > 0 &&
+        meta.src_dev_type != GPU) {
+      const size_t esz = meta.data_type.size() > 1 ? ElemSize(meta.data_type[1]) : 1;
+      if (len <= static_cast<uint64_t>(meta.val_len) * esz) {
+        seg.reset(reinterpret_cast<char*>(meta.addr), len, [](char*) {});
+      }
+    }
+    if (seg.size() != len) seg = AllocSegment(len);
+    // the bytes (will) live in host memory of this node
+    seg.src_device_type_ = CPU;
+    seg.src_device_id_ = 0;
+    seg.dst_device_type_ = i == 1 && meta.dst_dev_type != UNK ? meta.dst_dev_type : CPU;
+    seg.dst_device_id_ = i == 1 && meta.dst_dev_id >= 0 ? meta.dst_dev_id : 0;
+    return seg;
+  }
+
+  /*!
+   * \brief in-process hand-off (sender side, any thread): build the message the peer van would
+   *        have parsed from our frame — segments copied into ITS destinations — and give it to
+   *        that van directly: no serialisation, no ring, no hop through its receive thread.
+   */
+  bool HandOff(Peer* peer, const Message& msg) {
+    std::shared_lock<std::shared_mutex> lk(LocalVans().mu);
+    auto it = LocalVans().by_port.find(peer->port);
+    if (it == LocalVans().by_port.end()) return false;
+    TcpVan* dst = it->second;
+    if (dst == this || !dst->AllowLocalHandoff()) return false;
+    Message m;
+    m.meta = msg.meta;
+    m.meta.sender = my_node_.id;
+    m.meta.recver = dst->my_node_.id;
+    if (m.meta.recver != msg.meta.recver) return false;  // stale registry entry
+    for (uint32_t i = 0; i < msg.data.size(); ++i) {
+      const SArray<char>& src = msg.data[i];
+      CHECK(src.size() == 0 || !src.on_gpu()) << "TcpVan cannot send device memory";
+      SArray<char> seg = dst->SegmentDestination(m.meta, i, src.size());
+      if (src.size() && seg.data() != src.data()) memcpy(seg.data(), src.data(), src.size());
+      m.data.push_back(seg);
+    }
+    if (!m.meta.control.empty()) {
+      // rendezvous traffic of a derived transport: it must stay ordered with the data
+      // messages it prepares (a pull request must not overtake its region announcement)
+      if (!dst->OnLocalControl(&m)) return false;
+      ++handoffs_;
+      return true;
+    }
+    dst->OnLocalDeliver(&m);
+    if (!dst->AcceptHandoff(&m)) return false;
+    ++handoffs_;
+    return true;
+  }
+
   /*! \brief everything after the FrameHeader; `take(dst, n)` pulls the next n stream bytes */
   template <typename TakeFn>
   int ParseFrame(const FrameHeader& hdr, Message* msg, TakeFn take) {
@@ -770,35 +868,8 @@ class TcpVan : public Van {
     size_t total = sizeof(hdr) + meta_buf.size();
     msg->data.clear();
     for (uint32_t i = 0; i < hdr.num_segments; ++i) {
-      SArray<char> seg;
-      if (i == 1 && msg->meta.push && msg->meta.request) {
-        std::lock_guard<std::mutex> lk(reg_mu_);
-        auto it = registered_.find(std::make_pair(msg->meta.sender, msg->meta.key));
-        if (it != registered_.end()) {
-          CHECK_GE(it->second.size(), seg_len[i]) << "registered buffer too small";
-          seg = it->second.segment(0, seg_len[i]);
-        }
-      }
-      // a pull response can land straight in the buffer the request named (meta.addr
-      // is this process's own pointer, echoed back by the server): zero-copy pull
-      if (i == 1 && direct_pull_ && !msg->meta.request && !msg->meta.push && msg->meta.addr != 0 &&
-          seg_len[i] > 0 && msg->meta.src_dev_type != GPU) {
-        const size_t esz = msg->meta.data_type.size() > 1 ? ElemSize(msg->meta.data_type[1]) : 1;
-        if (seg_len[i] <= static_cast<uint64_t>(msg->meta.val_len) * esz) {
-          seg.reset(reinterpret_cast<char*>(msg->meta.addr), seg_len[i], [](char*) {});
-        }
-      }
-      if (seg.size() != seg_len[i]) seg = AllocSegment(seg_len[i]);
+      SArray<char> seg = SegmentDestination(msg->meta, i, seg_len[i]);
       if (seg_len[i]) CHECK(take(seg.data(), seg_len[i]));
-      // the bytes now live in host memory of this node
-      seg.src_device_type_ = CPU;
-      seg.src_device_id_ = 0;
-      seg.dst_device_type_ = msg->meta.dst_dev_type == UNK ? CPU : msg->meta.dst_dev_type;
-      seg.dst_device_id_ = msg->meta.dst_dev_id < 0 ? 0 : msg->meta.dst_dev_id;
-      if (i != 1) {
-        seg.dst_device_type_ = CPU;
-        seg.dst_device_id_ = 0;
-      }
       msg->data.push_back(seg);
       total += seg_len[i];
     }
@@ -811,6 +882,12 @@ class TcpVan : public Van {
    *        receive thread at the top of every RecvMsg iteration; return true with a message
    *        whose payload has completed. HasDeferred() == true turns the idle wait into a poll.
    */
+  /*! \brief may this van take part in in-process hand-offs (both ends must agree)? */
+  virtual bool AllowLocalHandoff() const { return true; }
+  /*! \brief what the derived RecvMsg would have done to a message that was handed off */
+  virtual void OnLocalDeliver(Message* /*msg*/) {}
+  /*! \brief handle a transport-level control message (ADDR_*) handed off in-process; false = not mine */
+  virtual bool OnLocalControl(Message* /*msg*/) { return false; }
   virtual bool PollDeferred(Message* /*msg*/) { return false; }
   virtual bool HasDeferred() { return false; }
   /*! \brief enqueue a message for this van's own RecvMsg and wake it */
@@ -875,6 +952,24 @@ class TcpVan : public Van {
     __builtin_ia32_pause();
 #endif
   }
+  /*! \brief the TcpVans of this process, by listening port */
+  struct LocalVanTable {
+    std::shared_mutex mu;
+    std::map<int, TcpVan*> by_port;
+  };
+  static LocalVanTable& LocalVans() {
+    static LocalVanTable* t = new LocalVanTable();
+    return *t;
+  }
+  /*!
+   * \brief PS_LOCAL_HANDOFF=1: data messages between vans of one process skip the wire format and
+   *        the receiver's van thread. Off by default: it removes serialisation (-14 % per key on
+   *        the TCP van, joint 1 KB) but moves the receive work onto the sending thread, which
+   *        costs more than it saves once that thread also issues the copies (+10 % on the
+   *        one-sided shm van) — measured in the development container.
+   */
+  bool handoff_ = GetEnv("PS_LOCAL_HANDOFF", 0) != 0;
+  std::atomic<uint64_t> handoffs_{0};
   uint32_t spin_polls_ = 0;
   std::vector<int> pipe_fds_;                                  // inbound connections with a ring
   size_t pipe_cursor_ = 0;

@@ -59,6 +59,18 @@ def test_tutorial_example_runs(built_native_tree):
     assert rc == 0 and out.count("kv_hello PASSED") == 2, out[-3000:]
 
 
+@pytest.mark.parametrize("van", ["zmq", "shm"])
+def test_in_process_handoff(built_native_tree, van):
+    """PS_LOCAL_HANDOFF=1: vans of one process (joint role) pass data messages — and the one-sided
+    van's rendezvous messages — directly, bypassing wire format and receive thread"""
+    env = {"PS_LOCAL_HANDOFF": 1, "PS_VAN_TYPE": van, "JOINT": 1, "PS_VERBOSE": 0}
+    rc, out = launch(built_native_tree, 2, 2, "test_kv_app", env=env)
+    assert rc == 0 and out.count("test_kv_app PASSED") == 2, out[-3000:]
+    env.update({"NUM_KEY_PER_SERVER": 8, "TOTAL_DURATION": 50, "LOG_DURATION": 25})
+    rc, out = launch(built_native_tree, 2, 2, "test_ipc_benchmark", 65536, 50, env=env)
+    assert rc == 0 and "goodput" in out, out[-3000:]
+
+
 def test_kv_app_ipc_sockets(built_native_tree):
     rc, out = launch(built_native_tree, 2, 2, "test_kv_app", env={"DMLC_LOCAL": 1})
     assert rc == 0 and out.count("PASSED") == 2, out[-3000:]
