@@ -90,6 +90,23 @@ int main(int argc, char* argv[]) {
         std::atomic<int> fired{0};
         kv.Wait(kv.ZPull(zk, &zv, nullptr, 0, [&fired] { ++fired; }));
         if (fired.load() != 1 || std::fabs(zv[1] - scale * vals[1]) > 1e-3) ++bad;
+        // host one-sided van: a multi-key pull into exportable (shared) memory lands in place —
+        // every server writes its slice of the list straight into this buffer
+        Van* van = Postoffice::GetWorker(inst)->van();
+        if (van->GetType() == "shm") {
+          const size_t bytes = vals.size() * sizeof(float);
+          float* raw = static_cast<float*>(van->AllocExportable(bytes));
+          memset(raw, 0, bytes);
+          SArray<float> ev(raw, vals.size(), false);
+          kv.Wait(kv.ZPull(zk, &ev));
+          double e2 = 0;
+          for (size_t i = 0; i < vals.size(); ++i) e2 += std::fabs(raw[i] - scale * vals[i]);
+          if (e2 > 1e-3 * vals.size()) {
+            ++bad;
+            LL << "instance " << inst << " exportable multi-key pull mismatch " << e2;
+          }
+          van->FreeExportable(raw);
+        }
       });
     }
     for (auto& t : threads) t.join();
