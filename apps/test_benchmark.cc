@@ -7,6 +7,7 @@
  * loop, :489-553 main):
  *   argv:  [1] bytes per value (1024000)  [2] repeat (10, mode 0 only)
  *          [3] mode 0=PUSH_THEN_PULL 1=PUSH_PULL 2=PUSH_ONLY 3=PULL_ONLY
+ *              4=PUSHPULL_FUSED (new: KVWorker::ZPushPull, one request + one reply per key)
  *   env :  DMLC_* topology, NUM_KEY_PER_SERVER (40), LOG_DURATION (10),
  *          TOTAL_DURATION, BENCHMARK_NTHREAD, ENABLE_RECV_BUFFER,
  *          TEST_NUM_GPU_WORKER / TEST_NUM_GPU_SERVER (>0: values live in HBM and
@@ -40,7 +41,7 @@ using namespace ps;
 
 namespace {
 
-enum Mode { PUSH_THEN_PULL = 0, PUSH_PULL = 1, PUSH_ONLY = 2, PULL_ONLY = 3 };
+enum Mode { PUSH_THEN_PULL = 0, PUSH_PULL = 1, PUSH_ONLY = 2, PULL_ONLY = 3, PUSHPULL_FUSED = 4 };
 
 struct Options {
   int len = 1024000;
@@ -193,6 +194,15 @@ void ServerHandle(const KVMeta& req, const KVPairs<char>& data, KVServer<char>* 
     LOG(INFO) << "recved tensor! key=" << key << "\tlen: " << data.vals.size()
               << "\tsender: " << req.sender << "\taddr: " << static_cast<const void*>(data.vals.data());
   }
+  if (req.pull) {  // fused push-pull: the stored values are the reply, there is no ack
+    KVPairs<char> res;
+    {
+      std::lock_guard<std::mutex> lk(g_server.mu);
+      res = g_server.store[key];
+    }
+    server->Response(req, res);
+    return;
+  }
   server->Response(req);  // empty ack
 }
 
@@ -230,7 +240,9 @@ void StartServers(std::vector<KVServer<char>*>* servers) {
 // worker
 // ---------------------------------------------------------------------------
 void SteadyState(KVWorker<char>* kv, KeySet& ks, int total_keys, int tid) {
-  const char* name = opt.mode == PUSH_PULL ? "PUSH_PULL" : (opt.mode == PUSH_ONLY ? "PUSH_ONLY" : "PULL_ONLY");
+  const char* name = opt.mode == PUSH_PULL ? "PUSH_PULL"
+                     : opt.mode == PUSH_ONLY ? "PUSH_ONLY"
+                     : opt.mode == PULL_ONLY ? "PULL_ONLY" : "PUSHPULL_FUSED";
   LOG(INFO) << "========= " << name << " mode =========";
   LOG(INFO) << "========= msg_size=" << opt.len << " bytes =========";
   std::vector<int> in_flight;
@@ -245,6 +257,10 @@ void SteadyState(KVWorker<char>* kv, KeySet& ks, int total_keys, int tid) {
     {
       Van::CorkScope cork(van);  // released before the first Wait: the messages leave here
       for (int k = 0; k < total_keys; ++k) {
+        if (opt.mode == PUSHPULL_FUSED) {
+          in_flight.push_back(kv->ZPushPull(ks.keys[k], ks.vals[k], &ks.vals[k], &ks.lens[k]));
+          continue;
+        }
         if (opt.mode != PULL_ONLY) in_flight.push_back(kv->ZPush(ks.keys[k], ks.vals[k], ks.lens[k]));
         // the destination arrays must outlive the asynchronous pull (the reference
         // test passes pointers to loop locals, which only works by stack-slot luck)

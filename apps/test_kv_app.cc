@@ -42,7 +42,8 @@ int main(int argc, char* argv[]) {
             v.resize(k, 0.f);
             for (int j = 0; j < k; ++j) v[j] += data.vals[i * k + j];
           }
-        } else {
+        }
+        if (!req.push || req.pull) {  // a pull, or the reply half of a fused push-pull
           res.keys = data.keys;
           res.vals.resize(n * k);
           for (size_t i = 0; i < n; ++i) {
@@ -106,6 +107,26 @@ int main(int argc, char* argv[]) {
             LL << "instance " << inst << " exportable multi-key pull mismatch " << e2;
           }
           van->FreeExportable(raw);
+        }
+        // every worker has finished reading the sums above before anyone changes them again
+        if (inst == 0) Postoffice::GetWorker(0)->Barrier(0, kWorkerGroup);
+        else std::this_thread::sleep_for(std::chrono::milliseconds(300));
+        // fused push-pull: one more contribution from every worker, one message pair per server.
+        // Workers race, so a worker sees between 1 and W of the new contributions.
+        {
+          std::vector<float> after;
+          kv.Wait(kv.PushPull(keys, vals, &after));
+          const float W = static_cast<float>(Postoffice::GetWorker(inst)->num_workers());
+          int off_grid = 0;
+          for (size_t i = 0; i < vals.size(); ++i) {
+            if (vals[i] == 0.f) continue;
+            const float extra = after[i] / vals[i] - scale;  // how many new pushes it already contains
+            if (extra < 1.f - 1e-3f || extra > W + 1e-3f || std::fabs(extra - std::round(extra)) > 1e-3f) ++off_grid;
+          }
+          if (after.size() != vals.size() || off_grid) {
+            ++bad;
+            LL << "instance " << inst << " push-pull: " << off_grid << " values off the expected grid";
+          }
         }
       });
     }

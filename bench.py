@@ -57,6 +57,8 @@ def parse_args():
     ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "llama-1b", "tiny"])
     ap.add_argument("--ckpt-layers", type=int, default=-1)
     ap.add_argument("--attn-backend", default="auto", choices=["auto", "cudnn", "flash", "efficient", "math"])
+    ap.add_argument("--fused-pushpull", action="store_true",
+                    help="llama: one KVWorker::ZPushPull per parameter chunk instead of push + pull")
     ap.add_argument("--nvls-reduce", action="store_true",
                     help="with --symmetric: bf16 gradients staged in symmetric memory and summed inside "
                          "the NVSwitch by the update kernel (multimem.ld_reduce)")
@@ -314,7 +316,7 @@ def run_llama(args, dist: Dist) -> dict:
         kv = C.KVWorker(0, 0)
         opt = PSWorkerOptimizer(model.parameters(), kv, S, W, ctx.worker_rank,
                                 grad_wire=args.grad_wire, symmetric=use_symm,
-                                grad_buffer=gbuf).attach()
+                                grad_buffer=gbuf, fused_pushpull=args.fused_pushpull and gbuf is None).attach()
         opt.init_parameters(barrier=lambda: C.barrier(0, C.WORKER_GROUP, "worker"))
     dist.barrier()
     g = torch.Generator().manual_seed(1234 + dist.rank)

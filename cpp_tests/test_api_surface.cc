@@ -29,6 +29,8 @@ void KVWorkerSurface(KVWorker<float>* w) {
   ts = w->ZPush(zk, zv, zl, 7, cb);
   ts = w->ZPull(zk, &zv);
   ts = w->ZPull(zk, &zv, &zl, 7, cb);
+  ts = w->ZPushPull(zk, zv, &zv);                 // extension: fused push + pull
+  ts = w->PushPull(keys, vals, &vals);
   KVWorker<float>::Slicer slicer = [](const KVPairs<float>&, const std::vector<Range>&,
                                       KVWorker<float>::SlicedKVs*) {};
   w->set_slicer(slicer);

@@ -192,7 +192,7 @@ struct Meta {
       os << ", control={ " << control.DebugString() << " }";
     } else {
       os << ", app_id=" << app_id << ", customer_id=" << customer_id
-         << ", simple_app=" << simple_app << ", push=" << push << ", sid=" << sid;
+         << ", simple_app=" << simple_app << ", push=" << push << (pull ? "+pull" : "") << ", sid=" << sid;
     }
     if (head != kEmpty) os << ", head=" << head;
     if (control.empty() && !simple_app) os << ", key=" << key;
@@ -232,6 +232,15 @@ struct Meta {
   uint64_t addr = 0;
   /*! \brief number of value elements */
   int64_t val_len = 0;
+  /*!
+   * \brief fused push-pull: a push request that also asks for the (updated) values. The reply
+   *        is a pull response that lands at `pull_addr` (`pull_len` elements) / `pull_mem`;
+   *        there is no separate push ack. Halves the messages of a push + pull pair.
+   */
+  bool pull = false;
+  uint64_t pull_addr = 0;
+  int64_t pull_len = 0;
+  MemRef pull_mem;
   /*! \brief free 4-byte field for applications / transports */
   int option = 0;
   /*! \brief per-peer sequence id (ordered delivery) */
@@ -261,6 +270,8 @@ struct SendOpts {
   MemRef dest_mem;
   /*! \brief push with a symmetric `dest_mem`: local address the values are encoded into */
   void* stage = nullptr;
+  /*! \brief fused push-pull: caller-named destination of the reply (like `dest_mem` for a pull) */
+  MemRef pull_dest_mem;
 };
 
 /*! \brief MemRef::region value meaning "offset inside the job-wide symmetric buffer" */

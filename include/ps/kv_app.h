@@ -60,6 +60,15 @@ struct KVMeta {
   /*! \brief WireCodec the sender applied to the values, and its scale */
   int codec = 0;
   float scale = 1.0f;
+  /*!
+   * \brief fused push-pull (KVWorker::ZPushPull): `push` is true AND the worker wants the values
+   *        back. Answer with Response(req, result) — it is delivered as the pull reply to
+   *        `pull_addr` / `pull_mem` — and do not send a separate ack.
+   */
+  bool pull = false;
+  uint64_t pull_addr = 0;
+  int64_t pull_len = 0;
+  MemRef pull_mem;
 };
 
 namespace kv_detail {
@@ -166,6 +175,28 @@ class KVWorker : public SimpleApp {
     return Pull_(keys, vals, lens, cmd, cb, opts);
   }
 
+  /*!
+   * \brief fused push + pull: push `vals`, and receive the server's values for the same keys in
+   *        `*outs` with ONE request and ONE reply per server instead of two each. The server
+   *        handler sees `req.push && req.pull`. When the keys span several servers `*outs` must
+   *        mirror `vals` (same size, same layout); a request that goes to a single server may
+   *        pull a differently sized result (e.g. push fp32 gradients, receive bf16 parameters).
+   *        `opts.pull_dest_mem` names a destination the server already knows (symmetric buffer).
+   */
+  int ZPushPull(const SArray<Key>& keys, const SArray<Val>& vals, SArray<Val>* outs,
+                SArray<int>* lens = nullptr, int cmd = 0, const Callback& cb = nullptr,
+                const SendOpts& opts = SendOpts()) {
+    CHECK_NOTNULL(outs);
+    return Pull_(keys, outs, lens, cmd, cb, opts, &vals);
+  }
+  /*! \brief copying convenience form of ZPushPull */
+  int PushPull(const std::vector<Key>& keys, const std::vector<Val>& vals, std::vector<Val>* outs,
+               int cmd = 0, const Callback& cb = nullptr) {
+    CHECK_NOTNULL(outs)->resize(vals.size());
+    SArray<Val> v(vals);  // owned copy: the caller may drop `vals` right away
+    return Pull_(SArray<Key>(keys), outs, static_cast<std::vector<int>*>(nullptr), cmd, cb, SendOpts(), &v);
+  }
+
   using SlicedKVs = std::vector<std::pair<bool, KVPairs<Val>>>;
   /*! \brief cuts `send` by `ranges`; sliced[i].first==false means "nothing for server i" */
   using Slicer = std::function<void(const KVPairs<Val>& send, const std::vector<Range>& ranges,
@@ -178,7 +209,7 @@ class KVWorker : public SimpleApp {
  private:
   template <typename C, typename D>
   int Pull_(const SArray<Key>& keys, C* vals, D* lens, int cmd, const Callback& cb,
-            const SendOpts& opts = SendOpts());
+            const SendOpts& opts = SendOpts(), const SArray<Val>* push_vals = nullptr);
 
   void AddCallback(int timestamp, const Callback& cb) {
     if (!cb) return;
@@ -186,7 +217,8 @@ class KVWorker : public SimpleApp {
     callbacks_[timestamp] = cb;
   }
   void RunCallback(int timestamp);
-  void Send(int timestamp, bool push, int cmd, KVPairs<Val>& kvs, const SendOpts& opts = SendOpts());
+  void Send(int timestamp, bool push, int cmd, KVPairs<Val>& kvs, const SendOpts& opts = SendOpts(),
+            const SArray<Val>* pull_dest = nullptr);
   void Process(const Message& msg);
   void DefaultSlicer(const KVPairs<Val>& send, const std::vector<Range>& ranges,
                      SlicedKVs* sliced);
@@ -276,7 +308,8 @@ struct KVServerDefaultHandle {
     if (req_meta.push) {
       CHECK_EQ(n, req_data.vals.size());
       for (size_t i = 0; i < n; ++i) store[req_data.keys[i]] += req_data.vals[i];
-    } else {
+    }
+    if (!req_meta.push || req_meta.pull) {  // a pull, or the reply half of a fused push-pull
       res.keys = req_data.keys;
       res.vals.resize(n);
       for (size_t i = 0; i < n; ++i) res.vals[i] = store[req_data.keys[i]];
@@ -327,6 +360,10 @@ void KVServer<Val>::Process(const Message& msg) {
   meta.mem = msg.meta.mem;
   meta.codec = msg.meta.codec;
   meta.scale = msg.meta.scale;
+  meta.pull = msg.meta.pull;
+  meta.pull_addr = msg.meta.pull_addr;
+  meta.pull_len = msg.meta.pull_len;
+  meta.pull_mem = msg.meta.pull_mem;
   KVPairs<Val> data;
   const size_t n = msg.data.size();
   if (n) {
@@ -365,6 +402,14 @@ void KVServer<Val>::Response(const KVMeta& req, const KVPairs<Val>& res, const S
   msg.meta.val_len = req.val_len;
   msg.meta.option = req.option;
   msg.meta.mem = req.mem;
+  if (req.push && req.pull) {
+    // fused push-pull: the one reply is a pull response aimed at the worker's destination
+    CHECK(res.keys.size()) << "a push-pull request must be answered with the values";
+    msg.meta.push = false;
+    msg.meta.addr = req.pull_addr;
+    msg.meta.val_len = req.pull_len;
+    msg.meta.mem = req.pull_mem;
+  }
   msg.meta.codec = opts.codec;
   msg.meta.scale = opts.scale;
   msg.wait_event = opts.wait_event;
@@ -432,7 +477,7 @@ void KVWorker<Val>::DefaultSlicer(const KVPairs<Val>& send, const std::vector<Ra
 
 template <typename Val>
 void KVWorker<Val>::Send(int timestamp, bool push, int cmd, KVPairs<Val>& kvs,
-                         const SendOpts& opts) {
+                         const SendOpts& opts, const SArray<Val>* pull_dest) {
   SlicedKVs sliced;
   slicer_(kvs, postoffice_->GetServerKeyRanges(), &sliced);
 
@@ -458,6 +503,21 @@ void KVWorker<Val>::Send(int timestamp, bool push, int cmd, KVPairs<Val>& kvs,
     msg.meta.addr = reinterpret_cast<uint64_t>(part.vals.data());
     msg.meta.val_len = static_cast<int64_t>(part.vals.size());
     if (part.keys.size()) msg.meta.key = part.keys[0];
+    if (pull_dest) {
+      // fused push-pull: the reply lands in the slice of *pull_dest that mirrors this slice of
+      // vals — or in all of it when this server gets the whole request
+      CHECK(push);
+      size_t off = 0, cnt = pull_dest->size();
+      if (static_cast<size_t>(skipped) + 1 != sliced.size()) {
+        CHECK_EQ(pull_dest->size(), kvs.vals.size()) << "ZPushPull over several servers: *outs must mirror vals";
+        off = static_cast<size_t>(part.vals.data() - kvs.vals.data());
+        cnt = part.vals.size();
+      }
+      msg.meta.pull = true;
+      msg.meta.pull_addr = reinterpret_cast<uint64_t>(pull_dest->data() + off);
+      msg.meta.pull_len = static_cast<int64_t>(cnt);
+      if (opts.pull_dest_mem.valid()) msg.meta.pull_mem = opts.pull_dest_mem;
+    }
     msg.meta.codec = opts.codec;
     msg.meta.scale = opts.scale;
     msg.wait_event = opts.wait_event;
@@ -518,7 +578,7 @@ void KVWorker<Val>::RunCallback(int timestamp) {
 template <typename Val>
 template <typename C, typename D>
 int KVWorker<Val>::Pull_(const SArray<Key>& keys, C* vals, D* lens, int cmd, const Callback& cb,
-                         const SendOpts& opts) {
+                         const SendOpts& opts, const SArray<Val>* push_vals) {
   CHECK_NOTNULL(vals);
   const int ts = obj_->NewRequest(kServerGroup);
   AddCallback(ts, [this, ts, keys, vals, lens, cb]() mutable {
@@ -582,6 +642,15 @@ int KVWorker<Val>::Pull_(const SArray<Key>& keys, C* vals, D* lens, int cmd, con
 
   KVPairs<Val> kvs;
   kvs.keys = keys;
+  if (push_vals) {
+    // fused push-pull: the request carries the values to push, the completion above stitches
+    // the reply into *vals exactly as for a pull
+    kvs.vals = *push_vals;
+    if (lens && !lens->empty()) kvs.lens = kv_detail::ViewOf(lens);  // in: push lengths, out: pulled lengths
+    const SArray<Val> dest = kv_detail::ViewOf(vals);
+    Send(ts, true, cmd, kvs, opts, &dest);
+    return ts;
+  }
   kvs.vals = kv_detail::ViewOf(vals);
   if (lens && !lens->empty()) kvs.lens = kv_detail::ViewOf(lens);
   Send(ts, false, cmd, kvs, opts);

@@ -130,6 +130,33 @@ class PyKVWorker {
     }, opts);
   }
 
+  /*! \brief fused push + pull of one key: push `t`, receive the server's values in `out` */
+  int push_pull(uint64_t key, const torch::Tensor& t, torch::Tensor out, int cmd, int codec, float scale,
+                bool order_after_current_stream, int64_t pull_symm_offset) {
+    SArray<char> vals = ViewOf(t);
+    auto* dst = new SArray<char>(ViewOf(out));
+    auto* len = new SArray<int>(OneLen(dst->size()));
+    SendOpts opts;
+    opts.codec = codec;
+    opts.scale = scale;
+    if (pull_symm_offset >= 0) {
+      opts.pull_dest_mem.region = kSymmetricRegion;
+      opts.pull_dest_mem.offset = static_cast<uint64_t>(pull_symm_offset);
+      opts.pull_dest_mem.bytes = dst->size();
+    }
+    cudaEvent_t ev = nullptr;
+    if (t.is_cuda() && order_after_current_stream) {
+      ev = RecordOnCurrentStream(t.get_device());
+      opts.wait_event = ev;
+    }
+    py::gil_scoped_release nogil;
+    return kv_->ZPushPull(OneKey(key), vals, dst, len, cmd, [dst, len, ev]() {
+      delete dst;
+      delete len;
+      if (ev) cudaEventDestroy(ev);
+    }, opts);
+  }
+
   void wait(int ts) {
     py::gil_scoped_release nogil;
     kv_->Wait(ts);
@@ -273,7 +300,17 @@ class PyBenchServer {
           }
         }
         ++pushes_;
-        s->Response(m);
+        if (m.pull) {  // fused push-pull: reply with the stored values instead of an ack
+          KVPairs<char> res;
+          {
+            std::lock_guard<std::mutex> lk(mu_);
+            res = store_[key];
+          }
+          ++pulls_;
+          s->Response(m, res);
+        } else {
+          s->Response(m);
+        }
       } else {
         KVPairs<char> res;
         {
@@ -438,6 +475,9 @@ PYBIND11_MODULE(_C, m) {
            py::arg("symm_base") = 0)
       .def("pull", &PyKVWorker::pull, py::arg("key"), py::arg("tensor"), py::arg("cmd") = 0,
            py::arg("symm_offset") = -1)
+      .def("push_pull", &PyKVWorker::push_pull, py::arg("key"), py::arg("tensor"), py::arg("out"),
+           py::arg("cmd") = 0, py::arg("codec") = 0, py::arg("scale") = 1.0f,
+           py::arg("order_after_current_stream") = true, py::arg("pull_symm_offset") = -1)
       .def("wait", &PyKVWorker::wait)
       .def("wait_all", &PyKVWorker::wait_all)
       .def("push_pull_batch", &PyKVWorker::push_pull_batch, py::arg("keys"), py::arg("tensors"),

@@ -105,7 +105,8 @@ class PSWorkerOptimizer:
 
     def __init__(self, params, kv, num_servers: int, num_workers: int, worker_rank: int,
                  grad_wire: str = "fp8", chunk_elems: int = 32 << 20, app_barrier=None,
-                 symmetric: bool = False, grad_buffer: torch.Tensor | None = None):
+                 symmetric: bool = False, grad_buffer: torch.Tensor | None = None,
+                 fused_pushpull: bool = False):
         C = native()
         self._C = C
         self.kv = kv
@@ -125,6 +126,9 @@ class PSWorkerOptimizer:
         self.symm_off = [o * 2 for o in symmetric_layout(self.params)[0]] if symmetric else None
         # NVLS aggregation: gradients are staged (bf16) in this symmetric buffer and the server
         # reads the sum over all workers with multimem.ld_reduce (see setup_symmetric_grads)
+        # one request + one reply per chunk (KVWorker::ZPushPull) instead of push, ack, pull, reply
+        self.fused_pushpull = fused_pushpull
+        assert not (fused_pushpull and grad_buffer is not None), "push-pull stages no symmetric gradients"
         self.grad_buffer = grad_buffer
         if grad_buffer is not None:
             assert symmetric, "in-switch reduction uses the symmetric parameter layout"
@@ -209,6 +213,14 @@ class PSWorkerOptimizer:
         codec = self._codec(g)
         for c in self.chunks[i]:
             gs = gflat[c.start:c.stop]
+            if self.fused_pushpull:
+                self._pending.append(self.kv.push_pull(c.key, gs, pflat[c.start:c.stop], cmd=self._C.CMD_GRAD,
+                                                       codec=codec, scale=1.0, pull_symm_offset=self._symm(c)))
+                self.stats.pushes += 1
+                self.stats.pulls += 1
+                self.stats.push_bytes_wire += self._C.wire_bytes(codec, gs.numel() * gs.element_size())
+                self.stats.pull_bytes += (c.stop - c.start) * 2
+                continue
             if self.grad_buffer is not None:
                 self._pending.append(self.kv.push(c.key, gs, cmd=self._C.CMD_GRAD, codec=codec, scale=1.0,
                                                   symm_offset=self._symm(c),

@@ -14,6 +14,7 @@ enum MetaFlags : uint16_t {
   kFlagSimpleApp = 1u << 2,
   kFlagHasControl = 1u << 3,
   kFlagHasMem = 1u << 4,
+  kFlagPull = 1u << 5,
 };
 }  // namespace
 
@@ -76,6 +77,7 @@ void PackMeta(const Meta& m, std::vector<char>* out) {
   if (m.simple_app) flags |= kFlagSimpleApp;
   if (!m.control.empty()) flags |= kFlagHasControl;
   if (m.mem.valid()) flags |= kFlagHasMem;
+  if (m.pull) flags |= kFlagPull;
   w.Put<uint16_t>(flags);
   w.Put<int32_t>(m.head);
   w.Put<int32_t>(m.app_id);
@@ -96,6 +98,13 @@ void PackMeta(const Meta& m, std::vector<char>* out) {
     w.Put<uint64_t>(m.mem.offset);
     w.Put<uint64_t>(m.mem.bytes);
     w.Put<uint64_t>(m.mem.flag_seq);
+  }
+  if (flags & kFlagPull) {
+    w.Put<uint64_t>(m.pull_addr);
+    w.Put<int64_t>(m.pull_len);
+    w.Put<int32_t>(m.pull_mem.region);
+    w.Put<uint64_t>(m.pull_mem.offset);
+    w.Put<uint64_t>(m.pull_mem.bytes);
   }
   w.Put<int32_t>(m.codec);
   w.Put<float>(m.scale);
@@ -124,6 +133,7 @@ bool UnpackMeta(const char* buf, size_t len, Meta* m) {
   uint16_t flags = r.Get<uint16_t>();
   m->request = flags & kFlagRequest;
   m->push = flags & kFlagPush;
+  m->pull = flags & kFlagPull;
   m->simple_app = flags & kFlagSimpleApp;
   m->head = r.Get<int32_t>();
   m->app_id = r.Get<int32_t>();
@@ -145,6 +155,16 @@ bool UnpackMeta(const char* buf, size_t len, Meta* m) {
     m->mem.offset = r.Get<uint64_t>();
     m->mem.bytes = r.Get<uint64_t>();
     m->mem.flag_seq = r.Get<uint64_t>();
+  }
+  m->pull_addr = 0;
+  m->pull_len = 0;
+  m->pull_mem = MemRef();
+  if (flags & kFlagPull) {
+    m->pull_addr = r.Get<uint64_t>();
+    m->pull_len = r.Get<int64_t>();
+    m->pull_mem.region = r.Get<int32_t>();
+    m->pull_mem.offset = r.Get<uint64_t>();
+    m->pull_mem.bytes = r.Get<uint64_t>();
   }
   m->codec = r.Get<int32_t>();
   m->scale = r.Get<float>();

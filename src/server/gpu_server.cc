@@ -270,9 +270,21 @@ void GpuServer::Handle(const KVMeta& req, const KVPairs<char>& data, KVServer<ch
   if (req.push) {
     Shard* s = GetShard(key, ElemsOf(req));
     if (req.cmd == kCmdInitBf16 || req.cmd == kCmdInitF32) {
+      CHECK(!req.pull) << "initial values are pushed, not push-pulled";
       HandleInit(s, req, data);
     } else {
       HandleGrad(s, req, data);
+      if (req.pull) {
+        // fused push-pull: the same message is also this worker's pull of the round's result;
+        // it is answered once, by the pull reply (HandleGrad sent no ack)
+        KVMeta pull = req;
+        pull.push = false;
+        pull.pull = false;
+        pull.addr = req.pull_addr;
+        pull.val_len = req.pull_len;
+        pull.mem = req.pull_mem;
+        HandlePull(s, pull, data);
+      }
       MaybeRunRound(key, s);
     }
   } else {
@@ -341,6 +353,7 @@ void GpuServer::HandleGrad(Shard* s, const KVMeta& req, const KVPairs<char>& dat
     CHECK_NE(fmt, (int)PS_GRAD_MC_BF16) << "in-switch reduction is a synchronous-round feature";
     s->grad_format = fmt;
     ApplyOnArrival(s, rank);
+    if (req.pull) return;  // answered by the pull half
     if (be_->on_device()) {
       // ack only after the update has consumed the slot (descriptor gated on this stream)
       SendOpts after_update;
@@ -350,6 +363,7 @@ void GpuServer::HandleGrad(Shard* s, const KVMeta& req, const KVPairs<char>& dat
       return;
     }
   }
+  if (req.pull) return;  // fused push-pull: the pull reply is the only answer
   // the payload already sits in its slot: the push is complete for the worker
   server_->Response(req);
 }

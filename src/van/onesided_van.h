@@ -135,6 +135,14 @@ class OneSidedVan : public TcpVan {
       if (msg.meta.codec == kCodecPlaced) return SendPlacedResponse(msg);
       return SendPullResponse(msg);
     }
+    if (msg.meta.request && msg.meta.push && msg.meta.pull && !msg.meta.pull_mem.valid() &&
+        msg.meta.pull_addr != 0) {
+      // fused push-pull whose values travel two-sided (e.g. a gradient tensor that cannot be
+      // exported): the reply can still be written in place if its destination can
+      const size_t esz = msg.meta.data_type.size() > 1 ? DataTypeSize(msg.meta.data_type[1]) : 1;
+      DescribeDestination(msg.meta.recver, msg.meta.pull_addr,
+                          static_cast<uint64_t>(msg.meta.pull_len) * esz, &msg.meta.pull_mem);
+    }
     // nothing was placed one-sidedly: do not let the receiver rebuild a payload
     if (!msg.meta.request) msg.meta.mem = MemRef();
     if (!msg.meta.request && msg.meta.codec == kCodecPlaced) {
@@ -274,6 +282,12 @@ class OneSidedVan : public TcpVan {
     desc.meta.mem.region = slot.region;
     desc.meta.mem.offset = slot.offset;
     desc.meta.mem.bytes = wire;
+    if (msg.meta.pull && !msg.meta.pull_mem.valid() && msg.meta.pull_addr != 0) {
+      // fused push-pull: tell the server where the reply goes, as a pull request would
+      const size_t esz = msg.meta.data_type.size() > 1 ? DataTypeSize(msg.meta.data_type[1]) : 1;
+      DescribeDestination(recver, msg.meta.pull_addr, static_cast<uint64_t>(msg.meta.pull_len) * esz,
+                          &desc.meta.pull_mem);
+    }
     desc.data = msg.data;
     desc.data[1] = vals.segment(0, 0);  // payload already placed; keep the segment slot
     desc.meta.data_size = msg.meta.data_size - static_cast<int64_t>(vals.size());
@@ -378,19 +392,23 @@ class OneSidedVan : public TcpVan {
 
   // -- pull ----------------------------------------------------------------------
 
-  /*! \brief name the pull destination so the server can write into it */
-  void AttachPullDestination(Message* msg) {
+  /*!
+   * \brief describe [addr, addr+bytes) of this process so that `recver` can write into it:
+   *        export the containing allocation (announcing it to that peer once) and fill `out`.
+   *        False if the memory cannot be exported (the reply then travels two-sided).
+   */
+  bool DescribeDestination(int recver, uint64_t addr, uint64_t bytes, MemRef* out) {
     RegionDesc d;
-    if (!domain_->Export(reinterpret_cast<void*>(msg->meta.addr), &d)) return;  // two-sided
+    if (!domain_->Export(reinterpret_cast<void*>(addr), &d)) return false;
     const int32_t id = RegionIdFor(&d);
     bool need_announce = false;
     {
       std::lock_guard<std::mutex> lk(rv_mu_);
-      need_announce = announced_.insert(std::make_pair(msg->meta.recver, id)).second;
+      need_announce = announced_.insert(std::make_pair(recver, id)).second;
     }
     if (need_announce) {
       Message ann;
-      ann.meta.recver = msg->meta.recver;
+      ann.meta.recver = recver;
       ann.meta.request = true;
       ann.meta.control.cmd = Control::ADDR_RESOLVED;
       ann.meta.head = kAnnounceRegion;
@@ -398,10 +416,17 @@ class OneSidedVan : public TcpVan {
       ann.meta.timestamp = GetTimestamp();
       CHECK_GT(TcpVan::SendMsg(ann), 0);
     }
+    out->region = id;
+    out->offset = addr - d.base;
+    out->bytes = bytes;
+    return true;
+  }
+
+  /*! \brief name the pull destination so the server can write into it */
+  void AttachPullDestination(Message* msg) {
     const size_t esz = msg->meta.data_type.size() > 1 ? DataTypeSize(msg->meta.data_type[1]) : 1;
-    msg->meta.mem.region = id;
-    msg->meta.mem.offset = msg->meta.addr - d.base;
-    msg->meta.mem.bytes = static_cast<uint64_t>(msg->meta.val_len) * esz;
+    DescribeDestination(msg->meta.recver, msg->meta.addr,
+                        static_cast<uint64_t>(msg->meta.val_len) * esz, &msg->meta.mem);
   }
 
   int SendPullResponse(Message& msg) {

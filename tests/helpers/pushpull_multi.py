@@ -19,6 +19,7 @@ from pslite_b200.parallel.launch import init_ps  # noqa: E402
 def main():
     van, length, kps, rounds = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     topo = sys.argv[5] if len(sys.argv) > 5 else "split"
+    fused = os.environ.get("PSLITE_TEST_PUSHPULL", "0") == "1"  # one ZPushPull per key instead of ZPush + ZPull
     rank = int(os.environ["RANK"])
     dist.init_process_group("gloo")
     C = pslite_b200.native()
@@ -39,7 +40,12 @@ def main():
     dist.barrier()
     if ctx.is_worker:
         for _ in range(rounds):
-            kv.wait_all(kv.push_pull_batch(keys, vals, order_after_current_stream=False))
+            if fused:
+                ts = [kv.push_pull(keys[k], vals[k], vals[k], order_after_current_stream=False) for k in range(total)]
+                for t in ts:
+                    kv.wait(t)
+            else:
+                kv.wait_all(kv.push_pull_batch(keys, vals, order_after_current_stream=False))
         # every pull must have returned the value stored by the key's first pusher
         for k in range(total):
             lo, hi = int(vals[k].min()), int(vals[k].max())

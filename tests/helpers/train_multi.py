@@ -24,6 +24,7 @@ def main():
     nvls_reduce = len(sys.argv) > 4 and sys.argv[4] == "nvls"
     # asynchronous SGD: every push is its own optimizer step, workers never wait for each other
     async_sgd = len(sys.argv) > 4 and sys.argv[4] == "async"
+    fused_pp = os.environ.get("PSLITE_TEST_PUSHPULL", "0") == "1"  # KVWorker::ZPushPull per chunk
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
     use_cuda = torch.cuda.is_available()
@@ -86,7 +87,7 @@ def main():
         kv = C.KVWorker(0, 0)
         opt = PSWorkerOptimizer(model.parameters(), kv, S, W, ctx.worker_rank, grad_wire=wire,
                                 chunk_elems=1 << 14, symmetric=symmetric,
-                                grad_buffer=gbuf if nvls_reduce else None).attach()
+                                grad_buffer=gbuf if nvls_reduce else None, fused_pushpull=fused_pp).attach()
         opt.init_parameters(barrier=lambda: C.barrier(0, C.WORKER_GROUP, "worker"))
         g = torch.Generator(device=dev).manual_seed(100 + ctx.worker_rank)
         tok = torch.randint(0, cfg.vocab_size, (2, 65), device=dev, generator=g)

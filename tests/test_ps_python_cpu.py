@@ -85,7 +85,7 @@ def test_trainer_logic_on_cpu(native):
 
 @pytest.mark.parametrize("nproc,topo,length,async_copies", [
     (8, "split", 4096, "1"), (8, "split", 1 << 20, "1"), (4, "joint", 65536, "1"), (4, "split", 4096, "0")])
-def test_bench_loop_many_peers(native, nproc, topo, length, async_copies, coalesce="0"):
+def test_bench_loop_many_peers(native, nproc, topo, length, async_copies, coalesce="0", fused="0"):
     """bench.py's push_pull_batch loop under torchrun with several workers AND servers, over the
     one-sided van with *asynchronous* copies (PS_SHM_ASYNC: copies complete later, as kernels
     on a CUDA stream do). Descriptors for different peers then share completion batches — the
@@ -93,7 +93,7 @@ def test_bench_loop_many_peers(native, nproc, topo, length, async_copies, coales
     helper = os.path.join(HERE, "helpers", "pushpull_multi.py")
     env = dict(os.environ)
     env.update({"PSLITE_NO_AUTOBUILD": "1", "PS_SHM_ASYNC": async_copies, "OMP_NUM_THREADS": "1",
-                "PS_COALESCE_LAUNCHES": coalesce})
+                "PS_COALESCE_LAUNCHES": coalesce, "PSLITE_TEST_PUSHPULL": fused})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()), helper, "shm", str(length), "10",
            "10", topo]
@@ -105,3 +105,8 @@ def test_bench_loop_many_peers(native, nproc, topo, length, async_copies, coales
 def test_bench_loop_with_launch_coalescing(native):
     """the same loop with every push_pull_batch call and every handler batch corked"""
     test_bench_loop_many_peers(native, 8, "split", 65536, "1", coalesce="1")
+
+
+def test_bench_loop_with_fused_push_pull(native):
+    """one KVWorker::ZPushPull per key (request carries the push, the single reply the pulled values)"""
+    test_bench_loop_many_peers(native, 8, "split", 65536, "1", fused="1")

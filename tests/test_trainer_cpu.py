@@ -82,3 +82,10 @@ def test_launch_coalescing_keeps_results(native):
     one batch and the held messages leave in order afterwards; training must be unaffected"""
     out = _run(4, "joint", "fp8", 5, PSLITE_TEST_EXPORTABLE_PARAMS=1, PS_SHM_ASYNC=1, PS_COALESCE_LAUNCHES=1)
     assert "engine=host" in out
+
+
+@pytest.mark.timeout(300)
+def test_trainer_with_fused_push_pull(native):
+    """PSWorkerOptimizer(fused_pushpull=True): one message pair per parameter chunk; same losses"""
+    out = _run(4, "joint", "fp8", 5, PSLITE_TEST_EXPORTABLE_PARAMS=1, PS_SHM_ASYNC=1, PSLITE_TEST_PUSHPULL=1)
+    assert "engine=host" in out and "fused=0 " not in out
