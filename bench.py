@@ -58,7 +58,8 @@ def parse_args():
     ap.add_argument("--ckpt-layers", type=int, default=-1)
     ap.add_argument("--attn-backend", default="auto", choices=["auto", "cudnn", "flash", "efficient", "math"])
     ap.add_argument("--fused-pushpull", action="store_true",
-                    help="llama: one KVWorker::ZPushPull per parameter chunk instead of push + pull")
+                    help="llama: one KVWorker::ZPushPull per parameter chunk instead of push + pull; "
+                         "pushpull: additionally time the fused operation (reported as fused_pushpull)")
     ap.add_argument("--nvls-reduce", action="store_true",
                     help="with --symmetric: bf16 gradients staged in symmetric memory and summed inside "
                          "the NVSwitch by the update kernel (multimem.ld_reduce)")
@@ -206,6 +207,21 @@ def run_pushpull(args, dist: Dist) -> dict:
                "h2d_bytes_per_step": int(args.len) * total_keys * W,
                "d2h_bytes_per_step": int(args.len) * total_keys * W, "steps": e2e_steps}
 
+    fused = None
+    if args.fused_pushpull:
+        # same bytes per key, but ONE KVWorker::ZPushPull instead of ZPush + ZPull (extension over the
+        # reference API; reported next to the headline, never instead of it)
+        def fused_round():
+            ts = [kv.push_pull(keys[k], vals[k], vals[k], order_after_current_stream=False)
+                  for k in range(total_keys)]
+            for t in ts:
+                kv.wait(t)
+        if ctx.is_worker:
+            for _ in range(max(3, args.warmup)):
+                fused_round()
+        ms_f, _ = timed(fused_round, args.steps)
+        fused = {"value": payload * args.steps / (ms_f * 1e-3) / 1e9, "unit": "GB/s", "ms_per_step": ms_f / args.steps}
+
     sweep = []
     for sz in [int(x) for x in args.sweep.split(",") if x]:
         nk = max(1, min(args.keys_per_server, (512 << 20) // max(sz, 1))) * S
@@ -236,6 +252,7 @@ def run_pushpull(args, dist: Dist) -> dict:
     ctx.shutdown()
     return {
         "sweep": sweep,
+        "fused_pushpull": fused,
         "metric": METRIC_NAME["pushpull"], "value": value, "unit": "GB/s",
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "uint8 payload (bit-exact copy)", "data": "synthetic",

@@ -24,6 +24,8 @@ echo "== 4. bench N=1"
 timeout 400 python bench.py --steps 20 --warmup 3 2>gpurun_out/v_b1.err | tee gpurun_out/v_bench1.json | tail -c 900
 echo "== 4. bench N=1 with launch coalescing"
 PS_COALESCE_LAUNCHES=1 timeout 400 python bench.py --steps 20 --warmup 3 --no-e2e 2>gpurun_out/v_b1c.err | tee gpurun_out/v_bench1_coalesce.json | tail -c 600
+echo "== 4. bench N=1 with the fused push-pull operation reported as well"
+timeout 400 python bench.py --steps 20 --warmup 3 --no-e2e --fused-pushpull 2>gpurun_out/v_b1f.err | tee gpurun_out/v_bench1_fused.json | tail -c 700
 echo "== 4. bench N=2"
 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29931 \
   bench.py --gpus 2 --steps 20 --warmup 3 2>gpurun_out/v_b2.err | tee gpurun_out/v_bench2.json | tail -c 900
