@@ -83,11 +83,12 @@ def test_kv_app_lockless_queue_and_direct_dispatch(built_native_tree):
 
 def test_kv_app_survives_message_drops_with_resend(built_native_tree):
     env = {"PS_RESEND": 1, "PS_RESEND_TIMEOUT": 100, "PS_DROP_MSG": 10}
-    rc, out = launch(built_native_tree, 1, 1, "test_kv_app", 200, 2, 3, env=env, timeout=180)
+    # 40 pushes + the rest: ~100 messages, so "no message was dropped" has probability < 1e-4
+    rc, out = launch(built_native_tree, 1, 1, "test_kv_app", 200, 2, 40, env=env, timeout=180)
     assert "test_kv_app PASSED" in out, out[-3000:]   # every push/pull survived 10 % loss
     assert "Drop message" in out                      # the injector really fired
     if rc != 0:  # teardown with messages still being retransmitted is best-effort: retry once
-        rc, out = launch(built_native_tree, 1, 1, "test_kv_app", 200, 2, 3, env=env, timeout=180)
+        rc, out = launch(built_native_tree, 1, 1, "test_kv_app", 200, 2, 40, env=env, timeout=180)
     assert rc == 0, out[-3000:]
 
 
