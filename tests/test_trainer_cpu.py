@@ -89,3 +89,16 @@ def test_trainer_with_fused_push_pull(native):
     """PSWorkerOptimizer(fused_pushpull=True): one message pair per parameter chunk; same losses"""
     out = _run(4, "joint", "fp8", 5, PSLITE_TEST_EXPORTABLE_PARAMS=1, PS_SHM_ASYNC=1, PSLITE_TEST_PUSHPULL=1)
     assert "engine=host" in out and "fused=0 " not in out
+
+
+@pytest.mark.timeout(300)
+def test_llama_example_script_runs(native):
+    """examples/train_llama_ps.py (the tutorial as a script) on the host engine, two ranks"""
+    env = dict(os.environ)
+    env.update({"PSLITE_NO_AUTOBUILD": "1", "OMP_NUM_THREADS": "1", "CUDA_VISIBLE_DEVICES": ""})
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", str(free_port()),
+           os.path.join(ROOT, "examples", "train_llama_ps.py"), "--model", "tiny", "--steps", "4"]
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=280, cwd=ROOT)
+    out = p.stdout + p.stderr
+    assert p.returncode == 0 and "step 3: loss" in out and "host engine" in out, out[-3000:]
