@@ -84,7 +84,7 @@ def test_trainer_logic_on_cpu(native):
 
 
 @pytest.mark.parametrize("nproc,topo,length,async_copies", [
-    (8, "split", 4096, "1"), (8, "split", 1 << 20, "1"), (4, "joint", 65536, "1"), (4, "split", 4096, "0")])
+    (8, "split", 4096, "1"), (4, "split", 1 << 20, "1"), (4, "joint", 65536, "1"), (4, "split", 4096, "0")])
 def test_bench_loop_many_peers(native, nproc, topo, length, async_copies, coalesce="0", fused="0"):
     """bench.py's push_pull_batch loop under torchrun with several workers AND servers, over the
     one-sided van with *asynchronous* copies (PS_SHM_ASYNC: copies complete later, as kernels
@@ -97,7 +97,7 @@ def test_bench_loop_many_peers(native, nproc, topo, length, async_copies, coales
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()), helper, "shm", str(length), "10",
            "10", topo]
-    for attempt in range(2):  # the hang this guards against was probabilistic: run it a few times
+    for attempt in range(2 if nproc == 8 and coalesce == "0" and fused == "0" else 1):  # the hang was probabilistic
         p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=150)
         assert p.returncode == 0 and "PASS" in p.stdout, (p.stdout + p.stderr)[-3000:]
 
