@@ -43,6 +43,14 @@ def main():
         server = C.GpuServer(0, num_workers=W, optimizer="adamw", lr=3e-3 / (W if async_sgd else 1), beta1=0.9,
                              beta2=0.95, eps=1e-8, weight_decay=0.0, grad_scale=1.0 if async_sgd else 1.0 / W,
                              fuse_pull=True, async_updates=async_sgd)
+    # checkpoint / resume: every server keeps its shards in <dir>/server<rank>.ckpt
+    ckpt_dir = os.environ.get("PSLITE_CKPT_DIR", "")
+    ckpt = os.path.join(ckpt_dir, f"server{ctx.server_rank}.ckpt") if ckpt_dir and server is not None else ""
+    resumed = False
+    if ckpt and os.path.exists(ckpt):
+        resumed = server.load(ckpt)  # before any worker initialises: loaded shards win over init pushes
+        assert resumed, f"cannot load {ckpt}"
+    dist.barrier(group=gloo)
     ok = True
     checksum = torch.zeros(1, dtype=torch.float64)
     losses = []
@@ -101,6 +109,10 @@ def main():
         with torch.no_grad():
             checksum[0] = sum(float(p.double().sum()) for p in model.parameters())
         ok = losses[-1] < losses[0]
+    if ckpt:
+        dist.barrier(group=gloo)  # every worker has finished its last step
+        assert server.save(ckpt)
+        print(f"rank {rank}: checkpoint {'resumed and ' if resumed else ''}saved to {ckpt}", flush=True)
     # all workers pulled the same parameters
     sums = [torch.zeros(1, dtype=torch.float64) for _ in range(world)]
     dist.all_gather(sums, checksum, group=gloo)

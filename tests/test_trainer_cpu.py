@@ -102,3 +102,24 @@ def test_llama_example_script_runs(native):
     p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=280, cwd=ROOT)
     out = p.stdout + p.stderr
     assert p.returncode == 0 and "step 3: loss" in out and "host engine" in out, out[-3000:]
+
+
+@pytest.mark.timeout(400)
+def test_checkpoint_resume_across_jobs(native, tmp_path):
+    """job 1 trains 4 steps and every server saves its shards; job 2 loads them before the workers
+    initialise and continues exactly where job 1 stopped (fp32 masters, Adam moments, step count)"""
+    import re
+
+    first = _run(2, "joint", "bf16", 4, PSLITE_CKPT_DIR=str(tmp_path))
+    assert (tmp_path / "server0.ckpt").exists() and (tmp_path / "server1.ckpt").exists()
+    second = _run(2, "joint", "bf16", 2, PSLITE_CKPT_DIR=str(tmp_path))
+    assert "checkpoint resumed and saved" in second
+    uninterrupted = _run(2, "joint", "bf16", 6)
+
+    def losses(out):
+        m = re.search(r"rank 0: engine=\w+ losses \[(.*?)\]\.\.\[(.*?)\]", out)
+        return [float(x.strip("' ")) for x in (m.group(1) + "," + m.group(2)).split(",")]
+
+    # steps 5 and 6 of the uninterrupted run == steps 1 and 2 of the resumed job
+    assert losses(second)[:2] == losses(uninterrupted)[-2:], (losses(second), losses(uninterrupted))
+    assert losses(first)[0] == losses(uninterrupted)[0]
