@@ -162,11 +162,28 @@ TEST(wire_roundtrip_data_meta) {
   CHECK_EQ(r.mem.region, 4); CHECK_EQ(r.mem.bytes, (uint64_t)1234567);
   CHECK_EQ(r.codec, 3); CHECK_EQ(r.scale, 0.125f);
   CHECK_EQ((int)r.dst_dev_type, (int)GPU); CHECK_EQ(r.dst_dev_id, 6);
+  CHECK(!r.pull);
+  CHECK(!r.pull_mem.valid());
   // truncated buffers are rejected, never mis-parsed
   for (size_t cut : {(size_t)0, (size_t)3, buf.size() / 2, buf.size() - 1}) {
     Meta bad;
     CHECK(!wire::UnpackMeta(buf.data(), cut, &bad));
   }
+  // fused push-pull: the optional block travels only when the flag is set
+  const size_t plain = buf.size();
+  m.pull = true;
+  m.pull_addr = 0x7f00deadb000ULL;
+  m.pull_len = (int64_t)7 << 30;
+  m.pull_mem.region = 0x40000000; m.pull_mem.offset = 1 << 20; m.pull_mem.bytes = 99;
+  wire::PackMeta(m, &buf);
+  CHECK_GT(buf.size(), plain);
+  Meta p;
+  CHECK(wire::UnpackMeta(buf.data(), buf.size(), &p));
+  CHECK(p.push); CHECK(p.pull);
+  CHECK_EQ(p.pull_addr, 0x7f00deadb000ULL); CHECK_EQ(p.pull_len, (int64_t)7 << 30);
+  CHECK_EQ(p.pull_mem.region, 0x40000000); CHECK_EQ(p.pull_mem.offset, (uint64_t)1 << 20);
+  CHECK_EQ(p.pull_mem.bytes, (uint64_t)99);
+  CHECK_EQ(p.mem.region, 4);  // the push slot reference is independent of it
 }
 
 TEST(wire_roundtrip_control_nodes) {
