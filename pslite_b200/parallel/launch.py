@@ -100,9 +100,17 @@ def init_ps(topology: str = "joint", van: str | None = None, extra_env: dict | N
     env = {
         "DMLC_NUM_WORKER": nw, "DMLC_NUM_SERVER": ns,
         "DMLC_PS_ROOT_URI": host if host not in ("localhost",) else "127.0.0.1",
-        "DMLC_PS_ROOT_PORT": port, "DMLC_NODE_HOST": "127.0.0.1",
+        "DMLC_PS_ROOT_PORT": port,
         "PS_VAN_TYPE": van, "PS_CUDA_DEVICE": local_rank, "DMLC_ROLE": role,
     }
+    # one node: everything on loopback (the container's hostname may not resolve). Several nodes
+    # (torchrun --nnodes > 1): every process advertises its own address — DMLC_NODE_HOST if the
+    # user set it, else the van picks the first non-loopback interface (or DMLC_INTERFACE).
+    single_node = int(os.environ.get("LOCAL_WORLD_SIZE", str(world))) >= world
+    if single_node:
+        env["DMLC_NODE_HOST"] = "127.0.0.1"
+    elif os.environ.get("DMLC_NODE_HOST"):
+        env["DMLC_NODE_HOST"] = os.environ["DMLC_NODE_HOST"]
     if extra_env:
         env.update(extra_env)
     sched = None
