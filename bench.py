@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "llama-1b", "tiny"])
     ap.add_argument("--ckpt-layers", type=int, default=-1)
     ap.add_argument("--attn-backend", default="auto", choices=["auto", "cudnn", "flash", "efficient", "math"])
+    ap.add_argument("--lazy-wait", action="store_true",
+                    help="llama: step() does not wait; every module waits for its own parameters before its "
+                         "forward (hides the step tail)")
     ap.add_argument("--fused-pushpull", action="store_true",
                     help="llama: one KVWorker::ZPushPull per parameter chunk instead of push + pull; "
                          "pushpull: additionally time the fused operation (reported as fused_pushpull)")
@@ -335,6 +338,8 @@ def run_llama(args, dist: Dist) -> dict:
                                 grad_wire=args.grad_wire, symmetric=use_symm,
                                 grad_buffer=gbuf, fused_pushpull=args.fused_pushpull and gbuf is None).attach()
         opt.init_parameters(barrier=lambda: C.barrier(0, C.WORKER_GROUP, "worker"))
+        if args.lazy_wait:
+            opt.enable_lazy_wait(model)
     dist.barrier()
     g = torch.Generator().manual_seed(1234 + dist.rank)
     host_tok = torch.randint(0, cfg.vocab_size, (B, T + 1), generator=g).pin_memory()
@@ -360,6 +365,7 @@ def run_llama(args, dist: Dist) -> dict:
         if ctx.is_worker:
             for _ in range(steps):
                 fn()
+            opt.wait_all()  # lazy waits: the last step's parameters must have arrived inside the timed region
         torch.cuda.synchronize()
         e1.record()
         e1.synchronize()

@@ -119,6 +119,8 @@ class PSWorkerOptimizer:
         self.grad_wire = grad_wire
         self.stats = PSTrainerStats()
         self._pending: list[int] = []
+        self._pending_by_param: dict[int, list[int]] = {}
+        self._lazy = False
         self._hooks = []
         self._barrier = app_barrier
         self.accumulate = False  # True on non-final micro-batches: keep grads local
@@ -205,7 +207,45 @@ class PSWorkerOptimizer:
             self._push_pull(i, g)
         return hook
 
+    def enable_lazy_wait(self, model: torch.nn.Module):
+        """Hide the tail of a step: `step()` stops waiting and every module instead waits, right
+        before its forward, for the chunks of *its own* parameters. The pulls of late layers then
+        overlap the next forward of the early ones (gradients are pushed last-layer-first, so the
+        first layers' parameters — needed first — are also the last to come back). Call
+        `wait_all()` before reading parameters outside a forward pass (evaluation, checksums)."""
+        index = {id(p): i for i, p in enumerate(self.params)}
+        for module in model.modules():
+            mine = [index[id(p)] for p in module.parameters(recurse=False) if id(p) in index]
+            if mine:
+                self._hooks.append(module.register_forward_pre_hook(
+                    lambda _m, _inp, mine=tuple(mine): self._wait_params(mine)))
+        self._lazy = True
+        return self
+
+    def _wait_params(self, indices):
+        for i in indices:
+            pend = self._pending_by_param.pop(i, None)
+            if pend:
+                for ts in pend:
+                    self.kv.wait(ts)
+
+    def wait_all(self):
+        """Block until nothing is in flight (also what a non-lazy step() does)."""
+        self._wait_params(list(self._pending_by_param.keys()))
+        pend, self._pending = self._pending, []
+        for ts in pend:
+            self.kv.wait(ts)
+
     def _push_pull(self, i: int, g: torch.Tensor):
+        if self._lazy:
+            mark = len(self._pending)
+            self._push_pull_now(i, g)
+            self._pending_by_param.setdefault(i, []).extend(self._pending[mark:])
+            del self._pending[mark:]
+            return
+        self._push_pull_now(i, g)
+
+    def _push_pull_now(self, i: int, g: torch.Tensor):
         if not g.is_contiguous():
             g = g.contiguous()
         gflat = g.view(-1)
@@ -235,7 +275,10 @@ class PSWorkerOptimizer:
 
     # -- optimizer-like surface ---------------------------------------------------------
     def step(self):
-        """Block until every parameter chunk of this round has been rewritten by its server."""
+        """Block until every parameter chunk of this round has been rewritten by its server
+        (with enable_lazy_wait(): return at once, the modules wait for their own parameters)."""
+        if self._lazy:
+            return
         pend, self._pending = self._pending, []
         for ts in pend:
             self.kv.wait(ts)

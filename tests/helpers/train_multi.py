@@ -97,6 +97,8 @@ def main():
                                 chunk_elems=1 << 14, symmetric=symmetric,
                                 grad_buffer=gbuf if nvls_reduce else None, fused_pushpull=fused_pp).attach()
         opt.init_parameters(barrier=lambda: C.barrier(0, C.WORKER_GROUP, "worker"))
+        if os.environ.get("PSLITE_TEST_LAZY", "0") == "1":
+            opt.enable_lazy_wait(model)  # step() returns at once; modules wait for their own parameters
         g = torch.Generator(device=dev).manual_seed(100 + ctx.worker_rank)
         tok = torch.randint(0, cfg.vocab_size, (2, 65), device=dev, generator=g)
         for _ in range(steps):
@@ -104,6 +106,7 @@ def main():
             loss.backward()
             opt.step()
             losses.append(loss.item())
+        opt.wait_all()
         if use_cuda:
             torch.cuda.synchronize()
         with torch.no_grad():

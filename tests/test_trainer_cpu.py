@@ -123,3 +123,18 @@ def test_checkpoint_resume_across_jobs(native, tmp_path):
     # steps 5 and 6 of the uninterrupted run == steps 1 and 2 of the resumed job
     assert losses(second)[:2] == losses(uninterrupted)[-2:], (losses(second), losses(uninterrupted))
     assert losses(first)[0] == losses(uninterrupted)[0]
+
+
+@pytest.mark.timeout(300)
+def test_lazy_per_module_waits_keep_the_loss_curve(native):
+    """enable_lazy_wait(): step() returns at once and each module waits for its own parameters right
+    before its forward; the numbers must not change"""
+    import re
+
+    def curve(out):
+        m = re.search(r"rank 0: engine=\w+ losses \[(.*?)\]\.\.\[(.*?)\]", out)
+        return m.group(1) + m.group(2)
+
+    eager = _run(2, "joint", "fp8", 5, PSLITE_TEST_EXPORTABLE_PARAMS=1)
+    lazy = _run(2, "joint", "fp8", 5, PSLITE_TEST_EXPORTABLE_PARAMS=1, PSLITE_TEST_LAZY=1)
+    assert curve(eager) == curve(lazy)
