@@ -30,7 +30,7 @@ echo "== 4. bench N=2"
 timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29931 \
   bench.py --gpus 2 --steps 20 --warmup 3 2>gpurun_out/v_b2.err | tee gpurun_out/v_bench2.json | tail -c 900
 echo "== 4. llama-1b N=2 joint, unicast / multicast / in-switch reduce"
-for extra in "" "--symmetric" "--symmetric --nvls-reduce --grad-wire bf16"; do
+for extra in "" "--lazy-wait" "--fused-pushpull" "--symmetric" "--symmetric --nvls-reduce --grad-wire bf16"; do
   timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29932 \
     bench.py --metric llama --model llama-1b --seq-len 4096 --gpus 2 --steps 4 --warmup 2 --no-e2e $extra 2>>gpurun_out/v_l2.err \
     | python -c "
