@@ -363,6 +363,7 @@ class PyGpuServer {
     impl_.reset();
   }
   void set_lr(float lr) { impl_->SetLearningRate(lr); }
+  float lr() { return impl_->learning_rate(); }
   void set_symmetric(uint64_t mc_ptr, const std::vector<uint64_t>& peer_ptrs, uint64_t bytes) {
     std::vector<void*> peers;
     for (uint64_t p : peer_ptrs) peers.push_back(reinterpret_cast<void*>(p));
@@ -443,6 +444,7 @@ PYBIND11_MODULE(_C, m) {
   m.attr("CMD_INIT_F32") = static_cast<int>(kCmdInitF32);
   m.attr("GRAD_F32") = static_cast<int>(PS_GRAD_F32);
   m.attr("GRAD_BF16") = static_cast<int>(PS_GRAD_BF16);
+  m.attr("CMD_SET_LR") = static_cast<int>(kCmdSetLr);
   m.attr("GRAD_FP8BLOCK") = static_cast<int>(PS_GRAD_FP8BLOCK);
   m.attr("GRAD_MC_BF16") = static_cast<int>(PS_GRAD_MC_BF16);
 
@@ -504,6 +506,7 @@ PYBIND11_MODULE(_C, m) {
            py::arg("fuse_pull") = true, py::arg("raw_grad") = "bf16", py::arg("max_ctas") = 0,
            py::arg("async_updates") = false)
       .def("set_lr", &PyGpuServer::set_lr)
+      .def("lr", &PyGpuServer::lr)
       .def("set_symmetric", &PyGpuServer::set_symmetric, py::arg("mc_ptr"), py::arg("peer_ptrs"),
            py::arg("bytes"))
       .def("num_multicast_fanouts", &PyGpuServer::num_multicast_fanouts)

@@ -283,6 +283,23 @@ class PSWorkerOptimizer:
         for ts in pend:
             self.kv.wait(ts)
 
+    def set_lr(self, lr: float):
+        """Learning-rate schedules: tell every server its new rate (they may live in other processes).
+        Every worker may call it with the same value; only worker 0 sends. Takes effect with the next
+        update a server runs, so call it between `step()` and the next backward."""
+        if self.rank != 0:
+            return
+        value = torch.tensor([lr], dtype=torch.float32)
+        seen = set()
+        ts = []
+        for per in self.chunks:
+            for c in per:
+                if c.server not in seen:
+                    seen.add(c.server)
+                    ts.append(self.kv.push(c.key, value, cmd=self._C.CMD_SET_LR))
+        for t in ts:
+            self.kv.wait(t)
+
     def zero_grad(self, set_to_none: bool = True):
         for p in self.params:
             p.grad = None

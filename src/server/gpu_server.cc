@@ -192,6 +192,11 @@ void GpuServer::SetLearningRate(float lr) {
   cfg_.opt.lr = lr;
 }
 
+float GpuServer::learning_rate() {
+  std::lock_guard<std::mutex> lk(mu_);
+  return cfg_.opt.lr;
+}
+
 void GpuServer::SetSymmetricParams(void* mc_base, const std::vector<void*>& peer_bases,
                                    size_t bytes) {
   std::lock_guard<std::mutex> lk(mu_);
@@ -267,6 +272,16 @@ void GpuServer::Handle(const KVMeta& req, const KVPairs<char>& data, KVServer<ch
   be_->Bind();
   std::lock_guard<std::mutex> lk(mu_);
   const Key key = data.keys.size() ? data.keys[0] : req.key;
+  if (req.push && req.cmd == kCmdSetLr) {
+    // remote control for learning-rate schedules: servers may live in other processes
+    CHECK_EQ(data.vals.size(), sizeof(float)) << "CMD_SET_LR carries exactly one fp32 value";
+    float lr = 0.f;
+    if (data.vals.on_gpu()) be_->Download(&lr, data.vals.data(), sizeof(float));
+    else memcpy(&lr, data.vals.data(), sizeof(float));
+    cfg_.opt.lr = lr;
+    server_->Response(req);
+    return;
+  }
   if (req.push) {
     Shard* s = GetShard(key, ElemsOf(req));
     if (req.cmd == kCmdInitBf16 || req.cmd == kCmdInitF32) {

@@ -45,6 +45,7 @@ enum GpuServerCmd : int {
   kCmdGrad = 0,        // push: gradient contribution for the current round
   kCmdInitBf16 = 101,  // push: initial parameter values, bf16 (first writer wins)
   kCmdInitF32 = 102,   // push: initial parameter values, fp32
+  kCmdSetLr = 103,     // push: one fp32 value = new learning rate of this server (any key it owns)
 };
 
 struct GpuServerConfig {
@@ -82,6 +83,7 @@ class GpuServer {
   ~GpuServer();
 
   void SetLearningRate(float lr);
+  float learning_rate();
   /*!
    * \brief NVLS pull fan-out. Every worker keeps its parameters in a buffer that is
    *        symmetric across the job (same layout at the same offset) and bound to one

@@ -101,7 +101,12 @@ def main():
             opt.enable_lazy_wait(model)  # step() returns at once; modules wait for their own parameters
         g = torch.Generator(device=dev).manual_seed(100 + ctx.worker_rank)
         tok = torch.randint(0, cfg.vocab_size, (2, 65), device=dev, generator=g)
-        for _ in range(steps):
+        freeze_after = int(os.environ.get("PSLITE_TEST_FREEZE_AFTER", "0"))  # learning rate -> 0 from there
+        for it in range(steps):
+            if freeze_after and it == freeze_after:
+                opt.wait_all()
+                opt.set_lr(0.0)
+                C.barrier(0, C.WORKER_GROUP, "worker")  # every server has the new rate before anyone pushes
             loss = model(tok[:, :-1], tok[:, 1:])
             loss.backward()
             opt.step()
@@ -112,6 +117,8 @@ def main():
         with torch.no_grad():
             checksum[0] = sum(float(p.double().sum()) for p in model.parameters())
         ok = losses[-1] < losses[0]
+        if freeze_after:
+            print(f"rank {rank}: all losses {['%.4f' % x for x in losses]}", flush=True)
     if ckpt:
         dist.barrier(group=gloo)  # every worker has finished its last step
         assert server.save(ckpt)

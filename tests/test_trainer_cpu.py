@@ -138,3 +138,17 @@ def test_lazy_per_module_waits_keep_the_loss_curve(native):
     eager = _run(2, "joint", "fp8", 5, PSLITE_TEST_EXPORTABLE_PARAMS=1)
     lazy = _run(2, "joint", "fp8", 5, PSLITE_TEST_EXPORTABLE_PARAMS=1, PSLITE_TEST_LAZY=1)
     assert curve(eager) == curve(lazy)
+
+
+@pytest.mark.timeout(300)
+def test_remote_learning_rate_control(native):
+    """opt.set_lr() reaches servers in other processes (CMD_SET_LR): with the rate set to 0 after
+    step 3 the parameters — and, on a fixed batch, the loss — stop changing"""
+    import re
+
+    out = _run(4, "split", "bf16", 7, PSLITE_TEST_FREEZE_AFTER=3)
+    m = re.search(r"rank 0: all losses \[(.*?)\]", out)
+    losses = [float(x.strip("' ")) for x in m.group(1).split(",")]
+    assert losses[2] < losses[0]                    # it was learning
+    # the update of step 3's gradients already ran with rate 0: from step 4 on the loss is frozen
+    assert losses[4] == losses[5] == losses[6], losses
