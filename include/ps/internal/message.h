@@ -272,6 +272,8 @@ struct SendOpts {
   void* stage = nullptr;
   /*! \brief fused push-pull: caller-named destination of the reply (like `dest_mem` for a pull) */
   MemRef pull_dest_mem;
+  /*! \brief value of Meta::option / KVMeta::option (application-defined flags) */
+  int option = 0;
 };
 
 /*! \brief MemRef::region value meaning "offset inside the job-wide symmetric buffer" */

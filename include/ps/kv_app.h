@@ -520,6 +520,7 @@ void KVWorker<Val>::Send(int timestamp, bool push, int cmd, KVPairs<Val>& kvs,
     }
     msg.meta.codec = opts.codec;
     msg.meta.scale = opts.scale;
+    msg.meta.option = opts.option;
     msg.wait_event = opts.wait_event;
     if (opts.dest_mem.valid()) {
       msg.meta.mem = opts.dest_mem;

@@ -87,11 +87,12 @@ class PyKVWorker {
   }
 
   int push(uint64_t key, const torch::Tensor& t, int cmd, int codec, float scale,
-           bool order_after_current_stream, int64_t symm_offset, uint64_t symm_base) {
+           bool order_after_current_stream, int64_t symm_offset, uint64_t symm_base, int option) {
     SArray<char> vals = ViewOf(t);
     SendOpts opts;
     opts.codec = codec;
     opts.scale = scale;
+    opts.option = option;
     if (symm_offset >= 0) {
       // stage the encoded gradient in this worker's symmetric buffer; the server reads the
       // sum of all workers' copies through the multicast address (multimem.ld_reduce)
@@ -445,6 +446,7 @@ PYBIND11_MODULE(_C, m) {
   m.attr("GRAD_F32") = static_cast<int>(PS_GRAD_F32);
   m.attr("GRAD_BF16") = static_cast<int>(PS_GRAD_BF16);
   m.attr("CMD_SET_LR") = static_cast<int>(kCmdSetLr);
+  m.attr("INIT_NO_WEIGHT_DECAY") = static_cast<int>(kInitNoWeightDecay);
   m.attr("GRAD_FP8BLOCK") = static_cast<int>(PS_GRAD_FP8BLOCK);
   m.attr("GRAD_MC_BF16") = static_cast<int>(PS_GRAD_MC_BF16);
 
@@ -474,7 +476,7 @@ PYBIND11_MODULE(_C, m) {
       .def("push", &PyKVWorker::push, py::arg("key"), py::arg("tensor"), py::arg("cmd") = 0,
            py::arg("codec") = 0, py::arg("scale") = 1.0f,
            py::arg("order_after_current_stream") = true, py::arg("symm_offset") = -1,
-           py::arg("symm_base") = 0)
+           py::arg("symm_base") = 0, py::arg("option") = 0)
       .def("pull", &PyKVWorker::pull, py::arg("key"), py::arg("tensor"), py::arg("cmd") = 0,
            py::arg("symm_offset") = -1)
       .def("push_pull", &PyKVWorker::push_pull, py::arg("key"), py::arg("tensor"), py::arg("out"),

@@ -106,7 +106,7 @@ class PSWorkerOptimizer:
     def __init__(self, params, kv, num_servers: int, num_workers: int, worker_rank: int,
                  grad_wire: str = "fp8", chunk_elems: int = 32 << 20, app_barrier=None,
                  symmetric: bool = False, grad_buffer: torch.Tensor | None = None,
-                 fused_pushpull: bool = False):
+                 fused_pushpull: bool = False, no_decay_1d: bool = True):
         C = native()
         self._C = C
         self.kv = kv
@@ -130,6 +130,9 @@ class PSWorkerOptimizer:
         # reads the sum over all workers with multimem.ld_reduce (see setup_symmetric_grads)
         # one request + one reply per chunk (KVWorker::ZPushPull) instead of push, ack, pull, reply
         self.fused_pushpull = fused_pushpull
+        # the usual rule: norm gains / biases (1-D tensors) are not weight-decayed; the server
+        # learns it per shard from the option bits of the initial push
+        self.no_decay_1d = no_decay_1d
         assert not (fused_pushpull and grad_buffer is not None), "push-pull stages no symmetric gradients"
         self.grad_buffer = grad_buffer
         if grad_buffer is not None:
@@ -170,8 +173,9 @@ class PSWorkerOptimizer:
             for p, per in zip(self.params, self.chunks):
                 flat = p.data.view(-1)
                 cmd = C.CMD_INIT_F32 if p.dtype == torch.float32 else C.CMD_INIT_BF16
+                opt_bits = C.INIT_NO_WEIGHT_DECAY if (self.no_decay_1d and p.dim() <= 1) else 0
                 for c in per:
-                    ts.append(self.kv.push(c.key, flat[c.start:c.stop], cmd=cmd))
+                    ts.append(self.kv.push(c.key, flat[c.start:c.stop], cmd=cmd, option=opt_bits))
             for t in ts:
                 self.kv.wait(t)
         (barrier or self._barrier or (lambda: None))()

@@ -325,6 +325,7 @@ void GpuServer::HandleInit(Shard* s, const KVMeta& req, const KVPairs<char>& dat
       be_->Free(staged);
     }
     s->initialized = true;
+    s->no_weight_decay = (req.option & kInitNoWeightDecay) != 0;
   }
   server_->Response(req);
 }
@@ -415,6 +416,7 @@ void GpuServer::ApplyOnArrival(Shard* s, int rank) {
   a.m = s->m;
   a.v = s->v;
   ps_opt_params o = cfg_.opt;
+  if (s->no_weight_decay) o.weight_decay = 0.f;
   ++s->step;
   if (o.optimizer == PS_OPT_ADAMW) {
     o.bias_corr1 = 1.f - std::pow(o.beta1, static_cast<float>(s->step));
@@ -472,6 +474,7 @@ void GpuServer::MaybeRunRound(Key key, Shard* s) {
     ++mcast_;
   }
   ps_opt_params o = cfg_.opt;
+  if (s->no_weight_decay) o.weight_decay = 0.f;
   ++s->step;
   if (o.optimizer == PS_OPT_ADAMW) {
     o.bias_corr1 = 1.f - std::pow(o.beta1, static_cast<float>(s->step));
@@ -588,7 +591,7 @@ bool GpuServer::SaveCheckpoint(const std::string& path) {
   std::vector<float> buf;
   for (auto& kv : shards_) {
     const Shard& s = kv.second;
-    CkptEntry e{kv.first, s.n, s.step, s.initialized ? 1 : 0};
+    CkptEntry e{kv.first, s.n, s.step, (s.initialized ? 1 : 0) | (s.no_weight_decay ? 2 : 0)};
     ok = ok && fwrite(&e, sizeof(e), 1, f) == 1;
     buf.resize(s.n);
     for (float* src : {s.master, s.m, s.v}) {
@@ -614,7 +617,8 @@ bool GpuServer::LoadCheckpoint(const std::string& path) {
     if (!ok) break;
     Shard* s = GetShard(e.key, e.n);
     s->step = e.step;
-    s->initialized = e.initialized != 0;
+    s->initialized = (e.initialized & 1) != 0;
+    s->no_weight_decay = (e.initialized & 2) != 0;
     buf.resize(e.n);
     for (float* dst : {s->master, s->m, s->v}) {
       ok = ok && fread(buf.data(), 4, e.n, f) == e.n;

@@ -40,6 +40,11 @@
 
 namespace ps {
 
+/*! \brief KVMeta::option bits of an initial-value push (per-shard optimizer settings) */
+enum GpuServerInitOption : int {
+  kInitNoWeightDecay = 1,  // norms, biases, embeddings: exclude this shard from weight decay
+};
+
 /*! \brief `cmd` values understood by GpuServer */
 enum GpuServerCmd : int {
   kCmdGrad = 0,        // push: gradient contribution for the current round
@@ -133,6 +138,7 @@ class GpuServer {
     float* m = nullptr;
     float* v = nullptr;
     bool initialized = false;
+    bool no_weight_decay = false;
     int step = 0;
     int grad_format = PS_GRAD_BF16;
     std::vector<const void*> slots;      // per worker rank: landing slot of this round

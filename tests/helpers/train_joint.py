@@ -44,7 +44,10 @@ def main():
             keep.append(buf)
     # local reference: fp32 master copy + torch AdamW, bf16 compute weights
     masters = [p.detach().float().clone().requires_grad_(True) for p in ref.parameters()]
-    ropt = torch.optim.AdamW(masters, lr=lr, betas=(0.9, 0.95), eps=1e-8, weight_decay=wd)
+    # same rule as PSWorkerOptimizer(no_decay_1d=True): norm gains are not decayed
+    ropt = torch.optim.AdamW([{"params": [m for m in masters if m.dim() > 1], "weight_decay": wd},
+                              {"params": [m for m in masters if m.dim() <= 1], "weight_decay": 0.0}],
+                             lr=lr, betas=(0.9, 0.95), eps=1e-8)
     kv = C.KVWorker(0, 0)
     opt = PSWorkerOptimizer(model.parameters(), kv, 1, 1, 0, grad_wire=wire, chunk_elems=1 << 14).attach()
     opt.init_parameters(barrier=lambda: None)
