@@ -102,7 +102,13 @@ def main():
         g = torch.Generator(device=dev).manual_seed(100 + ctx.worker_rank)
         tok = torch.randint(0, cfg.vocab_size, (2, 65), device=dev, generator=g)
         freeze_after = int(os.environ.get("PSLITE_TEST_FREEZE_AFTER", "0"))  # learning rate -> 0 from there
+        ckpt_at = int(os.environ.get("PSLITE_CKPT_AT", "0"))  # joint topology: also save after that many steps
         for it in range(steps):
+            if ckpt_at and it == ckpt_at and ckpt:
+                opt.wait_all()
+                dist.barrier(group=gloo)   # every worker has finished step `ckpt_at`
+                assert server.save(ckpt)
+                dist.barrier(group=gloo)
             if freeze_after and it == freeze_after:
                 opt.wait_all()
                 opt.set_lr(0.0)
@@ -117,9 +123,9 @@ def main():
         with torch.no_grad():
             checksum[0] = sum(float(p.double().sum()) for p in model.parameters())
         ok = losses[-1] < losses[0]
-        if freeze_after:
+        if freeze_after or ckpt:
             print(f"rank {rank}: all losses {['%.4f' % x for x in losses]}", flush=True)
-    if ckpt:
+    if ckpt and not int(os.environ.get("PSLITE_CKPT_AT", "0")):  # (a mid-run save is kept as it is)
         dist.barrier(group=gloo)  # every worker has finished its last step
         assert server.save(ckpt)
         print(f"rank {rank}: checkpoint {'resumed and ' if resumed else ''}saved to {ckpt}", flush=True)

@@ -27,6 +27,30 @@ def _run(nproc, topo, wire, steps, **env_extra):
     return out
 
 
+_cache = {}
+
+
+def _run_cached(nproc, topo, wire, steps, **env_extra):
+    key = (nproc, topo, wire, steps, tuple(sorted(env_extra.items())))
+    if key not in _cache:
+        _cache[key] = _run(nproc, topo, wire, steps, **env_extra)
+    return _cache[key]
+
+
+def _curve(out):
+    import re
+
+    m = re.search(r"rank 0: engine=\w+ losses \[(.*?)\]\.\.\[(.*?)\]", out)
+    return m.group(1) + " .. " + m.group(2)
+
+
+def _all_losses(out):
+    import re
+
+    m = re.search(r"rank 0: all losses \[(.*?)\]", out)
+    return [float(x.strip("' ")) for x in m.group(1).split(",")]
+
+
 @pytest.mark.timeout(300)
 def test_two_sided_fallback_with_fp8_wire(native):
     """plain torch tensors cannot be exported: gradients are fp8-encoded on the host and travel
@@ -35,18 +59,38 @@ def test_two_sided_fallback_with_fp8_wire(native):
     assert "engine=host" in out and "fused=0 " in out
 
 
+PLAIN = dict(PSLITE_TEST_EXPORTABLE_PARAMS=1, PS_SHM_ASYNC=1)
+
+
 @pytest.mark.timeout(300)
 def test_zero_copy_fused_fanout_many_peers_async(native):
     """parameters in shared memory, copies completing asynchronously (as on a CUDA stream):
     every update writes the new bf16 parameters straight into all 4 workers' buffers"""
-    out = _run(4, "joint", "fp8", 5, PSLITE_TEST_EXPORTABLE_PARAMS=1, PS_SHM_ASYNC=1)
+    out = _run_cached(4, "joint", "fp8", 5, **PLAIN)
     assert "engine=host" in out and "fused=0 " not in out
 
 
 @pytest.mark.timeout(300)
-def test_split_topology_bf16_wire(native):
-    """dedicated server processes (2 workers + 2 servers), bf16 gradient wire"""
-    _run(4, "split", "bf16", 5, PSLITE_TEST_EXPORTABLE_PARAMS=1)
+def test_all_transport_options_keep_the_loss_curve(native):
+    """launch coalescing (corked handlers and batch calls), fused push-pull (one message pair per
+    chunk) and lazy per-module waits instead of a blocking step(), all at once: the numbers
+    must be those of the plain run"""
+    plain = _run_cached(4, "joint", "fp8", 5, **PLAIN)
+    tuned = _run(4, "joint", "fp8", 5, PS_COALESCE_LAUNCHES=1, PSLITE_TEST_PUSHPULL=1, PSLITE_TEST_LAZY=1, **PLAIN)
+    assert _curve(plain) == _curve(tuned)
+    assert "fused=0 " not in tuned
+
+
+@pytest.mark.timeout(300)
+def test_split_topology_and_remote_learning_rate_control(native):
+    """dedicated server processes (2 workers + 2 servers, bf16 wire); opt.set_lr() reaches them
+    (CMD_SET_LR): with the rate set to 0 after step 3 the parameters — and, on a fixed batch,
+    the loss — stop changing"""
+    out = _run(4, "split", "bf16", 7, PSLITE_TEST_FREEZE_AFTER=3, PSLITE_TEST_EXPORTABLE_PARAMS=1)
+    losses = _all_losses(out)
+    assert losses[2] < losses[0]                    # it was learning
+    # the update of step 3's gradients already ran with rate 0: from step 4 on the loss is frozen
+    assert losses[4] == losses[5] == losses[6], losses
 
 
 @pytest.mark.timeout(300)
@@ -77,21 +121,6 @@ def test_asynchronous_sgd(native):
 
 
 @pytest.mark.timeout(300)
-def test_launch_coalescing_keeps_results(native):
-    """PS_COALESCE_LAUNCHES=1: handlers and batch calls run corked — their copies are issued as
-    one batch and the held messages leave in order afterwards; training must be unaffected"""
-    out = _run(4, "joint", "fp8", 5, PSLITE_TEST_EXPORTABLE_PARAMS=1, PS_SHM_ASYNC=1, PS_COALESCE_LAUNCHES=1)
-    assert "engine=host" in out
-
-
-@pytest.mark.timeout(300)
-def test_trainer_with_fused_push_pull(native):
-    """PSWorkerOptimizer(fused_pushpull=True): one message pair per parameter chunk; same losses"""
-    out = _run(4, "joint", "fp8", 5, PSLITE_TEST_EXPORTABLE_PARAMS=1, PS_SHM_ASYNC=1, PSLITE_TEST_PUSHPULL=1)
-    assert "engine=host" in out and "fused=0 " not in out
-
-
-@pytest.mark.timeout(300)
 def test_llama_example_script_runs(native):
     """examples/train_llama_ps.py (the tutorial as a script) on the host engine, two ranks"""
     env = dict(os.environ)
@@ -106,49 +135,11 @@ def test_llama_example_script_runs(native):
 
 @pytest.mark.timeout(400)
 def test_checkpoint_resume_across_jobs(native, tmp_path):
-    """job 1 trains 4 steps and every server saves its shards; job 2 loads them before the workers
-    initialise and continues exactly where job 1 stopped (fp32 masters, Adam moments, step count)"""
-    import re
-
-    first = _run(2, "joint", "bf16", 4, PSLITE_CKPT_DIR=str(tmp_path))
+    """job 1 trains 6 steps and every server saves its shards after step 4; job 2 loads them before
+    its workers initialise and reproduces steps 5 and 6 of job 1 exactly (fp32 masters, Adam
+    moments, step count all restored)"""
+    first = _run(2, "joint", "bf16", 6, PSLITE_CKPT_DIR=str(tmp_path), PSLITE_CKPT_AT=4)
     assert (tmp_path / "server0.ckpt").exists() and (tmp_path / "server1.ckpt").exists()
     second = _run(2, "joint", "bf16", 2, PSLITE_CKPT_DIR=str(tmp_path))
     assert "checkpoint resumed and saved" in second
-    uninterrupted = _run(2, "joint", "bf16", 6)
-
-    def losses(out):
-        m = re.search(r"rank 0: engine=\w+ losses \[(.*?)\]\.\.\[(.*?)\]", out)
-        return [float(x.strip("' ")) for x in (m.group(1) + "," + m.group(2)).split(",")]
-
-    # steps 5 and 6 of the uninterrupted run == steps 1 and 2 of the resumed job
-    assert losses(second)[:2] == losses(uninterrupted)[-2:], (losses(second), losses(uninterrupted))
-    assert losses(first)[0] == losses(uninterrupted)[0]
-
-
-@pytest.mark.timeout(300)
-def test_lazy_per_module_waits_keep_the_loss_curve(native):
-    """enable_lazy_wait(): step() returns at once and each module waits for its own parameters right
-    before its forward; the numbers must not change"""
-    import re
-
-    def curve(out):
-        m = re.search(r"rank 0: engine=\w+ losses \[(.*?)\]\.\.\[(.*?)\]", out)
-        return m.group(1) + m.group(2)
-
-    eager = _run(2, "joint", "fp8", 5, PSLITE_TEST_EXPORTABLE_PARAMS=1)
-    lazy = _run(2, "joint", "fp8", 5, PSLITE_TEST_EXPORTABLE_PARAMS=1, PSLITE_TEST_LAZY=1)
-    assert curve(eager) == curve(lazy)
-
-
-@pytest.mark.timeout(300)
-def test_remote_learning_rate_control(native):
-    """opt.set_lr() reaches servers in other processes (CMD_SET_LR): with the rate set to 0 after
-    step 3 the parameters — and, on a fixed batch, the loss — stop changing"""
-    import re
-
-    out = _run(4, "split", "bf16", 7, PSLITE_TEST_FREEZE_AFTER=3)
-    m = re.search(r"rank 0: all losses \[(.*?)\]", out)
-    losses = [float(x.strip("' ")) for x in m.group(1).split(",")]
-    assert losses[2] < losses[0]                    # it was learning
-    # the update of step 3's gradients already ran with rate 0: from step 4 on the loss is frozen
-    assert losses[4] == losses[5] == losses[6], losses
+    assert _all_losses(second)[:2] == _all_losses(first)[4:6], (_all_losses(second), _all_losses(first))
