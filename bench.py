@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--keys-per-server", type=int, default=40)
     ap.add_argument("--topology", default=None, choices=[None, "joint", "split"])
     ap.add_argument("--van", default=None)
+    ap.add_argument("--device", default="cuda", choices=["cuda", "cpu"],
+                    help="cpu: self-check of this script's control flow on a GPU-less box (shm van, host "
+                         "engine, host clock); its numbers are not benchmark results")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--sweep", default="", help="comma-separated extra message sizes (bytes) to report")
     # llama
@@ -115,6 +118,64 @@ class Dist:
             dist.destroy_process_group()
 
 
+class Gpu:
+    """The few torch.cuda calls of this script behind one switch, so that `--device cpu` walks the
+    same code (different MemDomain, different kernel implementations, host clock)."""
+
+    def __init__(self, args, local_rank: int):
+        import torch
+
+        self.cuda = args.device == "cuda"
+        self.dev = torch.device("cuda", local_rank) if self.cuda else torch.device("cpu")
+        if self.cuda:
+            torch.cuda.set_device(local_rank)
+
+    def sync(self):
+        if self.cuda:
+            import torch
+
+            torch.cuda.synchronize()
+
+    def timer(self):
+        """returns stop() -> elapsed milliseconds since this call (CUDA events on the GPU)"""
+        import torch
+
+        if not self.cuda:
+            t0 = time.perf_counter()
+            return lambda: (time.perf_counter() - t0) * 1e3
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+
+        def stop():
+            e1.record()
+            e1.synchronize()
+            return e0.elapsed_time(e1)
+        return stop
+
+    def stream(self):
+        import torch
+
+        return torch.cuda.Stream(device=self.dev) if self.cuda else None
+
+    def on(self, stream):
+        import contextlib
+
+        import torch
+
+        return torch.cuda.stream(stream) if self.cuda else contextlib.nullcontext()
+
+    def buffer(self, C, nbytes: int, fill: int):
+        """uint8 buffer the van can move one-sidedly: HBM, or shared memory on the host"""
+        import torch
+
+        if self.cuda:
+            return torch.full((nbytes,), fill, dtype=torch.uint8, device=self.dev)
+        return C.alloc_exportable(nbytes, "worker").fill_(fill)
+
+    def pinned(self, t):
+        return t.pin_memory() if self.cuda else t
+
+
 # ----------------------------------------------------------------------------------------
 # ours: push/pull
 # ----------------------------------------------------------------------------------------
@@ -126,18 +187,17 @@ def run_pushpull(args, dist: Dist) -> dict:
     from pslite_b200.utils.timing import ClockSampler
 
     C = native()
-    torch.cuda.set_device(dist.local_rank)
+    gpu = Gpu(args, dist.local_rank)
     topo = args.topology or ("joint" if dist.world == 1 else "split")
-    ctx = init_ps(topo, van=args.van)
+    ctx = init_ps(topo, van=args.van or ("nvl" if gpu.cuda else "shm"))
     server = C.BenchServer(0) if ctx.is_server else None
     S, W = ctx.num_servers, ctx.num_workers
     total_keys = S * args.keys_per_server
-    dev = torch.device("cuda", dist.local_rank)
     kv = keys = vals = None
     if ctx.is_worker:
         kv = C.KVWorker(0, 0)
         keys = [kv.server_key(k % S, k) for k in range(total_keys)]
-        vals = [torch.full((args.len,), 1, dtype=torch.uint8, device=dev) for _ in range(total_keys)]
+        vals = [gpu.buffer(C, args.len, 1) for _ in range(total_keys)]
         for k in range(total_keys):  # rendezvous + store creation, untimed (as the reference does)
             kv.wait(kv.push(keys[k], vals[k], order_after_current_stream=False))
     dist.barrier()
@@ -148,24 +208,21 @@ def run_pushpull(args, dist: Dist) -> dict:
 
     def timed(fn, steps: int):
         dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gpu.sync()
         launches0 = C.kernel_launch_count()
-        e0.record()
+        stop = gpu.timer()
         if ctx.is_worker:
             for _ in range(steps):
                 fn()
-        torch.cuda.synchronize()
-        e1.record()
-        e1.synchronize()
-        ms = e0.elapsed_time(e1)
+        gpu.sync()
+        ms = stop()
         dist.barrier()  # servers keep serving until every worker is done
         launches = C.kernel_launch_count() - launches0
         return dist.reduce(ms, "max"), dist.reduce(float(launches), "sum")
 
     # clocks are sampled from the warm-up on (same load as the timed steps): K steps of this
     # benchmark can be shorter than one nvidia-smi sampling period
-    sampler = ClockSampler(dist.local_rank, period_ms=100).start() if dist.rank == 0 else None
+    sampler = ClockSampler(dist.local_rank, period_ms=100).start() if dist.rank == 0 and gpu.cuda else None
     if ctx.is_worker:
         t_end = time.time() + 1.0
         n_warm = 0
@@ -181,26 +238,27 @@ def run_pushpull(args, dist: Dist) -> dict:
     if not args.no_e2e:
         host_in = host_out = None
         if ctx.is_worker:
-            host_in = [torch.full((args.len,), 2, dtype=torch.uint8).pin_memory() for _ in range(total_keys)]
-            host_out = [torch.empty(args.len, dtype=torch.uint8).pin_memory() for _ in range(total_keys)]
+            host_in = [gpu.pinned(torch.full((args.len,), 2, dtype=torch.uint8)) for _ in range(total_keys)]
+            host_out = [gpu.pinned(torch.empty(args.len, dtype=torch.uint8)) for _ in range(total_keys)]
 
-        h2d_stream = torch.cuda.Stream(device=dev) if ctx.is_worker else None
-        d2h_stream = torch.cuda.Stream(device=dev) if ctx.is_worker else None
+        h2d_stream = gpu.stream() if ctx.is_worker else None
+        d2h_stream = gpu.stream() if ctx.is_worker else None
 
         def e2e_round():
             # software pipeline over keys: H2D of key k+1 | push+pull of key k | D2H of key k-1
             # (PCIe is full duplex; the push waits on the event of its own H2D copy only)
             pulls = []
-            with torch.cuda.stream(h2d_stream):
+            with gpu.on(h2d_stream):
                 for k in range(total_keys):
                     vals[k].copy_(host_in[k], non_blocking=True)      # H2D of this step's input
                     kv.push(keys[k], vals[k], order_after_current_stream=True)
                     pulls.append(kv.pull(keys[k], vals[k]))
-            with torch.cuda.stream(d2h_stream):
+            with gpu.on(d2h_stream):
                 for k in range(total_keys):
                     kv.wait(pulls[k])                                 # value k is back in HBM
                     host_out[k].copy_(vals[k], non_blocking=True)     # D2H of the pulled result
-            d2h_stream.synchronize()
+            if d2h_stream is not None:
+                d2h_stream.synchronize()
 
         if ctx.is_worker:
             e2e_round()
@@ -230,7 +288,7 @@ def run_pushpull(args, dist: Dist) -> dict:
         nk = max(1, min(args.keys_per_server, (512 << 20) // max(sz, 1))) * S
         if ctx.is_worker:
             skeys = [kv.server_key(k % S, 100000 + k) for k in range(nk)]
-            svals = [torch.full((sz,), 1, dtype=torch.uint8, device=dev) for _ in range(nk)]
+            svals = [gpu.buffer(C, sz, 1) for _ in range(nk)]
             for k in range(nk):
                 kv.wait(kv.push(skeys[k], svals[k], order_after_current_stream=False))
 
@@ -262,7 +320,8 @@ def run_pushpull(args, dist: Dist) -> dict:
         "config": {"model": "test_benchmark PUSH_PULL", "msg_bytes": args.len,
                    "keys_per_server": args.keys_per_server, "num_workers": W, "num_servers": S,
                    "global_batch": total_keys * W, "seq_len": args.len,
-                   "parallelism": f"{W}w+{S}s {'co-located' if topo == 'joint' else 'split'} on {dist.world} GPU(s), nvl van",
+                   "parallelism": f"{W}w+{S}s {'co-located' if topo == 'joint' else 'split'} on {dist.world} "
+                                  f"{'GPU(s), nvl van' if gpu.cuda else 'CPU process(es), shm van (self-check, not a result)'}",
                    "l2": f"working set {args.len * total_keys / 1e6:.0f} MB per worker > 126 MB L2"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
     }
@@ -281,10 +340,10 @@ def run_llama(args, dist: Dist) -> dict:
     from pslite_b200.utils.timing import ClockSampler
 
     C = native()
-    torch.cuda.set_device(dist.local_rank)
-    dev = torch.device("cuda", dist.local_rank)
+    gpu = Gpu(args, dist.local_rank)
+    dev = gpu.dev
     topo = args.topology or "joint"
-    ctx = init_ps(topo, van=args.van)
+    ctx = init_ps(topo, van=args.van or ("nvl" if gpu.cuda else "shm"))
     W, S = ctx.num_workers, ctx.num_servers
     server = None
     if ctx.is_server:
@@ -309,7 +368,7 @@ def run_llama(args, dist: Dist) -> dict:
             model = Llama(cfg).to(torch.bfloat16)
         model.init_weights(seed=0)
         model.train()
-    use_symm = args.symmetric and dist.world > 1
+    use_symm = args.symmetric and dist.world > 1 and gpu.cuda
     mc = 0
     if use_symm:
         import torch.distributed as tdist
@@ -342,7 +401,7 @@ def run_llama(args, dist: Dist) -> dict:
             opt.enable_lazy_wait(model)
     dist.barrier()
     g = torch.Generator().manual_seed(1234 + dist.rank)
-    host_tok = torch.randint(0, cfg.vocab_size, (B, T + 1), generator=g).pin_memory()
+    host_tok = gpu.pinned(torch.randint(0, cfg.vocab_size, (B, T + 1), generator=g))
 
     def step(e2e: bool):
         if e2e:
@@ -358,25 +417,22 @@ def run_llama(args, dist: Dist) -> dict:
 
     def timed(fn, steps):
         dist.barrier()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        gpu.sync()
         l0 = C.kernel_launch_count()
-        e0.record()
+        stop = gpu.timer()
         if ctx.is_worker:
             for _ in range(steps):
                 fn()
             opt.wait_all()  # lazy waits: the last step's parameters must have arrived inside the timed region
-        torch.cuda.synchronize()
-        e1.record()
-        e1.synchronize()
-        ms = e0.elapsed_time(e1)
+        gpu.sync()
+        ms = stop()
         dist.barrier()
         return dist.reduce(ms, "max"), dist.reduce(float(C.kernel_launch_count() - l0), "sum")
 
     if ctx.is_worker:
         for _ in range(args.warmup):
             step(False)
-    sampler = ClockSampler(dist.local_rank).start() if dist.rank == 0 else None
+    sampler = ClockSampler(dist.local_rank).start() if dist.rank == 0 and gpu.cuda else None
     ms, launches = timed(lambda: step(False), args.steps)
     clocks = sampler.stop() if sampler else None
     tokens = B * T * W
@@ -392,7 +448,7 @@ def run_llama(args, dist: Dist) -> dict:
     if ctx.is_worker:
         peak = 1386e12
         mfu = cfg.flops_per_token(T) * B * T / (ms / args.steps * 1e-3) / peak
-    peak_mem = round(torch.cuda.max_memory_allocated() / 2**30, 1)
+    peak_mem = round(torch.cuda.max_memory_allocated() / 2**30, 1) if gpu.cuda else None
     stats = {"server_updates": server.num_updates() if server else 0,
              "server_fused_fanouts": server.num_fused_fanouts() if server else 0,
              "server_multicast_fanouts": server.num_multicast_fanouts() if server else 0,

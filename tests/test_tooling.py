@@ -72,3 +72,37 @@ def test_reference_arm_runs_unmodified_reference():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference"
     assert "unavailable" in line or line["value"] > 0
+
+
+REQUIRED_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                 "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches"}
+
+
+@pytest.mark.parametrize("extra", [[], ["--metric", "llama", "--model", "tiny", "--seq-len", "64"]])
+def test_bench_script_control_flow_on_cpu(extra):
+    """bench.py --device cpu walks the same code as a GPU run (warm-up, timed region, end-to-end
+    pass, JSON line) over the shm van and the host engine: a typo in the script must not wait for
+    the round-end GPU run to be found. The numbers it prints are not benchmark results."""
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--device", "cpu", "--steps", "3", "--warmup", "3",
+           "--len", "65536", "--keys-per-server", "4", "--sweep", "4096", *extra]
+    env = dict(os.environ, PSLITE_NO_AUTOBUILD="1", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert REQUIRED_KEYS <= set(line), REQUIRED_KEYS - set(line)
+    assert line["value"] > 0 and line["e2e"]["value"] > 0
+    assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+
+
+def test_bench_script_multi_process_on_cpu():
+    """the torchrun form the driver uses for N > 1 (2 workers + 2 servers)"""
+    from pslite_b200.utils.env import free_port
+
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr",
+           "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "bench.py"), "--device", "cpu",
+           "--gpus", "4", "--steps", "3", "--warmup", "3", "--len", "65536", "--keys-per-server", "4"]
+    env = dict(os.environ, PSLITE_NO_AUTOBUILD="1", CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    line = json.loads([l for l in r.stdout.strip().splitlines() if l.startswith("{")][-1])
+    assert line["n_gpus"] == 4 and line["config"]["num_workers"] == 2 and line["value"] > 0
