@@ -450,6 +450,14 @@ PYBIND11_MODULE(_C, m) {
   m.attr("GRAD_FP8BLOCK") = static_cast<int>(PS_GRAD_FP8BLOCK);
   m.attr("GRAD_MC_BF16") = static_cast<int>(PS_GRAD_MC_BF16);
 
+  m.def("dead_nodes", [](int timeout_s, const std::string& as_role) {
+    // liveness as the scheduler sees it (PS_HEARTBEAT_INTERVAL must be set): ids of nodes that
+    // have not reported for `timeout_s` seconds
+    Postoffice* po = as_role == "scheduler" ? Postoffice::GetScheduler()
+                     : as_role == "server"  ? Postoffice::GetServer() : Postoffice::GetWorker();
+    TORCH_CHECK(po != nullptr, "no such role in this process");
+    return po->GetDeadNodes(timeout_s);
+  }, py::arg("timeout_s") = 60, py::arg("as_role") = "worker");
   m.def("wire_bytes", [](int codec, uint64_t src_bytes) { return WireBytes(codec, src_bytes); });
   m.def("kernel_launch_count", []() { return ps_kernel_launch_count(); });
   m.def("van_bytes", []() {
