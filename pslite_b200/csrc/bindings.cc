@@ -579,6 +579,9 @@ PYBIND11_MODULE(_C, m) {
     return dgu;
   });
 
+  // the engine is not tied to a GPU (host backend on host vans): a neutral alias
+  m.attr("ParamServer") = m.attr("GpuServer");
+
   // ---- raw kernel entry points (numerics tests, standalone use) ----
   m.def("copy_codec", [](torch::Tensor dst, const torch::Tensor& src, int codec, float scale,
                          int max_ctas) {
