@@ -544,6 +544,12 @@ def run_reference(args, dist: Dist) -> dict:
 
 def main():
     args = parse_args()
+    if args.impl != "reference":
+        # a wedged run should say where it is stuck instead of dying silently under the caller's
+        # timeout: after PS_BENCH_WATCHDOG_S seconds dump every Python thread's stack and exit
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ.get("PS_BENCH_WATCHDOG_S", "1500")), exit=True)
     dist = Dist()
     if args.gpus != dist.world and dist.world > 1:
         args.gpus = dist.world
@@ -559,6 +565,10 @@ def main():
         out.setdefault("steps", args.steps)
         out.setdefault("warmup", args.warmup)
         print(json.dumps(out), flush=True)
+    if args.impl != "reference":
+        import faulthandler
+
+        faulthandler.cancel_dump_traceback_later()
     dist.shutdown()
 
 
