@@ -3,6 +3,7 @@
  * \brief Customer inbox + ring-recycled request tracker (see customer.h).
  */
 #include "ps/internal/customer.h"
+#include <chrono>
 #include <limits>
 #include "ps/internal/postoffice.h"
 
@@ -78,11 +79,25 @@ int Customer::NewRequest(int recver, int num_expected) {
 
 void Customer::WaitRequest(int timestamp) {
   std::unique_lock<std::mutex> lk(tracker_mu_);
-  tracker_cv_.wait(lk, [this, timestamp] {
+  auto done = [this, timestamp] {
     Slot* s = Find(timestamp);
     // a recycled slot means the request completed long ago
     return s == nullptr || s->received >= s->expected;
-  });
+  };
+  // a request that never completes is the usual face of a transport bug or a dead peer: say
+  // which one it is instead of hanging silently (PS_WAIT_WARN_S seconds, 0 = never)
+  static const int warn_s = GetEnv("PS_WAIT_WARN_S", 60);
+  if (warn_s <= 0) {
+    tracker_cv_.wait(lk, done);
+    return;
+  }
+  while (!tracker_cv_.wait_for(lk, std::chrono::seconds(warn_s), done)) {
+    Slot* s = Find(timestamp);
+    LOG(WARNING) << "app " << app_id_ << " customer " << customer_id_ << " on node "
+                 << postoffice_->van()->my_node().id << ": request " << timestamp << " still waiting after "
+                 << warn_s << " s (" << (s ? s->received : -1) << " of " << (s ? s->expected : -1)
+                 << " responses)";
+  }
 }
 
 int Customer::NumResponse(int timestamp) {
