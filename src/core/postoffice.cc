@@ -235,7 +235,19 @@ void Postoffice::DoBarrier(int customer_id, int node_group, bool instance_barrie
   req.meta.control.barrier_group = node_group;
   req.meta.timestamp = van_->GetTimestamp();
   CHECK_GT(van_->Send(req), 0);
-  barrier_cond_.wait(ulk, [this, customer_id] { return barrier_done_[0][customer_id]; });
+  // a barrier that never releases means some member never arrived (crashed, or still busy):
+  // name the barrier every PS_WAIT_WARN_S seconds instead of hanging silently
+  static const int warn_s = GetEnv("PS_WAIT_WARN_S", 60);
+  auto released = [this, customer_id] { return barrier_done_[0][customer_id]; };
+  if (warn_s <= 0) {
+    barrier_cond_.wait(ulk, released);
+    return;
+  }
+  while (!barrier_cond_.wait_for(ulk, std::chrono::seconds(warn_s), released)) {
+    LOG(WARNING) << "node " << van_->my_node().id << " (" << role_str() << ") still inside "
+                 << (instance_barrier ? "instance " : "") << "barrier of group " << node_group << " after "
+                 << warn_s << " s: a member has not arrived";
+  }
 }
 
 void Postoffice::Barrier(int customer_id, int node_group) {
