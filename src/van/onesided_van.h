@@ -28,6 +28,7 @@
  */
 #ifndef PS_VAN_ONESIDED_VAN_H_
 #define PS_VAN_ONESIDED_VAN_H_
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <atomic>
@@ -315,7 +316,10 @@ class OneSidedVan : public TcpVan {
     req.meta.timestamp = GetTimestamp();
     CHECK_GT(TcpVan::SendMsg(req), 0);
     lk.lock();
-    rv_cv_.wait(lk, [&] { return push_slots_.count(pk) > 0; });
+    while (!rv_cv_.wait_for(lk, std::chrono::seconds(60), [&] { return push_slots_.count(pk) > 0; })) {
+      LOG(WARNING) << type_ << " van " << my_node_.id << ": no landing slot from node " << recver
+                   << " for key " << key << " (" << bytes << " B) after 60 s";
+    }
     return push_slots_[pk];
   }
 
