@@ -1,5 +1,7 @@
 // Unit tests: SArray, Range, Environment, queues, wire codec, allocators.
 #include <sys/wait.h>
+#include <condition_variable>
+#include <mutex>
 #include <thread>
 #include "core/wire.h"
 #include "ps/internal/parallel_sort.h"
@@ -273,6 +275,56 @@ TEST(shm_pipe_stream_and_doorbell) {
   CHECK(tx->ReaderNeedsDoorbell());
   CHECK(!rx->PrepareSleep());
   CHECK(rx->Read(&got, sizeof(got)));
+}
+
+TEST(shm_pipe_no_lost_wakeups) {
+  // the reader really sleeps (on a condition variable standing in for the socket doorbell) and
+  // must be woken for every frame that arrives while it sleeps: a lost wake-up shows as a timeout
+  const std::string name = "/pslite_test_wake_" + std::to_string(getpid());
+  auto tx = ShmPipe::Create(name, 4096);
+  auto rx = ShmPipe::Attach(name);
+  CHECK(tx != nullptr && rx != nullptr);
+  rx->Unlink();
+  std::mutex mu;
+  std::condition_variable bell;
+  int rings = 0;
+  const int kFrames = 20000;
+  std::atomic<bool> lost{false};
+  std::thread writer([&] {
+    unsigned seed = 7;
+    for (int f = 0; f < kFrames; ++f) {
+      uint32_t v = static_cast<uint32_t>(f);
+      CHECK(tx->Write(&v, sizeof(v)));
+      if (tx->ReaderNeedsDoorbell()) {
+        std::lock_guard<std::mutex> lk(mu);
+        ++rings;
+        bell.notify_one();
+      }
+      if ((rand_r(&seed) & 127) == 0) std::this_thread::sleep_for(std::chrono::microseconds(rand_r(&seed) % 300));
+    }
+  });
+  int seen_rings = 0, sleeps = 0;
+  for (int f = 0; f < kFrames && !lost.load(); ++f) {
+    while (rx->Readable() < sizeof(uint32_t)) {
+      if (!rx->PrepareSleep()) continue;  // data showed up while announcing the sleep
+      std::unique_lock<std::mutex> lk(mu);
+      ++sleeps;
+      if (!bell.wait_for(lk, std::chrono::seconds(5), [&] { return rings > seen_rings || rx->Readable() > 0; })) {
+        lost.store(true);
+        break;
+      }
+      seen_rings = rings;
+      lk.unlock();
+      rx->CancelSleep();
+    }
+    if (lost.load()) break;
+    uint32_t v = 0;
+    CHECK(rx->Read(&v, sizeof(v)));
+    CHECK_EQ(v, static_cast<uint32_t>(f));
+  }
+  writer.join();
+  CHECK(!lost.load()) << "a frame arrived while the reader slept and nobody rang";
+  CHECK_GT(sleeps, 0);
 }
 
 TEST(stale_shm_sweep) {
