@@ -24,6 +24,42 @@ int main() {
   CHECK_EQ(out.size(), (size_t)3);
   CHECK_EQ(out[0], 3.0f); CHECK_EQ(out[2], 7.0f);
   LOG(INFO) << "push/pull ok: " << out[0] << " " << out[1] << " " << out[2];
+
+  // edges of the key space: the first key, the last key below kMaxKey, an isolated key
+  std::vector<Key> edge = {0, 7, kMaxKey - 1};
+  std::vector<float> ev = {10.f, 20.f, 30.f};
+  kv.Wait(kv.Push(edge, ev));
+  std::vector<float> eo;
+  kv.Wait(kv.Pull(edge, &eo));
+  CHECK_EQ(eo.size(), (size_t)3);
+  CHECK_EQ(eo[0], 10.f); CHECK_EQ(eo[1], 20.f); CHECK_EQ(eo[2], 30.f);
+
+  // pulling into a larger pre-sized vector is allowed: only the front is written
+  std::vector<float> big(8, -1.f);
+  kv.Wait(kv.Pull(keys, &big));
+  CHECK_EQ(big.size(), (size_t)8);
+  CHECK_EQ(big[0], 3.0f); CHECK_EQ(big[2], 7.0f); CHECK_EQ(big[3], -1.f);
+
+  // callbacks run exactly once, before Wait returns
+  std::atomic<int> fired{0};
+  kv.Wait(kv.Push(keys, vals, {}, 0, [&fired] { ++fired; }));
+  CHECK_EQ(fired.load(), 1);
+
+  // fused push-pull: push once more and get the new sums in one round trip
+  std::vector<float> pp;
+  kv.Wait(kv.PushPull(keys, vals, &pp));
+  CHECK_EQ(pp.size(), (size_t)3);
+  CHECK_EQ(pp[0], 1.5f * 4); CHECK_EQ(pp[2], 3.5f * 4);
+
+  // zero-copy variants keep working on caller-owned arrays
+  SArray<Key> zk(keys);
+  SArray<float> zv(3, 0.f);
+  kv.Wait(kv.ZPull(zk, &zv));
+  CHECK_EQ(zv[1], 2.5f * 4);
+  SArray<float> zin(vals), zout(3, 0.f);
+  kv.Wait(kv.ZPushPull(zk, zin, &zout));
+  CHECK_EQ(zout[1], 2.5f * 5);
+  LOG(INFO) << "edge cases ok";
   std::thread fs([] { Postoffice::GetScheduler()->Finalize(0, true); });
   std::thread fv([] { Postoffice::GetServer()->Finalize(0, true); });
   std::thread fw([] { Postoffice::GetWorker()->Finalize(0, true); });

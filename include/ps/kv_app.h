@@ -629,7 +629,8 @@ int KVWorker<Val>::Pull_(const SArray<Key>& keys, C* vals, D* lens, int cmd, con
         if (s.vals.data() != out && s.vals.size()) {
           CHECK(!s.vals.on_gpu()) << "pulled values are in device memory but did not land in the "
                                      "destination; pull into an exportable device buffer";
-          memcpy(out, s.vals.data(), s.vals.size() * sizeof(Val));
+          // memmove: a slice that landed further right in the same buffer may overlap its final place
+          memmove(out, s.vals.data(), s.vals.size() * sizeof(Val));
         }
         out += s.vals.size();
         if (out_len) {
@@ -652,8 +653,12 @@ int KVWorker<Val>::Pull_(const SArray<Key>& keys, C* vals, D* lens, int cmd, con
     Send(ts, true, cmd, kvs, opts, &dest);
     return ts;
   }
-  kvs.vals = kv_detail::ViewOf(vals);
-  if (lens && !lens->empty()) kvs.lens = kv_detail::ViewOf(lens);
+  // the destination is cut per server so that replies can land in place — possible when its
+  // size says how many values each key has. A buffer merely pre-sized "large enough" (allowed:
+  // only the front is written) does not: then the replies are gathered and stitched afterwards.
+  const bool lens_known = lens && !lens->empty();
+  if (lens_known || (keys.size() && vals->size() % keys.size() == 0)) kvs.vals = kv_detail::ViewOf(vals);
+  if (lens_known) kvs.lens = kv_detail::ViewOf(lens);
   Send(ts, false, cmd, kvs, opts);
   return ts;
 }
