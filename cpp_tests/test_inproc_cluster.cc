@@ -59,6 +59,14 @@ int main() {
   SArray<float> zin(vals), zout(3, 0.f);
   kv.Wait(kv.ZPushPull(zk, zin, &zout));
   CHECK_EQ(zout[1], 2.5f * 5);
+  // SimpleApp surface of the KV classes: a request to the server group, answered with a body
+  server->SimpleApp::set_request_handle([](const SimpleData& req, SimpleApp* app) {
+    app->Response(req, "echo:" + req.body);
+  });
+  std::string reply;
+  kv.SimpleApp::set_response_handle([&reply](const SimpleData& res, SimpleApp*) { reply = res.body; });
+  kv.SimpleApp::Wait(kv.Request(42, "ping", kServerGroup));
+  CHECK_EQ(reply, std::string("echo:ping"));
   LOG(INFO) << "edge cases ok";
   std::thread fs([] { Postoffice::GetScheduler()->Finalize(0, true); });
   std::thread fv([] { Postoffice::GetServer()->Finalize(0, true); });
