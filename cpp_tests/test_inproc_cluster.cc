@@ -1,4 +1,5 @@
 // In-process cluster smoke test: scheduler + 1 server + 1 worker as threads.
+#include <map>
 #include "ps/ps.h"
 using namespace ps;
 int main() {
@@ -59,6 +60,45 @@ int main() {
   SArray<float> zin(vals), zout(3, 0.f);
   kv.Wait(kv.ZPushPull(zk, zin, &zout));
   CHECK_EQ(zout[1], 2.5f * 5);
+  // variable-length values (lens): a second app with a handler that stores a vector per key
+  auto* vserver = new KVServer<float>(1);
+  auto vstore = std::make_shared<std::map<Key, std::vector<float>>>();
+  vserver->set_request_handle([vstore](const KVMeta& req, const KVPairs<float>& d, KVServer<float>* srv) {
+    KVPairs<float> res;
+    if (req.push) {
+      CHECK_EQ(d.lens.size(), d.keys.size());
+      size_t at = 0;
+      for (size_t i = 0; i < d.keys.size(); ++i) {
+        (*vstore)[d.keys[i]].assign(d.vals.data() + at, d.vals.data() + at + d.lens[i]);
+        at += static_cast<size_t>(d.lens[i]);
+      }
+      CHECK_EQ(at, d.vals.size());
+    } else {
+      res.keys = d.keys;
+      for (Key k : d.keys) {
+        const auto& v = (*vstore)[k];
+        res.lens.push_back(static_cast<int>(v.size()));
+        for (float x : v) res.vals.push_back(x);
+      }
+    }
+    srv->Response(req, res);
+  });
+  {
+    KVWorker<float> vkv(1, 1);
+    std::vector<Key> vk = {2, 9, 11};
+    std::vector<float> vv = {1.f, 2.f, 2.5f, 3.f, 3.25f, 3.5f};
+    std::vector<int> vl = {1, 2, 3};
+    vkv.Wait(vkv.Push(vk, vv, vl));
+    std::vector<float> got;   // 0-sized: filled by the pull
+    std::vector<int> got_len; // 0-sized: filled by the pull
+    vkv.Wait(vkv.Pull(vk, &got, &got_len));
+    CHECK_EQ(got.size(), (size_t)6);
+    CHECK_EQ(got_len.size(), (size_t)3);
+    CHECK_EQ(got_len[0], 1); CHECK_EQ(got_len[2], 3);
+    CHECK_EQ(got[1], 2.f); CHECK_EQ(got[5], 3.5f);
+  }
+  delete vserver;
+
   // SimpleApp surface of the KV classes: a request to the server group, answered with a body
   server->SimpleApp::set_request_handle([](const SimpleData& req, SimpleApp* app) {
     app->Response(req, "echo:" + req.body);
