@@ -108,10 +108,13 @@ int main() {
   kv.SimpleApp::Wait(kv.Request(42, "ping", kServerGroup));
   CHECK_EQ(reply, std::string("echo:ping"));
   LOG(INFO) << "edge cases ok";
+  std::atomic<int> exit_calls{0};
+  Postoffice::GetWorker()->RegisterExitCallback([&exit_calls] { ++exit_calls; });
   std::thread fs([] { Postoffice::GetScheduler()->Finalize(0, true); });
   std::thread fv([] { Postoffice::GetServer()->Finalize(0, true); });
   std::thread fw([] { Postoffice::GetWorker()->Finalize(0, true); });
   fs.join(); fv.join(); fw.join();
+  CHECK_EQ(exit_calls.load(), 1);  // the exit callback ran during the worker's Finalize
   delete server;
   LOG(INFO) << "done";
   return 0;
