@@ -13,6 +13,29 @@ int main() {
   std::thread tw([] { Postoffice::GetWorker()->Start(0, Node::WORKER, -1, true, nullptr); });
   ts.join(); tv.join(); tw.join();
   LOG(INFO) << "cluster up";
+  // node numbering of the reference: scheduler 1, server rank r -> 2r+8, worker rank r -> 2r+9;
+  // group ids are bit masks whose members are the union of the named groups
+  CHECK_EQ(Postoffice::ServerRankToID(0), 8); CHECK_EQ(Postoffice::WorkerRankToID(0), 9);
+  CHECK_EQ(Postoffice::ServerRankToID(3), 14); CHECK_EQ(Postoffice::WorkerRankToID(3), 15);
+  CHECK_EQ(Postoffice::IDtoRank(14), 3); CHECK_EQ(Postoffice::IDtoRank(15), 3);
+  {
+    Postoffice* po = Postoffice::GetWorker();
+    CHECK_EQ(po->GetNodeIDs(kScheduler).size(), (size_t)1);
+    CHECK_EQ(po->GetNodeIDs(kScheduler)[0], 1);
+    CHECK_EQ(po->GetNodeIDs(kServerGroup).size(), (size_t)1);
+    CHECK_EQ(po->GetNodeIDs(kServerGroup)[0], 8);
+    CHECK_EQ(po->GetNodeIDs(kWorkerGroup)[0], 9);
+    CHECK_EQ(po->GetNodeIDs(kWorkerGroup + kServerGroup).size(), (size_t)2);
+    CHECK_EQ(po->GetNodeIDs(kWorkerGroup + kServerGroup + kScheduler).size(), (size_t)3);
+    CHECK_EQ(po->num_workers(), 1); CHECK_EQ(po->num_servers(), 1);
+    CHECK(po->is_worker()); CHECK(!po->is_server());
+    CHECK_EQ(po->my_rank(), 0);
+    const auto& ranges = po->GetServerKeyRanges();
+    CHECK_EQ(ranges.size(), (size_t)1);
+    CHECK_EQ(ranges[0].begin(), (uint64_t)0);
+    CHECK(Postoffice::GetServer()->is_server());
+    CHECK(Postoffice::GetScheduler()->is_scheduler());
+  }
   auto* server = new KVServer<float>(0);
   server->set_request_handle(KVServerDefaultHandle<float>());
   KVWorker<float> kv(0, 0);
