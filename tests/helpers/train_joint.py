@@ -80,6 +80,7 @@ def main():
     ok = ps_losses[-1] < ps_losses[0] and abs(ps_losses[-1] - ref_losses[-1]) < (0.02 if wire == "bf16" else 0.08)
     ok = ok and server.num_fused_fanouts() > 0
     ok = ok and server.on_device() == use_cuda
+    ok = ok and list(C.dead_nodes(60, "worker")) == []  # liveness query is callable from any node
     if not ok:
         print("FAIL (before the checkpoint stage)")
     # checkpoint round trip: save, train on, restore -> the fp32 master is back to the saved one

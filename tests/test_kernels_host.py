@@ -15,6 +15,14 @@ def test_host_raw_copy(native, n):
     assert torch.equal(dst, src)
 
 
+def test_host_multi_segment_copy(native):
+    """copy_multi on CPU tensors (the GPU version is one launch for all segments)"""
+    srcs = [torch.randint(0, 255, (n,), dtype=torch.uint8) for n in (1, 15, 16, 4097, 1 << 20, 3 * (1 << 20) + 5)]
+    dsts = [torch.zeros_like(s) for s in srcs]
+    native.copy_multi(dsts, srcs)
+    assert all(torch.equal(d, s) for d, s in zip(dsts, srcs))
+
+
 @pytest.mark.parametrize("n", [8, 1000, 100003, 600001])
 def test_host_f32_to_bf16_scaled(native, n):
     x = torch.randn(n)
