@@ -59,7 +59,11 @@ class Van {
   /*! \brief stop the receive thread and the transport */
   virtual void Stop();
   /*! \brief next control-plane timestamp */
-  int GetTimestamp() { return timestamp_++; }
+  int GetTimestamp() {
+    int ts = timestamp_++;
+    if (ts == Meta::kEmpty) ts = timestamp_++;  // the sentinel is never a real timestamp
+    return ts;
+  }
   bool IsReady() { return ready_.load(); }
   virtual std::string GetType() const = 0;
 

@@ -39,16 +39,24 @@ else
     pids+=($!)
   done
 fi
+# fail fast: stop everybody as soon as one process fails. `wait -n` returns 127 once no child is
+# left to report — it can get there early, because bash may retire several children that exited
+# together on one call — so the authoritative exit codes are collected per pid afterwards
+# (`wait <pid>` also answers for children that are already gone).
 rc=0
 remaining=${#pids[@]}
 while [ $remaining -gt 0 ]; do
   wait -n; st=$?
   remaining=$((remaining - 1))
+  if [ $st -eq 127 ]; then break; fi
   if [ $st -ne 0 ]; then
     rc=$st
     for p in "${pids[@]}"; do kill $p 2>/dev/null; done
     break
   fi
 done
-wait 2>/dev/null
+for p in "${pids[@]}"; do
+  wait $p 2>/dev/null; st=$?
+  if [ $rc -eq 0 ] && [ $st -ne 0 ] && [ $st -ne 127 ]; then rc=$st; fi
+done
 exit $rc

@@ -58,6 +58,10 @@ int Customer::NewRequest(int recver, int num_expected) {
     groups = is_group ? std::max(1, members / postoffice_->group_size()) : members;
   }
   std::lock_guard<std::mutex> lk(tracker_mu_);
+  // Meta::kEmpty (32767) means "no timestamp" in several places: never hand it out (the
+  // reference does, and its resender then aborts on the 32768th request of a customer)
+  if (next_ts_ == Meta::kEmpty) ++next_ts_;
+  if (next_ts_ < 0) next_ts_ = 0;  // wrapped after 2^31 requests
   const int ts = next_ts_++;
   for (;;) {
     Slot& s = ring_[static_cast<size_t>(ts) & (ring_.size() - 1)];

@@ -15,6 +15,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <mutex>
 #include <thread>
 #include <unordered_map>
@@ -69,6 +70,15 @@ class Resender {
     {
       std::lock_guard<std::mutex> lk(mu_);
       duplicated = !seen_.insert(sig).second;
+      if (!duplicated) {
+        // a retransmission follows its original within a few timeouts: remembering the last
+        // kSeenWindow messages is enough, and keeps a long job's memory bounded
+        seen_order_.push_back(sig);
+        if (seen_order_.size() > kSeenWindow) {
+          seen_.erase(seen_order_.front());
+          seen_order_.pop_front();
+        }
+      }
     }
     Message ack;
     ack.meta.recver = msg.meta.sender;
@@ -109,16 +119,27 @@ class Resender {
     return std::chrono::duration_cast<std::chrono::milliseconds>(
                std::chrono::steady_clock::now().time_since_epoch()).count();
   }
-  /*! \brief [app:14][sender:16][recver:16][timestamp:17][request:1] */
+  /*!
+   * \brief identity of a message on both ends of a link: a 64-bit mix of (app, customer, sender,
+   *        receiver, full 32-bit timestamp, request bit). The reference packs truncated fields
+   *        (8-bit node ids, src/resender.h:98-100); any fixed packing of these fields into 64
+   *        bits has to drop something that eventually repeats — a long job wraps a 17-bit
+   *        timestamp after 131072 requests and would see its own new messages as duplicates.
+   */
   uint64_t Signature(const Message& msg) {
     CHECK_NE(msg.meta.timestamp, Meta::kEmpty) << msg.DebugString();
-    const uint64_t app = static_cast<uint64_t>(msg.meta.app_id) & 0x3fff;
     const int s = msg.meta.sender == Node::kEmpty ? van_->my_node_.id : msg.meta.sender;
-    const uint64_t sender = static_cast<uint64_t>(s) & 0xffff;
-    const uint64_t recver = static_cast<uint64_t>(msg.meta.recver) & 0xffff;
-    const uint64_t ts = static_cast<uint64_t>(msg.meta.timestamp) & 0x1ffff;
-    return (app << 50) | (sender << 34) | (recver << 18) | (ts << 1) |
-           (msg.meta.request ? 1u : 0u);
+    uint64_t h = Mix(static_cast<uint32_t>(msg.meta.timestamp));
+    h = Mix(h ^ (static_cast<uint64_t>(static_cast<uint32_t>(s)) << 32 | static_cast<uint32_t>(msg.meta.recver)));
+    h = Mix(h ^ (static_cast<uint64_t>(static_cast<uint32_t>(msg.meta.app_id)) << 32 |
+                 static_cast<uint32_t>(msg.meta.customer_id)));
+    return Mix(h ^ (msg.meta.request ? 0x9e3779b97f4a7c15ull : 0));
+  }
+  static uint64_t Mix(uint64_t x) {  // splitmix64 finaliser
+    x += 0x9e3779b97f4a7c15ull;
+    x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+    x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+    return x ^ (x >> 31);
   }
   void Monitor() {
     std::unique_lock<std::mutex> lk(mu_);
@@ -157,7 +178,9 @@ class Resender {
 
   std::thread monitor_;
   std::unordered_map<uint64_t, Pending> pending_;
+  static constexpr size_t kSeenWindow = 1u << 18;
   std::unordered_set<uint64_t> seen_;
+  std::deque<uint64_t> seen_order_;  // insertion order of seen_, oldest first
   bool exit_ = false;
   bool lenient_ = false;
   std::mutex mu_;

@@ -208,6 +208,10 @@ int Van::SendBestEffort(Message& msg) {
 }
 
 int Van::Send(Message& msg) {
+  // remember the message BEFORE it leaves: over a shared-memory ring the ACK can be back before
+  // SendMsg returns, and an ACK for a message nobody remembers is dropped (the message would be
+  // retransmitted a timeout later for nothing; the reference registers it after the send)
+  if (resender_) resender_->AddOutgoing(msg);
   const int n = SendMsg(msg);
   if (n == -1 && (stopping_.load() || msg.meta.control.cmd == Control::ACK)) {
     // the peer already left (shutdown races with late ACKs / retransmissions)
@@ -216,7 +220,6 @@ int Van::Send(Message& msg) {
   }
   CHECK_NE(n, -1) << GetType() << " sent -1 bytes";
   send_bytes_ += static_cast<size_t>(n);
-  if (resender_) resender_->AddOutgoing(msg);
   LOG_IF(INFO, postoffice_->verbose() >= 2)
       << GetType() << " " << my_node_.id << "\tsent: " << msg.DebugString();
   return n;
