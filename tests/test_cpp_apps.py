@@ -172,7 +172,8 @@ def test_van_profiling_log(built_native_tree, tmp_path):
     assert server_log and server_log[0].split("\t")[1] in ("server_van_recv_push", "server_van_recv_pull")
 
 
-def test_dead_node_is_replaced_by_late_registration(built_native_tree):
+@pytest.mark.parametrize("van", ["zmq", "shm"])
+def test_dead_node_is_replaced_by_late_registration(built_native_tree, van):
     """heartbeats -> dead-node detection -> a late worker inherits the dead worker's id."""
     import random
     import time
@@ -181,7 +182,7 @@ def test_dead_node_is_replaced_by_late_registration(built_native_tree):
     env = dict(os.environ)
     env.update({"DMLC_NUM_SERVER": "1", "DMLC_NUM_WORKER": "2", "DMLC_PS_ROOT_URI": "127.0.0.1",
                 "DMLC_PS_ROOT_PORT": str(21000 + random.randrange(10000)), "DMLC_NODE_HOST": "127.0.0.1",
-                "PS_HEARTBEAT_INTERVAL": "1", "PS_HEARTBEAT_TIMEOUT": "2"})
+                "PS_HEARTBEAT_INTERVAL": "1", "PS_HEARTBEAT_TIMEOUT": "2", "PS_VAN_TYPE": van})
     env.pop("DMLC_RANK", None)
 
     def spawn(role, **extra):
