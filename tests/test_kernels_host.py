@@ -104,6 +104,28 @@ def test_host_fused_adamw_update(native, fmt, W, fan):
         assert torch.equal(o, pk.to(torch.bfloat16))
 
 
+@pytest.mark.parametrize("n", [1, 5, 7, 9, 33, 257])
+@pytest.mark.parametrize("fmt", ["bf16", "fp8", "f32"])
+def test_host_update_of_tiny_and_ragged_shards(native, n, fmt):
+    """shards shorter than one 8-element group / one 32-element fp8 block, and ragged tails"""
+    torch.manual_seed(n)
+    p, m, v = torch.randn(n), torch.zeros(n), torch.zeros(n)
+    g32 = torch.randn(n) * 0.1
+    if fmt == "bf16":
+        wire, dec, gfmt = g32.to(torch.bfloat16), g32.to(torch.bfloat16).float(), native.GRAD_BF16
+    elif fmt == "f32":
+        wire, dec, gfmt = g32, g32, native.GRAD_F32
+    else:
+        wire = torch.zeros(native.wire_bytes(native.CODEC_F32_TO_FP8BLOCK, n * 4), dtype=torch.uint8)
+        native.copy_codec(wire, g32.view(torch.uint8), native.CODEC_F32_TO_FP8BLOCK, 1.0)
+        dec, gfmt = ref_fp8_block(g32), native.GRAD_FP8BLOCK
+    out = torch.empty(n, dtype=torch.bfloat16)
+    pk = p.clone()
+    native.fused_update([wire], gfmt, pk, m, v, [out], "sgd", 0.5, 0.0, 0.0, 0.0, 0.0, 1, 1.0, 0)
+    assert torch.allclose(pk, p - 0.5 * dec, rtol=1e-6, atol=1e-7)
+    assert torch.equal(out, pk.to(torch.bfloat16))
+
+
 def test_host_fused_sgd_update(native):
     n = 4099
     p = torch.randn(n)
