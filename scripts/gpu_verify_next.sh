@@ -13,7 +13,7 @@ echo "== 1. pytest -m gpu (without the multi-GPU module); PSLITE_TEST_UNVERIFIED
 export PSLITE_TEST_UNVERIFIED=1
 timeout 900 python -m pytest tests -m gpu -x -q --ignore=tests/test_multigpu.py 2>&1 | tail -n 8
 echo "== 2. kernels written after the GPU budget ran out (multi-segment copy, host/GPU bit-exactness)"
-PSLITE_TEST_UNVERIFIED=1 timeout 400 python -m pytest tests/test_kernels_gpu.py tests/test_kernels_host.py -m gpu -q -k "multi_segment or wire_bytes" 2>&1 | tail -n 8
+PSLITE_TEST_UNVERIFIED=1 timeout 400 python -m pytest tests/test_kernels_gpu.py tests/test_kernels_host.py -m gpu -q -k "multi_segment or wire_bytes or tiny_and_ragged" 2>&1 | tail -n 8
 echo "== 2b. two-group update kernel (PS_UPDATE_X2=1): same numerics tests, then its bandwidth"
 PS_UPDATE_X2=1 timeout 400 python -m pytest tests/test_kernels_gpu.py -m gpu -q -k "fused_adamw or fused_sgd" 2>&1 | tail -n 4
 for x2 in 0 1; do PS_UPDATE_X2=$x2 timeout 200 build/kernel_bench 2>/dev/null | grep -i update | head -6 | sed "s/^/x2=$x2 /"; done

@@ -120,6 +120,33 @@ def test_fused_adamw_update(native, fmt, W, fan):
         assert torch.equal(o, pk.to(torch.bfloat16))
 
 
+@pytest.mark.skipif(__import__("os").environ.get("PSLITE_TEST_UNVERIFIED", "0") != "1",
+                    reason="added after the GPU budget ran out; set PSLITE_TEST_UNVERIFIED=1")
+@pytest.mark.parametrize("n", [1, 5, 7, 9, 33, 257])
+@pytest.mark.parametrize("fmt", ["bf16", "fp8", "f32"])
+def test_update_of_tiny_and_ragged_shards(native, n, fmt):
+    """same cases as tests/test_kernels_host.py: shards shorter than one group / one fp8 block"""
+    _require_cuda()
+    torch.manual_seed(n)
+    p = torch.randn(n, device="cuda")
+    m, v = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+    g32 = torch.randn(n, device="cuda") * 0.1
+    if fmt == "bf16":
+        wire, dec, gfmt = g32.to(torch.bfloat16), g32.to(torch.bfloat16).float(), native.GRAD_BF16
+    elif fmt == "f32":
+        wire, dec, gfmt = g32, g32, native.GRAD_F32
+    else:
+        wire = torch.zeros(native.wire_bytes(native.CODEC_F32_TO_FP8BLOCK, n * 4), dtype=torch.uint8, device="cuda")
+        native.copy_codec(wire, g32.view(torch.uint8), native.CODEC_F32_TO_FP8BLOCK, 1.0)
+        dec, gfmt = ref_fp8_block(g32), native.GRAD_FP8BLOCK
+    out = torch.empty(n, dtype=torch.bfloat16, device="cuda")
+    pk = p.clone()
+    native.fused_update([wire], gfmt, pk, m, v, [out], "sgd", 0.5, 0.0, 0.0, 0.0, 0.0, 1, 1.0, 0)
+    torch.cuda.synchronize()
+    assert torch.allclose(pk, p - 0.5 * dec, rtol=1e-6, atol=1e-7)
+    assert torch.equal(out, pk.to(torch.bfloat16))
+
+
 def test_fused_sgd_update(native):
     _require_cuda()
     n = 4099
