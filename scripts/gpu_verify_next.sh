@@ -17,6 +17,9 @@ PSLITE_TEST_UNVERIFIED=1 timeout 400 python -m pytest tests/test_kernels_gpu.py 
 echo "== 2b. two-group update kernel (PS_UPDATE_X2=1): same numerics tests, then its bandwidth"
 PS_UPDATE_X2=1 timeout 400 python -m pytest tests/test_kernels_gpu.py -m gpu -q -k "fused_adamw or fused_sgd" 2>&1 | tail -n 4
 for x2 in 0 1; do PS_UPDATE_X2=$x2 timeout 200 build/kernel_bench 2>/dev/null | grep -i update | head -6 | sed "s/^/x2=$x2 /"; done
+echo "== 2c. TMA-staged update kernel (PS_UPDATE_TMA=1): numerics first (under timeout: a wrong mbarrier phase would hang), then bandwidth"
+PS_UPDATE_TMA=1 timeout 300 python -m pytest tests/test_kernels_gpu.py -m gpu -q -k "fused_adamw or fused_sgd" 2>&1 | tail -n 4
+for t in 0 1; do PS_UPDATE_TMA=$t timeout 200 build/kernel_bench 2>/dev/null | grep -i update | head -6 | sed "s/^/tma=$t /"; done
 echo "== 3a. multi-GPU module, verified flows"
 timeout 900 python -m pytest tests/test_multigpu.py -m gpu -q 2>&1 | tail -n 8
 echo "== 3b. in-switch gradient reduction"

@@ -367,6 +367,166 @@ k_update_x2(const UpdateDev a, const ps_opt_params o) {
   }
 }
 
+// ---------------------------------------------------------------------------
+// K_update, TMA flavour (PS_UPDATE_TMA=1, experimental until it has run on hardware)
+//
+// The register-file version above can keep ~28 KB of loads in flight per SM (4 CTAs x 256 threads
+// x one 8-element group); its remaining stall is the first use of a load. Here one elected
+// thread per CTA streams whole tiles — fp32 master / m / v and the W gradient slots — into shared
+// memory with cp.async.bulk behind mbarriers, kTmaStages - 1 tiles (up to ~110 KB) ahead of the
+// 256 consumer threads, which compute from shared memory and write results with plain vector
+// stores (stores do not stall). One persistent CTA per SM.
+//   tile   = 2048 elements; thread t owns elements [4t, 4t+4) and [1024+4t, 1024+4t+4) of it,
+//            so every shared-memory access of a warp is contiguous (no bank conflicts)
+//   stage  = 24 KB of state + W x (4 KB bf16 | 2 KB fp8 | 8 KB f32) of gradients
+//   tail   = the elements after the last full tile are done by CTA 0 with the scalar path
+// ---------------------------------------------------------------------------
+constexpr int kTile = 2048;
+constexpr int kTmaStagesU = 3;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init_u(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_u(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait_u(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+  } while (!done);
+}
+__device__ __forceinline__ void bulk_load_u(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_addr(smem_dst)),
+      "l"(gsrc), "r"(bytes), "r"(smem_addr(bar))
+      : "memory");
+}
+__device__ __forceinline__ void st8(void* p, uint32_t a, uint32_t b) {
+  asm volatile("st.global.L1::no_allocate.v2.b32 [%0], {%1,%2};" ::"l"(p), "r"(a), "r"(b) : "memory");
+}
+__device__ __forceinline__ void multimem_st8(void* p, uint32_t a, uint32_t b) {
+  asm volatile("multimem.st.relaxed.sys.global.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(__uint_as_float(a)),
+               "f"(__uint_as_float(b))
+               : "memory");
+}
+
+template <int FMT>
+__host__ __device__ constexpr int GradTileBytes() {
+  return FMT == PS_GRAD_BF16 ? kTile * 2 : (FMT == PS_GRAD_FP8BLOCK ? kTile : kTile * 4);
+}
+
+template <int FMT, int OPT>
+__global__ void __launch_bounds__(kThreads, 1)
+k_update_tma(const UpdateDev a, const ps_opt_params o) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ __align__(8) uint64_t full[kTmaStagesU];
+  constexpr int kStateBytes = kTile * 4;
+  constexpr int kGradBytes = GradTileBytes<FMT>();
+  const int W = a.num_grads;
+  const int stage_bytes = 3 * kStateBytes + W * kGradBytes;
+  const size_t n_tiles = a.n / kTile;
+  const size_t first = blockIdx.x, stride = gridDim.x;
+  const size_t mine = first < n_tiles ? (n_tiles - first + stride - 1) / stride : 0;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < kTmaStagesU; ++s) mbar_init_u(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // producer (thread 0): all loads of my k-th tile into its stage
+  auto issue = [&](size_t k) {
+    const int s = static_cast<int>(k % kTmaStagesU);
+    const size_t e0 = (first + k * stride) * static_cast<size_t>(kTile);
+    unsigned char* st = smem + static_cast<size_t>(s) * stage_bytes;
+    mbar_expect_u(&full[s], static_cast<uint32_t>(OPT == PS_OPT_ADAMW ? stage_bytes : stage_bytes - kStateBytes));
+    bulk_load_u(st, a.master + e0, kStateBytes, &full[s]);
+    bulk_load_u(st + kStateBytes, a.m + e0, kStateBytes, &full[s]);
+    if (OPT == PS_OPT_ADAMW) bulk_load_u(st + 2 * kStateBytes, a.v + e0, kStateBytes, &full[s]);
+    for (int w = 0; w < W; ++w) {
+      const unsigned char* g = static_cast<const unsigned char*>(a.grads[w]);
+      const size_t goff = FMT == PS_GRAD_BF16 ? e0 * 2 : (FMT == PS_GRAD_FP8BLOCK ? e0 : e0 * 4);
+      bulk_load_u(st + 3 * kStateBytes + w * kGradBytes, g + goff, kGradBytes, &full[s]);
+    }
+  };
+  if (tid == 0) {
+    for (size_t k = 0; k < mine && k < static_cast<size_t>(kTmaStagesU - 1); ++k) issue(k);
+  }
+
+  const size_t npad = (a.n + 31) / 32 * 32;
+  for (size_t j = 0; j < mine; ++j) {
+    const int s = static_cast<int>(j % kTmaStagesU);
+    const unsigned char* st = smem + static_cast<size_t>(s) * stage_bytes;
+    mbar_wait_u(&full[s], static_cast<uint32_t>((j / kTmaStagesU) & 1));
+    const size_t e0 = (first + j * stride) * static_cast<size_t>(kTile);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int le = h * (kTile / 2) + 4 * tid;  // first of my 4 elements inside the tile
+      float4 p = *reinterpret_cast<const float4*>(st + le * 4);
+      float4 m = *reinterpret_cast<const float4*>(st + kStateBytes + le * 4);
+      float4 v = make_float4(0, 0, 0, 0);
+      if (OPT == PS_OPT_ADAMW) v = *reinterpret_cast<const float4*>(st + 2 * kStateBytes + le * 4);
+      float g[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int w = 0; w < W; ++w) {
+        const unsigned char* gs = st + 3 * kStateBytes + w * kGradBytes;
+        if (FMT == PS_GRAD_BF16) {
+          const uint2 q = *reinterpret_cast<const uint2*>(gs + le * 2);
+          float2 f;
+          f = bf2(q.x); g[0] += f.x; g[1] += f.y;
+          f = bf2(q.y); g[2] += f.x; g[3] += f.y;
+        } else if (FMT == PS_GRAD_FP8BLOCK) {
+          const uint32_t q = *reinterpret_cast<const uint32_t*>(gs + le);
+          const unsigned char* base = static_cast<const unsigned char*>(a.grads[w]);
+          const float sc = e8m0(base[npad + ((e0 + le) >> 5)]);  // scales are tiny: straight from global
+          float t[4];
+          fp8x4_to_f32(q, sc, t);
+          g[0] += t[0]; g[1] += t[1]; g[2] += t[2]; g[3] += t[3];
+        } else {
+          const float4 q = *reinterpret_cast<const float4*>(gs + le * 4);
+          g[0] += q.x; g[1] += q.y; g[2] += q.z; g[3] += q.w;
+        }
+      }
+      step<OPT>(p.x, m.x, v.x, g[0] * o.grad_scale, o); step<OPT>(p.y, m.y, v.y, g[1] * o.grad_scale, o);
+      step<OPT>(p.z, m.z, v.z, g[2] * o.grad_scale, o); step<OPT>(p.w, m.w, v.w, g[3] * o.grad_scale, o);
+      const size_t e = e0 + le;
+      stf4(a.master + e, p);
+      stf4(a.m + e, m);
+      if (OPT == PS_OPT_ADAMW) stf4(a.v + e, v);
+      const uint32_t lo = pk(p.x, p.y), hi = pk(p.z, p.w);
+#pragma unroll 1
+      for (int k = 0; k < a.body_outs; ++k) st8(static_cast<char*>(a.outs[k]) + e * 2, lo, hi);
+      if (a.mc_out) multimem_st8(static_cast<char*>(a.mc_out) + e * 2, lo, hi);
+    }
+    __syncthreads();  // every thread has read stage s (and the stage of tile j-1 long before)
+    if (tid == 0 && j + kTmaStagesU - 1 < mine) issue(j + kTmaStagesU - 1);
+  }
+
+  // elements after the last full tile: scalar path, CTA 0
+  if (blockIdx.x == 0) {
+    for (size_t e = n_tiles * kTile + tid; e < a.n; e += kThreads) {
+      float p = a.master[e], m = a.m[e], v = OPT == PS_OPT_ADAMW ? a.v[e] : 0.f;
+      const float g = gather_one<FMT>(a, e) * o.grad_scale;
+      step<OPT>(p, m, v, g, o);
+      a.master[e] = p;
+      a.m[e] = m;
+      if (OPT == PS_OPT_ADAMW) a.v[e] = v;
+      for (int k = 0; k < a.num_outs; ++k) static_cast<__nv_bfloat16*>(a.outs[k])[e] = __float2bfloat16_rn(p);
+    }
+  }
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(kThreads)
 k_sum(float* __restrict__ out, const UpdateDev a, float scale, int accumulate) {
@@ -398,6 +558,50 @@ int GridFor(size_t items, int max_ctas, int per_sm) {
   return want < 1 ? 1 : static_cast<int>(want);
 }
 
+bool UseTma() {
+  static const bool on = [] {
+    const char* v = getenv("PS_UPDATE_TMA");
+    return v != nullptr && atoi(v) != 0;
+  }();
+  return on;
+}
+
+template <int FMT, int OPT>
+bool LaunchUpdateTmaImpl(const UpdateDev& d, const ps_opt_params& o, bool out_f32, int max_ctas, cudaStream_t st) {
+  if (!UseTma() || out_f32) return false;
+  const size_t tiles = d.n / kTile;
+  const int stage = 3 * kTile * 4 + d.num_grads * GradTileBytes<FMT>();
+  const int smem = kTmaStagesU * stage;
+  if (tiles < 4 || smem > 220 * 1024) return false;
+  // cp.async.bulk needs 16-byte aligned sources (landing slots are 512-byte aligned, state is cudaMalloc'ed)
+  if ((reinterpret_cast<uintptr_t>(d.master) | reinterpret_cast<uintptr_t>(d.m) |
+       reinterpret_cast<uintptr_t>(d.v)) & 15) {
+    return false;
+  }
+  for (int w = 0; w < d.num_grads; ++w) {
+    if (reinterpret_cast<uintptr_t>(d.grads[w]) & 15) return false;
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(k_update_tma<FMT, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_set = true;
+  }
+  int grid = static_cast<int>(tiles < static_cast<size_t>(kNumSMs) ? tiles : kNumSMs);
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  k_update_tma<FMT, OPT><<<grid, kThreads, smem, st>>>(d, o);
+  return true;
+}
+
+/*! \brief true if the TMA flavour took the launch (bf16 outputs, enough full tiles, stage fits) */
+template <int FMT, int OPT>
+bool LaunchUpdateTma(const UpdateDev& d, const ps_opt_params& o, bool out_f32, int max_ctas, cudaStream_t st) {
+  if constexpr (FMT == PS_GRAD_MC_BF16) {
+    return false;  // the switch does the reduction inside the load; nothing to stage
+  } else {
+    return LaunchUpdateTmaImpl<FMT, OPT>(d, o, out_f32, max_ctas, st);
+  }
+}
+
 bool UseX2() {
   static const bool on = [] {
     const char* v = getenv("PS_UPDATE_X2");
@@ -409,6 +613,7 @@ bool UseX2() {
 template <int FMT, int OPT>
 void LaunchUpdate(const UpdateDev& d, const ps_opt_params& o, bool out_f32, int grid,
                   cudaStream_t st) {
+  if (LaunchUpdateTma<FMT, OPT>(d, o, out_f32, grid, st)) return;
   if (UseX2()) {
     if (out_f32) k_update_x2<FMT, OPT, true><<<grid, kThreads, 0, st>>>(d, o);
     else k_update_x2<FMT, OPT, false><<<grid, kThreads, 0, st>>>(d, o);
