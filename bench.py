@@ -52,6 +52,9 @@ def parse_args():
                     help="cpu: self-check of this script's control flow on a GPU-less box (shm van, host "
                          "engine, host clock); its numbers are not benchmark results")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-native", action="store_true",
+                    help="also time the end-to-end round through KVWorker.staged_push_pull (the H2D / push / "
+                         "pull / D2H pipeline in one native call instead of a Python loop)")
     ap.add_argument("--sweep", default="", help="comma-separated extra message sizes (bytes) to report")
     # llama
     ap.add_argument("--seq-len", type=int, default=8192)
@@ -267,6 +270,14 @@ def run_pushpull(args, dist: Dist) -> dict:
         e2e = {"value": payload * e2e_steps / (ms2 * 1e-3) / 1e9, "unit": "GB/s",
                "h2d_bytes_per_step": int(args.len) * total_keys * W,
                "d2h_bytes_per_step": int(args.len) * total_keys * W, "steps": e2e_steps}
+        if args.e2e_native:
+            def native_round():
+                kv.staged_push_pull(keys, vals, host_in, host_out)
+            if ctx.is_worker:
+                native_round()
+                assert all(int(h[0]) == 2 and int(h[-1]) == 2 for h in host_out), "staged round lost data"
+            ms3, _ = timed(native_round, e2e_steps)
+            e2e["native_call"] = {"value": payload * e2e_steps / (ms3 * 1e-3) / 1e9, "unit": "GB/s"}
 
     fused = None
     if args.fused_pushpull:

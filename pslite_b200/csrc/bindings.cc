@@ -13,6 +13,7 @@
  */
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
+#include <c10/cuda/CUDAGuard.h>
 #include <c10/cuda/CUDAStream.h>
 
 #include <cuda_runtime.h>
@@ -208,6 +209,74 @@ class PyKVWorker {
   void wait_all(const std::vector<int>& ts) {
     py::gil_scoped_release nogil;
     for (int t : ts) kv_->Wait(t);
+  }
+
+  /*!
+   * \brief a whole staged round in one call: for every key copy this step's input from (pinned) host
+   *        memory into its device tensor, push it, pull the result back into the same tensor and copy
+   *        that to host memory. Software-pipelined over the keys on two streams: the H2D copy of key
+   *        k+1, the push + pull of key k and the D2H copy of key k-1 overlap (PCIe is full duplex);
+   *        a push waits for the event of its own H2D copy only. Returns when `host_out` is complete.
+   *        On a GPU-less build of the job (shm van) the "device" tensors are host tensors and the
+   *        copies are plain memcpys: same control flow.
+   */
+  void staged_push_pull(const std::vector<uint64_t>& keys, std::vector<torch::Tensor> dev,
+                        const std::vector<torch::Tensor>& host_in, std::vector<torch::Tensor> host_out, int cmd,
+                        int codec, float scale) {
+    const size_t n = keys.size();
+    TORCH_CHECK(dev.size() == n && host_in.size() == n && host_out.size() == n, "list lengths differ");
+    if (n == 0) return;
+    const bool cuda = dev[0].is_cuda();
+    for (size_t i = 0; i < n; ++i) {
+      TORCH_CHECK(dev[i].is_cuda() == cuda && !host_in[i].is_cuda() && !host_out[i].is_cuda(),
+                  "dev tensors on one device kind, host_in / host_out in host memory");
+      TORCH_CHECK(dev[i].nbytes() == host_in[i].nbytes() && dev[i].nbytes() == host_out[i].nbytes(),
+                  "size mismatch at position ", i);
+    }
+    py::gil_scoped_release nogil;
+    at::NoGradGuard no_grad;
+    std::vector<int> pushes(n), pulls(n);
+    c10::optional<c10::cuda::CUDAStream> h2d, d2h;
+    if (cuda) {
+      const auto idx = static_cast<c10::DeviceIndex>(dev[0].get_device());
+      h2d = c10::cuda::getStreamFromPool(false, idx);
+      d2h = c10::cuda::getStreamFromPool(false, idx);
+      // the device tensors may have been written on the caller's stream
+      cudaEvent_t ready = RecordOnCurrentStream(idx);
+      cudaStreamWaitEvent(h2d->stream(), ready, 0);
+      cudaEventDestroy(ready);
+    }
+    {
+      c10::optional<c10::cuda::CUDAStreamGuard> guard;
+      if (cuda) guard.emplace(*h2d);
+      for (size_t i = 0; i < n; ++i) {
+        dev[i].copy_(host_in[i], /*non_blocking=*/true);
+        SArray<char> view = ViewOf(dev[i]);
+        SendOpts opts;
+        opts.codec = codec;
+        opts.scale = scale;
+        cudaEvent_t ev = cuda ? RecordOnCurrentStream(dev[i].get_device()) : nullptr;
+        opts.wait_event = ev;
+        auto cb = ev ? KVWorker<char>::Callback([ev]() { cudaEventDestroy(ev); }) : KVWorker<char>::Callback();
+        pushes[i] = kv_->ZPush(OneKey(keys[i]), view, OneLen(view.size()), cmd, cb, opts);
+        auto* dst = new SArray<char>(view);
+        auto* len = new SArray<int>(OneLen(dst->size()));
+        pulls[i] = kv_->ZPull(OneKey(keys[i]), dst, len, cmd, [dst, len]() {
+          delete dst;
+          delete len;
+        });
+      }
+    }
+    {
+      c10::optional<c10::cuda::CUDAStreamGuard> guard;
+      if (cuda) guard.emplace(*d2h);
+      for (size_t i = 0; i < n; ++i) {
+        kv_->Wait(pulls[i]);  // the server's copy into dev[i] has completed
+        host_out[i].copy_(dev[i], /*non_blocking=*/true);
+      }
+    }
+    for (size_t i = 0; i < n; ++i) kv_->Wait(pushes[i]);
+    if (cuda) d2h->synchronize();
   }
 
  private:
@@ -495,7 +564,10 @@ PYBIND11_MODULE(_C, m) {
       .def("push_pull_batch", &PyKVWorker::push_pull_batch, py::arg("keys"), py::arg("tensors"),
            py::arg("cmd") = 0, py::arg("codec") = 0, py::arg("scale") = 1.0f,
            py::arg("order_after_current_stream") = true, py::arg("push") = true,
-           py::arg("pull") = true);
+           py::arg("pull") = true)
+      .def("staged_push_pull", &PyKVWorker::staged_push_pull, py::arg("keys"), py::arg("dev"),
+           py::arg("host_in"), py::arg("host_out"), py::arg("cmd") = 0, py::arg("codec") = 0,
+           py::arg("scale") = 1.0f);
 
   py::class_<PyKVServer>(m, "KVServer")
       .def(py::init<int>(), py::arg("app_id") = 0)

@@ -28,6 +28,9 @@ echo "== 3c. nccl van"
 PSLITE_TEST_NCCL_VAN=1 timeout 400 python -m pytest tests/test_multigpu.py -m gpu -q -k nccl 2>&1 | tail -n 15
 echo "== 4. bench N=1"
 timeout 400 python bench.py --steps 20 --warmup 3 2>gpurun_out/v_b1.err | tee gpurun_out/v_bench1.json | tail -c 900
+echo "== 4a. PCIe bound of the end-to-end pass, then the pass through the native staged call"
+timeout 120 python scripts/pcie_probe.py | tee gpurun_out/v_pcie.json
+timeout 400 python bench.py --steps 20 --warmup 3 --e2e-native 2>gpurun_out/v_b1n.err | tee gpurun_out/v_bench1_native.json | tail -c 700
 echo "== 4. bench N=1 with launch coalescing"
 PS_COALESCE_LAUNCHES=1 timeout 400 python bench.py --steps 20 --warmup 3 --no-e2e 2>gpurun_out/v_b1c.err | tee gpurun_out/v_bench1_coalesce.json | tail -c 600
 echo "== 4. bench N=1 with the fused push-pull operation reported as well"

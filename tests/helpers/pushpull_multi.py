@@ -20,6 +20,7 @@ def main():
     van, length, kps, rounds = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     topo = sys.argv[5] if len(sys.argv) > 5 else "split"
     fused = os.environ.get("PSLITE_TEST_PUSHPULL", "0") == "1"  # one ZPushPull per key instead of ZPush + ZPull
+    staged = os.environ.get("PSLITE_TEST_STAGED", "0") == "1"  # KVWorker.staged_push_pull rounds
     rank = int(os.environ["RANK"])
     dist.init_process_group("gloo")
     C = pslite_b200.native()
@@ -39,8 +40,16 @@ def main():
             kv.wait(kv.push(keys[k], vals[k], order_after_current_stream=False))
     dist.barrier()
     if ctx.is_worker:
+        host_in = [torch.full((length,), 1 + ctx.worker_rank, dtype=torch.uint8) for _ in range(total)] if staged else None
+        host_out = [torch.zeros(length, dtype=torch.uint8) for _ in range(total)] if staged else None
         for _ in range(rounds):
-            if fused:
+            if staged:
+                for h in host_out:
+                    h.zero_()
+                kv.staged_push_pull(keys, vals, host_in, host_out)
+                for k in range(total):  # the pulled bytes reached host memory before the call returned
+                    assert torch.equal(host_out[k], vals[k]), f"key {k}: host copy differs from the pulled tensor"
+            elif fused:
                 ts = [kv.push_pull(keys[k], vals[k], vals[k], order_after_current_stream=False) for k in range(total)]
                 for t in ts:
                     kv.wait(t)

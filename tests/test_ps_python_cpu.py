@@ -85,7 +85,7 @@ def test_trainer_logic_on_cpu(native):
 
 @pytest.mark.parametrize("nproc,topo,length,async_copies", [
     (8, "split", 4096, "1"), (4, "split", 1 << 20, "1"), (4, "joint", 65536, "1"), (4, "split", 4096, "0")])
-def test_bench_loop_many_peers(native, nproc, topo, length, async_copies, coalesce="0", fused="0"):
+def test_bench_loop_many_peers(native, nproc, topo, length, async_copies, coalesce="0", fused="0", staged="0"):
     """bench.py's push_pull_batch loop under torchrun with several workers AND servers, over the
     one-sided van with *asynchronous* copies (PS_SHM_ASYNC: copies complete later, as kernels
     on a CUDA stream do). Descriptors for different peers then share completion batches — the
@@ -93,11 +93,11 @@ def test_bench_loop_many_peers(native, nproc, topo, length, async_copies, coales
     helper = os.path.join(HERE, "helpers", "pushpull_multi.py")
     env = dict(os.environ)
     env.update({"PSLITE_NO_AUTOBUILD": "1", "PS_SHM_ASYNC": async_copies, "OMP_NUM_THREADS": "1",
-                "PS_COALESCE_LAUNCHES": coalesce, "PSLITE_TEST_PUSHPULL": fused})
+                "PS_COALESCE_LAUNCHES": coalesce, "PSLITE_TEST_PUSHPULL": fused, "PSLITE_TEST_STAGED": staged})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", str(free_port()), helper, "shm", str(length), "10",
            "10", topo]
-    for attempt in range(2 if nproc == 8 and coalesce == "0" and fused == "0" else 1):  # the hang was probabilistic
+    for attempt in range(2 if nproc == 8 and coalesce == "0" and fused == "0" and staged == "0" else 1):  # the hang was probabilistic
         p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=150)
         assert p.returncode == 0 and "PASS" in p.stdout, (p.stdout + p.stderr)[-3000:]
 
@@ -110,3 +110,8 @@ def test_bench_loop_with_launch_coalescing(native):
 def test_bench_loop_with_fused_push_pull(native):
     """one KVWorker::ZPushPull per key (request carries the push, the single reply the pulled values)"""
     test_bench_loop_many_peers(native, 8, "split", 65536, "1", fused="1")
+
+
+def test_bench_loop_with_staged_rounds(native):
+    """KVWorker.staged_push_pull: host -> tensor -> push -> pull -> host for every key in one call"""
+    test_bench_loop_many_peers(native, 4, "split", 65536, "1", staged="1")

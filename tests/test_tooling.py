@@ -78,7 +78,8 @@ REQUIRED_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per
                  "scaling", "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches"}
 
 
-@pytest.mark.parametrize("extra", [[], ["--metric", "llama", "--model", "tiny", "--seq-len", "64"]])
+@pytest.mark.parametrize("extra", [["--e2e-native", "--fused-pushpull"],
+                                   ["--metric", "llama", "--model", "tiny", "--seq-len", "64"]])
 def test_bench_script_control_flow_on_cpu(extra):
     """bench.py --device cpu walks the same code as a GPU run (warm-up, timed region, end-to-end
     pass, JSON line) over the shm van and the host engine: a typo in the script must not wait for
@@ -92,6 +93,8 @@ def test_bench_script_control_flow_on_cpu(extra):
     assert REQUIRED_KEYS <= set(line), REQUIRED_KEYS - set(line)
     assert line["value"] > 0 and line["e2e"]["value"] > 0
     assert line["e2e"]["h2d_bytes_per_step"] > 0 and line["e2e"]["d2h_bytes_per_step"] > 0
+    if "--e2e-native" in extra:
+        assert line["e2e"]["native_call"]["value"] > 0 and line["fused_pushpull"]["value"] > 0
 
 
 def test_bench_script_multi_process_on_cpu():
@@ -100,7 +103,7 @@ def test_bench_script_multi_process_on_cpu():
 
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr",
            "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "bench.py"), "--device", "cpu",
-           "--gpus", "4", "--steps", "3", "--warmup", "3", "--len", "65536", "--keys-per-server", "4"]
+           "--gpus", "4", "--steps", "3", "--warmup", "3", "--len", "65536", "--keys-per-server", "4", "--e2e-native"]
     env = dict(os.environ, PSLITE_NO_AUTOBUILD="1", CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1")
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
