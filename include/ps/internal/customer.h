@@ -25,6 +25,7 @@
 #include <utility>
 #include <vector>
 #include "ps/internal/message.h"
+#include "ps/internal/spin_mutex.h"
 #include "ps/internal/threadsafe_queue.h"
 
 namespace ps {
@@ -81,8 +82,11 @@ class Customer {
     int ts = -1;
     int expected = 0;
     int received = 0;
+    int waiters = 0;  // threads blocked in WaitRequest(ts): only they are woken, and only on completion
   };
   Slot* Find(int ts);  // caller holds tracker_mu_
+  /*! \brief count `num` responses for `ts`; wakes the request's waiters when it completes */
+  void CountResponse(int ts, int num);
   void Deliver(const Message& m);
   void Receiving();
 
@@ -96,10 +100,12 @@ class Customer {
   ThreadsafeQueue<Message> inbox_;
   std::unique_ptr<std::thread> recv_thread_;
 
-  std::mutex tracker_mu_;
-  std::condition_variable tracker_cv_;
+  SpinMutex tracker_mu_;
+  std::condition_variable_any tracker_cv_;
   std::vector<Slot> ring_;
   int next_ts_ = 0;
+  /*! \brief requests completed so far: lets a waiter poll without taking tracker_mu_ */
+  std::atomic<uint64_t> completions_{0};
 };
 
 }  // namespace ps

@@ -20,6 +20,7 @@
 #include <utility>
 #include "ps/internal/env.h"
 #include "ps/internal/utils.h"
+#include "ps/internal/spin_mutex.h"
 #include "ps/internal/spsc_queue.h"
 
 namespace ps {
@@ -47,7 +48,7 @@ class ThreadsafeQueue {
       return;
     }
     {
-      std::lock_guard<std::mutex> lk(mu_);
+      std::lock_guard<SpinMutex> lk(mu_);
       items_.push_back(std::move(v));
       count_.fetch_add(1, std::memory_order_release);
     }
@@ -81,7 +82,7 @@ class ThreadsafeQueue {
         CpuRelax();
       }
     }
-    std::unique_lock<std::mutex> lk(mu_);
+    std::unique_lock<SpinMutex> lk(mu_);
     cv_.wait(lk, [this] { return !items_.empty(); });
     *out = std::move(items_.front());
     items_.pop_front();
@@ -92,7 +93,7 @@ class ThreadsafeQueue {
   bool TryPop(T* out) {
     if (lockless_) return ring_->try_pop(out);
     if (count_.load(std::memory_order_acquire) == 0) return false;
-    std::lock_guard<std::mutex> lk(mu_);
+    std::lock_guard<SpinMutex> lk(mu_);
     if (items_.empty()) return false;
     *out = std::move(items_.front());
     items_.pop_front();
@@ -102,14 +103,11 @@ class ThreadsafeQueue {
 
   size_t Size() {
     if (lockless_) return ring_->size();
-    std::lock_guard<std::mutex> lk(mu_);
+    std::lock_guard<SpinMutex> lk(mu_);
     return items_.size();
   }
 
- private:
-  static constexpr size_t kRingCapacity = 32768;
-  bool lockless_ = false;
-  long long spin_ns_ = 1000;
+  /*! \brief one polite busy-wait step */
   static void CpuRelax() {
 #if defined(__x86_64__) || defined(__i386__)
     __builtin_ia32_pause();
@@ -117,11 +115,16 @@ class ThreadsafeQueue {
     std::this_thread::yield();
 #endif
   }
-  std::mutex mu_;
-  std::condition_variable cv_;
+
+ private:
+  static constexpr size_t kRingCapacity = 32768;
+  bool lockless_ = false;
+  long long spin_ns_ = 1000;
+  SpinMutex mu_;  // never held for longer than a deque operation
+  std::condition_variable_any cv_;
   std::deque<T> items_;
   std::atomic<size_t> count_{0};  // == items_.size(), readable without the lock
-  int spin_us_ = GetEnv("PS_QUEUE_SPIN_US", 20);
+  int spin_us_ = GetEnv("PS_QUEUE_SPIN_US", 100);
   std::unique_ptr<SPSCQueue<T>> ring_;
   std::atomic_flag push_lock_ = ATOMIC_FLAG_INIT;
 };

@@ -28,6 +28,7 @@
 #include <utility>
 #include <vector>
 #include "ps/base.h"
+#include "ps/internal/spin_mutex.h"
 #include "ps/simple_app.h"
 
 namespace ps {
@@ -213,7 +214,7 @@ class KVWorker : public SimpleApp {
 
   void AddCallback(int timestamp, const Callback& cb) {
     if (!cb) return;
-    std::lock_guard<std::mutex> lk(mu_);
+    std::lock_guard<SpinMutex> lk(mu_);
     callbacks_[timestamp] = cb;
   }
   void RunCallback(int timestamp);
@@ -225,7 +226,7 @@ class KVWorker : public SimpleApp {
 
   std::unordered_map<int, std::vector<KVPairs<Val>>> recv_kvs_;
   std::unordered_map<int, Callback> callbacks_;
-  std::mutex mu_;
+  SpinMutex mu_;  // callbacks_ / recv_kvs_: touched once per request and per response
   Slicer slicer_;
   int instance_idx_;
 };
@@ -556,7 +557,7 @@ void KVWorker<Val>::Process(const Message& msg) {
     kvs.keys = msg.data[0];
     kvs.vals = msg.data[1];
     if (msg.data.size() > 2) kvs.lens = msg.data[2];
-    std::lock_guard<std::mutex> lk(mu_);
+    std::lock_guard<SpinMutex> lk(mu_);
     recv_kvs_[ts].push_back(kvs);
   }
   // the tracker counts this response *after* the handler returns, hence the -1
@@ -567,7 +568,7 @@ template <typename Val>
 void KVWorker<Val>::RunCallback(int timestamp) {
   Callback cb;
   {
-    std::lock_guard<std::mutex> lk(mu_);
+    std::lock_guard<SpinMutex> lk(mu_);
     auto it = callbacks_.find(timestamp);
     if (it == callbacks_.end()) return;
     cb = std::move(it->second);
@@ -585,7 +586,7 @@ int KVWorker<Val>::Pull_(const SArray<Key>& keys, C* vals, D* lens, int cmd, con
   AddCallback(ts, [this, ts, keys, vals, lens, cb]() mutable {
     std::vector<KVPairs<Val>> parts;
     {
-      std::lock_guard<std::mutex> lk(mu_);
+      std::lock_guard<SpinMutex> lk(mu_);
       auto it = recv_kvs_.find(ts);
       if (it != recv_kvs_.end()) {
         parts.swap(it->second);

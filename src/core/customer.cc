@@ -6,6 +6,7 @@
 #include <chrono>
 #include <limits>
 #include "ps/internal/postoffice.h"
+#include "core/event_trace.h"
 
 namespace ps {
 
@@ -57,7 +58,7 @@ int Customer::NewRequest(int recver, int num_expected) {
     const bool is_group = recver < 8;
     groups = is_group ? std::max(1, members / postoffice_->group_size()) : members;
   }
-  std::lock_guard<std::mutex> lk(tracker_mu_);
+  std::lock_guard<SpinMutex> lk(tracker_mu_);
   // Meta::kEmpty (32767) means "no timestamp" in several places: never hand it out (the
   // reference does, and its resender then aborts on the 32768th request of a customer)
   if (next_ts_ == Meta::kEmpty) ++next_ts_;
@@ -82,53 +83,85 @@ int Customer::NewRequest(int recver, int num_expected) {
 }
 
 void Customer::WaitRequest(int timestamp) {
-  std::unique_lock<std::mutex> lk(tracker_mu_);
+  EventTrace::Mark("wait", timestamp);
+  std::unique_lock<SpinMutex> lk(tracker_mu_);
   auto done = [this, timestamp] {
     Slot* s = Find(timestamp);
     // a recycled slot means the request completed long ago
     return s == nullptr || s->received >= s->expected;
   };
+  if (done()) return;
+  // responses of a busy connection arrive microseconds apart: look a few more times before
+  // paying for a sleep and a wake-up (PS_QUEUE_SPIN_US, shared with the inbox)
+  static const int spin_us = GetEnv("PS_QUEUE_SPIN_US", 100);
+  if (spin_us > 0) {
+    // poll the completion counter, not the tracker: the customer thread needs tracker_mu_ for
+    // every response and must not fight this thread for it
+    const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us);
+    uint64_t seen = completions_.load(std::memory_order_acquire);
+    lk.unlock();
+    for (;;) {
+      for (int i = 0; i < 16; ++i) ThreadsafeQueue<Message>::CpuRelax();
+      const uint64_t now = completions_.load(std::memory_order_acquire);
+      if (now != seen) {
+        seen = now;
+        lk.lock();
+        if (done()) return;
+        lk.unlock();
+      }
+      if (std::chrono::steady_clock::now() >= until) break;
+    }
+    lk.lock();
+    if (done()) return;
+  }
+  // responses wake only the threads that wait for *their* request (a round of the benchmark
+  // has 80 requests in flight: waking the application thread for each costs two system calls)
+  if (Slot* s = Find(timestamp)) ++s->waiters;
   // a request that never completes is the usual face of a transport bug or a dead peer: say
   // which one it is instead of hanging silently (PS_WAIT_WARN_S seconds, 0 = never)
   static const int warn_s = GetEnv("PS_WAIT_WARN_S", 60);
   if (warn_s <= 0) {
     tracker_cv_.wait(lk, done);
-    return;
+  } else {
+    while (!tracker_cv_.wait_for(lk, std::chrono::seconds(warn_s), done)) {
+      Slot* s = Find(timestamp);
+      LOG(WARNING) << "app " << app_id_ << " customer " << customer_id_ << " on node "
+                   << postoffice_->van()->my_node().id << ": request " << timestamp << " still waiting after "
+                   << warn_s << " s (" << (s ? s->received : -1) << " of " << (s ? s->expected : -1)
+                   << " responses)";
+    }
   }
-  while (!tracker_cv_.wait_for(lk, std::chrono::seconds(warn_s), done)) {
-    Slot* s = Find(timestamp);
-    LOG(WARNING) << "app " << app_id_ << " customer " << customer_id_ << " on node "
-                 << postoffice_->van()->my_node().id << ": request " << timestamp << " still waiting after "
-                 << warn_s << " s (" << (s ? s->received : -1) << " of " << (s ? s->expected : -1)
-                 << " responses)";
-  }
+  if (Slot* s = Find(timestamp)) --s->waiters;
 }
 
 int Customer::NumResponse(int timestamp) {
-  std::lock_guard<std::mutex> lk(tracker_mu_);
+  std::lock_guard<SpinMutex> lk(tracker_mu_);
   Slot* s = Find(timestamp);
   return s ? s->received : 0;
 }
 
-void Customer::AddResponse(int timestamp, int num) {
+void Customer::CountResponse(int ts, int num) {
+  bool wake = false;
   {
-    std::lock_guard<std::mutex> lk(tracker_mu_);
-    Slot* s = Find(timestamp);
-    if (s) s->received += num;
+    std::lock_guard<SpinMutex> lk(tracker_mu_);
+    Slot* s = Find(ts);
+    if (s) {
+      s->received += num;
+      if (s->received >= s->expected) {
+        completions_.fetch_add(1, std::memory_order_release);
+        wake = s->waiters > 0;
+      }
+    }
   }
-  tracker_cv_.notify_all();
+  if (wake) tracker_cv_.notify_all();
 }
 
+void Customer::AddResponse(int timestamp, int num) { CountResponse(timestamp, num); }
+
 void Customer::Deliver(const Message& m) {
+  EventTrace::Mark("handle", m.meta.timestamp, m.meta.request * 2 + m.meta.push);
   recv_handle_(m);
-  if (!m.meta.request) {
-    {
-      std::lock_guard<std::mutex> lk(tracker_mu_);
-      Slot* s = Find(m.meta.timestamp);
-      if (s) ++s->received;
-    }
-    tracker_cv_.notify_all();
-  }
+  if (!m.meta.request) CountResponse(m.meta.timestamp, 1);
 }
 
 void Customer::Accept(const Message& recved) {

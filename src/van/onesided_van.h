@@ -74,7 +74,7 @@ class OneSidedVan : public TcpVan {
       PS_VLOG(1) << type_ << " van " << my_node_.id << ": " << coalesced_copies_.load() << " copies in "
                  << coalesced_batches_.load() << " coalesced batches";
     }
-    std::lock_guard<std::mutex> lk(rv_mu_);
+    std::lock_guard<SpinMutex> lk(rv_mu_);
     push_slots_.clear();
     landing_.clear();
     peer_regions_.clear();
@@ -93,7 +93,7 @@ class OneSidedVan : public TcpVan {
       TcpVan::RegisterRecvBuffer(msg);  // plain host buffer: two-sided path
       return;
     }
-    std::lock_guard<std::mutex> lk(rv_mu_);
+    std::lock_guard<SpinMutex> lk(rv_mu_);
     registered_slots_[std::make_pair(msg.meta.sender, msg.meta.key)] = msg.data[1];
   }
 
@@ -109,7 +109,7 @@ class OneSidedVan : public TcpVan {
 
   /*! \brief local address of `mem` inside a region node `peer` announced, or null */
   void* ResolvePeerMem(int peer, const MemRef& mem) override {
-    std::lock_guard<std::mutex> lk(rv_mu_);
+    std::lock_guard<SpinMutex> lk(rv_mu_);
     auto it = peer_regions_.find(std::make_pair(peer, mem.region));
     return it == peer_regions_.end() ? nullptr : it->second + mem.offset;
   }
@@ -222,7 +222,7 @@ class OneSidedVan : public TcpVan {
 
   /*! \brief id of the exported region with d->base (assigned on first sight); fills d */
   int32_t RegionIdFor(RegionDesc* d) {
-    std::lock_guard<std::mutex> lk(rv_mu_);
+    std::lock_guard<SpinMutex> lk(rv_mu_);
     auto it = region_of_base_.find(d->base);
     if (it == region_of_base_.end()) {
       const int32_t id = static_cast<int32_t>(my_regions_.size());
@@ -240,12 +240,12 @@ class OneSidedVan : public TcpVan {
 
   char* ImportPeerRegion(int peer, const RegionDesc& d) {
     {
-      std::lock_guard<std::mutex> lk(rv_mu_);
+      std::lock_guard<SpinMutex> lk(rv_mu_);
       auto it = peer_regions_.find(std::make_pair(peer, d.region));
       if (it != peer_regions_.end()) return it->second;
     }
     char* base = static_cast<char*>(domain_->Import(d));
-    std::lock_guard<std::mutex> lk(rv_mu_);
+    std::lock_guard<SpinMutex> lk(rv_mu_);
     peer_regions_[std::make_pair(peer, d.region)] = base;
     return base;
   }
@@ -298,7 +298,7 @@ class OneSidedVan : public TcpVan {
 
   /*! \brief landing slot at `recver` for `key`; rendezvous on first use or growth */
   Slot AcquirePushSlot(int recver, uint64_t key, uint64_t bytes) {
-    std::unique_lock<std::mutex> lk(rv_mu_);
+    std::unique_lock<SpinMutex> lk(rv_mu_);
     const PeerKey pk(recver, key);
     auto it = push_slots_.find(pk);
     if (it != push_slots_.end() && it->second.capacity >= bytes &&
@@ -333,7 +333,7 @@ class OneSidedVan : public TcpVan {
     char* ptr = nullptr;
     uint64_t cap = 0;
     {
-      std::lock_guard<std::mutex> lk(rv_mu_);
+      std::lock_guard<SpinMutex> lk(rv_mu_);
       auto reg = registered_slots_.find(pk);
       auto have = landing_.find(pk);
       if (reg != registered_slots_.end()) {
@@ -359,7 +359,7 @@ class OneSidedVan : public TcpVan {
     CHECK(domain_->Export(ptr, &d)) << "landing slot is not exportable";
     RegionIdFor(&d);
     {
-      std::lock_guard<std::mutex> lk(rv_mu_);
+      std::lock_guard<SpinMutex> lk(rv_mu_);
       landing_[pk] = std::make_pair(ptr, cap);
     }
     Message rep;
@@ -387,7 +387,7 @@ class OneSidedVan : public TcpVan {
       s.region = d.region;
       s.offset = m.meta.addr;
       {
-        std::lock_guard<std::mutex> lk(rv_mu_);
+        std::lock_guard<SpinMutex> lk(rv_mu_);
         push_slots_[PeerKey(m.meta.sender, m.meta.key)] = s;
       }
       rv_cv_.notify_all();
@@ -407,7 +407,7 @@ class OneSidedVan : public TcpVan {
     const int32_t id = RegionIdFor(&d);
     bool need_announce = false;
     {
-      std::lock_guard<std::mutex> lk(rv_mu_);
+      std::lock_guard<SpinMutex> lk(rv_mu_);
       need_announce = announced_.insert(std::make_pair(recver, id)).second;
     }
     if (need_announce) {
@@ -438,7 +438,7 @@ class OneSidedVan : public TcpVan {
     const int recver = msg.meta.recver;
     char* base = nullptr;
     {
-      std::lock_guard<std::mutex> lk(rv_mu_);
+      std::lock_guard<SpinMutex> lk(rv_mu_);
       auto it = peer_regions_.find(std::make_pair(recver, msg.meta.mem.region));
       CHECK(it != peer_regions_.end()) << "pull destination region " << msg.meta.mem.region
                                        << " of node " << recver << " was never announced";
@@ -493,7 +493,7 @@ class OneSidedVan : public TcpVan {
     char* ptr = nullptr;
     if (msg->meta.request && msg->meta.push) {
       if (mem.region == kSymmetricRegion) return;  // the handler resolves the offset itself
-      std::lock_guard<std::mutex> lk(rv_mu_);
+      std::lock_guard<SpinMutex> lk(rv_mu_);
       CHECK_LT(static_cast<size_t>(mem.region), my_regions_.size());
       ptr = reinterpret_cast<char*>(my_regions_[mem.region].base + mem.offset);
     } else if (!msg->meta.request && !msg->meta.push) {
@@ -677,8 +677,8 @@ class OneSidedVan : public TcpVan {
   std::unique_ptr<MemDomain> domain_;
   std::string type_;
 
-  std::mutex rv_mu_;
-  std::condition_variable rv_cv_;
+  SpinMutex rv_mu_;  // slot / region tables: looked up on every push, pull reply and received descriptor
+  std::condition_variable_any rv_cv_;
   std::map<PeerKey, Slot> push_slots_;                          // sender: where my pushes land
   std::map<PeerKey, std::pair<char*, uint64_t>> landing_;       // receiver: slots I handed out
   std::map<PeerKey, SArray<char>> registered_slots_;            // receiver: user-registered

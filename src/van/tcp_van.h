@@ -47,6 +47,8 @@
 #include "ps/internal/postoffice.h"
 #include "ps/internal/van.h"
 #include "van/mem_domain.h"
+#include "core/event_trace.h"
+#include "ps/internal/spin_mutex.h"
 #include "van/shm_pipe.h"
 #include "van/shm_util.h"
 
@@ -150,7 +152,7 @@ class TcpVan : public Van {
     direct_pull_ = GetEnv("PS_TCP_DIRECT_PULL", 1) != 0 && GetEnv("PS_RESEND", 0) == 0;
     use_pipes_ = GetEnv("PS_SHM_PIPE", 1) != 0;
     pipe_bytes_ = static_cast<size_t>(GetEnv("PS_SHM_PIPE_KB", 256)) << 10;
-    pipe_spin_us_ = GetEnv("PS_SHM_PIPE_SPIN_US", 50);
+    pipe_spin_us_ = GetEnv("PS_SHM_PIPE_SPIN_US", 200);
     if (use_pipes_) {
       static const int swept = SweepStaleShm("pslb200_");  // rings of processes that were killed
       (void)swept;
@@ -271,7 +273,7 @@ class TcpVan : public Van {
     }
     std::shared_ptr<Peer> old;
     {
-      std::lock_guard<std::mutex> lk(peers_mu_);
+      std::lock_guard<SpinMutex> lk(peers_mu_);
       auto it = peers_.find(node.id);
       if (it != peers_.end()) old = it->second;
       peers_[node.id] = peer;
@@ -303,13 +305,14 @@ class TcpVan : public Van {
 
   /*! \brief serialise one message to its peer (socket, ring or own loopback queue) */
   int SendFrame(Message& msg) {
+    EventTrace::Mark("send_frame", msg.meta.timestamp, msg.meta.request * 2 + msg.meta.push);
     if (msg.meta.mem.region == kEncodedOnHost) msg.meta.mem = MemRef();
     const int recver = msg.meta.recver;
     if (recver == my_node_.id) return Loopback(msg);
 
     std::shared_ptr<Peer> peer;
     {
-      std::lock_guard<std::mutex> lk(peers_mu_);
+      std::lock_guard<SpinMutex> lk(peers_mu_);
       auto it = peers_.find(recver);
       if (it == peers_.end()) {
         LOG(WARNING) << "there is no socket to node " << recver;
@@ -381,7 +384,7 @@ class TcpVan : public Van {
     }
     std::shared_ptr<Peer> peer;
     {
-      std::lock_guard<std::mutex> lk(peers_mu_);
+      std::lock_guard<SpinMutex> lk(peers_mu_);
       auto it = peers_.find(recver);
       if (it == peers_.end()) return -1;
       peer = it->second;
@@ -432,7 +435,10 @@ class TcpVan : public Van {
       if (PollDeferred(msg)) return 1 + static_cast<int>(msg->meta.data_size & 0x3fffffff);
       if (PopLoopback(msg)) return 1 + static_cast<int>(msg->meta.data_size & 0x3fffffff);
       // same-host peers: frames arrive in shared-memory rings (round-robin for fairness)
-      if (int bytes = PollPipes(msg)) return bytes;
+      if (int bytes = PollPipes(msg)) {
+        EventTrace::Mark("recv_frame", msg->meta.timestamp, msg->meta.request * 2 + msg->meta.push);
+        return bytes;
+      }
       // sockets epoll reported readable and that we have not looked at yet; only
       // this thread reads them, so each still holds at least one byte
       while (!ready_fds_.empty()) {
@@ -914,7 +920,7 @@ class TcpVan : public Van {
   void CloseAll() {
     std::lock_guard<std::mutex> ilk(init_mu_);
     {
-      std::lock_guard<std::mutex> lk(peers_mu_);
+      std::lock_guard<SpinMutex> lk(peers_mu_);
       for (auto& kv : peers_) {
         std::lock_guard<std::mutex> plk(kv.second->mu);
         if (kv.second->fd >= 0) close(kv.second->fd);
@@ -975,9 +981,9 @@ class TcpVan : public Van {
   size_t pipe_cursor_ = 0;
   bool use_pipes_ = true;
   size_t pipe_bytes_ = 256u << 10;
-  int pipe_spin_us_ = 50;
+  int pipe_spin_us_ = 200;
   std::deque<int> ready_fds_;      // touched by the receive thread only
-  std::mutex peers_mu_;
+  SpinMutex peers_mu_;  // a map lookup per send
   std::unordered_map<int, std::shared_ptr<Peer>> peers_;
   std::mutex loop_mu_;
   std::deque<Message> loop_q_;
