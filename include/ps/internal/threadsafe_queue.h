@@ -72,15 +72,21 @@ class ThreadsafeQueue {
       }
       return;
     }
-    // stay hot for a moment before sleeping: a producer that finds no sleeper skips the futex
-    // wake (a system call per message otherwise), and the consumer skips the context switch
-    if (spin_us_ > 0 && count_.load(std::memory_order_acquire) == 0) {
-      const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us_);
-      int polls = 0;
-      while (count_.load(std::memory_order_acquire) == 0) {
-        if ((++polls & 63) == 0 && std::chrono::steady_clock::now() >= deadline) break;
-        CpuRelax();
-      }
+    // stay hot for a while before sleeping: a producer that finds no sleeper skips the futex
+    // wake (a system call per message otherwise), and the consumer skips the context switch.
+    // How long is decided by the gaps seen lately (SpinBudget).
+    if (count_.load(std::memory_order_acquire) == 0) {
+      const auto t0 = std::chrono::steady_clock::now();
+      SpinPoll([this] { return count_.load(std::memory_order_acquire) != 0; }, budget_.floor_us(),
+               budget_.window_us());
+      std::unique_lock<SpinMutex> lk(mu_);
+      cv_.wait(lk, [this] { return !items_.empty(); });
+      budget_.Observe(std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0)
+                          .count());
+      *out = std::move(items_.front());
+      items_.pop_front();
+      count_.fetch_sub(1, std::memory_order_release);
+      return;
     }
     std::unique_lock<SpinMutex> lk(mu_);
     cv_.wait(lk, [this] { return !items_.empty(); });
@@ -124,7 +130,7 @@ class ThreadsafeQueue {
   std::condition_variable_any cv_;
   std::deque<T> items_;
   std::atomic<size_t> count_{0};  // == items_.size(), readable without the lock
-  int spin_us_ = GetEnv("PS_QUEUE_SPIN_US", 100);
+  SpinBudget budget_{GetEnv("PS_QUEUE_SPIN_US", 20), GetEnv("PS_SPIN_MAX_US", 1000)};
   std::unique_ptr<SPSCQueue<T>> ring_;
   std::atomic_flag push_lock_ = ATOMIC_FLAG_INIT;
 };

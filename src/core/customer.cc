@@ -92,8 +92,8 @@ void Customer::WaitRequest(int timestamp) {
   };
   if (done()) return;
   // responses of a busy connection arrive microseconds apart: look a few more times before
-  // paying for a sleep and a wake-up (PS_QUEUE_SPIN_US, shared with the inbox)
-  static const int spin_us = GetEnv("PS_QUEUE_SPIN_US", 100);
+  // paying for a sleep and a wake-up (PS_WAIT_SPIN_US)
+  static const int spin_us = GetEnv("PS_WAIT_SPIN_US", 100);
   if (spin_us > 0) {
     // poll the completion counter, not the tracker: the customer thread needs tracker_mu_ for
     // every response and must not fight this thread for it

@@ -25,6 +25,7 @@
 #include <unistd.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdint>
 #include <cstring>
@@ -355,6 +356,7 @@ class ShmDomain : public MemDomain {
       {
         std::lock_guard<std::mutex> lk(q_mu_);
         q_.push_back(op);
+        q_len_.fetch_add(1, std::memory_order_release);
       }
       q_cv_.notify_one();
       Ticket t;
@@ -388,10 +390,21 @@ class ShmDomain : public MemDomain {
   void CopierLoop() {
     std::unique_lock<std::mutex> lk(q_mu_);
     for (;;) {
+      if (q_.empty() && !q_stop_) {
+        // a GPU stream does not go to sleep between kernels: poll for a while so that this
+        // stand-in adds copy latency, not the wake-up latency of an idle host thread
+        lk.unlock();
+        const auto until = std::chrono::steady_clock::now() + std::chrono::milliseconds(2);
+        while (q_len_.load(std::memory_order_acquire) == 0 && std::chrono::steady_clock::now() < until) {
+          std::this_thread::yield();  // the tests run more stand-in threads than the host has cores
+        }
+        lk.lock();
+      }
       q_cv_.wait(lk, [this] { return q_stop_ || !q_.empty(); });
       if (q_.empty()) return;
       AsyncOp* op = q_.front();
       q_.erase(q_.begin());
+      q_len_.fetch_sub(1, std::memory_order_release);
       lk.unlock();
       if (op->n) ps_host_copy(op->dst, op->src, op->n, op->codec, op->scale);
       op->done.store(true, std::memory_order_release);
@@ -409,6 +422,7 @@ class ShmDomain : public MemDomain {
   std::mutex q_mu_;
   std::condition_variable q_cv_;
   std::vector<AsyncOp*> q_;
+  std::atomic<int> q_len_{0};
   bool q_stop_ = false;
   Arena* NewArena(uint64_t bytes) {
     static std::atomic<int> counter{0};

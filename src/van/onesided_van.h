@@ -57,7 +57,7 @@ class OneSidedVan : public TcpVan {
 
   void Start(int customer_id, bool standalone) override {
     {
-      std::lock_guard<std::mutex> lk(cq_mu_);
+      std::lock_guard<SpinMutex> lk(cq_mu_);
       if (!completer_) {
         cq_stop_ = false;
         completer_.reset(new std::thread(&OneSidedVan::CompletionLoop, this));
@@ -602,13 +602,14 @@ class OneSidedVan : public TcpVan {
    */
   int Ordered(Message& msg, Ticket t, const SArray<char>& keep_alive = SArray<char>()) {
     {
-      std::lock_guard<std::mutex> lk(cq_mu_);
+      std::lock_guard<SpinMutex> lk(cq_mu_);
       if (t.event != nullptr || !cq_.empty() || cq_busy_) {
         Pending p;
         p.msg = msg;
         p.ticket = t;
         p.keep_alive = keep_alive;
         cq_.push_back(std::move(p));
+        cq_size_.fetch_add(1, std::memory_order_release);
         cq_cv_.notify_one();
         return 1 + static_cast<int>(msg.meta.data_size & 0x3fffffff);
       }
@@ -617,17 +618,33 @@ class OneSidedVan : public TcpVan {
   }
 
   void CompletionLoop() {
-    std::unique_lock<std::mutex> lk(cq_mu_);
+    std::unique_lock<SpinMutex> lk(cq_mu_);
     std::vector<Pending> batch;
+    // a sleeping thread takes 100+ us to come back on a virtual machine: between the bursts of a
+    // round stay on the CPU as long as the recent gaps suggest before giving it up
+    SpinBudget budget(GetEnv("PS_QUEUE_SPIN_US", 20), GetEnv("PS_SPIN_MAX_US", 1000));
     for (;;) {
+      const auto t0 = std::chrono::steady_clock::now();
+      const bool was_idle = cq_.empty();
+      if (was_idle && !cq_stop_) {
+        lk.unlock();
+        SpinPoll([this] { return cq_size_.load(std::memory_order_acquire) != 0; }, budget.floor_us(),
+                 budget.window_us());
+        lk.lock();
+      }
       cq_cv_.wait(lk, [this] { return cq_stop_ || !cq_.empty(); });
       if (cq_.empty()) {
         if (cq_stop_) return;
         continue;
       }
+      if (was_idle) {
+        budget.Observe(
+            std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count());
+      }
       batch.clear();
       batch.push_back(std::move(cq_.front()));
       cq_.pop_front();
+      cq_size_.fetch_sub(1, std::memory_order_release);
       cq_busy_ = true;
       lk.unlock();
       domain_->Wait(batch[0].ticket);  // payload is globally visible after this
@@ -637,6 +654,7 @@ class OneSidedVan : public TcpVan {
       while (!cq_.empty() && batch.size() < 48 && domain_->Ready(cq_.front().ticket)) {
         batch.push_back(std::move(cq_.front()));
         cq_.pop_front();
+        cq_size_.fetch_sub(1, std::memory_order_release);
       }
       lk.unlock();
       for (size_t i = 1; i < batch.size(); ++i) domain_->Wait(batch[i].ticket);  // recycle tickets
@@ -664,7 +682,7 @@ class OneSidedVan : public TcpVan {
   void StopCompleter() {
     std::unique_ptr<std::thread> t;
     {
-      std::lock_guard<std::mutex> lk(cq_mu_);
+      std::lock_guard<SpinMutex> lk(cq_mu_);
       cq_stop_ = true;
       t.swap(completer_);
     }
@@ -687,8 +705,9 @@ class OneSidedVan : public TcpVan {
   std::map<std::pair<int, int32_t>, char*> peer_regions_;       // (peer, region) -> mapping
   std::set<std::pair<int, int32_t>> announced_;                 // (peer, my region) announced
 
-  std::mutex cq_mu_;
-  std::condition_variable cq_cv_;
+  SpinMutex cq_mu_;
+  std::condition_variable_any cq_cv_;
+  std::atomic<int> cq_size_{0};  // lets the idle completer poll without the lock
   std::deque<Pending> cq_;
   bool cq_stop_ = false;
   bool cq_busy_ = false;

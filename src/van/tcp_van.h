@@ -152,7 +152,6 @@ class TcpVan : public Van {
     direct_pull_ = GetEnv("PS_TCP_DIRECT_PULL", 1) != 0 && GetEnv("PS_RESEND", 0) == 0;
     use_pipes_ = GetEnv("PS_SHM_PIPE", 1) != 0;
     pipe_bytes_ = static_cast<size_t>(GetEnv("PS_SHM_PIPE_KB", 256)) << 10;
-    pipe_spin_us_ = GetEnv("PS_SHM_PIPE_SPIN_US", 200);
     if (use_pipes_) {
       static const int swept = SweepStaleShm("pslb200_");  // rings of processes that were killed
       (void)swept;
@@ -429,6 +428,15 @@ class TcpVan : public Van {
   }
 
   int RecvMsg(Message* msg) override {
+    // busy-poll window of this call: as long as the recent gaps between bursts suggest
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = RecvOne(msg, pipe_budget_.window_us());
+    pipe_budget_.Observe(
+        std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t0).count());
+    return rc;
+  }
+
+  int RecvOne(Message* msg, int spin_window_us) {
     msg->data.clear();
     auto last_activity = std::chrono::steady_clock::now();
     for (;;) {
@@ -454,7 +462,7 @@ class TcpVan : public Van {
         // stay hot for a short while after the last message, then declare ourselves asleep
         // on every ring so that the next writer rings the doorbell
         const auto idle = std::chrono::steady_clock::now() - last_activity;
-        if (idle < std::chrono::microseconds(pipe_spin_us_)) {
+        if (idle < std::chrono::microseconds(spin_window_us)) {
           timeout_ms = 0;
         } else if (!SleepOnPipes()) {
           last_activity = std::chrono::steady_clock::now();
@@ -464,8 +472,13 @@ class TcpVan : public Van {
       if (timeout_ms == 0 && (++spin_polls_ & 15) != 0) {
         // busy phase: the rings and the loopback queue are checked every pass, the sockets
         // (control traffic, doorbells, new connections) only every 16th: epoll_wait is a
-        // system call even when it returns at once
-        CpuRelax();
+        // system call even when it returns at once. Past the floor window the polling turns
+        // polite (sched_yield): a thread with real work must get this CPU if it needs one
+        if (std::chrono::steady_clock::now() - last_activity < std::chrono::microseconds(pipe_budget_.floor_us())) {
+          CpuRelax();
+        } else {
+          std::this_thread::yield();
+        }
         continue;
       }
       struct epoll_event evs[16];
@@ -663,6 +676,7 @@ class TcpVan : public Van {
   }
   /*! \brief flag every ring "reader asleep"; false (flags cleared) if one has data after all */
   bool SleepOnPipes() {
+    EventTrace::Mark("recv_sleep", pipe_budget_.window_us());
     for (int fd : pipe_fds_) {
       auto it = inbound_.find(fd);
       if (it == inbound_.end() || !it->second->pipe) continue;
@@ -981,7 +995,7 @@ class TcpVan : public Van {
   size_t pipe_cursor_ = 0;
   bool use_pipes_ = true;
   size_t pipe_bytes_ = 256u << 10;
-  int pipe_spin_us_ = 200;
+  SpinBudget pipe_budget_{GetEnv("PS_SHM_PIPE_SPIN_US", 50), GetEnv("PS_SPIN_MAX_US", 1000)};
   std::deque<int> ready_fds_;      // touched by the receive thread only
   SpinMutex peers_mu_;  // a map lookup per send
   std::unordered_map<int, std::shared_ptr<Peer>> peers_;
