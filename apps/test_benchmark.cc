@@ -211,6 +211,9 @@ void StartServers(std::vector<KVServer<char>*>* servers) {
   for (int i = 0; i < opt.group_size; ++i) {
     auto* s = new KVServer<char>(0, false, i);
     s->set_request_handle(ServerHandle);
+    // neither the handler nor the (absent) worker callbacks wait for the network: both sides may
+    // run on the receive threads (BENCHMARK_INLINE=0 restores the reference's thread structure)
+    s->set_inline_dispatch(EnvInt("BENCHMARK_INLINE", 1) != 0);
     servers->push_back(s);
   }
   if (!opt.recv_buffer) return;
@@ -371,6 +374,7 @@ int main(int argc, char* argv[]) {
     std::vector<std::thread> threads;
     for (int i = 0; i < opt.nthread; ++i) {
       kvs.push_back(new KVWorker<char>(0, 0, i));
+      kvs.back()->set_inline_dispatch(EnvInt("BENCHMARK_INLINE", 1) != 0);
       threads.emplace_back(RunWorker, kvs.back(), i);
     }
     for (auto& t : threads) t.join();

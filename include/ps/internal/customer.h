@@ -47,6 +47,18 @@ class Customer {
            bool start_now = true);
   /*! \brief register + start the receive thread (idempotent) */
   void Start();
+  /*!
+   * \brief run the handler on the van's receive thread whenever this customer's queue is idle
+   *        (one thread hop less per message; a hop costs microseconds when the next thread polls
+   *        and 100+ us when it sleeps). Order and exclusivity are kept: a message is handled
+   *        inline only while nothing is queued or being handled by the customer thread.
+   *        ONLY for handlers that never wait for the network: the receive thread is the one that
+   *        would deliver what they wait for, and a handler that *sends* from it must not have a
+   *        peer that does the same (two receive threads blocked on each other's full ring).
+   *        May be switched at any time. Ignored with PS_LOCAL_HANDOFF (several delivering threads).
+   */
+  void set_inline_dispatch(bool on);
+  bool inline_dispatch() const { return inline_.load(std::memory_order_acquire); }
   ~Customer();
   Customer(const Customer&) = delete;
   Customer& operator=(const Customer&) = delete;
@@ -94,7 +106,11 @@ class Customer {
   const int customer_id_;
   RecvHandle recv_handle_;
   Postoffice* postoffice_;
-  bool direct_dispatch_ = false;
+  bool direct_dispatch_ = false;       // PS_DIRECT_DISPATCH=1: no customer thread at all
+  std::atomic<bool> inline_{false};    // set_inline_dispatch
+  std::atomic<int> pending_{0};        // queued or being handled by the customer thread
+  SpinMutex deliver_mu_;               // one handler at a time (several vans may deliver: MultiVan)
+  bool TryInline(const Message& m);
   bool started_ = false;
 
   ThreadsafeQueue<Message> inbox_;

@@ -83,6 +83,12 @@ class SimpleApp {
     on_response_ = h;
   }
   virtual Customer* get_customer() { return obj_; }
+  /*!
+   * \brief handle this app's messages on the van's receive thread instead of the customer
+   *        thread whenever the queue is idle (extension; see Customer::set_inline_dispatch for
+   *        the rules: handlers and callbacks must never wait for the network)
+   */
+  void set_inline_dispatch(bool on) { obj_->set_inline_dispatch(on); }
 
  protected:
   /*! \brief for subclasses (KVWorker / KVServer) that build their Customer themselves */

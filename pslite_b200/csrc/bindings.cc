@@ -78,7 +78,10 @@ cudaEvent_t RecordOnCurrentStream(int dev) {
 class PyKVWorker {
  public:
   PyKVWorker(int app_id, int customer_id, int instance_idx)
-      : kv_(new KVWorker<char>(app_id, customer_id, instance_idx)), instance_(instance_idx) {}
+      : kv_(new KVWorker<char>(app_id, customer_id, instance_idx)), instance_(instance_idx) {
+    // every completion callback of this class only releases references: safe on the receive thread
+    kv_->set_inline_dispatch(GetEnv("PS_WORKER_INLINE", 1) != 0);
+  }
 
   /*! \brief encode "the idx-th key owned by server `server`" like the benchmarks do */
   uint64_t server_key(int server, uint64_t idx) {
@@ -393,6 +396,7 @@ class PyBenchServer {
         s->Response(m, res);
       }
     });
+    kv_->set_inline_dispatch(GetEnv("PS_SERVER_INLINE", 1) != 0);  // the handler never waits for the network
   }
   ~PyBenchServer() {
     py::gil_scoped_release nogil;

@@ -164,10 +164,29 @@ void Customer::Deliver(const Message& m) {
   if (!m.meta.request) CountResponse(m.meta.timestamp, 1);
 }
 
+void Customer::set_inline_dispatch(bool on) {
+  static const bool handoff = GetEnv("PS_LOCAL_HANDOFF", 0) != 0;  // senders deliver too: not one thread
+  inline_.store(on && !handoff, std::memory_order_release);
+}
+
+bool Customer::TryInline(const Message& m) {
+  if (!inline_.load(std::memory_order_acquire) || pending_.load(std::memory_order_acquire) != 0) return false;
+  if (!deliver_mu_.try_lock()) return false;  // another van's receive thread is in the handler
+  if (pending_.load(std::memory_order_acquire) != 0) {  // it queued something meanwhile: keep the order
+    deliver_mu_.unlock();
+    return false;
+  }
+  Deliver(m);
+  deliver_mu_.unlock();
+  return true;
+}
+
 void Customer::Accept(const Message& recved) {
   if (direct_dispatch_) {
     Deliver(recved);
+  } else if (TryInline(recved)) {
   } else {
+    pending_.fetch_add(1, std::memory_order_acq_rel);
     inbox_.Push(recved);
   }
 }
@@ -175,7 +194,9 @@ void Customer::Accept(const Message& recved) {
 void Customer::Accept(Message&& recved) {
   if (direct_dispatch_) {
     Deliver(recved);
+  } else if (TryInline(recved)) {
   } else {
+    pending_.fetch_add(1, std::memory_order_acq_rel);
     inbox_.Push(std::move(recved));
   }
 }
@@ -189,20 +210,28 @@ void Customer::Receiving() {
     inbox_.WaitAndPop(&m);
     if (!m.meta.control.empty() && m.meta.control.cmd == Control::TERMINATE) break;
     if (!coalesce) {
-      Deliver(m);
+      {
+        std::lock_guard<SpinMutex> one(deliver_mu_);
+        Deliver(m);
+      }
+      pending_.fetch_sub(1, std::memory_order_acq_rel);
       continue;
     }
     bool stop = false;
     {
       Van::CorkScope cork(postoffice_->van());
+      std::lock_guard<SpinMutex> one(deliver_mu_);
       Deliver(m);
+      int handled = 1;
       for (int n = 1; n < 32 && inbox_.TryPop(&m); ++n) {
         if (!m.meta.control.empty() && m.meta.control.cmd == Control::TERMINATE) {
           stop = true;
           break;
         }
         Deliver(m);
+        ++handled;
       }
+      pending_.fetch_sub(handled, std::memory_order_acq_rel);
     }
     if (stop) break;
   }
