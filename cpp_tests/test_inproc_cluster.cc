@@ -1,5 +1,6 @@
 // In-process cluster smoke test: scheduler + 1 server + 1 worker as threads.
 #include <map>
+#include <set>
 #include "ps/ps.h"
 using namespace ps;
 int main() {
@@ -121,6 +122,49 @@ int main() {
     CHECK_EQ(got[1], 2.f); CHECK_EQ(got[5], 3.5f);
   }
   delete vserver;
+
+  // inline dispatch: handlers run on the receive thread while the customer queue is idle and on
+  // the customer thread otherwise; either way one at a time and in arrival order. A second app
+  // whose handler checks both, fed with bursts of back-to-back requests so that both paths occur
+  {
+    auto* iserver = new KVServer<float>(11);
+    std::atomic<int> in_handler{0}, handled{0}, out_of_order{0}, overlapped{0};
+    std::set<std::thread::id> handler_threads;
+    float last = 0.f;
+    iserver->set_request_handle([&](const KVMeta& req, const KVPairs<float>& data, KVServer<float>* srv) {
+      if (in_handler.fetch_add(1) != 0) ++overlapped;
+      handler_threads.insert(std::this_thread::get_id());
+      if (req.push) {
+        if (data.vals[0] != last + 1.f) ++out_of_order;
+        last = data.vals[0];
+      }
+      ++handled;
+      in_handler.fetch_sub(1);
+      srv->Response(req);
+    });
+    iserver->set_inline_dispatch(true);
+    KVWorker<float> ikv(11, 1);
+    ikv.set_inline_dispatch(true);
+    std::vector<Key> one = {4};
+    float next = 1.f;
+    for (int burst = 0; burst < 50; ++burst) {
+      std::vector<int> ts;
+      // every other burst starts queued and switches to inline half-way: the switch must not let
+      // an inline message overtake the queued ones or run beside them
+      if (burst % 2 == 1) iserver->set_inline_dispatch(false);
+      for (int i = 0; i < 40; ++i, next += 1.f) {
+        if (i == 20) iserver->set_inline_dispatch(true);
+        ts.push_back(ikv.Push(one, std::vector<float>{next}));
+      }
+      for (int t : ts) ikv.Wait(t);
+      if (burst % 10 == 9) std::this_thread::sleep_for(std::chrono::milliseconds(2));  // let the queue drain
+    }
+    CHECK_EQ(handled.load(), 2000);
+    CHECK_EQ(out_of_order.load(), 0);
+    CHECK_EQ(overlapped.load(), 0);
+    LOG(INFO) << "inline dispatch ok: 2000 requests on " << handler_threads.size() << " handler thread(s)";
+    delete iserver;
+  }
 
   // SimpleApp surface of the KV classes: a request to the server group, answered with a body
   server->SimpleApp::set_request_handle([](const SimpleData& req, SimpleApp* app) {

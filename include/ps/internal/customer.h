@@ -55,6 +55,9 @@ class Customer {
    *        ONLY for handlers that never wait for the network: the receive thread is the one that
    *        would deliver what they wait for, and a handler that *sends* from it must not have a
    *        peer that does the same (two receive threads blocked on each other's full ring).
+   *        Messages whose payload (or requested reply) travels inside frames and exceeds
+   *        PS_INLINE_MAX_BYTES (64 KB) still go through the customer thread: streaming megabytes
+   *        through a ring from the receive thread would stop it from receiving meanwhile.
    *        May be switched at any time. Ignored with PS_LOCAL_HANDOFF (several delivering threads).
    */
   void set_inline_dispatch(bool on);
@@ -110,6 +113,8 @@ class Customer {
   std::atomic<bool> inline_{false};    // set_inline_dispatch
   std::atomic<int> pending_{0};        // queued or being handled by the customer thread
   SpinMutex deliver_mu_;               // one handler at a time (several vans may deliver: MultiVan)
+  int64_t inline_max_bytes_ = 65536;   // larger two-sided payloads keep the customer thread (PS_INLINE_MAX_BYTES)
+  bool payload_in_frames_ = true;      // false on one-sided vans: their messages are descriptors
   bool TryInline(const Message& m);
   bool started_ = false;
 
