@@ -284,10 +284,7 @@ def run_pushpull(args, dist: Dist) -> dict:
         # same bytes per key, but ONE KVWorker::ZPushPull instead of ZPush + ZPull (extension over the
         # reference API; reported next to the headline, never instead of it)
         def fused_round():
-            ts = [kv.push_pull(keys[k], vals[k], vals[k], order_after_current_stream=False)
-                  for k in range(total_keys)]
-            for t in ts:
-                kv.wait(t)
+            kv.wait_all(kv.push_pull_batch(keys, vals, order_after_current_stream=False, fused=True))
         if ctx.is_worker:
             for _ in range(max(3, args.warmup)):
                 fused_round()

@@ -171,7 +171,7 @@ class PyKVWorker {
   std::vector<int> push_pull_batch(const std::vector<uint64_t>& keys,
                                    const std::vector<torch::Tensor>& tensors, int cmd, int codec,
                                    float scale, bool order_after_current_stream, bool do_push,
-                                   bool do_pull) {
+                                   bool do_pull, bool fused) {
     TORCH_CHECK(keys.size() == tensors.size(), "keys / tensors length mismatch");
     std::vector<SArray<char>> views;
     views.reserve(keys.size());
@@ -187,6 +187,21 @@ class PyKVWorker {
     ts.reserve(keys.size() * 2);
     auto remaining = std::make_shared<std::atomic<int>>(do_push ? static_cast<int>(keys.size()) : 0);
     for (size_t i = 0; i < keys.size(); ++i) {
+      if (fused && do_push && do_pull) {
+        // one ZPushPull per key: the request carries the push, its single reply the pulled values
+        SendOpts opts;
+        opts.codec = codec;
+        opts.scale = scale;
+        opts.wait_event = ev;
+        auto* dst = new SArray<char>(views[i]);
+        auto* len = new SArray<int>(OneLen(dst->size()));
+        ts.push_back(kv_->ZPushPull(OneKey(keys[i]), views[i], dst, len, cmd, [dst, len, ev, remaining]() {
+          delete dst;
+          delete len;
+          if (ev && remaining->fetch_sub(1) == 1) cudaEventDestroy(ev);
+        }, opts));
+        continue;
+      }
       if (do_push) {
         SendOpts opts;
         opts.codec = codec;
@@ -568,7 +583,7 @@ PYBIND11_MODULE(_C, m) {
       .def("push_pull_batch", &PyKVWorker::push_pull_batch, py::arg("keys"), py::arg("tensors"),
            py::arg("cmd") = 0, py::arg("codec") = 0, py::arg("scale") = 1.0f,
            py::arg("order_after_current_stream") = true, py::arg("push") = true,
-           py::arg("pull") = true)
+           py::arg("pull") = true, py::arg("fused") = false)
       .def("staged_push_pull", &PyKVWorker::staged_push_pull, py::arg("keys"), py::arg("dev"),
            py::arg("host_in"), py::arg("host_out"), py::arg("cmd") = 0, py::arg("codec") = 0,
            py::arg("scale") = 1.0f);
