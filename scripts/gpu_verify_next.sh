@@ -28,6 +28,8 @@ echo "== 3c. nccl van"
 PSLITE_TEST_NCCL_VAN=1 timeout 400 python -m pytest tests/test_multigpu.py -m gpu -q -k nccl 2>&1 | tail -n 15
 echo "== 4. bench N=1"
 timeout 400 python bench.py --steps 20 --warmup 3 2>gpurun_out/v_b1.err | tee gpurun_out/v_bench1.json | tail -c 900
+echo "== 4-. bench N=1 with the thread structure of the measured runs (no inline dispatch, fixed short poll windows)"
+PS_SERVER_INLINE=0 PS_WORKER_INLINE=0 PS_SPIN_MAX_US=0 timeout 400 python bench.py --steps 20 --warmup 3 --no-e2e 2>gpurun_out/v_b1q.err | tee gpurun_out/v_bench1_queued.json | tail -c 500
 echo "== 4a. PCIe bound of the end-to-end pass, then the pass through the native staged call"
 timeout 120 python scripts/pcie_probe.py | tee gpurun_out/v_pcie.json
 timeout 400 python bench.py --steps 20 --warmup 3 --e2e-native 2>gpurun_out/v_b1n.err | tee gpurun_out/v_bench1_native.json | tail -c 700
