@@ -5,6 +5,7 @@
 #include <thread>
 #include "core/wire.h"
 #include "ps/internal/parallel_sort.h"
+#include "ps/internal/spin_mutex.h"
 #include "ps/internal/parallel_kv_match.h"
 #include "test_util.h"
 #include "van/mem_domain.h"
@@ -138,6 +139,71 @@ TEST(threadsafe_queue_both_modes) {
     CHECK_EQ(sum, 20000LL * 19999 / 2);
   }
   Environment::Get()->set("DMLC_LOCKLESS_QUEUE", "0");
+}
+
+TEST(spin_mutex_and_condition) {
+  // mutual exclusion under contention, and sleeping on it through condition_variable_any
+  SpinMutex mu;
+  long counter = 0;
+  std::vector<std::thread> th;
+  for (int t = 0; t < 4; ++t) {
+    th.emplace_back([&] {
+      for (int i = 0; i < 50000; ++i) {
+        std::lock_guard<SpinMutex> lk(mu);
+        ++counter;
+      }
+    });
+  }
+  for (auto& t : th) t.join();
+  CHECK_EQ(counter, 200000L);
+  CHECK(mu.try_lock());
+  CHECK(!mu.try_lock());
+  mu.unlock();
+  std::condition_variable_any cv;
+  bool ready = false;
+  std::thread waker([&] {
+    std::this_thread::sleep_for(std::chrono::milliseconds(5));
+    {
+      std::lock_guard<SpinMutex> lk(mu);
+      ready = true;
+    }
+    cv.notify_all();
+  });
+  {
+    std::unique_lock<SpinMutex> lk(mu);
+    cv.wait(lk, [&] { return ready; });
+  }
+  waker.join();
+}
+
+TEST(spin_budget_and_poll) {
+  // the window follows the long gaps: short ones (inside a burst) are ignored, gaps shorter than
+  // the cap are polled through, gaps longer than the cap end the polling
+  SpinBudget b(20, 1000);
+  CHECK_EQ(b.window_us(), 1000);  // starts optimistic
+  for (int i = 0; i < 100; ++i) b.Observe(3);  // inside a burst: no information
+  CHECK_EQ(b.window_us(), 1000);
+  for (int i = 0; i < 20; ++i) b.Observe(300);  // typical gap 300 us -> poll for twice that
+  CHECK_GE(b.window_us(), 550);
+  CHECK_LE(b.window_us(), 700);
+  for (int i = 0; i < 20; ++i) b.Observe(50000);  // idle job: give up polling
+  CHECK_EQ(b.window_us(), 20);
+  for (int i = 0; i < 20; ++i) b.Observe(100);  // traffic is back
+  CHECK_LE(b.window_us(), 400);
+  CHECK_GE(b.window_us(), 150);
+  SpinBudget fixed(50, 0);  // cap 0: fixed floor window
+  fixed.Observe(10000);
+  CHECK_EQ(fixed.window_us(), 50);
+
+  std::atomic<bool> flag{false};
+  CHECK(!SpinPoll([&] { return flag.load(); }, 10, 200));  // times out
+  std::thread setter([&] {
+    std::this_thread::sleep_for(std::chrono::microseconds(300));
+    flag = true;
+  });
+  CHECK(SpinPoll([&] { return flag.load(); }, 10, 2000000));  // sees it in the polite phase
+  setter.join();
+  CHECK(SpinPoll([&] { return true; }, 0, 0));
 }
 
 TEST(wire_roundtrip_data_meta) {
