@@ -79,7 +79,11 @@ int main(int argc, char* argv[]) {
     }
   });
 
+  // neither the handler above nor this worker's callbacks wait for the network
+  const bool inline_dispatch = GetEnv("BENCHMARK_INLINE", 1) != 0;
+  server.set_inline_dispatch(inline_dispatch);
   KVWorker<char> kv(0, 0);
+  kv.set_inline_dispatch(inline_dispatch);
   const auto& ranges = Postoffice::GetWorker()->GetServerKeyRanges();
   const int nodes = static_cast<int>(ranges.size());
   const int sessions = nthread * nodes;
