@@ -17,6 +17,7 @@
 #define PS_VAN_SHM_PIPE_H_
 #include <fcntl.h>
 #include <sys/mman.h>
+#include <sys/uio.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
@@ -124,6 +125,44 @@ class ShmPipe {
     }
     return true;
   }
+  /*!
+   * \brief append all pieces of one frame. A frame of at most half the ring is published with ONE
+   *        store of `tail` once it fits (the reader never sees a partial frame, and the cache line
+   *        of `tail` changes hands once per frame instead of once per piece); larger frames stream.
+   */
+  bool WriteV(const struct iovec* iov, int niov) {
+    size_t total = 0;
+    for (int i = 0; i < niov; ++i) total += iov[i].iov_len;
+    const uint64_t cap = ctl_->capacity, mask = cap - 1;
+    if (total > cap / 2) {
+      for (int i = 0; i < niov; ++i) {
+        if (!Write(iov[i].iov_base, iov[i].iov_len)) return false;
+      }
+      return true;
+    }
+    uint64_t tail = ctl_->tail.load(std::memory_order_relaxed);
+    auto idle_since = std::chrono::steady_clock::time_point();
+    while (cap - (tail - ctl_->head.load(std::memory_order_acquire)) < total) {
+      if (idle_since == std::chrono::steady_clock::time_point()) {
+        idle_since = std::chrono::steady_clock::now();
+      } else if (std::chrono::steady_clock::now() - idle_since > std::chrono::seconds(60)) {
+        return false;
+      }
+      if (full_hook_) full_hook_();
+      std::this_thread::yield();
+    }
+    for (int i = 0; i < niov; ++i) {
+      const char* p = static_cast<const char*>(iov[i].iov_base);
+      const size_t n = iov[i].iov_len;
+      const size_t at = static_cast<size_t>(tail & mask);
+      const size_t first = std::min(n, static_cast<size_t>(cap - at));
+      memcpy(data_ + at, p, first);
+      if (n > first) memcpy(data_, p + first, n - first);
+      tail += n;
+    }
+    ctl_->tail.store(tail, std::memory_order_release);
+    return true;
+  }
   /*! \brief after a frame: true if the reader declared itself asleep (ring its doorbell) */
   bool ReaderNeedsDoorbell() {
     std::atomic_thread_fence(std::memory_order_seq_cst);
@@ -135,18 +174,21 @@ class ShmPipe {
 
   // ---- consumer ---------------------------------------------------------------
   size_t Readable() const {
-    return static_cast<size_t>(ctl_->tail.load(std::memory_order_acquire) -
-                               ctl_->head.load(std::memory_order_relaxed));
+    return static_cast<size_t>(ctl_->tail.load(std::memory_order_acquire) - rcur_);
   }
-  /*! \brief consume exactly n bytes, waiting for the writer if needed; false on a dead writer */
+  /*!
+   * \brief consume exactly n bytes, waiting for the writer if needed; false on a dead writer.
+   *        The space is handed back to the writer (store of `head`) only every quarter ring or
+   *        at Commit(): one store per frame instead of one per piece.
+   */
   bool Read(void* dst, size_t n) {
     char* p = static_cast<char*>(dst);
     const uint64_t cap = ctl_->capacity, mask = cap - 1;
-    uint64_t head = ctl_->head.load(std::memory_order_relaxed);
     auto idle_since = std::chrono::steady_clock::time_point();
     while (n) {
-      const uint64_t avail = ctl_->tail.load(std::memory_order_acquire) - head;
+      const uint64_t avail = ctl_->tail.load(std::memory_order_acquire) - rcur_;
       if (avail == 0) {
+        Commit();  // the writer may be waiting for exactly the space we have not returned yet
         if (idle_since == std::chrono::steady_clock::time_point()) {
           idle_since = std::chrono::steady_clock::now();
         } else if (std::chrono::steady_clock::now() - idle_since > std::chrono::seconds(60)) {
@@ -157,16 +199,23 @@ class ShmPipe {
       }
       idle_since = std::chrono::steady_clock::time_point();
       const size_t chunk = static_cast<size_t>(std::min<uint64_t>(avail, n));
-      const size_t at = static_cast<size_t>(head & mask);
+      const size_t at = static_cast<size_t>(rcur_ & mask);
       const size_t first = std::min(chunk, static_cast<size_t>(cap - at));
       memcpy(p, data_ + at, first);
       if (chunk > first) memcpy(p + first, data_, chunk - first);
-      head += chunk;
+      rcur_ += chunk;
       p += chunk;
       n -= chunk;
-      ctl_->head.store(head, std::memory_order_release);
+      if (rcur_ - published_ >= cap / 4) Commit();
     }
     return true;
+  }
+  /*! \brief end of a frame: return everything consumed so far to the writer */
+  void Commit() {
+    if (published_ != rcur_) {
+      published_ = rcur_;
+      ctl_->head.store(rcur_, std::memory_order_release);
+    }
   }
   /*! \brief announce "about to sleep"; returns false (and cancels) if data is already there */
   bool PrepareSleep() {
@@ -201,6 +250,7 @@ class ShmPipe {
     data_ = static_cast<char*>(p) + sizeof(Ctl);
     name_ = name;
     owner_ = owner;
+    if (!owner) rcur_ = published_ = ctl_->head.load(std::memory_order_relaxed);
   }
   void* base_ = nullptr;
   size_t map_bytes_ = 0;
@@ -209,6 +259,8 @@ class ShmPipe {
   std::string name_;
   bool owner_ = false;
   std::function<void()> full_hook_;
+  uint64_t rcur_ = 0;       // consumer only: bytes consumed
+  uint64_t published_ = 0;  // consumer only: value of `head` the writer can see
 };
 
 }  // namespace ps

@@ -604,9 +604,7 @@ class TcpVan : public Van {
 
   /*! \brief write whole frames into the peer's ring; doorbell only if the reader sleeps */
   bool SendThroughPipe(Peer* peer, const struct iovec* iov, int niov) {
-    for (int i = 0; i < niov; ++i) {
-      if (!peer->pipe->Write(iov[i].iov_base, iov[i].iov_len)) return false;
-    }
+    if (!peer->pipe->WriteV(iov, niov)) return false;
     if (peer->pipe->ReaderNeedsDoorbell()) RingDoorbell(peer->fd);
     return true;
   }
@@ -802,7 +800,9 @@ class TcpVan : public Van {
   int ReadFramePipe(ShmPipe* pipe, Message* msg) {
     FrameHeader hdr;
     CHECK(pipe->Read(&hdr, sizeof(hdr))) << "shared-memory ring writer vanished";
-    return ParseFrame(hdr, msg, [&](void* dst, size_t n) { return pipe->Read(dst, n); });
+    const int rc = ParseFrame(hdr, msg, [&](void* dst, size_t n) { return pipe->Read(dst, n); });
+    pipe->Commit();  // hand the frame's space back with one store
+    return rc;
   }
 
   /*!
