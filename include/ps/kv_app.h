@@ -485,7 +485,7 @@ void KVWorker<Val>::Send(int timestamp, bool push, int cmd, KVPairs<Val>& kvs,
   // servers that get nothing are accounted for up front
   int skipped = 0;
   for (const auto& s : sliced) skipped += s.first ? 0 : 1;
-  obj_->AddResponse(timestamp, skipped);
+  if (skipped) obj_->AddResponse(timestamp, skipped);
   if (static_cast<size_t>(skipped) == sliced.size()) RunCallback(timestamp);
 
   for (size_t i = 0; i < sliced.size(); ++i) {

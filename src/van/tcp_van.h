@@ -329,7 +329,8 @@ class TcpVan : public Van {
       }
       peer->handoff_state.store(2, std::memory_order_release);
     }
-    std::vector<char> meta_buf;
+    thread_local std::vector<char> meta_buf;  // reused: no allocation per message
+    meta_buf.clear();
     PackMeta(msg.meta, &meta_buf);
     const uint32_t nseg = static_cast<uint32_t>(msg.data.size());
     CHECK_LE(nseg, kMaxSegments);
