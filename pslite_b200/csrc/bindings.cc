@@ -411,7 +411,8 @@ class PyBenchServer {
         s->Response(m, res);
       }
     });
-    kv_->set_inline_dispatch(GetEnv("PS_SERVER_INLINE", 1) != 0);  // the handler never waits for the network
+    // the handler never waits for the network; with launch coalescing the customer thread batches instead
+    kv_->set_inline_dispatch(GetEnv("PS_SERVER_INLINE", 1) != 0 && GetEnv("PS_COALESCE_LAUNCHES", 0) == 0);
   }
   ~PyBenchServer() {
     py::gil_scoped_release nogil;

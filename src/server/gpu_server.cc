@@ -170,7 +170,8 @@ GpuServer::GpuServer(int app_id, const GpuServerConfig& cfg, int instance_idx)
   server_->set_request_handle(std::bind(&GpuServer::Handle, this, _1, _2, _3));
   // Handle() never waits for the network (it enqueues kernels and sends replies): run it on the
   // receive thread while the queue is idle — one thread hop less per request
-  server_->set_inline_dispatch(GetEnv("PS_SERVER_INLINE", 1) != 0);
+  // (not with launch coalescing: there the customer thread handles whole batches under one cork)
+  server_->set_inline_dispatch(GetEnv("PS_SERVER_INLINE", 1) != 0 && GetEnv("PS_COALESCE_LAUNCHES", 0) == 0);
 }
 
 GpuServer::~GpuServer() {
