@@ -212,10 +212,10 @@ class KVWorker : public SimpleApp {
   int Pull_(const SArray<Key>& keys, C* vals, D* lens, int cmd, const Callback& cb,
             const SendOpts& opts = SendOpts(), const SArray<Val>* push_vals = nullptr);
 
-  void AddCallback(int timestamp, const Callback& cb) {
+  void AddCallback(int timestamp, Callback cb) {
     if (!cb) return;
     std::lock_guard<SpinMutex> lk(mu_);
-    callbacks_[timestamp] = cb;
+    callbacks_[timestamp] = std::move(cb);  // by value + move: the closure is built exactly once
   }
   void RunCallback(int timestamp);
   void Send(int timestamp, bool push, int cmd, KVPairs<Val>& kvs, const SendOpts& opts = SendOpts(),
