@@ -28,6 +28,9 @@ def _load_native():
     global _C
     if _C is not None:
         return _C
+    # the extension hands torch tensors to Python (alloc_exportable, ...): the torch Python
+    # package must be initialised first, or wrapping the first tensor dereferences a null type
+    import torch  # noqa: F401
     try:
         _C = importlib.import_module("pslite_b200._C")
     except ImportError:
