@@ -109,3 +109,41 @@ def test_bench_script_multi_process_on_cpu():
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     line = json.loads([l for l in r.stdout.strip().splitlines() if l.startswith("{")][-1])
     assert line["n_gpus"] == 4 and line["config"]["num_workers"] == 2 and line["value"] > 0
+
+
+def test_native_initialises_torch_first():
+    """the extension hands tensors to Python: loading it without the torch package crashed later"""
+    code = "import sys; import pslite_b200; pslite_b200.native(); assert 'torch' in sys.modules; print('ok')"
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=ROOT,
+                       env=dict(os.environ, PSLITE_NO_AUTOBUILD="1", CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 0 and "ok" in r.stdout, (r.stdout + r.stderr)[-2000:]
+
+
+def test_scheduler_child_dies_with_a_crashed_launcher():
+    """init_ps spawns the scheduler; if the launching process dies without cleanup the scheduler
+    must not stay behind (it would hold the port and the launcher's output pipe)"""
+    import time
+
+    code = ("import os, sys; sys.path.insert(0, %r)\n"
+            "import pslite_b200\n"
+            "from pslite_b200.parallel.launch import init_ps\n"
+            "pslite_b200.native()\n"
+            "ctx = init_ps('joint', van='shm')\n"
+            "print('SCHED', ctx.scheduler.pid, flush=True)\n"
+            "os._exit(3)\n" % ROOT)
+    r = subprocess.run([sys.executable, "-c", code], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                       timeout=300, cwd=ROOT, env=dict(os.environ, PSLITE_NO_AUTOBUILD="1", CUDA_VISIBLE_DEVICES=""))
+    assert r.returncode == 3
+    pid = int([l for l in r.stdout.splitlines() if l.startswith("SCHED")][0].split()[1])
+    for _ in range(100):
+        if not os.path.exists(f"/proc/{pid}"):
+            break
+        try:  # a zombie whose parent is gone is reaped by init; "Z" counts as gone
+            if open(f"/proc/{pid}/stat").read().split(")")[1].split()[0] == "Z":
+                break
+        except OSError:
+            break
+        time.sleep(0.1)
+    else:
+        os.kill(pid, 15)
+        raise AssertionError(f"scheduler {pid} outlived its launcher")
