@@ -433,6 +433,28 @@ void KVWorker<Val>::DefaultSlicer(const KVPairs<Val>& send, const std::vector<Ra
   sliced->assign(n, std::make_pair(false, KVPairs<Val>()));
   if (send.keys.empty()) return;
 
+  if (send.keys.size() == 1) {
+    // one key (a tensor per request, the common case): no cut table, no binary searches
+    const Key key = send.keys[0];
+    for (size_t i = 0; i < n; ++i) {
+      const bool open_end = i + 1 == n && static_cast<Key>(ranges[i].end()) == kMaxKey;
+      if (key < static_cast<Key>(ranges[i].begin()) || !(key < static_cast<Key>(ranges[i].end()) || open_end)) continue;
+      auto& out = (*sliced)[i];
+      out.first = true;
+      out.second.keys = send.keys;
+      if (send.lens.empty()) {
+        out.second.vals = send.vals;
+      } else {
+        CHECK_EQ(send.lens.size(), (size_t)1);
+        out.second.lens = send.lens;
+        const size_t val_to = static_cast<size_t>(send.lens[0]);
+        if (val_to <= send.vals.size()) out.second.vals = send.vals.segment(0, val_to);  // a pull carries none yet
+      }
+      return;
+    }
+    LOG(FATAL) << "key " << key << " lies outside every server range";
+  }
+
   // cut[i] = index of the first key owned by server i; keys are sorted
   std::vector<size_t> cut(n + 1, 0);
   const Key* kb = send.keys.begin();
