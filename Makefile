@@ -7,24 +7,29 @@
 USE_CUDA ?= 1
 USE_KEY32 ?= 0
 ASAN ?= 0
+DEBUG ?= 0
 TSAN ?= 0
 CUDA_HOME ?= /usr/local/cuda
 BUILD ?= build
 
 CXX ?= g++
 NVCC ?= $(CUDA_HOME)/bin/nvcc
-CXXFLAGS := -std=c++17 -O2 -g -Wall -Wno-unused-function -Wno-overloaded-virtual -fPIC -Iinclude -Isrc -pthread
+CXXFLAGS := -std=c++17 -O2 -Wall -Wno-unused-function -Wno-overloaded-virtual -fPIC -Iinclude -Isrc -pthread
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -Isrc -Iinclude
 LDFLAGS := -pthread -lrt
 ifeq ($(USE_KEY32),1)
 CXXFLAGS += -DUSE_KEY32=1
 endif
+# DWARF is opt-in: the default tree must stay small enough to ship to the GPU box (<256 MiB).
+ifeq ($(DEBUG),1)
+CXXFLAGS += -g
+endif
 ifeq ($(ASAN),1)
-CXXFLAGS += -fsanitize=address -fno-omit-frame-pointer
+CXXFLAGS += -g -fsanitize=address -fno-omit-frame-pointer
 LDFLAGS += -fsanitize=address
 endif
 ifeq ($(TSAN),1)
-CXXFLAGS += -fsanitize=thread -fno-omit-frame-pointer
+CXXFLAGS += -g -fsanitize=thread -fno-omit-frame-pointer
 LDFLAGS += -fsanitize=thread
 endif
 

@@ -147,3 +147,36 @@ def test_scheduler_child_dies_with_a_crashed_launcher():
     else:
         os.kill(pid, 15)
         raise AssertionError(f"scheduler {pid} outlived its launcher")
+
+
+def _snapshot_bytes(root):
+    """Size of what gpurun would push: the tree minus .git/, gpurun_out/ and the .gpurunignore rules."""
+    import fnmatch
+
+    rules = [ln.strip() for ln in open(os.path.join(root, ".gpurunignore")) if ln.strip() and not ln.startswith("#")]
+    dir_rules = {r.rstrip("/") for r in rules if r.endswith("/")} | {".git", "gpurun_out"}
+    file_rules = [r for r in rules if not r.endswith("/")]
+    total, biggest = 0, []
+    for dirpath, dirnames, filenames in os.walk(root):
+        rel = os.path.relpath(dirpath, root)
+        dirnames[:] = [d for d in dirnames if d not in dir_rules
+                       and os.path.normpath(os.path.join(rel, d)) not in dir_rules]
+        for f in filenames:
+            if any(fnmatch.fnmatch(f, r) for r in file_rules):
+                continue
+            p = os.path.join(dirpath, f)
+            if os.path.islink(p):
+                continue
+            n = os.path.getsize(p)
+            total += n
+            biggest.append((n, os.path.relpath(p, root)))
+    return total, sorted(biggest, reverse=True)[:8]
+
+
+def test_snapshot_under_256MiB():
+    """Round 1 shipped 691 MB of DWARF and every driver GPU run was refused (limit 512 MiB)."""
+    total, biggest = _snapshot_bytes(ROOT)
+    assert total < 256 << 20, f"snapshot {total >> 20} MiB; biggest: {biggest}"
+    mk = open(os.path.join(ROOT, "Makefile")).read()
+    flags = [ln for ln in mk.splitlines() if ln.startswith("CXXFLAGS :=")][0]
+    assert " -g" not in flags, "default CXXFLAGS must not carry DWARF (use DEBUG=1)"
