@@ -145,6 +145,22 @@ class MemDomain {
     if (items.empty()) last = CopyAsync(nullptr, nullptr, 0, 0, 1.f, nullptr);
     return last;
   }
+  /*!
+   * \brief make the 8-byte completion word at `host_word` (inside the page-aligned host range
+   *        [page, page+bytes), e.g. the control block of a shared-memory ring) storable by this
+   *        domain's copy engine; returns the address that engine must use, or null if the
+   *        domain cannot signal completion by itself (the van then falls back to tickets).
+   */
+  virtual void* MapSignalWord(void* /*page*/, size_t /*bytes*/, void* /*host_word*/) { return nullptr; }
+  virtual void UnmapSignalWord(void* /*page*/) {}
+  /*!
+   * \brief CopyAsync without a ticket: when the bytes of `item` are globally visible (and all
+   *        work enqueued before it has completed), the copy engine ITSELF stores `value` to
+   *        `word` (an address from MapSignalWord) with release semantics at system scope.
+   *        `item.n_src_bytes == 0` only signals (after `item.wait_event`). Values passed for
+   *        one word must be increasing. False: not supported for this item (use CopyAsync).
+   */
+  virtual bool CopySignal(const CopyItem& /*item*/, void* /*word*/, uint64_t /*value*/) { return false; }
   /*! \brief block until the copy behind `t` is globally visible; recycles the ticket */
   virtual void Wait(Ticket t) = 0;
   /*! \brief non-blocking: has the copy behind `t` completed? (does not recycle the ticket) */

@@ -68,6 +68,7 @@ class ShmPipe {
     new (&c->tail) std::atomic<uint64_t>(0);
     new (&c->head) std::atomic<uint64_t>(0);
     new (&c->sleeping) std::atomic<uint32_t>(1);  // the first message rings the doorbell
+    new (&c->gate_done) std::atomic<uint64_t>(0);
     c->capacity = static_cast<uint32_t>(cap);
     std::atomic_thread_fence(std::memory_order_seq_cst);
     return pipe;
@@ -172,9 +173,35 @@ class ShmPipe {
   /*! \brief called while the ring is full (lets the owner ring the doorbell) */
   void set_full_hook(std::function<void()> f) { full_hook_ = std::move(f); }
 
+  // ---- completion gate ---------------------------------------------------------
+  // A frame may announce a payload that a device kernel is still writing into the reader's
+  // memory. Such a frame carries gate = k (the k-th gated frame of this ring); whoever moves
+  // the payload stores k to `gate_done` once it is globally visible (the copy kernel itself,
+  // with st.release.sys through a device mapping of this word, or the CPU twin). The reader
+  // leaves the frame in the ring until gate_done >= k: the role of the reference's
+  // RDMA WRITE_WITH_IMM completion (src/rdma_transport.h:211-231), with no host thread in
+  // between the copy and the descriptor.
+  /*! \brief host address of the 8-byte completion word (its page can be mapped into a device) */
+  void* gate_word() { return &ctl_->gate_done; }
+  uint64_t gate_done() const { return ctl_->gate_done.load(std::memory_order_acquire); }
+  /*! \brief producer side, CPU twin of the kernel's store */
+  void SignalGate(uint64_t k) { ctl_->gate_done.store(k, std::memory_order_release); }
+  /*! \brief start of the mapping and the bytes in front of the data area (page-lockable) */
+  void* map_base() { return base_; }
+
   // ---- consumer ---------------------------------------------------------------
   size_t Readable() const {
     return static_cast<size_t>(ctl_->tail.load(std::memory_order_acquire) - rcur_);
+  }
+  /*! \brief copy the next n bytes without consuming them; false if fewer have been published */
+  bool Peek(void* dst, size_t n) const {
+    if (Readable() < n) return false;
+    const uint64_t cap = ctl_->capacity, mask = cap - 1;
+    const size_t at = static_cast<size_t>(rcur_ & mask);
+    const size_t first = std::min(n, static_cast<size_t>(cap - at));
+    memcpy(dst, data_ + at, first);
+    if (n > first) memcpy(static_cast<char*>(dst) + first, data_, n - first);
+    return true;
   }
   /*!
    * \brief consume exactly n bytes, waiting for the writer if needed; false on a dead writer.
@@ -241,6 +268,8 @@ class ShmPipe {
     alignas(128) std::atomic<uint32_t> sleeping;
     uint32_t capacity;
     char pad[128 - sizeof(std::atomic<uint32_t>) - sizeof(uint32_t)];
+    alignas(128) std::atomic<uint64_t> gate_done;  // written by a device kernel or the CPU twin
+    char pad2[128 - sizeof(std::atomic<uint64_t>)];
   };
   ShmPipe() {}
   void Adopt(void* p, size_t bytes, const std::string& name, bool owner) {
