@@ -343,6 +343,41 @@ TEST(shm_pipe_stream_and_doorbell) {
   CHECK(rx->Read(&got, sizeof(got)));
 }
 
+TEST(shm_pipe_gate_and_peek) {
+  // a gated frame is visible (Peek) but must not be consumed before the completion word says so
+  const std::string name = "/pslite_test_gate_" + std::to_string(getpid());
+  auto tx = ShmPipe::Create(name, 4096);
+  auto rx = ShmPipe::Attach(name);
+  CHECK(tx != nullptr && rx != nullptr);
+  rx->Unlink();
+  CHECK_EQ(rx->gate_done(), (uint64_t)0);
+  struct Hdr { uint32_t magic; uint32_t pad; uint64_t gate; } h = {0x1234u, 0, 1}, peeked = {0, 0, 0};
+  CHECK(!rx->Peek(&peeked, sizeof(peeked)));  // nothing published yet
+  // wrap the header around the end of the ring: Peek must stitch it like Read does
+  std::vector<char> filler(4096 - 8);
+  CHECK(tx->Write(filler.data(), filler.size()));
+  CHECK(rx->Read(filler.data(), filler.size()));
+  rx->Commit();
+  CHECK(tx->Write(&h, sizeof(h)));
+  CHECK(rx->Peek(&peeked, sizeof(peeked)));
+  CHECK_EQ(peeked.magic, 0x1234u);
+  CHECK_EQ(peeked.gate, (uint64_t)1);
+  CHECK_EQ(rx->Readable(), sizeof(h));        // peeking consumed nothing
+  CHECK(rx->gate_done() < peeked.gate);       // gate closed
+  // the "copy engine": another thread stores the completion through the word's address
+  std::thread engine([&] {
+    std::this_thread::sleep_for(std::chrono::milliseconds(5));
+    static_cast<std::atomic<uint64_t>*>(tx->gate_word())->store(1, std::memory_order_release);
+  });
+  while (rx->gate_done() < peeked.gate) std::this_thread::yield();
+  engine.join();
+  Hdr got = {0, 0, 0};
+  CHECK(rx->Read(&got, sizeof(got)));
+  CHECK_EQ(got.gate, (uint64_t)1);
+  tx->SignalGate(2);
+  CHECK_EQ(rx->gate_done(), (uint64_t)2);
+}
+
 TEST(shm_pipe_no_lost_wakeups) {
   // the reader really sleeps (on a condition variable standing in for the socket doorbell) and
   // must be woken for every frame that arrives while it sleeps: a lost wake-up shows as a timeout

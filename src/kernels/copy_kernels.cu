@@ -31,7 +31,20 @@ namespace {
 std::atomic<unsigned long long> g_launches{0};
 
 constexpr int kThreads = 256;
-constexpr int kNumSMs = 148;
+
+/*! \brief SM count of the current device (148 on B200), asked once per device */
+int NumSMs() {
+  static std::atomic<int> cached[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 16) dev = 0;
+  int n = cached[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev].store(n, std::memory_order_relaxed);
+  }
+  return n;
+}
 
 __device__ __forceinline__ int4 ld_stream(const int4* p) {
   int4 r;
@@ -51,11 +64,41 @@ __device__ __forceinline__ void st_stream8(uint2* p, const uint2& v) {
 }
 
 // ---------------------------------------------------------------------------
+// in-kernel completion signal (ps_signal): every CTA fences its stores at system scope and
+// counts itself in; the last one publishes the value with st.release.sys. No cudaEvent, no
+// host thread between the copy and the receiver that polls the flag.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+/*! \brief called by ONE thread of a CTA after all of that CTA's stores are ordered before it */
+__device__ __forceinline__ void signal_arrive(const ps_signal& sig) {
+  __threadfence_system();
+  const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+  if (atomicAdd(sig.counter, 1u) == total - 1) {
+    *sig.counter = 0;        // the next kernel on this stream starts from zero again
+    __threadfence_system();  // acquire side of the counter: all CTAs' stores are ordered before the flag
+    st_release_sys(sig.flag, sig.value);
+  }
+}
+/*! \brief tail of a kernel whose CTAs all reach this point with all their threads */
+__device__ __forceinline__ void signal_tail(const ps_signal& sig) {
+  if (sig.flag == nullptr) return;
+  __syncthreads();
+  if (threadIdx.x == 0) signal_arrive(sig);
+}
+
+__global__ void k_signal(const ps_signal sig) {
+  __threadfence_system();
+  st_release_sys(sig.flag, sig.value);
+}
+
+// ---------------------------------------------------------------------------
 // raw copy, LDG/STG flavour
 // ---------------------------------------------------------------------------
 template <int UNROLL>
 __global__ void __launch_bounds__(kThreads)
-k_copy_vec16(int4* __restrict__ dst, const int4* __restrict__ src, size_t n16) {
+k_copy_vec16(int4* __restrict__ dst, const int4* __restrict__ src, size_t n16, const ps_signal sig) {
   const size_t stride = static_cast<size_t>(gridDim.x) * kThreads;
   size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
   // UNROLL independent 16-byte loads are issued before the first store
@@ -67,13 +110,15 @@ k_copy_vec16(int4* __restrict__ dst, const int4* __restrict__ src, size_t n16) {
     for (int u = 0; u < UNROLL; ++u) st_stream(dst + i + u * stride, v[u]);
   }
   for (; i < n16; i += stride) st_stream(dst + i, ld_stream(src + i));
+  signal_tail(sig);
 }
 
 __global__ void k_copy_bytes(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src,
-                             size_t n) {
+                             size_t n, const ps_signal sig) {
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += stride)
     dst[i] = src[i];
+  signal_tail(sig);
 }
 
 // ---------------------------------------------------------------------------
@@ -158,7 +203,7 @@ __device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, uint3
 
 __global__ void __launch_bounds__(32)
 k_copy_tma(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src,
-           size_t n_chunks, size_t n_bytes) {
+           size_t n_chunks, size_t n_bytes, const ps_signal sig) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ __align__(8) uint64_t full[kTmaStages];
   if (threadIdx.x == 0) {
@@ -201,6 +246,9 @@ k_copy_tma(unsigned char* __restrict__ dst, const unsigned char* __restrict__ sr
   }
   // all stores complete (not just smem reads) before the kernel retires
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  // the bulk stores went through the async proxy: order them before the generic-proxy flag store
+  asm volatile("fence.proxy.async;" ::: "memory");
+  if (sig.flag != nullptr) signal_arrive(sig);
 }
 
 // ---------------------------------------------------------------------------
@@ -217,7 +265,8 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
 
 /*! 8 fp32 in (2 x LDG.128) -> 8 bf16 out (1 x STG.128) per thread-iteration */
 __global__ void __launch_bounds__(kThreads)
-k_f32_to_bf16(int4* __restrict__ dst, const int4* __restrict__ src, size_t n8, float scale) {
+k_f32_to_bf16(int4* __restrict__ dst, const int4* __restrict__ src, size_t n8, float scale,
+              const ps_signal sig) {
   const size_t stride = static_cast<size_t>(gridDim.x) * kThreads;
   for (size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x; i < n8; i += stride) {
     const int4 a = ld_stream(src + 2 * i), b = ld_stream(src + 2 * i + 1);
@@ -228,15 +277,18 @@ k_f32_to_bf16(int4* __restrict__ dst, const int4* __restrict__ src, size_t n8, f
     o.w = pack_bf16x2(__int_as_float(b.z) * scale, __int_as_float(b.w) * scale);
     st_stream(dst + i, o);
   }
+  signal_tail(sig);
 }
 __global__ void k_f32_to_bf16_tail(__nv_bfloat16* dst, const float* src, size_t from, size_t n,
-                                   float scale) {
+                                   float scale, const ps_signal sig) {
   size_t i = from + blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __float2bfloat16_rn(src[i] * scale);
+  signal_tail(sig);
 }
 
 __global__ void __launch_bounds__(kThreads)
-k_bf16_scale(int4* __restrict__ dst, const int4* __restrict__ src, size_t n8, float scale) {
+k_bf16_scale(int4* __restrict__ dst, const int4* __restrict__ src, size_t n8, float scale,
+             const ps_signal sig) {
   const size_t stride = static_cast<size_t>(gridDim.x) * kThreads;
   for (size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x; i < n8; i += stride) {
     const int4 a = ld_stream(src + i);
@@ -248,11 +300,13 @@ k_bf16_scale(int4* __restrict__ dst, const int4* __restrict__ src, size_t n8, fl
     f = unpack_bf16x2(a.w); o.w = pack_bf16x2(f.x * scale, f.y * scale);
     st_stream(dst + i, o);
   }
+  signal_tail(sig);
 }
 __global__ void k_bf16_scale_tail(__nv_bfloat16* dst, const __nv_bfloat16* src, size_t from,
-                                  size_t n, float scale) {
+                                  size_t n, float scale, const ps_signal sig) {
   size_t i = from + blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = __float2bfloat16_rn(__bfloat162float(src[i]) * scale);
+  signal_tail(sig);
 }
 
 // ---------------------------------------------------------------------------
@@ -292,7 +346,7 @@ __device__ __forceinline__ uint32_t quant4(float a, float b, float c, float d) {
 template <bool SRC_BF16>
 __global__ void __launch_bounds__(kThreads)
 k_quant_fp8_block(unsigned char* __restrict__ payload, unsigned char* __restrict__ scales,
-                  const void* __restrict__ src, size_t n, float scale) {
+                  const void* __restrict__ src, size_t n, float scale, const ps_signal sig) {
   const size_t n8 = (n + 31) / 32 * 4;  // thread-iterations, padded to whole blocks
   const size_t stride = static_cast<size_t>(gridDim.x) * kThreads;
   for (size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x; i < n8; i += stride) {
@@ -342,6 +396,7 @@ k_quant_fp8_block(unsigned char* __restrict__ payload, unsigned char* __restrict
     st_stream8(reinterpret_cast<uint2*>(payload) + i, q);
     if ((threadIdx.x & 3) == 0) scales[i >> 2] = static_cast<unsigned char>(eb);
   }
+  signal_tail(sig);
 }
 
 // ---------------------------------------------------------------------------
@@ -385,7 +440,7 @@ __global__ void k_checksum_u32(const uint32_t* src, size_t n, unsigned long long
 int GridFor(size_t work_items, int max_ctas, int resident_per_sm) {
   size_t want = (work_items + kThreads - 1) / kThreads;
   size_t cap = max_ctas > 0 ? static_cast<size_t>(max_ctas)
-                            : static_cast<size_t>(kNumSMs) * resident_per_sm;
+                            : static_cast<size_t>(NumSMs()) * resident_per_sm;
   if (want > cap) want = cap;
   return want < 1 ? 1 : static_cast<int>(want);
 }
@@ -404,40 +459,58 @@ extern "C" unsigned long long ps_kernel_launch_count(void) { return g_launches.l
 
 namespace ps_kernels_internal {
 void CountLaunch(int n) { g_launches += static_cast<unsigned long long>(n); }
+int NumSMs() { return ::NumSMs(); }
+}
+
+extern "C" int ps_launch_signal(const ps_signal* sig, ps_stream_t stream_) {
+  if (!sig || !sig->flag) return 0;
+  k_signal<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream_)>>>(*sig);
+  ++g_launches;
+  return static_cast<int>(cudaGetLastError());
 }
 
 extern "C" int ps_launch_copy(void* dst, const void* src, size_t n, int codec, float scale,
                               int max_ctas, ps_stream_t stream_) {
+  return ps_launch_copy_signal(dst, src, n, codec, scale, max_ctas, nullptr, stream_);
+}
+
+extern "C" int ps_launch_copy_signal(void* dst, const void* src, size_t n, int codec, float scale,
+                                     int max_ctas, const ps_signal* sig_, ps_stream_t stream_) {
   cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-  if (n == 0) return 0;
+  const ps_signal none = {nullptr, nullptr, 0};
+  const ps_signal sig = (sig_ && sig_->flag) ? *sig_ : none;
+  if (n == 0) return ps_launch_signal(&sig, stream_);
+  // a transfer made of a body and a tail kernel signals from the one launched last
+  // (stream order: the body has completed before the tail starts)
+  auto sig_if = [&](bool last) -> const ps_signal& { return last ? sig : none; };
   const uintptr_t d = reinterpret_cast<uintptr_t>(dst), s = reinterpret_cast<uintptr_t>(src);
   switch (codec) {
     case PS_CODEC_RAW: {
       if (((d | s) & 15) != 0) {
         k_copy_bytes<<<GridFor(n, max_ctas, 8), kThreads, 0, stream>>>(
-            static_cast<unsigned char*>(dst), static_cast<const unsigned char*>(src), n);
+            static_cast<unsigned char*>(dst), static_cast<const unsigned char*>(src), n, sig);
         ++g_launches;
         break;
       }
       if (UseTma() && n >= static_cast<size_t>(kTmaChunk)) {
-        static bool attr_set = false;
+        static std::atomic<bool> attr_set{false};
         const int smem_bytes = kTmaStages * kTmaChunk;
-        if (!attr_set) {
+        if (!attr_set.load(std::memory_order_acquire)) {
           cudaFuncSetAttribute(k_copy_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-          attr_set = true;
+          attr_set.store(true, std::memory_order_release);
         }
         const size_t body = n & ~size_t(15);
         const size_t chunks = (body + kTmaChunk - 1) / kTmaChunk;
-        int grid = static_cast<int>(chunks < static_cast<size_t>(kNumSMs) ? chunks : kNumSMs);
+        int grid = static_cast<int>(chunks < static_cast<size_t>(NumSMs()) ? chunks : NumSMs());
         if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
         k_copy_tma<<<grid, 32, smem_bytes, stream>>>(static_cast<unsigned char*>(dst),
                                                       static_cast<const unsigned char*>(src),
-                                                      chunks, body);
+                                                      chunks, body, sig_if(n == body));
         ++g_launches;
         if (n > body) {
           k_copy_bytes<<<1, 32, 0, stream>>>(static_cast<unsigned char*>(dst) + body,
                                              static_cast<const unsigned char*>(src) + body,
-                                             n - body);
+                                             n - body, sig);
           ++g_launches;
         }
         break;
@@ -445,46 +518,50 @@ extern "C" int ps_launch_copy(void* dst, const void* src, size_t n, int codec, f
       const size_t n16 = n / 16;
       if (n16) {
         k_copy_vec16<4><<<GridFor((n16 + 3) / 4, max_ctas, 8), kThreads, 0, stream>>>(
-            static_cast<int4*>(dst), static_cast<const int4*>(src), n16);
+            static_cast<int4*>(dst), static_cast<const int4*>(src), n16, sig_if((n & 15) == 0));
         ++g_launches;
       }
       if (n & 15) {
         k_copy_bytes<<<1, 32, 0, stream>>>(static_cast<unsigned char*>(dst) + n16 * 16,
                                            static_cast<const unsigned char*>(src) + n16 * 16,
-                                           n & 15);
+                                           n & 15, sig);
         ++g_launches;
       }
       break;
     }
     case PS_CODEC_F32_TO_BF16: {
       const size_t ne = n / 4, n8 = ((d & 15) || (s & 15)) ? 0 : ne / 8;
+      const bool tail = ne > n8 * 8;
       if (n8) {
         k_f32_to_bf16<<<GridFor(n8, max_ctas, 8), kThreads, 0, stream>>>(
-            static_cast<int4*>(dst), static_cast<const int4*>(src), n8, scale);
+            static_cast<int4*>(dst), static_cast<const int4*>(src), n8, scale, sig_if(!tail));
         ++g_launches;
       }
-      if (ne > n8 * 8) {
+      if (tail) {
         const size_t rest = ne - n8 * 8;
         k_f32_to_bf16_tail<<<static_cast<int>((rest + 255) / 256), 256, 0, stream>>>(
-            static_cast<__nv_bfloat16*>(dst), static_cast<const float*>(src), n8 * 8, ne, scale);
+            static_cast<__nv_bfloat16*>(dst), static_cast<const float*>(src), n8 * 8, ne, scale, sig);
         ++g_launches;
       }
+      if (!n8 && !tail) return ps_launch_signal(&sig, stream_);
       break;
     }
     case PS_CODEC_BF16_SCALE: {
       const size_t ne = n / 2, n8 = ((d & 15) || (s & 15)) ? 0 : ne / 8;
+      const bool tail = ne > n8 * 8;
       if (n8) {
         k_bf16_scale<<<GridFor(n8, max_ctas, 8), kThreads, 0, stream>>>(
-            static_cast<int4*>(dst), static_cast<const int4*>(src), n8, scale);
+            static_cast<int4*>(dst), static_cast<const int4*>(src), n8, scale, sig_if(!tail));
         ++g_launches;
       }
-      if (ne > n8 * 8) {
+      if (tail) {
         const size_t rest = ne - n8 * 8;
         k_bf16_scale_tail<<<static_cast<int>((rest + 255) / 256), 256, 0, stream>>>(
             static_cast<__nv_bfloat16*>(dst), static_cast<const __nv_bfloat16*>(src), n8 * 8, ne,
-            scale);
+            scale, sig);
         ++g_launches;
       }
+      if (!n8 && !tail) return ps_launch_signal(&sig, stream_);
       break;
     }
     case PS_CODEC_F32_TO_FP8BLOCK:
@@ -495,11 +572,12 @@ extern "C" int ps_launch_copy(void* dst, const void* src, size_t n, int codec, f
       unsigned char* payload = static_cast<unsigned char*>(dst);
       unsigned char* scales = payload + npad;
       if ((s & 15) || (d & 7)) return static_cast<int>(cudaErrorMisalignedAddress);
+      if (npad == 0) return ps_launch_signal(&sig, stream_);
       const int grid = GridFor(npad / 8, max_ctas, 8);
       if (bf) {
-        k_quant_fp8_block<true><<<grid, kThreads, 0, stream>>>(payload, scales, src, ne, scale);
+        k_quant_fp8_block<true><<<grid, kThreads, 0, stream>>>(payload, scales, src, ne, scale, sig);
       } else {
-        k_quant_fp8_block<false><<<grid, kThreads, 0, stream>>>(payload, scales, src, ne, scale);
+        k_quant_fp8_block<false><<<grid, kThreads, 0, stream>>>(payload, scales, src, ne, scale, sig);
       }
       ++g_launches;
       break;
@@ -535,7 +613,7 @@ extern "C" int ps_launch_copy_multi(const ps_copy_seg* segs, int nseg, int max_c
     // enough x-blocks that the longest segment gets 4 x 16 B per thread per pass, but not more
     // than 8 resident CTAs per SM over all segments
     size_t want = (longest / 64 + kThreads - 1) / kThreads;
-    size_t cap = static_cast<size_t>(max_ctas > 0 ? max_ctas : kNumSMs * 8) / static_cast<size_t>(cnt);
+    size_t cap = static_cast<size_t>(max_ctas > 0 ? max_ctas : NumSMs() * 8) / static_cast<size_t>(cnt);
     if (cap < 1) cap = 1;
     if (want > cap) want = cap;
     if (want < 1) want = 1;

@@ -62,6 +62,26 @@ enum { PS_OPT_SGD = 0, PS_OPT_ADAMW = 1 };
 int ps_launch_copy(void* dst, const void* src, size_t n_src_bytes, int codec, float scale,
                    int max_ctas, ps_stream_t stream);
 
+/*!
+ * \brief in-kernel completion: when every CTA of the (last) kernel of a launch has stored its
+ *        bytes, the last one to finish stores `value` to `*flag` with st.release.sys — the
+ *        receiver of the payload (a van thread polling a shared-memory ring, or a peer GPU)
+ *        needs no host thread of the sender to learn that the data has landed. This is the
+ *        "immediate" of the reference's RDMA WRITE_WITH_IMM (src/rdma_transport.h:211-231).
+ *        `counter` is a zero-initialised device word owned by the stream (reset by the kernel).
+ */
+typedef struct {
+  unsigned* counter;
+  unsigned long long* flag;   // device-visible address (device memory or mapped host memory)
+  unsigned long long value;
+} ps_signal;
+
+/*! \brief ps_launch_copy + completion signal (sig may be null) */
+int ps_launch_copy_signal(void* dst, const void* src, size_t n_src_bytes, int codec, float scale,
+                          int max_ctas, const ps_signal* sig, ps_stream_t stream);
+/*! \brief only the signal: ordered after everything enqueued on `stream` before it */
+int ps_launch_signal(const ps_signal* sig, ps_stream_t stream);
+
 /*! \brief byte copies of up to PS_MAX_COPY_SEGS unrelated buffers per kernel launch */
 #define PS_MAX_COPY_SEGS 32
 typedef struct {

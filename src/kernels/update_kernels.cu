@@ -30,12 +30,12 @@
 
 namespace ps_kernels_internal {
 void CountLaunch(int n);
+int NumSMs();
 }
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kNumSMs = 148;
 
 struct UpdateDev {
   size_t n;
@@ -553,7 +553,7 @@ k_sum(float* __restrict__ out, const UpdateDev a, float scale, int accumulate) {
 
 int GridFor(size_t items, int max_ctas, int per_sm) {
   size_t want = (items + kThreads - 1) / kThreads;
-  size_t cap = max_ctas > 0 ? static_cast<size_t>(max_ctas) : static_cast<size_t>(kNumSMs) * per_sm;
+  size_t cap = max_ctas > 0 ? static_cast<size_t>(max_ctas) : static_cast<size_t>(ps_kernels_internal::NumSMs()) * per_sm;
   if (want > cap) want = cap;
   return want < 1 ? 1 : static_cast<int>(want);
 }
@@ -586,7 +586,8 @@ bool LaunchUpdateTmaImpl(const UpdateDev& d, const ps_opt_params& o, bool out_f3
     cudaFuncSetAttribute(k_update_tma<FMT, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     attr_set = true;
   }
-  int grid = static_cast<int>(tiles < static_cast<size_t>(kNumSMs) ? tiles : kNumSMs);
+  const int num_sms = ps_kernels_internal::NumSMs();
+  int grid = static_cast<int>(tiles < static_cast<size_t>(num_sms) ? tiles : num_sms);
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   k_update_tma<FMT, OPT><<<grid, kThreads, smem, st>>>(d, o);
   return true;

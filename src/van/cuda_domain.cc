@@ -46,6 +46,7 @@ class CudaDomain : public MemDomain {
     for (cudaEvent_t e : free_events_) cudaEventDestroy(e);
     for (auto& kv : imported_) cudaIpcCloseMemHandle(kv.second);
     for (auto& a : arenas_) cudaFree(a->base);
+    if (sig_counter_) cudaFree(sig_counter_);
     cudaStreamDestroy(stream_);
   }
   const char* name() const override { return "nvl"; }
@@ -253,6 +254,76 @@ class CudaDomain : public MemDomain {
     return t;
   }
 
+  /*!
+   * The completion word lives in host shared memory (the control block of a descriptor ring the
+   * receiving van polls). Page-lock and map that block so that a copy kernel can store to it:
+   * the GPU, not a host thread, announces that a payload has landed.
+   */
+  void* MapSignalWord(void* page, size_t bytes, void* host_word) override {
+    if (cudaSetDevice(dev_) != cudaSuccess) return nullptr;
+    cudaError_t e = cudaHostRegister(page, bytes, cudaHostRegisterMapped | cudaHostRegisterPortable);
+    if (e != cudaSuccess && e != cudaErrorHostMemoryAlreadyRegistered) {
+      LOG(WARNING) << "cudaHostRegister of a descriptor ring failed (" << cudaGetErrorString(e)
+                   << "): completions of this connection go through events and a host thread";
+      cudaGetLastError();
+      return nullptr;
+    }
+    cudaGetLastError();
+    void* dptr = nullptr;
+    if (cudaHostGetDevicePointer(&dptr, host_word, 0) != cudaSuccess) {
+      cudaGetLastError();
+      cudaHostUnregister(page);
+      return nullptr;
+    }
+    std::lock_guard<std::mutex> lk(mu_);
+    if (!sig_counter_) {
+      PS_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&sig_counter_), 256));
+      PS_CUDA_CHECK(cudaMemset(sig_counter_, 0, 256));
+    }
+    return dptr;
+  }
+  void UnmapSignalWord(void* page) override {
+    cudaSetDevice(dev_);
+    cudaStreamSynchronize(stream_);  // no kernel may still want to store to the word
+    cudaHostUnregister(page);
+    cudaGetLastError();
+  }
+
+  bool CopySignal(const CopyItem& item, void* word, uint64_t value) override {
+    if (!sig_counter_ || !word) return false;
+    PS_CUDA_CHECK(cudaSetDevice(dev_));
+    if (item.wait_event) {
+      PS_CUDA_CHECK(cudaStreamWaitEvent(stream_, static_cast<cudaEvent_t>(item.wait_event), 0));
+    }
+    ps_signal sig;
+    sig.counter = sig_counter_;
+    sig.flag = static_cast<unsigned long long*>(word);
+    sig.value = value;
+    const ps_stream_t st = reinterpret_cast<ps_stream_t>(stream_);
+    int rc = 0;
+    if (item.n_src_bytes == 0) {
+      rc = ps_launch_signal(&sig, st);
+    } else {
+      bool src_on_device = item.src_device_type == GPU;
+      if (item.src_device_type == UNK) {
+        cudaPointerAttributes attr;
+        src_on_device = cudaPointerGetAttributes(&attr, item.src) == cudaSuccess &&
+                        (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged);
+        if (!src_on_device) cudaGetLastError();
+      }
+      if (!src_on_device) {
+        CHECK_EQ(item.codec, (int)kCodecRaw) << "host-resident values can only be sent raw";
+        PS_CUDA_CHECK(cudaMemcpyAsync(item.dst, item.src, item.n_src_bytes, cudaMemcpyDefault, stream_));
+        rc = ps_launch_signal(&sig, st);
+      } else {
+        rc = ps_launch_copy_signal(item.dst, item.src, item.n_src_bytes, item.codec, item.scale,
+                                   max_ctas_, &sig, st);
+      }
+    }
+    CHECK_EQ(rc, 0) << "copy kernel launch failed: " << cudaGetErrorString(static_cast<cudaError_t>(rc));
+    return true;
+  }
+
   bool Ready(Ticket t) override {
     if (!t.event) return true;
     cudaError_t e = cudaEventQuery(static_cast<cudaEvent_t>(t.event));
@@ -294,6 +365,7 @@ class CudaDomain : public MemDomain {
   std::vector<std::unique_ptr<DevArena>> arenas_;
   int dev_;
   int max_ctas_ = 0;
+  unsigned* sig_counter_ = nullptr;  // CTA arrival counter of the signalling kernels (self-resetting)
   cudaStream_t stream_ = nullptr;
   std::mutex mu_;
   std::vector<cudaEvent_t> free_events_;

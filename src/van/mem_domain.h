@@ -384,6 +384,32 @@ class ShmDomain : public MemDomain {
     std::atomic_thread_fence(std::memory_order_release);
     return Ticket();
   }
+  void* MapSignalWord(void* /*page*/, size_t /*bytes*/, void* host_word) override { return host_word; }
+  bool CopySignal(const CopyItem& item, void* word, uint64_t value) override {
+    auto* flag = static_cast<std::atomic<uint64_t>*>(word);
+    const size_t n = (item.dst != item.src || item.codec != kCodecRaw) ? item.n_src_bytes : 0;
+    if (copier_) {
+      // the stand-in for a stream: the copier thread stores the flag after the bytes, in order
+      AsyncOp* op = new AsyncOp();
+      op->dst = item.dst;
+      op->src = item.src;
+      op->n = n;
+      op->codec = item.codec;
+      op->scale = item.scale;
+      op->flag = flag;
+      op->flag_value = value;
+      {
+        std::lock_guard<std::mutex> lk(q_mu_);
+        q_.push_back(op);
+        q_len_.fetch_add(1, std::memory_order_release);
+      }
+      q_cv_.notify_one();
+      return true;
+    }
+    if (n) CHECK_EQ(ps_host_copy(item.dst, item.src, n, item.codec, item.scale), 0) << "unknown wire codec " << item.codec;
+    flag->store(value, std::memory_order_release);
+    return true;
+  }
   bool Ready(Ticket t) override {
     return !t.event || static_cast<AsyncOp*>(t.event)->done.load(std::memory_order_acquire);
   }
@@ -402,6 +428,8 @@ class ShmDomain : public MemDomain {
     int codec = 0;
     float scale = 1.f;
     std::atomic<bool> done{false};
+    std::atomic<uint64_t>* flag = nullptr;  // CopySignal: store flag_value here, then self-delete
+    uint64_t flag_value = 0;
   };
   void CopierLoop() {
     std::unique_lock<std::mutex> lk(q_mu_);
@@ -423,7 +451,12 @@ class ShmDomain : public MemDomain {
       q_len_.fetch_sub(1, std::memory_order_release);
       lk.unlock();
       if (op->n) ps_host_copy(op->dst, op->src, op->n, op->codec, op->scale);
-      op->done.store(true, std::memory_order_release);
+      if (op->flag) {
+        op->flag->store(op->flag_value, std::memory_order_release);
+        delete op;  // nobody holds a ticket for a signalled copy
+      } else {
+        op->done.store(true, std::memory_order_release);
+      }
       lk.lock();
     }
   }

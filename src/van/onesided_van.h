@@ -74,6 +74,8 @@ class OneSidedVan : public TcpVan {
       PS_VLOG(1) << type_ << " van " << my_node_.id << ": " << coalesced_copies_.load() << " copies in "
                  << coalesced_batches_.load() << " coalesced batches";
     }
+    PS_VLOG(1) << type_ << " van " << my_node_.id << ": " << copies_.load() << " one-sided copies, "
+               << gated_frames_.load() << " descriptors gated by the copy engine";
     std::lock_guard<SpinMutex> lk(rv_mu_);
     push_slots_.clear();
     landing_.clear();
@@ -558,6 +560,20 @@ class OneSidedVan : public TcpVan {
         return 1 + static_cast<int>(msg.meta.data_size & 0x3fffffff);
       }
     }
+    if (signal_ && PeerGated(msg.meta.recver)) {
+      // same-host peer with a descriptor ring: the frame goes into the ring NOW and the copy
+      // kernel itself opens its gate (st.release.sys on the ring's completion word) — no event,
+      // no completion thread, no second hop for the descriptor. Frames without a copy simply
+      // queue behind the gated ones in the ring, which keeps the order of the SendMsg calls.
+      if (!item) return TcpVan::SendMsg(msg);  // (encodes host-resident values that asked for a wire codec)
+      MemDomain::CopyItem it = *item;
+      if (gate_only) it.n_src_bytes = 0;
+      const GateIssue issue = [this, &it](void* word, uint64_t seq) { return domain_->CopySignal(it, word, seq); };
+      const int rc = TcpVan::SendFrame(msg, &issue, &keep_alive);
+      CHECK_NE(rc, kNotGated) << type_ << " van: the copy engine refused to signal a gated frame";
+      ++gated_frames_;
+      return rc;
+    }
     Ticket t;
     if (item) {
       t = domain_->CopyAsync(item->dst, item->src, gate_only ? 0 : item->n_src_bytes, item->codec,
@@ -565,6 +581,12 @@ class OneSidedVan : public TcpVan {
     }
     return Ordered(msg, t, keep_alive);
   }
+
+  void* MapGateWord(ShmPipe* pipe) override {
+    if (!signal_) return nullptr;
+    return domain_->MapSignalWord(pipe->map_base(), 4096, pipe->gate_word());
+  }
+  void ReleaseGateWord(ShmPipe* pipe) override { domain_->UnmapSignalWord(pipe->map_base()); }
 
  public:
   void Cork() override {
@@ -591,6 +613,8 @@ class OneSidedVan : public TcpVan {
     c.held.clear();
     c.gate = false;
   }
+  /*! \brief descriptors whose delivery was gated on a completion signalled by the copy engine */
+  uint64_t num_gated_frames() const { return gated_frames_.load(); }
   /*! \brief batches flushed by Uncork / copies that shared a batch (tests, benchmarks) */
   uint64_t num_coalesced_batches() const { return coalesced_batches_.load(); }
   uint64_t num_coalesced_copies() const { return coalesced_copies_.load(); }
@@ -717,6 +741,10 @@ class OneSidedVan : public TcpVan {
   std::atomic<uint64_t> copy_bytes_{0};
   /*! \brief PS_COALESCE_LAUNCHES: honour Cork / Uncork (off: every copy is its own launch) */
   bool coalesce_ = GetEnv("PS_COALESCE_LAUNCHES", 0) != 0;
+  /*! \brief PS_GATED_FRAMES (default 1): completion signalled by the copy engine into the peer's
+   *  descriptor ring; 0 = cudaEvent + completion thread for every message (round-1 behaviour) */
+  bool signal_ = GetEnv("PS_GATED_FRAMES", 1) != 0;
+  std::atomic<uint64_t> gated_frames_{0};
   std::atomic<uint64_t> coalesced_batches_{0};
   std::atomic<uint64_t> coalesced_copies_{0};
 };

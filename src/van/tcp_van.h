@@ -175,6 +175,8 @@ class TcpVan : public Van {
     uint32_t meta_len;
     uint32_t num_segments;
     uint32_t reserved;
+    /*! \brief 0, or "deliver only once the ring's completion word has reached this value" */
+    uint64_t gate;
   };
   static constexpr uint32_t kFrameMagic = 0x4d524650u;  // "PFRM"
   static constexpr uint32_t kMaxSegments = 16;
@@ -191,7 +193,20 @@ class TcpVan : public Van {
      *  ever needed the wire keeps using it, so a handed-off message can never overtake one
      *  that is still in the ring (or parked at the receiver). */
     std::atomic<int> handoff_state{0};
+    /*! \brief gated frames (see ShmPipe): sequence of the last one, the address the copy engine
+     *  stores completions to (null: no gating on this connection), and what must stay alive
+     *  until a given completion. All under `mu`. */
+    uint64_t gate_seq = 0;
+    void* gate_word = nullptr;
+    std::deque<std::pair<uint64_t, SArray<char>>> gate_keep;
   };
+  /*!
+   * \brief issues the work a gated frame announces. Called under the peer's lock, after the
+   *        frame's sequence number is fixed and BEFORE the frame is published, so the order of
+   *        completions on `word` is the order of the frames in the ring. Must arrange for `seq`
+   *        to be stored to `word` when the work is globally visible; false = nothing was issued.
+   */
+  using GateIssue = std::function<bool(void* word, uint64_t seq)>;
   /*! \brief transient MemRef::region marker, never on the wire (see SendMsg) */
   static constexpr int32_t kEncodedOnHost = 0x4000007f;
   static constexpr uint32_t kPipeMagic = 0x45504950u;  // "PIPE": "frames follow in shm ring <name>"
@@ -281,6 +296,11 @@ class TcpVan : public Van {
       std::lock_guard<std::mutex> lk(old->mu);
       if (old->fd >= 0) close(old->fd);
       old->fd = -1;
+      if (old->pipe && old->gate_word) {
+        ReleaseGateWord(old->pipe.get());
+        old->gate_word = nullptr;
+        old->gate_keep.clear();
+      }
     }
   }
 
@@ -302,8 +322,22 @@ class TcpVan : public Van {
     return SendFrame(msg);
   }
 
-  /*! \brief serialise one message to its peer (socket, ring or own loopback queue) */
-  int SendFrame(Message& msg) {
+  /*! \brief can frames to `recver` be gated on completions the copy engine signals itself? */
+  bool PeerGated(int recver) {
+    std::lock_guard<SpinMutex> lk(peers_mu_);
+    auto it = peers_.find(recver);
+    return it != peers_.end() && it->second->pipe && it->second->gate_word != nullptr;
+  }
+
+  /*! \brief -2 from SendFrame: the gate could not be issued, nothing was sent */
+  static constexpr int kNotGated = -2;
+
+  /*!
+   * \brief serialise one message to its peer (socket, ring or own loopback queue). With `issue`
+   *        the frame is gated: it enters the ring now but the receiver delivers it only after the
+   *        work `issue` started has signalled completion; `keep` stays referenced until then.
+   */
+  int SendFrame(Message& msg, const GateIssue* issue = nullptr, const SArray<char>* keep = nullptr) {
     EventTrace::Mark("send_frame", msg.meta.timestamp, msg.meta.request * 2 + msg.meta.push);
     if (msg.meta.mem.region == kEncodedOnHost) msg.meta.mem = MemRef();
     const int recver = msg.meta.recver;
@@ -321,6 +355,9 @@ class TcpVan : public Van {
     }
     const bool transport_ctrl = msg.meta.control.cmd == Control::ADDR_REQUEST ||
                                 msg.meta.control.cmd == Control::ADDR_RESOLVED;
+    // a gated frame needs the ring (its completion word lives there); from then on everything
+    // for this peer does, so nothing handed off later can overtake it
+    if (issue) peer->handoff_state.store(2, std::memory_order_release);
     if (peer->same_process && handoff_ && (msg.meta.control.empty() || transport_ctrl) &&
         peer->handoff_state.load(std::memory_order_acquire) != 2) {
       if (HandOff(peer.get(), msg)) {
@@ -341,6 +378,7 @@ class TcpVan : public Van {
     hdr.meta_len = static_cast<uint32_t>(meta_buf.size());
     hdr.num_segments = nseg;
     hdr.reserved = 0;
+    hdr.gate = 0;
     uint64_t seg_len[kMaxSegments];
     struct iovec iov[3 + kMaxSegments];
     int niov = 0;
@@ -358,6 +396,17 @@ class TcpVan : public Van {
 
     std::lock_guard<std::mutex> lk(peer->mu);
     if (peer->fd < 0) return -1;
+    if (issue) {
+      if (!peer->pipe || !peer->gate_word) return kNotGated;
+      // completions seen so far release what they kept alive
+      const uint64_t done = peer->pipe->gate_done();
+      while (!peer->gate_keep.empty() && peer->gate_keep.front().first <= done) peer->gate_keep.pop_front();
+      const uint64_t seq = peer->gate_seq + 1;
+      if (!(*issue)(peer->gate_word, seq)) return kNotGated;
+      peer->gate_seq = seq;
+      hdr.gate = seq;
+      if (keep && keep->size()) peer->gate_keep.emplace_back(seq, *keep);
+    }
     if (!(peer->pipe ? SendThroughPipe(peer.get(), iov, niov) : SendAll(peer->fd, iov, niov))) {
       LOG(WARNING) << "failed to send to node " << recver << ": " << strerror(errno);
       return -1;
@@ -401,7 +450,7 @@ class TcpVan : public Van {
       PackMeta(m.meta, &metas[i]);
       const uint32_t nseg = static_cast<uint32_t>(m.data.size());
       CHECK_LE(nseg, kMaxSegments);
-      hdrs[i] = {kFrameMagic, my_node_.id, recver, static_cast<uint32_t>(metas[i].size()), nseg, 0};
+      hdrs[i] = {kFrameMagic, my_node_.id, recver, static_cast<uint32_t>(metas[i].size()), nseg, 0, 0};
       iov.push_back({&hdrs[i], sizeof(FrameHeader)});
       if (nseg) iov.push_back({lens[i].data(), sizeof(uint64_t) * nseg});
       iov.push_back({metas[i].data(), metas[i].size()});
@@ -441,6 +490,7 @@ class TcpVan : public Van {
     msg->data.clear();
     auto last_activity = std::chrono::steady_clock::now();
     for (;;) {
+      gates_pending_ = false;
       if (PollDeferred(msg)) return 1 + static_cast<int>(msg->meta.data_size & 0x3fffffff);
       if (PopLoopback(msg)) return 1 + static_cast<int>(msg->meta.data_size & 0x3fffffff);
       // same-host peers: frames arrive in shared-memory rings (round-robin for fairness)
@@ -458,7 +508,8 @@ class TcpVan : public Van {
       }
       if (int bytes = PollPipes(msg)) return bytes;
       // a derived van with asynchronous receives in flight keeps this thread polling
-      int timeout_ms = HasDeferred() ? 0 : -1;
+      // ... and so does a ring whose head frame waits for a completion only the device signals
+      int timeout_ms = (HasDeferred() || gates_pending_) ? 0 : -1;
       if (timeout_ms != 0 && !pipe_fds_.empty()) {
         // stay hot for a short while after the last message, then declare ourselves asleep
         // on every ring so that the next writer rings the doorbell
@@ -585,7 +636,7 @@ class TcpVan : public Van {
                              "_" + std::to_string(seq++);
     std::unique_ptr<ShmPipe> pipe = ShmPipe::Create(name, pipe_bytes_);
     if (!pipe) return;  // no /dev/shm: stay on the socket
-    FrameHeader hello = {kPipeMagic, my_node_.id, peer_id, static_cast<uint32_t>(name.size()), 0, 0};
+    FrameHeader hello = {kPipeMagic, my_node_.id, peer_id, static_cast<uint32_t>(name.size()), 0, 0, 0};
     struct iovec iov[2] = {{&hello, sizeof(hello)}, {const_cast<char*>(name.data()), name.size()}};
     if (!SendAll(peer->fd, iov, 2)) return;
     const int fd = peer->fd;
@@ -594,6 +645,7 @@ class TcpVan : public Van {
     pipe->set_full_hook([fd, raw] {
       if (raw->ReaderNeedsDoorbell()) RingDoorbell(fd);
     });
+    peer->gate_word = MapGateWord(raw);
     peer->pipe = std::move(pipe);
   }
 
@@ -667,9 +719,17 @@ class TcpVan : public Van {
       const size_t idx = (pipe_cursor_ + k) % n;
       auto it = inbound_.find(pipe_fds_[idx]);
       if (it == inbound_.end() || !it->second->pipe) continue;
-      if (it->second->pipe->Readable() == 0) continue;
+      ShmPipe* pipe = it->second->pipe.get();
+      if (pipe->Readable() == 0) continue;
+      FrameHeader hdr;
+      // a gated frame stays in the ring until the copy engine has signalled its payload; the
+      // frames behind it wait too (a pull must not overtake the push it follows)
+      if (pipe->Peek(&hdr, sizeof(hdr)) && hdr.gate != 0 && pipe->gate_done() < hdr.gate) {
+        gates_pending_ = true;
+        continue;
+      }
       pipe_cursor_ = (idx + 1) % n;
-      return ReadFramePipe(it->second->pipe.get(), msg);
+      return ReadFramePipe(pipe, msg);
     }
     return 0;
   }
@@ -911,6 +971,11 @@ class TcpVan : public Van {
   virtual bool OnLocalControl(Message* /*msg*/) { return false; }
   virtual bool PollDeferred(Message* /*msg*/) { return false; }
   virtual bool HasDeferred() { return false; }
+  /*! \brief a ring to a same-host peer was created: return where the copy engine signals the
+   *  completion of gated frames (see ShmPipe::gate_word), or null for "no gating" */
+  virtual void* MapGateWord(ShmPipe* /*pipe*/) { return nullptr; }
+  /*! \brief the ring of a gated connection is about to be unmapped */
+  virtual void ReleaseGateWord(ShmPipe* /*pipe*/) {}
   /*! \brief enqueue a message for this van's own RecvMsg and wake it */
   int Loopback(const Message& msg) {
     {
@@ -940,6 +1005,11 @@ class TcpVan : public Van {
         std::lock_guard<std::mutex> plk(kv.second->mu);
         if (kv.second->fd >= 0) close(kv.second->fd);
         kv.second->fd = -1;
+        if (kv.second->pipe && kv.second->gate_word) {
+          ReleaseGateWord(kv.second->pipe.get());
+          kv.second->gate_word = nullptr;
+          kv.second->gate_keep.clear();
+        }
       }
       peers_.clear();
     }
@@ -992,6 +1062,7 @@ class TcpVan : public Van {
   bool handoff_ = GetEnv("PS_LOCAL_HANDOFF", 0) != 0;
   std::atomic<uint64_t> handoffs_{0};
   uint32_t spin_polls_ = 0;
+  bool gates_pending_ = false;                                 // receive thread: a ring head waits for its gate
   std::vector<int> pipe_fds_;                                  // inbound connections with a ring
   size_t pipe_cursor_ = 0;
   bool use_pipes_ = true;

@@ -53,6 +53,26 @@ def test_benchmark_one_sided_async_copies_many_peers(built_native_tree):
     assert rc == 0 and "goodput" in out, out[-3000:]
 
 
+@pytest.mark.parametrize("async_copies", [0, 1])
+def test_descriptors_gated_by_copy_engine(built_native_tree, async_copies):
+    """same-host peers: the descriptor of a one-sided transfer waits in the ring for the completion
+    word its copy stores (no ticket, no completion thread); PS_GATED_FRAMES=0 restores the tickets"""
+    import re
+
+    env = {"PS_VAN_TYPE": "shm", "PS_SHM_ASYNC": async_copies, "TEST_EXPORTABLE_VALS": 1, "NUM_KEY_PER_SERVER": 6,
+           "TOTAL_DURATION": 4, "LOG_DURATION": 2, "PS_VERBOSE": 1}
+    rc, out = launch(built_native_tree, 2, 2, "test_benchmark", 65536, 50, 1, env=env)
+    assert rc == 0 and "goodput" in out, out[-3000:]
+    gated = [int(x) for x in re.findall(r"(\d+) descriptors gated by the copy engine", out)]
+    copies = [int(x) for x in re.findall(r"(\d+) one-sided copies", out)]
+    # (the scheduler's van reports 0 / 0)
+    assert len([g for g in gated if g > 0]) == 4 and gated == copies, out[-2000:]
+    env["PS_GATED_FRAMES"] = 0
+    rc, out = launch(built_native_tree, 2, 2, "test_benchmark", 65536, 50, 1, env=env)
+    assert rc == 0 and "goodput" in out, out[-3000:]
+    assert all(int(x) == 0 for x in re.findall(r"(\d+) descriptors gated by the copy engine", out))
+
+
 def test_tutorial_example_runs(built_native_tree):
     """examples/kv_hello.cc is the program printed in docs/tutorials.md"""
     rc, out = launch(built_native_tree, 2, 2, "kv_hello")
