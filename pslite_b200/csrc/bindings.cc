@@ -687,6 +687,25 @@ PYBIND11_MODULE(_C, m) {
                            scale, max_ctas, CurrentStream(src)), "ps_launch_copy");
   }, py::arg("dst"), py::arg("src"), py::arg("codec") = 0, py::arg("scale") = 1.0f,
      py::arg("max_ctas") = 0);
+  // the same copy, finishing with the in-kernel completion signal: `flag` (a one-element int64
+  // tensor in pinned host memory or on the device) receives `value` once the bytes are visible
+  m.def("copy_signal", [](torch::Tensor dst, const torch::Tensor& src, int codec, float scale, int max_ctas,
+                          torch::Tensor flag, int64_t value, torch::Tensor counter) {
+    TORCH_CHECK(dst.is_cuda() && src.is_cuda() && counter.is_cuda(), "copy_signal is a device operation");
+    TORCH_CHECK(flag.numel() == 1 && flag.element_size() == 8, "flag: one 64-bit word");
+    void* fptr = flag.data_ptr();
+    if (!flag.is_cuda()) {
+      TORCH_CHECK(flag.is_pinned(), "a host flag must live in pinned memory");
+      TORCH_CHECK(cudaHostGetDevicePointer(&fptr, flag.data_ptr(), 0) == cudaSuccess, "flag is not device-mapped");
+    }
+    ps_signal sig;
+    sig.counter = reinterpret_cast<unsigned*>(counter.data_ptr());
+    sig.flag = static_cast<unsigned long long*>(fptr);
+    sig.value = static_cast<unsigned long long>(value);
+    CheckRc(ps_launch_copy_signal(dst.data_ptr(), src.data_ptr(), static_cast<size_t>(src.nbytes()), codec,
+                                  scale, max_ctas, &sig, CurrentStream(src)), "ps_launch_copy_signal");
+  }, py::arg("dst"), py::arg("src"), py::arg("codec"), py::arg("scale"), py::arg("max_ctas"),
+     py::arg("flag"), py::arg("value"), py::arg("counter"));
   m.def("copy_multi", [](std::vector<torch::Tensor> dsts, const std::vector<torch::Tensor>& srcs, int max_ctas) {
     TORCH_CHECK(dsts.size() == srcs.size(), "dsts / srcs length mismatch");
     if (dsts.empty()) return;

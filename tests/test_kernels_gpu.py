@@ -33,8 +33,6 @@ def test_raw_copy(native, n):
     assert torch.equal(dst, src)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("PSLITE_TEST_UNVERIFIED", "0") != "1",
-                    reason="k_copy_multi not yet validated on hardware; set PSLITE_TEST_UNVERIFIED=1")
 def test_multi_segment_copy(native):
     """one launch, many unrelated buffers (launch coalescing), incl. unaligned and tiny ones"""
     _require_cuda()
@@ -46,6 +44,44 @@ def test_multi_segment_copy(native):
     torch.cuda.synchronize()
     for d, s in zip(dsts, srcs):
         assert torch.equal(d, s)
+
+
+@pytest.mark.parametrize("codec_name,n", [("raw", 1), ("raw", 4096000), ("raw", 100003), ("bf16", 100003),
+                                          ("fp8", 1 << 20), ("fp8", 40)])
+def test_copy_with_in_kernel_completion_signal(native, codec_name, n):
+    """the copy kernels finish with st.release.sys on a flag word (the descriptor gate of the nvl van):
+    a host thread that only POLLS the flag — no event, no synchronize — must then find every byte"""
+    _require_cuda()
+    x = torch.randn(n, device="cuda")
+    if codec_name == "raw":
+        src = x.view(torch.uint8)
+        codec, out_bytes = native.CODEC_RAW, src.numel()
+    elif codec_name == "bf16":
+        src = x.view(torch.uint8)
+        codec, out_bytes = native.CODEC_F32_TO_BF16, 2 * n
+    else:
+        src = x.view(torch.uint8)
+        codec, out_bytes = native.CODEC_F32_TO_FP8BLOCK, native.wire_bytes(native.CODEC_F32_TO_FP8BLOCK, 4 * n)
+    ref = torch.zeros(out_bytes, dtype=torch.uint8, device="cuda")
+    native.copy_codec(ref, src, codec, 0.5)
+    torch.cuda.synchronize()
+    flag = torch.zeros(1, dtype=torch.int64).pin_memory()
+    counter = torch.zeros(64, dtype=torch.int32, device="cuda")
+    side = torch.cuda.Stream()
+    for value in (1, 2, 7):  # the arrival counter resets itself: the same word serves every launch
+        dst = torch.zeros(out_bytes, dtype=torch.uint8, device="cuda")
+        torch.cuda.synchronize()
+        native.copy_signal(dst, src, codec, 0.5, 0, flag, value, counter)
+        import time
+
+        t0 = time.time()
+        while int(flag[0]) != value:
+            assert time.time() - t0 < 20, "the kernel never signalled"
+        with torch.cuda.stream(side):  # an unrelated stream: ordering comes from the flag alone
+            got = dst.to("cpu", non_blocking=False)
+        assert torch.equal(got, ref.cpu()), f"bytes missing after the signal (value {value})"
+    torch.cuda.synchronize()
+    assert int(counter[0]) == 0
 
 
 @pytest.mark.parametrize("n", [8, 1000, 100003])
@@ -120,8 +156,6 @@ def test_fused_adamw_update(native, fmt, W, fan):
         assert torch.equal(o, pk.to(torch.bfloat16))
 
 
-@pytest.mark.skipif(__import__("os").environ.get("PSLITE_TEST_UNVERIFIED", "0") != "1",
-                    reason="added after the GPU budget ran out; set PSLITE_TEST_UNVERIFIED=1")
 @pytest.mark.parametrize("n", [1, 5, 7, 9, 33, 257])
 @pytest.mark.parametrize("fmt", ["bf16", "fp8", "f32"])
 def test_update_of_tiny_and_ragged_shards(native, n, fmt):

@@ -139,8 +139,6 @@ def test_host_fused_sgd_update(native):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(__import__("os").environ.get("PSLITE_TEST_UNVERIFIED", "0") != "1",
-                    reason="written after the GPU budget ran out; set PSLITE_TEST_UNVERIFIED=1")
 @pytest.mark.parametrize("codec_name", ["CODEC_F32_TO_BF16", "CODEC_F32_TO_FP8BLOCK", "CODEC_BF16_TO_FP8BLOCK"])
 def test_gpu_wire_bytes_equal_host_wire_bytes(native, codec_name):
     """the sm_100a push kernels and their CPU twins produce the same bytes for the same input"""

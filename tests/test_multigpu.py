@@ -48,8 +48,6 @@ def test_multicast_pull_fanout_two_gpus():
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.skipif(os.environ.get("PSLITE_TEST_NVLS_REDUCE", "0") != "1",
-                    reason="multimem.ld_reduce path not yet validated on hardware; set PSLITE_TEST_NVLS_REDUCE=1")
 def test_in_switch_gradient_reduction_two_gpus():
     """gradients summed by multimem.ld_reduce inside the update kernel (no landing slots)"""
     import torch.distributed._symmetric_memory  # noqa: F401  (present in this torch)
@@ -61,8 +59,6 @@ def test_in_switch_gradient_reduction_two_gpus():
 
 
 @pytest.mark.timeout(300)
-@pytest.mark.skipif(os.environ.get("PSLITE_TEST_NCCL_VAN", "0") != "1",
-                    reason="nccl van not yet validated on hardware; set PSLITE_TEST_NCCL_VAN=1")
 def test_nccl_van_benchmark_two_gpus():
     """worker on GPU 0, server on GPU 1, values in HBM, payloads over ncclSend / ncclRecv"""
     env = dict(os.environ)
