@@ -434,19 +434,23 @@ TEST(stale_shm_sweep) {
   if (child == 0) _exit(0);
   int status = 0;
   waitpid(child, &status, 0);
-  const std::string dead = "/pslite_sweeptest_" + std::to_string(child) + "_0";
-  const std::string live = "/pslite_sweeptest_" + std::to_string(getpid()) + "_0";
-  for (const std::string& n : {dead, live}) {
+  const std::string dead = "/" + ShmScopedPrefix("pslite_sweeptest_") + std::to_string(child) + "_0";
+  const std::string live = "/" + ShmScopedPrefix("pslite_sweeptest_") + std::to_string(getpid()) + "_0";
+  // same pid, but created in another pid namespace (another container sharing /dev/shm): not ours
+  const std::string foreign = "/pslite_sweeptest_n1_" + std::to_string(child) + "_0";
+  for (const std::string& n : {dead, live, foreign}) {
     int fd = shm_open(n.c_str(), O_CREAT | O_RDWR, 0600);
     CHECK_GE(fd, 0);
     close(fd);
   }
   CHECK_GE(SweepStaleShm("pslite_sweeptest_"), 1);
   CHECK_LT(shm_open(dead.c_str(), O_RDWR, 0600), 0);
-  int fd = shm_open(live.c_str(), O_RDWR, 0600);
-  CHECK_GE(fd, 0);
-  close(fd);
-  shm_unlink(live.c_str());
+  for (const std::string& n : {live, foreign}) {
+    int fd = shm_open(n.c_str(), O_RDWR, 0600);
+    CHECK_GE(fd, 0) << n << " was swept";
+    close(fd);
+    shm_unlink(n.c_str());
+  }
 }
 
 TEST(index_pool) {

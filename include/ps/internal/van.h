@@ -194,6 +194,8 @@ class Van {
 
   std::mutex parked_mu_;
   std::vector<Message> parked_;  // data messages waiting for their customer to be created
+  std::atomic<int> parked_n_{0};  // parked_.size(), readable without the lock
+  void DrainParkedLocked();
 
   std::vector<int> instance_barrier_count_;
   std::unordered_map<int, std::vector<int>> group_barrier_requests_;

@@ -70,6 +70,7 @@ int Customer::NewRequest(int recver, int num_expected) {
       s.ts = ts;
       s.expected = groups;
       s.received = 0;
+      s.waiters = 0;  // a waiter of the recycled request finds its slot gone and never decrements
       break;
     }
     // the slot we would recycle is still in flight: double the ring and re-home
@@ -190,6 +191,8 @@ bool Customer::TryInline(const Message& m) {
 
 void Customer::Accept(const Message& recved) {
   if (direct_dispatch_) {
+    // several vans (MultiVan rails) may deliver at once: still one handler at a time
+    std::lock_guard<SpinMutex> one(deliver_mu_);
     Deliver(recved);
   } else if (TryInline(recved)) {
   } else {
@@ -200,6 +203,7 @@ void Customer::Accept(const Message& recved) {
 
 void Customer::Accept(Message&& recved) {
   if (direct_dispatch_) {
+    std::lock_guard<SpinMutex> one(deliver_mu_);
     Deliver(recved);
   } else if (TryInline(recved)) {
   } else {

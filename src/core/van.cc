@@ -295,14 +295,25 @@ void Van::ProcessDataMsg(Message* msg) {
     const unsigned char* k = reinterpret_cast<const unsigned char*>(msg->data[0].data());
     key16 = k[0] + 256 * k[1];
   }
-  if (!postoffice_->DeliverOwned(app_id, customer_id, msg)) {
+  // Fast path: nothing is parked (only receive threads park, so the count cannot grow behind
+  // this thread's back) and the customer exists.
+  if (parked_n_.load(std::memory_order_acquire) != 0 || !postoffice_->DeliverOwned(app_id, customer_id, msg)) {
     // The application has not created this customer yet (e.g. it is still inside the
-    // start-up barrier). Park the message instead of blocking the receive thread — the
-    // reference waits here for up to 5 s (src/van.cc:435), during which no barrier
-    // release, ACK or heartbeat can be processed.
+    // start-up barrier), or older messages are still parked. Park the message instead of
+    // blocking the receive thread — the reference waits here for up to 5 s (src/van.cc:435),
+    // during which no barrier release, ACK or heartbeat can be processed. The look-up is
+    // repeated under parked_mu_: Postoffice::AddCustomer inserts the customer and THEN drains
+    // under the same lock, so either this thread sees the customer now or the drain sees the
+    // parked message. While anything is parked, new messages queue behind it (a sender's stream
+    // keeps its order) and the queue is drained in order right here.
     std::lock_guard<std::mutex> lk(parked_mu_);
-    parked_.push_back(*msg);
-    return;
+    if (parked_.empty() && postoffice_->DeliverOwned(app_id, customer_id, msg)) {
+      // delivered after all
+    } else {
+      parked_.push_back(*msg);
+      DrainParkedLocked();
+      return;
+    }
   }
   if (log_it) {
     auto us = std::chrono::duration_cast<std::chrono::microseconds>(
@@ -329,19 +340,20 @@ bool Van::AcceptHandoff(Message* msg) {
 }
 
 void Van::DeliverParked() {
-  std::vector<Message> todo;
-  {
-    std::lock_guard<std::mutex> lk(parked_mu_);
-    if (parked_.empty()) return;
-    todo.swap(parked_);
-  }
-  for (Message& m : todo) {
+  std::lock_guard<std::mutex> lk(parked_mu_);
+  DrainParkedLocked();
+}
+
+void Van::DrainParkedLocked() {
+  // in arrival order; a message whose customer is still missing stays, and so does everything
+  // behind it for the same customer (Deliver fails for those as well)
+  std::vector<Message> keep;
+  for (Message& m : parked_) {
     const int customer_id = postoffice_->is_worker() ? m.meta.customer_id : m.meta.app_id;
-    if (!postoffice_->Deliver(m.meta.app_id, customer_id, m)) {
-      std::lock_guard<std::mutex> lk(parked_mu_);
-      parked_.push_back(m);
-    }
+    if (!postoffice_->Deliver(m.meta.app_id, customer_id, m)) keep.push_back(std::move(m));
   }
+  parked_.swap(keep);
+  parked_n_.store(static_cast<int>(parked_.size()), std::memory_order_release);
 }
 
 // ---------------------------------------------------------------------------

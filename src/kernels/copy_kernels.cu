@@ -349,10 +349,17 @@ k_quant_fp8_block(unsigned char* __restrict__ payload, unsigned char* __restrict
                   const void* __restrict__ src, size_t n, float scale, const ps_signal sig) {
   const size_t n8 = (n + 31) / 32 * 4;  // thread-iterations, padded to whole blocks
   const size_t stride = static_cast<size_t>(gridDim.x) * kThreads;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x; i < n8; i += stride) {
+  // n8 is a multiple of 4 and every loop bound below a multiple of 32, so the four lanes of a
+  // block stay together; the trip count is made WARP-uniform on top of that (a lane past the end
+  // idles through the shuffles): the full-mask shuffles and the __syncthreads of the signal tail
+  // must be reached by whole warps
+  for (size_t base = static_cast<size_t>(blockIdx.x) * kThreads + (threadIdx.x & ~31u); base < n8;
+       base += stride) {
+    const size_t i = base + (threadIdx.x & 31u);
+    const bool live = i < n8;
     float x[8];
     const size_t e0 = i * 8;
-    if (e0 + 8 <= n) {
+    if (live && e0 + 8 <= n) {
       if (SRC_BF16) {
         const int4 a = ld_stream(reinterpret_cast<const int4*>(src) + i);
         float2 f;
@@ -373,7 +380,7 @@ k_quant_fp8_block(unsigned char* __restrict__ payload, unsigned char* __restrict
       for (int j = 0; j < 8; ++j) {
         const size_t e = e0 + j;
         float v = 0.f;
-        if (e < n) {
+        if (live && e < n) {
           v = SRC_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(src)[e])
                        : reinterpret_cast<const float*>(src)[e];
         }
@@ -393,8 +400,10 @@ k_quant_fp8_block(unsigned char* __restrict__ payload, unsigned char* __restrict
     uint2 q;
     q.x = quant4(x[0] * inv, x[1] * inv, x[2] * inv, x[3] * inv);
     q.y = quant4(x[4] * inv, x[5] * inv, x[6] * inv, x[7] * inv);
-    st_stream8(reinterpret_cast<uint2*>(payload) + i, q);
-    if ((threadIdx.x & 3) == 0) scales[i >> 2] = static_cast<unsigned char>(eb);
+    if (live) {
+      st_stream8(reinterpret_cast<uint2*>(payload) + i, q);
+      if ((threadIdx.x & 3) == 0) scales[i >> 2] = static_cast<unsigned char>(eb);
+    }
   }
   signal_tail(sig);
 }

@@ -476,7 +476,7 @@ class ShmDomain : public MemDomain {
   Arena* NewArena(uint64_t bytes) {
     static std::atomic<int> counter{0};
     std::unique_ptr<Arena> a(new Arena());
-    a->name = "/pslite_b200_" + std::to_string(getpid()) + "_" + std::to_string(counter++);
+    a->name = "/" + ShmScopedPrefix("pslite_b200_") + std::to_string(getpid()) + "_" + std::to_string(counter++);
     a->size = AlignUp(bytes, 4096);
     shm_unlink(a->name.c_str());
     int fd = shm_open(a->name.c_str(), O_CREAT | O_RDWR | O_EXCL, 0600);

@@ -40,6 +40,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <tuple>
 #include <unordered_map>
 #include <utility>
 #include <vector>
@@ -186,6 +187,9 @@ class TcpVan : public Van {
     std::mutex mu;  // serialises whole frames on this socket
     /*! \brief same-host fast path: frames go through this ring, the socket carries doorbells */
     std::unique_ptr<ShmPipe> pipe;
+    /*! \brief a ring the peer has not accepted yet (and the gate mapping that goes with it) */
+    std::unique_ptr<ShmPipe> offered;
+    void* offered_gate_word = nullptr;
     /*! \brief the peer lives in this very process (joint roles, in-process clusters) */
     bool same_process = false;
     int port = 0;
@@ -209,7 +213,14 @@ class TcpVan : public Van {
   using GateIssue = std::function<bool(void* word, uint64_t seq)>;
   /*! \brief transient MemRef::region marker, never on the wire (see SendMsg) */
   static constexpr int32_t kEncodedOnHost = 0x4000007f;
-  static constexpr uint32_t kPipeMagic = 0x45504950u;  // "PIPE": "frames follow in shm ring <name>"
+  // Same-host ring negotiation (all on the connection's socket):
+  //   sender   -> receiver : kPipeMagic + name      "I created shm ring <name>, can you map it?"
+  //   receiver -> sender   : one byte 'A' / 'D'     accept (mapped) or decline (e.g. a container
+  //                                                 with the same IP but a private /dev/shm)
+  //   sender   -> receiver : kPipeSwitchMagic       "every later frame is in the ring"
+  // Until the switch the socket carries the frames, so a declined or unanswered offer costs nothing.
+  static constexpr uint32_t kPipeMagic = 0x45504950u;        // "PIPE"
+  static constexpr uint32_t kPipeSwitchMagic = 0x57535050u;  // "PPSW"
 
   int Bind(Node& node, int max_retry) override {
     int port = node.port;
@@ -301,6 +312,10 @@ class TcpVan : public Van {
         old->gate_word = nullptr;
         old->gate_keep.clear();
       }
+      if (old->offered && old->offered_gate_word) {
+        ReleaseGateWord(old->offered.get());
+        old->offered_gate_word = nullptr;
+      }
     }
   }
 
@@ -341,6 +356,18 @@ class TcpVan : public Van {
     EventTrace::Mark("send_frame", msg.meta.timestamp, msg.meta.request * 2 + msg.meta.push);
     if (msg.meta.mem.region == kEncodedOnHost) msg.meta.mem = MemRef();
     const int recver = msg.meta.recver;
+    if (direct_pull_ && msg.meta.request && msg.meta.control.empty() && msg.meta.src_dev_type != GPU) {
+      // remember where the reply of this pull may land: the address echoed back on the wire is
+      // only ever compared with this record, never trusted (see SegmentDestination)
+      const bool fused = msg.meta.push && msg.meta.pull;
+      const uint64_t addr = fused ? msg.meta.pull_addr : (msg.meta.push ? 0 : msg.meta.addr);
+      if (addr != 0) {
+        const size_t esz = msg.meta.data_type.size() > 1 ? ElemSize(msg.meta.data_type[1]) : 1;
+        const uint64_t bytes = static_cast<uint64_t>(fused ? msg.meta.pull_len : msg.meta.val_len) * esz;
+        std::lock_guard<SpinMutex> lk(pull_mu_);
+        pull_dests_[PullKey(recver, msg.meta.app_id, msg.meta.customer_id, msg.meta.timestamp)] = {addr, bytes};
+      }
+    }
     if (recver == my_node_.id) return Loopback(msg);
 
     std::shared_ptr<Peer> peer;
@@ -629,11 +656,11 @@ class TcpVan : public Van {
     AddToEpoll(fd);
   }
 
-  /*! \brief create a ring for this connection and tell the peer its name over the socket */
+  /*! \brief create a ring for this connection and offer it to the peer over the socket */
   void OfferPipe(Peer* peer, int peer_id) {
     static std::atomic<int> seq{0};
-    const std::string name = "/pslb200_" + std::to_string(getpid()) + "_" + std::to_string(peer_id) +
-                             "_" + std::to_string(seq++);
+    const std::string name = "/" + ShmScopedPrefix("pslb200_") + std::to_string(getpid()) + "_" +
+                             std::to_string(peer_id) + "_" + std::to_string(seq++);
     std::unique_ptr<ShmPipe> pipe = ShmPipe::Create(name, pipe_bytes_);
     if (!pipe) return;  // no /dev/shm: stay on the socket
     FrameHeader hello = {kPipeMagic, my_node_.id, peer_id, static_cast<uint32_t>(name.size()), 0, 0, 0};
@@ -645,8 +672,50 @@ class TcpVan : public Van {
     pipe->set_full_hook([fd, raw] {
       if (raw->ReaderNeedsDoorbell()) RingDoorbell(fd);
     });
-    peer->gate_word = MapGateWord(raw);
-    peer->pipe = std::move(pipe);
+    peer->offered_gate_word = MapGateWord(raw);
+    peer->offered = std::move(pipe);
+    {
+      std::lock_guard<std::mutex> lk(offer_mu_);
+      offer_fds_[fd] = peer_id;
+    }
+    AddToEpoll(fd);  // the answer arrives on this (otherwise write-only) socket
+  }
+
+  /*! \brief receive thread: the peer answered our offer on outbound socket `fd` */
+  void OnPipeAnswer(int fd, int peer_id) {
+    char answer = 0;
+    const ssize_t r = recv(fd, &answer, 1, MSG_DONTWAIT);
+    if (r < 0 && (errno == EAGAIN || errno == EWOULDBLOCK || errno == EINTR)) return;
+    epoll_ctl(epfd_, EPOLL_CTL_DEL, fd, nullptr);  // one answer per connection (or EOF)
+    {
+      std::lock_guard<std::mutex> lk(offer_mu_);
+      offer_fds_.erase(fd);
+    }
+    std::shared_ptr<Peer> peer;
+    {
+      std::lock_guard<SpinMutex> lk(peers_mu_);
+      auto it = peers_.find(peer_id);
+      if (it != peers_.end()) peer = it->second;
+    }
+    if (!peer) return;
+    std::lock_guard<std::mutex> lk(peer->mu);
+    if (peer->fd != fd || !peer->offered) return;  // a reconnect replaced this connection
+    if (r == 1 && answer == 'A') {
+      FrameHeader sw = {kPipeSwitchMagic, my_node_.id, peer_id, 0, 0, 0, 0};
+      struct iovec iov[1] = {{&sw, sizeof(sw)}};
+      if (SendAll(fd, iov, 1)) {
+        peer->gate_word = peer->offered_gate_word;
+        peer->pipe = std::move(peer->offered);
+        peer->offered_gate_word = nullptr;
+        return;
+      }
+    } else if (r == 1) {
+      PS_VLOG(1) << "node " << peer_id << " cannot map our shared-memory ring (private /dev/shm?): "
+                 << "descriptors for it stay on the socket";
+    }
+    if (peer->offered_gate_word) ReleaseGateWord(peer->offered.get());
+    peer->offered_gate_word = nullptr;
+    peer->offered.reset();  // unlinks the name
   }
 
   static void RingDoorbell(int fd) {
@@ -776,8 +845,9 @@ class TcpVan : public Van {
     std::unique_ptr<char[]> buf{new char[kCap]};
     size_t head = 0, tail = 0;
     size_t avail() const { return tail - head; }
-    /*! \brief once the peer offered a ring, its frames arrive here and the socket only rings */
+    /*! \brief once the peer switched to its ring, its frames arrive here and the socket only rings */
     std::unique_ptr<ShmPipe> pipe;
+    std::unique_ptr<ShmPipe> offered;  // mapped and accepted, the switch marker is still to come
   };
 
   /*! \brief make >= n bytes available in the buffer (n <= kCap). 1 ok, 0 closed, -1 error */
@@ -825,7 +895,16 @@ class TcpVan : public Van {
   /*! \brief read one whole frame from fd; >0 bytes, 0 if nothing to deliver (closed / doorbell) */
   int ReadFrame(int fd, Message* msg) {
     auto iit = inbound_.find(fd);
-    if (iit == inbound_.end()) return 0;
+    if (iit == inbound_.end()) {
+      int offered_to = -1;
+      {
+        std::lock_guard<std::mutex> lk(offer_mu_);
+        auto oit = offer_fds_.find(fd);
+        if (oit != offer_fds_.end()) offered_to = oit->second;
+      }
+      if (offered_to >= 0) OnPipeAnswer(fd, offered_to);
+      return 0;
+    }
     Inbound* in = iit->second.get();
     if (in->pipe) {
       // the socket of a pipe-backed connection only carries 1-byte doorbells (or EOF)
@@ -845,9 +924,26 @@ class TcpVan : public Van {
     if (hdr.magic == kPipeMagic) {
       std::string name(hdr.meta_len, '\0');
       CHECK_EQ(Take(fd, in, &name[0], name.size()), 1);
-      in->pipe = ShmPipe::Attach(name);
-      CHECK(in->pipe) << "cannot attach shared-memory ring " << name << ": " << strerror(errno);
-      in->pipe->Unlink();  // both ends have it mapped: the name is no longer needed
+      in->offered = ShmPipe::Attach(name);
+      // PS_TEST_DECLINE_PIPE: behave like a container that cannot see the sender's /dev/shm
+      static const bool decline_all = GetEnv("PS_TEST_DECLINE_PIPE", 0) != 0;
+      if (decline_all) in->offered.reset();
+      if (in->offered) in->offered->Unlink();  // both ends have it mapped: the name is no longer needed
+      const char answer = in->offered ? 'A' : 'D';
+      if (!in->offered) {
+        PS_VLOG(1) << "cannot map the shared-memory ring node " << hdr.sender << " offered (" << name
+                   << ": " << strerror(errno) << "): its descriptors stay on the socket";
+      }
+      ssize_t w = send(fd, &answer, 1, MSG_NOSIGNAL);
+      (void)w;
+      if (in->avail() > 0) ready_fds_.push_back(fd);
+      return 0;
+    }
+    if (hdr.magic == kPipeSwitchMagic) {
+      // everything the peer sent before this marker has been read from the socket: from here
+      // on its frames are in the ring
+      CHECK(in->offered) << "ring switch without an accepted offer from node " << hdr.sender;
+      in->pipe = std::move(in->offered);
       pipe_fds_.push_back(fd);
       return 0;
     }
@@ -882,11 +978,22 @@ class TcpVan : public Van {
     }
     // a pull response can land straight in the buffer the request named (meta.addr
     // is this process's own pointer, echoed back by the server): zero-copy pull
+    // — but only the buffer THIS van recorded when it sent the request: a frame from the network
+    // must never be able to name an address to write to, and a late duplicate of a reply that
+    // was already consumed finds no record and lands in fresh memory
     if (i == 1 && direct_pull_ && !meta.request && !meta.push && meta.addr != 0 && len > 0 &&
         meta.src_dev_type != GPU) {
-      const size_t esz = meta.data_type.size() > 1 ? ElemSize(meta.data_type[1]) : 1;
-      if (len <= static_cast<uint64_t>(meta.val_len) * esz) {
-        seg.reset(reinterpret_cast<char*>(meta.addr), len, [](char*) {});
+      PullDest rec = {0, 0};
+      {
+        std::lock_guard<SpinMutex> lk(pull_mu_);
+        auto it = pull_dests_.find(PullKey(meta.sender, meta.app_id, meta.customer_id, meta.timestamp));
+        if (it != pull_dests_.end()) {
+          rec = it->second;
+          pull_dests_.erase(it);
+        }
+      }
+      if (rec.addr != 0 && rec.addr == meta.addr && len <= rec.bytes) {
+        seg.reset(reinterpret_cast<char*>(rec.addr), len, [](char*) {});
       }
     }
     if (seg.size() != len) seg = AllocSegment(len);
@@ -1010,6 +1117,10 @@ class TcpVan : public Van {
           kv.second->gate_word = nullptr;
           kv.second->gate_keep.clear();
         }
+        if (kv.second->offered && kv.second->offered_gate_word) {
+          ReleaseGateWord(kv.second->offered.get());
+          kv.second->offered_gate_word = nullptr;
+        }
       }
       peers_.clear();
     }
@@ -1075,6 +1186,16 @@ class TcpVan : public Van {
   std::deque<Message> loop_q_;
   std::mutex reg_mu_;
   std::map<std::pair<int, uint64_t>, SArray<char>> registered_;
+  /*! \brief destinations of the pulls in flight, by (server, app, customer, timestamp) */
+  struct PullDest {
+    uint64_t addr;
+    uint64_t bytes;
+  };
+  using PullKey = std::tuple<int, int, int, int>;
+  std::mutex offer_mu_;
+  std::unordered_map<int, int> offer_fds_;  // outbound socket -> peer id, while an offer is unanswered
+  SpinMutex pull_mu_;
+  std::map<PullKey, PullDest> pull_dests_;
 };
 
 }  // namespace ps

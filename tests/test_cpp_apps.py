@@ -73,6 +73,19 @@ def test_descriptors_gated_by_copy_engine(built_native_tree, async_copies):
     assert all(int(x) == 0 for x in re.findall(r"(\d+) descriptors gated by the copy engine", out))
 
 
+@pytest.mark.parametrize("van", ["zmq", "shm"])
+def test_declined_ring_offer_falls_back_to_socket(built_native_tree, van):
+    """a peer that cannot map the offered shared-memory ring (same IP, private /dev/shm) declines it:
+    the job runs over the sockets, one-sided transfers fall back to tickets"""
+    import re
+
+    env = {"PS_VAN_TYPE": van, "PS_TEST_DECLINE_PIPE": 1, "PS_VERBOSE": 1, "TEST_EXPORTABLE_VALS": 1}
+    rc, out = launch(built_native_tree, 2, 2, "test_kv_app", env=env)
+    assert rc == 0 and out.count("test_kv_app PASSED") == 2, out[-3000:]
+    assert "stay on the socket" in out
+    assert all(int(x) == 0 for x in re.findall(r"(\d+) descriptors gated by the copy engine", out))
+
+
 def test_tutorial_example_runs(built_native_tree):
     """examples/kv_hello.cc is the program printed in docs/tutorials.md"""
     rc, out = launch(built_native_tree, 2, 2, "kv_hello")
