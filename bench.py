@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--e2e-native", action="store_true",
                     help="also time the end-to-end round through KVWorker.staged_push_pull (the H2D / push / "
                          "pull / D2H pipeline in one native call instead of a Python loop)")
+    ap.add_argument("--copy-engine", type=int, default=int(os.environ.get("PS_COPY_ENGINE", "0")),
+                    help="1: raw copies without a producer event are posted to the copy engine (on-demand "
+                         "persistent kernel fed from a host-mapped ring) instead of one launch each")
     ap.add_argument("--sweep", default="", help="comma-separated extra message sizes (bytes) to report")
     # llama
     ap.add_argument("--seq-len", type=int, default=8192)
@@ -192,7 +195,8 @@ def run_pushpull(args, dist: Dist) -> dict:
     C = native()
     gpu = Gpu(args, dist.local_rank)
     topo = args.topology or ("joint" if dist.world == 1 else "split")
-    ctx = init_ps(topo, van=args.van or ("nvl" if gpu.cuda else "shm"))
+    ctx = init_ps(topo, van=args.van or ("nvl" if gpu.cuda else "shm"),
+                  extra_env={"PS_COPY_ENGINE": int(args.copy_engine)})
     server = C.BenchServer(0) if ctx.is_server else None
     S, W = ctx.num_servers, ctx.num_workers
     total_keys = S * args.keys_per_server
@@ -208,6 +212,31 @@ def run_pushpull(args, dist: Dist) -> dict:
     def one_round():
         # one call issues ZPush + ZPull for every key (test_benchmark's inner loop), then Wait all
         kv.wait_all(kv.push_pull_batch(keys, vals, order_after_current_stream=False))
+
+    def verify(tag: str):
+        """untimed data check: distinct patterns go up, the buffers are cleared, the pull must bring
+        every byte back (the timed rounds move constant bytes and would not notice a lost copy)"""
+        if not ctx.is_worker:
+            return
+        idx = sorted({0, 1, total_keys // 2, total_keys - 1})
+        want = {}
+        for k in idx:
+            pat = (torch.arange(args.len, dtype=torch.int32, device=vals[k].device) * (k + 3) + ctx.worker_rank + 7).to(torch.uint8)
+            vals[k].copy_(pat)
+            want[k] = pat
+        gpu.sync()
+        kv.wait_all(kv.push_pull_batch([keys[k] for k in idx], [vals[k] for k in idx],
+                                       order_after_current_stream=False, pull=False))
+        for k in idx:
+            vals[k].zero_()
+        gpu.sync()
+        kv.wait_all(kv.push_pull_batch([keys[k] for k in idx], [vals[k] for k in idx],
+                                       order_after_current_stream=False, push=False))
+        gpu.sync()
+        for k in idx:
+            assert torch.equal(vals[k], want[k]), f"{tag}: key {k} came back different from what was pushed"
+            vals[k].fill_(1)
+        gpu.sync()
 
     def timed(fn, steps: int):
         dist.barrier()
@@ -232,8 +261,10 @@ def run_pushpull(args, dist: Dist) -> dict:
         while n_warm < args.warmup or time.time() < t_end:
             one_round()
             n_warm += 1
+    verify("before the timed rounds")
     ms, launches = timed(one_round, args.steps)
     clocks = sampler.stop() if sampler else None
+    verify("after the timed rounds")
     payload = float(args.len) * total_keys * W  # per step, counted once per push+pull pair
     value = payload * args.steps / (ms * 1e-3) / 1e9
 
@@ -318,9 +349,12 @@ def run_pushpull(args, dist: Dist) -> dict:
         if ctx.is_worker:
             del svals
 
+    stats = {}
+    for role in (["worker"] if ctx.is_worker else []) + (["server"] if ctx.is_server else []):
+        stats[role] = {k: int(v) for k, v in C.van_stats(role).items()}
     ctx.shutdown()
     return {
-        "sweep": sweep,
+        "sweep": sweep, "van_stats_rank0": stats,
         "fused_pushpull": fused,
         "metric": METRIC_NAME["pushpull"], "value": value, "unit": "GB/s",
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -79,6 +79,8 @@ class Van {
   virtual void FreeExportable(void* p) { free(p); }
   /*! \brief this process's mapping of a span a peer announced (one-sided vans), else null */
   virtual void* ResolvePeerMem(int /*node_id*/, const MemRef& /*mem*/) { return nullptr; }
+  /*! \brief transport-specific counters by name (one-sided copies, gated descriptors, ...) */
+  virtual void TransportStats(std::vector<std::pair<std::string, uint64_t>>* /*out*/) {}
   /*! \brief stream the van's copy kernels run on (cudaStream_t), null for CPU vans */
   virtual void* DataStream() { return nullptr; }
   /*!

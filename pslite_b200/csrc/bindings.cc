@@ -549,6 +549,14 @@ PYBIND11_MODULE(_C, m) {
   }, py::arg("timeout_s") = 60, py::arg("as_role") = "worker");
   m.def("wire_bytes", [](int codec, uint64_t src_bytes) { return WireBytes(codec, src_bytes); });
   m.def("kernel_launch_count", []() { return ps_kernel_launch_count(); });
+  m.def("van_stats", [](const std::string& as_role) {
+    Postoffice* po = as_role == "server" ? Postoffice::GetServer() : Postoffice::GetWorker();
+    std::vector<std::pair<std::string, uint64_t>> kv;
+    if (po && po->van()) po->van()->TransportStats(&kv);
+    py::dict d;
+    for (auto& e : kv) d[py::str(e.first)] = e.second;
+    return d;
+  }, py::arg("as_role") = "worker");
   m.def("van_bytes", []() {
     Van* v = Postoffice::Get()->van();
     return std::make_pair(v->send_bytes(), v->recv_bytes());

@@ -10,7 +10,7 @@ import sys
 import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SOURCES = ["src/kernels/copy_kernels.cu", "src/kernels/update_kernels.cu", "src/kernels/model_kernels.cu"]
+SOURCES = ["src/kernels/copy_kernels.cu", "src/kernels/update_kernels.cu", "src/kernels/model_kernels.cu", "src/kernels/engine_kernels.cu"]
 INTERESTING = re.compile(r"^(F2FP|LDG|STG|LDGMC|REDG|MUFU\.(RCP|SQRT|EX2)|SYNCS|UBLKCP|UTMA|UTC)")
 HEADER = (
     "# ptxas -v summary and SASS mnemonic census of every sm_100a kernel in src/kernels\n"

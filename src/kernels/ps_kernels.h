@@ -82,6 +82,22 @@ int ps_launch_copy_signal(void* dst, const void* src, size_t n_src_bytes, int co
 /*! \brief only the signal: ordered after everything enqueued on `stream` before it */
 int ps_launch_signal(const ps_signal* sig, ps_stream_t stream);
 
+/*!
+ * \brief the copy engine (engine_kernels.cu): descriptors are POSTED into a ring in mapped host
+ *        memory and executed by an on-demand persistent kernel — no driver call per copy.
+ *        Completions are published in posting order: `value` is stored to `*flag`
+ *        (st.release.sys; flag may be null) once the bytes are visible system-wide.
+ */
+typedef struct ps_engine ps_engine;
+ps_engine* ps_engine_create(int device, int num_ctas, int idle_us);
+void ps_engine_destroy(ps_engine* e);
+int ps_engine_post(ps_engine* e, void* dst, const void* src, size_t bytes, unsigned long long* flag,
+                   unsigned long long value);
+/*! \brief has everything posted so far been completed? / wait until it has */
+int ps_engine_idle(ps_engine* e);
+void ps_engine_drain(ps_engine* e);
+void ps_engine_stats(ps_engine* e, unsigned long long* launches, unsigned long long* items);
+
 /*! \brief byte copies of up to PS_MAX_COPY_SEGS unrelated buffers per kernel launch */
 #define PS_MAX_COPY_SEGS 32
 typedef struct {

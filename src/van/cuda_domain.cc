@@ -7,6 +7,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <map>
 #include <unordered_map>
 
@@ -39,9 +40,18 @@ class CudaDomain : public MemDomain {
     PS_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
     PS_CUDA_CHECK(cudaStreamCreateWithPriority(&stream_, cudaStreamNonBlocking, hi));
     max_ctas_ = GetEnv("PS_COPY_CTAS", 0);
+    // PS_COPY_ENGINE=1: raw copies that need no stream ordering are posted to the copy engine
+    // (an on-demand persistent kernel fed through a ring in mapped host memory) instead of
+    // costing a kernel launch each. Meant for processes that own their GPU: a resident kernel
+    // and another process's kernels would only alternate by time slice.
+    if (GetEnv("PS_COPY_ENGINE", 0) != 0) {
+      engine_ = ps_engine_create(dev_, GetEnv("PS_ENGINE_CTAS", 0), GetEnv("PS_ENGINE_IDLE_US", 200));
+      if (!engine_) LOG(WARNING) << "PS_COPY_ENGINE: the copy engine could not be created; copies are launched";
+    }
   }
   ~CudaDomain() override {
     cudaSetDevice(dev_);
+    if (engine_) ps_engine_destroy(engine_);
     cudaStreamSynchronize(stream_);
     for (cudaEvent_t e : free_events_) cudaEventDestroy(e);
     for (auto& kv : imported_) cudaIpcCloseMemHandle(kv.second);
@@ -51,7 +61,12 @@ class CudaDomain : public MemDomain {
   }
   const char* name() const override { return "nvl"; }
   int device() const override { return dev_; }
-  void* Stream() override { return stream_; }
+  void* Stream() override {
+    // whoever asks may enqueue work of their own here: from now on the engine path checks that
+    // the stream is idle every time (see CopySignal)
+    stream_shared_.store(true, std::memory_order_release);
+    return stream_;
+  }
 
   bool Handles(int device_type, const void* /*ptr*/) override { return device_type == GPU; }
 
@@ -193,6 +208,10 @@ class CudaDomain : public MemDomain {
   Ticket CopyAsync(void* dst, const void* src, size_t n, int codec, float scale,
                    void* wait_event, int src_device_type = UNK) override {
     PS_CUDA_CHECK(cudaSetDevice(dev_));
+    if (engine_) {
+      ps_engine_drain(engine_);
+      launch_pending_.store(true, std::memory_order_release);
+    }
     if (wait_event) {
       PS_CUDA_CHECK(cudaStreamWaitEvent(stream_, static_cast<cudaEvent_t>(wait_event), 0));
     }
@@ -224,6 +243,10 @@ class CudaDomain : public MemDomain {
   /*! \brief raw device-to-device items share launches (ps_launch_copy_multi), one event in all */
   Ticket CopyBatchAsync(const std::vector<CopyItem>& items) override {
     PS_CUDA_CHECK(cudaSetDevice(dev_));
+    if (engine_) {
+      ps_engine_drain(engine_);
+      launch_pending_.store(true, std::memory_order_release);
+    }
     for (const CopyItem& it : items) {
       if (it.wait_event) {
         PS_CUDA_CHECK(cudaStreamWaitEvent(stream_, static_cast<cudaEvent_t>(it.wait_event), 0));
@@ -292,6 +315,21 @@ class CudaDomain : public MemDomain {
   bool CopySignal(const CopyItem& item, void* word, uint64_t value) override {
     if (!sig_counter_ || !word) return false;
     PS_CUDA_CHECK(cudaSetDevice(dev_));
+    if (engine_) {
+      // The two paths must not overtake each other (completions on one word are ordered): the
+      // engine takes a copy only while nothing is pending on the stream, and the stream gets work
+      // only once the engine has retired everything it was given.
+      const bool eligible = item.wait_event == nullptr && item.codec == kCodecRaw &&
+                            (item.n_src_bytes == 0 || item.src_device_type == GPU);
+      if (eligible && StreamIdle()) {
+        CHECK_EQ(ps_engine_post(engine_, item.dst, item.src, item.n_src_bytes,
+                                static_cast<unsigned long long*>(word), value), 0)
+            << "copy engine: post failed";
+        return true;
+      }
+      ps_engine_drain(engine_);
+      launch_pending_.store(true, std::memory_order_release);
+    }
     if (item.wait_event) {
       PS_CUDA_CHECK(cudaStreamWaitEvent(stream_, static_cast<cudaEvent_t>(item.wait_event), 0));
     }
@@ -342,7 +380,27 @@ class CudaDomain : public MemDomain {
     free_events_.push_back(ev);
   }
 
+  void EngineStats(uint64_t* launches, uint64_t* items) override {
+    unsigned long long l = 0, i = 0;
+    if (engine_) ps_engine_stats(engine_, &l, &i);
+    *launches = l;
+    *items = i;
+  }
+
  private:
+  /*! \brief has everything ever enqueued on the data stream completed? */
+  bool StreamIdle() {
+    if (!launch_pending_.load(std::memory_order_acquire) && !stream_shared_.load(std::memory_order_acquire)) {
+      return true;
+    }
+    const cudaError_t e = cudaStreamQuery(stream_);
+    if (e == cudaSuccess) {
+      launch_pending_.store(false, std::memory_order_release);
+      return true;
+    }
+    cudaGetLastError();
+    return false;
+  }
   cudaEvent_t AcquireEvent() {
     {
       std::lock_guard<std::mutex> lk(mu_);
@@ -365,6 +423,9 @@ class CudaDomain : public MemDomain {
   std::vector<std::unique_ptr<DevArena>> arenas_;
   int dev_;
   int max_ctas_ = 0;
+  ps_engine* engine_ = nullptr;
+  std::atomic<bool> launch_pending_{false};  // the launch path has been used since the stream was last seen idle
+  std::atomic<bool> stream_shared_{false};   // Stream() was handed out: foreign work may be on it
   unsigned* sig_counter_ = nullptr;  // CTA arrival counter of the signalling kernels (self-resetting)
   cudaStream_t stream_ = nullptr;
   std::mutex mu_;

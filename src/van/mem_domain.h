@@ -165,6 +165,11 @@ class MemDomain {
   virtual void Wait(Ticket t) = 0;
   /*! \brief non-blocking: has the copy behind `t` completed? (does not recycle the ticket) */
   virtual bool Ready(Ticket t) { return t.event == nullptr; }
+  /*! \brief copy-engine accounting (kernel launches it needed, descriptors it executed) */
+  virtual void EngineStats(uint64_t* launches, uint64_t* items) {
+    *launches = 0;
+    *items = 0;
+  }
   /*! \brief stream-like handle applications may enqueue their own work on (may be null) */
   virtual void* Stream() { return nullptr; }
   /*! \brief the van stopped: drop global names (mappings stay valid until the process ends) */

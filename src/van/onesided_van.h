@@ -107,6 +107,15 @@ class OneSidedVan : public TcpVan {
   void* AllocExportable(size_t bytes) override { return domain_->Alloc(bytes); }
   void FreeExportable(void* p) override { domain_->Free(p); }
   void* DataStream() override { return domain_->Stream(); }
+  void TransportStats(std::vector<std::pair<std::string, uint64_t>>* out) override {
+    uint64_t launches = 0, items = 0;
+    domain_->EngineStats(&launches, &items);
+    out->emplace_back("onesided_copies", copies_.load());
+    out->emplace_back("onesided_bytes", copy_bytes_.load());
+    out->emplace_back("gated_frames", gated_frames_.load());
+    out->emplace_back("engine_launches", launches);
+    out->emplace_back("engine_items", items);
+  }
   MemDomain* domain() { return domain_.get(); }
 
   /*! \brief local address of `mem` inside a region node `peer` announced, or null */
