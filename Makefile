@@ -48,7 +48,7 @@ LIB := $(BUILD)/libpslite.a
 
 APPS := $(BUILD)/kv_hello $(BUILD)/test_benchmark $(BUILD)/test_kv_app $(BUILD)/test_simple_app $(BUILD)/test_connection $(BUILD)/test_ipc_benchmark $(BUILD)/test_benchmark_stress $(BUILD)/test_recovery
 ifeq ($(USE_CUDA),1)
-APPS += $(BUILD)/kernel_bench
+APPS += $(BUILD)/kernel_bench $(BUILD)/engine_bench
 endif
 TESTS := $(patsubst cpp_tests/%.cc,$(BUILD)/cpp_tests/%,$(wildcard cpp_tests/*.cc))
 

@@ -253,10 +253,12 @@ void SteadyState(KVWorker<char>* kv, KeySet& ks, int total_keys, int tid) {
   auto t0 = std::chrono::steady_clock::now();
   int rounds_in_window = 0;
   double best_gbps = 0;
+  double issue_ns = 0, wait_ns = 0;  // per window: time spent issuing the round's requests / waiting for them
   Van* van = Postoffice::GetWorker(tid)->van();
   for (int round = 0; round < opt.total_rounds; ++round) {
     // all messages of a round are issued back to back: with PS_COALESCE_LAUNCHES their one-sided
     // copies share kernel launches and one completion event (a no-op otherwise)
+    const auto t_round = std::chrono::steady_clock::now();
     {
       Van::CorkScope cork(van);  // released before the first Wait: the messages leave here
       for (int k = 0; k < total_keys; ++k) {
@@ -270,15 +272,21 @@ void SteadyState(KVWorker<char>* kv, KeySet& ks, int total_keys, int tid) {
         if (opt.mode != PUSH_ONLY) in_flight.push_back(kv->ZPull(ks.keys[k], &ks.vals[k], &ks.lens[k]));
       }
     }
+    const auto t_issued = std::chrono::steady_clock::now();
     for (int ts : in_flight) kv->Wait(ts);
     in_flight.clear();
+    issue_ns += std::chrono::duration<double, std::nano>(t_issued - t_round).count();
+    wait_ns += std::chrono::duration<double, std::nano>(std::chrono::steady_clock::now() - t_issued).count();
     if (++rounds_in_window % opt.log_every != 0) continue;
     const auto t1 = std::chrono::steady_clock::now();
     const double ns = std::chrono::duration<double, std::nano>(t1 - t0).count();
     const double gbps = 8.0 * opt.len * total_keys * rounds_in_window / ns;
     best_gbps = std::max(best_gbps, gbps);
     LL << "[" << tid << "]\tApplication goodput: " << gbps
-       << " Gbps.\tAvg latency = " << ns / rounds_in_window / total_keys / 1000.0 << " ns per key";
+       << " Gbps.\tAvg latency = " << ns / rounds_in_window / total_keys / 1000.0 << " ns per key"
+       << " (issue " << issue_ns / rounds_in_window / total_keys / 1000.0 << " + wait "
+       << wait_ns / rounds_in_window / total_keys / 1000.0 << " us per key)";
+    issue_ns = wait_ns = 0;
     if (opt.json) {
       fprintf(stdout,
               "{\"bench\":\"test_benchmark\",\"mode\":%d,\"len\":%d,\"keys\":%d,\"tid\":%d,"

@@ -8,8 +8,11 @@ BASELINE.json "push+pull GB/s ... (test_benchmark)"): every worker ZPush-es and 
 `keys_per_server x num_servers` values of `len` bytes per step (= one round of the
 reference's timing loop) and the job reports payload goodput with the reference's
 formula (payload counted once per push+pull pair), in GB/s, summed over workers.
-    N = 1        : 1 worker + 1 server co-located on the GPU (test_ipc_benchmark shape)
-    N = 2, 4, 8  : N/2 worker GPUs + N/2 server GPUs over the NVLink van (4w+4s at N=8)
+    every N      : N workers + N servers, one of each co-located on every GPU ("joint"; the same
+                   topology at every N, so the payload per step grows with N and the driver's
+                   scaling efficiency compares like with like). Worker r talks to all N servers:
+                   1/N of its traffic stays in local HBM, the rest crosses NVLink.
+    --topology split : N/2 worker GPUs + N/2 server GPUs (4w+4s at N=8, BASELINE.json config 2)
 Values live in HBM and move as one-sided sm_100a copy kernels into peer memory; only
 descriptors use TCP. `--metric llama` instead times Llama-3-8B synchronous PS training
 (fp8 gradient push, fused server-side AdamW, bf16 pull) in tokens/s.
@@ -55,7 +58,7 @@ def parse_args():
     ap.add_argument("--e2e-native", action="store_true",
                     help="also time the end-to-end round through KVWorker.staged_push_pull (the H2D / push / "
                          "pull / D2H pipeline in one native call instead of a Python loop)")
-    ap.add_argument("--copy-engine", type=int, default=int(os.environ.get("PS_COPY_ENGINE", "0")),
+    ap.add_argument("--copy-engine", type=int, default=int(os.environ.get("PS_COPY_ENGINE", "1")),
                     help="1: raw copies without a producer event are posted to the copy engine (on-demand "
                          "persistent kernel fed from a host-mapped ring) instead of one launch each")
     ap.add_argument("--sweep", default="", help="comma-separated extra message sizes (bytes) to report")
@@ -194,7 +197,7 @@ def run_pushpull(args, dist: Dist) -> dict:
 
     C = native()
     gpu = Gpu(args, dist.local_rank)
-    topo = args.topology or ("joint" if dist.world == 1 else "split")
+    topo = args.topology or "joint"
     ctx = init_ps(topo, van=args.van or ("nvl" if gpu.cuda else "shm"),
                   extra_env={"PS_COPY_ENGINE": int(args.copy_engine)})
     server = C.BenchServer(0) if ctx.is_server else None
@@ -527,7 +530,8 @@ def run_reference(args, dist: Dist) -> dict:
         return {"impl": "reference", "unavailable": res["why"]}
     out = None
     if dist.rank == 0:
-        W = S = 1 if dist.world == 1 else dist.world // 2
+        # same shape as our arm: N workers + N servers (N/2 + N/2 with --topology split)
+        W = S = dist.world if (args.topology or "joint") == "joint" else max(1, dist.world // 2)
         port = 12000 + (os.getpid() % 20000)
         env = dict(os.environ)
         env.update({"DMLC_NUM_WORKER": str(W), "DMLC_NUM_SERVER": str(S),
@@ -577,6 +581,9 @@ def run_reference(args, dist: Dist) -> dict:
                               "parallelism": f"{W}w+{S}s processes, reference ZMQ van over ipc:// with CPU buffers "
                                              "(its RDMA/UCX vans need ibverbs/UCX, absent in this image; ZMQ cannot carry device pointers)"},
                    "timing": "host clock inside the reference binary (its own goodput print), last LOG_DURATION window",
+                   # the reference's buffers live in host memory: its goodput IS host-to-host end to end
+                   "e2e": {"value": value, "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                           "note": "values start and end in host memory; no device involved"},
                    "wall_s": wall, "gpu_launches": 0}
         else:
             out = {"impl": "reference", "unavailable": "reference test_benchmark did not report goodput"}

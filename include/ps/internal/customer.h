@@ -109,6 +109,7 @@ class Customer {
   const int customer_id_;
   RecvHandle recv_handle_;
   Postoffice* postoffice_;
+  std::atomic<uint64_t> wait_sleeps_{0};  // WaitRequest calls that outlasted the spin window
   bool direct_dispatch_ = false;       // PS_DIRECT_DISPATCH=1: no customer thread at all
   std::atomic<bool> inline_{false};    // set_inline_dispatch
   std::atomic<int> pending_{0};        // queued or being handled by the customer thread

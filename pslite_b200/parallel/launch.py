@@ -111,6 +111,10 @@ def init_ps(topology: str = "joint", van: str | None = None, extra_env: dict | N
         env["DMLC_NODE_HOST"] = "127.0.0.1"
     elif os.environ.get("DMLC_NODE_HOST"):
         env["DMLC_NODE_HOST"] = os.environ["DMLC_NODE_HOST"]
+    if van == "nvl":
+        # one process per GPU: raw copies without a producer event go through the copy engine (an
+        # on-demand persistent kernel fed from a host-mapped ring) instead of one launch each
+        env["PS_COPY_ENGINE"] = os.environ.get("PS_COPY_ENGINE", "1")
     if extra_env:
         env.update(extra_env)
     sched = None

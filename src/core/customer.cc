@@ -36,6 +36,10 @@ void Customer::Start() {
 }
 
 Customer::~Customer() {
+  if (postoffice_->verbose() >= 1) {
+    LOG(INFO) << "customer " << customer_id_ << " of app " << app_id_ << ": Wait() went to sleep "
+              << wait_sleeps_.load() << " times";
+  }
   if (started_) postoffice_->RemoveCustomer(this);
   if (recv_thread_) {
     Message bye;
@@ -98,11 +102,23 @@ void Customer::WaitRequest(int timestamp) {
   if (spin_us > 0) {
     // poll the completion counter, not the tracker: the customer thread needs tracker_mu_ for
     // every response and must not fight this thread for it
-    const auto until = std::chrono::steady_clock::now() + std::chrono::microseconds(spin_us);
+    // A short hot phase, then sched_yield between polls: the thread that completes the request
+    // may have been put on THIS cpu by the scheduler (it wakes us with a futex, and wake-affine
+    // placement then lets the woken spinner run in front of its own waker) — a waiter that only
+    // executes `pause` would keep it off the cpu for the whole window.
+    static const int hot_us = GetEnv("PS_WAIT_HOT_US", 2);
+    const auto t0 = std::chrono::steady_clock::now();
+    const auto hot_until = t0 + std::chrono::microseconds(hot_us);
+    const auto until = t0 + std::chrono::microseconds(spin_us);
     uint64_t seen = completions_.load(std::memory_order_acquire);
     lk.unlock();
+    bool hot = true;
     for (;;) {
-      for (int i = 0; i < 16; ++i) ThreadsafeQueue<Message>::CpuRelax();
+      if (hot) {
+        for (int i = 0; i < 16; ++i) ThreadsafeQueue<Message>::CpuRelax();
+      } else {
+        std::this_thread::yield();
+      }
       const uint64_t now = completions_.load(std::memory_order_acquire);
       if (now != seen) {
         seen = now;
@@ -110,7 +126,9 @@ void Customer::WaitRequest(int timestamp) {
         if (done()) return;
         lk.unlock();
       }
-      if (std::chrono::steady_clock::now() >= until) break;
+      const auto t = std::chrono::steady_clock::now();
+      if (t >= until) break;
+      if (hot && t >= hot_until) hot = false;
     }
     lk.lock();
     if (done()) return;
@@ -118,6 +136,7 @@ void Customer::WaitRequest(int timestamp) {
   // responses wake only the threads that wait for *their* request (a round of the benchmark
   // has 80 requests in flight: waking the application thread for each costs two system calls)
   if (Slot* s = Find(timestamp)) ++s->waiters;
+  wait_sleeps_.fetch_add(1, std::memory_order_relaxed);
   // a request that never completes is the usual face of a transport bug or a dead peer: say
   // which one it is instead of hanging silently (PS_WAIT_WARN_S seconds, 0 = never)
   static const int warn_s = GetEnv("PS_WAIT_WARN_S", 60);
@@ -177,7 +196,8 @@ bool Customer::TryInline(const Message& m) {
   if (!inline_.load(std::memory_order_acquire) || pending_.load(std::memory_order_acquire) != 0) return false;
   // bytes this thread would have to stream itself: the payload it just received in a frame, and on
   // two-sided vans the reply a pull asks for
-  if (m.meta.data_size > inline_max_bytes_) return false;
+  // (a one-sided van only delivers a descriptor: the payload is already in place, however large)
+  if (payload_in_frames_ && m.meta.data_size > inline_max_bytes_) return false;
   if (payload_in_frames_ && m.meta.request && !m.meta.push && m.meta.val_len > inline_max_bytes_) return false;
   if (!deliver_mu_.try_lock()) return false;  // another van's receive thread is in the handler
   if (pending_.load(std::memory_order_acquire) != 0) {  // it queued something meanwhile: keep the order

@@ -10,18 +10,20 @@
  * on the issuing thread, every time. Here the van POSTS a 64-byte descriptor into a ring in
  * mapped host memory (a few stores, no driver call) and a resident kernel executes it:
  *
- *   CTA 0 (dispatcher, one thread)   polls `posted` in host memory, copies new descriptors into
- *                                    a device-side ring and publishes its tail at gpu scope
- *   CTAs 1..G-1 (workers)            walk the device ring in order; an item is cut into 64 KB
+ *   CTA 0, warp 0 (dispatcher)       polls `posted` in host memory, copies new descriptors into
+ *                                    a device-side ring (eight per PCIe round trip) and
+ *                                    publishes its tail at gpu scope
+ *   CTAs 1..G-1 (workers)            walk the device ring in order; an item is cut into 256 KB
  *                                    chunks and spread over as many workers as it has chunks
  *                                    (start CTA rotates, so small items land on different CTAs
  *                                    and many items are in flight at once); stores may target
  *                                    peer HBM over NVLink
- *   completion                       every participating CTA fences at system scope and counts
- *                                    itself in; the last one waits for its turn (completions
- *                                    are published in posting order, like a stream) and stores
- *                                    the item's value to its flag with st.release.sys — the
- *                                    gate word of the receiver's descriptor ring
+ *   completion (one thread of CTA 0) every participating CTA fences at system scope and counts
+ *                                    itself in; the completer walks the items in posting order
+ *                                    (completions are published like on a stream) and stores an
+ *                                    item's value to its flag with st.release.sys — the gate
+ *                                    word of the receiver's descriptor ring. Finished neighbours
+ *                                    that signal the same word are folded into one store.
  *
  * The kernel is "on-demand persistent": it exits after `idle_us` without work (so device-wide
  * synchronisation still terminates) and the next post relaunches it. The exit is a two-phase
@@ -53,8 +55,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr unsigned kHostRing = 4096;     // descriptors in mapped host memory (power of two)
-constexpr unsigned kDevRing = 256;       // descriptors staged in device memory (power of two)
-constexpr unsigned long long kChunk = 64 * 1024;
+constexpr unsigned kDevRing = 1024;      // descriptors staged in device memory (power of two)
+constexpr unsigned kMaxWorkers = 512;
 
 struct Item {  // 64 bytes
   unsigned char* dst;
@@ -81,6 +83,7 @@ struct DevState {
   unsigned long long tail;          // descriptors published to the workers
   unsigned long long signal_head;   // next completion to publish
   unsigned long long stop_at;       // ~0 while running; the dispatcher's final head when leaving
+  unsigned long long progress[kMaxWorkers];  // per worker CTA: first descriptor it has not read yet
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const volatile unsigned long long* p) {
@@ -140,55 +143,143 @@ __device__ __forceinline__ void copy_chunk(unsigned char* __restrict__ dst,
   for (unsigned long long i = done + threadIdx.x; i < len; i += kThreads) dst[i] = src[i];
 }
 
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_sys(volatile unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+/*! \brief how many worker CTAs an item of `bytes` is spread over */
+__device__ __forceinline__ unsigned Participants(unsigned long long bytes, unsigned W, unsigned long long kChunk) {
+  const unsigned long long nchunks = (bytes + kChunk - 1) / kChunk;
+  return nchunks >= W ? W : (nchunks ? static_cast<unsigned>(nchunks) : 1u);
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_copy_engine(HostCtl* ctl, const Item* host_ring, DevState* st, unsigned long long head0,
-              unsigned long long epoch, unsigned long long idle_ns) {
+              unsigned long long epoch, unsigned long long idle_ns, unsigned long long kChunk) {
   const unsigned W = gridDim.x - 1;  // worker CTAs
   if (blockIdx.x == 0) {
-    // ---------------- dispatcher ----------------
-    if (threadIdx.x != 0) return;
-    unsigned long long head = head0, idle_since = 0;
-    for (;;) {
-      const unsigned long long posted = ld_acquire_sys(&ctl->posted);
-      if (posted != head) {
-        idle_since = 0;
-        while (head != posted) {
-          // a slot of the device ring is free again once its completion has been published
-          while (head - ld_acquire_gpu(&st->signal_head) >= kDevRing) {
+    const unsigned warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp == 0) {
+      // ---------------- dispatcher (one warp) ----------------
+      // lane 0 polls `posted` in host memory; new descriptors cross PCIe eight at a time (every
+      // lane moves 16 bytes), so a burst costs one round trip per eight messages, not one each
+      unsigned long long head = head0, idle_since = 0, safe = head0;
+      for (;;) {
+        unsigned long long posted = 0;
+        if (lane == 0) posted = ld_acquire_sys(&ctl->posted);
+        posted = __shfl_sync(0xffffffffu, posted, 0);
+        if (posted != head) {
+          idle_since = 0;
+          while (head != posted) {
+            const unsigned n = posted - head < 8 ? static_cast<unsigned>(posted - head) : 8u;
+            // a slot of the device ring is free again once its completion has been published AND
+            // every worker has read it (workers that take no part in an item still read it to keep
+            // their rotation in step, and may lag behind the completer)
+            if (head + n - safe > kDevRing) {
+              for (;;) {
+                unsigned long long m = ld_acquire_gpu(&st->signal_head);
+                for (unsigned w = lane; w < W; w += 32) {
+                  const unsigned long long p = ld_acquire_gpu(&st->progress[w]);
+                  m = p < m ? p : m;
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                  const unsigned long long other = __shfl_xor_sync(0xffffffffu, m, o);
+                  m = other < m ? other : m;
+                }
+                safe = m;
+                if (head + n - safe <= kDevRing) break;
+              }
+            }
+            __syncwarp();
+            if ((lane >> 2) < n) {
+              const unsigned long long idx = head + (lane >> 2);
+              const int4 v = __ldcv(reinterpret_cast<const int4*>(host_ring + (idx & (kHostRing - 1))) + (lane & 3));
+              reinterpret_cast<int4*>(&st->ring[idx & (kDevRing - 1)])[lane & 3] = v;
+            }
+            __syncwarp();
+            head += n;
+            if (lane == 0) {
+              __threadfence();
+              st_release_gpu(&st->tail, head);
+            }
           }
-          const int4* s = reinterpret_cast<const int4*>(host_ring + (head & (kHostRing - 1)));
-          int4* d = reinterpret_cast<int4*>(&st->ring[head & (kDevRing - 1)]);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) d[q] = __ldcv(s + q);  // host memory: never from a stale cache line
-          ++head;
-          st_release_gpu(&st->tail, head);
+          continue;
         }
-        continue;
+        int leave = 0;
+        if (lane == 0) {
+          const unsigned long long now = globaltimer_ns();
+          if (ld_acquire_gpu(&st->signal_head) != head) {
+            idle_since = 0;  // copies still running: not idle
+          } else if (idle_since == 0) {
+            idle_since = now;
+          } else if (now - idle_since >= idle_ns) {
+            // nothing for a while: leave — unless the host posts right now. Phase 1: say so ...
+            st_release_sys(&ctl->exit_intent, head + 1);
+            __threadfence_system();
+            // ... phase 2: look again. The host does the mirror image (post, fence, read the
+            // intent), so one of the two always notices the other.
+            if (ld_acquire_sys(&ctl->posted) != head) {
+              st_release_sys(&ctl->exit_intent, 0ull);
+              idle_since = 0;
+            } else {
+              st_release_gpu(&st->stop_at, head);  // the completer finishes the handshake
+              leave = 1;
+            }
+          }
+        }
+        if (__shfl_sync(0xffffffffu, leave, 0)) return;
       }
-      const unsigned long long now = globaltimer_ns();
-      if (idle_since == 0) {
-        idle_since = now;
-        continue;
-      }
-      if (now - idle_since < idle_ns) continue;
-      // nothing for a while: leave — unless the host posts right now. Phase 1: say so ...
-      st_release_sys(&ctl->exit_intent, head + 1);
-      __threadfence_system();
-      // ... phase 2: look again. The host does the mirror image (post, fence, read the intent),
-      // so one of the two always notices the other.
-      if (ld_acquire_sys(&ctl->posted) != head) {
-        st_release_sys(&ctl->exit_intent, 0ull);
-        idle_since = 0;
-        continue;
-      }
-      st_release_gpu(&st->stop_at, head);
-      while (ld_acquire_gpu(&st->signal_head) != head) {
-      }
-      ctl->exit_head = head;
-      __threadfence_system();
-      st_release_sys(&ctl->exit_final, epoch);
-      return;
     }
+    if (warp == 1 && lane == 0) {
+      // ---------------- completer (one thread) ----------------
+      // Publishes completions in posting order, like a stream: item k is complete when all of
+      // its participants have counted themselves in (each after a system-scope fence behind its
+      // stores). Consecutive finished items that signal the same word are folded into ONE
+      // st.release.sys of the newest value: the receiver only compares "reached k yet?".
+      unsigned long long k = head0;
+      for (;;) {
+        unsigned long long tail = ld_acquire_gpu(&st->tail);
+        if (tail == k) {
+          if (ld_acquire_gpu(&st->stop_at) == k) {
+            ctl->exit_head = k;
+            __threadfence_system();
+            st_release_sys(&ctl->exit_final, epoch);
+            return;
+          }
+          continue;
+        }
+        const Item* it = &st->ring[k & (kDevRing - 1)];
+        const unsigned P = Participants(it->bytes, W, kChunk);
+        while (ld_acquire_gpu_u32(&st->arrive[k & (kDevRing - 1)]) != P) {
+        }
+        st->arrive[k & (kDevRing - 1)] = 0;
+        unsigned long long* flag = it->flag;
+        unsigned long long value = it->flag_value;
+        ++k;
+        // fold in whatever else has finished already
+        while (k != tail) {
+          const Item* nx = &st->ring[k & (kDevRing - 1)];
+          if (nx->flag != flag) break;
+          if (ld_acquire_gpu_u32(&st->arrive[k & (kDevRing - 1)]) != Participants(nx->bytes, W, kChunk)) break;
+          st->arrive[k & (kDevRing - 1)] = 0;
+          value = nx->flag_value;
+          ++k;
+        }
+        if (flag) {
+          st_release_sys(flag, value);
+          st_relaxed_sys(&ctl->retired, k);
+        } else {
+          st_release_sys(&ctl->retired, k);
+        }
+        st_release_gpu(&st->signal_head, k);
+      }
+    }
+    return;
   }
   // ---------------- workers ----------------
   __shared__ Item item;
@@ -201,6 +292,7 @@ k_copy_engine(HostCtl* ctl, const Item* host_ring, DevState* st, unsigned long l
       for (;;) {
         if (ld_acquire_gpu(&st->tail) > k) {
           item = st->ring[k & (kDevRing - 1)];
+          st_release_gpu(&st->progress[me], k + 1);  // the dispatcher may reuse the slot
           break;
         }
         if (ld_acquire_gpu(&st->stop_at) <= k) {
@@ -212,8 +304,8 @@ k_copy_engine(HostCtl* ctl, const Item* host_ring, DevState* st, unsigned long l
     __syncthreads();
     if (leave) return;
     const unsigned long long bytes = item.bytes;
-    const unsigned long long nchunks = bytes ? (bytes + kChunk - 1) / kChunk : 0;
-    const unsigned P = nchunks >= W ? W : (nchunks ? static_cast<unsigned>(nchunks) : 1u);
+    const unsigned long long nchunks = (bytes + kChunk - 1) / kChunk;
+    const unsigned P = Participants(bytes, W, kChunk);
     const unsigned r = (me + W - rot) % W;
     rot = (rot + P) % W;
     if (r < P) {
@@ -226,17 +318,8 @@ k_copy_engine(HostCtl* ctl, const Item* host_ring, DevState* st, unsigned long l
       }
       __syncthreads();
       if (threadIdx.x == 0) {
-        __threadfence_system();
-        if (atomicAdd(&st->arrive[k & (kDevRing - 1)], 1u) == P - 1) {
-          // every chunk of item k is in place; completions leave in posting order
-          while (ld_acquire_gpu(&st->signal_head) != k) {
-          }
-          st->arrive[k & (kDevRing - 1)] = 0;
-          __threadfence_system();
-          if (item.flag) st_release_sys(item.flag, item.flag_value);
-          st_release_sys(&ctl->retired, k + 1);
-          st_release_gpu(&st->signal_head, k + 1);
-        }
+        __threadfence_system();  // this CTA's bytes are visible system-wide before it counts itself in
+        atomicAdd(&st->arrive[k & (kDevRing - 1)], 1u);
       }
     }
     __syncthreads();  // `item` is overwritten by the next iteration
@@ -253,6 +336,9 @@ struct ps_engine {
   int device = 0;
   int grid = 0;
   unsigned long long idle_ns = 0;
+  // bytes one worker CTA moves per turn (PS_ENGINE_CHUNK_KB). Measured over NVLink, 4 MB messages,
+  // 296 workers: 32 KB 490 GB/s, 64 KB 595, 128 KB 613, 256 KB 675 (profiles/r2/engine_bench_peer_sweep.txt)
+  unsigned long long chunk = 256 * 1024;
   cudaStream_t stream = nullptr;
   HostCtl* ctl = nullptr;        // host address
   HostCtl* ctl_dev = nullptr;    // the same memory as the device sees it
@@ -278,7 +364,7 @@ bool EngineLaunch(ps_engine* e) {
     return false;
   }
   k_copy_engine<<<e->grid, kThreads, 0, e->stream>>>(e->ctl_dev, e->ring_dev, e->state, e->next_head, e->epoch,
-                                                     e->idle_ns);
+                                                     e->idle_ns, e->chunk);
   if (cudaGetLastError() != cudaSuccess) return false;
   ps_kernels_internal::CountLaunch(1);
   ++e->launches;
@@ -300,11 +386,16 @@ extern "C" ps_engine* ps_engine_create(int device, int num_ctas, int idle_us) {
     return nullptr;
   }
   const int sms = ps_kernels_internal::NumSMs();
-  int grid = num_ctas > 0 ? num_ctas : sms + 1;  // default: one worker per SM + the dispatcher
-  if (grid > sms * (per_sm > 2 ? 2 : per_sm)) grid = sms * (per_sm > 2 ? 2 : per_sm);
+  int grid = num_ctas > 0 ? num_ctas : 2 * sms + 1;  // default: two workers per SM + the dispatcher's CTA
+  if (grid > sms * (per_sm > 2 ? 2 : per_sm) + 1) grid = sms * (per_sm > 2 ? 2 : per_sm) + 1;
+  if (grid > static_cast<int>(kMaxWorkers)) grid = static_cast<int>(kMaxWorkers);
   if (grid < 2) grid = 2;
   e->grid = grid;
   e->idle_ns = static_cast<unsigned long long>(idle_us > 0 ? idle_us : 200) * 1000ull;
+  if (const char* ck = getenv("PS_ENGINE_CHUNK_KB")) {
+    const long kb = atol(ck);
+    if (kb >= 4 && kb <= 16384) e->chunk = static_cast<unsigned long long>(kb) * 1024ull;
+  }
   bool ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
   ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&e->ctl), sizeof(HostCtl), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess;
   ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&e->ring), sizeof(Item) * kHostRing, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess;

@@ -76,6 +76,7 @@ class OneSidedVan : public TcpVan {
     }
     PS_VLOG(1) << type_ << " van " << my_node_.id << ": " << copies_.load() << " one-sided copies, "
                << gated_frames_.load() << " descriptors gated by the copy engine";
+    PS_VLOG(1) << type_ << " van: receive thread slept " << num_blocking_waits() << " times";
     std::lock_guard<SpinMutex> lk(rv_mu_);
     push_slots_.clear();
     landing_.clear();
@@ -113,6 +114,7 @@ class OneSidedVan : public TcpVan {
     out->emplace_back("onesided_copies", copies_.load());
     out->emplace_back("onesided_bytes", copy_bytes_.load());
     out->emplace_back("gated_frames", gated_frames_.load());
+    out->emplace_back("recv_thread_sleeps", num_blocking_waits());
     out->emplace_back("engine_launches", launches);
     out->emplace_back("engine_items", items);
   }

@@ -151,7 +151,9 @@ class TcpVan : public Van {
     // wanted: with PS_RESEND a retransmitted duplicate can arrive after the caller has
     // already consumed the first copy and released the buffer
     direct_pull_ = GetEnv("PS_TCP_DIRECT_PULL", 1) != 0 && GetEnv("PS_RESEND", 0) == 0;
-    use_pipes_ = GetEnv("PS_SHM_PIPE", 1) != 0;
+    // BYTEPS_ENABLE_IPC=0 (the reference's switch for its shared-memory side transport,
+    // src/rdma_van.h:44-46) turns the same-host rings off as well
+    use_pipes_ = GetEnv("PS_SHM_PIPE", 1) != 0 && GetEnv("BYTEPS_ENABLE_IPC", 1) != 0;
     pipe_bytes_ = static_cast<size_t>(GetEnv("PS_SHM_PIPE_KB", 256)) << 10;
     if (use_pipes_) {
       static const int swept = SweepStaleShm("pslb200_");  // rings of processes that were killed
@@ -336,6 +338,9 @@ class TcpVan : public Van {
     }
     return SendFrame(msg);
   }
+
+  /*! \brief how often the receive thread gave up polling and slept (each wake-up costs 50-300 us on a VM) */
+  uint64_t num_blocking_waits() const { return blocking_waits_.load(); }
 
   /*! \brief can frames to `recver` be gated on completions the copy engine signals itself? */
   bool PeerGated(int recver) {
@@ -561,6 +566,7 @@ class TcpVan : public Van {
         continue;
       }
       struct epoll_event evs[16];
+      if (timeout_ms != 0) ++blocking_waits_;
       int n = epoll_wait(epfd_, evs, 16, timeout_ms);
       if (timeout_ms != 0) {
         WakeFromPipes();
@@ -1173,6 +1179,7 @@ class TcpVan : public Van {
   bool handoff_ = GetEnv("PS_LOCAL_HANDOFF", 0) != 0;
   std::atomic<uint64_t> handoffs_{0};
   uint32_t spin_polls_ = 0;
+  std::atomic<uint64_t> blocking_waits_{0};                    // times the receive thread went to sleep in epoll
   bool gates_pending_ = false;                                 // receive thread: a ring head waits for its gate
   std::vector<int> pipe_fds_;                                  // inbound connections with a ring
   size_t pipe_cursor_ = 0;
