@@ -219,27 +219,35 @@ def run_pushpull(args, dist: Dist) -> dict:
     def verify(tag: str):
         """untimed data check: distinct patterns go up, the buffers are cleared, the pull must bring
         every byte back (the timed rounds move constant bytes and would not notice a lost copy)"""
-        if not ctx.is_worker:
-            return
         idx = sorted({0, 1, total_keys // 2, total_keys - 1})
         want = {}
-        for k in idx:
-            pat = (torch.arange(args.len, dtype=torch.int32, device=vals[k].device) * (k + 3) + ctx.worker_rank + 7).to(torch.uint8)
-            vals[k].copy_(pat)
-            want[k] = pat
-        gpu.sync()
-        kv.wait_all(kv.push_pull_batch([keys[k] for k in idx], [vals[k] for k in idx],
-                                       order_after_current_stream=False, pull=False))
-        for k in idx:
-            vals[k].zero_()
-        gpu.sync()
-        kv.wait_all(kv.push_pull_batch([keys[k] for k in idx], [vals[k] for k in idx],
-                                       order_after_current_stream=False, push=False))
-        gpu.sync()
-        for k in idx:
-            assert torch.equal(vals[k], want[k]), f"{tag}: key {k} came back different from what was pushed"
-            vals[k].fill_(1)
-        gpu.sync()
+        if ctx.is_worker:
+            # every worker pushes the same bytes for a key (the benchmark's servers answer a pull from
+            # the slot of whichever worker pushed that key first)
+            for k in idx:
+                pat = (torch.arange(args.len, dtype=torch.int32, device=vals[k].device) * (k + 3) + 7).to(torch.uint8)
+                vals[k].copy_(pat)
+                want[k] = pat
+            gpu.sync()
+            kv.wait_all(kv.push_pull_batch([keys[k] for k in idx], [vals[k] for k in idx],
+                                           order_after_current_stream=False, pull=False))
+            for k in idx:
+                vals[k].zero_()
+            gpu.sync()
+        dist.barrier()  # all patterns are up before anybody pulls
+        if ctx.is_worker:
+            kv.wait_all(kv.push_pull_batch([keys[k] for k in idx], [vals[k] for k in idx],
+                                           order_after_current_stream=False, push=False))
+            gpu.sync()
+            for k in idx:
+                assert torch.equal(vals[k], want[k]), f"{tag}: key {k} came back different from what was pushed"
+        dist.barrier()  # nobody restores the constant bytes while a peer still compares
+        if ctx.is_worker:
+            for k in idx:
+                vals[k].fill_(1)
+            gpu.sync()
+            kv.wait_all(kv.push_pull_batch([keys[k] for k in idx], [vals[k] for k in idx],
+                                           order_after_current_stream=False, pull=False))
 
     def timed(fn, steps: int):
         dist.barrier()
