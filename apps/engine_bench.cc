@@ -165,6 +165,50 @@ int main(int argc, char** argv) {
       fflush(stdout);
     }
   }
+  if (peer) {
+    // both directions at once: an engine on each GPU writes into the other one's memory (what every
+    // GPU of a joint job does: its worker pushes out while its server answers pulls)
+    CK(cudaSetDevice(1));
+    cudaError_t pe = cudaDeviceEnablePeerAccess(0, 0);
+    if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) CK(pe);
+    cudaGetLastError();
+    unsigned char *src1 = nullptr, *dst0 = nullptr;
+    CK(cudaMalloc(&src1, kMaxMsg * kSlots));
+    CK(cudaSetDevice(0));
+    CK(cudaMalloc(&dst0, kMaxMsg * kSlots));
+    unsigned long long* flag1 = nullptr;
+    CK(cudaHostAlloc(reinterpret_cast<void**>(&flag1), 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    unsigned long long* flag1_dev = nullptr;
+    CK(cudaSetDevice(1));
+    CK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&flag1_dev), flag1, 0));
+    ps_engine* eng1 = ps_engine_create(1, ctas, idle_us);
+    if (!eng1) return 2;
+    for (size_t sz : {static_cast<size_t>(4096000), static_cast<size_t>(16u << 20)}) {
+      for (int both = 0; both < 2; ++both) {
+        const int burst = 240;
+        double best_us = 1e30;
+        for (int rep = 0; rep < 4; ++rep) {
+          *flag = 0;
+          *flag1 = 0;
+          const double t0 = NowUs();
+          for (int i = 0; i < burst; ++i) {
+            const size_t off = static_cast<size_t>(i % kSlots) * kMaxMsg;
+            ps_engine_post(eng, dst + off, src + off, sz, flag_dev, static_cast<unsigned long long>(i + 1));
+            if (both) ps_engine_post(eng1, dst0 + off, src1 + off, sz, flag1_dev, static_cast<unsigned long long>(i + 1));
+          }
+          if (!WaitFlag(flag, burst, 20) || (both && !WaitFlag(flag1, burst, 20))) return 4;
+          const double t1 = NowUs();
+          if (rep > 0 && t1 - t0 < best_us) best_us = t1 - t0;
+        }
+        printf("{\"bench\":\"engine_bench\",\"path\":\"engine\",\"pattern\":\"%s\",\"bytes\":%zu,"
+               "\"GBps_per_direction\":%.1f}\n", both ? "0->1 and 1->0 at once" : "0->1 only", sz,
+               sz * static_cast<double>(burst) / best_us / 1e3);
+        fflush(stdout);
+      }
+    }
+    ps_engine_destroy(eng1);
+    CK(cudaSetDevice(0));
+  }
   unsigned long long launches = 0, items = 0;
   ps_engine_stats(eng, &launches, &items);
   printf("{\"engine_launches\":%llu,\"engine_items\":%llu,\"data_failures\":%d}\n", launches, items, failures);

@@ -130,17 +130,93 @@ __device__ __forceinline__ void copy_chunk(unsigned char* __restrict__ dst,
     int4* d4 = reinterpret_cast<int4*>(dst);
     const int4* s4 = reinterpret_cast<const int4*>(src);
     unsigned long long i = threadIdx.x;
-    for (; i + 3 * kThreads < n16; i += 4 * kThreads) {
+    const unsigned T = blockDim.x;
+    for (; i + 3 * T < n16; i += 4 * T) {
       int4 v[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) v[u] = ld_stream(s4 + i + u * kThreads);
+      for (int u = 0; u < 4; ++u) v[u] = ld_stream(s4 + i + u * T);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) st_stream(d4 + i + u * kThreads, v[u]);
+      for (int u = 0; u < 4; ++u) st_stream(d4 + i + u * T, v[u]);
     }
-    for (; i < n16; i += kThreads) st_stream(d4 + i, ld_stream(s4 + i));
+    for (; i < n16; i += T) st_stream(d4 + i, ld_stream(s4 + i));
     done = n16 * 16;
   }
-  for (unsigned long long i = done + threadIdx.x; i < len; i += kThreads) dst[i] = src[i];
+  for (unsigned long long i = done + threadIdx.x; i < len; i += blockDim.x) dst[i] = src[i];
+}
+
+// ---- TMA flavour of the chunk copy: one elected thread streams the chunk global -> shared ->
+// global with cp.async.bulk (UBLKCP), kTmaStages x 32 KB in flight per CTA and no register staging.
+// A CTA sustains 2-3x the bytes in flight of the LDG/STG loop, so far fewer CTAs saturate NVLink.
+constexpr int kTmaStages = 4;
+constexpr unsigned kTmaSub = 32 * 1024;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) {
+  return static_cast<unsigned>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "ENG_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra ENG_DONE;\n\t"
+      "bra ENG_WAIT;\n\t"
+      "ENG_DONE:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                   "r"(smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gdst, const void* smem_src, unsigned bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)),
+               "r"(bytes)
+               : "memory");
+}
+
+/*!
+ * \brief ONE thread copies [0, len16) (a multiple of 16, both addresses 16-byte aligned). `seq`
+ *        counts the 32 KB pieces this CTA has ever moved: it picks the stage and the mbarrier
+ *        parity, so the barriers keep their phase from chunk to chunk. All stores have completed
+ *        (not just left shared memory) when this returns.
+ */
+__device__ __forceinline__ void tma_copy(unsigned char* dst, const unsigned char* src, unsigned long long len16,
+                                         unsigned char* smem, unsigned long long* full, unsigned long long& seq) {
+  const unsigned long long n = (len16 + kTmaSub - 1) / kTmaSub;
+  constexpr int kLook = kTmaStages - 2;  // loads run this many pieces ahead of the stores
+  auto piece = [&](unsigned long long j) -> unsigned {
+    const unsigned long long left = len16 - j * kTmaSub;
+    return static_cast<unsigned>(left < kTmaSub ? left : kTmaSub);
+  };
+  for (unsigned long long j = 0; j < n + kLook; ++j) {
+    if (j < n) {
+      const int sidx = static_cast<int>((seq + j) % kTmaStages);
+      // the stage was last read by the store of piece j - kTmaStages (issued kLook steps after its
+      // load): at most one younger store may still be reading shared memory
+      if (j >= static_cast<unsigned long long>(kTmaStages)) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      const unsigned b = piece(j);
+      mbar_expect_tx(&full[sidx], b);
+      bulk_g2s(smem + static_cast<size_t>(sidx) * kTmaSub, src + j * kTmaSub, b, &full[sidx]);
+    }
+    if (j >= static_cast<unsigned long long>(kLook)) {
+      const unsigned long long i = j - kLook;
+      const int sidx = static_cast<int>((seq + i) % kTmaStages);
+      mbar_wait(&full[sidx], static_cast<unsigned>(((seq + i) / kTmaStages) & 1));
+      bulk_s2g(dst + i * kTmaSub, smem + static_cast<size_t>(sidx) * kTmaSub, piece(i));
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+  }
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  asm volatile("fence.proxy.async;" ::: "memory");  // async-proxy stores before the generic-proxy signalling
+  seq += n;
 }
 
 __device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* p) {
@@ -158,6 +234,7 @@ __device__ __forceinline__ unsigned Participants(unsigned long long bytes, unsig
   return nchunks >= W ? W : (nchunks ? static_cast<unsigned>(nchunks) : 1u);
 }
 
+template <bool TMA>
 __global__ void __launch_bounds__(kThreads)
 k_copy_engine(HostCtl* ctl, const Item* host_ring, DevState* st, unsigned long long head0,
               unsigned long long epoch, unsigned long long idle_ns, unsigned long long kChunk) {
@@ -284,6 +361,16 @@ k_copy_engine(HostCtl* ctl, const Item* host_ring, DevState* st, unsigned long l
   // ---------------- workers ----------------
   __shared__ Item item;
   __shared__ int leave;
+  extern __shared__ __align__(128) unsigned char stage_mem[];  // TMA flavour: kTmaStages x 32 KB
+  __shared__ __align__(8) unsigned long long full[kTmaStages];
+  unsigned long long tma_seq = 0;
+  if (TMA) {
+    if (threadIdx.x == 0) {
+      for (int q = 0; q < kTmaStages; ++q) mbar_init(&full[q], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+  }
   const unsigned me = blockIdx.x - 1;
   unsigned rot = 0;  // where the participants of the current item start (same sequence in every CTA)
   for (unsigned long long k = head0;; ++k) {
@@ -314,7 +401,15 @@ k_copy_engine(HostCtl* ctl, const Item* host_ring, DevState* st, unsigned long l
       for (unsigned long long c = r; c < nchunks; c += P) {
         const unsigned long long off = c * kChunk;
         const unsigned long long len = bytes - off < kChunk ? bytes - off : kChunk;
-        copy_chunk(item.dst + off, item.src + off, len, aligned);
+        if (TMA && aligned) {
+          const unsigned long long len16 = len & ~15ull;
+          if (threadIdx.x == 0) {
+            if (len16) tma_copy(item.dst + off, item.src + off, len16, stage_mem, full, tma_seq);
+            for (unsigned long long t = len16; t < len; ++t) item.dst[off + t] = item.src[off + t];  // < 16 bytes
+          }
+        } else {
+          copy_chunk(item.dst + off, item.src + off, len, aligned);
+        }
       }
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -336,9 +431,13 @@ struct ps_engine {
   int device = 0;
   int grid = 0;
   unsigned long long idle_ns = 0;
-  // bytes one worker CTA moves per turn (PS_ENGINE_CHUNK_KB). Measured over NVLink, 4 MB messages,
-  // 296 workers: 32 KB 490 GB/s, 64 KB 595, 128 KB 613, 256 KB 675 (profiles/r2/engine_bench_peer_sweep.txt)
-  unsigned long long chunk = 256 * 1024;
+  // bytes one worker CTA moves per turn (PS_ENGINE_CHUNK_KB) and how it moves them (PS_ENGINE_TMA=1:
+  // cp.async.bulk through shared memory, one worker per SM; 0: LDG/STG, two workers per SM). Measured,
+  // 4 MB / 16 MB messages (profiles/r2/engine_bench_tma_sweep.txt):
+  //   local HBM   LDG 256 KB 1300 / 1984 GB/s   TMA 256 KB 1637 / 2662   TMA 512 KB 1789 / 2967 (0.90 of the copy roofline)
+  //   NVLink      LDG 256 KB  649 /  666 GB/s   TMA 256 KB  611 /  676   TMA 512 KB  649 /  700
+  unsigned long long chunk = 512 * 1024;
+  bool tma = true;
   cudaStream_t stream = nullptr;
   HostCtl* ctl = nullptr;        // host address
   HostCtl* ctl_dev = nullptr;    // the same memory as the device sees it
@@ -363,8 +462,13 @@ bool EngineLaunch(ps_engine* e) {
   if (cudaMemsetAsync(&e->state->stop_at, 0xff, sizeof(unsigned long long), e->stream) != cudaSuccess) {  // "never"
     return false;
   }
-  k_copy_engine<<<e->grid, kThreads, 0, e->stream>>>(e->ctl_dev, e->ring_dev, e->state, e->next_head, e->epoch,
-                                                     e->idle_ns, e->chunk);
+  if (e->tma) {
+    k_copy_engine<true><<<e->grid, 64, kTmaStages * kTmaSub, e->stream>>>(e->ctl_dev, e->ring_dev, e->state,
+                                                                         e->next_head, e->epoch, e->idle_ns, e->chunk);
+  } else {
+    k_copy_engine<false><<<e->grid, kThreads, 0, e->stream>>>(e->ctl_dev, e->ring_dev, e->state, e->next_head,
+                                                             e->epoch, e->idle_ns, e->chunk);
+  }
   if (cudaGetLastError() != cudaSuccess) return false;
   ps_kernels_internal::CountLaunch(1);
   ++e->launches;
@@ -378,16 +482,25 @@ extern "C" ps_engine* ps_engine_create(int device, int num_ctas, int idle_us) {
   if (cudaSetDevice(device) != cudaSuccess) return nullptr;
   ps_engine* e = new ps_engine();
   e->device = device;
-  // every CTA must be resident at once (workers wait for each other's completions)
+  if (const char* t = getenv("PS_ENGINE_TMA")) e->tma = atoi(t) != 0;
+  // every CTA must be resident at once (the dispatcher waits for the slowest worker)
   int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_copy_engine, kThreads, 0) != cudaSuccess || per_sm < 1) {
+  cudaError_t occ;
+  if (e->tma) {
+    cudaFuncSetAttribute(k_copy_engine<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTmaStages * kTmaSub);
+    occ = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_copy_engine<true>, 64, kTmaStages * kTmaSub);
+  } else {
+    occ = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_copy_engine<false>, kThreads, 0);
+  }
+  if (occ != cudaSuccess || per_sm < 1) {
     cudaGetLastError();
     delete e;
     return nullptr;
   }
   const int sms = ps_kernels_internal::NumSMs();
-  int grid = num_ctas > 0 ? num_ctas : 2 * sms + 1;  // default: two workers per SM + the dispatcher's CTA
-  if (grid > sms * (per_sm > 2 ? 2 : per_sm) + 1) grid = sms * (per_sm > 2 ? 2 : per_sm) + 1;
+  const int cap = per_sm > 2 ? 2 : per_sm;            // LDG: two workers per SM; TMA (128 KB each): one
+  int grid = num_ctas > 0 ? num_ctas : cap * sms;     // (the dispatcher's CTA takes one of the slots)
+  if (grid > sms * cap) grid = sms * cap;
   if (grid > static_cast<int>(kMaxWorkers)) grid = static_cast<int>(kMaxWorkers);
   if (grid < 2) grid = 2;
   e->grid = grid;
