@@ -114,7 +114,7 @@ int main(int argc, char** argv) {
           unsigned char* d = dst + static_cast<size_t>(i % kSlots) * kMaxMsg;
           const unsigned char* s = src + static_cast<size_t>(i % kSlots) * kMaxMsg;
           if (mode == 0) {
-            if (ps_engine_post(eng, d, s, sz, flag_dev, static_cast<unsigned long long>(i + 1)) != 0) return 3;
+            if (ps_engine_post(eng, d, s, sz, flag_dev, static_cast<unsigned long long>(i + 1), nullptr) != 0) return 3;
           } else {
             ps_signal sig = {counter, flag_dev, static_cast<unsigned long long>(i + 1)};
             if (ps_launch_copy_signal(d, s, sz, PS_CODEC_RAW, 1.f, 0, &sig,
@@ -150,7 +150,7 @@ int main(int argc, char** argv) {
       for (int i = 0; i < n1 + 20; ++i) {
         const double t0 = NowUs();
         if (mode == 0) {
-          ps_engine_post(eng, dst, src, sz, flag_dev, static_cast<unsigned long long>(i + 1));
+          ps_engine_post(eng, dst, src, sz, flag_dev, static_cast<unsigned long long>(i + 1), nullptr);
         } else {
           ps_signal sig = {counter, flag_dev, static_cast<unsigned long long>(i + 1)};
           ps_launch_copy_signal(dst, src, sz, PS_CODEC_RAW, 1.f, 0, &sig, reinterpret_cast<ps_stream_t>(stream));
@@ -193,8 +193,8 @@ int main(int argc, char** argv) {
           const double t0 = NowUs();
           for (int i = 0; i < burst; ++i) {
             const size_t off = static_cast<size_t>(i % kSlots) * kMaxMsg;
-            ps_engine_post(eng, dst + off, src + off, sz, flag_dev, static_cast<unsigned long long>(i + 1));
-            if (both) ps_engine_post(eng1, dst0 + off, src1 + off, sz, flag1_dev, static_cast<unsigned long long>(i + 1));
+            ps_engine_post(eng, dst + off, src + off, sz, flag_dev, static_cast<unsigned long long>(i + 1), nullptr);
+            if (both) ps_engine_post(eng1, dst0 + off, src1 + off, sz, flag1_dev, static_cast<unsigned long long>(i + 1), nullptr);
           }
           if (!WaitFlag(flag, burst, 20) || (both && !WaitFlag(flag1, burst, 20))) return 4;
           const double t1 = NowUs();
@@ -208,6 +208,28 @@ int main(int argc, char** argv) {
     }
     ps_engine_destroy(eng1);
     CK(cudaSetDevice(0));
+    // local and NVLink copies alternating in ONE queue (a joint worker's pushes: every other key lives
+    // on the local server): the slow ones must not hold up the fast ones
+    {
+      const size_t sz = 4096000;
+      const int burst = 240;
+      double best_us = 1e30;
+      for (int rep = 0; rep < 4; ++rep) {
+        *flag = 0;
+        const double t0 = NowUs();
+        for (int i = 0; i < burst; ++i) {
+          const size_t off = static_cast<size_t>(i % kSlots) * kMaxMsg;
+          unsigned char* d = (i & 1) ? dst + off : dst0 + off;  // odd: GPU 1 (NVLink), even: GPU 0 (local)
+          ps_engine_post(eng, d, src + off, sz, flag_dev, static_cast<unsigned long long>(i + 1), nullptr);
+        }
+        if (!WaitFlag(flag, burst, 20)) return 4;
+        const double t1 = NowUs();
+        if (rep > 0 && t1 - t0 < best_us) best_us = t1 - t0;
+      }
+      printf("{\"bench\":\"engine_bench\",\"path\":\"engine\",\"pattern\":\"local and 0->1 alternating\",\"bytes\":%zu,"
+             "\"GBps_per_direction\":%.1f,\"us_per_msg\":%.2f}\n", sz, sz * static_cast<double>(burst) / best_us / 1e3,
+             best_us / burst);
+    }
   }
   unsigned long long launches = 0, items = 0;
   ps_engine_stats(eng, &launches, &items);

@@ -18,6 +18,7 @@
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <string>
 
 namespace ps {
@@ -61,7 +62,9 @@ class EventTrace {
       const char* p = getenv("PS_EVENT_TRACE");
       if (p && *p) {
         st->path = std::string(p) + "." + std::to_string(getpid());
-        st->events = static_cast<Event*>(calloc(kMax, sizeof(Event)));
+        st->events = static_cast<Event*>(malloc(sizeof(Event) * kMax));
+        // touch every page now: a first-touch fault inside Mark() would cost more than the event it records
+        if (st->events) memset(st->events, 0, sizeof(Event) * kMax);
         st->on = st->events != nullptr;
         if (st->on) atexit(&Dump);
       }

@@ -13,11 +13,11 @@
  *   CTA 0, warp 0 (dispatcher)       polls `posted` in host memory, copies new descriptors into
  *                                    a device-side ring (eight per PCIe round trip) and
  *                                    publishes its tail at gpu scope
- *   CTAs 1..G-1 (workers)            walk the device ring in order; an item is cut into 256 KB
- *                                    chunks and spread over as many workers as it has chunks
- *                                    (start CTA rotates, so small items land on different CTAs
- *                                    and many items are in flight at once); stores may target
- *                                    peer HBM over NVLink
+ *   CTAs 1..G-1 (workers)            walk the device ring in order; an item is cut into 512 KB
+ *                                    chunks which the workers TAKE one at a time (claim counter
+ *                                    per item) and move with cp.async.bulk through shared memory
+ *                                    (TMA) — many items are in flight at once, a slow chunk
+ *                                    (NVLink) never holds up the rest; stores may target peer HBM
  *   completion (one thread of CTA 0) every participating CTA fences at system scope and counts
  *                                    itself in; the completer walks the items in posting order
  *                                    (completions are published like on a stream) and stores an
@@ -79,7 +79,8 @@ struct HostCtl {
 
 struct DevState {
   Item ring[kDevRing];
-  unsigned arrive[kDevRing];
+  unsigned arrive[kDevRing];   // chunks of the item in this slot that are in place
+  unsigned claim[kDevRing];    // chunks of the item in this slot that have been taken
   unsigned long long tail;          // descriptors published to the workers
   unsigned long long signal_head;   // next completion to publish
   unsigned long long stop_at;       // ~0 while running; the dispatcher's final head when leaving
@@ -228,10 +229,10 @@ __device__ __forceinline__ void st_relaxed_sys(volatile unsigned long long* p, u
   asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-/*! \brief how many worker CTAs an item of `bytes` is spread over */
-__device__ __forceinline__ unsigned Participants(unsigned long long bytes, unsigned W, unsigned long long kChunk) {
-  const unsigned long long nchunks = (bytes + kChunk - 1) / kChunk;
-  return nchunks >= W ? W : (nchunks ? static_cast<unsigned>(nchunks) : 1u);
+/*! \brief pieces an item is cut into (an empty item — a pure signal — counts as one) */
+__device__ __forceinline__ unsigned NumChunks(unsigned long long bytes, unsigned long long kChunk) {
+  const unsigned long long n = (bytes + kChunk - 1) / kChunk;
+  return n ? static_cast<unsigned>(n) : 1u;
 }
 
 template <bool TMA>
@@ -255,8 +256,8 @@ k_copy_engine(HostCtl* ctl, const Item* host_ring, DevState* st, unsigned long l
           while (head != posted) {
             const unsigned n = posted - head < 8 ? static_cast<unsigned>(posted - head) : 8u;
             // a slot of the device ring is free again once its completion has been published AND
-            // every worker has read it (workers that take no part in an item still read it to keep
-            // their rotation in step, and may lag behind the completer)
+            // every worker has moved past it (a worker that found nothing left to take may still be
+            // about to look at the slot's claim counter)
             if (head + n - safe > kDevRing) {
               for (;;) {
                 unsigned long long m = ld_acquire_gpu(&st->signal_head);
@@ -277,6 +278,10 @@ k_copy_engine(HostCtl* ctl, const Item* host_ring, DevState* st, unsigned long l
               const unsigned long long idx = head + (lane >> 2);
               const int4 v = __ldcv(reinterpret_cast<const int4*>(host_ring + (idx & (kHostRing - 1))) + (lane & 3));
               reinterpret_cast<int4*>(&st->ring[idx & (kDevRing - 1)])[lane & 3] = v;
+              if ((lane & 3) == 0) {  // nobody looks at the slot's old counters any more (see `safe`)
+                st->arrive[idx & (kDevRing - 1)] = 0;
+                st->claim[idx & (kDevRing - 1)] = 0;
+              }
             }
             __syncwarp();
             head += n;
@@ -331,10 +336,9 @@ k_copy_engine(HostCtl* ctl, const Item* host_ring, DevState* st, unsigned long l
           continue;
         }
         const Item* it = &st->ring[k & (kDevRing - 1)];
-        const unsigned P = Participants(it->bytes, W, kChunk);
+        const unsigned P = NumChunks(it->bytes, kChunk);
         while (ld_acquire_gpu_u32(&st->arrive[k & (kDevRing - 1)]) != P) {
         }
-        st->arrive[k & (kDevRing - 1)] = 0;
         unsigned long long* flag = it->flag;
         unsigned long long value = it->flag_value;
         ++k;
@@ -342,8 +346,7 @@ k_copy_engine(HostCtl* ctl, const Item* host_ring, DevState* st, unsigned long l
         while (k != tail) {
           const Item* nx = &st->ring[k & (kDevRing - 1)];
           if (nx->flag != flag) break;
-          if (ld_acquire_gpu_u32(&st->arrive[k & (kDevRing - 1)]) != Participants(nx->bytes, W, kChunk)) break;
-          st->arrive[k & (kDevRing - 1)] = 0;
+          if (ld_acquire_gpu_u32(&st->arrive[k & (kDevRing - 1)]) != NumChunks(nx->bytes, kChunk)) break;
           value = nx->flag_value;
           ++k;
         }
@@ -372,14 +375,16 @@ k_copy_engine(HostCtl* ctl, const Item* host_ring, DevState* st, unsigned long l
     __syncthreads();
   }
   const unsigned me = blockIdx.x - 1;
-  unsigned rot = 0;  // where the participants of the current item start (same sequence in every CTA)
+  __shared__ unsigned my_chunk;
+  // Every worker walks the items in posting order and TAKES chunks (atomic claim counter per item)
+  // until none is left: a worker stuck on a slow chunk (NVLink) never holds up chunks that were
+  // statically "its own", the others simply take more — items of different cost mix freely.
   for (unsigned long long k = head0;; ++k) {
     if (threadIdx.x == 0) {
       leave = 0;
       for (;;) {
         if (ld_acquire_gpu(&st->tail) > k) {
           item = st->ring[k & (kDevRing - 1)];
-          st_release_gpu(&st->progress[me], k + 1);  // the dispatcher may reuse the slot
           break;
         }
         if (ld_acquire_gpu(&st->stop_at) <= k) {
@@ -391,15 +396,22 @@ k_copy_engine(HostCtl* ctl, const Item* host_ring, DevState* st, unsigned long l
     __syncthreads();
     if (leave) return;
     const unsigned long long bytes = item.bytes;
-    const unsigned long long nchunks = (bytes + kChunk - 1) / kChunk;
-    const unsigned P = Participants(bytes, W, kChunk);
-    const unsigned r = (me + W - rot) % W;
-    rot = (rot + P) % W;
-    if (r < P) {
-      const bool aligned =
-          ((reinterpret_cast<unsigned long long>(item.dst) | reinterpret_cast<unsigned long long>(item.src)) & 15) == 0;
-      for (unsigned long long c = r; c < nchunks; c += P) {
-        const unsigned long long off = c * kChunk;
+    const unsigned nchunks = NumChunks(bytes, kChunk);
+    const bool aligned =
+        ((reinterpret_cast<unsigned long long>(item.dst) | reinterpret_cast<unsigned long long>(item.src)) & 15) == 0;
+    unsigned* claim = &st->claim[k & (kDevRing - 1)];
+    for (;;) {
+      if (threadIdx.x == 0) {
+        // look before taking: once an item is fully handed out the other ~150 workers pass with a load
+        unsigned c = nchunks;
+        if (ld_acquire_gpu_u32(claim) < nchunks) c = atomicAdd(claim, 1u);
+        my_chunk = c;
+      }
+      __syncthreads();
+      const unsigned c = my_chunk;
+      if (c >= nchunks) break;
+      if (bytes) {
+        const unsigned long long off = static_cast<unsigned long long>(c) * kChunk;
         const unsigned long long len = bytes - off < kChunk ? bytes - off : kChunk;
         if (TMA && aligned) {
           const unsigned long long len16 = len & ~15ull;
@@ -413,11 +425,12 @@ k_copy_engine(HostCtl* ctl, const Item* host_ring, DevState* st, unsigned long l
       }
       __syncthreads();
       if (threadIdx.x == 0) {
-        __threadfence_system();  // this CTA's bytes are visible system-wide before it counts itself in
+        __threadfence_system();  // the chunk is visible system-wide before it is counted
         atomicAdd(&st->arrive[k & (kDevRing - 1)], 1u);
       }
     }
-    __syncthreads();  // `item` is overwritten by the next iteration
+    if (threadIdx.x == 0) st_release_gpu(&st->progress[me], k + 1);  // done with this slot for good
+    __syncthreads();  // `item` / `my_chunk` are overwritten by the next iteration
   }
 }
 
@@ -478,7 +491,37 @@ bool EngineLaunch(ps_engine* e) {
 
 }  // namespace
 
+namespace {
+// One engine per device and process: two of them (the worker van's and the server van's of a joint
+// process) would fight for the SMs' shared memory and take turns instead of running together.
+std::mutex g_registry_mu;
+ps_engine* g_engines[64] = {nullptr};
+int g_refs[64] = {0};
+ps_engine* EngineCreate(int device, int num_ctas, int idle_us);
+void EngineDestroy(ps_engine* e);
+}  // namespace
+
 extern "C" ps_engine* ps_engine_create(int device, int num_ctas, int idle_us) {
+  if (device < 0 || device >= 64) return nullptr;
+  std::lock_guard<std::mutex> lk(g_registry_mu);
+  if (!g_engines[device]) g_engines[device] = EngineCreate(device, num_ctas, idle_us);
+  if (g_engines[device]) ++g_refs[device];
+  return g_engines[device];
+}
+
+extern "C" void ps_engine_destroy(ps_engine* e) {
+  if (!e) return;
+  std::lock_guard<std::mutex> lk(g_registry_mu);
+  const int device = e->device;
+  if (device >= 0 && device < 64 && g_engines[device] == e) {
+    if (--g_refs[device] > 0) return;
+    g_engines[device] = nullptr;
+  }
+  EngineDestroy(e);
+}
+
+namespace {
+ps_engine* EngineCreate(int device, int num_ctas, int idle_us) {
   if (cudaSetDevice(device) != cudaSuccess) return nullptr;
   ps_engine* e = new ps_engine();
   e->device = device;
@@ -522,13 +565,13 @@ extern "C" ps_engine* ps_engine_create(int device, int num_ctas, int idle_us) {
   }
   if (!ok) {
     cudaGetLastError();
-    ps_engine_destroy(e);
+    EngineDestroy(e);
     return nullptr;
   }
   return e;
 }
 
-extern "C" void ps_engine_destroy(ps_engine* e) {
+void EngineDestroy(ps_engine* e) {
   if (!e) return;
   cudaSetDevice(e->device);
   if (e->stream) cudaStreamSynchronize(e->stream);  // the kernel leaves by itself once idle
@@ -539,9 +582,10 @@ extern "C" void ps_engine_destroy(ps_engine* e) {
   cudaGetLastError();
   delete e;
 }
+}  // namespace
 
 extern "C" int ps_engine_post(ps_engine* e, void* dst, const void* src, size_t bytes, unsigned long long* flag,
-                              unsigned long long value) {
+                              unsigned long long value, unsigned long long* ticket) {
   std::lock_guard<std::mutex> lk(e->mu);
   // back-pressure: the host ring holds kHostRing descriptors that have not been retired
   while (e->posted - HostLoad(&e->ctl->retired) >= kHostRing - 1) std::this_thread::yield();
@@ -552,6 +596,7 @@ extern "C" int ps_engine_post(ps_engine* e, void* dst, const void* src, size_t b
   it.flag = flag;
   it.flag_value = value;
   ++e->posted;
+  if (ticket) *ticket = e->posted;
   __atomic_store_n(const_cast<unsigned long long*>(&e->ctl->posted), e->posted, __ATOMIC_RELEASE);
   ++e->items;
   std::atomic_thread_fence(std::memory_order_seq_cst);
@@ -584,6 +629,14 @@ extern "C" void ps_engine_drain(ps_engine* e) {
     upto = e->posted;
   }
   while (HostLoad(&e->ctl->retired) < upto) std::this_thread::yield();
+}
+
+extern "C" int ps_engine_done(ps_engine* e, unsigned long long ticket) {
+  return HostLoad(&e->ctl->retired) >= ticket;
+}
+
+extern "C" void ps_engine_wait(ps_engine* e, unsigned long long ticket) {
+  while (HostLoad(&e->ctl->retired) < ticket) std::this_thread::yield();
 }
 
 extern "C" void ps_engine_stats(ps_engine* e, unsigned long long* launches, unsigned long long* items) {

@@ -84,7 +84,8 @@ int ps_launch_signal(const ps_signal* sig, ps_stream_t stream);
 
 /*!
  * \brief the copy engine (engine_kernels.cu): descriptors are POSTED into a ring in mapped host
- *        memory and executed by an on-demand persistent kernel — no driver call per copy.
+ *        memory and executed by an on-demand persistent kernel — no driver call per copy. One
+ *        engine per device and process (ps_engine_create hands out the shared instance).
  *        Completions are published in posting order: `value` is stored to `*flag`
  *        (st.release.sys; flag may be null) once the bytes are visible system-wide.
  */
@@ -92,7 +93,11 @@ typedef struct ps_engine ps_engine;
 ps_engine* ps_engine_create(int device, int num_ctas, int idle_us);
 void ps_engine_destroy(ps_engine* e);
 int ps_engine_post(ps_engine* e, void* dst, const void* src, size_t bytes, unsigned long long* flag,
-                   unsigned long long value);
+                   unsigned long long value, unsigned long long* ticket);
+/*! \brief completions are published in posting order: has / wait until the post that returned `ticket` completed
+ *  (an engine is shared by everything on its device; a user waits for ITS last ticket, not for everybody) */
+int ps_engine_done(ps_engine* e, unsigned long long ticket);
+void ps_engine_wait(ps_engine* e, unsigned long long ticket);
 /*! \brief has everything posted so far been completed? / wait until it has */
 int ps_engine_idle(ps_engine* e);
 void ps_engine_drain(ps_engine* e);

@@ -208,10 +208,7 @@ class CudaDomain : public MemDomain {
   Ticket CopyAsync(void* dst, const void* src, size_t n, int codec, float scale,
                    void* wait_event, int src_device_type = UNK) override {
     PS_CUDA_CHECK(cudaSetDevice(dev_));
-    if (engine_) {
-      ps_engine_drain(engine_);
-      launch_pending_.store(true, std::memory_order_release);
-    }
+    if (engine_) EngineQuiesce();
     if (wait_event) {
       PS_CUDA_CHECK(cudaStreamWaitEvent(stream_, static_cast<cudaEvent_t>(wait_event), 0));
     }
@@ -243,10 +240,7 @@ class CudaDomain : public MemDomain {
   /*! \brief raw device-to-device items share launches (ps_launch_copy_multi), one event in all */
   Ticket CopyBatchAsync(const std::vector<CopyItem>& items) override {
     PS_CUDA_CHECK(cudaSetDevice(dev_));
-    if (engine_) {
-      ps_engine_drain(engine_);
-      launch_pending_.store(true, std::memory_order_release);
-    }
+    if (engine_) EngineQuiesce();
     for (const CopyItem& it : items) {
       if (it.wait_event) {
         PS_CUDA_CHECK(cudaStreamWaitEvent(stream_, static_cast<cudaEvent_t>(it.wait_event), 0));
@@ -322,13 +316,14 @@ class CudaDomain : public MemDomain {
       const bool eligible = item.wait_event == nullptr && item.codec == kCodecRaw &&
                             (item.n_src_bytes == 0 || item.src_device_type == GPU);
       if (eligible && StreamIdle()) {
+        unsigned long long ticket = 0;
         CHECK_EQ(ps_engine_post(engine_, item.dst, item.src, item.n_src_bytes,
-                                static_cast<unsigned long long*>(word), value), 0)
+                                static_cast<unsigned long long*>(word), value, &ticket), 0)
             << "copy engine: post failed";
+        engine_ticket_.store(ticket, std::memory_order_release);
         return true;
       }
-      ps_engine_drain(engine_);
-      launch_pending_.store(true, std::memory_order_release);
+      EngineQuiesce();
     }
     if (item.wait_event) {
       PS_CUDA_CHECK(cudaStreamWaitEvent(stream_, static_cast<cudaEvent_t>(item.wait_event), 0));
@@ -388,6 +383,11 @@ class CudaDomain : public MemDomain {
   }
 
  private:
+  /*! \brief before the stream gets work: everything THIS domain gave the engine must have completed */
+  void EngineQuiesce() {
+    ps_engine_wait(engine_, engine_ticket_.load(std::memory_order_acquire));
+    launch_pending_.store(true, std::memory_order_release);
+  }
   /*! \brief has everything ever enqueued on the data stream completed? */
   bool StreamIdle() {
     if (!launch_pending_.load(std::memory_order_acquire) && !stream_shared_.load(std::memory_order_acquire)) {
@@ -424,6 +424,7 @@ class CudaDomain : public MemDomain {
   int dev_;
   int max_ctas_ = 0;
   ps_engine* engine_ = nullptr;
+  std::atomic<unsigned long long> engine_ticket_{0};  // this domain's newest post to the (shared) engine
   std::atomic<bool> launch_pending_{false};  // the launch path has been used since the stream was last seen idle
   std::atomic<bool> stream_shared_{false};   // Stream() was handed out: foreign work may be on it
   unsigned* sig_counter_ = nullptr;  // CTA arrival counter of the signalling kernels (self-resetting)
