@@ -17,6 +17,7 @@
 #ifndef PS_INTERNAL_VAN_H_
 #define PS_INTERNAL_VAN_H_
 #include <atomic>
+#include "ps/internal/symmetric.h"
 #include <ctime>
 #include <fstream>
 #include <memory>
@@ -79,6 +80,19 @@ class Van {
   virtual void FreeExportable(void* p) { free(p); }
   /*! \brief this process's mapping of a span a peer announced (one-sided vans), else null */
   virtual void* ResolvePeerMem(int /*node_id*/, const MemRef& /*mem*/) { return nullptr; }
+  /*!
+   * \brief collective over all worker and server PROCESSES of the job (one call per process and
+   *        `tag`; a joint process's second van gets the first one's result): allocate `bytes` of
+   *        zero-filled symmetric memory — a block in every process, each mapped by all the
+   *        others, plus an NVSwitch multicast address over all of them where the hardware has
+   *        one (out->mc). HBM on the nvl van, shared memory on the shm van; false elsewhere.
+   */
+  virtual bool AllocSymmetric(const std::string& /*tag*/, size_t /*bytes*/, SymmetricBuffer* /*out*/) { return false; }
+  /*! \brief every node of the job as the scheduler announced it (empty before ADD_NODE completes) */
+  std::vector<Node> ClusterNodes() {
+    std::lock_guard<std::mutex> lk(cluster_mu_);
+    return cluster_;
+  }
   /*! \brief transport-specific counters by name (one-sided copies, gated descriptors, ...) */
   virtual void TransportStats(std::vector<std::pair<std::string, uint64_t>>* /*out*/) {}
   /*! \brief stream the van's copy kernels run on (cudaStream_t), null for CPU vans */
@@ -197,6 +211,8 @@ class Van {
   std::mutex parked_mu_;
   std::vector<Message> parked_;  // data messages waiting for their customer to be created
   std::atomic<int> parked_n_{0};  // parked_.size(), readable without the lock
+  std::mutex cluster_mu_;
+  std::vector<Node> cluster_;     // node table of the job (workers and servers), by arrival
   void DrainParkedLocked();
 
   std::vector<int> instance_barrier_count_;

@@ -574,6 +574,36 @@ PYBIND11_MODULE(_C, m) {
     return torch::from_blob(p, {nbytes}, [van](void* q) { van->FreeExportable(q); }, opts);
   }, py::arg("nbytes"), py::arg("as_role") = "worker");
 
+  /*!
+   * \brief collective over all worker / server processes: symmetric memory without torch's private
+   *        API. Returns (local uint8 tensor, multicast address or 0, [address of every member's block
+   *        as mapped here], my index, member count).
+   */
+  m.def("alloc_symmetric", [](const std::string& tag, int64_t nbytes, const std::string& as_role) {
+    Postoffice* po = as_role == "server" ? Postoffice::GetServer() : Postoffice::GetWorker();
+    TORCH_CHECK(po != nullptr && po->van() != nullptr, "the PS runtime is not started");
+    Van* van = po->van();
+    SymmetricBuffer sb;
+    bool ok;
+    {
+      py::gil_scoped_release nogil;
+      ok = van->AllocSymmetric(tag, static_cast<size_t>(nbytes), &sb);
+    }
+    TORCH_CHECK(ok, "AllocSymmetric('", tag, "') failed on the ", van->GetType(), " van");
+    auto opts = torch::TensorOptions().dtype(torch::kUInt8);
+    if (van->GetType() == "nvl") opts = opts.device(torch::kCUDA, van->my_node().dev_id);
+    torch::Tensor local = torch::from_blob(sb.local, {static_cast<int64_t>(sb.bytes)}, [](void*) {}, opts);
+    std::vector<uint64_t> peers;
+    for (void* p : sb.peers) peers.push_back(reinterpret_cast<uint64_t>(p));
+    return py::make_tuple(local, reinterpret_cast<uint64_t>(sb.mc), peers, sb.index, sb.count);
+  }, py::arg("tag"), py::arg("nbytes"), py::arg("as_role") = "worker");
+  /*! \brief a uint8 view of `nbytes` at a raw address of this process (a peer mapping from alloc_symmetric) */
+  m.def("tensor_at", [](uint64_t addr, int64_t nbytes, int cuda_device) {
+    auto opts = torch::TensorOptions().dtype(torch::kUInt8);
+    if (cuda_device >= 0) opts = opts.device(torch::kCUDA, cuda_device);
+    return torch::from_blob(reinterpret_cast<void*>(addr), {nbytes}, [](void*) {}, opts);
+  }, py::arg("addr"), py::arg("nbytes"), py::arg("cuda_device") = -1);
+
   py::class_<PyKVWorker>(m, "KVWorker")
       .def(py::init<int, int, int>(), py::arg("app_id") = 0, py::arg("customer_id") = 0,
            py::arg("instance_idx") = 0)

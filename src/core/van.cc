@@ -367,6 +367,20 @@ void Van::OnAddNode(Message* msg) {
   }
   auto& nodes = msg->meta.control.node;
   AdoptIdentity(nodes);
+  {
+    std::lock_guard<std::mutex> lk(cluster_mu_);
+    for (const Node& n : nodes) {
+      if (n.role != Node::SERVER && n.role != Node::WORKER) continue;
+      bool known = false;
+      for (Node& c : cluster_) {
+        if (c.id == n.id) {
+          c = n;  // a recovered node replaces its predecessor
+          known = true;
+        }
+      }
+      if (!known) cluster_.push_back(n);
+    }
+  }
   for (const Node& n : nodes) {
     const std::string addr = n.Address();
     if (!connected_.count(addr)) {

@@ -12,6 +12,7 @@
 #include <unordered_map>
 
 #include "kernels/ps_kernels.h"
+#include "van/fd_exchange.h"
 
 namespace ps {
 
@@ -31,6 +32,68 @@ int CudaDeviceCount() {
 }
 
 namespace {
+
+/*!
+ * \brief the driver entry points of virtual memory management and NVSwitch multicast, resolved
+ *        through the runtime (no link-time dependency on libcuda.so, absent on build hosts).
+ *        This replaces what round 1 borrowed from torch.distributed._symmetric_memory.
+ */
+struct VmmApi {
+  CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+  CUresult (*DeviceGetAttribute)(int*, CUdevice_attribute, CUdevice) = nullptr;
+  CUresult (*MemGetAllocationGranularity)(size_t*, const CUmemAllocationProp*, CUmemAllocationGranularity_flags) = nullptr;
+  CUresult (*MemCreate)(CUmemGenericAllocationHandle*, size_t, const CUmemAllocationProp*, unsigned long long) = nullptr;
+  CUresult (*MemRelease)(CUmemGenericAllocationHandle) = nullptr;
+  CUresult (*MemAddressReserve)(CUdeviceptr*, size_t, size_t, CUdeviceptr, unsigned long long) = nullptr;
+  CUresult (*MemAddressFree)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
+  CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
+  CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
+  CUresult (*MemExportToShareableHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+  CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
+  CUresult (*MulticastCreate)(CUmemGenericAllocationHandle*, const CUmulticastObjectProp*) = nullptr;
+  CUresult (*MulticastAddDevice)(CUmemGenericAllocationHandle, CUdevice) = nullptr;
+  CUresult (*MulticastBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long) = nullptr;
+  CUresult (*MulticastGetGranularity)(size_t*, const CUmulticastObjectProp*, CUmulticastGranularity_flags) = nullptr;
+  bool vmm = false, multicast = false;
+
+  static const VmmApi& Get() {
+    static const VmmApi api = [] {
+      VmmApi a;
+      auto load = [](const char* name, void* slot) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) {
+          cudaGetLastError();
+          fn = nullptr;
+        }
+        *static_cast<void**>(slot) = fn;
+        return fn != nullptr;
+      };
+      bool v = true, m = true;
+      v &= load("cuDeviceGet", &a.DeviceGet);
+      v &= load("cuDeviceGetAttribute", &a.DeviceGetAttribute);
+      v &= load("cuMemGetAllocationGranularity", &a.MemGetAllocationGranularity);
+      v &= load("cuMemCreate", &a.MemCreate);
+      v &= load("cuMemRelease", &a.MemRelease);
+      v &= load("cuMemAddressReserve", &a.MemAddressReserve);
+      v &= load("cuMemAddressFree", &a.MemAddressFree);
+      v &= load("cuMemMap", &a.MemMap);
+      v &= load("cuMemUnmap", &a.MemUnmap);
+      v &= load("cuMemSetAccess", &a.MemSetAccess);
+      v &= load("cuMemExportToShareableHandle", &a.MemExportToShareableHandle);
+      v &= load("cuMemImportFromShareableHandle", &a.MemImportFromShareableHandle);
+      m &= load("cuMulticastCreate", &a.MulticastCreate);
+      m &= load("cuMulticastAddDevice", &a.MulticastAddDevice);
+      m &= load("cuMulticastBindMem", &a.MulticastBindMem);
+      m &= load("cuMulticastGetGranularity", &a.MulticastGetGranularity);
+      a.vmm = v;
+      a.multicast = v && m;
+      return a;
+    }();
+    return api;
+  }
+};
 
 class CudaDomain : public MemDomain {
  public:
@@ -373,6 +436,147 @@ class CudaDomain : public MemDomain {
     PS_CUDA_CHECK(cudaEventSynchronize(ev));
     std::lock_guard<std::mutex> lk(mu_);
     free_events_.push_back(ev);
+  }
+
+  /*!
+   * Symmetric memory, natively: every member cuMemCreate()s a block with a shareable POSIX
+   * handle, publishes the descriptor through FdExchange, imports and maps every other member's
+   * block; on an NVSwitch box member 0 creates a multicast object, everybody adds its device and
+   * binds its block, and maps the multicast address (NVLS: multimem.st / multimem.ld_reduce).
+   * Counterpart of the reference's registered-memory exchange (src/rdma_utils.h:75-140,
+   * src/rdma_transport.h:469-633), for NVLink + NVSwitch.
+   */
+  bool SymmetricAlloc(const SymmetricGroup& g, const std::string& tag, size_t bytes, SymmetricBuffer* out) override {
+    const VmmApi& api = VmmApi::Get();
+    FdExchange* fx = FdExchange::Get(g.job_port);
+    if (!api.vmm || !fx || g.index < 0 || g.pids.empty()) return false;
+    if (cudaSetDevice(dev_) != cudaSuccess) return false;
+    cudaFree(nullptr);  // make sure the primary context exists and is current
+    const int n = static_cast<int>(g.pids.size());
+    CUdevice cudev;
+    if (api.DeviceGet(&cudev, dev_) != CUDA_SUCCESS) return false;
+    CUmemAllocationProp prop;
+    memset(&prop, 0, sizeof(prop));
+    prop.type = CU_MEM_ALLOCATION_TYPE_PINNED;
+    prop.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+    prop.location.id = dev_;
+    prop.requestedHandleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t gran = 0;
+    if (api.MemGetAllocationGranularity(&gran, &prop, CU_MEM_ALLOC_GRANULARITY_RECOMMENDED) != CUDA_SUCCESS || !gran) {
+      return false;
+    }
+    int mc_cap = 0;
+    if (api.multicast && n > 1) api.DeviceGetAttribute(&mc_cap, CU_DEVICE_ATTRIBUTE_MULTICAST_SUPPORTED, cudev);
+    if (GetEnv("PS_DISABLE_MULTICAST", 0) != 0) mc_cap = 0;
+    CUmulticastObjectProp mcprop;
+    memset(&mcprop, 0, sizeof(mcprop));
+    mcprop.numDevices = static_cast<unsigned>(n);
+    mcprop.handleTypes = CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR;
+    size_t size = AlignUp(bytes ? bytes : 1, gran);
+    if (mc_cap) {
+      size_t mcgran = 0;
+      mcprop.size = size;
+      if (api.MulticastGetGranularity(&mcgran, &mcprop, CU_MULTICAST_GRANULARITY_RECOMMENDED) == CUDA_SUCCESS && mcgran) {
+        size = (size + mcgran - 1) / mcgran * mcgran;
+      } else {
+        mc_cap = 0;
+      }
+    }
+    mcprop.size = size;
+    auto map_rw = [&](CUmemGenericAllocationHandle h, CUdeviceptr* va) -> bool {
+      if (api.MemAddressReserve(va, size, gran, 0, 0) != CUDA_SUCCESS) return false;
+      if (api.MemMap(*va, size, 0, h, 0) != CUDA_SUCCESS) return false;
+      CUmemAccessDesc acc;
+      memset(&acc, 0, sizeof(acc));
+      acc.location.type = CU_MEM_LOCATION_TYPE_DEVICE;
+      acc.location.id = dev_;
+      acc.flags = CU_MEM_ACCESS_FLAGS_PROT_READWRITE;
+      return api.MemSetAccess(*va, size, &acc, 1) == CUDA_SUCCESS;
+    };
+    CUmemGenericAllocationHandle mine;
+    if (api.MemCreate(&mine, size, &prop, 0) != CUDA_SUCCESS) return false;
+    CUdeviceptr va = 0;
+    if (!map_rw(mine, &va)) return false;
+    if (cudaMemset(reinterpret_cast<void*>(va), 0, size) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    int fd = -1;
+    if (api.MemExportToShareableHandle(&fd, mine, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) != CUDA_SUCCESS) return false;
+    out->local = reinterpret_cast<void*>(va);
+    out->bytes = size;
+    out->index = g.index;
+    out->count = n;
+    out->peers.assign(static_cast<size_t>(n), nullptr);
+    out->peers[static_cast<size_t>(g.index)] = out->local;
+    out->mc = nullptr;
+    auto endpoint = [&](int i) { return FdExchange::EndpointName(g.job_port, g.pids[static_cast<size_t>(i)]); };
+    // value of the "/mem" token: block size, and in bit 63 "my device can do multicast"
+    fx->Publish(tag + "/mem", fd, static_cast<uint64_t>(size) | (mc_cap ? (1ull << 63) : 0ull));
+    bool ok = true, all_mc = mc_cap != 0;
+    for (int i = 0; i < n && ok; ++i) {
+      if (i == g.index) continue;
+      int pfd = -1;
+      uint64_t v = 0;
+      ok = FdExchange::Fetch(endpoint(i), tag + "/mem", &pfd, &v) && pfd >= 0 && (v & ~(1ull << 63)) == size;
+      if (!ok) {
+        if (pfd >= 0) close(pfd);
+        break;
+      }
+      all_mc = all_mc && (v >> 63) != 0;
+      CUmemGenericAllocationHandle ph;
+      ok = api.MemImportFromShareableHandle(&ph, reinterpret_cast<void*>(static_cast<uintptr_t>(pfd)),
+                                            CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) == CUDA_SUCCESS;
+      close(pfd);
+      CUdeviceptr pva = 0;
+      ok = ok && map_rw(ph, &pva);
+      if (ok) out->peers[static_cast<size_t>(i)] = reinterpret_cast<void*>(pva);
+    }
+    // a token every member publishes and fetches from every other member = a barrier
+    auto barrier = [&](const std::string& what, bool good) -> bool {
+      fx->Publish(tag + what, -1, good ? 1 : 0);
+      bool all = good;
+      for (int i = 0; i < n; ++i) {
+        if (i == g.index) continue;
+        uint64_t v = 0;
+        all = FdExchange::Fetch(endpoint(i), tag + what, nullptr, &v) && v == 1 && all;
+      }
+      return all;
+    };
+    ok = barrier("/mapped", ok);
+    if (ok && all_mc) {
+      // NVLS: one multicast object over all members' devices
+      CUmemGenericAllocationHandle mch = 0;
+      bool mc_ok = true;
+      int mcfd = -1;
+      if (g.index == 0) {
+        mc_ok = api.MulticastCreate(&mch, &mcprop) == CUDA_SUCCESS &&
+                api.MemExportToShareableHandle(&mcfd, mch, CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR, 0) == CUDA_SUCCESS;
+        fx->Publish(tag + "/mc", mc_ok ? mcfd : -1, mc_ok ? 1 : 0);
+      } else {
+        uint64_t v = 0;
+        mc_ok = FdExchange::Fetch(endpoint(0), tag + "/mc", &mcfd, &v) && v == 1 && mcfd >= 0 &&
+                api.MemImportFromShareableHandle(&mch, reinterpret_cast<void*>(static_cast<uintptr_t>(mcfd)),
+                                                 CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR) == CUDA_SUCCESS;
+      }
+      mc_ok = mc_ok && api.MulticastAddDevice(mch, cudev) == CUDA_SUCCESS;
+      mc_ok = barrier("/mc_added", mc_ok);  // every device is in the team before anybody binds
+      mc_ok = mc_ok && api.MulticastBindMem(mch, 0, mine, 0, size, 0) == CUDA_SUCCESS;
+      mc_ok = barrier("/mc_bound", mc_ok);
+      CUdeviceptr mcva = 0;
+      if (mc_ok && map_rw(mch, &mcva)) out->mc = reinterpret_cast<void*>(mcva);
+      const bool everybody = barrier("/mc_mapped", out->mc != nullptr);
+      if (!everybody) out->mc = nullptr;  // all or nobody: the members must agree on the path
+      if (mcfd >= 0) close(mcfd);
+      if (!out->mc) {
+        LOG(WARNING) << "symmetric buffer '" << tag << "': NVSwitch multicast could not be set up; "
+                     << "peers are reachable one by one";
+      }
+    }
+    ok = barrier("/done", ok);
+    fx->Retract(tag + "/mem");
+    close(fd);
+    return ok;
   }
 
   void EngineStats(uint64_t* launches, uint64_t* items) override {

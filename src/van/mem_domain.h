@@ -36,6 +36,7 @@
 #include <thread>
 #include <vector>
 
+#include "ps/internal/symmetric.h"
 #include "ps/internal/utils.h"
 #include "kernels/host_kernels.h"
 #include "ps/sarray.h"
@@ -102,6 +103,16 @@ inline uint64_t WireBytes(int codec, uint64_t n_src_bytes) {
 class MemDomain {
  public:
   virtual ~MemDomain() {}
+  /*!
+   * \brief collective over `group`: allocate `bytes` of zero-filled symmetric memory under the
+   *        job-wide name `tag`. Handles travel as file descriptors through FdExchange (unix
+   *        sockets); every step that needs all members doubles as a barrier. False if this
+   *        domain cannot share memory that way.
+   */
+  virtual bool SymmetricAlloc(const SymmetricGroup& /*group*/, const std::string& /*tag*/, size_t /*bytes*/,
+                              SymmetricBuffer* /*out*/) {
+    return false;
+  }
   virtual const char* name() const = 0;
   /*! \brief true if values tagged (type, ptr) should travel one-sided through this domain */
   virtual bool Handles(int device_type, const void* ptr) = 0;
@@ -389,6 +400,8 @@ class ShmDomain : public MemDomain {
     std::atomic_thread_fence(std::memory_order_release);
     return Ticket();
   }
+  /*! \brief CPU twin: memfd-backed blocks mapped by every member; no multicast (mc stays null) */
+  bool SymmetricAlloc(const SymmetricGroup& g, const std::string& tag, size_t bytes, SymmetricBuffer* out) override;
   void* MapSignalWord(void* /*page*/, size_t /*bytes*/, void* host_word) override { return host_word; }
   bool CopySignal(const CopyItem& item, void* word, uint64_t value) override {
     auto* flag = static_cast<std::atomic<uint64_t>*>(word);
@@ -510,5 +523,63 @@ class ShmDomain : public MemDomain {
   std::map<std::string, std::pair<void*, size_t>> imported_;
 };
 
+}  // namespace ps
+
+#include "van/fd_exchange.h"
+
+namespace ps {
+inline bool ShmDomain::SymmetricAlloc(const SymmetricGroup& g, const std::string& tag, size_t bytes,
+                                      SymmetricBuffer* out) {
+  FdExchange* fx = FdExchange::Get(g.job_port);
+  if (!fx || g.index < 0 || g.pids.empty()) return false;
+  const size_t size = AlignUp(bytes ? bytes : 1, 4096);
+  const std::string name = "/" + ShmScopedPrefix("pslite_b200_") + std::to_string(getpid()) + "_sym_" + tag;
+  shm_unlink(name.c_str());
+  const int fd = shm_open(name.c_str(), O_CREAT | O_RDWR | O_EXCL, 0600);
+  if (fd < 0) return false;
+  shm_unlink(name.c_str());  // the descriptor is all anybody needs
+  if (ftruncate(fd, static_cast<off_t>(size)) != 0) {
+    close(fd);
+    return false;
+  }
+  void* mine = mmap(nullptr, size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+  if (mine == MAP_FAILED) {
+    close(fd);
+    return false;
+  }
+  memset(mine, 0, size);
+  out->local = mine;
+  out->bytes = size;
+  out->index = g.index;
+  out->count = static_cast<int>(g.pids.size());
+  out->peers.assign(g.pids.size(), nullptr);
+  out->peers[g.index] = mine;
+  out->mc = nullptr;
+  fx->Publish(tag + "/mem", fd, size);
+  bool ok = true;
+  for (size_t i = 0; i < g.pids.size() && ok; ++i) {
+    if (static_cast<int>(i) == g.index) continue;
+    int pfd = -1;
+    uint64_t psize = 0;
+    ok = FdExchange::Fetch(FdExchange::EndpointName(g.job_port, g.pids[i]), tag + "/mem", &pfd, &psize) &&
+         pfd >= 0 && psize == size;
+    if (ok) {
+      void* m = mmap(nullptr, size, PROT_READ | PROT_WRITE, MAP_SHARED, pfd, 0);
+      ok = m != MAP_FAILED;
+      if (ok) out->peers[i] = m;
+    }
+    if (pfd >= 0) close(pfd);
+  }
+  // nobody retracts (or exits) before everybody has fetched
+  fx->Publish(tag + "/done", -1, ok ? 1 : 0);
+  for (size_t i = 0; i < g.pids.size(); ++i) {
+    if (static_cast<int>(i) == g.index) continue;
+    uint64_t v = 0;
+    ok = FdExchange::Fetch(FdExchange::EndpointName(g.job_port, g.pids[i]), tag + "/done", nullptr, &v) && v == 1 && ok;
+  }
+  fx->Retract(tag + "/mem");  // (the "/done" token stays: a slower member may not have asked for it yet)
+  close(fd);
+  return ok;
+}
 }  // namespace ps
 #endif  // PS_VAN_MEM_DOMAIN_H_

@@ -108,6 +108,46 @@ class OneSidedVan : public TcpVan {
   void* AllocExportable(size_t bytes) override { return domain_->Alloc(bytes); }
   void FreeExportable(void* p) override { domain_->Free(p); }
   void* DataStream() override { return domain_->Stream(); }
+
+  bool AllocSymmetric(const std::string& tag, size_t bytes, SymmetricBuffer* out) override {
+    // process-wide: the worker van and the server van of a joint process share ONE block
+    // (a device joins a multicast team once, and both roles must see the same bytes)
+    static std::mutex mu;
+    static std::map<std::string, SymmetricBuffer> done;
+    const int job_port = GetEnv("DMLC_PS_ROOT_PORT", 0);
+    const std::string key = std::to_string(job_port) + "/" + type_ + "/" + tag;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = done.find(key);
+    if (it != done.end()) {
+      *out = it->second;
+      return true;
+    }
+    // the participants: one entry per PROCESS that runs a worker or a server on this host, ordered by
+    // its smallest node id (every process derives the same list from the scheduler's node table)
+    std::vector<Node> nodes = ClusterNodes();
+    std::sort(nodes.begin(), nodes.end(), [](const Node& a, const Node& b) { return a.id < b.id; });
+    SymmetricGroup g;
+    g.job_port = job_port;
+    for (const Node& n : nodes) {
+      if (n.hostname != my_node_.hostname || n.pid == 0) continue;
+      if (std::find(g.pids.begin(), g.pids.end(), n.pid) == g.pids.end()) g.pids.push_back(n.pid);
+    }
+    const int me = static_cast<int>(getpid());
+    for (size_t i = 0; i < g.pids.size(); ++i) {
+      if (g.pids[i] == me) g.index = static_cast<int>(i);
+    }
+    if (g.index < 0) {
+      LOG(WARNING) << type_ << " van: AllocSymmetric before the node table arrived (or from a process that is "
+                   << "neither worker nor server)";
+      return false;
+    }
+    if (!domain_->SymmetricAlloc(g, tag, bytes, out)) return false;
+    done[key] = *out;
+    PS_VLOG(1) << type_ << " van: symmetric buffer '" << tag << "' " << out->bytes << " B, member " << out->index
+               << " of " << out->count << ", multicast " << (out->mc ? "yes" : "no");
+    return true;
+  }
+
   void TransportStats(std::vector<std::pair<std::string, uint64_t>>* out) override {
     uint64_t launches = 0, items = 0;
     domain_->EngineStats(&launches, &items);

@@ -44,6 +44,29 @@ def test_python_push_pull(native, van, nw, ns):
     assert passes == nw
 
 
+def test_symmetric_memory_shm(native):
+    """Van::AllocSymmetric on the shm van: 2 workers + 2 servers (4 processes) allocate one symmetric
+    buffer through FdExchange (descriptors over unix sockets) and read each other's blocks"""
+    port = str(free_port())
+    env = dict(os.environ)
+    env["PSLITE_NO_AUTOBUILD"] = "1"
+    helper = os.path.join(HERE, "helpers", "symm_node.py")
+    procs = [(role, subprocess.Popen([sys.executable, helper, role, "shm", "2", "2", port], env=env,
+                                     stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+             for role in ("scheduler", "server", "server", "worker", "worker")]
+    outs = []
+    for role, p in procs:
+        try:
+            o, _ = p.communicate(timeout=120)
+        except subprocess.TimeoutExpired:
+            for _, q in procs:
+                q.kill()
+            o, _ = p.communicate()
+        outs.append((role, p.returncode, o))
+    assert all(c == 0 for _, c, _ in outs), "\n".join(f"[{r} rc={c}]\n{o[-1500:]}" for r, c, o in outs)
+    assert sum(o.count("PASS") for _, _, o in outs) == 4
+
+
 def test_python_large_message_shm(native):
     rc, outs = run_cluster("shm", 1, 1, n_elems=2_000_000)
     assert rc == 0, "\n".join(f"[{r} rc={c}]\n{o[-1500:]}" for r, c, o in outs)
