@@ -744,6 +744,12 @@ PYBIND11_MODULE(_C, m) {
                                   scale, max_ctas, &sig, CurrentStream(src)), "ps_launch_copy_signal");
   }, py::arg("dst"), py::arg("src"), py::arg("codec"), py::arg("scale"), py::arg("max_ctas"),
      py::arg("flag"), py::arg("value"), py::arg("counter"));
+  // K_pull through the switch: src -> every buffer bound to the multicast address (one multimem.st stream)
+  m.def("copy_multicast", [](uint64_t mc_dst, const torch::Tensor& src, int max_ctas) {
+    TORCH_CHECK(src.is_cuda() && mc_dst != 0, "copy_multicast: device source and a multicast address");
+    CheckRc(ps_launch_copy_multicast(reinterpret_cast<void*>(mc_dst), src.data_ptr(), static_cast<size_t>(src.nbytes()),
+                                     max_ctas, nullptr, CurrentStream(src)), "ps_launch_copy_multicast");
+  }, py::arg("mc_dst"), py::arg("src"), py::arg("max_ctas") = 0);
   m.def("copy_multi", [](std::vector<torch::Tensor> dsts, const std::vector<torch::Tensor>& srcs, int max_ctas) {
     TORCH_CHECK(dsts.size() == srcs.size(), "dsts / srcs length mismatch");
     if (dsts.empty()) return;

@@ -22,7 +22,17 @@ if [ -n "${JOINT:-}" ]; then
   # co-located mode: every process is worker i + server i (DMLC_ROLE=joint)
   for ((i=0; i<${DMLC_NUM_WORKER}; ++i)); do
     if [ -n "${WORKER_GPU_BASE:-}" ]; then export PS_CUDA_DEVICE=$((WORKER_GPU_BASE + i)); fi
-    DMLC_ROLE=joint DMLC_RANK=$i ${bin} ${args} &
+    if [ "${BYTEPS_ENABLE_MIXED_MODE:-0}" != "0" ]; then
+      DMLC_ROLE=joint ${bin} ${args} &   # mixed mode orders the ranks itself (plain servers first)
+    else
+      DMLC_ROLE=joint DMLC_RANK=$i ${bin} ${args} &
+    fi
+    pids+=($!)
+  done
+  # mixed mode (BYTEPS_ENABLE_MIXED_MODE): servers beyond the co-located ones are plain processes
+  for ((i=${DMLC_NUM_WORKER}; i<${DMLC_NUM_SERVER}; ++i)); do
+    if [ -n "${SERVER_GPU_BASE:-}" ]; then export PS_CUDA_DEVICE=$((SERVER_GPU_BASE + i - DMLC_NUM_WORKER)); fi
+    DMLC_ROLE=server ${bin} ${args} &
     pids+=($!)
   done
 else

@@ -437,19 +437,23 @@ void Van::OrderRegistrants(std::vector<Node>* nodes) {
     return a.port < b.port;
   };
   if (mixed) {
-    // hosts that run only a server sort before hosts that co-locate worker+server
-    std::unordered_map<std::string, int> per_host;
+    // places that run only a server sort before places that co-locate worker+server. The
+    // reference counts nodes per IP (one machine = one place, src/van.cc:126-140); on one box all
+    // nodes share the IP, so a place is a PROCESS here: a joint process registers its worker
+    // and its server with the same pid.
+    auto place = [](const Node& n) { return n.hostname + "#" + std::to_string(n.pid); };
+    std::unordered_map<std::string, int> per_place;
     for (const Node& n : *nodes) {
-      ++per_host[n.hostname];
-      CHECK_LE(per_host[n.hostname], 2) << n.hostname;
+      ++per_place[place(n)];
+      CHECK_LE(per_place[place(n)], 2) << place(n);
     }
     std::stable_sort(nodes->begin(), nodes->end(), [&](const Node& a, const Node& b) {
-      const int ca = per_host[a.hostname], cb = per_host[b.hostname];
+      const int ca = per_place[place(a)], cb = per_place[place(b)];
       if (ca != cb) return ca < cb;
       return by_addr(a, b);
     });
     for (const Node& n : *nodes) {
-      if (per_host[n.hostname] == 1) CHECK_EQ(n.role, Node::SERVER) << n.DebugString();
+      if (per_place[place(n)] == 1) CHECK_EQ(n.role, Node::SERVER) << n.DebugString();
     }
   } else if (!ordered_hosts.empty()) {
     // rank follows the position of the node's IP in the comma-separated list

@@ -113,6 +113,34 @@ k_copy_vec16(int4* __restrict__ dst, const int4* __restrict__ src, size_t n16, c
   signal_tail(sig);
 }
 
+// ---------------------------------------------------------------------------
+// K_pull through the switch: the destination is a MULTICAST address bound to the same offset
+// of every worker's buffer — each 16-byte vector leaves this GPU once (multimem.st) and the
+// NVSwitch replicates it into all of them (NVLS). The source is read once, the server's
+// egress is 1x the payload instead of W x. The reference's IPC pull copies into one shared
+// segment per peer (src/rdma_transport.h:524-589).
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void multimem_st16(void* p, const int4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(v.x), "r"(v.y),
+               "r"(v.z), "r"(v.w)
+               : "memory");
+}
+template <int UNROLL>
+__global__ void __launch_bounds__(kThreads)
+k_copy_mc16(int4* __restrict__ mc_dst, const int4* __restrict__ src, size_t n16, const ps_signal sig) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * kThreads;
+  size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x;
+  for (; i + (UNROLL - 1) * stride < n16; i += UNROLL * stride) {
+    int4 v[UNROLL];
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) v[u] = ld_stream(src + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < UNROLL; ++u) multimem_st16(mc_dst + i + u * stride, v[u]);
+  }
+  for (; i < n16; i += stride) multimem_st16(mc_dst + i, ld_stream(src + i));
+  signal_tail(sig);
+}
+
 __global__ void k_copy_bytes(unsigned char* __restrict__ dst, const unsigned char* __restrict__ src,
                              size_t n, const ps_signal sig) {
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -594,6 +622,22 @@ extern "C" int ps_launch_copy_signal(void* dst, const void* src, size_t n, int c
     default:
       return static_cast<int>(cudaErrorInvalidValue);
   }
+  return static_cast<int>(cudaGetLastError());
+}
+
+extern "C" int ps_launch_copy_multicast(void* mc_dst, const void* src, size_t n, int max_ctas,
+                                        const ps_signal* sig_, ps_stream_t stream_) {
+  cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+  const ps_signal none = {nullptr, nullptr, 0};
+  const ps_signal sig = (sig_ && sig_->flag) ? *sig_ : none;
+  const uintptr_t d = reinterpret_cast<uintptr_t>(mc_dst), s = reinterpret_cast<uintptr_t>(src);
+  // multimem operates on naturally aligned 4 / 8 / 16-byte words: whole vectors only
+  if (((d | s) & 15) != 0 || (n & 15) != 0) return static_cast<int>(cudaErrorMisalignedAddress);
+  if (n == 0) return ps_launch_signal(&sig, stream_);
+  const size_t n16 = n / 16;
+  k_copy_mc16<4><<<GridFor((n16 + 3) / 4, max_ctas, 8), kThreads, 0, stream>>>(
+      static_cast<int4*>(mc_dst), static_cast<const int4*>(src), n16, sig);
+  ++g_launches;
   return static_cast<int>(cudaGetLastError());
 }
 

@@ -79,6 +79,13 @@ typedef struct {
 /*! \brief ps_launch_copy + completion signal (sig may be null) */
 int ps_launch_copy_signal(void* dst, const void* src, size_t n_src_bytes, int codec, float scale,
                           int max_ctas, const ps_signal* sig, ps_stream_t stream);
+/*!
+ * \brief pull fan-out through the switch: `mc_dst` is a multicast address (see
+ *        Van::AllocSymmetric) — every 16-byte vector is stored once with multimem.st and lands in
+ *        all bound buffers. Addresses and `n_bytes` must be multiples of 16.
+ */
+int ps_launch_copy_multicast(void* mc_dst, const void* src, size_t n_bytes, int max_ctas,
+                             const ps_signal* sig, ps_stream_t stream);
 /*! \brief only the signal: ordered after everything enqueued on `stream` before it */
 int ps_launch_signal(const ps_signal* sig, ps_stream_t stream);
 

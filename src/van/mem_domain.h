@@ -36,6 +36,7 @@
 #include <thread>
 #include <vector>
 
+#include "ps/internal/message.h"
 #include "ps/internal/symmetric.h"
 #include "ps/internal/utils.h"
 #include "kernels/host_kernels.h"
@@ -71,34 +72,6 @@ struct RegionDesc {
 struct Ticket {
   void* event = nullptr;  // domain-specific; nullptr = already complete
 };
-
-/*! \brief optional transform applied by the copy engine while it moves the bytes */
-enum WireCodec : int {
-  kCodecRaw = 0,           // byte copy
-  kCodecF32ToBf16 = 1,     // dst_bf16[i] = src_f32[i] * scale
-  kCodecBf16Scale = 2,     // dst_bf16[i] = src_bf16[i] * scale
-  kCodecF32ToFp8Block = 3, // block-scaled e4m3: 32 elements share one e8m0 exponent
-  kCodecBf16ToFp8Block = 4,
-  kCodecPlaced = 5,        // payload already written by the application; send descriptor only
-  kCodecNumCodecs
-};
-
-/*! \brief bytes the wire form of `n_src_bytes` of source occupies */
-inline uint64_t WireBytes(int codec, uint64_t n_src_bytes) {
-  switch (codec) {
-    case kCodecF32ToBf16: return n_src_bytes / 2;
-    case kCodecBf16Scale: return n_src_bytes;
-    case kCodecF32ToFp8Block: {  // n elements -> n bytes of e4m3 + n/32 scale bytes
-      const uint64_t n = n_src_bytes / 4;
-      return AlignUp(n, 32) + AlignUp(n, 32) / 32;
-    }
-    case kCodecBf16ToFp8Block: {
-      const uint64_t n = n_src_bytes / 2;
-      return AlignUp(n, 32) + AlignUp(n, 32) / 32;
-    }
-    default: return n_src_bytes;
-  }
-}
 
 class MemDomain {
  public:

@@ -23,6 +23,10 @@ def main():
                  "DMLC_PS_ROOT_PORT": port, "DMLC_NODE_HOST": "127.0.0.1", "PS_VAN_TYPE": van,
                  "DMLC_ROLE": role}.items():
         C.set_env(k, str(v))
+    dev = -1
+    if van == "nvl" and role != "scheduler":
+        dev = int(os.environ.get("PS_CUDA_DEVICE", "0"))
+        torch.cuda.set_device(dev)
     C.start_ps(0, role, -1, True)
     if role == "scheduler":
         C.finalize(0, role, True)
@@ -31,17 +35,29 @@ def main():
     local, mc, peers, index, count = C.alloc_symmetric("check", n, role)
     assert count == nw + ns and len(peers) == count and local.numel() >= n
     assert int(local.sum()) == 0, "a fresh symmetric block is zero-filled"
-    local[:n] = (torch.arange(n, dtype=torch.int32) * (index + 1) % 251).to(torch.uint8)
+    local[:n] = (torch.arange(n, dtype=torch.int32, device=local.device) * (index + 1) % 251).to(torch.uint8)
+    if dev >= 0:
+        torch.cuda.synchronize()
     # second call (any role of this process) returns the same block
     again = C.alloc_symmetric("check", n, role)
     assert again[0].data_ptr() == local.data_ptr() and again[3] == index
     C.barrier(0, C.WORKER_GROUP + C.SERVER_GROUP, role)
     ok = True
     for i, addr in enumerate(peers):
-        got = C.tensor_at(addr, n, -1)
+        got = C.tensor_at(addr, n, dev).cpu()  # on a GPU: loads over NVLink through the peer mapping
         want = (torch.arange(n, dtype=torch.int32) * (i + 1) % 251).to(torch.uint8)
         ok = ok and torch.equal(got, want)
     C.barrier(0, C.WORKER_GROUP + C.SERVER_GROUP, role)
+    if mc and dev >= 0:
+        # NVLS: member 0 stores ONE stream to the multicast address, every member finds it in its own block
+        if index == 0:
+            src = (torch.arange(n, dtype=torch.int32, device=local.device) % 199).to(torch.uint8)
+            C.copy_multicast(mc, src)
+            torch.cuda.synchronize()
+        C.barrier(0, C.WORKER_GROUP + C.SERVER_GROUP, role)
+        want = (torch.arange(n, dtype=torch.int32) % 199).to(torch.uint8)
+        ok = ok and torch.equal(local[:n].cpu(), want)
+        C.barrier(0, C.WORKER_GROUP + C.SERVER_GROUP, role)
     print(f"{role} member {index}/{count} multicast={'yes' if mc else 'no'} {'PASS' if ok else 'FAIL'}", flush=True)
     C.finalize(0, role, True)
     sys.exit(0 if ok else 1)

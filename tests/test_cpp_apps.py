@@ -86,6 +86,17 @@ def test_declined_ring_offer_falls_back_to_socket(built_native_tree, van):
     assert all(int(x) == 0 for x in re.findall(r"(\d+) descriptors gated by the copy engine", out))
 
 
+def test_ipc_benchmark_symmetric_buffer_and_mixed_mode(built_native_tree):
+    """test_ipc_benchmark: values in a symmetric buffer (IPC_NVLS_PULL; on the shm van the replies stay
+    unicast), and the reference's mixed mode — 2 co-located + 1 plain server, keys spread by its formula"""
+    env = {"PS_VAN_TYPE": "shm", "JOINT": 1, "IPC_NVLS_PULL": 1, "IPC_VERIFY": 1, "NUM_KEY_PER_SERVER": 4}
+    rc, out = launch(built_native_tree, 2, 2, "test_ipc_benchmark", 65536, 10, env=env)
+    assert rc == 0 and out.count("VERIFIED") == 2 and "symmetric buffer" in out, out[-3000:]
+    env = {"PS_VAN_TYPE": "shm", "JOINT": 1, "BYTEPS_ENABLE_MIXED_MODE": 1, "IPC_VERIFY": 1, "NUM_KEY_PER_SERVER": 6}
+    rc, out = launch(built_native_tree, 3, 2, "test_ipc_benchmark", 65536, 10, env=env)
+    assert rc == 0 and out.count("VERIFIED") == 2 and "mixed mode" in out, out[-3000:]
+
+
 def test_tutorial_example_runs(built_native_tree):
     """examples/kv_hello.cc is the program printed in docs/tutorials.md"""
     rc, out = launch(built_native_tree, 2, 2, "kv_hello")

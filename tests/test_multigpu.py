@@ -48,6 +48,42 @@ def test_multicast_pull_fanout_two_gpus():
 
 
 @pytest.mark.timeout(300)
+def test_native_symmetric_memory_and_multicast():
+    """Van::AllocSymmetric on the nvl van (cuMemCreate + POSIX handles over unix sockets + cuMulticast*),
+    no torch symmetric-memory API involved: one worker process and one server process per GPU pair map
+    each other's blocks; with an NVSwitch one multimem.st stream lands in every block"""
+    ngpu = min(torch.cuda.device_count(), 4)
+    nw = ns = ngpu // 2
+    port = str(_free_port())
+    helper = os.path.join(ROOT, "tests", "helpers", "symm_node.py")
+    procs = []
+    gpu = 0
+    for role, count in (("scheduler", 1), ("server", ns), ("worker", nw)):
+        for _ in range(count):
+            env = dict(os.environ)
+            env["PSLITE_NO_AUTOBUILD"] = "1"
+            if role != "scheduler":
+                env["PS_CUDA_DEVICE"] = str(gpu)
+                gpu += 1
+            procs.append((role, subprocess.Popen([sys.executable, helper, role, "nvl", str(nw), str(ns), port],
+                                                 env=env, cwd=ROOT, stdout=subprocess.PIPE,
+                                                 stderr=subprocess.STDOUT, text=True)))
+    outs = []
+    for role, p in procs:
+        try:
+            o, _ = p.communicate(timeout=240)
+        except subprocess.TimeoutExpired:
+            for _, q in procs:
+                q.kill()
+            o, _ = p.communicate()
+        outs.append((role, p.returncode, o))
+    report = "\n".join(f"[{r} rc={c}]\n{o[-1500:]}" for r, c, o in outs)
+    assert all(c == 0 for _, c, _ in outs), report
+    assert sum(o.count("PASS") for _, _, o in outs) == nw + ns, report
+    print(report)
+
+
+@pytest.mark.timeout(300)
 def test_in_switch_gradient_reduction_two_gpus():
     """gradients summed by multimem.ld_reduce inside the update kernel (no landing slots)"""
     import torch.distributed._symmetric_memory  # noqa: F401  (present in this torch)
