@@ -12,10 +12,21 @@
  * it pulls (DEBUG_MODE=1), so lost or crossed messages are detected, and prints per-phase
  * times. Roles: scheduler, or joint (BYTEPS_NODE_ID = this node's index, defaults to
  * DMLC_RANK).   usage: test_benchmark_stress [len=30720000] [repeat=20]   env: BENCHMARK_NTHREAD (8)
+ *
+ * On the nvl van (or STRESS_GPU=1) every buffer lives in HBM (the reference's GPU mode,
+ * tests/test_benchmark_stress.cc:249-432): a minibatch's payload is generated on the device
+ * (k_fill_u32, seeded by session / minibatch / destination), travels over NVLink, and what the
+ * Gather and DenseReduce phases pull back is CHECKSUMMED in full on the device (k_checksum_u32)
+ * against the checksum of what was pushed — not just an 8-byte stamp. Works under fault
+ * injection too: PS_DROP_MSG=5 PS_RESEND=1.
  */
 #include <chrono>
 #include <cstring>
 #include "ps/ps.h"
+#if PS_USE_CUDA
+#include <cuda_runtime.h>
+#include "kernels/ps_kernels.h"
+#endif
 using namespace ps;
 
 namespace {
@@ -45,13 +56,31 @@ int main(int argc, char* argv[]) {
   }
   CHECK(role == Node::JOINT) << "the stress test runs joint nodes";
   const int node_id = GetEnv("BYTEPS_NODE_ID", GetEnv("DMLC_RANK", 0));
+#if PS_USE_CUDA
+  if (GetEnvStr("PS_VAN_TYPE") == "nvl") cudaSetDevice(GetEnv("PS_CUDA_DEVICE", 0));
+#endif
   StartPS(0, role, node_id, true);
+  Van* van = Postoffice::GetWorker()->van();
+  bool gpu = van->GetType() == "nvl";
+#if !PS_USE_CUDA
+  gpu = false;
+#endif
+  const int gpu_dev = gpu ? van->my_node().dev_id : 0;
 
   std::mutex mu;
   std::unordered_map<Key, SArray<char>> store;
   KVServer<char> server(0);
   server.set_request_handle([&](const KVMeta& req, const KVPairs<char>& d, KVServer<char>* s) {
     const Key key = d.keys[0];
+    if (req.push && gpu) {
+      // the landing slot in HBM is the store: a pull is answered from it, byte for byte
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        store[key] = d.vals;
+      }
+      s->Response(req);
+      return;
+    }
     if (req.push) {
       {
         std::lock_guard<std::mutex> lk(mu);
@@ -93,10 +122,41 @@ int main(int argc, char* argv[]) {
     threads.emplace_back([&, tid] {
       const int session = node_id * nthread + tid;
       // one buffer per (family, dst)
+#if PS_USE_CUDA
+      cudaStream_t stream = nullptr;
+      unsigned long long* sum_dev = nullptr;
+      if (gpu) {
+        CHECK(cudaSetDevice(gpu_dev) == cudaSuccess);
+        CHECK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking) == cudaSuccess);
+        CHECK(cudaMalloc(reinterpret_cast<void**>(&sum_dev), 16) == cudaSuccess);
+      }
+      // fill a device buffer with this minibatch's pattern / checksum all of it
+      auto gpu_fill = [&](Buf& b, uint32_t seed) {
+        CHECK_EQ(ps_launch_fill_u32(b.val.data(), static_cast<size_t>(len) / 4, seed, reinterpret_cast<ps_stream_t>(stream)), 0);
+        CHECK(cudaStreamSynchronize(stream) == cudaSuccess);
+      };
+      auto gpu_sum = [&](const Buf& b) {
+        unsigned long long h = 0;
+        CHECK_EQ(ps_launch_checksum_u32(b.val.data(), static_cast<size_t>(len) / 4, sum_dev, reinterpret_cast<ps_stream_t>(stream)), 0);
+        CHECK(cudaMemcpyAsync(&h, sum_dev, 8, cudaMemcpyDeviceToHost, stream) == cudaSuccess);
+        CHECK(cudaStreamSynchronize(stream) == cudaSuccess);
+        return h;
+      };
+      auto gpu_clear = [&](Buf& b) {
+        CHECK(cudaMemsetAsync(b.val.data(), 0, static_cast<size_t>(len), stream) == cudaSuccess);
+        CHECK(cudaStreamSynchronize(stream) == cudaSuccess);
+      };
+#endif
       auto make = [&](int family, int dst) {
         Buf b;
         b.key = SArray<Key>(1, MakeKey(ranges, family, session, dst, sessions));
-        b.val = SArray<char>(static_cast<size_t>(len), 1);
+        if (gpu) {
+          char* p = static_cast<char*>(van->AllocExportable(static_cast<size_t>(len)));
+          CHECK(p) << "out of device memory";
+          b.val.reset(p, static_cast<size_t>(len), [](char*) {}, GPU, gpu_dev, GPU, gpu_dev);
+        } else {
+          b.val = SArray<char>(static_cast<size_t>(len), 1);
+        }
         b.len = SArray<int>(1, len);
         return b;
       };
@@ -106,7 +166,17 @@ int main(int argc, char* argv[]) {
         gs.push_back(make(1, d));
         dense.push_back(make(2, d));
       }
-      auto stamp = [&](Buf& b, int mb) {
+      std::vector<unsigned long long> want_gs(static_cast<size_t>(nodes), 0), want_dense(static_cast<size_t>(nodes), 0);
+      auto stamp = [&](Buf& b, int mb, int dst = 0, unsigned long long* want = nullptr) {
+#if PS_USE_CUDA
+        if (gpu) {
+          gpu_fill(b, static_cast<uint32_t>(session * 1000003 + mb * 131 + dst));
+          if (want) *want = gpu_sum(b);
+          return;
+        }
+#endif
+        (void)dst;
+        (void)want;
         uint64_t s = (static_cast<uint64_t>(session) << 32) | static_cast<uint32_t>(mb);
         memcpy(b.val.data(), &s, 8);
       };
@@ -130,7 +200,7 @@ int main(int argc, char* argv[]) {
         t_ds += ms(a, b);
         for (int d = 0; d < nodes; ++d) {  // Scatter (push) ...
           if (d == node_id && nodes > 1) continue;
-          stamp(gs[d], mb);
+          stamp(gs[d], mb, d, &want_gs[static_cast<size_t>(d)]);
           ts.push_back(kv.ZPush(gs[d].key, gs[d].val, gs[d].len));
         }
         drain();
@@ -138,13 +208,27 @@ int main(int argc, char* argv[]) {
         t_s += ms(b, c);
         for (int d = 0; d < nodes; ++d) {  // ... then Gather (pull) the same keys back
           if (d == node_id && nodes > 1) continue;
-          memset(gs[d].val.data(), 0, 8);
+#if PS_USE_CUDA
+          if (gpu) gpu_clear(gs[d]);
+#endif
+          if (!gpu) memset(gs[d].val.data(), 0, 8);
           ts.push_back(kv.ZPull(gs[d].key, &gs[d].val, &gs[d].len));
         }
         drain();
         auto e = now();
         t_g += ms(c, e);
-        if (debug) {
+#if PS_USE_CUDA
+        if (gpu) {  // every byte that came back over NVLink is checked, every minibatch
+          for (int d = 0; d < nodes; ++d) {
+            if (d == node_id && nodes > 1) continue;
+            if (gpu_sum(gs[d]) != want_gs[static_cast<size_t>(d)]) {
+              ++failures;
+              LOG(ERROR) << "session " << session << " minibatch " << mb << ": gather from node " << d << " is corrupt";
+            }
+          }
+        }
+#endif
+        if (debug && !gpu) {
           for (int d = 0; d < nodes; ++d) {
             if (d == node_id && nodes > 1) continue;
             uint64_t s;
@@ -153,12 +237,22 @@ int main(int argc, char* argv[]) {
           }
         }
         for (int d = 0; d < nodes; ++d) {  // DenseReduce: push + pull against every node
-          stamp(dense[d], mb);
+          stamp(dense[d], mb, d + 100, &want_dense[static_cast<size_t>(d)]);
           ts.push_back(kv.ZPush(dense[d].key, dense[d].val, dense[d].len));
           ts.push_back(kv.ZPull(dense[d].key, &dense[d].val, &dense[d].len));
         }
         drain();
         t_d += ms(e, now());
+#if PS_USE_CUDA
+        if (gpu) {
+          for (int d = 0; d < nodes; ++d) {
+            if (gpu_sum(dense[d]) != want_dense[static_cast<size_t>(d)]) {
+              ++failures;
+              LOG(ERROR) << "session " << session << " minibatch " << mb << ": dense_reduce with node " << d << " is corrupt";
+            }
+          }
+        }
+#endif
       }
       LL << "[node " << node_id << " session " << tid << "] per minibatch: data_scatter "
          << t_ds / repeat << " ms, scatter " << t_s / repeat << " ms, gather " << t_g / repeat
@@ -167,7 +261,7 @@ int main(int argc, char* argv[]) {
   }
   for (auto& t : threads) t.join();
   LL << (failures.load() ? "test_benchmark_stress FAILED" : "test_benchmark_stress PASSED")
-     << " on node " << node_id;
+     << " on node " << node_id << (gpu ? " (HBM buffers, full-payload checksums)" : "");
   Finalize(0, role, true);
   return failures.load() ? 1 : 0;
 }

@@ -83,6 +83,43 @@ def test_native_symmetric_memory_and_multicast():
     print(report)
 
 
+def _local(nservers, nworkers, app, *args, env=None, timeout=240):
+    e = dict(os.environ)
+    e.pop("DMLC_RANK", None)
+    e.update({k: str(v) for k, v in (env or {}).items()})
+    p = subprocess.run([os.path.join(ROOT, "scripts", "local.sh"), str(nservers), str(nworkers),
+                        os.path.join(ROOT, "build", app), *map(str, args)],
+                       env=e, cwd=ROOT, capture_output=True, text=True, timeout=timeout)
+    return p.returncode, p.stdout + p.stderr
+
+
+@pytest.mark.timeout(300)
+def test_ipc_benchmark_nvls_pull():
+    """BASELINE config 5 in C++, no torch: co-located worker+server per GPU, values in a native symmetric
+    buffer, pulls answered through the switch (one multimem.st stream per key and round); bytes verified"""
+    n = min(torch.cuda.device_count(), 4)
+    rc, out = _local(n, n, "test_ipc_benchmark", 4096000, 30,
+                     env={"PS_VAN_TYPE": "nvl", "JOINT": 1, "WORKER_GPU_BASE": 0, "IPC_NVLS_PULL": 1,
+                          "IPC_VERIFY": 1, "NUM_KEY_PER_SERVER": 10})
+    assert rc == 0 and out.count("VERIFIED") == n, out[-3000:]
+    if "NVLS multicast pull" not in out:
+        pytest.skip("no NVSwitch multicast on this box (the unicast fallback passed)")
+    fanouts = [int(x) for x in __import__("re").findall(r"server multicast fan-outs (\d+)", out)]
+    assert all(f > 0 for f in fanouts), out[-2000:]
+    print("\n".join(l for l in out.splitlines() if "goodput" in l))
+
+
+@pytest.mark.timeout(300)
+def test_stress_gpu_buffers_with_message_loss():
+    """the four collective patterns of test_benchmark_stress with HBM buffers, every pulled payload
+    checksummed on the device, while 5 % of the messages are dropped and retransmitted"""
+    n = min(torch.cuda.device_count(), 8)
+    rc, out = _local(n, n, "test_benchmark_stress", 4096000, 4,
+                     env={"PS_VAN_TYPE": "nvl", "JOINT": 1, "WORKER_GPU_BASE": 0, "BENCHMARK_NTHREAD": 2,
+                          "PS_DROP_MSG": 5, "PS_RESEND": 1, "PS_RESEND_TIMEOUT": 200})
+    assert rc == 0 and out.count("test_benchmark_stress PASSED") == n and "full-payload checksums" in out, out[-3000:]
+
+
 @pytest.mark.timeout(300)
 def test_in_switch_gradient_reduction_two_gpus():
     """gradients summed by multimem.ld_reduce inside the update kernel (no landing slots)"""
