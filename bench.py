@@ -440,7 +440,8 @@ def run_llama(args, dist: Dist) -> dict:
     if use_symm and args.nvls_reduce and mc:
         from pslite_b200.parallel.ps_trainer import setup_symmetric_grads
 
-        gbuf, ghdl, gmc, gbytes = setup_symmetric_grads(total, tdist.group.WORLD, dev)
+        gbuf, ghdl, gmc, gbytes = setup_symmetric_grads(total, tdist.group.WORLD, dev,
+                                                              "worker" if ctx.is_worker else "server")
         if server is not None:
             server.set_symmetric_grads(gmc, gbytes)
         dist.barrier()

@@ -7,6 +7,7 @@
 #define PS_INTERNAL_SYMMETRIC_H_
 #include <cstddef>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace ps {
@@ -25,6 +26,14 @@ struct SymmetricBuffer {
   int count = 0;
   std::vector<void*> peers;
   void* mc = nullptr;
+  /*! \brief (node id, member index) for every worker / server node of the job: which block is worker r's? */
+  std::vector<std::pair<int, int>> node_member;
+  int MemberOfNode(int node_id) const {
+    for (const auto& nm : node_member) {
+      if (nm.first == node_id) return nm.second;
+    }
+    return -1;
+  }
 };
 
 /*! \brief who takes part in a symmetric allocation: the processes of a job on this host, in rank order */

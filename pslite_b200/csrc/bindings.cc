@@ -577,7 +577,7 @@ PYBIND11_MODULE(_C, m) {
   /*!
    * \brief collective over all worker / server processes: symmetric memory without torch's private
    *        API. Returns (local uint8 tensor, multicast address or 0, [address of every member's block
-   *        as mapped here], my index, member count).
+   *        as mapped here], my index, member count, [block of worker rank r], [block of server rank r]).
    */
   m.def("alloc_symmetric", [](const std::string& tag, int64_t nbytes, const std::string& as_role) {
     Postoffice* po = as_role == "server" ? Postoffice::GetServer() : Postoffice::GetWorker();
@@ -595,14 +595,49 @@ PYBIND11_MODULE(_C, m) {
     torch::Tensor local = torch::from_blob(sb.local, {static_cast<int64_t>(sb.bytes)}, [](void*) {}, opts);
     std::vector<uint64_t> peers;
     for (void* p : sb.peers) peers.push_back(reinterpret_cast<uint64_t>(p));
-    return py::make_tuple(local, reinterpret_cast<uint64_t>(sb.mc), peers, sb.index, sb.count);
+    // block of worker rank r / server rank r as mapped here (0 if that node is not a member)
+    std::vector<uint64_t> worker_blocks, server_blocks;
+    for (int r = 0; r < NumWorkers(); ++r) {
+      const int m = sb.MemberOfNode(Postoffice::WorkerRankToID(r));
+      worker_blocks.push_back(m >= 0 ? peers[static_cast<size_t>(m)] : 0);
+    }
+    for (int r = 0; r < NumServers(); ++r) {
+      const int m = sb.MemberOfNode(Postoffice::ServerRankToID(r));
+      server_blocks.push_back(m >= 0 ? peers[static_cast<size_t>(m)] : 0);
+    }
+    return py::make_tuple(local, reinterpret_cast<uint64_t>(sb.mc), peers, sb.index, sb.count, worker_blocks,
+                          server_blocks);
   }, py::arg("tag"), py::arg("nbytes"), py::arg("as_role") = "worker");
   /*! \brief a uint8 view of `nbytes` at a raw address of this process (a peer mapping from alloc_symmetric) */
   m.def("tensor_at", [](uint64_t addr, int64_t nbytes, int cuda_device) {
     auto opts = torch::TensorOptions().dtype(torch::kUInt8);
-    if (cuda_device >= 0) opts = opts.device(torch::kCUDA, cuda_device);
+    if (cuda_device >= 0) {
+      // a peer mapping reports its OWNER's device: name that one (any device of the process can
+      // still address the bytes — the mapping is in the unified address space)
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, reinterpret_cast<void*>(addr)) == cudaSuccess &&
+          (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) {
+        cuda_device = attr.device;
+      } else {
+        cudaGetLastError();
+      }
+      opts = opts.device(torch::kCUDA, cuda_device);
+    }
     return torch::from_blob(reinterpret_cast<void*>(addr), {nbytes}, [](void*) {}, opts);
   }, py::arg("addr"), py::arg("nbytes"), py::arg("cuda_device") = -1);
+
+  /*! \brief copy `nbytes` at a raw address of this process (host or device, e.g. a peer mapping) into a CPU tensor */
+  m.def("read_bytes", [](uint64_t addr, int64_t nbytes, bool device) {
+    torch::Tensor out = torch::empty({nbytes}, torch::TensorOptions().dtype(torch::kUInt8));
+    if (device) {
+      // through the CURRENT device: that is the one the mapping was made accessible to
+      TORCH_CHECK(cudaMemcpy(out.data_ptr(), reinterpret_cast<void*>(addr), static_cast<size_t>(nbytes),
+                             cudaMemcpyDeviceToHost) == cudaSuccess, "cudaMemcpy from a mapped address failed");
+    } else {
+      memcpy(out.data_ptr(), reinterpret_cast<void*>(addr), static_cast<size_t>(nbytes));
+    }
+    return out;
+  }, py::arg("addr"), py::arg("nbytes"), py::arg("device") = false);
 
   py::class_<PyKVWorker>(m, "KVWorker")
       .def(py::init<int, int, int>(), py::arg("app_id") = 0, py::arg("customer_id") = 0,

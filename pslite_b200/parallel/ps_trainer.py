@@ -64,12 +64,37 @@ def symmetric_layout(params) -> tuple[list[int], int]:
     return offs, max(cur, 64)
 
 
-def setup_symmetric_params(params, total_elems: int, group, device, worker_ranks: list[int]):
+def _native_symmetric() -> bool:
+    """PS_SYMM_BACKEND=torch falls back to torch.distributed._symmetric_memory (round-1 behaviour)"""
+    import os
+
+    return os.environ.get("PS_SYMM_BACKEND", "native") != "torch"
+
+
+
+def setup_symmetric_params(params, total_elems: int, group, device, worker_ranks: list[int],
+                           role: str | None = None):
     """Move `params` (may be None on server-only ranks) into a symmetric-memory buffer that
     every rank of `group` allocates identically, rendezvous, and return
-    (flat, multicast_ptr, peer_ptrs_of_workers, nbytes). With NVSwitch multicast support the
+    (flat, multicast_ptr, peer_ptrs_of_workers, nbytes). `role` names the van of this process to
+    allocate through ("worker" / "server"; default: worker if it has parameters). With NVSwitch multicast support the
     server's update kernel can then publish new parameters to ALL workers with one
     multimem.st stream (NVLS) instead of one unicast stream per worker."""
+    if _native_symmetric():
+        # the runtime's own allocator (Van::AllocSymmetric: cuMemCreate + POSIX handles over unix
+        # sockets + cuMulticast*) — no dependency on torch's private symmetric-memory module
+        local, mc, _, _, _, wblocks, _ = native().alloc_symmetric(
+            "params", total_elems * 2, role or ("worker" if params is not None else "server"))
+        flat = local.view(torch.bfloat16)[:total_elems]
+        hdl = local  # keeps the tensor alive next to its views
+        if params is not None:
+            offs, _ = symmetric_layout(params)
+            with torch.no_grad():
+                for p, off in zip(params, offs):
+                    view = flat[off:off + p.numel()].view(p.shape)
+                    view.copy_(p.data)
+                    p.data = view
+        return flat, hdl, int(mc), [int(wblocks[r]) for r in worker_ranks], total_elems * 2
     import torch.distributed._symmetric_memory as symm_mem
 
     flat = symm_mem.empty(total_elems, dtype=torch.bfloat16, device=device)
@@ -86,10 +111,14 @@ def setup_symmetric_params(params, total_elems: int, group, device, worker_ranks
     return flat, hdl, mc, peers, total_elems * 2
 
 
-def setup_symmetric_grads(total_elems: int, group, device):
+def setup_symmetric_grads(total_elems: int, group, device, role: str = "worker"):
     """Second job-wide symmetric bf16 buffer, for gradients (same layout as the parameters).
     Every rank of `group` allocates it zero-filled — server-only ranks never write theirs, so
     they add nothing to the in-switch sum. Returns (flat, handle, multicast_ptr, nbytes)."""
+    if _native_symmetric():
+        local, mc, _, _, _, _, _ = native().alloc_symmetric("grads", total_elems * 2, role)
+        flat = local.view(torch.bfloat16)[:total_elems]  # zero-filled by the allocator
+        return flat, local, int(mc), total_elems * 2
     import torch.distributed._symmetric_memory as symm_mem
 
     flat = symm_mem.empty(total_elems, dtype=torch.bfloat16, device=device)

@@ -142,6 +142,11 @@ class OneSidedVan : public TcpVan {
       return false;
     }
     if (!domain_->SymmetricAlloc(g, tag, bytes, out)) return false;
+    for (const Node& n : nodes) {
+      for (size_t i = 0; i < g.pids.size(); ++i) {
+        if (n.hostname == my_node_.hostname && n.pid == g.pids[i]) out->node_member.emplace_back(n.id, static_cast<int>(i));
+      }
+    }
     done[key] = *out;
     PS_VLOG(1) << type_ << " van: symmetric buffer '" << tag << "' " << out->bytes << " B, member " << out->index
                << " of " << out->count << ", multicast " << (out->mc ? "yes" : "no");

@@ -32,7 +32,10 @@ def main():
         C.finalize(0, role, True)
         return
     n = 1 << 16
-    local, mc, peers, index, count = C.alloc_symmetric("check", n, role)
+    local, mc, peers, index, count, wblocks, sblocks = C.alloc_symmetric("check", n, role)
+    assert len(wblocks) == nw and len(sblocks) == ns and all(wblocks) and all(sblocks)
+    mine = (wblocks if role == "worker" else sblocks)
+    assert local.data_ptr() in mine, "this process's block must be listed under its own rank"
     assert count == nw + ns and len(peers) == count and local.numel() >= n
     assert int(local.sum()) == 0, "a fresh symmetric block is zero-filled"
     local[:n] = (torch.arange(n, dtype=torch.int32, device=local.device) * (index + 1) % 251).to(torch.uint8)
@@ -44,7 +47,7 @@ def main():
     C.barrier(0, C.WORKER_GROUP + C.SERVER_GROUP, role)
     ok = True
     for i, addr in enumerate(peers):
-        got = C.tensor_at(addr, n, dev).cpu()  # on a GPU: loads over NVLink through the peer mapping
+        got = C.read_bytes(addr, n, dev >= 0)  # on a GPU: read over NVLink through the peer mapping
         want = (torch.arange(n, dtype=torch.int32) * (i + 1) % 251).to(torch.uint8)
         ok = ok and torch.equal(got, want)
     C.barrier(0, C.WORKER_GROUP + C.SERVER_GROUP, role)

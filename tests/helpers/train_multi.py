@@ -84,7 +84,8 @@ def main():
             server.set_symmetric(mc, peers, nbytes)
     gbuf = None
     if nvls_reduce:
-        gbuf, ghdl, gmc, gbytes = setup_symmetric_grads(total, dist.group.WORLD, dev)
+        gbuf, ghdl, gmc, gbytes = setup_symmetric_grads(total, dist.group.WORLD, dev,
+                                                           "worker" if ctx.is_worker else "server")
         if not gmc:  # no NVSwitch multicast here: fall back to landing slots
             nvls_reduce = False
             mcast_info += " nvls=unavailable"

@@ -71,7 +71,7 @@ def test_native_symmetric_memory_and_multicast():
     outs = []
     for role, p in procs:
         try:
-            o, _ = p.communicate(timeout=240)
+            o, _ = p.communicate(timeout=100)
         except subprocess.TimeoutExpired:
             for _, q in procs:
                 q.kill()
@@ -83,7 +83,7 @@ def test_native_symmetric_memory_and_multicast():
     print(report)
 
 
-def _local(nservers, nworkers, app, *args, env=None, timeout=240):
+def _local(nservers, nworkers, app, *args, env=None, timeout=150):
     e = dict(os.environ)
     e.pop("DMLC_RANK", None)
     e.update({k: str(v) for k, v in (env or {}).items()})
