@@ -23,6 +23,8 @@
 #include <cuda_fp8.h>
 #include <cuda_runtime.h>
 
+#include <atomic>
+
 #include <cstdint>
 #include <cstdlib>
 
@@ -281,91 +283,6 @@ k_update(const UpdateDev a, const ps_opt_params o) {
   }
 }
 
-/*!
- * Two groups of 8 elements per thread and pass: all loads of both groups are issued before the
- * first dependent instruction (PS_UPDATE_X2=1). The one-group kernel above spends 63 % of its
- * stall cycles waiting on the first use of a load (ncu, long scoreboard) at 50 % occupancy;
- * this variant trades registers for twice the bytes in flight per thread. Kept separate from
- * k_update so that the measured kernel stays exactly as profiled.
- */
-struct UpdGroup {
-  float4 p0, p1, m0, m1, v0, v1;
-  float g[8];
-};
-
-template <int FMT, int OPT>
-__device__ __forceinline__ void load_group(const UpdateDev& a, size_t i, UpdGroup& G) {
-  G.p0 = ldf4(a.master + i * 8); G.p1 = ldf4(a.master + i * 8 + 4);
-  G.m0 = ldf4(a.m + i * 8); G.m1 = ldf4(a.m + i * 8 + 4);
-  G.v0 = make_float4(0, 0, 0, 0); G.v1 = G.v0;
-  if (OPT == PS_OPT_ADAMW) {
-    G.v0 = ldf4(a.v + i * 8);
-    G.v1 = ldf4(a.v + i * 8 + 4);
-  }
-  gather_grads<FMT>(a, i, G.g);
-}
-
-template <int OPT, bool OUT_F32>
-__device__ __forceinline__ void finish_group(const UpdateDev& a, const ps_opt_params& o, size_t i,
-                                             UpdGroup& G) {
-#pragma unroll
-  for (int j = 0; j < 8; ++j) G.g[j] *= o.grad_scale;
-  step<OPT>(G.p0.x, G.m0.x, G.v0.x, G.g[0], o); step<OPT>(G.p0.y, G.m0.y, G.v0.y, G.g[1], o);
-  step<OPT>(G.p0.z, G.m0.z, G.v0.z, G.g[2], o); step<OPT>(G.p0.w, G.m0.w, G.v0.w, G.g[3], o);
-  step<OPT>(G.p1.x, G.m1.x, G.v1.x, G.g[4], o); step<OPT>(G.p1.y, G.m1.y, G.v1.y, G.g[5], o);
-  step<OPT>(G.p1.z, G.m1.z, G.v1.z, G.g[6], o); step<OPT>(G.p1.w, G.m1.w, G.v1.w, G.g[7], o);
-  stf4(a.master + i * 8, G.p0); stf4(a.master + i * 8 + 4, G.p1);
-  stf4(a.m + i * 8, G.m0); stf4(a.m + i * 8 + 4, G.m1);
-  if (OPT == PS_OPT_ADAMW) {
-    stf4(a.v + i * 8, G.v0);
-    stf4(a.v + i * 8 + 4, G.v1);
-  }
-  if (OUT_F32) {
-#pragma unroll 1
-    for (int k = 0; k < a.body_outs; ++k) {
-      stf4(static_cast<float*>(a.outs[k]) + i * 8, G.p0);
-      stf4(static_cast<float*>(a.outs[k]) + i * 8 + 4, G.p1);
-    }
-  } else {
-    int4 out;
-    out.x = pk(G.p0.x, G.p0.y); out.y = pk(G.p0.z, G.p0.w);
-    out.z = pk(G.p1.x, G.p1.y); out.w = pk(G.p1.z, G.p1.w);
-#pragma unroll 1
-    for (int k = 0; k < a.body_outs; ++k) st16(static_cast<char*>(a.outs[k]) + i * 16, out);
-    if (a.mc_out) multimem_st16(static_cast<char*>(a.mc_out) + i * 16, out);
-  }
-}
-
-template <int FMT, int OPT, bool OUT_F32>
-__global__ void __launch_bounds__(kThreads)
-k_update_x2(const UpdateDev a, const ps_opt_params o) {
-  const size_t n8 = a.n / 8;
-  const size_t stride = static_cast<size_t>(gridDim.x) * kThreads;
-  for (size_t i = static_cast<size_t>(blockIdx.x) * kThreads + threadIdx.x; i < n8; i += 2 * stride) {
-    UpdGroup A, B;
-    const size_t i2 = i + stride;
-    const bool two = i2 < n8;
-    load_group<FMT, OPT>(a, i, A);
-    if (two) load_group<FMT, OPT>(a, i2, B);
-    finish_group<OPT, OUT_F32>(a, o, i, A);
-    if (two) finish_group<OPT, OUT_F32>(a, o, i2, B);
-  }
-  if (blockIdx.x == 0) {  // ragged tail, as in k_update
-    const size_t e = n8 * 8 + threadIdx.x;
-    if (e < a.n) {
-      float p = a.master[e], m = a.m[e], v = OPT == PS_OPT_ADAMW ? a.v[e] : 0.f;
-      const float g = gather_one<FMT>(a, e) * o.grad_scale;
-      step<OPT>(p, m, v, g, o);
-      a.master[e] = p;
-      a.m[e] = m;
-      if (OPT == PS_OPT_ADAMW) a.v[e] = v;
-      for (int k = 0; k < a.num_outs; ++k) {
-        if (OUT_F32) static_cast<float*>(a.outs[k])[e] = p;
-        else static_cast<__nv_bfloat16*>(a.outs[k])[e] = __float2bfloat16_rn(p);
-      }
-    }
-  }
-}
 
 // ---------------------------------------------------------------------------
 // K_update, TMA flavour (PS_UPDATE_TMA=1, experimental until it has run on hardware)
@@ -558,17 +475,28 @@ int GridFor(size_t items, int max_ctas, int per_sm) {
   return want < 1 ? 1 : static_cast<int>(want);
 }
 
+/*!
+ * \brief which flavour runs a shard, decided by measurement on B200 (profiles/r2/r2_kernel_bench_*.txt,
+ *        fraction of the 6571 GB/s copy roofline, 64 M elements, W = 1..4, fan-out 1..5):
+ *          bf16 / f32 gradient slots   LDG 0.82-0.95   TMA-staged 0.93-1.01   -> TMA
+ *          fp8-block gradient slots    LDG 0.82-0.90   TMA-staged 0.66-0.72   -> LDG (byte-wise decode out of
+ *                                                                                shared memory bank-conflicts)
+ *        A third flavour (two groups per thread, "x2") lost at W = 4 (0.72-0.76) and was removed.
+ *        PS_UPDATE_TMA=0 / 1 forces one flavour for every format.
+ */
+template <int FMT>
 bool UseTma() {
-  static const bool on = [] {
+  static const int forced = [] {
     const char* v = getenv("PS_UPDATE_TMA");
-    return v != nullptr && atoi(v) != 0;
+    return v == nullptr ? -1 : (atoi(v) != 0 ? 1 : 0);
   }();
-  return on;
+  if (forced >= 0) return forced == 1;
+  return FMT == PS_GRAD_BF16 || FMT == PS_GRAD_F32;
 }
 
 template <int FMT, int OPT>
 bool LaunchUpdateTmaImpl(const UpdateDev& d, const ps_opt_params& o, bool out_f32, int max_ctas, cudaStream_t st) {
-  if (!UseTma() || out_f32) return false;
+  if (!UseTma<FMT>() || out_f32) return false;
   const size_t tiles = d.n / kTile;
   const int stage = 3 * kTile * 4 + d.num_grads * GradTileBytes<FMT>();
   const int smem = kTmaStagesU * stage;
@@ -581,10 +509,10 @@ bool LaunchUpdateTmaImpl(const UpdateDev& d, const ps_opt_params& o, bool out_f3
   for (int w = 0; w < d.num_grads; ++w) {
     if (reinterpret_cast<uintptr_t>(d.grads[w]) & 15) return false;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static std::atomic<bool> attr_set{false};  // (one per instantiation; launches come from several threads)
+  if (!attr_set.load(std::memory_order_acquire)) {
     cudaFuncSetAttribute(k_update_tma<FMT, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attr_set = true;
+    attr_set.store(true, std::memory_order_release);
   }
   const int num_sms = ps_kernels_internal::NumSMs();
   int grid = static_cast<int>(tiles < static_cast<size_t>(num_sms) ? tiles : num_sms);
@@ -603,23 +531,10 @@ bool LaunchUpdateTma(const UpdateDev& d, const ps_opt_params& o, bool out_f32, i
   }
 }
 
-bool UseX2() {
-  static const bool on = [] {
-    const char* v = getenv("PS_UPDATE_X2");
-    return v != nullptr && atoi(v) != 0;
-  }();
-  return on;
-}
-
 template <int FMT, int OPT>
 void LaunchUpdate(const UpdateDev& d, const ps_opt_params& o, bool out_f32, int grid,
                   cudaStream_t st) {
   if (LaunchUpdateTma<FMT, OPT>(d, o, out_f32, grid, st)) return;
-  if (UseX2()) {
-    if (out_f32) k_update_x2<FMT, OPT, true><<<grid, kThreads, 0, st>>>(d, o);
-    else k_update_x2<FMT, OPT, false><<<grid, kThreads, 0, st>>>(d, o);
-    return;
-  }
   if (out_f32) k_update<FMT, OPT, true><<<grid, kThreads, 0, st>>>(d, o);
   else k_update<FMT, OPT, false><<<grid, kThreads, 0, st>>>(d, o);
 }

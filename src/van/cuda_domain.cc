@@ -142,6 +142,7 @@ class CudaDomain : public MemDomain {
    */
   void* Alloc(size_t bytes) override {
     PS_CUDA_CHECK(cudaSetDevice(dev_));
+    ReclaimRetired(false);
     const uint64_t want = AlignUp(bytes ? bytes : 1, 512);
     {
       std::lock_guard<std::mutex> lk(mu_);
@@ -155,6 +156,17 @@ class CudaDomain : public MemDomain {
     a->size = std::max<uint64_t>(chunk, AlignUp(want, 2u << 20));
     void* base = nullptr;
     cudaError_t e = cudaMalloc(&base, a->size);
+    if (e != cudaSuccess) {
+      // memory may be sitting in retired slots: wait for their users, then look again
+      cudaGetLastError();
+      ReclaimRetired(true);
+      std::lock_guard<std::mutex> lk(mu_);
+      for (auto& old : arenas_) {
+        const uint64_t off = old->alloc.Alloc(want);
+        if (off != UINT64_MAX) return old->base + off;
+      }
+      e = cudaMalloc(&base, a->size);
+    }
     if (e != cudaSuccess && a->size > want) {  // little memory left: fall back to an exact fit
       cudaGetLastError();
       a->size = AlignUp(want, 2u << 20);
@@ -168,19 +180,65 @@ class CudaDomain : public MemDomain {
     arenas_.push_back(std::move(a));
     return arenas_.back()->base + off;
   }
+  /*!
+   * A kernel already enqueued may still read or write the slot, so its bytes must not be re-cut
+   * yet — but stalling the whole device for that (cudaDeviceSynchronize, round 1) also stalls a
+   * training step that happens to re-size one slot. The slot is RETIRED instead: an event marks
+   * "everything enqueued on the data stream so far" and the engine ticket "everything posted so
+   * far"; the bytes return to the arena once both have passed (checked on later Alloc / Free).
+   */
   void Free(void* p) override {
     cudaSetDevice(dev_);
-    // a kernel may still be reading the slot: drain the device before the bytes are re-cut
-    cudaDeviceSynchronize();
-    std::lock_guard<std::mutex> lk(mu_);
-    for (auto& a : arenas_) {
-      char* c = static_cast<char*>(p);
-      if (c >= a->base && c < a->base + a->size) {
-        a->alloc.Free(static_cast<uint64_t>(c - a->base));
-        return;
+    Retired r;
+    r.ptr = static_cast<char*>(p);
+    r.event = AcquireEvent();
+    if (cudaEventRecord(r.event, stream_) != cudaSuccess) {
+      cudaGetLastError();
+      cudaStreamSynchronize(stream_);  // cannot track it: fall back to waiting now
+    }
+    r.engine_ticket = engine_ticket_.load(std::memory_order_acquire);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      retired_.push_back(r);
+    }
+    ReclaimRetired(false);
+  }
+
+  /*! \brief give retired slots whose last possible user has finished back to their arena */
+  void ReclaimRetired(bool wait) {
+    std::vector<Retired> ready;
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      for (auto it = retired_.begin(); it != retired_.end();) {
+        bool done = !engine_ || ps_engine_done(engine_, it->engine_ticket);
+        if (done) {
+          const cudaError_t e = wait ? cudaEventSynchronize(it->event) : cudaEventQuery(it->event);
+          done = e == cudaSuccess;
+          if (!done) cudaGetLastError();
+        } else if (wait) {
+          ps_engine_wait(engine_, it->engine_ticket);
+          done = cudaEventSynchronize(it->event) == cudaSuccess;
+        }
+        if (done) {
+          ready.push_back(*it);
+          it = retired_.erase(it);
+        } else {
+          ++it;
+        }
+      }
+      for (const Retired& r : ready) {
+        free_events_.push_back(r.event);
+        bool ours = false;
+        for (auto& a : arenas_) {
+          if (r.ptr >= a->base && r.ptr < a->base + a->size) {
+            a->alloc.Free(static_cast<uint64_t>(r.ptr - a->base));
+            ours = true;
+            break;
+          }
+        }
+        if (!ours) cudaFree(r.ptr);  // not from an arena (never happens for slots handed out by Alloc)
       }
     }
-    cudaFree(p);  // not ours (never happens for slots handed out by Alloc)
   }
 
   bool Export(const void* p, RegionDesc* out) override {
@@ -619,6 +677,12 @@ class CudaDomain : public MemDomain {
     return e;
   }
 
+  struct Retired {
+    char* ptr = nullptr;
+    cudaEvent_t event = nullptr;
+    unsigned long long engine_ticket = 0;
+  };
+  std::vector<Retired> retired_;  // freed slots whose last possible reader has not finished yet
   struct DevArena {
     char* base = nullptr;
     uint64_t size = 0;

@@ -374,9 +374,18 @@ class OneSidedVan : public TcpVan {
     req.meta.timestamp = GetTimestamp();
     CHECK_GT(TcpVan::SendMsg(req), 0);
     lk.lock();
-    while (!rv_cv_.wait_for(lk, std::chrono::seconds(60), [&] { return push_slots_.count(pk) > 0; })) {
+    // bounded: a receiver that never answers (dead, or out of memory for the slot) must not hang the
+    // sender forever. PS_RENDEZVOUS_TIMEOUT_S (default 300, 0 = wait for ever) — past it the push
+    // fails loudly (dmlc::Error from CHECK), which the application can catch and act upon.
+    static const int limit_s = GetEnv("PS_RENDEZVOUS_TIMEOUT_S", 300);
+    int waited_s = 0;
+    while (!rv_cv_.wait_for(lk, std::chrono::seconds(30), [&] { return push_slots_.count(pk) > 0; })) {
+      waited_s += 30;
       LOG(WARNING) << type_ << " van " << my_node_.id << ": no landing slot from node " << recver
-                   << " for key " << key << " (" << bytes << " B) after 60 s";
+                   << " for key " << key << " (" << bytes << " B) after " << waited_s << " s";
+      CHECK(limit_s <= 0 || waited_s < limit_s)
+          << type_ << " van " << my_node_.id << ": node " << recver << " never granted a landing slot for key "
+          << key << " (" << bytes << " B): giving up after " << waited_s << " s (PS_RENDEZVOUS_TIMEOUT_S)";
     }
     return push_slots_[pk];
   }
