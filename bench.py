@@ -45,7 +45,9 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl-ddp"],
+                    help="nccl-ddp (with --metric llama): SECONDARY baseline, not the reference — the same model "
+                         "trained with NCCL all-reduce of the gradients + torch.optim.AdamW(fused=True) on every rank")
     ap.add_argument("--metric", default="pushpull", choices=["pushpull", "llama"])
     ap.add_argument("--len", type=int, default=4096000, help="bytes per value (reference test.sh preset)")
     ap.add_argument("--keys-per-server", type=int, default=40)
@@ -525,6 +527,89 @@ def run_llama(args, dist: Dist) -> dict:
 
 
 # ----------------------------------------------------------------------------------------
+# secondary baseline: NCCL data parallelism (NOT the reference — it has no trainer)
+# ----------------------------------------------------------------------------------------
+def run_llama_ddp(args, dist: Dist) -> dict:
+    """Same model, same batch, same step structure as run_llama, but the gradients are summed with
+    NCCL all-reduce (bucketed, overlapped by DistributedDataParallel) and every rank runs
+    torch.optim.AdamW(fused=True) on its full bf16 replica. Gives tokens/s an anchor."""
+    import torch
+    import torch.distributed as tdist
+
+    from pslite_b200.models.llama import Llama, LlamaConfig
+    from pslite_b200.utils.timing import ClockSampler
+
+    gpu = Gpu(args, dist.local_rank)
+    dev = gpu.dev
+    if args.model == "llama3-8b":
+        cfg = LlamaConfig.llama3_8b(max_seq_len=args.seq_len)
+    elif args.model == "llama-1b":
+        cfg = LlamaConfig(dim=2048, n_layers=16, n_heads=32, n_kv_heads=8, ffn_dim=8192, max_seq_len=args.seq_len)
+    else:
+        cfg = LlamaConfig.tiny(max_seq_len=args.seq_len)
+    cfg.ckpt_layers = args.ckpt_layers if args.ckpt_layers >= 0 else 0
+    cfg.attn_backend = args.attn_backend
+    B, T, W = args.micro_batch, args.seq_len, dist.world
+    with torch.device(dev):
+        model = Llama(cfg).to(torch.bfloat16)
+    model.init_weights(seed=0)
+    model.train()
+    net = model
+    if W > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+
+        net = DDP(model, device_ids=[dist.local_rank] if gpu.cuda else None, gradient_as_bucket_view=True,
+                  bucket_cap_mb=256)
+    opt = torch.optim.AdamW(model.parameters(), lr=3e-4, betas=(0.9, 0.95), eps=1e-8, weight_decay=0.1,
+                            fused=gpu.cuda)
+    g = torch.Generator().manual_seed(1234 + dist.rank)
+    host_tok = gpu.pinned(torch.randint(0, cfg.vocab_size, (B, T + 1), generator=g))
+    dev_tok = host_tok.to(dev)
+
+    def step(e2e: bool):
+        tok = host_tok.to(dev, non_blocking=True) if e2e else dev_tok
+        loss = net(tok[:, :-1], tok[:, 1:])
+        loss.backward()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        return loss.item() if e2e else loss
+
+    def timed(fn, steps):
+        dist.barrier()
+        gpu.sync()
+        stop = gpu.timer()
+        for _ in range(steps):
+            fn()
+        gpu.sync()
+        ms = stop()
+        dist.barrier()
+        return dist.reduce(ms, "max")
+
+    for _ in range(args.warmup):
+        step(False)
+    sampler = ClockSampler(dist.local_rank).start() if dist.rank == 0 and gpu.cuda else None
+    ms = timed(lambda: step(False), args.steps)
+    clocks = sampler.stop() if sampler else None
+    tokens = B * T * W
+    k = max(2, args.steps // 2)
+    ms2 = timed(lambda: step(True), k)
+    return {
+        "impl": "nccl-ddp", "note": "secondary baseline (NCCL all-reduce + fused AdamW), NOT the reference",
+        "metric": METRIC_NAME["llama"], "value": tokens * args.steps / (ms * 1e-3), "unit": "tokens/s",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16", "data": "synthetic tokens, random-init weights",
+        "config": {"model": args.model, "params": cfg.num_params(), "global_batch": B * W, "seq_len": T,
+                   "parallelism": f"dp{W} NCCL all-reduce, bf16 AdamW states on every rank",
+                   "ckpt_layers": cfg.ckpt_layers},
+        "clocks": clocks, "gpu_launches": 0,
+        "e2e": {"value": tokens * k / (ms2 * 1e-3), "unit": "tokens/s",
+                "h2d_bytes_per_step": int(host_tok.numel() * host_tok.element_size()) * W, "d2h_bytes_per_step": 4 * W},
+        "mfu_vs_sustained_bf16": cfg.flops_per_token(T) * B * T / (ms / args.steps * 1e-3) / 1386e12,
+        "peak_torch_mem_gb": round(torch.cuda.max_memory_allocated() / 2**30, 1) if gpu.cuda else None,
+    }
+
+
+# ----------------------------------------------------------------------------------------
 # reference arm
 # ----------------------------------------------------------------------------------------
 def run_reference(args, dist: Dist) -> dict:
@@ -613,6 +698,9 @@ def main():
         args.gpus = dist.world
     if args.impl == "reference":
         out = run_reference(args, dist)
+    elif args.impl == "nccl-ddp":
+        args.metric = "llama"
+        out = run_llama_ddp(args, dist)
     elif args.metric == "llama":
         out = run_llama(args, dist)
     else:
