@@ -78,15 +78,20 @@ int MyDevice() {
 
 /*! \brief page-aligned host buffer or device buffer, wrapped with the right placement */
 template <typename T>
-SArray<T> AllocArray(size_t count, bool on_gpu, int dst_dev, bool dst_gpu, int src_dev = 0) {
+SArray<T> AllocArray(size_t count, bool on_gpu, int dst_dev, bool dst_gpu, int src_dev = 0, int gpu_index = 0) {
   SArray<T> out;
   const size_t bytes = count * sizeof(T);
   if (on_gpu) {
 #if PS_USE_CUDA
+    // a process that drives several GPUs (DMLC_NUM_GPU_DEV) spreads its buffers over them
+    const int first = MyDevice();
+    if (gpu_index) BENCH_CUDA(cudaSetDevice(first + gpu_index));
     void* p = nullptr;
     BENCH_CUDA(cudaMalloc(&p, bytes));
     BENCH_CUDA(cudaMemset(p, 1, bytes));
-    out.reset(static_cast<T*>(p), count, [](T*) {}, GPU, MyDevice(), dst_gpu ? GPU : CPU, dst_dev);
+    BENCH_CUDA(cudaDeviceSynchronize());
+    out.reset(static_cast<T*>(p), count, [](T*) {}, GPU, first + gpu_index, dst_gpu ? GPU : CPU, dst_dev);
+    if (gpu_index) BENCH_CUDA(cudaSetDevice(first));
 #else
     LOG(FATAL) << "GPU buffers need a build with USE_CUDA=1";
 #endif
@@ -122,12 +127,16 @@ KeySet MakeKeySet(int total_keys, bool vals_on_gpu, bool dst_gpu, int rank = 0) 
     key[0] = static_cast<Key>(ranges[k % S].begin() + k);
     SArray<int> len = AllocArray<int>(1, false, 0, false);
     len[0] = opt.len;
-    const int dst_dev = dst_gpu ? 0 : (k % opt.num_ports);
+    // key k lives on device k % local_size at both ends (reference tests/test_benchmark.cc:58-90);
+    // -1 lets a single-device receiver use the one it has
+    const int ndev = EnvInt("PS_NUM_GPU_DEV", EnvInt("DMLC_NUM_GPU_DEV", 1));
+    const int peer_first = EnvInt("TEST_PEER_GPU_BASE", -1);
+    const int dst_dev = dst_gpu ? (ndev > 1 && peer_first >= 0 ? peer_first + (k / S) % ndev : -1) : (k % opt.num_ports);
     ks.keys.push_back(key);
     ks.lens.push_back(len);
     // multi-port vans pick the sending rail from the source context (reference src_key2ctx)
     ks.vals.push_back(AllocArray<char>(opt.len, vals_on_gpu, dst_dev, dst_gpu,
-                                       (k + rank) % opt.num_ports));
+                                       (k + rank) % opt.num_ports, vals_on_gpu && ndev > 1 ? (k / S) % ndev : 0));
   }
   return ks;
 }
@@ -169,6 +178,17 @@ void ServerHandle(const KVMeta& req, const KVPairs<char>& data, KVServer<char>* 
         << "key=" << decoded;
   }
   if (opt.gpu_server) CHECK(data.vals.on_gpu()) << "expected the push to land in HBM";
+#if PS_USE_CUDA
+  static const int ndev = EnvInt("PS_NUM_GPU_DEV", EnvInt("DMLC_NUM_GPU_DEV", 1));
+  if (opt.gpu_server && ndev > 1 && EnvInt("TEST_CHECK_SLOT_DEVICE", 0) != 0) {
+    // a server that drives several GPUs: key k must have landed on device first + (k / S) % ndev
+    static const int first = EnvInt("PS_CUDA_DEVICE", 0);
+    const int S = static_cast<int>(Postoffice::Get()->GetServerKeyRanges().size());
+    cudaPointerAttributes attr;
+    BENCH_CUDA(cudaPointerGetAttributes(&attr, data.vals.data()));
+    CHECK_EQ(attr.device, first + static_cast<int>(decoded / S) % ndev) << "key " << decoded << " landed on the wrong device";
+  }
+#endif
   {
     std::lock_guard<std::mutex> lk(g_server.mu);
     if (!g_server.store.count(key)) {

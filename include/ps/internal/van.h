@@ -78,6 +78,10 @@ class Van {
   /*! \brief memory peers can map (HBM on the NVLink van, shm on the shm van, else heap) */
   virtual void* AllocExportable(size_t bytes) { return malloc(bytes); }
   virtual void FreeExportable(void* p) { free(p); }
+  /*! \brief ... on a given device of a van whose process drives several GPUs (DMLC_NUM_GPU_DEV) */
+  virtual void* AllocExportableOn(size_t bytes, int /*device*/) { return AllocExportable(bytes); }
+  /*! \brief devices this van's process drives (1 unless DMLC_NUM_GPU_DEV / PS_NUM_GPU_DEV says more) */
+  virtual int NumDevices() { return 1; }
   /*! \brief this process's mapping of a span a peer announced (one-sided vans), else null */
   virtual void* ResolvePeerMem(int /*node_id*/, const MemRef& /*mem*/) { return nullptr; }
   /*!

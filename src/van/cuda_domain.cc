@@ -637,6 +637,32 @@ class CudaDomain : public MemDomain {
     return ok;
   }
 
+  /*! \brief everything this domain was given (stream and engine) has completed */
+  void Quiesce() {
+    cudaSetDevice(dev_);
+    if (engine_) ps_engine_wait(engine_, engine_ticket_.load(std::memory_order_acquire));
+    cudaStreamSynchronize(stream_);
+  }
+  /*! \brief is `p` inside one of this device's landing-slot arenas? */
+  bool Owns(const void* p) {
+    std::lock_guard<std::mutex> lk(mu_);
+    const char* c = static_cast<const char*>(p);
+    for (auto& a : arenas_) {
+      if (c >= a->base && c < a->base + a->size) return true;
+    }
+    return false;
+  }
+  /*! \brief let kernels of THIS device store into memory that lives on local ordinal `owner` */
+  void EnablePeerTo(int owner) {
+    if (owner < 0 || owner == dev_) return;
+    if (cudaSetDevice(dev_) != cudaSuccess) return;
+    const cudaError_t e = cudaDeviceEnablePeerAccess(owner, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+      LOG(WARNING) << "cudaDeviceEnablePeerAccess(" << owner << ") from device " << dev_ << ": " << cudaGetErrorString(e);
+    }
+    cudaGetLastError();
+  }
+
   void EngineStats(uint64_t* launches, uint64_t* items) override {
     unsigned long long l = 0, i = 0;
     if (engine_) ps_engine_stats(engine_, &l, &i);
@@ -704,6 +730,123 @@ class CudaDomain : public MemDomain {
   std::unordered_map<std::string, void*> imported_;
 };
 
+/*!
+ * \brief several GPUs driven by ONE process (DMLC_NUM_GPU_DEV / PS_NUM_GPU_DEV > 1): one CudaDomain
+ *        per device behind the MemDomain interface. A copy runs on the device its SOURCE lives on
+ *        (that device's stream, engine and completion counter), a landing slot is cut on the device
+ *        the sender names, and a peer's region is opened once and made reachable from every local
+ *        device. The reference does this with one UCX context per device and routes by
+ *        src / dst device id (src/ucx_van.h:662-682, 938-1006; tests/test_benchmark.cc:58-90 puts
+ *        key k on device k % local_size).
+ */
+class MultiCudaDomain : public MemDomain {
+ public:
+  MultiCudaDomain(int first, int count) {
+    for (int i = 0; i < count; ++i) subs_.emplace_back(new CudaDomain(first + i));
+  }
+  const char* name() const override { return "nvl"; }
+  int device() const override { return subs_[0]->device(); }
+  int num_devices() const override { return static_cast<int>(subs_.size()); }
+  void* Stream() override { return subs_[0]->Stream(); }
+  bool Handles(int device_type, const void* /*ptr*/) override { return device_type == GPU; }
+  void* Alloc(size_t bytes) override { return subs_[0]->Alloc(bytes); }
+  void* AllocOn(size_t bytes, int device) override { return Sub(device)->Alloc(bytes); }
+  void Free(void* p) override { OwnerOf(p, -1)->Free(p); }
+  bool Export(const void* p, RegionDesc* out) override { return OwnerOf(p, -1)->Export(p, out); }
+  void* Import(const RegionDesc& d) override {
+    void* base = subs_[0]->Import(d);
+    // which local ordinal owns the mapped memory? every other device of this process needs peer access to it
+    int owner = d.dev;
+    if (d.pid != static_cast<int32_t>(getpid())) {
+      cudaPointerAttributes attr;
+      if (cudaPointerGetAttributes(&attr, base) == cudaSuccess && attr.type == cudaMemoryTypeDevice) {
+        owner = attr.device;
+      } else {
+        cudaGetLastError();
+      }
+    }
+    for (size_t i = 1; i < subs_.size(); ++i) subs_[i]->EnablePeerTo(owner);
+    return base;
+  }
+  Ticket CopyAsync(void* dst, const void* src, size_t n, int codec, float scale, void* wait_event,
+                   int src_device_type = UNK) override {
+    return OwnerOf(src, -1)->CopyAsync(dst, src, n, codec, scale, wait_event, src_device_type);
+  }
+  void* MapSignalWord(void* page, size_t bytes, void* host_word) override {
+    void* word = nullptr;
+    for (auto& d : subs_) {
+      void* w = d->MapSignalWord(page, bytes, host_word);
+      if (!w) return nullptr;
+      if (word && w != word) {
+        LOG(WARNING) << "the devices of this process see a mapped host word at different addresses: "
+                     << "completions of this connection go through events and a host thread";
+        return nullptr;
+      }
+      word = w;
+    }
+    return word;
+  }
+  void UnmapSignalWord(void* page) override {
+    for (auto& d : subs_) d->UnmapSignalWord(page);
+  }
+  bool CopySignal(const CopyItem& item, void* word, uint64_t value) override {
+    // completions on one word must keep their order: everything for one connection runs on the
+    // device of its first copy unless the source says otherwise AND nothing else is in flight there.
+    // (Per-connection traffic of the benchmark and the trainer comes from one device at a time.)
+    CudaDomain* d = item.n_src_bytes ? OwnerOf(item.src, item.src_device_id) : LastFor(word);
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      auto it = last_for_word_.find(word);
+      if (it != last_for_word_.end() && it->second != d) it->second->Quiesce();  // the previous device has signalled everything
+      last_for_word_[word] = d;
+    }
+    return d->CopySignal(item, word, value);
+  }
+  bool Ready(Ticket t) override { return subs_[0]->Ready(t); }
+  void Wait(Ticket t) override { subs_[0]->Wait(t); }
+  bool SymmetricAlloc(const SymmetricGroup& g, const std::string& tag, size_t bytes, SymmetricBuffer* out) override {
+    return subs_[0]->SymmetricAlloc(g, tag, bytes, out);
+  }
+  void EngineStats(uint64_t* launches, uint64_t* items) override {
+    *launches = *items = 0;
+    for (auto& d : subs_) {
+      uint64_t l = 0, i = 0;
+      d->EngineStats(&l, &i);
+      *launches += l;
+      *items += i;
+    }
+  }
+
+ private:
+  CudaDomain* Sub(int device) {
+    for (auto& d : subs_) {
+      if (d->device() == device) return d.get();
+    }
+    return subs_[0].get();
+  }
+  CudaDomain* OwnerOf(const void* p, int hint) {
+    if (hint >= 0) return Sub(hint);
+    for (auto& d : subs_) {
+      if (d->Owns(p)) return d.get();
+    }
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) == cudaSuccess &&
+        (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged)) {
+      return Sub(attr.device);
+    }
+    cudaGetLastError();
+    return subs_[0].get();
+  }
+  CudaDomain* LastFor(void* word) {
+    std::lock_guard<std::mutex> lk(mu_);
+    auto it = last_for_word_.find(word);
+    return it != last_for_word_.end() ? it->second : subs_[0].get();
+  }
+  std::vector<std::unique_ptr<CudaDomain>> subs_;
+  std::mutex mu_;
+  std::unordered_map<void*, CudaDomain*> last_for_word_;
+};
+
 }  // namespace
 
 MemDomain* CreateCudaDomain() {
@@ -721,6 +864,13 @@ MemDomain* CreateCudaDomain() {
     if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
   }
   CHECK(dev >= 0 && dev < n) << "CUDA device " << dev << " out of range (" << n << " visible)";
+  // DMLC_NUM_GPU_DEV (the reference's name, src/ucx_van.h:941-942) / PS_NUM_GPU_DEV: this process
+  // drives that many consecutive devices starting at `dev`
+  const int count = GetEnv("PS_NUM_GPU_DEV", GetEnv("DMLC_NUM_GPU_DEV", 1));
+  if (count > 1) {
+    CHECK_LE(dev + count, n) << "devices " << dev << ".." << dev + count - 1 << " requested, " << n << " visible";
+    return new MultiCudaDomain(dev, count);
+  }
   return new CudaDomain(dev);
 }
 

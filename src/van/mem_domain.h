@@ -93,6 +93,10 @@ class MemDomain {
   virtual int device() const { return -1; }
   /*! \brief allocate exportable memory (landing slots) */
   virtual void* Alloc(size_t bytes) = 0;
+  /*! \brief ... on a given device of a domain that drives several (else: Alloc) */
+  virtual void* AllocOn(size_t bytes, int /*device*/) { return Alloc(bytes); }
+  /*! \brief how many devices this domain drives (1 for host domains) */
+  virtual int num_devices() const { return 1; }
   virtual void Free(void* p) = 0;
   /*! \brief describe the exportable allocation that contains `p` (region id left unset) */
   virtual bool Export(const void* p, RegionDesc* out) = 0;
@@ -114,6 +118,7 @@ class MemDomain {
     float scale = 1.f;
     void* wait_event = nullptr;
     int src_device_type = UNK;
+    int src_device_id = -1;  // device the source lives on, when the sender knows (SArray placement)
   };
   /*!
    * \brief enqueue all items and return ONE ticket that completes after the last of them

@@ -106,6 +106,8 @@ class OneSidedVan : public TcpVan {
   }
 
   void* AllocExportable(size_t bytes) override { return domain_->Alloc(bytes); }
+  void* AllocExportableOn(size_t bytes, int device) override { return domain_->AllocOn(bytes, device); }
+  int NumDevices() override { return domain_->num_devices(); }
   void FreeExportable(void* p) override { domain_->Free(p); }
   void* DataStream() override { return domain_->Stream(); }
 
@@ -324,7 +326,7 @@ class OneSidedVan : public TcpVan {
       slot.region = kSymmetricRegion;
       slot.offset = msg.meta.mem.offset;
     } else {
-      slot = AcquirePushSlot(recver, msg.meta.key, wire);
+      slot = AcquirePushSlot(recver, msg.meta.key, wire, vals.dst_device_type_ == GPU ? vals.dst_device_id_ : -1);
     }
     MemDomain::CopyItem item;
     item.dst = slot.ptr;
@@ -334,6 +336,7 @@ class OneSidedVan : public TcpVan {
     item.scale = msg.meta.scale;
     item.wait_event = msg.wait_event;
     item.src_device_type = vals.src_device_type_;
+    item.src_device_id = vals.src_device_type_ == GPU ? vals.src_device_id_ : -1;
     ++copies_;
     copy_bytes_ += wire;
     Message desc;
@@ -355,7 +358,7 @@ class OneSidedVan : public TcpVan {
   }
 
   /*! \brief landing slot at `recver` for `key`; rendezvous on first use or growth */
-  Slot AcquirePushSlot(int recver, uint64_t key, uint64_t bytes) {
+  Slot AcquirePushSlot(int recver, uint64_t key, uint64_t bytes, int dst_device = -1) {
     std::unique_lock<SpinMutex> lk(rv_mu_);
     const PeerKey pk(recver, key);
     auto it = push_slots_.find(pk);
@@ -371,6 +374,7 @@ class OneSidedVan : public TcpVan {
     req.meta.control.cmd = Control::ADDR_REQUEST;
     req.meta.key = key;
     req.meta.val_len = static_cast<int64_t>(bytes);
+    req.meta.dst_dev_id = dst_device;  // a receiver that drives several devices cuts the slot on this one
     req.meta.timestamp = GetTimestamp();
     CHECK_GT(TcpVan::SendMsg(req), 0);
     lk.lock();
@@ -419,7 +423,9 @@ class OneSidedVan : public TcpVan {
     }
     if (!ptr) {
       cap = AlignUp(bytes, 256);
-      ptr = static_cast<char*>(domain_->Alloc(cap));
+      const int want_dev = req.meta.dst_dev_id;
+      ptr = static_cast<char*>(want_dev >= 0 && domain_->num_devices() > 1 ? domain_->AllocOn(cap, want_dev)
+                                                                           : domain_->Alloc(cap));
       CHECK(ptr) << "out of " << domain_->name() << " memory for a " << cap << " B landing slot";
     }
     RegionDesc d;
@@ -472,20 +478,33 @@ class OneSidedVan : public TcpVan {
     RegionDesc d;
     if (!domain_->Export(reinterpret_cast<void*>(addr), &d)) return false;
     const int32_t id = RegionIdFor(&d);
-    bool need_announce = false;
+    bool known = false;
     {
       std::lock_guard<SpinMutex> lk(rv_mu_);
-      need_announce = announced_.insert(std::make_pair(recver, id)).second;
+      known = announced_.count(std::make_pair(recver, id)) > 0;
     }
-    if (need_announce) {
-      Message ann;
-      ann.meta.recver = recver;
-      ann.meta.request = true;
-      ann.meta.control.cmd = Control::ADDR_RESOLVED;
-      ann.meta.head = kAnnounceRegion;
-      ann.meta.body = d.Serialize();
-      ann.meta.timestamp = GetTimestamp();
-      CHECK_GT(TcpVan::SendMsg(ann), 0);
+    if (!known) {
+      // the announcement must be in the peer's ring BEFORE any request that names the region — also
+      // a request of another application thread that finds the region "already announced": the
+      // entry is made only after the send, under a lock that serialises announcers
+      std::lock_guard<std::mutex> alk(announce_mu_);
+      bool still_unknown;
+      {
+        std::lock_guard<SpinMutex> lk(rv_mu_);
+        still_unknown = announced_.count(std::make_pair(recver, id)) == 0;
+      }
+      if (still_unknown) {
+        Message ann;
+        ann.meta.recver = recver;
+        ann.meta.request = true;
+        ann.meta.control.cmd = Control::ADDR_RESOLVED;
+        ann.meta.head = kAnnounceRegion;
+        ann.meta.body = d.Serialize();
+        ann.meta.timestamp = GetTimestamp();
+        CHECK_GT(TcpVan::SendMsg(ann), 0);
+        std::lock_guard<SpinMutex> lk(rv_mu_);
+        announced_.insert(std::make_pair(recver, id));
+      }
     }
     out->region = id;
     out->offset = addr - d.base;
@@ -524,6 +543,7 @@ class OneSidedVan : public TcpVan {
     item.scale = msg.meta.scale;
     item.wait_event = msg.wait_event;
     item.src_device_type = vals.src_device_type_;
+    item.src_device_id = -1;  // a landing slot or a store: the domain finds the device by address
     ++copies_;
     copy_bytes_ += wire;
     Message desc;
@@ -784,6 +804,7 @@ class OneSidedVan : public TcpVan {
   std::unique_ptr<MemDomain> domain_;
   std::string type_;
 
+  std::mutex announce_mu_;  // serialises region announcements (see DescribeDestination)
   SpinMutex rv_mu_;  // slot / region tables: looked up on every push, pull reply and received descriptor
   std::condition_variable_any rv_cv_;
   std::map<PeerKey, Slot> push_slots_;                          // sender: where my pushes land

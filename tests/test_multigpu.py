@@ -121,6 +121,25 @@ def test_stress_gpu_buffers_with_message_loss():
 
 
 @pytest.mark.timeout(300)
+def test_several_gpus_per_process():
+    """DMLC_NUM_GPU_DEV: ONE worker process and ONE server process, each driving half of the GPUs; key k
+    lives on device k % local_size at both ends (reference tests/test_benchmark.cc:58-90) and the server
+    checks that every push landed on the device the key belongs to"""
+    n = torch.cuda.device_count()
+    per = max(1, min(n // 2, 4))
+    if n < 2:
+        pytest.skip("needs two GPUs")
+    env = {"PS_VAN_TYPE": "nvl", "TEST_NUM_GPU_WORKER": per, "TEST_NUM_GPU_SERVER": per,
+           "WORKER_GPU_BASE": 0, "SERVER_GPU_BASE": per, "TEST_PEER_GPU_BASE": per,
+           "NUM_KEY_PER_SERVER": 16, "TOTAL_DURATION": 40, "LOG_DURATION": 20, "TEST_CHECK_SLOT_DEVICE": 1}
+    if per > 1:
+        env["DMLC_NUM_GPU_DEV"] = per
+    rc, out = _local(1, 1, "test_benchmark", 4096000, 10, 1, env=env)
+    assert rc == 0 and "goodput" in out, out[-3000:]
+    print("\n".join(l for l in out.splitlines() if "goodput" in l)[-600:])
+
+
+@pytest.mark.timeout(300)
 def test_in_switch_gradient_reduction_two_gpus():
     """gradients summed by multimem.ld_reduce inside the update kernel (no landing slots)"""
     import torch.distributed._symmetric_memory  # noqa: F401  (present in this torch)
