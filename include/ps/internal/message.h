@@ -20,6 +20,7 @@
 #include <sstream>
 #include <string>
 #include <vector>
+#include "ps/internal/inline_vec.h"
 #include "ps/sarray.h"
 
 namespace ps {
@@ -218,7 +219,7 @@ struct Meta {
   bool push;
   bool simple_app;
   std::string body;
-  std::vector<DataType> data_type;
+  InlineVec<DataType, 4> data_type;
   DeviceType src_dev_type = UNK;
   int src_dev_id = -1;
   DeviceType dst_dev_type = UNK;
@@ -310,7 +311,7 @@ static const int32_t kSymmetricRegion = 0x40000000;
 /*! \brief meta + zero-copy payload segments */
 struct Message {
   Meta meta;
-  std::vector<SArray<char>> data;
+  InlineVec<SArray<char>, 4> data;
   /*! \brief local-only: event gating the one-sided copy of data[1] */
   void* wait_event = nullptr;
   /*! \brief local-only: staging address of a symmetric push (see SendOpts::stage) */

@@ -1054,13 +1054,15 @@ class TcpVan : public Van {
     CHECK_LE(hdr.num_segments, kMaxSegments);
     uint64_t seg_len[kMaxSegments];
     if (hdr.num_segments) CHECK(take(seg_len, sizeof(uint64_t) * hdr.num_segments));
-    std::vector<char> meta_buf(hdr.meta_len);
+    thread_local std::vector<char> meta_buf;  // reused: no allocation per frame
+    meta_buf.resize(hdr.meta_len);
     CHECK(take(meta_buf.data(), meta_buf.size()));
     CHECK(UnpackMeta(meta_buf.data(), meta_buf.size(), &msg->meta)) << "corrupt meta";
     msg->meta.sender = hdr.sender;
     msg->meta.recver = my_node_.id;
     size_t total = sizeof(hdr) + meta_buf.size();
     msg->data.clear();
+    msg->data.reserve(hdr.num_segments);
     for (uint32_t i = 0; i < hdr.num_segments; ++i) {
       SArray<char> seg = SegmentDestination(msg->meta, i, seg_len[i]);
       if (seg_len[i]) CHECK(take(seg.data(), seg_len[i]));
