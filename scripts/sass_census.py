@@ -1,7 +1,8 @@
 #!/usr/bin/env python3
-"""Regenerate profiles/ptxas_and_sass_census.md: per-kernel registers / spills / smem from
-`nvcc -Xptxas -v` and a census of the interesting SASS mnemonics from `cuobjdump -sass`.
-Needs only the CUDA toolkit (no GPU)."""
+"""Regenerate profiles/ptxas_and_sass_census.md (per-kernel registers / spills / smem from
+`nvcc -Xptxas -v`, census of the interesting SASS mnemonics from `cuobjdump -sass`) AND the full
+listings docs/sass/<file>.sm_100a.sass, from one compile of every kernel source with the
+Makefile's flags. Needs only the CUDA toolkit (no GPU)."""
 import collections
 import os
 import re
@@ -11,15 +12,15 @@ import tempfile
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SOURCES = ["src/kernels/copy_kernels.cu", "src/kernels/update_kernels.cu", "src/kernels/model_kernels.cu", "src/kernels/engine_kernels.cu"]
-INTERESTING = re.compile(r"^(F2FP|LDG|STG|LDGMC|REDG|MUFU\.(RCP|SQRT|EX2)|SYNCS|UBLKCP|UTMA|UTC)")
+INTERESTING = re.compile(r"^(F2FP|LDG|STG|ST\.E|LD\.E|LDGMC|REDG|ATOMG|MEMBAR|MUFU\.(RCP|SQRT|EX2)|SYNCS|UBLKCP|UTMA|UTC)")
 HEADER = (
     "# ptxas -v summary and SASS mnemonic census of every sm_100a kernel in src/kernels\n"
     "Generated on the build host (no GPU needed) by `scripts/sass_census.py` with "
     "`nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -Xptxas -v` and `cuobjdump -sass` (CUDA 12.9). "
     "No kernel spills; `UBLKCP.*`/`SYNCS.*` are the TMA bulk copy + mbarrier pipeline, `LDGMC.E.HPADD` is "
-    "`multimem.ld_reduce`, `STG.E.*` with the multicast address carries `multimem.st`. `k_copy_multi` (launch "
-    "coalescing), `k_update_x2` (two groups in flight) and `k_update_tma` (TMA-staged tiles) are opt-in variants "
-    "that have not run on hardware yet.\n\n"
+    "`multimem.ld_reduce`, `STG.E.*.STRONG.SYS` to a multicast address carries `multimem.st`, "
+    "`ST.E.*.STRONG.SYS` / `MEMBAR.*.SYS` are the in-kernel completion signals (st.release.sys). The full "
+    "listings are in `docs/sass/`. Every flavour listed here has run on B200 (profiles/r2/).\n\n"
 )
 
 
@@ -58,6 +59,9 @@ def main():
                     s = re.search(r"(\d+) bytes smem", line)
                     cur["smem"] = s.group(1) if s else "0"
             sass = subprocess.run(["cuobjdump", "-sass", obj], capture_output=True, text=True).stdout
+            listing = os.path.join(ROOT, "docs", "sass", os.path.basename(src).replace(".cu", ".sm_100a.sass"))
+            with open(listing, "w") as lf:
+                lf.write(sass)
         census = collections.Counter()
         for line in sass.splitlines():
             m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
