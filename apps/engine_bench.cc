@@ -194,7 +194,9 @@ int main(int argc, char** argv) {
           for (int i = 0; i < burst; ++i) {
             const size_t off = static_cast<size_t>(i % kSlots) * kMaxMsg;
             ps_engine_post(eng, dst + off, src + off, sz, flag_dev, static_cast<unsigned long long>(i + 1), nullptr);
-            if (both) ps_engine_post(eng1, dst0 + off, src1 + off, sz, flag1_dev, static_cast<unsigned long long>(i + 1), nullptr);
+            if (both) {
+              ps_engine_post(eng1, dst0 + off, src1 + off, sz, flag1_dev, static_cast<unsigned long long>(i + 1), nullptr);
+            }
           }
           if (!WaitFlag(flag, burst, 20) || (both && !WaitFlag(flag1, burst, 20))) return 4;
           const double t1 = NowUs();

@@ -186,7 +186,8 @@ void ServerHandle(const KVMeta& req, const KVPairs<char>& data, KVServer<char>* 
     const int S = static_cast<int>(Postoffice::Get()->GetServerKeyRanges().size());
     cudaPointerAttributes attr;
     BENCH_CUDA(cudaPointerGetAttributes(&attr, data.vals.data()));
-    CHECK_EQ(attr.device, first + static_cast<int>(decoded / S) % ndev) << "key " << decoded << " landed on the wrong device";
+    CHECK_EQ(attr.device, first + static_cast<int>(decoded / S) % ndev)
+        << "key " << decoded << " landed on the wrong device";
   }
 #endif
   {

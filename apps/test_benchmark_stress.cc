@@ -146,12 +146,14 @@ int main(int argc, char* argv[]) {
       }
       // fill a device buffer with this minibatch's pattern / checksum all of it
       auto gpu_fill = [&](Buf& b, uint32_t seed) {
-        CHECK_EQ(ps_launch_fill_u32(b.val.data(), static_cast<size_t>(len) / 4, seed, reinterpret_cast<ps_stream_t>(stream)), 0);
+        const ps_stream_t st = reinterpret_cast<ps_stream_t>(stream);
+        CHECK_EQ(ps_launch_fill_u32(b.val.data(), static_cast<size_t>(len) / 4, seed, st), 0);
         CHECK(cudaStreamSynchronize(stream) == cudaSuccess);
       };
       auto gpu_sum = [&](const Buf& b) {
         unsigned long long h = 0;
-        CHECK_EQ(ps_launch_checksum_u32(b.val.data(), static_cast<size_t>(len) / 4, sum_dev, reinterpret_cast<ps_stream_t>(stream)), 0);
+        const ps_stream_t st = reinterpret_cast<ps_stream_t>(stream);
+        CHECK_EQ(ps_launch_checksum_u32(b.val.data(), static_cast<size_t>(len) / 4, sum_dev, st), 0);
         CHECK(cudaMemcpyAsync(&h, sum_dev, 8, cudaMemcpyDeviceToHost, stream) == cudaSuccess);
         CHECK(cudaStreamSynchronize(stream) == cudaSuccess);
         return h;
@@ -262,7 +264,8 @@ int main(int argc, char* argv[]) {
           for (int d = 0; d < nodes; ++d) {
             if (gpu_sum(dense[d]) != want_dense[static_cast<size_t>(d)]) {
               ++failures;
-              LOG(ERROR) << "session " << session << " minibatch " << mb << ": dense_reduce with node " << d << " is corrupt";
+              LOG(ERROR) << "session " << session << " minibatch " << mb << ": dense_reduce with node " << d
+                         << " is corrupt";
             }
           }
         }

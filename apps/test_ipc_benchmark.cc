@@ -211,7 +211,8 @@ int main(int argc, char* argv[]) {
   }
   LL << "[joint " << Postoffice::GetWorker()->my_rank() << "]\tApplication goodput: "
      << 8.0 * len * total * rounds / ns << " Gbps.\tAvg latency = " << ns / rounds / total / 1000.0
-     << " us per key (" << wvan->GetType() << " van" << (nvls ? (mc_pull ? ", NVLS multicast pull" : ", symmetric buffer, unicast pull") : "")
+     << " us per key (" << wvan->GetType() << " van"
+     << (nvls ? (mc_pull ? ", NVLS multicast pull" : ", symmetric buffer, unicast pull") : "")
      << (mixed ? ", mixed mode" : "") << ", server multicast fan-outs " << mc_fanouts.load() << ")"
      << (verify ? (ok ? " VERIFIED" : " VERIFY FAILED") : "");
   Finalize(0, role, true);

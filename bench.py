@@ -362,12 +362,25 @@ def run_pushpull(args, dist: Dist) -> dict:
         if ctx.is_worker:
             del svals
 
+    # what bounds this configuration, from this pod's measured peaks (profiles/r2/README.md): per GPU and key
+    # pair, joint topology, (N-1)/N of the pushes and of the pull replies cross NVLink (672-703 GB/s in one
+    # direction); at N = 1 both copies stay in HBM (read + write = 4 bytes of traffic per payload byte)
+    if topo == "joint":
+        n = max(1, dist.world)
+        bound_per_gpu = 6571.0 / 4.0 if n == 1 else min(6571.0 / 4.0, 675.0 / (2.0 * (n - 1) / n))
+        bound_what = "HBM copy peak / 4" if n == 1 else "NVLink egress: 675 GB/s / (2 (N-1)/N)"
+    else:
+        n = max(1, dist.world // 2)
+        bound_per_gpu = 675.0  # every push leaves a worker GPU, every pull reply leaves a server GPU
+        bound_what = "NVLink one direction (peer-copy kernel 672-703 GB/s) per worker"
+    roofline = {"bound_GBps": round(bound_per_gpu * n, 1), "bound": bound_what,
+                "fraction_of_bound": round(value / (bound_per_gpu * n), 3)}
     stats = {}
     for role in (["worker"] if ctx.is_worker else []) + (["server"] if ctx.is_server else []):
         stats[role] = {k: int(v) for k, v in C.van_stats(role).items()}
     ctx.shutdown()
     return {
-        "sweep": sweep, "van_stats_rank0": stats,
+        "sweep": sweep, "van_stats_rank0": stats, "roofline": roofline,
         "fused_pushpull": fused,
         "metric": METRIC_NAME["pushpull"], "value": value, "unit": "GB/s",
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -7,6 +7,7 @@
 #include "ps/internal/parallel_sort.h"
 #include "ps/internal/spin_mutex.h"
 #include "ps/internal/parallel_kv_match.h"
+#include "ps/internal/message.h"
 #include "test_util.h"
 #include "van/mem_domain.h"
 #include "van/shm_pipe.h"
@@ -482,6 +483,90 @@ TEST(parallel_sort_and_match) {
   size_t matched = ParallelOrderedMatch(src_k, src_v, dst_k, &dst_v, 1, PLUS, 2);
   CHECK_EQ(matched, (size_t)2);
   CHECK_EQ(dst_v[0], 13.f); CHECK_EQ(dst_v[1], 10.f); CHECK_EQ(dst_v[2], 17.f);
+}
+
+TEST(inline_vec_inline_and_spill) {
+  // the first N elements live inside the object, more spill into a vector; copies are deep
+  InlineVec<SArray<char>, 4> v;
+  CHECK(v.empty());
+  std::vector<SArray<char>> keep;
+  for (int i = 0; i < 7; ++i) {
+    SArray<char> a(static_cast<size_t>(i + 1), static_cast<char>('a' + i));
+    keep.push_back(a);
+    v.push_back(a);
+    CHECK_EQ(v.size(), static_cast<size_t>(i + 1));
+    CHECK_EQ(v.back().size(), static_cast<size_t>(i + 1));
+  }
+  size_t n = 0;
+  for (const SArray<char>& a : v) {
+    CHECK_EQ(a.size(), n + 1);
+    CHECK_EQ(a[0], static_cast<char>('a' + n));
+    ++n;
+  }
+  CHECK_EQ(n, (size_t)7);
+  InlineVec<SArray<char>, 4> copy = v;
+  v.resize(2);
+  CHECK_EQ(v.size(), (size_t)2);
+  CHECK_EQ(copy.size(), (size_t)7);
+  CHECK_EQ(copy[6].size(), (size_t)7);
+  v.clear();
+  CHECK(v.empty());
+  v.push_back(keep[3]);
+  CHECK_EQ(v[0].data(), keep[3].data());  // a view, not a copy of the bytes
+  InlineVec<DataType, 4> t = {CHAR, INT32};
+  InlineVec<DataType, 4> u = {CHAR, INT32};
+  CHECK(t == u);
+  u.push_back(FLOAT);
+  CHECK(t != u);
+  // a Message with more segments than the inline capacity still round-trips
+  Message m;
+  for (int i = 0; i < 6; ++i) m.AddData(SArray<char>(static_cast<size_t>(8 + i), 'x'));
+  CHECK_EQ(m.data.size(), (size_t)6);
+  CHECK_EQ(m.meta.data_type.size(), (size_t)6);
+  CHECK_EQ(m.data[5].size(), (size_t)13);
+}
+
+TEST(fd_exchange_publish_fetch_and_barrier) {
+  // descriptors and small values between processes: the child publishes a pipe's write end under a
+  // key, the parent fetches it (blocking until it exists) and writes through it
+  const int job = 40000 + static_cast<int>(getpid() % 20000);
+  int sync_pipe[2];
+  CHECK_EQ(pipe(sync_pipe), 0);
+  pid_t child = fork();
+  if (child == 0) {
+    int data_pipe[2];
+    if (pipe(data_pipe) != 0) _exit(2);
+    FdExchange* fx = FdExchange::Get(job);
+    if (!fx) _exit(3);
+    usleep(50 * 1000);  // the parent is already waiting for the key by now
+    fx->Publish("tag/mem", data_pipe[1], 4242);
+    char got[6] = {0};
+    if (read(data_pipe[0], got, 5) != 5 || strcmp(got, "hello") != 0) _exit(4);
+    // the "everybody is done" token: fetch the parent's, which it publishes after writing
+    uint64_t v = 0;
+    const std::string parent = FdExchange::EndpointName(job, static_cast<int>(getppid()));
+    if (!FdExchange::Fetch(parent, "tag/done", nullptr, &v, 20) || v != 1) _exit(5);
+    _exit(0);
+  }
+  FdExchange* fx = FdExchange::Get(job);
+  CHECK(fx != nullptr);
+  int fd = -1;
+  uint64_t value = 0;
+  CHECK(FdExchange::Fetch(FdExchange::EndpointName(job, static_cast<int>(child)), "tag/mem", &fd, &value, 20));
+  CHECK_EQ(value, (uint64_t)4242);
+  CHECK_GE(fd, 0);
+  CHECK_EQ(write(fd, "hello", 5), (ssize_t)5);
+  close(fd);
+  fx->Publish("tag/done", -1, 1);
+  int status = 0;
+  waitpid(child, &status, 0);
+  CHECK(WIFEXITED(status));
+  CHECK_EQ(WEXITSTATUS(status), 0);
+  // a key nobody publishes times out instead of hanging
+  CHECK(!FdExchange::Fetch(FdExchange::EndpointName(job, static_cast<int>(getpid())), "tag/never", nullptr, &value, 1));
+  fx->Retract("tag/");
+  close(sync_pipe[0]);
+  close(sync_pipe[1]);
 }
 
 TEST(logging_check_throws) {

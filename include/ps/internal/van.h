@@ -75,6 +75,13 @@ class Van {
   virtual void RegisterRecvBuffer(Message& /*msg*/) {}
   /*! \brief make [addr, addr+length) reachable by peers (export / map) ahead of use */
   virtual void PinMemory(void* /*addr*/, size_t /*length*/, bool /*gpu*/, int /*dev_index*/ = 0) {}
+  /*!
+   * \brief forget everything cached about the exported allocation that contains `addr` — call it
+   *        BEFORE freeing memory that was pinned or used as a one-sided destination, so that a later
+   *        allocation at the same address is exported afresh (new handle, new region id) instead of
+   *        being mistaken for the old one.
+   */
+  virtual void UnpinMemory(void* /*addr*/) {}
   /*! \brief memory peers can map (HBM on the NVLink van, shm on the shm van, else heap) */
   virtual void* AllocExportable(size_t bytes) { return malloc(bytes); }
   virtual void FreeExportable(void* p) { free(p); }

@@ -553,14 +553,16 @@ ps_engine* EngineCreate(int device, int num_ctas, int idle_us) {
     if (kb >= 4 && kb <= 16384) e->chunk = static_cast<unsigned long long>(kb) * 1024ull;
   }
   bool ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
-  ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&e->ctl), sizeof(HostCtl), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess;
-  ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&e->ring), sizeof(Item) * kHostRing, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess;
+  const unsigned host_flags = cudaHostAllocMapped | cudaHostAllocPortable;
+  ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&e->ctl), sizeof(HostCtl), host_flags) == cudaSuccess;
+  ok = ok && cudaHostAlloc(reinterpret_cast<void**>(&e->ring), sizeof(Item) * kHostRing, host_flags) == cudaSuccess;
   ok = ok && cudaMalloc(reinterpret_cast<void**>(&e->state), sizeof(DevState)) == cudaSuccess;
   if (ok) {
     memset(const_cast<HostCtl*>(e->ctl), 0, sizeof(HostCtl));
     memset(e->ring, 0, sizeof(Item) * kHostRing);
     ok = cudaMemset(e->state, 0, sizeof(DevState)) == cudaSuccess && cudaDeviceSynchronize() == cudaSuccess;
-    ok = ok && cudaHostGetDevicePointer(reinterpret_cast<void**>(&e->ctl_dev), const_cast<HostCtl*>(e->ctl), 0) == cudaSuccess;
+    ok = ok && cudaHostGetDevicePointer(reinterpret_cast<void**>(&e->ctl_dev), const_cast<HostCtl*>(e->ctl), 0) ==
+                   cudaSuccess;
     ok = ok && cudaHostGetDevicePointer(reinterpret_cast<void**>(&e->ring_dev), e->ring, 0) == cudaSuccess;
   }
   if (!ok) {

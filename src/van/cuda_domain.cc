@@ -49,11 +49,13 @@ struct VmmApi {
   CUresult (*MemMap)(CUdeviceptr, size_t, size_t, CUmemGenericAllocationHandle, unsigned long long) = nullptr;
   CUresult (*MemUnmap)(CUdeviceptr, size_t) = nullptr;
   CUresult (*MemSetAccess)(CUdeviceptr, size_t, const CUmemAccessDesc*, size_t) = nullptr;
-  CUresult (*MemExportToShareableHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType, unsigned long long) = nullptr;
+  CUresult (*MemExportToShareableHandle)(void*, CUmemGenericAllocationHandle, CUmemAllocationHandleType,
+                                         unsigned long long) = nullptr;
   CUresult (*MemImportFromShareableHandle)(CUmemGenericAllocationHandle*, void*, CUmemAllocationHandleType) = nullptr;
   CUresult (*MulticastCreate)(CUmemGenericAllocationHandle*, const CUmulticastObjectProp*) = nullptr;
   CUresult (*MulticastAddDevice)(CUmemGenericAllocationHandle, CUdevice) = nullptr;
-  CUresult (*MulticastBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t, unsigned long long) = nullptr;
+  CUresult (*MulticastBindMem)(CUmemGenericAllocationHandle, size_t, CUmemGenericAllocationHandle, size_t, size_t,
+                               unsigned long long) = nullptr;
   CUresult (*MulticastGetGranularity)(size_t*, const CUmulticastObjectProp*, CUmulticastGranularity_flags) = nullptr;
   bool vmm = false, multicast = false;
 
@@ -299,6 +301,12 @@ class CudaDomain : public MemDomain {
     out->base = static_cast<uint64_t>(base);
     out->size = size;
     return true;
+  }
+
+  void Unexport(uint64_t base) override {
+    std::lock_guard<std::mutex> lk(mu_);
+    ranges_.erase(base);
+    exported_.erase(static_cast<CUdeviceptr>(base));
   }
 
   void* Import(const RegionDesc& d) override {
@@ -753,6 +761,9 @@ class MultiCudaDomain : public MemDomain {
   void* AllocOn(size_t bytes, int device) override { return Sub(device)->Alloc(bytes); }
   void Free(void* p) override { OwnerOf(p, -1)->Free(p); }
   bool Export(const void* p, RegionDesc* out) override { return OwnerOf(p, -1)->Export(p, out); }
+  void Unexport(uint64_t base) override {
+    for (auto& d : subs_) d->Unexport(base);
+  }
   void* Import(const RegionDesc& d) override {
     void* base = subs_[0]->Import(d);
     // which local ordinal owns the mapped memory? every other device of this process needs peer access to it
@@ -797,7 +808,8 @@ class MultiCudaDomain : public MemDomain {
     {
       std::lock_guard<std::mutex> lk(mu_);
       auto it = last_for_word_.find(word);
-      if (it != last_for_word_.end() && it->second != d) it->second->Quiesce();  // the previous device has signalled everything
+      // (after Quiesce the previous device has signalled everything it was given)
+      if (it != last_for_word_.end() && it->second != d) it->second->Quiesce();
       last_for_word_[word] = d;
     }
     return d->CopySignal(item, word, value);

@@ -100,6 +100,8 @@ class MemDomain {
   virtual void Free(void* p) = 0;
   /*! \brief describe the exportable allocation that contains `p` (region id left unset) */
   virtual bool Export(const void* p, RegionDesc* out) = 0;
+  /*! \brief drop cached export state of the allocation that starts at `base` (it is about to be freed) */
+  virtual void Unexport(uint64_t /*base*/) {}
   /*! \brief map a peer's region; returns the local address of its base */
   virtual void* Import(const RegionDesc& d) = 0;
   /*!

@@ -105,6 +105,17 @@ class OneSidedVan : public TcpVan {
     if (domain_->Export(addr, &d)) RegionIdFor(&d);
   }
 
+  void UnpinMemory(void* addr) override {
+    RegionDesc d;
+    if (!domain_->Export(addr, &d)) return;
+    {
+      // the region id stays reserved (peers may still hold its mapping) but is never handed out again:
+      // the next export of this base gets a fresh id and a fresh announcement
+      std::lock_guard<SpinMutex> lk(rv_mu_);
+      region_of_base_.erase(d.base);
+    }
+    domain_->Unexport(d.base);
+  }
   void* AllocExportable(size_t bytes) override { return domain_->Alloc(bytes); }
   void* AllocExportableOn(size_t bytes, int device) override { return domain_->AllocOn(bytes, device); }
   int NumDevices() override { return domain_->num_devices(); }
