@@ -98,7 +98,8 @@ def test_bench_script_control_flow_on_cpu(extra):
 
 
 def test_bench_script_multi_process_on_cpu():
-    """the torchrun form the driver uses for N > 1 (2 workers + 2 servers)"""
+    """the torchrun form the driver uses for N > 1: N workers + N servers, one of each per rank (the
+    same topology at every N); --topology split gives N/2 + N/2"""
     from pslite_b200.utils.env import free_port
 
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=4", "--master-addr",
@@ -108,7 +109,13 @@ def test_bench_script_multi_process_on_cpu():
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
     assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
     line = json.loads([l for l in r.stdout.strip().splitlines() if l.startswith("{")][-1])
-    assert line["n_gpus"] == 4 and line["config"]["num_workers"] == 2 and line["value"] > 0
+    assert line["n_gpus"] == 4 and line["config"]["num_workers"] == 4 and line["config"]["num_servers"] == 4
+    assert line["value"] > 0 and line["e2e"]["value"] > 0 and "roofline" in line
+    cmd = cmd[:-1] + ["--topology", "split", "--no-e2e"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    line = json.loads([l for l in r.stdout.strip().splitlines() if l.startswith("{")][-1])
+    assert line["config"]["num_workers"] == 2 and line["config"]["num_servers"] == 2 and line["value"] > 0
 
 
 def test_native_initialises_torch_first():
