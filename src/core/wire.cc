@@ -67,8 +67,8 @@ bool UnpackNode(Reader* r, Node* n) {
 
 void PackMeta(const Meta& m, std::vector<char>* out) {
   out->clear();
-  out->reserve(128 + m.body.size());
-  Writer w(out);
+  out->resize(256 + m.body.size());  // one growth for the common descriptor; the cursor starts at 0
+  Writer w(out, 0);
   w.Put<uint32_t>(kMetaMagic);
   w.Put<uint16_t>(kMetaVersion);
   uint16_t flags = 0;

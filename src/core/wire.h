@@ -11,6 +11,7 @@
  */
 #ifndef PS_CORE_WIRE_H_
 #define PS_CORE_WIRE_H_
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -23,29 +24,42 @@ namespace wire {
 static const uint32_t kMetaMagic = 0x32425350u;  // "PSB2"
 static const uint16_t kMetaVersion = 1;
 
-/*! \brief append-only little-endian writer over a byte vector */
+/*!
+ * \brief append-only little-endian writer over a byte vector. The vector is grown in large steps
+ *        and written through a cursor (a resize per field costs a capacity check plus a zero fill:
+ *        ~30 fields made PackMeta half a microsecond per message); Finish() trims it to size.
+ */
 class Writer {
  public:
-  explicit Writer(std::vector<char>* out) : out_(out) {}
+  explicit Writer(std::vector<char>* out) : out_(out), pos_(out->size()) {}
+  /*! \brief write from offset `at` of a vector the caller has already sized generously */
+  Writer(std::vector<char>* out, size_t at) : out_(out), pos_(at) {}
+  ~Writer() { Finish(); }
   template <typename T>
   void Put(T v) {
     static_assert(std::is_trivially_copyable<T>::value, "POD only");
-    size_t at = out_->size();
-    out_->resize(at + sizeof(T));
-    memcpy(out_->data() + at, &v, sizeof(T));
+    Ensure(sizeof(T));
+    memcpy(out_->data() + pos_, &v, sizeof(T));
+    pos_ += sizeof(T);
   }
   void PutBytes(const void* p, size_t n) {
-    size_t at = out_->size();
-    out_->resize(at + n);
-    if (n) memcpy(out_->data() + at, p, n);
+    Ensure(n);
+    if (n) memcpy(out_->data() + pos_, p, n);
+    pos_ += n;
   }
   void PutString(const std::string& s) {
     Put<uint32_t>(static_cast<uint32_t>(s.size()));
     PutBytes(s.data(), s.size());
   }
+  /*! \brief make the vector exactly as long as what was written */
+  void Finish() { out_->resize(pos_); }
 
  private:
+  void Ensure(size_t n) {
+    if (pos_ + n > out_->size()) out_->resize(std::max(out_->size() * 2, pos_ + n + 256));
+  }
   std::vector<char>* out_;
+  size_t pos_;
 };
 
 /*! \brief bounds-checked reader; ok() turns false on the first short read */
