@@ -115,7 +115,6 @@ class Customer {
   std::atomic<int> pending_{0};        // queued or being handled by the customer thread
   SpinMutex deliver_mu_;               // one handler at a time (several vans may deliver: MultiVan)
   int64_t inline_max_bytes_ = 65536;   // larger two-sided payloads keep the customer thread (PS_INLINE_MAX_BYTES)
-  bool payload_in_frames_ = true;      // false on one-sided vans: their messages are descriptors
   bool TryInline(const Message& m);
   bool started_ = false;
 

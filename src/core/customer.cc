@@ -187,18 +187,18 @@ void Customer::Deliver(const Message& m) {
 void Customer::set_inline_dispatch(bool on) {
   static const bool handoff = GetEnv("PS_LOCAL_HANDOFF", 0) != 0;  // senders deliver too: not one thread
   inline_max_bytes_ = GetEnv("PS_INLINE_MAX_BYTES", 65536);
-  const std::string van = postoffice_->van() ? postoffice_->van()->GetType() : "";
-  payload_in_frames_ = !(van == "nvl" || van == "shm");
   inline_.store(on && !handoff, std::memory_order_release);
 }
 
 bool Customer::TryInline(const Message& m) {
   if (!inline_.load(std::memory_order_acquire) || pending_.load(std::memory_order_acquire) != 0) return false;
-  // bytes this thread would have to stream itself: the payload it just received in a frame, and on
-  // two-sided vans the reply a pull asks for
-  // (a one-sided van only delivers a descriptor: the payload is already in place, however large)
-  if (payload_in_frames_ && m.meta.data_size > inline_max_bytes_) return false;
-  if (payload_in_frames_ && m.meta.request && !m.meta.push && m.meta.val_len > inline_max_bytes_) return false;
+  // bytes this thread would have to stream itself: a payload that arrived IN the frame (a one-sided
+  // descriptor names bytes that are already in place, however many: Meta::mem is valid) and the
+  // reply a two-sided pull asks for. A receive thread that streams megabytes into a peer's ring
+  // while that peer's receive thread does the same towards us would never drain its own ring.
+  const bool one_sided = m.meta.mem.valid();
+  if (!one_sided && m.meta.data_size > inline_max_bytes_) return false;
+  if (!one_sided && m.meta.request && !m.meta.push && m.meta.val_len > inline_max_bytes_) return false;
   if (!deliver_mu_.try_lock()) return false;  // another van's receive thread is in the handler
   if (pending_.load(std::memory_order_acquire) != 0) {  // it queued something meanwhile: keep the order
     deliver_mu_.unlock();

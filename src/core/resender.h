@@ -160,7 +160,10 @@ class Resender {
           LOG(WARNING) << van_->my_node_.ShortDebugString()
                        << ": Timeout to get the ACK message. Resend (retry=" << p.retries
                        << ") " << p.msg.DebugString();
-          CHECK_LT(p.retries, max_retry_);
+          CHECK_LT(p.retries, max_retry_)
+              << "no ACK after " << p.retries << " retransmissions over " << (now - p.sent_at) << " ms "
+              << "(PS_RESEND_TIMEOUT=" << timeout_ms_ << ", PS_RESEND_MAX_RETRY=" << max_retry_
+              << "): the peer is gone, or so loaded that the timeout is too short. " << p.msg.DebugString();
         }
         ++it;
       }

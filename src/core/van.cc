@@ -126,7 +126,7 @@ void Van::Start(int customer_id, bool standalone) {
       // processed without being recorded (and ACKed) would be processed *again* when its
       // sender retransmits it (the reference creates it after registration, src/van.cc:587).
       if (GetEnv("PS_RESEND", 0) != 0 && !resender_) {
-        resender_ = new Resender(GetEnv("PS_RESEND_TIMEOUT", 1000), 10, this);
+        resender_ = new Resender(GetEnv("PS_RESEND_TIMEOUT", 1000), GetEnv("PS_RESEND_MAX_RETRY", 10), this);
       }
       receiver_thread_.reset(new std::thread(&Van::Receiving, this));
       if (standalone) ready_ = true;

@@ -801,6 +801,22 @@ class TcpVan : public Van {
       // frames behind it wait too (a pull must not overtake the push it follows)
       if (pipe->Peek(&hdr, sizeof(hdr)) && hdr.gate != 0 && pipe->gate_done() < hdr.gate) {
         gates_pending_ = true;
+        // a gate that stays closed is the face of a lost completion (a copy that was never issued, a
+        // dead sender): say so instead of stalling silently (PS_WAIT_WARN_S seconds, 0 = never)
+        static const int warn_s = GetEnv("PS_WAIT_WARN_S", 60);
+        if (warn_s > 0) {
+          Inbound* in = it->second.get();
+          const auto now = std::chrono::steady_clock::now();
+          if (in->gate_waiting_for != hdr.gate) {
+            in->gate_waiting_for = hdr.gate;
+            in->gate_since = now;
+          } else if (now - in->gate_since > std::chrono::seconds(warn_s)) {
+            in->gate_since = now;
+            LOG(WARNING) << "node " << my_node_.id << ": the descriptor ring from node " << hdr.sender
+                         << " has waited " << warn_s << " s for completion " << hdr.gate << " (reached: "
+                         << pipe->gate_done() << "); everything behind it is held back";
+          }
+        }
         continue;
       }
       pipe_cursor_ = (idx + 1) % n;
@@ -854,6 +870,8 @@ class TcpVan : public Van {
     /*! \brief once the peer switched to its ring, its frames arrive here and the socket only rings */
     std::unique_ptr<ShmPipe> pipe;
     std::unique_ptr<ShmPipe> offered;  // mapped and accepted, the switch marker is still to come
+    uint64_t gate_waiting_for = 0;     // the gated frame at the head of the ring, and since when it waits
+    std::chrono::steady_clock::time_point gate_since;
   };
 
   /*! \brief make >= n bytes available in the buffer (n <= kCap). 1 ok, 0 closed, -1 error */

@@ -122,12 +122,14 @@ def test_stress_gpu_buffers_full_payload_checksums():
 @pytest.mark.timeout(300)
 def test_stress_gpu_buffers_with_message_loss():
     """the same while 5 % of the messages are dropped and retransmitted (PS_DROP_MSG + PS_RESEND).
-    Verified on 2 GPUs (profiles/r2/native_symmetric_nvls_ipc_stress_2gpu.txt); the one 8-GPU run of
-    round 2 aborted in one process and the GPU budget ended before it could be diagnosed
-    (profiles/r2/big8_partial.txt), so beyond 2 GPUs a failure is reported as xfail, with the reason."""
+    Verified on 2 GPUs (profiles/r2/native_symmetric_nvls_ipc_stress_2gpu.txt). The one 8-GPU run of
+    round 2 aborted in one process: reproduced without a GPU afterwards (8 nodes, 4 MB messages, asynchronous
+    shm copies) — with PS_RESEND_TIMEOUT=200 the resender gives up on a message that is 2.2 s old, which a
+    loaded 8-node job exceeds; the timeout is the default 1 s now. Not re-run on 8 GPUs (budget), so
+    beyond 2 GPUs a failure is still reported as xfail, with the reason."""
     n = min(torch.cuda.device_count(), 8)
     env = {"PS_VAN_TYPE": "nvl", "JOINT": 1, "WORKER_GPU_BASE": 0, "BENCHMARK_NTHREAD": 2,
-           "PS_DROP_MSG": 5, "PS_RESEND": 1, "PS_RESEND_TIMEOUT": 200}
+           "PS_DROP_MSG": 5, "PS_RESEND": 1, "PS_RESEND_TIMEOUT": 1000}
     rc, out = _local(2, 2, "test_benchmark_stress", 4096000, 4, env=env)
     assert rc == 0 and out.count("test_benchmark_stress PASSED") == 2, out[-3000:]
     if n > 2:
