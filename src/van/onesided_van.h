@@ -657,6 +657,10 @@ class OneSidedVan : public TcpVan {
       }
     }
     if (signal_ && PeerGated(msg.meta.recver)) {
+      // this peer's ring was accepted only a moment ago and earlier messages for it may still sit in
+      // the completion queue (ticket path): they must leave first, or a pull could overtake its push
+      std::atomic<int>& in_flight = TicketsFor(msg.meta.recver);
+      while (in_flight.load(std::memory_order_acquire) != 0) std::this_thread::yield();
       // same-host peer with a descriptor ring: the frame goes into the ring NOW and the copy
       // kernel itself opens its gate (st.release.sys on the ring's completion word) — no event,
       // no completion thread, no second hop for the descriptor. Frames without a copy simply
@@ -728,6 +732,7 @@ class OneSidedVan : public TcpVan {
         p.msg = msg;
         p.ticket = t;
         p.keep_alive = keep_alive;
+        TicketsFor(msg.meta.recver).fetch_add(1, std::memory_order_acq_rel);
         cq_.push_back(std::move(p));
         cq_size_.fetch_add(1, std::memory_order_release);
         cq_cv_.notify_one();
@@ -793,6 +798,9 @@ class OneSidedVan : public TcpVan {
           }
         }
       }
+      for (Pending& p : batch) {
+        TicketsFor(p.msg.meta.recver).fetch_sub(1, std::memory_order_acq_rel);
+      }
       batch.clear();  // drops the keep-alive references
       lk.lock();
       cq_busy_ = false;
@@ -834,6 +842,11 @@ class OneSidedVan : public TcpVan {
   bool cq_busy_ = false;
   std::unique_ptr<std::thread> completer_;
 
+  /*! \brief descriptors queued on the ticket path and not yet sent, by receiver id modulo the table
+   *  size (a collision only makes a gated send wait a little longer than it has to) */
+  static constexpr size_t kTicketSlots = 256;
+  std::atomic<int> tickets_in_flight_[kTicketSlots] = {};
+  std::atomic<int>& TicketsFor(int recver) { return tickets_in_flight_[static_cast<size_t>(recver) % kTicketSlots]; }
   std::atomic<uint64_t> copies_{0};
   std::atomic<uint64_t> copy_bytes_{0};
   /*! \brief PS_COALESCE_LAUNCHES: honour Cork / Uncork (off: every copy is its own launch) */

@@ -97,6 +97,17 @@ def test_ipc_benchmark_symmetric_buffer_and_mixed_mode(built_native_tree):
     assert rc == 0 and out.count("VERIFIED") == 2 and "mixed mode" in out, out[-3000:]
 
 
+def test_large_in_frame_payloads_with_inline_dispatch_and_message_loss(built_native_tree):
+    """plain heap buffers on the shm van travel INSIDE the frames; 4 joint nodes stream megabytes at each
+    other while 5 % of the messages are dropped and retransmitted. Receive threads must not handle such
+    messages inline (two of them streaming replies into each other's full ring would never drain their
+    own): this configuration deadlocked until the rings' 60 s write timeout fired"""
+    env = {"PS_VAN_TYPE": "shm", "JOINT": 1, "BENCHMARK_NTHREAD": 2, "DEBUG_MODE": 1, "PS_DROP_MSG": 5,
+           "PS_RESEND": 1, "PS_RESEND_TIMEOUT": 1000}
+    rc, out = launch(built_native_tree, 4, 4, "test_benchmark_stress", 2048000, 3, env=env, timeout=200)
+    assert rc == 0 and out.count("test_benchmark_stress PASSED") == 4, out[-3000:]
+
+
 def test_tutorial_example_runs(built_native_tree):
     """examples/kv_hello.cc is the program printed in docs/tutorials.md"""
     rc, out = launch(built_native_tree, 2, 2, "kv_hello")
