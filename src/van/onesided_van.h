@@ -76,7 +76,8 @@ class OneSidedVan : public TcpVan {
     }
     PS_VLOG(1) << type_ << " van " << my_node_.id << ": " << copies_.load() << " one-sided copies, "
                << gated_frames_.load() << " descriptors gated by the copy engine";
-    PS_VLOG(1) << type_ << " van: receive thread slept " << num_blocking_waits() << " times";
+    PS_VLOG(1) << type_ << " van: receive thread slept " << num_blocking_waits() << " times, " << num_deferred_sends()
+               << " of its sends went through the outbox";
     std::lock_guard<SpinMutex> lk(rv_mu_);
     push_slots_.clear();
     landing_.clear();
@@ -173,6 +174,7 @@ class OneSidedVan : public TcpVan {
     out->emplace_back("onesided_bytes", copy_bytes_.load());
     out->emplace_back("gated_frames", gated_frames_.load());
     out->emplace_back("recv_thread_sleeps", num_blocking_waits());
+    out->emplace_back("deferred_sends", num_deferred_sends());
     out->emplace_back("engine_launches", launches);
     out->emplace_back("engine_items", items);
   }

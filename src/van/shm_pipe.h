@@ -164,6 +164,12 @@ class ShmPipe {
     ctl_->tail.store(tail, std::memory_order_release);
     return true;
   }
+  /*! \brief bytes that can be written right now without waiting for the reader */
+  size_t FreeSpace() const {
+    const uint64_t used = ctl_->tail.load(std::memory_order_relaxed) - ctl_->head.load(std::memory_order_acquire);
+    return static_cast<size_t>(ctl_->capacity - used);
+  }
+  size_t capacity() const { return ctl_->capacity; }
   /*! \brief after a frame: true if the reader declared itself asleep (ring its doorbell) */
   bool ReaderNeedsDoorbell() {
     std::atomic_thread_fence(std::memory_order_seq_cst);

@@ -34,6 +34,7 @@
 #include <array>
 #include <shared_mutex>
 #include <chrono>
+#include <condition_variable>
 #include <deque>
 #include <map>
 #include <memory>
@@ -110,7 +111,10 @@ class RecvBufferPool : public std::enable_shared_from_this<RecvBufferPool> {
 class TcpVan : public Van {
  public:
   explicit TcpVan(Postoffice* postoffice) : Van(postoffice) {}
-  ~TcpVan() override { CloseAll(); }
+  ~TcpVan() override {
+    StopOutbox();
+    CloseAll();
+  }
 
   std::string GetType() const override { return "zmq"; }
 
@@ -130,6 +134,7 @@ class TcpVan : public Van {
       for (auto it = m.begin(); it != m.end();) it = it->second == this ? m.erase(it) : std::next(it);
     }
     Van::Stop();
+    StopOutbox();
     CloseAll();
   }
 
@@ -202,6 +207,8 @@ class TcpVan : public Van {
     /*! \brief gated frames (see ShmPipe): sequence of the last one, the address the copy engine
      *  stores completions to (null: no gating on this connection), and what must stay alive
      *  until a given completion. All under `mu`. */
+    /*! \brief messages of receive threads parked in the outbox for this peer (see Defer) */
+    std::atomic<int> deferred{0};
     uint64_t gate_seq = 0;
     void* gate_word = nullptr;
     std::deque<std::pair<uint64_t, SArray<char>>> gate_keep;
@@ -341,6 +348,8 @@ class TcpVan : public Van {
 
   /*! \brief how often the receive thread gave up polling and slept (each wake-up costs 50-300 us on a VM) */
   uint64_t num_blocking_waits() const { return blocking_waits_.load(); }
+  /*! \brief sends of receive threads that went through the outbox because they would have had to wait */
+  uint64_t num_deferred_sends() const { return deferred_sends_.load(); }
 
   /*! \brief can frames to `recver` be gated on completions the copy engine signals itself? */
   bool PeerGated(int recver) {
@@ -426,7 +435,30 @@ class TcpVan : public Van {
     }
     for (int i = 0; i < niov; ++i) total += iov[i].iov_len;
 
-    std::lock_guard<std::mutex> lk(peer->mu);
+    std::unique_lock<std::mutex> lk(peer->mu, std::defer_lock);
+    if (tls_receiving_ != nullptr && !tls_outbox_) {
+      // A receive thread must never wait for a connection: another thread of this process may be
+      // streaming megabytes into it (holding the lock, or having filled the ring), which only ends
+      // when the PEER's receive thread drains them — and that one may be waiting, symmetrically, for
+      // us. Replies, ACKs and rendezvous messages sent from a receive thread therefore go out
+      // through the outbox thread whenever they would have to wait; per peer they keep their order.
+      if (issue) {
+        while (peer->deferred.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+        lk.lock();  // gated frames are descriptors: nobody holds this lock for long on a one-sided van
+      } else {
+        bool wait_needed = peer->deferred.load(std::memory_order_acquire) != 0 || !lk.try_lock();
+        if (!wait_needed && peer->pipe && total <= peer->pipe->capacity() / 2 && peer->pipe->FreeSpace() < total) {
+          lk.unlock();
+          wait_needed = true;
+        }
+        if (wait_needed) {
+          Defer(peer, msg);
+          return static_cast<int>(std::min<size_t>(total, 0x7fffffff));
+        }
+      }
+    } else {
+      lk.lock();
+    }
     if (peer->fd < 0) return -1;
     if (issue) {
       if (!peer->pipe || !peer->gate_word) return kNotGated;
@@ -510,6 +542,7 @@ class TcpVan : public Van {
   }
 
   int RecvMsg(Message* msg) override {
+    tls_receiving_ = this;  // from here on this thread's sends must not wait for a connection (see SendFrame)
     // busy-poll window of this call: as long as the recent gaps between bursts suggest
     const auto t0 = std::chrono::steady_clock::now();
     const int rc = RecvOne(msg, pipe_budget_.window_us());
@@ -785,6 +818,50 @@ class TcpVan : public Van {
       got += static_cast<size_t>(r);
     }
     return 1;
+  }
+
+  // ---- outbox: sends of receive threads that would have had to wait ------------------------------
+  struct Outgoing {
+    std::shared_ptr<Peer> peer;
+    Message msg;
+  };
+  void Defer(const std::shared_ptr<Peer>& peer, const Message& msg) {
+    peer->deferred.fetch_add(1, std::memory_order_acq_rel);
+    {
+      std::lock_guard<std::mutex> lk(outbox_mu_);
+      outbox_.push_back(Outgoing{peer, msg});
+      if (!outbox_thread_) outbox_thread_.reset(new std::thread([this] { OutboxLoop(); }));
+    }
+    outbox_cv_.notify_one();
+    ++deferred_sends_;
+  }
+  void OutboxLoop() {
+    tls_outbox_ = true;  // this thread MAY wait: that is its job
+    std::unique_lock<std::mutex> lk(outbox_mu_);
+    for (;;) {
+      outbox_cv_.wait(lk, [this] { return outbox_stop_ || !outbox_.empty(); });
+      if (outbox_.empty()) return;  // (stopping, nothing left)
+      Outgoing o = std::move(outbox_.front());
+      outbox_.pop_front();
+      lk.unlock();
+      if (SendFrame(o.msg) < 0 && !outbox_stop_) {
+        LOG(WARNING) << "deferred message for node " << o.msg.meta.recver << " could not be sent";
+      }
+      o.peer->deferred.fetch_sub(1, std::memory_order_acq_rel);
+      lk.lock();
+    }
+  }
+  void StopOutbox() {
+    std::unique_ptr<std::thread> t;
+    {
+      std::lock_guard<std::mutex> lk(outbox_mu_);
+      outbox_stop_ = true;
+      t.swap(outbox_thread_);
+    }
+    outbox_cv_.notify_all();
+    if (t) t->join();
+    std::lock_guard<std::mutex> lk(outbox_mu_);
+    outbox_stop_ = false;  // the van may be started again
   }
 
   /*! \brief deliver the next frame of any ring that has bytes; 0 if all are empty */
@@ -1219,11 +1296,22 @@ class TcpVan : public Van {
     uint64_t bytes;
   };
   using PullKey = std::tuple<int, int, int, int>;
+  std::mutex outbox_mu_;
+  std::condition_variable outbox_cv_;
+  std::deque<Outgoing> outbox_;
+  std::unique_ptr<std::thread> outbox_thread_;
+  bool outbox_stop_ = false;
+  std::atomic<uint64_t> deferred_sends_{0};
+  static thread_local const TcpVan* tls_receiving_;  // set on a van's receive thread
+  static thread_local bool tls_outbox_;               // set on an outbox thread
   std::mutex offer_mu_;
   std::unordered_map<int, int> offer_fds_;  // outbound socket -> peer id, while an offer is unanswered
   SpinMutex pull_mu_;
   std::map<PullKey, PullDest> pull_dests_;
 };
+
+inline thread_local const TcpVan* TcpVan::tls_receiving_ = nullptr;
+inline thread_local bool TcpVan::tls_outbox_ = false;
 
 }  // namespace ps
 
