@@ -114,7 +114,7 @@ class Customer {
   std::atomic<bool> inline_{false};    // set_inline_dispatch
   std::atomic<int> pending_{0};        // queued or being handled by the customer thread
   SpinMutex deliver_mu_;               // one handler at a time (several vans may deliver: MultiVan)
-  int64_t inline_max_bytes_ = 65536;   // larger two-sided payloads keep the customer thread (PS_INLINE_MAX_BYTES)
+  std::atomic<int64_t> inline_max_bytes_{65536};  // in-frame payloads above this go to the customer thread
   bool TryInline(const Message& m);
   bool started_ = false;
 

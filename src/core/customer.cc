@@ -186,7 +186,7 @@ void Customer::Deliver(const Message& m) {
 
 void Customer::set_inline_dispatch(bool on) {
   static const bool handoff = GetEnv("PS_LOCAL_HANDOFF", 0) != 0;  // senders deliver too: not one thread
-  inline_max_bytes_ = GetEnv("PS_INLINE_MAX_BYTES", 65536);
+  inline_max_bytes_.store(GetEnv("PS_INLINE_MAX_BYTES", 65536), std::memory_order_relaxed);
   inline_.store(on && !handoff, std::memory_order_release);
 }
 
@@ -197,8 +197,9 @@ bool Customer::TryInline(const Message& m) {
   // reply a two-sided pull asks for. A receive thread that streams megabytes into a peer's ring
   // while that peer's receive thread does the same towards us would never drain its own ring.
   const bool one_sided = m.meta.mem.valid();
-  if (!one_sided && m.meta.data_size > inline_max_bytes_) return false;
-  if (!one_sided && m.meta.request && !m.meta.push && m.meta.val_len > inline_max_bytes_) return false;
+  const int64_t limit = inline_max_bytes_.load(std::memory_order_relaxed);
+  if (!one_sided && m.meta.data_size > limit) return false;
+  if (!one_sided && m.meta.request && !m.meta.push && m.meta.val_len > limit) return false;
   if (!deliver_mu_.try_lock()) return false;  // another van's receive thread is in the handler
   if (pending_.load(std::memory_order_acquire) != 0) {  // it queued something meanwhile: keep the order
     deliver_mu_.unlock();

@@ -176,35 +176,35 @@ class FdExchange {
   }
 
   bool Start(const std::string& endpoint) {
-    listen_fd_ = socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
-    if (listen_fd_ < 0) return false;
+    const int fd = socket(AF_UNIX, SOCK_STREAM | SOCK_CLOEXEC, 0);
+    if (fd < 0) return false;
     struct sockaddr_un sa;
     const socklen_t len = Addr(endpoint, &sa);
-    if (bind(listen_fd_, reinterpret_cast<struct sockaddr*>(&sa), len) != 0 || listen(listen_fd_, 256) != 0) {
-      close(listen_fd_);
-      listen_fd_ = -1;
+    if (bind(fd, reinterpret_cast<struct sockaddr*>(&sa), len) != 0 || listen(fd, 256) != 0) {
+      close(fd);
       return false;
     }
-    acceptor_.reset(new std::thread([this] { AcceptLoop(); }));
+    listen_fd_.store(fd);
+    acceptor_.reset(new std::thread([this, fd] { AcceptLoop(fd); }));
     return true;
   }
 
   void Stop() {
     stop_.store(true);
     cv_.notify_all();
-    if (listen_fd_ >= 0) {
-      shutdown(listen_fd_, SHUT_RDWR);
-      close(listen_fd_);
-      listen_fd_ = -1;
+    const int fd = listen_fd_.exchange(-1);
+    if (fd >= 0) {
+      shutdown(fd, SHUT_RDWR);
+      close(fd);
     }
     if (acceptor_) acceptor_->join();
     acceptor_.reset();
     while (active_.load() > 0) std::this_thread::yield();
   }
 
-  void AcceptLoop() {
+  void AcceptLoop(int listen_fd) {
     for (;;) {
-      const int c = accept4(listen_fd_, nullptr, nullptr, SOCK_CLOEXEC);
+      const int c = accept4(listen_fd, nullptr, nullptr, SOCK_CLOEXEC);
       if (c < 0) {
         if (stop_.load()) return;
         if (errno == EINTR) continue;
@@ -262,7 +262,7 @@ class FdExchange {
     } while (w < 0 && errno == EINTR);
   }
 
-  int listen_fd_ = -1;
+  std::atomic<int> listen_fd_{-1};
   std::unique_ptr<std::thread> acceptor_;
   std::atomic<bool> stop_{false};
   std::atomic<int> active_{0};
