@@ -251,10 +251,19 @@ def run_pushpull(args, dist: Dist) -> dict:
             kv.wait_all(kv.push_pull_batch([keys[k] for k in idx], [vals[k] for k in idx],
                                            order_after_current_stream=False, pull=False))
 
+    my_role = "worker" if ctx.is_worker else "server"
+
+    def engine_items() -> int:
+        # descriptors this GPU's copy engine has executed (one engine per device and process)
+        return int(C.van_stats(my_role).get("engine_items", 0))
+
+    engine_work = {"descriptors": 0}
+
     def timed(fn, steps: int):
         dist.barrier()
         gpu.sync()
         launches0 = C.kernel_launch_count()
+        items0 = engine_items()
         stop = gpu.timer()
         if ctx.is_worker:
             for _ in range(steps):
@@ -263,6 +272,7 @@ def run_pushpull(args, dist: Dist) -> dict:
         ms = stop()
         dist.barrier()  # servers keep serving until every worker is done
         launches = C.kernel_launch_count() - launches0
+        engine_work["descriptors"] = int(dist.reduce(float(engine_items() - items0), "sum"))
         return dist.reduce(ms, "max"), dist.reduce(float(launches), "sum")
 
     # clocks are sampled from the warm-up on (same load as the timed steps): K steps of this
@@ -276,6 +286,7 @@ def run_pushpull(args, dist: Dist) -> dict:
             n_warm += 1
     verify("before the timed rounds")
     ms, launches = timed(one_round, args.steps)
+    copies_by_engine = engine_work["descriptors"]
     clocks = sampler.stop() if sampler else None
     verify("after the timed rounds")
     payload = float(args.len) * total_keys * W  # per step, counted once per push+pull pair
@@ -392,6 +403,9 @@ def run_pushpull(args, dist: Dist) -> dict:
                                   f"{'GPU(s), nvl van' if gpu.cuda else 'CPU process(es), shm van (self-check, not a result)'}",
                    "l2": f"working set {args.len * total_keys / 1e6:.0f} MB per worker > 126 MB L2"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+        # with the copy engine a launch is one (re)start of the persistent kernel; the copies themselves are
+        # descriptors it executes — this many inside the timed region, summed over the GPUs
+        "gpu_copy_engine_descriptors": copies_by_engine,
     }
 
 
