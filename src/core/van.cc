@@ -78,7 +78,7 @@ void Van::Start(int customer_id, bool standalone) {
           }
           if (ip.empty()) ip = "127.0.0.1";  // loopback-only sandbox
         }
-        const int num_ports = std::max(1, GetEnv("DMLC_NUM_PORTS", 1));
+        const int num_ports = std::max(1, GetEnv("DMLC_NUM_PORTS", GetEnv("DMLC_NUM_CPU_DEV", 1)));
         CHECK_LE(num_ports, kMaxNodePorts);
         std::array<int, 32> ports;
         ports.fill(0);

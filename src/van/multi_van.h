@@ -30,7 +30,7 @@ class MultiVan : public Van {
 
   void Start(int customer_id, bool standalone) override {
     if (rails_.empty()) {
-      num_rails_ = std::max(1, GetEnv("DMLC_NUM_PORTS", 1));
+      num_rails_ = std::max(1, GetEnv("DMLC_NUM_PORTS", GetEnv("DMLC_NUM_CPU_DEV", 1)));
       CHECK_LE(num_rails_, kMaxNodePorts);
       for (int i = 0; i < num_rails_; ++i) rails_.emplace_back(new Rail(postoffice_ptr_));
     }
