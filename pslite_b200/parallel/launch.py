@@ -67,6 +67,39 @@ def _share_port(rank: int, world: int) -> int:
     return int(box[0])
 
 
+def bind_to_gpu_numa_node(device_index: int) -> list[int] | None:
+    """Restrict this process (and the threads it starts later: van receive threads, the outbox, torch's
+    helpers) to the CPUs of the NUMA node the GPU hangs off, so that pinned host buffers are first-touched
+    on that node and host<->device copies do not cross the socket interconnect. Eight ranks started by
+    torchrun otherwise land on arbitrary CPUs. Returns the CPU list, or None if nothing was changed
+    (no sysfs entry, a node with fewer than 4 CPUs, PS_NUMA_BIND=0)."""
+    if os.environ.get("PS_NUMA_BIND", "1") == "0":
+        return None
+    try:
+        import torch
+
+        if not torch.cuda.is_available():
+            return None
+        p = torch.cuda.get_device_properties(device_index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/local_cpulist") as f:
+            spec = f.read().strip()
+        cpus: list[int] = []
+        for part in spec.split(","):
+            if not part:
+                continue
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if len(cpus) < 4 or len(cpus) >= len(allowed):
+            return None  # no NUMA information worth acting on (or already bound)
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:  # a missing attribute / sysfs file must never stop a job
+        return None
+
+
 def init_ps(topology: str = "joint", van: str | None = None, extra_env: dict | None = None) -> PSContext:
     """Start the PS runtime for this torchrun rank and return its context."""
     from .. import native
@@ -130,6 +163,8 @@ def init_ps(topology: str = "joint", van: str | None = None, extra_env: dict | N
         atexit.register(lambda p=sched: p.poll() is None and p.kill())
     for k, v in env.items():
         C.set_env(k, str(v))
+    if van == "nvl":
+        bind_to_gpu_numa_node(local_rank)  # before the van starts its threads and anybody pins host memory
     preferred = wrank if is_worker else srank
     C.start_ps(0, role, preferred, True)
     return PSContext(rank, world, local_rank, topology, nw, ns, is_worker, is_server, wrank, srank,
