@@ -231,3 +231,28 @@ def test_fused_swiglu_matches_reference(native):
     out.backward(d)
     ref.backward(d.float())
     assert torch.allclose(gu.grad.float(), gu_ref.grad, atol=3e-2, rtol=3e-2)
+
+
+def test_copy_engine_selfcheck_and_message_rate():
+    """apps/engine_bench on one GPU: descriptors posted to the copy engine (persistent kernel, TMA workers)
+    against one launch per copy; every configuration verifies the bytes it moved. The engine must move a
+    small message in a fraction of what a launch costs, and 16 MB copies at HBM-class bandwidth."""
+    import json
+    import os
+    import subprocess
+
+    _require_cuda()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "build", "engine_bench")
+    if not os.path.exists(exe):
+        pytest.skip("build/engine_bench not built (make)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=240, cwd=root)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    rows = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+    summary = rows[-1]
+    assert summary["data_failures"] == 0 and summary["engine_items"] > 0 and summary["engine_launches"] >= 1
+    eng = {d["bytes"]: d for d in rows if d.get("path") == "engine" and "bytes" in d}
+    lau = {d["bytes"]: d for d in rows if d.get("path") == "launch" and "bytes" in d}
+    assert eng[1024]["us_per_msg"] < 0.6 * lau[1024]["us_per_msg"], (eng[1024], lau[1024])
+    assert eng[16 << 20]["GBps"] > 1000, eng[16 << 20]
+    print({b: (eng[b]["us_per_msg"], eng[b]["GBps"]) for b in sorted(eng)})
