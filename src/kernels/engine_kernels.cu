@@ -586,11 +586,45 @@ void EngineDestroy(ps_engine* e) {
 }
 }  // namespace
 
+namespace {
+/*!
+ * \brief wait until `target` descriptors have retired. A kernel that faulted (a descriptor naming
+ *        memory that is gone) never retires anything: after every second without progress the
+ *        engine's stream is asked for its status, and a CUDA error ends the process with a message
+ *        instead of a silent hang (the reference's counterpart: a failed work completion in PollCQ
+ *        is fatal, src/rdma_van.h:609-616).
+ */
+void WaitRetired(ps_engine* e, unsigned long long target) {
+  unsigned long long seen = HostLoad(&e->ctl->retired);
+  if (seen >= target) return;
+  auto since = std::chrono::steady_clock::now();
+  for (unsigned spins = 0;; ++spins) {
+    const unsigned long long now_retired = HostLoad(&e->ctl->retired);
+    if (now_retired >= target) return;
+    std::this_thread::yield();
+    if ((spins & 1023u) != 1023u) continue;
+    const auto now = std::chrono::steady_clock::now();
+    if (now_retired != seen) {
+      seen = now_retired;
+      since = now;
+    } else if (now - since > std::chrono::seconds(1)) {
+      since = now;
+      const cudaError_t st = cudaStreamQuery(e->stream);
+      if (st != cudaSuccess && st != cudaErrorNotReady) {
+        fprintf(stderr, "pslite copy engine (device %d): the engine kernel failed: %s; %llu of %llu descriptors retired\n",
+                e->device, cudaGetErrorString(st), now_retired, target);
+        abort();
+      }
+    }
+  }
+}
+}  // namespace
+
 extern "C" int ps_engine_post(ps_engine* e, void* dst, const void* src, size_t bytes, unsigned long long* flag,
                               unsigned long long value, unsigned long long* ticket) {
   std::lock_guard<std::mutex> lk(e->mu);
   // back-pressure: the host ring holds kHostRing descriptors that have not been retired
-  while (e->posted - HostLoad(&e->ctl->retired) >= kHostRing - 1) std::this_thread::yield();
+  if (e->posted - HostLoad(&e->ctl->retired) >= kHostRing - 1) WaitRetired(e, e->posted - (kHostRing - 2));
   Item& it = e->ring[e->posted & (kHostRing - 1)];
   it.dst = static_cast<unsigned char*>(dst);
   it.src = static_cast<const unsigned char*>(src);
@@ -630,7 +664,7 @@ extern "C" void ps_engine_drain(ps_engine* e) {
     std::lock_guard<std::mutex> lk(e->mu);
     upto = e->posted;
   }
-  while (HostLoad(&e->ctl->retired) < upto) std::this_thread::yield();
+  WaitRetired(e, upto);
 }
 
 extern "C" int ps_engine_done(ps_engine* e, unsigned long long ticket) {
@@ -638,7 +672,7 @@ extern "C" int ps_engine_done(ps_engine* e, unsigned long long ticket) {
 }
 
 extern "C" void ps_engine_wait(ps_engine* e, unsigned long long ticket) {
-  while (HostLoad(&e->ctl->retired) < ticket) std::this_thread::yield();
+  WaitRetired(e, ticket);
 }
 
 extern "C" void ps_engine_stats(ps_engine* e, unsigned long long* launches, unsigned long long* items) {
