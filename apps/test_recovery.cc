@@ -53,6 +53,56 @@ int main() {
   }
   KVWorker<float> kv(0, 0);
   std::vector<Key> keys = {7};
+  // RECOVERY_ONESIDED=1 (one-sided vans): values live in exportable memory, so pushes and pull replies
+  // are one-sided writes into regions the peers have mapped. The replacement process has the dead
+  // worker's node id but its own regions: everything the survivors cached about that id must go.
+  const bool onesided = GetEnv("RECOVERY_ONESIDED", 0) != 0;
+  Van* van = Postoffice::Get()->van();
+  auto exportable = [&](float v) {
+    float* p = static_cast<float*>(van->AllocExportable(256));
+    CHECK(p) << "RECOVERY_ONESIDED needs a van with exportable memory (shm / nvl)";
+    p[0] = v;
+    SArray<float> a;
+    a.reset(p, 1, [](float*) {});
+    return a;
+  };
+  if (onesided) {
+    SArray<Key> zkeys(keys);
+    if (crash) {
+      SArray<float> vals = exportable(5.f), got = exportable(-1.f);
+      kv.Wait(kv.ZPush(zkeys, vals));
+      kv.Wait(kv.ZPull(zkeys, &got));  // the server now has this process's region mapped
+      CHECK_GE(got[0], 5.f);
+      LL << "worker " << MyRank() << " crashing after its one-sided push and pull";
+      _exit(0);
+    }
+    if (late) {
+      CHECK(Postoffice::Get()->is_recovery()) << "late worker was not flagged as a recovery node";
+      LL << "recovery worker adopted rank " << MyRank() << " id " << van->my_node().id;
+      SArray<float> got = exportable(-1.f);
+      kv.Wait(kv.ZPull(zkeys, &got));
+      CHECK_EQ(got[0], 6.f) << "the pull reply did not land in the replacement's memory";
+      SArray<float> vals = exportable(10.f);
+      kv.Wait(kv.ZPush(zkeys, vals));
+      kv.Wait(kv.ZPull(zkeys, &got));
+      CHECK_EQ(got[0], 16.f);
+      LL << "test_recovery PASSED";
+      SimpleApp app(1, 2);
+      app.Wait(app.Request(0, "done", kServerGroup));
+      SimpleApp app2(0, 3);
+      app2.Wait(app2.Request(0, "done", kScheduler));
+      Finalize(0, role, false);
+      return 0;
+    }
+    SArray<float> vals = exportable(1.f), got = exportable(-1.f);
+    kv.Wait(kv.ZPush(zkeys, vals));
+    kv.Wait(kv.ZPull(zkeys, &got));
+    SimpleApp app2(0, 3);
+    std::this_thread::sleep_for(std::chrono::seconds(GetEnv("RECOVERY_SURVIVOR_WAIT", 8)));
+    app2.Wait(app2.Request(0, "done", kScheduler));
+    Finalize(0, role, false);
+    return 0;
+  }
   if (crash) {
     std::vector<float> vals = {5.f};
     kv.Wait(kv.Push(keys, vals));

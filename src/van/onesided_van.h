@@ -101,6 +101,31 @@ class OneSidedVan : public TcpVan {
     registered_slots_[std::make_pair(msg.meta.sender, msg.meta.key)] = msg.data[1];
   }
 
+  /*!
+   * \brief a node id that is connected AGAIN belongs to a NEW process: after a recovery the
+   *        replacement takes over the dead node's id but brings its own regions and knows none of
+   *        ours. Everything cached under that id — mappings of its regions (region ids start from
+   *        0 again over there), the slots it granted, what we announced to it — is forgotten, or a
+   *        pull reply would be written into the dead process's memory (the reference re-creates
+   *        the endpoint and its memory-region tables on reconnect, src/rdma_van.h:759-777).
+   */
+  void Connect(const Node& node) override {
+    if (HasPeer(node.id)) {
+      std::lock_guard<SpinMutex> lk(rv_mu_);
+      const int id = node.id;
+      for (auto it = peer_regions_.begin(); it != peer_regions_.end();) {
+        it = it->first.first == id ? peer_regions_.erase(it) : std::next(it);
+      }
+      for (auto it = push_slots_.begin(); it != push_slots_.end();) {
+        it = it->first.first == id ? push_slots_.erase(it) : std::next(it);
+      }
+      for (auto it = announced_.begin(); it != announced_.end();) {
+        it = it->first == id ? announced_.erase(it) : std::next(it);
+      }
+    }
+    TcpVan::Connect(node);
+  }
+
   void PinMemory(void* addr, size_t /*length*/, bool /*gpu*/, int /*dev*/ = 0) override {
     RegionDesc d;
     if (domain_->Export(addr, &d)) RegionIdFor(&d);

@@ -358,6 +358,12 @@ class TcpVan : public Van {
     return it != peers_.end() && it->second->pipe && it->second->gate_word != nullptr;
   }
 
+  /*! \brief is there a connection to node `id` already (then Connect(id) is a reconnect after recovery) */
+  bool HasPeer(int id) {
+    std::lock_guard<SpinMutex> lk(peers_mu_);
+    return peers_.count(id) > 0;
+  }
+
   /*! \brief -2 from SendFrame: the gate could not be issued, nothing was sent */
   static constexpr int kNotGated = -2;
 

@@ -227,9 +227,11 @@ def test_van_profiling_log(built_native_tree, tmp_path):
     assert server_log and server_log[0].split("\t")[1] in ("server_van_recv_push", "server_van_recv_pull")
 
 
-@pytest.mark.parametrize("van", ["zmq", "shm"])
+@pytest.mark.parametrize("van", ["zmq", "shm", "shm-onesided"])
 def test_dead_node_is_replaced_by_late_registration(built_native_tree, van):
-    """heartbeats -> dead-node detection -> a late worker inherits the dead worker's id."""
+    """heartbeats -> dead-node detection -> a late worker inherits the dead worker's id. "shm-onesided":
+    values in exportable memory, so the survivors hold mappings of the dead process's regions under the
+    node id the replacement takes over — its pull replies must land in ITS memory."""
     import random
     import time
 
@@ -237,7 +239,9 @@ def test_dead_node_is_replaced_by_late_registration(built_native_tree, van):
     env = dict(os.environ)
     env.update({"DMLC_NUM_SERVER": "1", "DMLC_NUM_WORKER": "2", "DMLC_PS_ROOT_URI": "127.0.0.1",
                 "DMLC_PS_ROOT_PORT": str(21000 + random.randrange(10000)), "DMLC_NODE_HOST": "127.0.0.1",
-                "PS_HEARTBEAT_INTERVAL": "1", "PS_HEARTBEAT_TIMEOUT": "2", "PS_VAN_TYPE": van})
+                "PS_HEARTBEAT_INTERVAL": "1", "PS_HEARTBEAT_TIMEOUT": "2", "PS_VAN_TYPE": van.split("-")[0]})
+    if van.endswith("-onesided"):
+        env["RECOVERY_ONESIDED"] = "1"
     env.pop("DMLC_RANK", None)
 
     def spawn(role, **extra):
