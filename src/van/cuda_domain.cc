@@ -253,7 +253,7 @@ class CudaDomain : public MemDomain {
         --it;
         if (reinterpret_cast<uint64_t>(p) < it->first + it->second.first) {
           memcpy(out->handle, &it->second.second, 64);
-          out->pid = static_cast<int32_t>(getpid());
+          out->pid = pid_;
           out->dev = dev_;
           out->base = it->first;
           out->size = it->second.first;
@@ -296,7 +296,7 @@ class CudaDomain : public MemDomain {
     }
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle must fit RegionDesc::handle");
     memcpy(out->handle, &it->second, 64);
-    out->pid = static_cast<int32_t>(getpid());
+    out->pid = pid_;
     out->dev = dev_;
     out->base = static_cast<uint64_t>(base);
     out->size = size;
@@ -311,7 +311,7 @@ class CudaDomain : public MemDomain {
 
   void* Import(const RegionDesc& d) override {
     PS_CUDA_CHECK(cudaSetDevice(dev_));
-    if (d.pid == static_cast<int32_t>(getpid())) {
+    if (d.pid == pid_) {
       // same address space: no IPC; only make sure the two devices can see each other
       if (d.dev >= 0 && d.dev != dev_) {
         cudaError_t e = cudaDeviceEnablePeerAccess(d.dev, 0);
@@ -724,6 +724,7 @@ class CudaDomain : public MemDomain {
   };
   std::vector<std::unique_ptr<DevArena>> arenas_;
   int dev_;
+  const int32_t pid_ = static_cast<int32_t>(getpid());  // (a system call each time otherwise)
   int max_ctas_ = 0;
   ps_engine* engine_ = nullptr;
   std::atomic<unsigned long long> engine_ticket_{0};  // this domain's newest post to the (shared) engine

@@ -334,7 +334,7 @@ class ShmDomain : public MemDomain {
   bool Export(const void* p, RegionDesc* out) override {
     Arena* a = FindArena(p);
     if (!a || a->retired) return false;
-    out->pid = static_cast<int32_t>(getpid());
+    out->pid = pid_;
     out->dev = -1;
     out->base = reinterpret_cast<uint64_t>(a->base);
     out->size = a->size;
@@ -343,7 +343,7 @@ class ShmDomain : public MemDomain {
     return true;
   }
   void* Import(const RegionDesc& d) override {
-    if (d.pid == static_cast<int32_t>(getpid())) return reinterpret_cast<void*>(d.base);
+    if (d.pid == pid_) return reinterpret_cast<void*>(d.base);
     std::lock_guard<std::mutex> lk(mu_);
     std::string key(d.handle);
     auto it = imported_.find(key);
@@ -419,6 +419,7 @@ class ShmDomain : public MemDomain {
   }
 
  private:
+  const int32_t pid_ = static_cast<int32_t>(getpid());  // (a system call each time otherwise: glibc does not cache it)
   struct AsyncOp {
     void* dst = nullptr;
     const void* src = nullptr;

@@ -378,13 +378,18 @@ class TcpVan : public Van {
     const int recver = msg.meta.recver;
     if (direct_pull_ && msg.meta.request && msg.meta.control.empty() && msg.meta.src_dev_type != GPU) {
       // remember where the reply of this pull may land: the address echoed back on the wire is
-      // only ever compared with this record, never trusted (see SegmentDestination)
+      // only ever compared with this record, never trusted (see SegmentDestination). A request
+      // that DESCRIBES its destination (one-sided vans) is answered by a write into it and a
+      // descriptor: no segment will ever arrive to consume a record, so none is made.
       const bool fused = msg.meta.push && msg.meta.pull;
-      const uint64_t addr = fused ? msg.meta.pull_addr : (msg.meta.push ? 0 : msg.meta.addr);
+      const bool described = fused ? msg.meta.pull_mem.valid() : msg.meta.mem.valid();
+      const uint64_t addr = described ? 0 : (fused ? msg.meta.pull_addr : (msg.meta.push ? 0 : msg.meta.addr));
       if (addr != 0) {
         const size_t esz = msg.meta.data_type.size() > 1 ? ElemSize(msg.meta.data_type[1]) : 1;
         const uint64_t bytes = static_cast<uint64_t>(fused ? msg.meta.pull_len : msg.meta.val_len) * esz;
         std::lock_guard<SpinMutex> lk(pull_mu_);
+        // (replies that never come — a dead server, an empty value — must not pile up for ever)
+        if (pull_dests_.size() >= kMaxPullRecords) pull_dests_.erase(pull_dests_.begin());
         pull_dests_[PullKey(recver, msg.meta.app_id, msg.meta.customer_id, msg.meta.timestamp)] = {addr, bytes};
       }
     }
@@ -1302,6 +1307,7 @@ class TcpVan : public Van {
     uint64_t bytes;
   };
   using PullKey = std::tuple<int, int, int, int>;
+  static constexpr size_t kMaxPullRecords = 1 << 16;
   std::mutex outbox_mu_;
   std::condition_variable outbox_cv_;
   std::deque<Outgoing> outbox_;
