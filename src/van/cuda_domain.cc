@@ -862,7 +862,7 @@ class MultiCudaDomain : public MemDomain {
 
 }  // namespace
 
-MemDomain* CreateCudaDomain() {
+MemDomain* CreateCudaDomain(int instance_idx) {
   const int n = CudaDeviceCount();
   if (n <= 0) {
     LOG(ERROR) << "the nvl van needs a CUDA device and none is visible";
@@ -876,10 +876,15 @@ MemDomain* CreateCudaDomain() {
   } else {
     if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
   }
-  CHECK(dev >= 0 && dev < n) << "CUDA device " << dev << " out of range (" << n << " visible)";
   // DMLC_NUM_GPU_DEV (the reference's name, src/ucx_van.h:941-942) / PS_NUM_GPU_DEV: this process
   // drives that many consecutive devices starting at `dev`
   const int count = GetEnv("PS_NUM_GPU_DEV", GetEnv("DMLC_NUM_GPU_DEV", 1));
+  // DMLC_GROUP_SIZE instances in one process (the reference gives each its own rail / NIC port,
+  // src/postoffice.cc:38-47): PS_INSTANCE_GPU_STRIDE=s moves instance i to device dev + i * s * count,
+  // so every instance gets its own GPU(s), NVLink ports and copy engine. 0 (default): all instances
+  // of the process share its device.
+  dev += instance_idx * GetEnv("PS_INSTANCE_GPU_STRIDE", 0) * std::max(1, count);
+  CHECK(dev >= 0 && dev < n) << "CUDA device " << dev << " out of range (" << n << " visible)";
   if (count > 1) {
     CHECK_LE(dev + count, n) << "devices " << dev << ".." << dev + count - 1 << " requested, " << n << " visible";
     return new MultiCudaDomain(dev, count);

@@ -9,9 +9,10 @@
  * worker + server: the reference's IPCTransport case, src/rdma_van.h:231-244).
  * CopyAsync launches the sm_100a copy / cast / fp8-quant kernels of
  * src/kernels on a dedicated high-priority stream; the Ticket is a pooled
- * cudaEvent. One process drives one GPU (UCXVan picks a context per device,
- * src/ucx_van.h:948-995; here: PS_CUDA_DEVICE, else LOCAL_RANK, else the
- * current device).
+ * cudaEvent (the default path is the copy engine: posted descriptors, completion
+ * signalled by the kernel). A process drives one GPU (PS_CUDA_DEVICE, else LOCAL_RANK, else the
+ * current device), several consecutive ones (DMLC_NUM_GPU_DEV: a context per device like
+ * src/ucx_van.h:948-995), or one per instance of a group (PS_INSTANCE_GPU_STRIDE).
  */
 #ifndef PS_VAN_CUDA_DOMAIN_H_
 #define PS_VAN_CUDA_DOMAIN_H_
@@ -19,7 +20,7 @@
 
 namespace ps {
 /*! \brief nullptr (with a log line) if no CUDA device is usable */
-MemDomain* CreateCudaDomain();
+MemDomain* CreateCudaDomain(int instance_idx = 0);
 /*! \brief number of visible CUDA devices, 0 if the driver is absent */
 int CudaDeviceCount();
 }  // namespace ps

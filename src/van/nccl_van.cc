@@ -556,7 +556,7 @@ class NcclVan : public TcpVan {
 
 Van* CreateNcclVan(Postoffice* postoffice) {
   if (!NcclApi::Get()) return nullptr;
-  MemDomain* dom = CreateCudaDomain();
+  MemDomain* dom = CreateCudaDomain(postoffice ? postoffice->instance_idx() : 0);
   if (!dom) return nullptr;
   return new NcclVan(postoffice, dom);
 }

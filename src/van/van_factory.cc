@@ -27,7 +27,7 @@ Van* CreateVanByType(const std::string& type, Postoffice* postoffice) {
   if (type == "shm") return new OneSidedVan(postoffice, new ShmDomain(), "shm");
   if (type == "nvl" || type == "1" || type == "ibverbs" || type == "ucx" || type == "fabric") {
 #ifdef PS_USE_CUDA
-    MemDomain* dom = CreateCudaDomain();
+    MemDomain* dom = CreateCudaDomain(postoffice ? postoffice->instance_idx() : 0);
     CHECK(dom) << "van type '" << type << "' maps to the NVLink van, which needs a GPU";
     return new OneSidedVan(postoffice, dom, "nvl");
 #else
