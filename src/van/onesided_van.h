@@ -13,9 +13,11 @@
  *   RDMA WRITE of the payload    -> MemDomain::CopyAsync: an sm_100a kernel storing
  *                                   straight into peer HBM over NVLink, optionally
  *                                   fused with scale / bf16 cast / fp8 block quant
- *   WRITE_WITH_IMM of the meta   -> the descriptor (Meta with MemRef) sent on the
- *                                   TCP control channel *after* the copy's ticket
- *                                   completes, by the completion thread
+ *   WRITE_WITH_IMM of the meta   -> the descriptor (Meta with MemRef): same-host peers get
+ *                                   it in their shared-memory ring at once, GATED on a
+ *                                   completion word the copy itself stores (PollCQ = the
+ *                                   receiver polling that word); other peers get it over
+ *                                   TCP after the copy's ticket completes
  *   zero-copy pull               -> the pull request carries the MemRef of the
  *                                   worker's destination tensor; the server's copy
  *                                   kernel writes the values there
