@@ -85,4 +85,8 @@ clean:
 	rm -rf $(BUILD)
 
 -include $(CORE_OBJS:.o=.d)
-.PHONY: all check clean
+# API reference (needs doxygen; the prose documentation is docs/*.md)
+docs:
+	doxygen docs/Doxyfile
+
+.PHONY: all check clean docs
