@@ -46,7 +46,7 @@ CORE_OBJS := $(patsubst %.cc,$(BUILD)/%.o,$(CORE_SRCS))
 CU_OBJS := $(patsubst %.cu,$(BUILD)/%.o,$(CU_SRCS))
 LIB := $(BUILD)/libpslite.a
 
-APPS := $(BUILD)/kv_hello $(BUILD)/test_benchmark $(BUILD)/test_kv_app $(BUILD)/test_simple_app $(BUILD)/test_connection $(BUILD)/test_ipc_benchmark $(BUILD)/test_benchmark_stress $(BUILD)/test_recovery
+APPS := $(BUILD)/kv_hello $(BUILD)/test_benchmark $(BUILD)/test_kv_app $(BUILD)/test_simple_app $(BUILD)/test_connection $(BUILD)/test_ipc_benchmark $(BUILD)/test_benchmark_stress $(BUILD)/test_recovery $(BUILD)/test_foreign_host
 ifeq ($(USE_CUDA),1)
 APPS += $(BUILD)/kernel_bench $(BUILD)/engine_bench
 endif

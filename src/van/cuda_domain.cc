@@ -366,6 +366,23 @@ class CudaDomain : public MemDomain {
     return t;
   }
 
+  // Peers on another host cannot map HBM: their payloads are staged through host memory and
+  // travel in socket frames (the reference without GPUDirect does the same, src/ucx_van.h:1097-1115)
+  bool NeedsStaging(int device_type, const void* /*ptr*/) override { return device_type == GPU; }
+  void CopyToHost(void* host, const void* src, size_t n, void* wait_event) override {
+    PS_CUDA_CHECK(cudaSetDevice(dev_));
+    if (engine_) EngineQuiesce();
+    if (wait_event) PS_CUDA_CHECK(cudaStreamWaitEvent(stream_, static_cast<cudaEvent_t>(wait_event), 0));
+    PS_CUDA_CHECK(cudaMemcpyAsync(host, src, n, cudaMemcpyDeviceToHost, stream_));
+    PS_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  }
+  void CopyFromHost(void* dst, const void* host, size_t n) override {
+    PS_CUDA_CHECK(cudaSetDevice(dev_));
+    if (engine_) EngineQuiesce();
+    PS_CUDA_CHECK(cudaMemcpyAsync(dst, host, n, cudaMemcpyHostToDevice, stream_));
+    PS_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  }
+
   /*! \brief raw device-to-device items share launches (ps_launch_copy_multi), one event in all */
   Ticket CopyBatchAsync(const std::vector<CopyItem>& items) override {
     PS_CUDA_CHECK(cudaSetDevice(dev_));
@@ -784,6 +801,11 @@ class MultiCudaDomain : public MemDomain {
                    int src_device_type = UNK) override {
     return OwnerOf(src, -1)->CopyAsync(dst, src, n, codec, scale, wait_event, src_device_type);
   }
+  bool NeedsStaging(int device_type, const void* /*ptr*/) override { return device_type == GPU; }
+  void CopyToHost(void* host, const void* src, size_t n, void* wait_event) override {
+    OwnerOf(src, -1)->CopyToHost(host, src, n, wait_event);
+  }
+  void CopyFromHost(void* dst, const void* host, size_t n) override { OwnerOf(dst, -1)->CopyFromHost(dst, host, n); }
   void* MapSignalWord(void* page, size_t bytes, void* host_word) override {
     void* word = nullptr;
     for (auto& d : subs_) {

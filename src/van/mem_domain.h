@@ -89,6 +89,15 @@ class MemDomain {
   virtual const char* name() const = 0;
   /*! \brief true if values tagged (type, ptr) should travel one-sided through this domain */
   virtual bool Handles(int device_type, const void* ptr) = 0;
+  /*!
+   * \brief peers on ANOTHER host cannot map this domain's memory: their payloads travel in socket
+   *        frames. Must bytes at `ptr` be staged through host memory for that (device memory)?
+   */
+  virtual bool NeedsStaging(int /*device_type*/, const void* /*ptr*/) { return false; }
+  /*! \brief blocking copy of this domain's memory to plain host memory, after `wait_event` (may be null) */
+  virtual void CopyToHost(void* host, const void* src, size_t n, void* /*wait_event*/) { memcpy(host, src, n); }
+  /*! \brief blocking copy of plain host memory into this domain's memory */
+  virtual void CopyFromHost(void* dst, const void* host, size_t n) { memcpy(dst, host, n); }
   /*! \brief CUDA ordinal this domain is bound to, -1 for host domains */
   virtual int device() const { return -1; }
   /*! \brief allocate exportable memory (landing slots) */
@@ -312,6 +321,12 @@ class ShmDomain : public MemDomain {
   }
 
   bool Handles(int /*device_type*/, const void* ptr) override { return FindArena(ptr) != nullptr; }
+  /*! \brief PS_TEST_STAGE_ARENA=1: treat arena memory like device memory (exercises the staging of
+   *         the nvl van for peers on other hosts without a GPU) */
+  bool NeedsStaging(int /*device_type*/, const void* ptr) override {
+    static const bool pretend = GetEnv("PS_TEST_STAGE_ARENA", 0) != 0;
+    return pretend && FindArena(ptr) != nullptr;
+  }
 
   void* Alloc(size_t bytes) override {
     {

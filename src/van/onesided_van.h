@@ -40,6 +40,7 @@
 #include <set>
 #include <string>
 #include <thread>
+#include <tuple>
 #include <utility>
 #include <vector>
 
@@ -125,6 +126,18 @@ class OneSidedVan : public TcpVan {
         it = it->first == id ? announced_.erase(it) : std::next(it);
       }
     }
+    // a peer on another host cannot map our memory, nor we its: everything for it travels in frames
+    static const bool across = GetEnv("PS_ONESIDED_ACROSS_HOSTS", 0) != 0;  // (hosts sharing /dev/shm, for tests)
+    if (node.id != my_node_.id) {
+      const bool foreign = !across && !my_node_.hostname.empty() && node.hostname != my_node_.hostname;
+      std::lock_guard<SpinMutex> lk(rv_mu_);
+      if (foreign) {
+        foreign_.insert(node.id);
+        any_foreign_.store(true, std::memory_order_release);
+      } else {
+        foreign_.erase(node.id);
+      }
+    }
     TcpVan::Connect(node);
   }
 
@@ -200,6 +213,7 @@ class OneSidedVan : public TcpVan {
     out->emplace_back("onesided_copies", copies_.load());
     out->emplace_back("onesided_bytes", copy_bytes_.load());
     out->emplace_back("gated_frames", gated_frames_.load());
+    out->emplace_back("staged_copies", staged_copies_.load());
     out->emplace_back("recv_thread_sleeps", num_blocking_waits());
     out->emplace_back("deferred_sends", num_deferred_sends());
     out->emplace_back("engine_launches", launches);
@@ -222,6 +236,7 @@ class OneSidedVan : public TcpVan {
   int SendMsg(Message& msg) override {
     if (!msg.meta.control.empty() || msg.meta.simple_app) return TcpVan::SendMsg(msg);
     const bool has_vals = msg.data.size() >= 2 && msg.data[1].size() > 0;
+    if (any_foreign_.load(std::memory_order_acquire) && IsForeign(msg.meta.recver)) return SendToForeignHost(msg);
     if (msg.meta.request && msg.meta.push && has_vals &&
         domain_->Handles(msg.data[1].src_device_type_, msg.data[1].data())) {
       return SendPush(msg);
@@ -290,6 +305,9 @@ class OneSidedVan : public TcpVan {
       }
       if (msg->meta.control.empty() && !msg->meta.simple_app && msg->meta.mem.valid()) {
         RebuildPayload(msg);
+      } else if (any_foreign_.load(std::memory_order_acquire) && msg->meta.control.empty() &&
+                 !msg->meta.simple_app && !msg->meta.request && !msg->meta.push) {
+        LandForeignPull(msg);
       }
       return n;
     }
@@ -316,6 +334,85 @@ class OneSidedVan : public TcpVan {
       case INT64: case UINT64: case DOUBLE: return 8;
       default: return 1;
     }
+  }
+
+  // -- peers on other hosts: two-sided, device memory staged through the host ------------------
+
+  bool IsForeign(int node_id) {
+    std::lock_guard<SpinMutex> lk(rv_mu_);
+    return foreign_.count(node_id) > 0;
+  }
+
+  /*!
+   * \brief the peer lives on another host: nothing can be written into its memory. Values in
+   *        device memory are copied to the host and travel in the frame; the destination of a
+   *        pull that lies in device memory is remembered, the reply is copied into it on arrival
+   *        (LandForeignPull). The reference's vans do the same whenever the fabric cannot reach
+   *        the memory directly (ZMQ van for CPU tensors, UCX without GPUDirect).
+   */
+  int SendToForeignHost(Message& msg) {
+    msg.meta.mem = MemRef();
+    msg.meta.pull_mem = MemRef();
+    if (msg.meta.request) {
+      const bool fused = msg.meta.push && msg.meta.pull;
+      const uint64_t addr = fused ? msg.meta.pull_addr : (msg.meta.push ? 0 : msg.meta.addr);
+      // (a fused push-pull does not tag its destination: it lives where the pushed values live)
+      const int dev_type = fused && msg.data.size() >= 2 ? msg.data[1].src_device_type_ : msg.meta.src_dev_type;
+      const int dev_id = fused && msg.data.size() >= 2 ? msg.data[1].src_device_id_ : msg.meta.src_dev_id;
+      if (addr != 0 && domain_->NeedsStaging(dev_type, reinterpret_cast<void*>(addr))) {
+        const size_t esz = msg.meta.data_type.size() > 1 ? DataTypeSize(msg.meta.data_type[1]) : 1;
+        ForeignPull rec;
+        rec.addr = addr;
+        rec.bytes = static_cast<uint64_t>(fused ? msg.meta.pull_len : msg.meta.val_len) * esz;
+        rec.dev_type = dev_type;
+        rec.dev_id = dev_id;
+        {
+          std::lock_guard<SpinMutex> lk(rv_mu_);
+          if (foreign_pulls_.size() >= (1u << 16)) foreign_pulls_.erase(foreign_pulls_.begin());
+          foreign_pulls_[std::make_tuple(msg.meta.recver, msg.meta.app_id, msg.meta.customer_id,
+                                         msg.meta.timestamp)] = rec;
+        }
+        // the address means nothing over there, and no socket may land bytes at it over here
+        if (fused) msg.meta.pull_addr = 0; else msg.meta.addr = 0;
+      }
+    }
+    if (msg.data.size() >= 2 && msg.data[1].size() > 0 &&
+        domain_->NeedsStaging(msg.data[1].src_device_type_, msg.data[1].data())) {
+      const SArray<char>& dev = msg.data[1];
+      SArray<char> host(dev.size());
+      domain_->CopyToHost(host.data(), dev.data(), dev.size(), msg.wait_event);
+      host.src_device_type_ = CPU;
+      host.src_device_id_ = 0;
+      host.dst_device_type_ = dev.dst_device_type_;
+      host.dst_device_id_ = dev.dst_device_id_;
+      msg.data[1] = host;
+      msg.wait_event = nullptr;
+      ++staged_copies_;
+    }
+    if (!msg.meta.request && msg.meta.codec == kCodecPlaced) msg.meta.codec = kCodecRaw;
+    return Submit(msg, nullptr, false);
+  }
+
+  /*! \brief a pull reply from another host arrived in host memory: copy it to where the request wanted it */
+  void LandForeignPull(Message* msg) {
+    if (msg->data.size() < 2 || msg->data[1].size() == 0) return;
+    ForeignPull rec;
+    {
+      std::lock_guard<SpinMutex> lk(rv_mu_);
+      auto it = foreign_pulls_.find(std::make_tuple(msg->meta.sender, msg->meta.app_id, msg->meta.customer_id,
+                                                    msg->meta.timestamp));
+      if (it == foreign_pulls_.end()) return;
+      rec = it->second;
+      foreign_pulls_.erase(it);
+    }
+    const SArray<char>& got = msg->data[1];
+    CHECK_LE(got.size(), rec.bytes) << "pull reply larger than the destination it was requested for";
+    domain_->CopyFromHost(reinterpret_cast<void*>(rec.addr), got.data(), got.size());
+    SArray<char> placed;
+    placed.reset(reinterpret_cast<char*>(rec.addr), got.size(), [](char*) {}, static_cast<DeviceType>(rec.dev_type),
+                 rec.dev_id, static_cast<DeviceType>(rec.dev_type), rec.dev_id);
+    msg->data[1] = placed;
+    ++staged_copies_;
   }
 
   // -- region bookkeeping -----------------------------------------------------
@@ -862,6 +959,17 @@ class OneSidedVan : public TcpVan {
   std::map<uint64_t, int32_t> region_of_base_;
   std::map<std::pair<int, int32_t>, char*> peer_regions_;       // (peer, region) -> mapping
   std::set<std::pair<int, int32_t>> announced_;                 // (peer, my region) announced
+  /*! \brief peers on other hosts, the device destinations of pulls sent to them, staging copies made */
+  struct ForeignPull {
+    uint64_t addr = 0;
+    uint64_t bytes = 0;
+    int dev_type = UNK;
+    int dev_id = 0;
+  };
+  std::set<int> foreign_;
+  std::atomic<bool> any_foreign_{false};
+  std::map<std::tuple<int, int, int, int>, ForeignPull> foreign_pulls_;
+  std::atomic<uint64_t> staged_copies_{0};
 
   SpinMutex cq_mu_;
   std::condition_variable_any cq_cv_;

@@ -264,3 +264,22 @@ def test_dead_node_is_replaced_by_late_registration(built_native_tree, van):
     assert "test_recovery PASSED" in joined, joined[-4000:]
     assert "recovery worker adopted rank" in joined  # whichever rank the dead worker had
     assert all(p.returncode == 0 for p in procs), [p.returncode for p in procs]
+
+
+@pytest.mark.parametrize("staged", [0, 1])
+def test_onesided_van_with_a_peer_on_another_host(built_native_tree, staged):
+    """a peer whose host name differs cannot map memory: the one-sided van sends frames instead, and with
+    device-like memory (PS_TEST_STAGE_ARENA: the arena pretends to be HBM) stages through the host on both
+    ends; plain pull and fused push-pull must return the pushed bytes exactly"""
+    import re
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests", "helpers"))
+    from foreign_host import run_foreign_host
+
+    rcs, out = run_foreign_host({"PS_VAN_TYPE": "shm", "PS_TEST_STAGE_ARENA": staged})
+    assert rcs == [0, 0, 0], out[-3000:]
+    m = re.search(r"PASSED: one-sided copies (\d+), staged copies (\d+)", out)
+    assert m, out[-3000:]
+    assert int(m.group(1)) == 0  # nothing was written into the peer's memory
+    assert int(m.group(2)) == (4 if staged else 0)  # push, pull, and both halves of the push-pull
