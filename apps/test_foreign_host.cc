@@ -95,7 +95,9 @@ int main() {
   kv.Wait(kv.ZPush(keys, vals));
   kv.Wait(kv.ZPull(keys, &out));
   download(got, out);
-  for (int i = 0; i < n; ++i) CHECK_EQ(got[static_cast<size_t>(i)], pattern[static_cast<size_t>(i)]) << "pull, element " << i;
+  for (int i = 0; i < n; ++i) {
+    CHECK_EQ(got[static_cast<size_t>(i)], pattern[static_cast<size_t>(i)]) << "pull, element " << i;
+  }
   // fused push-pull: the store becomes 2 x pattern and comes back in the same reply
   kv.Wait(kv.ZPushPull(keys, vals, &out2));
   download(got, out2);
