@@ -186,6 +186,9 @@ GpuServer::~GpuServer() {
     be_->Free(kv.second.master);
     be_->Free(kv.second.m);
     be_->Free(kv.second.v);
+    for (void* p : kv.second.staged) {
+      if (p) be_->Free(p);
+    }
   }
 }
 
@@ -350,14 +353,31 @@ void GpuServer::HandleGrad(Shard* s, const KVMeta& req, const KVPairs<char>& dat
     fmt = PS_GRAD_MC_BF16;
     slot = static_cast<const char*>(mc_grad_base_) + req.mem.offset;
   } else {
-    if (be_->on_device()) {
-      CHECK(data.vals.on_gpu()) << "gradient pushes must arrive through a GPU van (nvl / nccl)";
-    } else {
+    slot = data.vals.data();
+    if (be_->on_device() && !data.vals.on_gpu()) {
+      // the gradient arrived in host memory: its worker sits on another host (the one-sided van sent a
+      // frame, staged through the host over there) or the transport is host-only. Upload it into a
+      // per-rank device buffer on the update stream; the round's kernel runs behind it.
+      const size_t bytes = data.vals.size();
+      if (s->staged.size() < static_cast<size_t>(cfg_.num_workers)) {
+        s->staged.resize(static_cast<size_t>(cfg_.num_workers), nullptr);
+        s->staged_cap.resize(static_cast<size_t>(cfg_.num_workers), 0);
+      }
+      if (s->staged_cap[rank] < bytes) {
+        if (s->staged[rank]) {
+          be_->Sync();  // (an earlier round may still read it)
+          be_->Free(s->staged[rank]);
+        }
+        s->staged[rank] = be_->Alloc(bytes + 16);
+        s->staged_cap[rank] = bytes;
+      }
+      be_->Upload(s->staged[rank], data.vals.data(), bytes);
+      slot = s->staged[rank];
+    } else if (!be_->on_device()) {
       CHECK(!data.vals.on_gpu()) << "this server keeps its shards in host memory";
       s->slot_refs[rank] = data.vals;  // a two-sided payload lives in a pooled receive buffer
     }
     fmt = FormatOf(req, cfg_.raw_grad_format);
-    slot = data.vals.data();
   }
   if (s->num_pushed == 0) s->grad_format = fmt;
   CHECK_EQ(s->grad_format, fmt) << "workers disagree on the gradient wire format";

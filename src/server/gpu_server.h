@@ -143,6 +143,8 @@ class GpuServer {
     int grad_format = PS_GRAD_BF16;
     std::vector<const void*> slots;      // per worker rank: landing slot of this round
     std::vector<SArray<char>> slot_refs; // host shards: keeps a two-sided payload alive until the round runs
+    std::vector<void*> staged;           // device shards: per rank, where a gradient that arrived in HOST memory
+    std::vector<size_t> staged_cap;      //   (worker on another host) is uploaded to; kept and reused
     std::vector<char> pushed;            // per worker rank: pushed in the open round
     int num_pushed = 0;
     std::vector<KVMeta> waiting_pulls;   // pulls of workers that already pushed this round
