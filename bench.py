@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark of pslite_b200 (driver contract: see the task statement).
 
-    python bench.py --gpus N --steps K --warmup W [--impl ours|reference] [--metric pushpull|llama]
+    python bench.py --gpus N --steps K --warmup W [--impl ours|reference] [--metric pushpull|llama|resnet]
 
 Default metric — the reference's own headline benchmark (tests/test_benchmark.cc,
 BASELINE.json "push+pull GB/s ... (test_benchmark)"): every worker ZPush-es and ZPull-s
@@ -15,7 +15,8 @@ formula (payload counted once per push+pull pair), in GB/s, summed over workers.
     --topology split : N/2 worker GPUs + N/2 server GPUs (4w+4s at N=8, BASELINE.json config 2)
 Values live in HBM and move as one-sided sm_100a copy kernels into peer memory; only
 descriptors use TCP. `--metric llama` instead times Llama-3-8B synchronous PS training
-(fp8 gradient push, fused server-side AdamW, bf16 pull) in tokens/s.
+(fp8 gradient push, fused server-side AdamW, bf16 pull) in tokens/s, `--metric resnet` ResNet-50
+(BASELINE.json config 3: ZPush gradients / ZPull parameters, fused server-side SGD) in images/s.
 
 `--impl reference` runs the UNMODIFIED reference build (baseline/_ref, ZMQ van — the
 only reference transport buildable without ibverbs/UCX) through its own test_benchmark
@@ -37,6 +38,7 @@ sys.path.insert(0, ROOT)
 METRIC_NAME = {
     "pushpull": "test_benchmark push+pull goodput",
     "llama": "Llama-3-8B PS training throughput",
+    "resnet": "ResNet-50 PS training throughput",
 }
 
 
@@ -48,7 +50,7 @@ def parse_args():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "nccl-ddp"],
                     help="nccl-ddp (with --metric llama): SECONDARY baseline, not the reference — the same model "
                          "trained with NCCL all-reduce of the gradients + torch.optim.AdamW(fused=True) on every rank")
-    ap.add_argument("--metric", default="pushpull", choices=["pushpull", "llama"])
+    ap.add_argument("--metric", default="pushpull", choices=["pushpull", "llama", "resnet"])
     ap.add_argument("--len", type=int, default=4096000, help="bytes per value (reference test.sh preset)")
     ap.add_argument("--keys-per-server", type=int, default=40)
     ap.add_argument("--topology", default=None, choices=[None, "joint", "split"])
@@ -68,7 +70,9 @@ def parse_args():
     ap.add_argument("--seq-len", type=int, default=8192)
     ap.add_argument("--micro-batch", type=int, default=1)
     ap.add_argument("--grad-wire", default="fp8", choices=["fp8", "bf16"])
-    ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "llama-1b", "tiny"])
+    ap.add_argument("--model", default="llama3-8b", choices=["llama3-8b", "llama-1b", "tiny"],
+                    help="llama: which size; resnet: 'tiny' selects the smoke-test network, anything else ResNet-50")
+    ap.add_argument("--image-batch", type=int, default=128, help="resnet: images per worker and step (224 x 224)")
     ap.add_argument("--ckpt-layers", type=int, default=-1)
     ap.add_argument("--attn-backend", default="auto", choices=["auto", "cudnn", "flash", "efficient", "math"])
     ap.add_argument("--lazy-wait", action="store_true",
@@ -554,6 +558,114 @@ def run_llama(args, dist: Dist) -> dict:
 
 
 # ----------------------------------------------------------------------------------------
+# ours: ResNet-50 PS training (BASELINE.json config 3)
+# ----------------------------------------------------------------------------------------
+def run_resnet(args, dist: Dist) -> dict:
+    """ResNet-50, bf16, channels-last, synchronous data parallelism through the parameter server: every
+    worker pushes its gradients (KVWorker ZPush, bf16 or block-scaled fp8 on the wire), the servers run the
+    fused sum + SGD update on their key ranges and the workers pull the new parameters (ZPull). Convolutions
+    are cuDNN's; what this repo contributes to the step is the gradient / parameter traffic and the update.
+    BatchNorm statistics stay worker-local."""
+    import torch
+
+    from pslite_b200 import native
+    from pslite_b200.models.resnet import resnet50, resnet_tiny
+    from pslite_b200.parallel.launch import init_ps
+    from pslite_b200.parallel.ps_trainer import PSWorkerOptimizer
+    from pslite_b200.utils.timing import ClockSampler
+
+    C = native()
+    gpu = Gpu(args, dist.local_rank)
+    dev = gpu.dev
+    topo = args.topology or "joint"
+    ctx = init_ps(topo, van=args.van or ("nvl" if gpu.cuda else "shm"))
+    W, S = ctx.num_workers, ctx.num_servers
+    server = None
+    if ctx.is_server:
+        server = C.GpuServer(0, num_workers=W, optimizer="sgd", lr=0.1, weight_decay=1e-4, grad_scale=1.0 / W,
+                             fuse_pull=True)
+    tiny = args.model == "tiny"
+    B = args.image_batch if not tiny else min(args.image_batch, 4)
+    side = 224 if not tiny else 32
+    classes = 1000 if not tiny else 10
+    model = opt = None
+    if ctx.is_worker:
+        with torch.device(dev):
+            model = (resnet_tiny(classes) if tiny else resnet50(classes)).to(torch.bfloat16)
+        # (weights stay in the default layout — the PS moves them as flat contiguous buffers; activations are
+        #  channels-last, so cuDNN runs its NHWC kernels and re-lays the 25 M weights out itself)
+        model.train()
+        kv = C.KVWorker(0, 0)
+        opt = PSWorkerOptimizer(model.parameters(), kv, S, W, ctx.worker_rank, grad_wire=args.grad_wire,
+                                fused_pushpull=args.fused_pushpull).attach()
+        opt.init_parameters(barrier=lambda: C.barrier(0, C.WORKER_GROUP, "worker"))
+    dist.barrier()
+    g = torch.Generator().manual_seed(4321 + dist.rank)
+    host_img = gpu.pinned(torch.randn(B, 3, side, side, generator=g).to(torch.bfloat16))
+    host_lbl = gpu.pinned(torch.randint(0, classes, (B,), generator=g))
+    loss_fn = torch.nn.CrossEntropyLoss()
+
+    def step(e2e: bool):
+        if e2e:
+            img = host_img.to(dev, non_blocking=True).contiguous(memory_format=torch.channels_last)
+            lbl = host_lbl.to(dev, non_blocking=True)
+        else:
+            img, lbl = step.dev
+        loss = loss_fn(model(img).float(), lbl)
+        loss.backward()
+        opt.step()
+        return loss.item() if e2e else loss
+
+    if ctx.is_worker:
+        step.dev = (host_img.to(dev).contiguous(memory_format=torch.channels_last), host_lbl.to(dev))
+
+    def timed(fn, steps):
+        dist.barrier()
+        gpu.sync()
+        l0 = C.kernel_launch_count()
+        stop = gpu.timer()
+        if ctx.is_worker:
+            for _ in range(steps):
+                fn()
+            opt.wait_all()
+        gpu.sync()
+        ms = stop()
+        dist.barrier()
+        return dist.reduce(ms, "max"), dist.reduce(float(C.kernel_launch_count() - l0), "sum")
+
+    if ctx.is_worker:
+        for _ in range(args.warmup):
+            step(False)
+    sampler = ClockSampler(dist.local_rank).start() if dist.rank == 0 and gpu.cuda else None
+    ms, launches = timed(lambda: step(False), args.steps)
+    clocks = sampler.stop() if sampler else None
+    images = B * W
+    value = images * args.steps / (ms * 1e-3)
+    e2e = None
+    if not args.no_e2e:
+        k = max(2, args.steps // 2)
+        ms2, _ = timed(lambda: step(True), k)
+        e2e = {"value": images * k / (ms2 * 1e-3), "unit": "images/s",
+               "h2d_bytes_per_step": int(host_img.numel() * host_img.element_size()
+                                         + host_lbl.numel() * host_lbl.element_size()) * W,
+               "d2h_bytes_per_step": 4 * W, "steps": k}
+    params = sum(p.numel() for p in model.parameters()) if model is not None else None
+    stats = {"server_updates": server.num_updates() if server else 0,
+             "server_fused_fanouts": server.num_fused_fanouts() if server else 0}
+    ctx.shutdown()
+    return {
+        "metric": METRIC_NAME["resnet"], "value": value, "unit": "images/s",
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16", "data": "synthetic images, random-init weights",
+        "config": {"model": "resnet-tiny" if tiny else "resnet50", "params": params, "global_batch": B * W,
+                   "seq_len": side,
+                   "parallelism": f"ps-dp{W} ({W}w+{S}s {topo}), grad wire {args.grad_wire}, server SGD",
+                   "l2": "activations of a step >> 126 MB L2"},
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "server": stats,
+    }
+
+
+# ----------------------------------------------------------------------------------------
 # secondary baseline: NCCL data parallelism (NOT the reference — it has no trainer)
 # ----------------------------------------------------------------------------------------
 def run_llama_ddp(args, dist: Dist) -> dict:
@@ -730,6 +842,8 @@ def main():
         out = run_llama_ddp(args, dist)
     elif args.metric == "llama":
         out = run_llama(args, dist)
+    elif args.metric == "resnet":
+        out = run_resnet(args, dist)
     else:
         out = run_pushpull(args, dist)
     if dist.rank == 0 and out is not None:

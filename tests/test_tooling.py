@@ -79,7 +79,8 @@ REQUIRED_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per
 
 
 @pytest.mark.parametrize("extra", [["--e2e-native", "--fused-pushpull"],
-                                   ["--metric", "llama", "--model", "tiny", "--seq-len", "64"]])
+                                   ["--metric", "llama", "--model", "tiny", "--seq-len", "64"],
+                                   ["--metric", "resnet", "--model", "tiny", "--image-batch", "2"]])
 def test_bench_script_control_flow_on_cpu(extra):
     """bench.py --device cpu walks the same code as a GPU run (warm-up, timed region, end-to-end
     pass, JSON line) over the shm van and the host engine: a typo in the script must not wait for
