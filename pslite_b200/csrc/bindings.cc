@@ -385,6 +385,10 @@ class PyBenchServer {
             slot.keys.CopyFrom(d.keys);
             slot.lens.CopyFrom(d.lens);
             slot.vals = d.vals;
+          } else if (it->second.vals.data() != d.vals.data()) {
+            // a one-sided push lands in the same slot every time (nothing to do); a push that travelled
+            // in a frame (TCP van, peer on another host) arrives in a fresh buffer: the newest one is the value
+            it->second.vals = d.vals;
           }
         }
         ++pushes_;

@@ -142,6 +142,10 @@ def init_ps(topology: str = "joint", van: str | None = None, extra_env: dict | N
     single_node = int(os.environ.get("LOCAL_WORLD_SIZE", str(world))) >= world
     if single_node:
         env["DMLC_NODE_HOST"] = "127.0.0.1"
+        if os.environ.get("PS_TEST_HOST_PER_RANK"):
+            # tests: every rank announces another loopback address, so the vans take the other ranks for
+            # other hosts (frames instead of one-sided writes, device values staged through the host)
+            env["DMLC_NODE_HOST"] = f"127.0.0.{rank + 1}"
     elif os.environ.get("DMLC_NODE_HOST"):
         env["DMLC_NODE_HOST"] = os.environ["DMLC_NODE_HOST"]
     if van == "nvl":

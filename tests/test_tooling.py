@@ -119,6 +119,25 @@ def test_bench_script_multi_process_on_cpu():
     assert line["config"]["num_workers"] == 2 and line["config"]["num_servers"] == 2 and line["value"] > 0
 
 
+def test_bench_script_across_hosts_on_cpu():
+    """two ranks that take each other for different hosts: half of the keys move one-sidedly (own server),
+    the other half in socket frames with the values staged through the host; bench.py's own data check
+    (every pulled byte compared with what was pushed) must hold on both halves"""
+    from pslite_b200.utils.env import free_port
+
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", str(free_port()), os.path.join(ROOT, "bench.py"), "--device", "cpu",
+           "--gpus", "2", "--steps", "3", "--warmup", "3", "--len", "65536", "--keys-per-server", "4"]
+    env = dict(os.environ, PSLITE_NO_AUTOBUILD="1", CUDA_VISIBLE_DEVICES="", OMP_NUM_THREADS="1",
+               PS_TEST_HOST_PER_RANK="1", PS_TEST_STAGE_ARENA="1")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, cwd=ROOT, env=env)
+    assert r.returncode == 0, (r.stdout + r.stderr)[-3000:]
+    line = json.loads([l for l in r.stdout.strip().splitlines() if l.startswith("{")][-1])
+    stats = line["van_stats_rank0"]["worker"]
+    assert stats["staged_copies"] > 0 and stats["onesided_copies"] > 0, stats
+    assert line["value"] > 0 and line["e2e"]["value"] > 0
+
+
 def test_native_initialises_torch_first():
     """the extension hands tensors to Python: loading it without the torch package crashed later"""
     code = "import sys; import pslite_b200; pslite_b200.native(); assert 'torch' in sys.modules; print('ok')"

@@ -82,6 +82,17 @@ def test_all_transport_options_keep_the_loss_curve(native):
 
 
 @pytest.mark.timeout(300)
+def test_ranks_on_different_hosts_keep_the_loss_curve(native):
+    """every rank announces another host name (and the arena pretends to be device memory): each worker
+    reaches its own server one-sidedly and the three others through socket frames, gradients staged and
+    fp8-encoded on the host, pull replies copied into the parameters on arrival — the numbers must be those
+    of the run in which everybody shares a host"""
+    plain = _run_cached(4, "joint", "fp8", 5, **PLAIN)
+    spread = _run(4, "joint", "fp8", 5, PS_TEST_HOST_PER_RANK=1, PS_TEST_STAGE_ARENA=1, **PLAIN)
+    assert _curve(plain) == _curve(spread)
+
+
+@pytest.mark.timeout(300)
 def test_split_topology_and_remote_learning_rate_control(native):
     """dedicated server processes (2 workers + 2 servers, bf16 wire); opt.set_lr() reaches them
     (CMD_SET_LR): with the rate set to 0 after step 3 the parameters — and, on a fixed batch,
