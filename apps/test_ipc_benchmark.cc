@@ -111,6 +111,7 @@ int main(int argc, char* argv[]) {
       res = store.at(key);
       nth = pulls_served[key]++;
     }
+    (void)nth;  // (only the multicast path of a CUDA build looks at it)
 #if PS_USE_CUDA
     if (mc_pull && gpu && req.mem.region == kSymmetricRegion) {
       // the first pull of a round publishes the value to ALL workers with one multimem.st stream;
