@@ -72,7 +72,7 @@ def bind_to_gpu_numa_node(device_index: int) -> list[int] | None:
     helpers) to the CPUs of the NUMA node the GPU hangs off, so that pinned host buffers are first-touched
     on that node and host<->device copies do not cross the socket interconnect. Eight ranks started by
     torchrun otherwise land on arbitrary CPUs. Returns the CPU list, or None if nothing was changed
-    (no sysfs entry, a node with fewer than 4 CPUs, PS_NUMA_BIND=0)."""
+    (no sysfs entry, a node with fewer than 8 CPUs, PS_NUMA_BIND=0)."""
     if os.environ.get("PS_NUMA_BIND", "1") == "0":
         return None
     try:
@@ -92,8 +92,10 @@ def bind_to_gpu_numa_node(device_index: int) -> list[int] | None:
             cpus.extend(range(int(lo), int(hi or lo) + 1))
         allowed = os.sched_getaffinity(0)
         cpus = [c for c in cpus if c in allowed]
-        if len(cpus) < 4 or len(cpus) >= len(allowed):
-            return None  # no NUMA information worth acting on (or already bound)
+        if len(cpus) < 8 or len(cpus) >= len(allowed):
+            # no NUMA information worth acting on (or already bound); a rank keeps three threads busy (the
+            # issuing thread and one receive thread per van), so a node with a handful of CPUs is no home
+            return None
         os.sched_setaffinity(0, cpus)
         return cpus
     except Exception:  # a missing attribute / sysfs file must never stop a job
