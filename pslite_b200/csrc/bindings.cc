@@ -26,6 +26,7 @@
 #include "kernels/host_kernels.h"
 #include "kernels/ps_kernels.h"
 #include "ps/ps.h"
+#include "ps/simple_app.h"
 #include "server/gpu_server.h"
 #include "van/mem_domain.h"
 
@@ -368,6 +369,59 @@ class PyKVServer {
 };
 
 /*!
+ * \brief SimpleApp from Python: small control messages (an int head and a byte-string body) between
+ *        any two nodes, with handlers written in Python. `role` picks the postoffice of a joint process
+ *        ("worker" / "server"); ids and groups are the reference's (kScheduler 1, kServerGroup 2,
+ *        kWorkerGroup 4, or a node id). As in the reference, a server (and the scheduler) finds the
+ *        customer of an incoming request by its APP id: create server-side apps with customer_id == app_id.
+ */
+class PySimpleApp {
+ public:
+  PySimpleApp(int app_id, int customer_id, const std::string& role) {
+    Postoffice* po = role == "server" ? Postoffice::GetServer() : (role == "worker" ? Postoffice::GetWorker()
+                                                                                      : Postoffice::Get());
+    app_.reset(new SimpleApp(app_id, customer_id, po));
+  }
+  ~PySimpleApp() {
+    py::gil_scoped_release nogil;
+    app_.reset();
+  }
+  int request(int head, const std::string& body, int recv_id) {
+    py::gil_scoped_release nogil;
+    return app_->Request(head, body, recv_id);
+  }
+  void wait(int timestamp) {
+    py::gil_scoped_release nogil;
+    app_->Wait(timestamp);
+  }
+  /*! \brief handler(head, body: bytes, sender, timestamp) -> None | bytes | str (the body of the reply) */
+  void set_request_handle(py::function fn) {
+    on_request_ = fn;
+    app_->set_request_handle([this](const SimpleData& req, SimpleApp* app) {
+      std::string reply;
+      {
+        py::gil_scoped_acquire gil;
+        py::object r = on_request_(req.head, py::bytes(req.body), req.sender, req.timestamp);
+        if (!r.is_none()) reply = r.cast<std::string>();
+      }
+      app->Response(req, reply);
+    });
+  }
+  /*! \brief handler(head, body: bytes, sender, timestamp) for every response that arrives */
+  void set_response_handle(py::function fn) {
+    on_response_ = fn;
+    app_->set_response_handle([this](const SimpleData& res, SimpleApp*) {
+      py::gil_scoped_acquire gil;
+      on_response_(res.head, py::bytes(res.body), res.sender, res.timestamp);
+    });
+  }
+
+ private:
+  std::unique_ptr<SimpleApp> app_;
+  py::function on_request_, on_response_;
+};
+
+/*!
  * \brief native twin of test_benchmark's server: the first push of a key becomes its
  *        store (the landing slot itself), pulls are answered from the store.
  */
@@ -670,6 +724,14 @@ PYBIND11_MODULE(_C, m) {
       .def(py::init<int>(), py::arg("app_id") = 0)
       .def("set_request_handle", &PyKVServer::set_request_handle)
       .def("response", &PyKVServer::response, py::arg("id"), py::arg("vals") = py::none());
+
+  py::class_<PySimpleApp>(m, "SimpleApp")
+      .def(py::init<int, int, const std::string&>(), py::arg("app_id") = 0, py::arg("customer_id") = 0,
+           py::arg("role") = "")
+      .def("request", &PySimpleApp::request, py::arg("head"), py::arg("body") = "", py::arg("recv_id") = 2)
+      .def("wait", &PySimpleApp::wait)
+      .def("set_request_handle", &PySimpleApp::set_request_handle)
+      .def("set_response_handle", &PySimpleApp::set_response_handle);
 
   py::class_<PyBenchServer>(m, "BenchServer")
       .def(py::init<int>(), py::arg("app_id") = 0)

@@ -36,6 +36,9 @@ def main():
                 srv.response(meta["id"], store[key].view(torch.uint8))
 
         srv.set_request_handle(handle)
+        # control messages next to the KV traffic: reply with the reversed body
+        ctl = C.SimpleApp(7, 7)  # on servers a customer is found by its app id (as in the reference)
+        ctl.set_request_handle(lambda head, body, sender, ts: body[::-1] if head == 3 else None)
         C.finalize(0, role, True)
         return
     if role == "worker":
@@ -61,6 +64,19 @@ def main():
                 ok = False
                 print(f"worker {rank}: key {i} mismatch {out[:4]} vs {expect[:4]}", flush=True)
             C.barrier(0, C.WORKER_GROUP, "worker")
+        # SimpleApp: one request to every server, each answers with the reversed body
+        ctl = C.SimpleApp(7, 1)
+        answers = []
+        ctl.set_response_handle(lambda head, body, sender, ts: answers.append((head, body, sender)))
+        ctl.wait(ctl.request(3, f"hello from {rank}", C.SERVER_GROUP))
+        want = f"hello from {rank}"[::-1].encode()
+        if len(answers) != ns or any(h != 3 or b != want for h, b, _ in answers):
+            ok = False
+            print(f"worker {rank}: SimpleApp answers {answers}", flush=True)
+        ctl.wait(ctl.request(4, "", C.SERVER_GROUP))  # a handler that returns None: empty reply
+        if len(answers) != 2 * ns or answers[-1][1] != b"":
+            ok = False
+            print(f"worker {rank}: SimpleApp empty answers {answers}", flush=True)
         print(f"worker {rank}: {'PASS' if ok else 'FAIL'}", flush=True)
         C.finalize(0, role, True)
         sys.exit(0 if ok else 1)
