@@ -592,8 +592,9 @@ def run_resnet(args, dist: Dist) -> dict:
     if ctx.is_worker:
         with torch.device(dev):
             model = (resnet_tiny(classes) if tiny else resnet50(classes)).to(torch.bfloat16)
-        # (weights stay in the default layout — the PS moves them as flat contiguous buffers; activations are
-        #  channels-last, so cuDNN runs its NHWC kernels and re-lays the 25 M weights out itself)
+        # weights and activations channels-last (cuDNN's NHWC kernels); the PS moves a weight as the flat buffer
+        # of its storage, whatever the order of the dimensions in it
+        model = model.to(memory_format=torch.channels_last)
         model.train()
         kv = C.KVWorker(0, 0)
         opt = PSWorkerOptimizer(model.parameters(), kv, S, W, ctx.worker_rank, grad_wire=args.grad_wire,

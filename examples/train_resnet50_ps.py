@@ -55,11 +55,8 @@ def main():
     if ctx.is_worker:
         model = (resnet_tiny() if args.tiny else resnet50()).to(dev).to(torch.bfloat16)
         model = model.to(memory_format=torch.channels_last)
-        # PS keys need contiguous storage; channels_last conv weights are contiguous in that format
+        # (channels-last weights are dense: the PS moves each as the flat buffer of its storage)
         params = [p for p in model.parameters()]
-        for p in params:
-            if not p.is_contiguous():
-                p.data = p.data.contiguous()
         kv = C.KVWorker(0, 0)
         opt = PSWorkerOptimizer(params, kv, S, W, ctx.worker_rank, grad_wire=args.grad_wire,
                                 chunk_elems=4 << 20).attach()

@@ -129,6 +129,18 @@ def setup_symmetric_grads(total_elems: int, group, device, role: str = "worker")
     return flat, hdl, mc, total_elems * 2
 
 
+def _flat(t: torch.Tensor) -> torch.Tensor:
+    """The parameter (or gradient) as the 1-D buffer that travels: a view of its storage in STORAGE order.
+    Contiguous tensors are the usual case; channels-last convolution weights are dense but permuted, and
+    their storage order is as good a wire order as any — as long as gradient and parameter agree on it."""
+    if t.is_contiguous():
+        return t.view(-1)
+    dense = (t.dim() == 4 and t.is_contiguous(memory_format=torch.channels_last)) or \
+            (t.dim() == 5 and t.is_contiguous(memory_format=torch.channels_last_3d))
+    assert dense, "PS parameters must be dense (contiguous or channels-last)"
+    return t.as_strided((t.numel(),), (1,), t.storage_offset())
+
+
 class PSWorkerOptimizer:
     """Drop-in "optimizer" for a worker: hooks gradients, exposes step()/zero_grad()."""
 
@@ -171,7 +183,7 @@ class PSWorkerOptimizer:
         self.chunks: list[list[_Chunk]] = []
         j = 0
         for i, p in enumerate(self.params):
-            assert p.is_contiguous(), "PS parameters must be contiguous"
+            _flat(p.data)  # (asserts that the parameter is dense)
             per = []
             n = p.numel()
             for a in range(0, n, chunk_elems):
@@ -200,7 +212,7 @@ class PSWorkerOptimizer:
         if self.rank == 0:
             ts = []
             for p, per in zip(self.params, self.chunks):
-                flat = p.data.view(-1)
+                flat = _flat(p.data)
                 cmd = C.CMD_INIT_F32 if p.dtype == torch.float32 else C.CMD_INIT_BF16
                 opt_bits = C.INIT_NO_WEIGHT_DECAY if (self.no_decay_1d and p.dim() <= 1) else 0
                 for c in per:
@@ -211,7 +223,7 @@ class PSWorkerOptimizer:
         ts = []
         for p, per in zip(self.params, self.chunks):
             assert p.dtype == torch.bfloat16, "servers emit bf16 parameters"
-            flat = p.data.view(-1)
+            flat = _flat(p.data)
             for c in per:
                 ts.append(self.kv.pull(c.key, flat[c.start:c.stop], symm_offset=self._symm(c)))
         for t in ts:
@@ -279,10 +291,14 @@ class PSWorkerOptimizer:
         self._push_pull_now(i, g)
 
     def _push_pull_now(self, i: int, g: torch.Tensor):
-        if not g.is_contiguous():
-            g = g.contiguous()
-        gflat = g.view(-1)
-        pflat = self.params[i].data.view(-1)
+        p = self.params[i].data
+        if p.is_contiguous():
+            if not g.is_contiguous():
+                g = g.contiguous()
+        elif g.stride() != p.stride():
+            g = torch.empty_like(p, dtype=g.dtype).copy_(g)  # the parameter's (dense, permuted) layout
+        gflat = _flat(g)
+        pflat = _flat(p)
         codec = self._codec(g)
         for c in self.chunks[i]:
             gs = gflat[c.start:c.stop]

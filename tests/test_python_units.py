@@ -1,4 +1,5 @@
 """Pure-Python / CPU unit tests: model definitions, op references, trainer bookkeeping."""
+import pytest
 import torch
 
 from pslite_b200.models.llama import Llama, LlamaConfig, apply_rope, precompute_rope
@@ -80,3 +81,23 @@ def test_symmetric_layout_alignment():
     offs, total = symmetric_layout(params)
     assert offs == [0, 64, 128] and total == 128 + 320
     assert all(o % 64 == 0 for o in offs)  # 128-byte aligned bf16 offsets
+
+
+def test_trainer_flat_view_of_channels_last_parameters():
+    """the PS moves a parameter as the flat buffer of its storage: for a channels-last convolution weight that
+    is a permuted order, and a gradient that arrives in another layout must be brought into the same one"""
+    from pslite_b200.parallel.ps_trainer import _flat
+
+    w = torch.arange(2 * 3 * 2 * 2, dtype=torch.float32).reshape(2, 3, 2, 2).contiguous(memory_format=torch.channels_last)
+    f = _flat(w)
+    assert f.numel() == w.numel() and f.data_ptr() == w.data_ptr() and f.is_contiguous()
+    assert torch.equal(f, w.permute(0, 2, 3, 1).reshape(-1))          # storage order: N, H, W, C
+    g = torch.randn(2, 3, 2, 2)                                        # a gradient in the default layout
+    g2 = torch.empty_like(w).copy_(g)
+    assert g2.stride() == w.stride()
+    _flat(w).copy_(_flat(g2))                                          # what a pull does with the server's answer
+    assert torch.equal(w, g)
+    c = torch.randn(4, 5)
+    assert _flat(c).data_ptr() == c.data_ptr() and _flat(c).shape == (20,)
+    with pytest.raises(AssertionError):
+        _flat(torch.randn(4, 6)[:, ::2])                               # not dense: cannot be a PS parameter
