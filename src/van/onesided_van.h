@@ -128,6 +128,9 @@ class OneSidedVan : public TcpVan {
     }
     // a peer on another host cannot map our memory, nor we its: everything for it travels in frames
     static const bool across = GetEnv("PS_ONESIDED_ACROSS_HOSTS", 0) != 0;  // (hosts sharing /dev/shm, for tests)
+    if (node.id >= 0 && static_cast<size_t>(node.id) < kNegotiated) {
+      negotiated_[node.id].store(false, std::memory_order_release);
+    }
     if (node.id != my_node_.id) {
       const bool foreign = !across && !my_node_.hostname.empty() && node.hostname != my_node_.hostname;
       std::lock_guard<SpinMutex> lk(rv_mu_);
@@ -236,7 +239,8 @@ class OneSidedVan : public TcpVan {
   int SendMsg(Message& msg) override {
     if (!msg.meta.control.empty() || msg.meta.simple_app) return TcpVan::SendMsg(msg);
     const bool has_vals = msg.data.size() >= 2 && msg.data[1].size() > 0;
-    if (any_foreign_.load(std::memory_order_acquire) && IsForeign(msg.meta.recver)) return SendToForeignHost(msg);
+    AwaitNegotiation(msg.meta.recver);
+    if (any_foreign_.load(std::memory_order_acquire) && IsForeign(msg.meta.recver)) return SendTwoSided(msg, true);
     if (msg.meta.request && msg.meta.push && has_vals &&
         domain_->Handles(msg.data[1].src_device_type_, msg.data[1].data())) {
       return SendPush(msg);
@@ -245,7 +249,8 @@ class OneSidedVan : public TcpVan {
         domain_->Handles(msg.meta.src_dev_type, reinterpret_cast<void*>(msg.meta.addr))) {
       // a caller-named destination (symmetric buffer) needs no export / announcement
       if (!msg.meta.mem.valid()) AttachPullDestination(&msg);
-      return Submit(msg, nullptr, false);
+      if (msg.meta.mem.valid()) return Submit(msg, nullptr, false);
+      return SendTwoSided(msg, false);  // memory that cannot be exported: the reply comes in a frame
     }
     if (!msg.meta.request && !msg.meta.push && msg.meta.mem.valid() && has_vals) {
       if (msg.meta.codec == kCodecPlaced) return SendPlacedResponse(msg);
@@ -269,7 +274,8 @@ class OneSidedVan : public TcpVan {
       gate.wait_event = msg.wait_event;
       return Submit(msg, &gate, true);
     }
-    return Submit(msg, nullptr, false);
+    // whatever is left travels two-sided: device memory cannot ride in a frame, nor receive one
+    return SendTwoSided(msg, false);
   }
 
   /*! \brief a descriptor handed over in-process still has to be turned into its payload view */
@@ -305,9 +311,9 @@ class OneSidedVan : public TcpVan {
       }
       if (msg->meta.control.empty() && !msg->meta.simple_app && msg->meta.mem.valid()) {
         RebuildPayload(msg);
-      } else if (any_foreign_.load(std::memory_order_acquire) && msg->meta.control.empty() &&
+      } else if (staged_pulls_pending_.load(std::memory_order_acquire) > 0 && msg->meta.control.empty() &&
                  !msg->meta.simple_app && !msg->meta.request && !msg->meta.push) {
-        LandForeignPull(msg);
+        LandStagedPull(msg);
       }
       return n;
     }
@@ -338,41 +344,75 @@ class OneSidedVan : public TcpVan {
 
   // -- peers on other hosts: two-sided, device memory staged through the host ------------------
 
+  /*! \brief a same-host peer could not map our ring, or we could not map its ring: no shared memory */
+  void OnPipeVerdict(int peer_id, bool accepted) override {
+    if (accepted) return;
+    std::lock_guard<SpinMutex> lk(rv_mu_);
+    foreign_.insert(peer_id);
+    any_foreign_.store(true, std::memory_order_release);
+  }
+
+  /*!
+   * \brief before the first data message for a peer: wait until the ring negotiation with it has a
+   *        verdict (milliseconds at start-up; bounded, because a peer configured without rings never
+   *        offers one). Afterwards `foreign_` says whether the peer shares memory with us.
+   */
+  void AwaitNegotiation(int recver) {
+    const size_t slot = static_cast<size_t>(recver);
+    if (slot < kNegotiated && negotiated_[slot].load(std::memory_order_acquire)) return;
+    // the receive thread is the one that processes offers and answers: it cannot wait for them. What it
+    // sends are replies, and a reply that cannot travel one-sidedly is staged into a frame (SendTwoSided).
+    if (OnReceiveThread()) return;
+    static const int limit_ms = GetEnv("PS_NEGOTIATION_TIMEOUT_MS", 3000);
+    const auto deadline = std::chrono::steady_clock::now() + std::chrono::milliseconds(limit_ms);
+    while (NegotiationOpen(recver) && std::chrono::steady_clock::now() < deadline) {
+      std::this_thread::sleep_for(std::chrono::microseconds(200));
+    }
+    if (slot < kNegotiated) negotiated_[slot].store(true, std::memory_order_release);
+  }
+
   bool IsForeign(int node_id) {
     std::lock_guard<SpinMutex> lk(rv_mu_);
     return foreign_.count(node_id) > 0;
   }
 
   /*!
-   * \brief the peer lives on another host: nothing can be written into its memory. Values in
-   *        device memory are copied to the host and travel in the frame; the destination of a
-   *        pull that lies in device memory is remembered, the reply is copied into it on arrival
-   *        (LandForeignPull). The reference's vans do the same whenever the fabric cannot reach
-   *        the memory directly (ZMQ van for CPU tensors, UCX without GPUDirect).
+   * \brief send `msg` two-sided (its payload inside the frame): the peer lives on another host
+   *        (`foreign`: nothing can be written into its memory, every MemRef is dropped), or this
+   *        particular message cannot go one-sidedly (memory that cannot be exported, a request that
+   *        named no destination). Values in device memory are copied to the host first; the
+   *        destination of a pull that lies in device memory and is not described by a MemRef is
+   *        remembered, and the reply is copied into it on arrival (LandStagedPull). The reference's
+   *        vans do the same whenever the fabric cannot reach the memory (ZMQ van for CPU tensors,
+   *        UCX without GPUDirect).
    */
-  int SendToForeignHost(Message& msg) {
-    msg.meta.mem = MemRef();
-    msg.meta.pull_mem = MemRef();
+  int SendTwoSided(Message& msg, bool foreign) {
+    if (foreign) {
+      msg.meta.mem = MemRef();
+      msg.meta.pull_mem = MemRef();
+    }
     if (msg.meta.request) {
       const bool fused = msg.meta.push && msg.meta.pull;
+      const bool described = fused ? msg.meta.pull_mem.valid() : msg.meta.mem.valid();
       const uint64_t addr = fused ? msg.meta.pull_addr : (msg.meta.push ? 0 : msg.meta.addr);
       // (a fused push-pull does not tag its destination: it lives where the pushed values live)
       const int dev_type = fused && msg.data.size() >= 2 ? msg.data[1].src_device_type_ : msg.meta.src_dev_type;
       const int dev_id = fused && msg.data.size() >= 2 ? msg.data[1].src_device_id_ : msg.meta.src_dev_id;
-      if (addr != 0 && domain_->NeedsStaging(dev_type, reinterpret_cast<void*>(addr))) {
+      if (!described && addr != 0 && domain_->NeedsStaging(dev_type, reinterpret_cast<void*>(addr))) {
         const size_t esz = msg.meta.data_type.size() > 1 ? DataTypeSize(msg.meta.data_type[1]) : 1;
-        ForeignPull rec;
+        StagedPull rec;
         rec.addr = addr;
         rec.bytes = static_cast<uint64_t>(fused ? msg.meta.pull_len : msg.meta.val_len) * esz;
         rec.dev_type = dev_type;
         rec.dev_id = dev_id;
         {
           std::lock_guard<SpinMutex> lk(rv_mu_);
-          if (foreign_pulls_.size() >= (1u << 16)) foreign_pulls_.erase(foreign_pulls_.begin());
-          foreign_pulls_[std::make_tuple(msg.meta.recver, msg.meta.app_id, msg.meta.customer_id,
-                                         msg.meta.timestamp)] = rec;
+          if (staged_pulls_.size() >= (1u << 16)) staged_pulls_.erase(staged_pulls_.begin());
+          staged_pulls_[std::make_tuple(msg.meta.recver, msg.meta.app_id, msg.meta.customer_id,
+                                        msg.meta.timestamp)] = rec;
+          staged_pulls_pending_.store(static_cast<int>(staged_pulls_.size()), std::memory_order_release);
         }
-        // the address means nothing over there, and no socket may land bytes at it over here
+        // the address means nothing to the peer, and no socket may land bytes at it over here
         if (fused) msg.meta.pull_addr = 0; else msg.meta.addr = 0;
       }
     }
@@ -393,17 +433,18 @@ class OneSidedVan : public TcpVan {
     return Submit(msg, nullptr, false);
   }
 
-  /*! \brief a pull reply from another host arrived in host memory: copy it to where the request wanted it */
-  void LandForeignPull(Message* msg) {
+  /*! \brief a pull reply arrived in host memory (frame): copy it to the device destination its request named */
+  void LandStagedPull(Message* msg) {
     if (msg->data.size() < 2 || msg->data[1].size() == 0) return;
-    ForeignPull rec;
+    StagedPull rec;
     {
       std::lock_guard<SpinMutex> lk(rv_mu_);
-      auto it = foreign_pulls_.find(std::make_tuple(msg->meta.sender, msg->meta.app_id, msg->meta.customer_id,
-                                                    msg->meta.timestamp));
-      if (it == foreign_pulls_.end()) return;
+      auto it = staged_pulls_.find(std::make_tuple(msg->meta.sender, msg->meta.app_id, msg->meta.customer_id,
+                                                   msg->meta.timestamp));
+      if (it == staged_pulls_.end()) return;
       rec = it->second;
-      foreign_pulls_.erase(it);
+      staged_pulls_.erase(it);
+      staged_pulls_pending_.store(static_cast<int>(staged_pulls_.size()), std::memory_order_release);
     }
     const SArray<char>& got = msg->data[1];
     CHECK_LE(got.size(), rec.bytes) << "pull reply larger than the destination it was requested for";
@@ -960,15 +1001,18 @@ class OneSidedVan : public TcpVan {
   std::map<std::pair<int, int32_t>, char*> peer_regions_;       // (peer, region) -> mapping
   std::set<std::pair<int, int32_t>> announced_;                 // (peer, my region) announced
   /*! \brief peers on other hosts, the device destinations of pulls sent to them, staging copies made */
-  struct ForeignPull {
+  struct StagedPull {
     uint64_t addr = 0;
     uint64_t bytes = 0;
     int dev_type = UNK;
     int dev_id = 0;
   };
   std::set<int> foreign_;
+  static constexpr size_t kNegotiated = 4096;
+  std::atomic<bool> negotiated_[kNegotiated] = {};  // by node id: the first data message has waited for the verdict
   std::atomic<bool> any_foreign_{false};
-  std::map<std::tuple<int, int, int, int>, ForeignPull> foreign_pulls_;
+  std::map<std::tuple<int, int, int, int>, StagedPull> staged_pulls_;
+  std::atomic<int> staged_pulls_pending_{0};
   std::atomic<uint64_t> staged_copies_{0};
 
   SpinMutex cq_mu_;

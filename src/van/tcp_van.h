@@ -32,6 +32,7 @@
 
 #include <algorithm>
 #include <array>
+#include <set>
 #include <shared_mutex>
 #include <chrono>
 #include <condition_variable>
@@ -209,6 +210,8 @@ class TcpVan : public Van {
      *  until a given completion. All under `mu`. */
     /*! \brief messages of receive threads parked in the outbox for this peer (see Defer) */
     std::atomic<int> deferred{0};
+    /*! \brief we offered this peer a ring (so it will offer us one too) */
+    bool made_offer = false;
     uint64_t gate_seq = 0;
     void* gate_word = nullptr;
     std::deque<std::pair<uint64_t, SArray<char>>> gate_keep;
@@ -357,6 +360,41 @@ class TcpVan : public Van {
     auto it = peers_.find(recver);
     return it != peers_.end() && it->second->pipe && it->second->gate_word != nullptr;
   }
+
+  /*!
+   * \brief ring negotiation with a same-host peer reached a verdict: it answered OUR offer, or we
+   *        answered ITS offer (`accepted`: the ring could be mapped). A declined ring means the two
+   *        processes share an address but not /dev/shm (containers): one-sided vans then treat
+   *        the peer like one on another host. Called on the receive thread, no locks held.
+   */
+  virtual void OnPipeVerdict(int /*peer_id*/, bool /*accepted*/) {}
+
+  /*!
+   * \brief is the ring negotiation with same-host peer `id` still open? True while our offer is
+   *        unanswered, or — if we offered one — while the peer's own offer has not arrived yet (both
+   *        sides offer when both have rings enabled).
+   */
+  bool NegotiationOpen(int id) {
+    std::shared_ptr<Peer> peer;
+    {
+      std::lock_guard<SpinMutex> lk(peers_mu_);
+      auto it = peers_.find(id);
+      if (it == peers_.end()) return false;
+      peer = it->second;
+    }
+    bool offered_one = false;
+    {
+      std::lock_guard<std::mutex> lk(peer->mu);
+      if (peer->offered) return true;
+      offered_one = peer->made_offer;
+    }
+    if (!offered_one) return false;
+    std::lock_guard<std::mutex> lk(offer_mu_);
+    return offers_seen_.count(id) == 0;
+  }
+
+  /*! \brief is the caller this van's receive thread? (it must not wait for events only it can process) */
+  bool OnReceiveThread() const { return tls_receiving_ == this; }
 
   /*! \brief is there a connection to node `id` already (then Connect(id) is a reconnect after recovery) */
   bool HasPeer(int id) {
@@ -724,6 +762,7 @@ class TcpVan : public Van {
     });
     peer->offered_gate_word = MapGateWord(raw);
     peer->offered = std::move(pipe);
+    peer->made_offer = true;
     {
       std::lock_guard<std::mutex> lk(offer_mu_);
       offer_fds_[fd] = peer_id;
@@ -748,6 +787,7 @@ class TcpVan : public Van {
       if (it != peers_.end()) peer = it->second;
     }
     if (!peer) return;
+    if (r == 1 && answer != 'A') OnPipeVerdict(peer_id, false);  // (before the offer stops being "pending")
     std::lock_guard<std::mutex> lk(peer->mu);
     if (peer->fd != fd || !peer->offered) return;  // a reconnect replaced this connection
     if (r == 1 && answer == 'A') {
@@ -1046,6 +1086,11 @@ class TcpVan : public Van {
         PS_VLOG(1) << "cannot map the shared-memory ring node " << hdr.sender << " offered (" << name
                    << ": " << strerror(errno) << "): its descriptors stay on the socket";
       }
+      if (!in->offered) OnPipeVerdict(hdr.sender, false);  // (before the peer's offer counts as "seen")
+      {
+        std::lock_guard<std::mutex> lk(offer_mu_);
+        offers_seen_.insert(hdr.sender);
+      }
       ssize_t w = send(fd, &answer, 1, MSG_NOSIGNAL);
       (void)w;
       if (in->avail() > 0) ready_fds_.push_back(fd);
@@ -1318,6 +1363,7 @@ class TcpVan : public Van {
   static thread_local bool tls_outbox_;               // set on an outbox thread
   std::mutex offer_mu_;
   std::unordered_map<int, int> offer_fds_;  // outbound socket -> peer id, while an offer is unanswered
+  std::set<int> offers_seen_;               // peers whose own ring offer has arrived (under offer_mu_)
   SpinMutex pull_mu_;
   std::map<PullKey, PullDest> pull_dests_;
 };

@@ -75,8 +75,9 @@ def test_descriptors_gated_by_copy_engine(built_native_tree, async_copies):
 
 @pytest.mark.parametrize("van", ["zmq", "shm"])
 def test_declined_ring_offer_falls_back_to_socket(built_native_tree, van):
-    """a peer that cannot map the offered shared-memory ring (same IP, private /dev/shm) declines it:
-    the job runs over the sockets, one-sided transfers fall back to tickets"""
+    """a peer that cannot map the offered shared-memory ring (same IP, private /dev/shm) declines it: the
+    job runs over the sockets, and a one-sided van takes the verdict for what it means — no shared memory
+    with that peer — and sends frames instead of exchanging regions it could not map"""
     import re
 
     env = {"PS_VAN_TYPE": van, "PS_TEST_DECLINE_PIPE": 1, "PS_VERBOSE": 1, "TEST_EXPORTABLE_VALS": 1}
@@ -84,6 +85,7 @@ def test_declined_ring_offer_falls_back_to_socket(built_native_tree, van):
     assert rc == 0 and out.count("test_kv_app PASSED") == 2, out[-3000:]
     assert "stay on the socket" in out
     assert all(int(x) == 0 for x in re.findall(r"(\d+) descriptors gated by the copy engine", out))
+    assert all(int(x) == 0 for x in re.findall(r"(\d+) one-sided copies", out))
 
 
 def test_ipc_benchmark_symmetric_buffer_and_mixed_mode(built_native_tree):
