@@ -102,6 +102,7 @@ class OneSidedVan : public TcpVan {
     }
     std::lock_guard<SpinMutex> lk(rv_mu_);
     registered_slots_[std::make_pair(msg.meta.sender, msg.meta.key)] = msg.data[1];
+    registered_count_.store(static_cast<int>(registered_slots_.size()), std::memory_order_release);
   }
 
   /*!
@@ -314,6 +315,9 @@ class OneSidedVan : public TcpVan {
       } else if (staged_pulls_pending_.load(std::memory_order_acquire) > 0 && msg->meta.control.empty() &&
                  !msg->meta.simple_app && !msg->meta.request && !msg->meta.push) {
         LandStagedPull(msg);
+      } else if (registered_count_.load(std::memory_order_acquire) > 0 && msg->meta.control.empty() &&
+                 !msg->meta.simple_app && msg->meta.request && msg->meta.push) {
+        LandInRegisteredBuffer(msg);
       }
       return n;
     }
@@ -454,6 +458,32 @@ class OneSidedVan : public TcpVan {
                  rec.dev_id, static_cast<DeviceType>(rec.dev_type), rec.dev_id);
     msg->data[1] = placed;
     ++staged_copies_;
+  }
+
+  /*!
+   * \brief a push arrived IN a frame (its sender is on another host, or could not go one-sidedly) for a
+   *        (sender, key) the application registered a receive buffer for: the contract is that the
+   *        handler sees the values in THAT buffer (KVServer::RegisterRecvBuffer, reference
+   *        src/rdma_van.h:293-319), so they are copied there — host to device if the buffer is in HBM.
+   */
+  void LandInRegisteredBuffer(Message* msg) {
+    if (msg->data.size() < 2 || msg->data[1].size() == 0) return;
+    SArray<char> reg;
+    {
+      std::lock_guard<SpinMutex> lk(rv_mu_);
+      auto it = registered_slots_.find(std::make_pair(msg->meta.sender, static_cast<uint64_t>(msg->meta.key)));
+      if (it == registered_slots_.end()) return;
+      reg = it->second;
+    }
+    const SArray<char>& got = msg->data[1];
+    if (got.data() == reg.data() || got.size() > reg.size() || got.on_gpu()) return;
+    if (domain_->NeedsStaging(reg.src_device_type_, reg.data())) {
+      domain_->CopyFromHost(reg.data(), got.data(), got.size());
+      ++staged_copies_;
+    } else {
+      memcpy(reg.data(), got.data(), got.size());
+    }
+    msg->data[1] = reg.segment(0, got.size());
   }
 
   // -- region bookkeeping -----------------------------------------------------
@@ -1013,6 +1043,7 @@ class OneSidedVan : public TcpVan {
   std::atomic<bool> any_foreign_{false};
   std::map<std::tuple<int, int, int, int>, StagedPull> staged_pulls_;
   std::atomic<int> staged_pulls_pending_{0};
+  std::atomic<int> registered_count_{0};  // size of registered_slots_ (checked without the lock per frame)
   std::atomic<uint64_t> staged_copies_{0};
 
   SpinMutex cq_mu_;

@@ -8,16 +8,17 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def run_foreign_host(env_extra, timeout=90):
-    app = os.path.join(ROOT, "build", "test_foreign_host")
+def run_foreign_host(env_extra, timeout=90, app="test_foreign_host", args=()):
+    name = app
+    app = os.path.join(ROOT, "build", name)
     if not os.path.exists(app):
-        return None, "build/test_foreign_host not built (make)"
+        return None, f"build/{name} not built (make)"
     env = dict(os.environ)
     env.update({"DMLC_NUM_SERVER": "1", "DMLC_NUM_WORKER": "1", "DMLC_PS_ROOT_URI": "127.0.0.1",
                 "DMLC_PS_ROOT_PORT": str(21000 + random.randrange(10000))})
     env.update({k: str(v) for k, v in env_extra.items()})
     env.pop("DMLC_RANK", None)
-    procs = [subprocess.Popen([app], env=dict(env, DMLC_ROLE=role, DMLC_NODE_HOST=host), cwd=ROOT,
+    procs = [subprocess.Popen([app, *[str(a) for a in args]], env=dict(env, DMLC_ROLE=role, DMLC_NODE_HOST=host), cwd=ROOT,
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
              for role, host in (("scheduler", "127.0.0.1"), ("server", "127.0.0.1"), ("worker", "127.0.0.2"))]
     outs = []

@@ -285,3 +285,19 @@ def test_onesided_van_with_a_peer_on_another_host(built_native_tree, staged):
     assert m, out[-3000:]
     assert int(m.group(1)) == 0  # nothing was written into the peer's memory
     assert int(m.group(2)) == (4 if staged else 0)  # push, pull, and both halves of the push-pull
+
+
+@pytest.mark.parametrize("staged", [0, 1])
+def test_registered_receive_buffers_with_a_sender_on_another_host(built_native_tree, staged):
+    """KVServer::RegisterRecvBuffer promises the handler the values IN the registered buffer; a push from
+    another host arrives in a frame, so the van copies it there (host to device for a buffer in HBM; the
+    arena plays HBM with PS_TEST_STAGE_ARENA). test_benchmark checks the pointer on every push."""
+    import sys
+
+    sys.path.insert(0, os.path.join(ROOT, "tests", "helpers"))
+    from foreign_host import run_foreign_host
+
+    rcs, out = run_foreign_host({"PS_VAN_TYPE": "shm", "TEST_EXPORTABLE_VALS": 1, "ENABLE_RECV_BUFFER": 1,
+                                 "NUM_KEY_PER_SERVER": 4, "TOTAL_DURATION": 20, "LOG_DURATION": 10,
+                                 "PS_TEST_STAGE_ARENA": staged}, app="test_benchmark", args=(65536, 20, 1))
+    assert rcs == [0, 0, 0] and "goodput" in out, out[-3000:]
